@@ -1,0 +1,392 @@
+"""Host-side mirror of the reference's graph / context / processor API over the C ABI.
+
+Names, argument meaning and error behaviour follow firewheel-graph so that tests read
+like the reference's own (crates/firewheel-graph/src/graph/compiler/schedule.rs:392-711):
+
+    cx = FirewheelGraphCtx(lib, AudioGraphConfig(num_graph_inputs=2, num_graph_outputs=2))
+    vol = cx.graph.add_node(2, 2, VolumeNode(50.0))
+    cx.graph.connect(cx.graph.graph_in_node(), 0, vol, 0, False)
+    ...
+    proc = cx.activate(48000, 2, 2, 256)
+    cx.update()
+    proc.process_interleaved(inp, out, 2, 2, frames, 0.0, 0)
+
+Every class is a thin handle; all state and all arithmetic live behind the C ABI
+(`lib` is a `_capi.Lib`: the CUDA product, or the CPU oracle in tests).
+"""
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _capi as K
+
+
+# ---- ids -------------------------------------------------------------------------------------
+class NodeID(int):
+    """thunderdome index: slot | generation << 32 (graph.rs:20-23)."""
+
+    @property
+    def slot(self):
+        return int(self) & 0xFFFFFFFF
+
+    @property
+    def generation(self):
+        return int(self) >> 32
+
+    def __repr__(self):
+        return f"NodeID({self.slot}-{self.generation})"
+
+
+class EdgeID(NodeID):
+    def __repr__(self):
+        return f"EdgeID({self.slot}-{self.generation})"
+
+
+class AddEdgeError(Exception):
+    """graph/error.rs:14-37. `kind` is the variant name; node/port carry its payload."""
+
+    def __init__(self, code, node=None, port=None):
+        self.code, self.kind, self.node, self.port = code, K.ADD_EDGE_ERRORS[code], node, port
+        super().__init__(f"Could not add edge: {self.kind} node={node} port={port}")
+
+
+class CompileGraphError(Exception):
+    """graph/error.rs:101-116."""
+
+    def __init__(self, code, node=None, port=None, message=""):
+        self.code, self.kind, self.node, self.port = code, K.COMPILE_ERRORS.get(code, str(code)), node, port
+        super().__init__(f"Failed to compile audio graph: {self.kind} {message}")
+
+
+# ---- nodes (values handed to add_node, like `impl Into<Box<dyn AudioNode>>`) -----------------
+@dataclass
+class _Node:
+    kind: int = K.NODE_DUMMY
+    u: tuple = (0, 0, 0)
+    f: tuple = (0.0, 0.0, 0.0, 0.0)
+    data: np.ndarray = None
+
+    def desc(self):
+        d = K.NodeDesc(kind=self.kind, u0=self.u[0], u1=self.u[1], u2=self.u[2],
+                       f0=self.f[0], f1=self.f[1], f2=self.f[2], f3=self.f[3])
+        if self.data is not None:
+            self._keep = np.ascontiguousarray(self.data, dtype=np.float32)
+            d.data = self._keep.ctypes.data_as(C.POINTER(C.c_float))
+            d.data_len = self._keep.size
+        return d
+
+
+def DummyAudioNode():
+    return _Node(K.NODE_DUMMY)
+
+
+def VolumeNode(percent_volume):  # volume.rs:16
+    return _Node(K.NODE_VOLUME, f=(float(percent_volume), 0.0, 0.0, 0.0))
+
+
+def SumNode():
+    return _Node(K.NODE_SUM)
+
+
+def MonoToStereoNode():
+    return _Node(K.NODE_MONO_TO_STEREO)
+
+
+def StereoToMonoNode():
+    return _Node(K.NODE_STEREO_TO_MONO)
+
+
+def HardClipNode(threshold_db):  # hard_clip.rs:8
+    return _Node(K.NODE_HARD_CLIP, f=(float(threshold_db), 0.0, 0.0, 0.0))
+
+
+def PanNode(pan):
+    return _Node(K.NODE_PAN, f=(float(pan), 0.0, 0.0, 0.0))
+
+
+def BiquadNode(num_stages):
+    return _Node(K.NODE_BIQUAD, u=(int(num_stages), 0, 0))
+
+
+def DelayNode(delay_frames):
+    return _Node(K.NODE_DELAY, u=(int(delay_frames), 0, 0))
+
+
+def ConvReverbNode(ir):
+    ir = np.atleast_2d(np.asarray(ir, dtype=np.float32))
+    return _Node(K.NODE_CONV_REVERB, u=(ir.shape[1], ir.shape[0], 0), data=ir)
+
+
+@dataclass
+class AudioGraphConfig:  # graph.rs:91-107 + batching
+    num_graph_inputs: int = 0
+    num_graph_outputs: int = 2
+    initial_node_capacity: int = 64
+    initial_edge_capacity: int = 256
+    num_voices: int = 1
+    master_bus: bool = False
+    device: int = 0
+
+
+@dataclass
+class ScheduledNode:  # schedule.rs:13-30
+    id: NodeID
+    input_buffers: list = field(default_factory=list)   # [(buffer_index, should_clear)]
+    output_buffers: list = field(default_factory=list)  # [buffer_index]
+
+
+@dataclass
+class UpdateStatus:  # context.rs:245-254
+    kind: str
+    graph_error: CompileGraphError = None
+    returned_user_cx: int = None
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        assert a.dtype == np.float32 and a.flags["C_CONTIGUOUS"], "f32 C-contiguous buffers only"
+        return a.ctypes.data
+    return int(a)  # raw (device or pinned) address
+
+
+class AudioGraph:
+    def __init__(self, lib, ctx):
+        self._lib, self._ctx = lib, ctx
+
+    def graph_in_node(self):
+        return NodeID(self._lib.graph_in_node(self._ctx))
+
+    def graph_out_node(self):
+        return NodeID(self._lib.graph_out_node(self._ctx))
+
+    def add_node(self, num_inputs, num_outputs, node):
+        d = node.desc()
+        nid = self._lib.graph_add_node(self._ctx, num_inputs, num_outputs, C.byref(d))
+        if nid == K.FW_ID_DANGLING:
+            raise ValueError(self._lib.ctx_last_error(self._ctx).decode())
+        return NodeID(nid)
+
+    def _removed(self, fn, *args):
+        cap = 4096
+        buf = (C.c_uint64 * cap)()
+        n = C.c_uint32(0)
+        rc = fn(self._ctx, *args, buf, cap, C.byref(n))
+        if rc != 0:
+            raise KeyError("Err(())")
+        return [EdgeID(buf[i]) for i in range(min(n.value, cap))]
+
+    def remove_node(self, node_id):
+        return self._removed(self._lib.graph_remove_node, node_id)
+
+    def set_num_inputs(self, node_id, n):
+        return self._removed(self._lib.graph_set_num_inputs, node_id, n)
+
+    def set_num_outputs(self, node_id, n):
+        return self._removed(self._lib.graph_set_num_outputs, node_id, n)
+
+    def connect(self, src_node, src_port, dst_node, dst_port, check_for_cycles):
+        e, en, ep = C.c_uint64(0), C.c_uint64(0), C.c_uint32(0)
+        rc = self._lib.graph_connect(self._ctx, src_node, src_port, dst_node, dst_port, int(check_for_cycles),
+                                     C.byref(e), C.byref(en), C.byref(ep))
+        if rc != 0:
+            raise AddEdgeError(rc, NodeID(en.value), ep.value)
+        return EdgeID(e.value)
+
+    def disconnect(self, src_node, src_port, dst_node, dst_port):
+        return bool(self._lib.graph_disconnect(self._ctx, src_node, src_port, dst_node, dst_port))
+
+    def disconnect_by_edge_id(self, edge_id):
+        return bool(self._lib.graph_disconnect_by_edge_id(self._ctx, edge_id))
+
+    def edge(self, edge_id):
+        info = K.EdgeInfoC()
+        if not self._lib.graph_edge(self._ctx, edge_id, C.byref(info)):
+            return None
+        return info
+
+    def node_info(self, node_id):
+        info = K.NodeInfoC()
+        if not self._lib.graph_node_info(self._ctx, node_id, C.byref(info)):
+            return None
+        return info
+
+    def nodes(self):
+        n = self._lib.graph_num_nodes(self._ctx)
+        buf = (C.c_uint64 * max(n, 1))()
+        self._lib.graph_nodes(self._ctx, buf, n)
+        return [NodeID(buf[i]) for i in range(n)]
+
+    def edges(self):
+        n = self._lib.graph_num_edges(self._ctx)
+        buf = (C.c_uint64 * max(n, 1))()
+        self._lib.graph_edges(self._ctx, buf, n)
+        return [EdgeID(buf[i]) for i in range(n)]
+
+    def cycle_detected(self):
+        return bool(self._lib.graph_cycle_detected(self._ctx))
+
+    def reset(self):
+        self._lib.graph_reset(self._ctx)
+
+    def needs_compile(self):
+        return bool(self._lib.graph_needs_compile(self._ctx))
+
+    def compile_internal(self, max_block_frames):
+        """graph.rs:629 — returns the schedule (list of ScheduledNode) + num_buffers, or raises."""
+        rc = self._lib.graph_compile_internal(self._ctx, max_block_frames)
+        if rc != 0:
+            raise CompileGraphError(rc)
+        out = []
+        for i in range(self._lib.schedule_len(self._ctx)):
+            sn = K.ScheduledNodeC()
+            assert self._lib.schedule_node(self._ctx, i, C.byref(sn))
+            out.append(ScheduledNode(NodeID(sn.id),
+                                     [(sn.in_buffer[k], bool(sn.in_should_clear[k])) for k in range(sn.num_inputs)],
+                                     [sn.out_buffer[k] for k in range(sn.num_outputs)]))
+        return out, self._lib.schedule_num_buffers(self._ctx)
+
+    # ---- parameters -------------------------------------------------------------------------
+    def _chk(self, rc, what):
+        if rc != 0:
+            raise ValueError(f"{what}: node is not of that kind / bad voice index")
+
+    def set_percent_volume(self, node_id, percent, voice=K.FW_ALL_VOICES):  # volume.rs:28
+        if np.ndim(percent) == 0:
+            self._chk(self._lib.volume_set_percent_volume(self._ctx, node_id, voice, float(percent)), "volume")
+        else:
+            a = np.ascontiguousarray(percent, dtype=np.float32)
+            self._chk(self._lib.volume_set_percent_volumes(self._ctx, node_id, a.ctypes.data, a.size), "volume")
+
+    def set_pan(self, node_id, pan, voice=K.FW_ALL_VOICES):
+        if np.ndim(pan) == 0:
+            self._chk(self._lib.pan_set_pan(self._ctx, node_id, voice, float(pan)), "pan")
+        else:
+            a = np.ascontiguousarray(pan, dtype=np.float32)
+            self._chk(self._lib.pan_set_pans(self._ctx, node_id, a.ctypes.data, a.size), "pan")
+
+    def set_pan_gains(self, node_id, gl, gr, voice=K.FW_ALL_VOICES):
+        self._chk(self._lib.pan_set_gains(self._ctx, node_id, voice, float(gl), float(gr)), "pan")
+
+    def set_biquad_coeffs(self, node_id, coeffs, voice=K.FW_ALL_VOICES, stage=None):
+        a = np.ascontiguousarray(coeffs, dtype=np.float32)
+        if a.ndim == 1:
+            self._chk(self._lib.biquad_set_coeffs(self._ctx, node_id, voice, stage, a.ctypes.data), "biquad")
+        elif a.ndim == 2:  # [stage][5], same for the selected voices
+            for s in range(a.shape[0]):
+                self._chk(self._lib.biquad_set_coeffs(self._ctx, node_id, voice, s, a[s].ctypes.data), "biquad")
+        else:  # [voice][stage][5]
+            self._chk(self._lib.biquad_set_all_coeffs(self._ctx, node_id, a.ctypes.data, a.shape[0], a.shape[1]), "biquad")
+
+
+def design_rbj(lib, ftype, fc, q, gain_db, sample_rate):
+    out = np.zeros(5, dtype=np.float32)
+    lib.biquad_design_rbj(int(ftype), float(fc), float(q), float(gain_db), float(sample_rate), out.ctypes.data)
+    return out
+
+
+class FirewheelProcessor:
+    """processor.rs:18 — owned by the stream side; `free()` is Drop."""
+
+    def __init__(self, lib, handle, cfg):
+        self._lib, self._h, self.cfg = lib, handle, cfg
+
+    def process_interleaved(self, input, output, num_in_channels, num_out_channels, frames, stream_time_secs=0.0, stream_status=0):
+        return self._lib.processor_process_interleaved(self._h, _ptr(input), _ptr(output), num_in_channels, num_out_channels,
+                                                       frames, stream_time_secs, stream_status)
+
+    def process_planar(self, input, output, num_in_channels, num_out_channels, frames, stream_time_secs=0.0, stream_status=0):
+        m = C.c_uint64(0)
+        rc = self._lib.processor_process_planar(self._h, _ptr(input), _ptr(output), num_in_channels, num_out_channels,
+                                                frames, stream_time_secs, stream_status, C.byref(m))
+        return rc, m.value
+
+    def process_planar_device(self, d_input, d_output, num_in_channels, num_out_channels, frames, stream_time_secs=0.0, stream_status=0):
+        return self._lib.processor_process_planar_device(self._h, _ptr(d_input), _ptr(d_output), num_in_channels,
+                                                         num_out_channels, frames, stream_time_secs, stream_status)
+
+    def h2d(self, dst, src, nbytes):
+        return self._lib.processor_h2d(self._h, _ptr(dst), _ptr(src), nbytes)
+
+    def d2h(self, dst, src, nbytes):
+        return self._lib.processor_d2h(self._h, _ptr(dst), _ptr(src), nbytes)
+
+    def sync(self):
+        return self._lib.processor_sync(self._h)
+
+    def event_record(self, slot):
+        return self._lib.processor_event_record(self._h, slot)
+
+    def event_elapsed_ms(self, a, b):
+        return self._lib.processor_event_elapsed_ms(self._h, a, b)
+
+    def kernel_launches(self):
+        return self._lib.processor_kernel_launches(self._h)
+
+    def l2_flush(self):
+        return self._lib.processor_l2_flush(self._h)
+
+    def comm_init(self, rank, world_size, id128):
+        buf = (C.c_uint8 * 128).from_buffer_copy(bytes(id128))
+        return self._lib.processor_comm_init(self._h, rank, world_size, buf)
+
+    def free(self):
+        if self._h:
+            self._lib.processor_free(self._h)
+            self._h = None
+
+
+class FirewheelGraphCtx:
+    """context.rs:29."""
+
+    def __init__(self, lib, graph_config=None):
+        self._lib = lib
+        gc = graph_config or AudioGraphConfig()
+        self.config = gc
+        c = K.GraphConfig(gc.num_graph_inputs, gc.num_graph_outputs, gc.initial_node_capacity, gc.initial_edge_capacity,
+                          gc.num_voices, int(gc.master_bus), gc.device, 0)
+        self._ctx = lib.ctx_new(C.byref(c))
+        if not self._ctx:
+            raise RuntimeError("ctx_new failed: " + (lib.last_device_error() or b"").decode())
+        self.graph = AudioGraph(lib, self._ctx)
+
+    def activate(self, sample_rate, num_stream_in_channels, num_stream_out_channels, max_block_frames, user_cx=None):
+        h = C.c_void_p(None)
+        rc = self._lib.ctx_activate(self._ctx, sample_rate, num_stream_in_channels, num_stream_out_channels,
+                                    max_block_frames, user_cx, C.byref(h))
+        if rc == 1:
+            return None  # already active (context.rs:57-59)
+        if rc != 0:
+            raise RuntimeError("activate failed: " + self.last_error())
+        return FirewheelProcessor(self._lib, h.value, self.config)
+
+    def is_activated(self):
+        return bool(self._lib.ctx_is_activated(self._ctx))
+
+    def update(self):
+        st = K.UpdateStatusC()
+        self._lib.ctx_update(self._ctx, C.byref(st))
+        kind = ["Inactive", "Active", "Deactivated"][st.kind]
+        err = None
+        if st.graph_error != 0:
+            err = CompileGraphError(st.graph_error, NodeID(st.error_node), st.error_port, self.last_error())
+        return UpdateStatus(kind, err, st.returned_user_cx)
+
+    def deactivate(self, stream_is_running):
+        return self._lib.ctx_deactivate(self._ctx, int(stream_is_running))
+
+    def last_error(self):
+        return (self._lib.ctx_last_error(self._ctx) or b"").decode()
+
+    def free(self):
+        if self._ctx:
+            self._lib.ctx_free(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass

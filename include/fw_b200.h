@@ -1,0 +1,252 @@
+/* fw_b200.h — C ABI of firewheel-b200: the drop-in boundary for the per-block
+ * audio-graph DSP path of BillyDM/firewheel @ 2dfa7ea.
+ *
+ * Every entry point names the reference interface it replaces (file:line relative
+ * to the reference tree). A Rust `-sys` crate binds these 1:1.
+ * Plain pointers and sizes only; no exceptions or panics cross this boundary.
+ *
+ * The SAME declarations are exported twice:
+ *   libfirewheel_b200.so   prefix fw_   — the product: CUDA sm_100a, no CPU fallback
+ *   oracle/_build/libfw_oracle.so  prefix fwo_  — CPU oracle (test infrastructure only)
+ * so parity tests drive both through identical code (FW_API_PREFIX selects).
+ *
+ * Batching extension over the reference: a context holds `num_voices` instances
+ * of one voice graph (same topology, per-voice parameters and state). With
+ * `master_bus = 1` the graph_out channels of all voices are mixed by a balanced
+ * binary tree of 2-port SumNodes (sum.rs:69-81) — level l adds neighbours
+ * (2i, 2i+1); an unpaired last element is carried up unchanged (the 1-port
+ * SumNode copy path, sum.rs:58-65). num_voices = 1, master_bus = 0 is exactly
+ * the reference.
+ *
+ * Buffer layouts (f32):
+ *   interleaved in : [voice][frames][n_in]      out: [voice][frames][n_out]  (master bus: [frames][n_out])
+ *   planar      in : [voice][n_in][frames]      out: [voice][n_out][frames]  (master bus: [n_out][frames])
+ */
+#ifndef FW_B200_H
+#define FW_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef FW_API_PREFIX
+#define FW_API_PREFIX fw_
+#endif
+#define FW_CAT2(a, b) a##b
+#define FW_CAT(a, b) FW_CAT2(a, b)
+#define FW_FN(name) FW_CAT(FW_API_PREFIX, name)
+#define FW_EXPORT __attribute__((visibility("default")))
+
+/* NodeID / EdgeID: thunderdome generational index (graph.rs:20-23, compiler.rs:63)
+ * packed as slot | generation << 32. */
+typedef uint64_t fw_node_id;
+typedef uint64_t fw_edge_id;
+#define FW_ID_DANGLING UINT64_MAX
+#define FW_ALL_VOICES UINT32_MAX
+#define FW_MAX_PORTS 64u /* node.rs:62,70; compiler.rs:202-203 */
+
+typedef struct fw_ctx fw_ctx;             /* FirewheelGraphCtx   context.rs:29 */
+typedef struct fw_processor fw_processor; /* FirewheelProcessor  processor.rs:18 */
+
+/* AudioGraphConfig (graph.rs:91-107) + batching fields */
+typedef struct fw_graph_config {
+    uint32_t num_graph_inputs;      /* default 0 */
+    uint32_t num_graph_outputs;     /* default 2 */
+    uint32_t initial_node_capacity; /* default 64 */
+    uint32_t initial_edge_capacity; /* default 256 */
+    uint32_t num_voices;            /* >= 1 */
+    uint32_t master_bus;            /* 0 | 1 */
+    int32_t device;                 /* CUDA ordinal (ignored by the oracle) */
+    uint32_t reserved;
+} fw_graph_config;
+
+/* Built-in node kinds. The Rust side constructs `impl Into<Box<dyn AudioNode>>`
+ * values (graph.rs:201-206); over the C ABI a node is described by value. */
+enum fw_node_kind {
+    FW_NODE_DUMMY = 0,          /* basic_nodes/dummy.rs */
+    FW_NODE_VOLUME = 1,         /* basic_nodes/volume.rs  f0 = percent_volume */
+    FW_NODE_SUM = 2,            /* basic_nodes/sum.rs */
+    FW_NODE_MONO_TO_STEREO = 3, /* basic_nodes/mono_to_stereo.rs */
+    FW_NODE_STEREO_TO_MONO = 4, /* basic_nodes/stereo_to_mono.rs */
+    FW_NODE_HARD_CLIP = 5,      /* basic_nodes/hard_clip.rs  f0 = threshold_db */
+    FW_NODE_PAN = 6,            /* spec ours  f0 = pan in [-1,1] */
+    FW_NODE_BIQUAD = 7,         /* spec ours (a11)  u0 = num_stages (<= 8) */
+    FW_NODE_DELAY = 8,          /* spec ours (a12)  u0 = delay in frames */
+    FW_NODE_CONV_REVERB = 9     /* spec ours (a14)  u0 = ir_len, u1 = ir_channels, data = IR [ch][len] */
+};
+typedef struct fw_node_desc {
+    uint32_t kind;
+    uint32_t u0, u1, u2;
+    float f0, f1, f2, f3;
+    const float* data;
+    uint64_t data_len; /* floats */
+} fw_node_desc;
+
+/* AddEdgeError (graph/error.rs:14-37) */
+enum fw_add_edge_error {
+    FW_EDGE_OK = 0,
+    FW_EDGE_SRC_NODE_NOT_FOUND = 1,
+    FW_EDGE_DST_NODE_NOT_FOUND = 2,
+    FW_EDGE_IN_PORT_OUT_OF_RANGE = 3,
+    FW_EDGE_OUT_PORT_OUT_OF_RANGE = 4,
+    FW_EDGE_ALREADY_EXISTS = 5,
+    FW_EDGE_INPUT_PORT_ALREADY_CONNECTED = 6,
+    FW_EDGE_CYCLE_DETECTED = 7
+};
+/* CompileGraphError (graph/error.rs:101-116) */
+enum fw_compile_error {
+    FW_COMPILE_OK = 0,
+    FW_COMPILE_CYCLE_DETECTED = 1,
+    FW_COMPILE_NODE_ON_EDGE_NOT_FOUND = 2,
+    FW_COMPILE_NODE_ID_NOT_UNIQUE = 3,
+    FW_COMPILE_EDGE_ID_NOT_UNIQUE = 4,
+    FW_COMPILE_MANY_TO_ONE = 5,
+    FW_COMPILE_NODE_ACTIVATION_FAILED = 6,
+    FW_COMPILE_MESSAGE_CHANNEL_FULL = 7,
+    /* product only: the graph is valid for the reference but has no device lowering yet */
+    FW_COMPILE_UNSUPPORTED_ON_DEVICE = 100
+};
+/* FirewheelProcessorStatus (processor.rs:12-16) + device-error code */
+enum fw_processor_status { FW_PROC_OK = 0, FW_PROC_DROP_PROCESSOR = 1, FW_PROC_DEVICE_ERROR = -1, FW_PROC_BAD_ARGS = -2 };
+/* StreamStatus bitflags (node.rs:120-132) */
+enum fw_stream_status { FW_STREAM_INPUT_OVERFLOW = 1, FW_STREAM_OUTPUT_UNDERFLOW = 2 };
+/* UpdateStatus (context.rs:245-254) */
+enum fw_update_kind { FW_UPDATE_INACTIVE = 0, FW_UPDATE_ACTIVE = 1, FW_UPDATE_DEACTIVATED = 2 };
+typedef struct fw_update_status {
+    int32_t kind;           /* fw_update_kind */
+    int32_t graph_error;    /* fw_compile_error; FW_COMPILE_OK if none */
+    fw_node_id error_node;  /* ManyToOne / NodeActivationFailed */
+    uint32_t error_port;
+    uint32_t reserved;
+    void* returned_user_cx; /* Deactivated { returned_user_cx } */
+} fw_update_status;
+
+typedef struct fw_node_info { /* NodeEntry (compiler.rs:12-23) + AudioNodeInfo (node.rs:57-79) */
+    uint32_t num_inputs, num_outputs;
+    uint32_t kind;
+    uint32_t num_min_supported_inputs, num_max_supported_inputs;
+    uint32_t num_min_supported_outputs, num_max_supported_outputs;
+    uint32_t updates;
+    char debug_name[32];
+} fw_node_info;
+typedef struct fw_edge_info { /* Edge (compiler.rs:68-78) */
+    fw_edge_id id;
+    fw_node_id src_node, dst_node;
+    uint32_t src_port, dst_port;
+} fw_edge_info;
+/* ScheduledNode (schedule.rs:13-30): debugging / visualisation view of the compiled schedule */
+typedef struct fw_scheduled_node {
+    fw_node_id id;
+    uint32_t num_inputs, num_outputs;
+    uint32_t in_buffer[FW_MAX_PORTS];
+    uint8_t in_should_clear[FW_MAX_PORTS];
+    uint32_t out_buffer[FW_MAX_PORTS];
+} fw_scheduled_node;
+
+/* ---- context + graph (context.rs:36, graph.rs:125-580) ---------------------------------- */
+FW_EXPORT void FW_FN(graph_config_default)(fw_graph_config* cfg);                  /* graph.rs:98-107 */
+FW_EXPORT fw_ctx* FW_FN(ctx_new)(const fw_graph_config* cfg);                      /* context.rs:36 */
+FW_EXPORT void FW_FN(ctx_free)(fw_ctx* ctx);                                        /* Drop context.rs:236-242 */
+FW_EXPORT const char* FW_FN(ctx_last_error)(fw_ctx* ctx);                           /* Display of the last error */
+FW_EXPORT fw_node_id FW_FN(graph_in_node)(fw_ctx* ctx);                             /* graph.rs:189 */
+FW_EXPORT fw_node_id FW_FN(graph_out_node)(fw_ctx* ctx);                            /* graph.rs:194 */
+FW_EXPORT fw_node_id FW_FN(graph_add_node)(fw_ctx* ctx, uint32_t num_inputs, uint32_t num_outputs,
+                                           const fw_node_desc* desc);               /* graph.rs:201 */
+/* Ok(Vec<EdgeID>) => 0 and *n_removed edges written (up to cap); Err(()) => -1 */
+FW_EXPORT int FW_FN(graph_remove_node)(fw_ctx* ctx, fw_node_id node, fw_edge_id* removed, uint32_t cap,
+                                       uint32_t* n_removed);                        /* graph.rs:268 */
+FW_EXPORT int FW_FN(graph_set_num_inputs)(fw_ctx* ctx, fw_node_id node, uint32_t n, fw_edge_id* removed,
+                                          uint32_t cap, uint32_t* n_removed);       /* graph.rs:315 */
+FW_EXPORT int FW_FN(graph_set_num_outputs)(fw_ctx* ctx, fw_node_id node, uint32_t n, fw_edge_id* removed,
+                                           uint32_t cap, uint32_t* n_removed);      /* graph.rs:349 */
+/* returns fw_add_edge_error; on error *err_node / *err_port carry the payload of the variant */
+FW_EXPORT int FW_FN(graph_connect)(fw_ctx* ctx, fw_node_id src, uint32_t src_port, fw_node_id dst,
+                                   uint32_t dst_port, int check_for_cycles, fw_edge_id* out_edge,
+                                   fw_node_id* err_node, uint32_t* err_port);       /* graph.rs:396 */
+FW_EXPORT int FW_FN(graph_disconnect)(fw_ctx* ctx, fw_node_id src, uint32_t src_port, fw_node_id dst,
+                                      uint32_t dst_port);                           /* graph.rs:483 -> bool */
+FW_EXPORT int FW_FN(graph_disconnect_by_edge_id)(fw_ctx* ctx, fw_edge_id edge);     /* graph.rs:507 -> bool */
+FW_EXPORT int FW_FN(graph_edge)(fw_ctx* ctx, fw_edge_id edge, fw_edge_info* out);   /* graph.rs:527 -> Option */
+FW_EXPORT int FW_FN(graph_node_info)(fw_ctx* ctx, fw_node_id node, fw_node_info* out); /* graph.rs:253 -> Option */
+FW_EXPORT uint32_t FW_FN(graph_num_nodes)(fw_ctx* ctx);                             /* graph.rs:302 */
+FW_EXPORT uint32_t FW_FN(graph_num_edges)(fw_ctx* ctx);                             /* graph.rs:307 */
+FW_EXPORT uint32_t FW_FN(graph_nodes)(fw_ctx* ctx, fw_node_id* out, uint32_t cap);  /* graph.rs:302 (slot order) */
+FW_EXPORT uint32_t FW_FN(graph_edges)(fw_ctx* ctx, fw_edge_id* out, uint32_t cap);  /* graph.rs:307 (slot order) */
+FW_EXPORT int FW_FN(graph_cycle_detected)(fw_ctx* ctx);                             /* graph.rs:573 */
+FW_EXPORT void FW_FN(graph_reset)(fw_ctx* ctx);                                     /* graph.rs:171 */
+FW_EXPORT int FW_FN(graph_needs_compile)(fw_ctx* ctx);                              /* graph.rs:582 */
+
+/* compile_internal (graph.rs:629): compile without activation; the schedule is kept for
+ * inspection through schedule_*. Returns fw_compile_error. */
+FW_EXPORT int FW_FN(graph_compile_internal)(fw_ctx* ctx, uint32_t max_block_frames);
+FW_EXPORT uint32_t FW_FN(schedule_len)(fw_ctx* ctx);                                /* schedule.rs:167 */
+FW_EXPORT uint32_t FW_FN(schedule_num_buffers)(fw_ctx* ctx);                        /* schedule.rs:171 */
+FW_EXPORT int FW_FN(schedule_node)(fw_ctx* ctx, uint32_t i, fw_scheduled_node* out);
+
+/* ---- node parameters (main-thread side; relaxed-atomic stores in the reference) -------- */
+FW_EXPORT int FW_FN(volume_set_percent_volume)(fw_ctx* ctx, fw_node_id node, uint32_t voice, float percent); /* volume.rs:28 */
+FW_EXPORT int FW_FN(volume_set_percent_volumes)(fw_ctx* ctx, fw_node_id node, const float* percent, uint32_t n_voices);
+FW_EXPORT int FW_FN(pan_set_pan)(fw_ctx* ctx, fw_node_id node, uint32_t voice, float pan);
+FW_EXPORT int FW_FN(pan_set_pans)(fw_ctx* ctx, fw_node_id node, const float* pan, uint32_t n_voices);
+FW_EXPORT int FW_FN(pan_set_gains)(fw_ctx* ctx, fw_node_id node, uint32_t voice, float gain_l, float gain_r);
+/* coeffs = {b0, b1, b2, a1, a2} (a0-normalised) */
+FW_EXPORT int FW_FN(biquad_set_coeffs)(fw_ctx* ctx, fw_node_id node, uint32_t voice, uint32_t stage, const float* coeffs5);
+/* coeffs: [voice][stage][5] */
+FW_EXPORT int FW_FN(biquad_set_all_coeffs)(fw_ctx* ctx, fw_node_id node, const float* coeffs, uint32_t n_voices, uint32_t n_stages);
+/* RBJ cookbook design, f64 -> f32, host only. type: 0 lowpass 1 highpass 2 bandpass 3 notch 4 peaking 5 lowshelf 6 highshelf */
+FW_EXPORT void FW_FN(biquad_design_rbj)(uint32_t type, double fc, double q, double gain_db, double sample_rate, float* coeffs5);
+
+/* ---- lifecycle (context.rs:46-211) ------------------------------------------------------- */
+/* 0 => *out_processor set (Some); 1 => already active (None) */
+FW_EXPORT int FW_FN(ctx_activate)(fw_ctx* ctx, uint32_t sample_rate, uint32_t num_stream_in_channels,
+                                  uint32_t num_stream_out_channels, uint32_t max_block_frames, void* user_cx,
+                                  fw_processor** out_processor);                    /* context.rs:46 */
+FW_EXPORT int FW_FN(ctx_is_activated)(fw_ctx* ctx);                                 /* context.rs:85 */
+FW_EXPORT int FW_FN(ctx_update)(fw_ctx* ctx, fw_update_status* out);                /* context.rs:93 */
+/* Blocks like the reference (Stop message, then 2 ms polls up to 3 s) until the processor has
+ * been dropped with processor_free on the stream side. Returns the user_cx or NULL. */
+FW_EXPORT void* FW_FN(ctx_deactivate)(fw_ctx* ctx, int stream_is_running);          /* context.rs:162 */
+
+/* ---- the hot path (processor.rs:61-248, schedule.rs:213-343) ---------------------------- */
+FW_EXPORT int FW_FN(processor_process_interleaved)(fw_processor* p, const float* input, float* output,
+                                                   uint32_t num_in_channels, uint32_t num_out_channels,
+                                                   uint64_t frames, double stream_time_secs,
+                                                   uint32_t stream_status);         /* processor.rs:61 */
+/* planar host buffers; *out_silence_mask = graph_out silence mask of the last block (schedule.rs:267-276) */
+FW_EXPORT int FW_FN(processor_process_planar)(fw_processor* p, const float* input, float* output,
+                                              uint32_t num_in_channels, uint32_t num_out_channels, uint64_t frames,
+                                              double stream_time_secs, uint32_t stream_status,
+                                              uint64_t* out_silence_mask);
+/* planar DEVICE buffers, asynchronous on the processor's stream (product only) */
+FW_EXPORT int FW_FN(processor_process_planar_device)(fw_processor* p, const float* d_input, float* d_output,
+                                                     uint32_t num_in_channels, uint32_t num_out_channels,
+                                                     uint64_t frames, double stream_time_secs, uint32_t stream_status);
+FW_EXPORT void FW_FN(processor_free)(fw_processor* p);                              /* Drop processor.rs:251 */
+
+/* ---- device plumbing for drivers and benchmarks (product only; oracle returns errors) --- */
+FW_EXPORT int FW_FN(device_count)(void);
+FW_EXPORT const char* FW_FN(last_device_error)(void);
+FW_EXPORT void* FW_FN(dev_malloc)(int device, uint64_t bytes);
+FW_EXPORT void FW_FN(dev_free)(int device, void* p);
+FW_EXPORT void* FW_FN(host_alloc_pinned)(uint64_t bytes);
+FW_EXPORT void FW_FN(host_free_pinned)(void* p);
+FW_EXPORT int FW_FN(processor_h2d)(fw_processor* p, void* dst, const void* src, uint64_t bytes);  /* async on the stream */
+FW_EXPORT int FW_FN(processor_d2h)(fw_processor* p, void* dst, const void* src, uint64_t bytes);
+FW_EXPORT int FW_FN(processor_sync)(fw_processor* p);
+/* CUDA events on the processor's stream: record slot 0/1, elapsed in ms */
+FW_EXPORT int FW_FN(processor_event_record)(fw_processor* p, int slot);
+FW_EXPORT float FW_FN(processor_event_elapsed_ms)(fw_processor* p, int slot_start, int slot_stop);
+FW_EXPORT uint64_t FW_FN(processor_kernel_launches)(fw_processor* p); /* kernels launched so far */
+FW_EXPORT int FW_FN(processor_l2_flush)(fw_processor* p);             /* writes a >L2 scratch buffer */
+
+/* ---- multi-GPU master bus (voices sharded by rank) --------------------------- */
+FW_EXPORT int FW_FN(comm_unique_id)(uint8_t* id128);                  /* ncclGetUniqueId */
+FW_EXPORT int FW_FN(processor_comm_init)(fw_processor* p, int rank, int world_size, const uint8_t* id128);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FW_B200_H */

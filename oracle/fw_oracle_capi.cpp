@@ -1,0 +1,473 @@
+// fw_oracle_capi.cpp — CPU ORACLE C API (TEST INFRASTRUCTURE, NOT PRODUCT CODE).
+//
+// Exports include/fw_b200.h with the `fwo_` prefix on top of fw_oracle.hpp. A context
+// with num_voices = V is literally V reference contexts (context.rs:29) driven in
+// lock-step; the master bus is a balanced tree of the restated 2-port SumNode
+// processor (sum.rs:69-81) evaluated per block, exactly as a tree of SumNodes inside
+// one reference graph would be.
+#define FW_API_PREFIX fwo_
+#include "../include/fw_b200.h"
+#include "fw_oracle.hpp"
+
+#include <chrono>
+#include <thread>
+
+using namespace fwo;
+
+static inline fw_node_id pack(Index i) { return (uint64_t)i.slot | ((uint64_t)i.generation << 32); }
+static inline Index unpack(uint64_t v) { return Index{(uint32_t)(v & 0xffffffffu), (uint32_t)(v >> 32)}; }
+static inline NodeID nid(uint64_t v) { return NodeID{unpack(v), ""}; }
+
+struct fw_ctx {
+    fw_graph_config cfg;
+    std::vector<std::unique_ptr<FirewheelGraphCtx>> voices;
+    std::unique_ptr<CompiledSchedule> dbg_schedule;
+    std::string last_error;
+    fw_processor* live_processor = nullptr;
+};
+struct fw_processor {
+    fw_ctx* ctx;
+    std::vector<std::unique_ptr<FirewheelProcessor>> procs;
+    uint32_t max_block_frames;
+};
+
+static std::unique_ptr<AudioNode> make_node(const fw_node_desc* d) {
+    switch (d->kind) {
+        case FW_NODE_DUMMY: return std::make_unique<DummyAudioNode>();
+        case FW_NODE_VOLUME: return std::make_unique<VolumeNode>(d->f0);
+        case FW_NODE_SUM: return std::make_unique<SumNode>();
+        case FW_NODE_MONO_TO_STEREO: return std::make_unique<MonoToStereoNode>();
+        case FW_NODE_STEREO_TO_MONO: return std::make_unique<StereoToMonoNode>();
+        case FW_NODE_HARD_CLIP: return std::make_unique<HardClipNode>(d->f0);
+        case FW_NODE_PAN: return std::make_unique<PanNode>(d->f0);
+        case FW_NODE_BIQUAD: return std::make_unique<BiquadNode>(d->u0);
+        case FW_NODE_DELAY: return std::make_unique<DelayNode>(d->u0);
+        case FW_NODE_CONV_REVERB:
+            if (!d->data || d->data_len < (uint64_t)d->u0 * d->u1) return nullptr;
+            return std::make_unique<ConvReverbNode>(d->data, d->u0, d->u1);
+        default: return nullptr;
+    }
+}
+static uint32_t kind_of(const AudioNode* n) {
+    if (dynamic_cast<const VolumeNode*>(n)) return FW_NODE_VOLUME;
+    if (dynamic_cast<const SumNode*>(n)) return FW_NODE_SUM;
+    if (dynamic_cast<const MonoToStereoNode*>(n)) return FW_NODE_MONO_TO_STEREO;
+    if (dynamic_cast<const StereoToMonoNode*>(n)) return FW_NODE_STEREO_TO_MONO;
+    if (dynamic_cast<const HardClipNode*>(n)) return FW_NODE_HARD_CLIP;
+    if (dynamic_cast<const PanNode*>(n)) return FW_NODE_PAN;
+    if (dynamic_cast<const BiquadNode*>(n)) return FW_NODE_BIQUAD;
+    if (dynamic_cast<const DelayNode*>(n)) return FW_NODE_DELAY;
+    if (dynamic_cast<const ConvReverbNode*>(n)) return FW_NODE_CONV_REVERB;
+    return FW_NODE_DUMMY;
+}
+template <class F> static void each_voice(fw_ctx* c, uint32_t voice, F&& f) {
+    if (voice == FW_ALL_VOICES) { for (auto& v : c->voices) f(*v); }
+    else if (voice < c->voices.size()) f(*c->voices[voice]);
+}
+static void write_edges(const std::vector<EdgeID>& rm, fw_edge_id* out, uint32_t cap, uint32_t* n) {
+    if (n) *n = (uint32_t)rm.size();
+    for (size_t i = 0; i < rm.size() && i < cap && out; ++i) out[i] = pack(rm[i].idx);
+}
+
+extern "C" {
+
+void fwo_graph_config_default(fw_graph_config* c) { *c = fw_graph_config{0, 2, 64, 256, 1, 0, 0, 0}; }
+
+fw_ctx* fwo_ctx_new(const fw_graph_config* cfg) {
+    if (!cfg || cfg->num_voices == 0 || cfg->num_graph_inputs > 64 || cfg->num_graph_outputs > 64) return nullptr;
+    auto* c = new fw_ctx();
+    c->cfg = *cfg;
+    AudioGraphConfig g{cfg->num_graph_inputs, cfg->num_graph_outputs, cfg->initial_node_capacity, cfg->initial_edge_capacity};
+    for (uint32_t v = 0; v < cfg->num_voices; ++v) c->voices.push_back(std::make_unique<FirewheelGraphCtx>(g));
+    return c;
+}
+void fwo_ctx_free(fw_ctx* c) {
+    if (!c) return;
+    if (c->live_processor) { fw_processor* p = c->live_processor; c->live_processor = nullptr; p->procs.clear(); delete p; }
+    for (auto& v : c->voices) if (v->is_activated()) v->deactivate(false);
+    delete c;
+}
+const char* fwo_ctx_last_error(fw_ctx* c) { return c ? c->last_error.c_str() : "null context"; }
+fw_node_id fwo_graph_in_node(fw_ctx* c) { return pack(c->voices[0]->graph.graph_in_node().idx); }
+fw_node_id fwo_graph_out_node(fw_ctx* c) { return pack(c->voices[0]->graph.graph_out_node().idx); }
+
+fw_node_id fwo_graph_add_node(fw_ctx* c, uint32_t ni, uint32_t no, const fw_node_desc* d) {
+    if (!c || !d || ni > 64 || no > 64) return FW_ID_DANGLING;
+    fw_node_id id = FW_ID_DANGLING;
+    for (auto& v : c->voices) {
+        auto n = make_node(d);
+        if (!n) { c->last_error = "bad node description"; return FW_ID_DANGLING; }
+        id = pack(v->graph.add_node(ni, no, std::move(n)).idx);
+    }
+    return id;
+}
+int fwo_graph_remove_node(fw_ctx* c, fw_node_id node, fw_edge_id* removed, uint32_t cap, uint32_t* n_removed) {
+    int rc = 0; std::vector<EdgeID> rm0;
+    for (size_t v = 0; v < c->voices.size(); ++v) {
+        std::vector<EdgeID> rm;
+        if (!c->voices[v]->graph.remove_node(nid(node), &rm)) rc = -1;
+        if (v == 0) rm0 = rm;
+    }
+    if (rc == 0) write_edges(rm0, removed, cap, n_removed); else if (n_removed) *n_removed = 0;
+    return rc;
+}
+int fwo_graph_set_num_inputs(fw_ctx* c, fw_node_id node, uint32_t n, fw_edge_id* removed, uint32_t cap, uint32_t* n_removed) {
+    if (n > 64) return -1;
+    int rc = 0; std::vector<EdgeID> rm0;
+    for (size_t v = 0; v < c->voices.size(); ++v) {
+        std::vector<EdgeID> rm;
+        if (!c->voices[v]->graph.set_num_inputs(nid(node), n, &rm)) rc = -1;
+        if (v == 0) rm0 = rm;
+    }
+    if (rc == 0) write_edges(rm0, removed, cap, n_removed); else if (n_removed) *n_removed = 0;
+    return rc;
+}
+int fwo_graph_set_num_outputs(fw_ctx* c, fw_node_id node, uint32_t n, fw_edge_id* removed, uint32_t cap, uint32_t* n_removed) {
+    if (n > 64) return -1;
+    int rc = 0; std::vector<EdgeID> rm0;
+    for (size_t v = 0; v < c->voices.size(); ++v) {
+        std::vector<EdgeID> rm;
+        if (!c->voices[v]->graph.set_num_outputs(nid(node), n, &rm)) rc = -1;
+        if (v == 0) rm0 = rm;
+    }
+    if (rc == 0) write_edges(rm0, removed, cap, n_removed); else if (n_removed) *n_removed = 0;
+    return rc;
+}
+int fwo_graph_connect(fw_ctx* c, fw_node_id src, uint32_t sp, fw_node_id dst, uint32_t dp, int check, fw_edge_id* out_edge,
+                      fw_node_id* err_node, uint32_t* err_port) {
+    AddEdgeError e0 = AddEdgeError::Ok; EdgeID id0{};
+    for (size_t v = 0; v < c->voices.size(); ++v) {
+        EdgeID id{};
+        AddEdgeError e = c->voices[v]->graph.connect(nid(src), sp, nid(dst), dp, check != 0, &id);
+        if (v == 0) { e0 = e; id0 = id; }
+    }
+    if (e0 == AddEdgeError::Ok) { if (out_edge) *out_edge = pack(id0.idx); return FW_EDGE_OK; }
+    if (err_node) {
+        switch (e0) {
+            case AddEdgeError::SrcNodeNotFound: case AddEdgeError::OutPortOutOfRange: *err_node = src; break;
+            case AddEdgeError::DstNodeNotFound: case AddEdgeError::InPortOutOfRange: case AddEdgeError::InputPortAlreadyConnected: *err_node = dst; break;
+            default: *err_node = FW_ID_DANGLING;
+        }
+    }
+    if (err_port) *err_port = (e0 == AddEdgeError::OutPortOutOfRange) ? sp : dp;
+    return (int)e0;
+}
+int fwo_graph_disconnect(fw_ctx* c, fw_node_id src, uint32_t sp, fw_node_id dst, uint32_t dp) {
+    int r = 0;
+    for (size_t v = 0; v < c->voices.size(); ++v) { bool b = c->voices[v]->graph.disconnect(nid(src), sp, nid(dst), dp); if (v == 0) r = b; }
+    return r;
+}
+int fwo_graph_disconnect_by_edge_id(fw_ctx* c, fw_edge_id e) {
+    int r = 0;
+    for (size_t v = 0; v < c->voices.size(); ++v) { bool b = c->voices[v]->graph.disconnect_by_edge_id(EdgeID{unpack(e)}); if (v == 0) r = b; }
+    return r;
+}
+int fwo_graph_edge(fw_ctx* c, fw_edge_id e, fw_edge_info* out) {
+    const Edge* ed = c->voices[0]->graph.edge(EdgeID{unpack(e)});
+    if (!ed) return 0;
+    if (out) *out = fw_edge_info{pack(ed->id.idx), pack(ed->src_node.idx), pack(ed->dst_node.idx), ed->src_port, ed->dst_port};
+    return 1;
+}
+int fwo_graph_node_info(fw_ctx* c, fw_node_id node, fw_node_info* out) {
+    const NodeEntry* ne = c->voices[0]->graph.node_info(nid(node));
+    if (!ne) return 0;
+    if (out) {
+        std::memset(out, 0, sizeof(*out));
+        AudioNodeInfo i = ne->weight.node->info();
+        out->num_inputs = ne->num_inputs; out->num_outputs = ne->num_outputs; out->kind = kind_of(ne->weight.node.get());
+        out->num_min_supported_inputs = i.num_min_supported_inputs; out->num_max_supported_inputs = i.num_max_supported_inputs;
+        out->num_min_supported_outputs = i.num_min_supported_outputs; out->num_max_supported_outputs = i.num_max_supported_outputs;
+        out->updates = i.updates;
+        std::strncpy(out->debug_name, ne->id.debug_name, sizeof(out->debug_name) - 1);
+    }
+    return 1;
+}
+uint32_t fwo_graph_num_nodes(fw_ctx* c) { return (uint32_t)c->voices[0]->graph.nodes.len(); }
+uint32_t fwo_graph_num_edges(fw_ctx* c) { return (uint32_t)c->voices[0]->graph.edges.len(); }
+uint32_t fwo_graph_nodes(fw_ctx* c, fw_node_id* out, uint32_t cap) {
+    uint32_t n = 0;
+    c->voices[0]->graph.nodes.for_each([&](Index i, NodeEntry&) { if (out && n < cap) out[n] = pack(i); ++n; });
+    return n;
+}
+uint32_t fwo_graph_edges(fw_ctx* c, fw_edge_id* out, uint32_t cap) {
+    uint32_t n = 0;
+    c->voices[0]->graph.edges.for_each([&](Index i, Edge&) { if (out && n < cap) out[n] = pack(i); ++n; });
+    return n;
+}
+int fwo_graph_cycle_detected(fw_ctx* c) { int r = 0; for (size_t v = 0; v < c->voices.size(); ++v) { bool b = c->voices[v]->graph.cycle_detected(); if (v == 0) r = b; } return r; }
+void fwo_graph_reset(fw_ctx* c) { for (auto& v : c->voices) v->graph.reset(); }
+int fwo_graph_needs_compile(fw_ctx* c) { return c->voices[0]->graph.needs_compile(); }
+
+int fwo_graph_compile_internal(fw_ctx* c, uint32_t max_block_frames) {
+    if (max_block_frames == 0) return FW_COMPILE_NODE_ACTIVATION_FAILED;
+    c->dbg_schedule.reset();
+    CompileErrorInfo e = c->voices[0]->graph.compile_internal(max_block_frames, &c->dbg_schedule);
+    return (int)e.code;
+}
+uint32_t fwo_schedule_len(fw_ctx* c) { return c->dbg_schedule ? (uint32_t)c->dbg_schedule->schedule.size() : 0; }
+uint32_t fwo_schedule_num_buffers(fw_ctx* c) { return c->dbg_schedule ? (uint32_t)c->dbg_schedule->num_buffers : 0; }
+int fwo_schedule_node(fw_ctx* c, uint32_t i, fw_scheduled_node* out) {
+    if (!c->dbg_schedule || i >= c->dbg_schedule->schedule.size() || !out) return 0;
+    const ScheduledNode& sn = c->dbg_schedule->schedule[i];
+    std::memset(out, 0, sizeof(*out));
+    out->id = pack(sn.id.idx);
+    out->num_inputs = (uint32_t)sn.input_buffers.size(); out->num_outputs = (uint32_t)sn.output_buffers.size();
+    for (size_t k = 0; k < sn.input_buffers.size() && k < 64; ++k) { out->in_buffer[k] = (uint32_t)sn.input_buffers[k].buffer_index; out->in_should_clear[k] = sn.input_buffers[k].should_clear; }
+    for (size_t k = 0; k < sn.output_buffers.size() && k < 64; ++k) out->out_buffer[k] = (uint32_t)sn.output_buffers[k].buffer_index;
+    return 1;
+}
+
+// ---- parameters -------------------------------------------------------------------------------
+int fwo_volume_set_percent_volume(fw_ctx* c, fw_node_id node, uint32_t voice, float pct) {
+    int ok = -1;
+    each_voice(c, voice, [&](FirewheelGraphCtx& v) { if (auto* n = dynamic_cast<VolumeNode*>(v.graph.node(nid(node)))) { n->set_percent_volume(pct); ok = 0; } });
+    return ok;
+}
+int fwo_volume_set_percent_volumes(fw_ctx* c, fw_node_id node, const float* pct, uint32_t n) {
+    if (n != c->voices.size()) return -1;
+    for (uint32_t v = 0; v < n; ++v) if (fwo_volume_set_percent_volume(c, node, v, pct[v]) != 0) return -1;
+    return 0;
+}
+int fwo_pan_set_pan(fw_ctx* c, fw_node_id node, uint32_t voice, float pan) {
+    int ok = -1;
+    each_voice(c, voice, [&](FirewheelGraphCtx& v) { if (auto* n = dynamic_cast<PanNode*>(v.graph.node(nid(node)))) { n->set_pan(pan); ok = 0; } });
+    return ok;
+}
+int fwo_pan_set_pans(fw_ctx* c, fw_node_id node, const float* pan, uint32_t n) {
+    if (n != c->voices.size()) return -1;
+    for (uint32_t v = 0; v < n; ++v) if (fwo_pan_set_pan(c, node, v, pan[v]) != 0) return -1;
+    return 0;
+}
+int fwo_pan_set_gains(fw_ctx* c, fw_node_id node, uint32_t voice, float gl, float gr) {
+    int ok = -1;
+    each_voice(c, voice, [&](FirewheelGraphCtx& v) { if (auto* n = dynamic_cast<PanNode*>(v.graph.node(nid(node)))) { n->set_gains(gl, gr); ok = 0; } });
+    return ok;
+}
+int fwo_biquad_set_coeffs(fw_ctx* c, fw_node_id node, uint32_t voice, uint32_t stage, const float* k) {
+    int ok = -1;
+    each_voice(c, voice, [&](FirewheelGraphCtx& v) {
+        if (auto* n = dynamic_cast<BiquadNode*>(v.graph.node(nid(node)))) if (stage < n->params->num_stages) { n->params->st[stage] = BiquadCoeffs{k[0], k[1], k[2], k[3], k[4]}; ok = 0; }
+    });
+    return ok;
+}
+int fwo_biquad_set_all_coeffs(fw_ctx* c, fw_node_id node, const float* k, uint32_t nv, uint32_t ns) {
+    if (nv != c->voices.size()) return -1;
+    for (uint32_t v = 0; v < nv; ++v) for (uint32_t s = 0; s < ns; ++s) if (fwo_biquad_set_coeffs(c, node, v, s, k + ((size_t)v * ns + s) * 5) != 0) return -1;
+    return 0;
+}
+// RBJ Audio-EQ-Cookbook, evaluated in f64, rounded once to f32. (Design helper; the DSP contract is the 5 coefficients.)
+void fwo_biquad_design_rbj(uint32_t type, double fc, double q, double gain_db, double sr, float* out) {
+    double w0 = 2.0 * M_PI * fc / sr, cw = std::cos(w0), sw = std::sin(w0), alpha = sw / (2.0 * q);
+    double A = std::pow(10.0, gain_db / 40.0), b0, b1, b2, a0, a1, a2;
+    switch (type) {
+        case 0: b0 = (1 - cw) / 2; b1 = 1 - cw; b2 = (1 - cw) / 2; a0 = 1 + alpha; a1 = -2 * cw; a2 = 1 - alpha; break;
+        case 1: b0 = (1 + cw) / 2; b1 = -(1 + cw); b2 = (1 + cw) / 2; a0 = 1 + alpha; a1 = -2 * cw; a2 = 1 - alpha; break;
+        case 2: b0 = alpha; b1 = 0; b2 = -alpha; a0 = 1 + alpha; a1 = -2 * cw; a2 = 1 - alpha; break;
+        case 3: b0 = 1; b1 = -2 * cw; b2 = 1; a0 = 1 + alpha; a1 = -2 * cw; a2 = 1 - alpha; break;
+        case 4: b0 = 1 + alpha * A; b1 = -2 * cw; b2 = 1 - alpha * A; a0 = 1 + alpha / A; a1 = -2 * cw; a2 = 1 - alpha / A; break;
+        case 5: { double s = 2 * std::sqrt(A) * alpha;
+            b0 = A * ((A + 1) - (A - 1) * cw + s); b1 = 2 * A * ((A - 1) - (A + 1) * cw); b2 = A * ((A + 1) - (A - 1) * cw - s);
+            a0 = (A + 1) + (A - 1) * cw + s; a1 = -2 * ((A - 1) + (A + 1) * cw); a2 = (A + 1) + (A - 1) * cw - s; break; }
+        default: { double s = 2 * std::sqrt(A) * alpha;
+            b0 = A * ((A + 1) + (A - 1) * cw + s); b1 = -2 * A * ((A - 1) + (A + 1) * cw); b2 = A * ((A + 1) + (A - 1) * cw - s);
+            a0 = (A + 1) - (A - 1) * cw + s; a1 = 2 * ((A - 1) - (A + 1) * cw); a2 = (A + 1) - (A - 1) * cw - s; break; }
+    }
+    out[0] = (float)(b0 / a0); out[1] = (float)(b1 / a0); out[2] = (float)(b2 / a0); out[3] = (float)(a1 / a0); out[4] = (float)(a2 / a0);
+}
+
+// ---- lifecycle -------------------------------------------------------------------------------
+int fwo_ctx_activate(fw_ctx* c, uint32_t sr, uint32_t n_in, uint32_t n_out, uint32_t mbf, void* user_cx, fw_processor** out) {
+    if (!c || !out || sr == 0 || mbf == 0 || n_in > 64 || n_out > 64) return -1;
+    if (c->voices[0]->is_activated()) return 1;
+    auto* p = new fw_processor();
+    p->ctx = c; p->max_block_frames = mbf;
+    for (auto& v : c->voices) p->procs.push_back(v->activate(sr, n_in, n_out, mbf, user_cx));
+    c->live_processor = p;
+    *out = p;
+    return 0;
+}
+int fwo_ctx_is_activated(fw_ctx* c) { return c->voices[0]->is_activated(); }
+int fwo_ctx_update(fw_ctx* c, fw_update_status* out) {
+    UpdateStatus s0;
+    for (size_t v = 0; v < c->voices.size(); ++v) { UpdateStatus s = c->voices[v]->update(); if (v == 0) s0 = s; }
+    if (out) {
+        std::memset(out, 0, sizeof(*out));
+        out->kind = (int32_t)s0.kind; out->graph_error = (int32_t)s0.graph_error.code;
+        out->error_node = pack(s0.graph_error.node.idx); out->error_port = s0.graph_error.port; out->returned_user_cx = s0.returned_user_cx;
+    }
+    if (s0.graph_error.code != CompileGraphError::Ok) c->last_error = s0.graph_error.message;
+    return 0;
+}
+void* fwo_ctx_deactivate(fw_ctx* c, int stream_is_running) {
+    void* cx = nullptr;
+    for (size_t v = 0; v < c->voices.size(); ++v) { void* r = c->voices[v]->deactivate(false); if (v == 0) cx = r; }
+    // The oracle's rings are single-threaded: a still-live processor cannot observe Stop from another
+    // thread, so `stream_is_running` is honoured only as "the caller already freed the processor".
+    (void)stream_is_running;
+    return cx;
+}
+
+// ---- hot path --------------------------------------------------------------------------------
+namespace {
+struct BusItem { std::vector<float> buf; SilenceMask mask; };  // [n_out][bf]
+
+// Balanced tree of 2-port SumNodes over `items` (n_out channels each); returns the root.
+BusItem master_bus_tree(std::vector<BusItem> level, size_t n_out, size_t bf) {
+    SumNodeProcessor sum2(2);
+    while (level.size() > 1) {
+        std::vector<BusItem> next;
+        for (size_t i = 0; i + 1 < level.size(); i += 2) {
+            BusItem o; o.buf.assign(n_out * bf, 0.0f);
+            std::vector<const float*> in; std::vector<float*> out; SilenceMask in_mask = SilenceMask::none();
+            for (size_t port = 0; port < 2; ++port) for (size_t ch = 0; ch < n_out; ++ch) {
+                const BusItem& s = level[i + port];
+                in.push_back(s.buf.data() + ch * bf);
+                if (s.mask.is_channel_silent(ch)) in_mask.set_channel(port * n_out + ch, true);
+            }
+            for (size_t ch = 0; ch < n_out; ++ch) out.push_back(o.buf.data() + ch * bf);
+            SilenceMask om = SilenceMask::none();
+            sum2.process(bf, in, out, ProcInfo{in_mask, &om, 0.0, 0, nullptr});
+            o.mask = om;
+            next.push_back(std::move(o));
+        }
+        if (level.size() & 1) next.push_back(std::move(level.back()));
+        level = std::move(next);
+    }
+    return std::move(level[0]);
+}
+}  // namespace
+
+int fwo_processor_process_planar(fw_processor* p, const float* input, float* output, uint32_t n_in, uint32_t n_out, uint64_t frames,
+                                 double t, uint32_t status, uint64_t* out_mask) {
+    if (!p) return FW_PROC_BAD_ARGS;
+    size_t V = p->procs.size(); bool bus = p->ctx->cfg.master_bus != 0;
+    size_t mbf = p->max_block_frames; int rc = FW_PROC_OK;
+    if (out_mask) *out_mask = 0;
+    std::vector<const float*> in_ptrs(n_in); std::vector<float*> out_ptrs(n_out);
+    std::vector<BusItem> items;
+    size_t done = 0;
+    // frames == 0 still polls messages like processor.rs:76-89
+    do {
+        size_t bf = std::min<size_t>(frames - done, mbf);
+        if (bus) { items.assign(V, BusItem{}); }
+        for (size_t v = 0; v < V; ++v) {
+            for (uint32_t c = 0; c < n_in; ++c) in_ptrs[c] = input + ((size_t)v * n_in + c) * frames + done;
+            uint64_t m = 0; ProcessorStatus st;
+            if (bus) {
+                items[v].buf.assign((size_t)n_out * bf, 0.0f);
+                for (uint32_t c = 0; c < n_out; ++c) out_ptrs[c] = items[v].buf.data() + (size_t)c * bf;
+                st = p->procs[v]->process_planar(in_ptrs.data(), out_ptrs.data(), n_in, n_out, bf, t, status, &m);
+                items[v].mask = SilenceMask{m};
+            } else {
+                for (uint32_t c = 0; c < n_out; ++c) out_ptrs[c] = output + ((size_t)v * n_out + c) * frames + done;
+                st = p->procs[v]->process_planar(in_ptrs.data(), out_ptrs.data(), n_in, n_out, bf, t, status, &m);
+                if (out_mask && v == 0) *out_mask = m;
+            }
+            if (st == ProcessorStatus::DropProcessor) rc = FW_PROC_DROP_PROCESSOR;
+        }
+        if (bus && bf > 0) {
+            BusItem root = master_bus_tree(std::move(items), n_out, bf);
+            for (uint32_t c = 0; c < n_out; ++c) std::memcpy(output + (size_t)c * frames + done, root.buf.data() + (size_t)c * bf, bf * sizeof(float));
+            if (out_mask) *out_mask = root.mask.bits;
+        }
+        if (rc != FW_PROC_OK) {  // processor.rs:71-74,150-155: zero-fill what was not produced
+            size_t rows = bus ? n_out : V * n_out;
+            for (size_t r = 0; r < rows; ++r) for (size_t i = done; i < frames; ++i) output[r * frames + i] = 0.0f;
+            break;
+        }
+        done += bf;
+    } while (done < frames);
+    return rc;
+}
+
+int fwo_processor_process_interleaved(fw_processor* p, const float* input, float* output, uint32_t n_in, uint32_t n_out, uint64_t frames,
+                                      double t, uint32_t status) {
+    if (!p) return FW_PROC_BAD_ARGS;
+    size_t V = p->procs.size(); bool bus = p->ctx->cfg.master_bus != 0;
+    if (!bus) {
+        int rc = FW_PROC_OK;
+        for (size_t v = 0; v < V; ++v) {
+            ProcessorStatus st = p->procs[v]->process_interleaved(input + v * frames * n_in, frames * n_in, output + v * frames * n_out, frames * n_out,
+                                                                  n_in, n_out, frames, t, status);
+            if (st == ProcessorStatus::DropProcessor) rc = FW_PROC_DROP_PROCESSOR;
+        }
+        return rc;
+    }
+    // master bus: de-interleave per voice, run the planar path, interleave the bus with the root mask
+    std::vector<float> pin((size_t)V * n_in * frames), pout((size_t)n_out * frames);
+    for (size_t v = 0; v < V; ++v) for (size_t f = 0; f < frames; ++f) for (uint32_t c = 0; c < n_in; ++c)
+        pin[((size_t)v * n_in + c) * frames + f] = input[((size_t)v * frames + f) * n_in + c];
+    uint64_t m = 0;
+    int rc = fwo_processor_process_planar(p, pin.data(), pout.data(), n_in, n_out, frames, t, status, &m);
+    SilenceMask mask{m};
+    std::vector<const float*> chans(n_out);
+    for (uint32_t c = 0; c < n_out; ++c) chans[c] = pout.data() + (size_t)c * frames;
+    if (n_out == 2) interleave_stereo(chans[0], chans[1], output, frames * 2, &mask);
+    else interleave(chans, frames, output, frames * n_out, n_out, &mask);
+    return rc;
+}
+int fwo_processor_process_planar_device(fw_processor*, const float*, float*, uint32_t, uint32_t, uint64_t, double, uint32_t) { return FW_PROC_DEVICE_ERROR; }
+void fwo_processor_free(fw_processor* p) {
+    if (!p) return;
+    if (p->ctx && p->ctx->live_processor == p) p->ctx->live_processor = nullptr;
+    p->procs.clear();  // Drop: each voice's processor posts Dropped{..} to its context
+    delete p;
+}
+
+// ---- device plumbing: not available in the oracle ---------------------------------------------
+int fwo_device_count(void) { return 0; }
+const char* fwo_last_device_error(void) { return "oracle: no device"; }
+void* fwo_dev_malloc(int, uint64_t) { return nullptr; }
+void fwo_dev_free(int, void*) {}
+void* fwo_host_alloc_pinned(uint64_t) { return nullptr; }
+void fwo_host_free_pinned(void*) {}
+int fwo_processor_h2d(fw_processor*, void*, const void*, uint64_t) { return -1; }
+int fwo_processor_d2h(fw_processor*, void*, const void*, uint64_t) { return -1; }
+int fwo_processor_sync(fw_processor*) { return 0; }
+int fwo_processor_event_record(fw_processor*, int) { return -1; }
+float fwo_processor_event_elapsed_ms(fw_processor*, int, int) { return -1.0f; }
+uint64_t fwo_processor_kernel_launches(fw_processor*) { return 0; }
+int fwo_processor_l2_flush(fw_processor*) { return -1; }
+int fwo_comm_unique_id(uint8_t*) { return -1; }
+int fwo_processor_comm_init(fw_processor*, int, int, const uint8_t*) { return -1; }
+
+// ---- oracle-only extras for known-answer tests and the CPU baseline ---------------------------
+// ParamSmoother driven directly (smoother.rs:93-205): returns the status after the last block.
+FW_EXPORT int fwo_smoother_run(float initial, uint32_t sample_rate, uint32_t max_block_frames, const float* targets, const uint32_t* frames_per_block,
+                               uint32_t n_blocks, float* out_curves /* [n_blocks][max_block_frames] */, uint32_t* out_len, uint32_t* out_status,
+                               float* out_ab) {
+    ParamSmoother s(initial, sample_rate, max_block_frames);
+    if (out_ab) { out_ab[0] = s.a; out_ab[1] = s.b; }
+    for (uint32_t k = 0; k < n_blocks; ++k) {
+        SmoothedOutput o = s.set_and_process(targets[k], frames_per_block[k]);
+        if (out_len) out_len[k] = (uint32_t)o.len;
+        if (out_status) out_status[k] = (uint32_t)o.status;
+        if (out_curves) std::memcpy(out_curves + (size_t)k * max_block_frames, o.values, std::min<size_t>(o.len, max_block_frames) * sizeof(float));
+    }
+    return (int)s.status;
+}
+FW_EXPORT float fwo_percent_volume_to_raw_gain(float p) { return percent_volume_to_raw_gain(p); }
+FW_EXPORT float fwo_db_to_gain_clamped_neg_100_db(float db) { return db_to_gain_clamped_neg_100_db(db); }
+FW_EXPORT float fwo_bf16_round(float x) { return bf16_round(x); }
+FW_EXPORT void fwo_pan_to_gains(float pan, float* gl, float* gr) { pan_to_gains(pan, gl, gr); }
+FW_EXPORT uint64_t fwo_silence_mask_new_all_silent(uint32_t n) { return SilenceMask::new_all_silent(n).bits; }
+FW_EXPORT int fwo_silence_mask_query(uint64_t bits, uint32_t n, int which) {
+    SilenceMask m{bits};
+    return which == 0 ? m.any_channel_silent(n) : which == 1 ? m.all_channels_silent(n) : m.is_channel_silent(n);
+}
+FW_EXPORT uint64_t fwo_deinterleave(float* planar /* [n_ch_out][frames], pre-filled (stale) */, uint32_t n_ch_out, uint32_t frames,
+                                    const float* interleaved, uint32_t n_interleaved, int calc_mask) {
+    std::vector<float*> ch(n_ch_out);
+    for (uint32_t c = 0; c < n_ch_out; ++c) ch[c] = planar + (size_t)c * frames;
+    return deinterleave(ch, frames, interleaved, (size_t)frames * n_interleaved, n_interleaved, calc_mask != 0).bits;
+}
+FW_EXPORT void fwo_interleave(const float* planar, uint32_t n_ch_in, uint32_t frames, float* interleaved, uint32_t n_interleaved,
+                              int use_mask, uint64_t mask_bits, int stereo_fast_path) {
+    std::vector<const float*> ch(n_ch_in);
+    for (uint32_t c = 0; c < n_ch_in; ++c) ch[c] = planar + (size_t)c * frames;
+    SilenceMask m{mask_bits};
+    if (stereo_fast_path) interleave_stereo(ch[0], ch[1], interleaved, (size_t)frames * 2, use_mask ? &m : nullptr);
+    else interleave(ch, frames, interleaved, (size_t)frames * n_interleaved, n_interleaved, use_mask ? &m : nullptr);
+}
+
+}  // extern "C"
