@@ -1,0 +1,167 @@
+// graph.hpp — product host side: AudioGraph + schedule compiler (pure C++, no CUDA).
+//
+// Mirrors the observable behaviour of firewheel-graph's control plane so the C ABI is a
+// drop-in: crates/firewheel-graph/src/graph.rs (AudioGraph), graph/compiler.rs (Kahn sort
+// + buffer assignment) and graph/error.rs. Node / edge ids are generational slot indices
+// with thunderdome 0.6.1's observable rules (LIFO slot reuse, generation bump on reuse,
+// ascending-slot iteration) because ids cross the boundary.
+//
+// Internals are NOT the reference's: slots live in flat vectors with an explicit free
+// stack, adjacency is rebuilt into CSR-style per-node port tables, and buffer lifetimes
+// are tracked with plain reference counts. The compiled result additionally carries what
+// the device lowering needs (per-port producer links).
+#pragma once
+#include <cstdint>
+#include <cstring>
+#include <deque>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <unordered_set>
+#include <vector>
+
+#include "../../include/fw_b200.h"
+
+namespace fw {
+
+struct Id {
+    uint32_t slot = UINT32_MAX, gen = UINT32_MAX;
+    bool operator==(const Id& o) const { return slot == o.slot && gen == o.gen; }
+    bool operator!=(const Id& o) const { return !(*this == o); }
+    uint64_t pack() const { return (uint64_t)slot | ((uint64_t)gen << 32); }
+    static Id unpack(uint64_t v) { return Id{(uint32_t)(v & 0xffffffffu), (uint32_t)(v >> 32)}; }
+};
+
+// Generational slot table. Free slots are reused most-recently-freed first.
+template <class T>
+class SlotTable {
+    struct Slot { uint32_t gen = 0; bool live = false; T value{}; };
+    std::vector<Slot> slots_;
+    std::vector<uint32_t> free_;  // stack
+    uint32_t live_ = 0;
+
+  public:
+    Id insert(T v) {
+        uint32_t s;
+        if (!free_.empty()) { s = free_.back(); free_.pop_back(); }
+        else { s = (uint32_t)slots_.size(); slots_.emplace_back(); }
+        Slot& sl = slots_[s];
+        sl.gen += 1; sl.live = true; sl.value = std::move(v);
+        ++live_;
+        return Id{s, sl.gen};
+    }
+    bool erase(Id id, T* out = nullptr) {
+        if (!has(id)) return false;
+        Slot& sl = slots_[id.slot];
+        if (out) *out = std::move(sl.value);
+        sl.value = T{}; sl.live = false;
+        free_.push_back(id.slot);
+        --live_;
+        return true;
+    }
+    bool has(Id id) const { return id.slot < slots_.size() && slots_[id.slot].live && slots_[id.slot].gen == id.gen; }
+    T* find(Id id) { return has(id) ? &slots_[id.slot].value : nullptr; }
+    const T* find(Id id) const { return has(id) ? &slots_[id.slot].value : nullptr; }
+    T* by_slot(uint32_t s, Id* id = nullptr) {
+        if (s >= slots_.size() || !slots_[s].live) return nullptr;
+        if (id) *id = Id{s, slots_[s].gen};
+        return &slots_[s].value;
+    }
+    uint32_t size() const { return live_; }
+    uint32_t slot_count() const { return (uint32_t)slots_.size(); }
+    template <class F> void each(F&& f) {
+        for (uint32_t s = 0; s < slots_.size(); ++s) if (slots_[s].live) f(Id{s, slots_[s].gen}, slots_[s].value);
+    }
+};
+
+// ---- node parameters (main-thread side; the stream side snapshots them at call start) -------
+struct NodeParams {
+    uint32_t kind = FW_NODE_DUMMY;
+    uint32_t num_voices = 1;
+    uint64_t version = 1;  // bumped on every change; the device mirror re-uploads when it differs
+    // volume (volume.rs:8-34)
+    std::vector<float> percent, raw_gain;
+    // pan
+    std::vector<float> pan, gain_l, gain_r;
+    // hard clip (hard_clip.rs:8-12)
+    float threshold_gain = 0.0f;
+    // biquad
+    uint32_t num_stages = 0;
+    std::vector<float> coeffs;  // [voice][stage][5]
+    // delay
+    uint32_t delay = 0;
+    // conv reverb
+    uint32_t ir_len = 0, ir_channels = 0;
+    std::vector<float> ir;  // [ch][len] f32 (rounded to bf16 on the device side)
+};
+
+const char* node_debug_name(uint32_t kind);
+// AudioNodeInfo per kind (node.rs:57-79 as filled in by each basic node)
+void node_supported_ports(uint32_t kind, uint32_t* min_in, uint32_t* max_in, uint32_t* min_out, uint32_t* max_out);
+// AudioNode::activate argument checks (volume.rs:63-65, sum.rs:27-29, hard_clip.rs:37-39, ours). "" => Ok.
+std::string node_check_activation(const NodeParams& p, uint32_t num_inputs, uint32_t num_outputs);
+
+struct EdgeRec { Id id; Id src, dst; uint32_t src_port = 0, dst_port = 0; };
+struct NodeRec {
+    Id id; uint32_t num_inputs = 0, num_outputs = 0;
+    std::shared_ptr<NodeParams> params;
+    bool activated = false;  // Q5: the reference never sets this to true; kept for fidelity
+};
+
+struct InAssign { uint32_t buffer; bool should_clear; uint32_t generation; Id producer; uint32_t producer_port; };
+struct OutAssign { uint32_t buffer; uint32_t generation; };
+struct SchedNode { Id id; std::vector<InAssign> in; std::vector<OutAssign> out; };
+struct Schedule { std::vector<SchedNode> nodes; uint32_t num_buffers = 0; uint32_t max_block_frames = 0; };
+
+struct CompileError { int code = FW_COMPILE_OK; Id node; uint32_t port = 0; std::string message; };
+
+class Graph {
+  public:
+    Graph(uint32_t num_graph_inputs, uint32_t num_graph_outputs, uint32_t num_voices);
+
+    Id graph_in() const { return gin_; }
+    Id graph_out() const { return gout_; }
+    Id add_node(uint32_t n_in, uint32_t n_out, std::shared_ptr<NodeParams> p);
+    bool remove_node(Id id, std::vector<Id>* removed_edges);
+    bool set_num_inputs(Id id, uint32_t n, std::vector<Id>* removed_edges);
+    bool set_num_outputs(Id id, uint32_t n, std::vector<Id>* removed_edges);
+    int connect(Id src, uint32_t sp, Id dst, uint32_t dp, bool check_cycles, Id* out_edge);
+    bool disconnect(Id src, uint32_t sp, Id dst, uint32_t dp);
+    bool disconnect_edge(Id edge);
+    const EdgeRec* edge(Id e) const { return edges_.find(e); }
+    NodeRec* node(Id n) { return nodes_.find(n); }
+    uint32_t num_nodes() const { return nodes_.size(); }
+    uint32_t num_edges() const { return edges_.size(); }
+    template <class F> void each_node(F&& f) { nodes_.each(f); }
+    template <class F> void each_edge(F&& f) { edges_.each(f); }
+    bool cycle_detected();
+    void reset();
+    bool needs_compile() const { return dirty_; }
+    void mark_dirty() { dirty_ = true; }
+    void clear_dirty() { dirty_ = false; }
+
+    // compiler.rs:139-152: topological order + buffer assignment
+    CompileError compile_schedule(uint32_t max_block_frames, Schedule* out);
+
+    // bookkeeping used by the context (graph.rs:119-121)
+    std::vector<Id> nodes_to_activate, nodes_removed_since_compile;
+
+  private:
+    bool topo_order(std::vector<Id>* order);  // false => cycle
+    void drop_edges_into(Id node, uint32_t port, std::vector<Id>* removed);
+    void drop_edges_from(Id node, uint32_t port, std::vector<Id>* removed);
+    static uint64_t port_key(Id n, uint32_t port) { return ((uint64_t)n.slot << 40) ^ ((uint64_t)n.gen << 8) ^ port; }
+    struct EdgeKey { uint64_t a, b; bool operator==(const EdgeKey& o) const { return a == o.a && b == o.b; } };
+    struct EdgeKeyHash { size_t operator()(const EdgeKey& k) const { return std::hash<uint64_t>()(k.a * 0x9E3779B97F4A7C15ull ^ k.b); } };
+    static EdgeKey edge_key(Id s, uint32_t sp, Id d, uint32_t dp) { return EdgeKey{s.pack() ^ ((uint64_t)sp << 56), d.pack() ^ ((uint64_t)dp << 56)}; }
+
+    SlotTable<NodeRec> nodes_;
+    SlotTable<EdgeRec> edges_;
+    std::unordered_set<uint64_t> connected_inputs_;        // (dst node, dst port)
+    std::unordered_map<EdgeKey, Id, EdgeKeyHash> by_ends_; // existing edges
+    Id gin_, gout_;
+    bool dirty_ = true;
+    uint32_t num_voices_;
+};
+
+}  // namespace fw

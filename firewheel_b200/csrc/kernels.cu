@@ -1,0 +1,482 @@
+// kernels.cu — sm_100a kernels for the per-block audio-graph DSP path.
+//
+// Bit-exactness rules: this TU is compiled with --fmad=false, -ftz=false,
+// -prec-div=true; recurrences additionally spell out __fmul_rn/__fadd_rn. Sum order equals the
+// graph's association order: no atomics, no order-agnostic shuffles on sample data.
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "../../include/fw_b200.h"
+#include "kernels.cuh"
+#include "plan.hpp"
+
+namespace fw {
+
+// =============================================================================================
+// K-ctl: per-voice control pass. One thread per voice walks the compiled schedule block by block
+// and restates the reference's control logic, emitting records for the data kernels.
+//   executor flags      schedule.rs:305-341
+//   ParamSmoother       smoother.rs:115-194 (Q1-Q3, Q10 stall)
+//   VolumeProcessor     volume.rs:92-110      SumNodeProcessor masks  sum.rs:52-65
+//   MonoToStereo        mono_to_stereo.rs:41  StereoToMono stereo_to_mono.rs:41-47
+//   HardClip masks      hard_clip.rs:60-93
+// Only state transitions and gain curves are computed here; no sample data is touched.
+// =============================================================================================
+struct SmLocal { float input, last; uint32_t status; };
+
+__device__ __forceinline__ uint64_t all_silent_mask(uint32_t n) { return n >= 64 ? ~0ull : ((1ull << n) - 1ull); }
+__device__ __forceinline__ bool all_channels_silent(uint64_t m, uint32_t n) { uint64_t a = all_silent_mask(n); return (m & a) == a; }
+
+__device__ __forceinline__ void sm_reset(SmLocal& s, float val, bool& changed) {  // smoother.rs:115-129
+    if (s.status != SM_INACTIVE) { s.status = SM_INACTIVE; s.input = val; s.last = val; changed = true; }
+    else if (s.input != val) { s.input = val; s.last = val; changed = true; }
+}
+
+// set_and_process (smoother.rs:133-140,159-194). Returns the record mode; *first = values[0].
+__device__ __forceinline__ uint32_t sm_set_and_process(SmLocal& s, float val, uint32_t frames, float a, float b, float eps,
+                                                       float* curve, float* const_val, bool* smoothing, bool& changed) {
+    if (!(s.input == val)) { s.input = val; s.status = SM_ACTIVE; changed = true; }
+    if (s.status != SM_ACTIVE || frames == 0) {  // Q1: the constant buffer (== input for any non-Active state)
+        *const_val = s.input; *smoothing = s.status != SM_INACTIVE;
+        return REC_CONST;
+    }
+    const float t = __fmul_rn(s.input, a);
+    const float y0 = __fadd_rn(t, __fmul_rn(s.last, b));
+    *smoothing = true;
+    if (fabsf(__fsub_rn(s.input, y0)) < eps) {  // Q3: settle test on output[0]; reset() overwrites the whole curve
+        s.last = s.input; s.status = SM_DEACTIVATING;  // Q2: stays Deactivating forever
+        changed = true;
+        *const_val = s.input;
+        return REC_CONST;
+    }
+    if (y0 == s.last) {  // Q10: f32 fixed point outside epsilon — the curve is constant and no state changes
+        *const_val = y0;
+        return REC_CONST;
+    }
+    float y = y0;
+    curve[0] = y0;
+    for (uint32_t i = 1; i < frames; ++i) { y = __fadd_rn(t, __fmul_rn(y, b)); curve[i] = y; }
+    s.last = y;
+    changed = true;
+    *const_val = y0;
+    return REC_CURVE;
+}
+
+__global__ void __launch_bounds__(128) control_kernel(ControlArgs a) {
+    const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t V = a.num_voices;
+    if (v >= V) return;
+    const CtlTables& tb = *a.tables;
+    const uint32_t NS = tb.n_smoothers, F = a.block_frames;
+    const uint32_t n_blocks = (a.frames + F - 1) / F;
+
+    SmLocal sm[kMaxSmoothers];
+    for (uint32_t s = 0; s < NS; ++s) { sm[s].input = tb.sm_input[s][v]; sm[s].last = tb.sm_last[s][v]; sm[s].status = tb.sm_status[s][v]; }
+    uint64_t flags = a.flags[v];
+    uint64_t gout_mask = 0;
+    uint32_t steady = 0xffffffffu, k = 0;
+
+    for (; k < n_blocks; ++k) {
+        if (k >= a.rec.kt_max) { *a.rec.error = 1; break; }
+        const uint32_t frames = min(F, a.frames - k * F);
+        bool changed = false;
+        uint32_t modes = 0;
+        for (uint32_t n = 0; n < tb.n_nodes; ++n) {
+            const CtlNode nd = tb.nodes[n];
+            uint64_t in_mask = 0;
+            for (uint32_t i = 0; i < nd.n_in; ++i) {  // schedule.rs:305-320
+                const uint64_t bit = 1ull << tb.in_buf[nd.in_off + i];
+                if (tb.in_clear[nd.in_off + i] && !(flags & bit)) { flags |= bit; changed = true; }
+                if (flags & bit) in_mask |= 1ull << i;
+            }
+            uint64_t out_mask = 0;  // processor.rs:233 NONE_SILENT
+            switch (nd.kind) {
+                case FW_NODE_VOLUME: {
+                    SmLocal& s = sm[nd.sm0];
+                    const float g = tb.sm_target[nd.sm0][v];  // volume.rs:92
+                    if (all_channels_silent(in_mask, nd.n_in)) {  // volume.rs:94-100
+                        sm_reset(s, g, changed);
+                        modes |= REC_CLEAR << (2 * nd.sm0);
+                        out_mask = all_silent_mask(nd.n_out);
+                    } else {
+                        float cv; bool smoothing;
+                        float* curve = a.rec.curves + ((size_t)(k * NS + nd.sm0) * V + v) * F;
+                        uint32_t m = sm_set_and_process(s, g, frames, a.a, a.b, a.eps, curve, &cv, &smoothing, changed);
+                        if (!smoothing && cv < 0.00001f) {  // volume.rs:104-108
+                            m = REC_CLEAR; out_mask = all_silent_mask(nd.n_out);
+                        } else {
+                            out_mask = in_mask;  // volume.rs:110
+                        }
+                        modes |= m << (2 * nd.sm0);
+                        a.rec.vals[(size_t)(k * NS + nd.sm0) * V + v] = cv;
+                    }
+                    break;
+                }
+                case FW_NODE_PAN: {
+                    const float gl = tb.sm_target[nd.sm0][v], gr = tb.sm_target[nd.sm1][v];
+                    if (all_channels_silent(in_mask, nd.n_in)) {
+                        sm_reset(sm[nd.sm0], gl, changed); sm_reset(sm[nd.sm1], gr, changed);
+                        modes |= (REC_CLEAR << (2 * nd.sm0)) | (REC_CLEAR << (2 * nd.sm1));
+                        out_mask = all_silent_mask(nd.n_out);
+                    } else {
+                        float cv; bool smoothing;
+                        uint32_t m = sm_set_and_process(sm[nd.sm0], gl, frames, a.a, a.b, a.eps,
+                                                        a.rec.curves + ((size_t)(k * NS + nd.sm0) * V + v) * F, &cv, &smoothing, changed);
+                        modes |= m << (2 * nd.sm0);
+                        a.rec.vals[(size_t)(k * NS + nd.sm0) * V + v] = cv;
+                        m = sm_set_and_process(sm[nd.sm1], gr, frames, a.a, a.b, a.eps,
+                                               a.rec.curves + ((size_t)(k * NS + nd.sm1) * V + v) * F, &cv, &smoothing, changed);
+                        modes |= m << (2 * nd.sm1);
+                        a.rec.vals[(size_t)(k * NS + nd.sm1) * V + v] = cv;
+                        out_mask = in_mask;
+                    }
+                    break;
+                }
+                case FW_NODE_SUM:  // sum.rs:52-65; the unrolled / generic sums never write the mask (Q7)
+                    if (all_channels_silent(in_mask, nd.n_in)) out_mask = all_silent_mask(nd.n_out);
+                    else if (nd.n_in == nd.n_out) out_mask = in_mask;
+                    break;
+                case FW_NODE_MONO_TO_STEREO:  // mono_to_stereo.rs:41-44
+                    if (in_mask & 1ull) out_mask = all_silent_mask(nd.n_out);
+                    break;
+                case FW_NODE_STEREO_TO_MONO:  // stereo_to_mono.rs:41-47
+                    if (all_channels_silent(in_mask, 2) || nd.n_in < 2 || nd.n_out == 0) out_mask = all_silent_mask(nd.n_out);
+                    break;
+                case FW_NODE_HARD_CLIP:  // hard_clip.rs:60-80 leaves the mask untouched on the stereo fast path
+                    if (!(nd.n_in == 2 && nd.n_out == 2 && (in_mask & 3ull) == 0)) out_mask = in_mask;
+                    break;
+                default: break;  // dummy / graph_in / graph_out / biquad / delay / reverb: NONE_SILENT
+            }
+            if (n + 1 == tb.n_nodes) gout_mask = in_mask;  // graph_out is scheduled last (compiler.rs:291)
+            for (uint32_t i = 0; i < nd.n_out; ++i) {  // schedule.rs:338-341
+                const uint64_t bit = 1ull << tb.out_buf[nd.out_off + i];
+                const uint64_t nf = (out_mask >> i) & 1ull ? (flags | bit) : (flags & ~bit);
+                if (nf != flags) { flags = nf; changed = true; }
+            }
+        }
+        a.rec.modes[(size_t)k * V + v] = modes;
+        if (!changed) { steady = k; break; }  // nothing moved: every later block replays this record
+    }
+    if (steady == 0xffffffffu) steady = (k == 0 ? 0 : min(k, n_blocks) - 1);
+    a.rec.steady_k[v] = steady;
+    a.rec.gout_mask[v] = gout_mask;
+    for (uint32_t s = 0; s < NS; ++s) { tb.sm_input[s][v] = sm[s].input; tb.sm_last[s][v] = sm[s].last; tb.sm_status[s][v] = sm[s].status; }
+    a.flags[v] = flags;
+}
+
+// =============================================================================================
+// K-chain: fused pointwise voice chain (+ master-bus tree). Replaces, for every voice at once,
+// the executor loop schedule.rs:299-342 over {VolumeProcessor volume.rs:116-143, PanProcessor,
+// HardClip hard_clip.rs:70-90, MonoToStereo :46-48, StereoToMono :49-54} and the SumNode tree
+// (sum.rs:69-81). Intermediate edges live in registers; HBM sees the input once and either the
+// per-voice output or a 1/64-size partial bus.
+//
+// Mapping: a warp owns kVPW consecutive voices x one 32*VEC-frame tile; a CTA of kWarps warps owns
+// kVPC = 64 consecutive voices. All 2*kVPW loads of a thread are issued before first use.
+// =============================================================================================
+template <int VEC> struct VecT;
+template <> struct VecT<4> {
+    using type = float4;
+    static __device__ __forceinline__ void load(const float* p, float (&x)[4]) { float4 v = __ldcs(reinterpret_cast<const float4*>(p)); x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w; }
+    static __device__ __forceinline__ void load_ca(const float* p, float (&x)[4]) { float4 v = __ldg(reinterpret_cast<const float4*>(p)); x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w; }
+    static __device__ __forceinline__ void store(float* p, const float (&x)[4]) { __stcs(reinterpret_cast<float4*>(p), make_float4(x[0], x[1], x[2], x[3])); }
+};
+template <> struct VecT<1> {
+    using type = float;
+    static __device__ __forceinline__ void load(const float* p, float (&x)[1]) { x[0] = __ldcs(p); }
+    static __device__ __forceinline__ void load_ca(const float* p, float (&x)[1]) { x[0] = __ldg(p); }
+    static __device__ __forceinline__ void store(float* p, const float (&x)[1]) { __stcs(p, x[0]); }
+};
+
+struct RecView {  // per-voice record access, either from the CTA's smem stage or straight from global
+    uint32_t kk, modes;
+    const float* vals;  // vals[s * stride]
+    uint32_t stride;
+};
+
+template <int VEC>
+__device__ __forceinline__ void apply_chain(const ChainArgs& a, const RecView& r, uint32_t v, uint32_t t_in_block, float (&x)[2][VEC]) {
+    const uint32_t NS = a.rec.n_smoothers, V = a.num_voices, F = a.block_frames;
+#pragma unroll 1
+    for (uint32_t o = 0; o < a.prog.n_ops; ++o) {
+        const ChainOp op = a.prog.ops[o];
+        switch (op.kind) {
+            case OP_GAIN: {  // volume.rs:116-143: out = in * gain[i] (both channels share the curve)
+                const uint32_t m = (r.modes >> (2 * op.sm0)) & 3u;
+                if (m == REC_CLEAR) {
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) { x[0][i] = 0.0f; x[1][i] = 0.0f; }
+                } else if (m == REC_CONST) {
+                    const float g = r.vals[op.sm0 * r.stride];
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) { x[0][i] = __fmul_rn(x[0][i], g); x[1][i] = __fmul_rn(x[1][i], g); }
+                } else {
+                    float g[VEC];
+                    VecT<VEC>::load_ca(a.rec.curves + ((size_t)(r.kk * NS + op.sm0) * V + v) * F + t_in_block, g);
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) { x[0][i] = __fmul_rn(x[0][i], g[i]); x[1][i] = __fmul_rn(x[1][i], g[i]); }
+                }
+                break;
+            }
+            case OP_PAN: {
+                const uint32_t m0 = (r.modes >> (2 * op.sm0)) & 3u, m1 = (r.modes >> (2 * op.sm1)) & 3u;
+                if (m0 == REC_CLEAR) {
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) { x[0][i] = 0.0f; x[1][i] = 0.0f; }
+                } else {
+                    float gl[VEC], gr[VEC];
+                    if (m0 == REC_CURVE) VecT<VEC>::load_ca(a.rec.curves + ((size_t)(r.kk * NS + op.sm0) * V + v) * F + t_in_block, gl);
+                    else { const float g = r.vals[op.sm0 * r.stride];
+#pragma unroll
+                        for (int i = 0; i < VEC; ++i) gl[i] = g; }
+                    if (m1 == REC_CURVE) VecT<VEC>::load_ca(a.rec.curves + ((size_t)(r.kk * NS + op.sm1) * V + v) * F + t_in_block, gr);
+                    else { const float g = r.vals[op.sm1 * r.stride];
+#pragma unroll
+                        for (int i = 0; i < VEC; ++i) gr[i] = g; }
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) { x[0][i] = __fmul_rn(x[0][i], gl[i]); x[1][i] = __fmul_rn(x[1][i], gr[i]); }
+                }
+                break;
+            }
+            case OP_CLIP: {  // hard_clip.rs:70-76: in.min(t).max(-t)
+                const float th = op.f0;
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) { x[0][i] = fmaxf(fminf(x[0][i], th), -th); x[1][i] = fmaxf(fminf(x[1][i], th), -th); }
+                break;
+            }
+            case OP_M2S:  // mono_to_stereo.rs:46-48
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) x[1][i] = x[0][i];
+                break;
+            case OP_S2M:  // stereo_to_mono.rs:49-54: (l + r) * 0.5
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) x[0][i] = __fmul_rn(__fadd_rn(x[0][i], x[1][i]), 0.5f);
+                break;
+            default: break;
+        }
+    }
+}
+
+constexpr int kVPW = 8, kWarps = 8, kVPC = kVPW * kWarps;
+
+template <int VEC, int CIN, bool BUS>
+__global__ void __launch_bounds__(kWarps * 32) chain_kernel(ChainArgs a) {
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t T = a.frames, V = a.num_voices, F = a.block_frames, NS = a.rec.n_smoothers;
+    const uint32_t c_out = a.prog.c_out;
+    const uint32_t t = (blockIdx.x * 32u + lane) * VEC;
+    const bool t_ok = t < T;
+    const uint32_t vcta = blockIdx.y * kVPC, v0 = vcta + warp * kVPW;
+    const uint32_t k = t_ok ? t / F : 0;
+    const uint32_t t_in_block = t - k * F;
+    const bool zero_in = a.zero_first_block && k == 0;  // Q11: first block after a schedule swap reads a fresh (zero) pool
+
+    // ---- issue every load of this thread up front -------------------------------------------
+    float x[kVPW][2][VEC];
+#pragma unroll
+    for (int j = 0; j < kVPW; ++j) {
+        const uint32_t v = v0 + j;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) x[j][c][i] = 0.0f;
+            if (c < CIN && t_ok && v < V && !zero_in) VecT<VEC>::load(a.in + ((size_t)v * CIN + c) * T + t, x[j][c]);
+        }
+    }
+
+    // ---- records: staged once per CTA when the whole tile lies in one block ------------------
+    __shared__ uint32_t s_kk[kVPC], s_modes[kVPC];
+    __shared__ float s_vals[kMaxSmoothers][kVPC];
+    const bool cta_uniform = (F % (32u * VEC)) == 0u;  // tile never straddles a block boundary
+    if (cta_uniform) {
+        const uint32_t kb = (blockIdx.x * 32u * VEC) / F;
+        if (threadIdx.x < kVPC) {
+            const uint32_t v = vcta + threadIdx.x;
+            uint32_t kk = 0, md = 0;
+            if (v < V) { kk = min(kb, a.rec.steady_k[v]); md = a.rec.modes[(size_t)kk * V + v]; }
+            s_kk[threadIdx.x] = kk; s_modes[threadIdx.x] = md;
+        }
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < NS * kVPC; i += blockDim.x) {
+            const uint32_t s = i / kVPC, vl = i % kVPC, v = vcta + vl;
+            s_vals[s][vl] = v < V ? a.rec.vals[(size_t)(s_kk[vl] * NS + s) * V + v] : 0.0f;
+        }
+        __syncthreads();
+    }
+
+#pragma unroll
+    for (int j = 0; j < kVPW; ++j) {
+        const uint32_t v = v0 + j;
+        if (v < V && t_ok) {
+            RecView r;
+            if (cta_uniform) {
+                const uint32_t vl = warp * kVPW + j;
+                r.kk = s_kk[vl]; r.modes = s_modes[vl]; r.vals = &s_vals[0][vl]; r.stride = kVPC;
+            } else {
+                r.kk = min(k, a.rec.steady_k[v]); r.modes = a.rec.modes[(size_t)r.kk * V + v];
+                r.vals = a.rec.vals + (size_t)r.kk * NS * V + v; r.stride = V;
+            }
+            apply_chain<VEC>(a, r, v, t_in_block, x[j]);
+            if (!BUS) {
+#pragma unroll
+                for (int c = 0; c < 2; ++c) if (c < c_out) VecT<VEC>::store(a.out + ((size_t)v * c_out + c) * T + t, x[j][c]);
+            }
+        }
+    }
+
+    if (BUS) {
+        // Balanced tree over voices: (2i, 2i+1) per level; a right operand that lies beyond the last voice
+        // is skipped (the 1-port SumNode copy, sum.rs:58-65). Levels 1-3 in registers per thread.
+#define FW_COMB(dst, rhs, rhs_first_voice)                                                    \
+    if ((rhs_first_voice) < V) {                                                              \
+        _Pragma("unroll") for (int c = 0; c < 2; ++c) _Pragma("unroll") for (int i = 0; i < VEC; ++i) \
+            dst[c][i] = __fadd_rn(dst[c][i], rhs[c][i]);                                      \
+    }
+        FW_COMB(x[0], x[1], v0 + 1) FW_COMB(x[2], x[3], v0 + 3) FW_COMB(x[4], x[5], v0 + 5) FW_COMB(x[6], x[7], v0 + 7)
+        FW_COMB(x[0], x[2], v0 + 2) FW_COMB(x[4], x[6], v0 + 6)
+        FW_COMB(x[0], x[4], v0 + 4)
+        // Levels 4-6 across the CTA's 8 warps through shared memory (each lane owns its own frames).
+        __shared__ float s_red[kWarps][2][32 * VEC];
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) s_red[warp][c][lane * VEC + i] = x[0][c][i];
+        __syncthreads();
+        if (warp == 0 && t_ok) {
+            float p[kWarps][2][VEC];
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w)
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) p[w][c][i] = s_red[w][c][lane * VEC + i];
+            FW_COMB(p[0], p[1], vcta + 1 * kVPW) FW_COMB(p[2], p[3], vcta + 3 * kVPW) FW_COMB(p[4], p[5], vcta + 5 * kVPW) FW_COMB(p[6], p[7], vcta + 7 * kVPW)
+            FW_COMB(p[0], p[2], vcta + 2 * kVPW) FW_COMB(p[4], p[6], vcta + 6 * kVPW)
+            FW_COMB(p[0], p[4], vcta + 4 * kVPW)
+#pragma unroll
+            for (int c = 0; c < 2; ++c) if (c < c_out) VecT<VEC>::store(a.out + ((size_t)blockIdx.y * c_out + c) * T + t, p[0][c]);
+        }
+#undef FW_COMB
+    }
+}
+
+// K-combine: radix-16 levels of the same balanced tree over partial buses [n_in][rows][T] -> [ceil(n_in/16)][rows][T].
+template <int VEC>
+__global__ void __launch_bounds__(128) combine_kernel(const float* __restrict__ pin, float* __restrict__ pout, uint32_t n_in, uint32_t rows, uint32_t T) {
+    const uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+    if (t >= T) return;
+    const uint32_t row = blockIdx.y, g = blockIdx.z, p0 = g * 16u;
+    float p[16][VEC];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) p[j][i] = 0.0f;
+        if (p0 + j < n_in) VecT<VEC>::load(pin + ((size_t)(p0 + j) * rows + row) * T + t, p[j]);
+    }
+#define FW_COMB1(d, s, first)                                                                  \
+    if ((first) < n_in) { _Pragma("unroll") for (int i = 0; i < VEC; ++i) p[d][i] = __fadd_rn(p[d][i], p[s][i]); }
+#pragma unroll
+    for (int step = 1; step < 16; step <<= 1)
+#pragma unroll
+        for (int j = 0; j + step < 16; j += 2 * step) FW_COMB1(j, j + step, p0 + j + step)
+#undef FW_COMB1
+    VecT<VEC>::store(pout + ((size_t)g * rows + row) * T + t, p[0]);
+}
+
+// =============================================================================================
+// Stream boundary: (de)interleave (util.rs:44-147) for the host-facing process_interleaved.
+// =============================================================================================
+__global__ void deinterleave_kernel(const float* __restrict__ inter, float* __restrict__ planar, uint32_t V, uint32_t C, uint32_t T) {
+    const size_t n = (size_t)V * C * T;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t f = i % T; const size_t vc = i / T; const uint32_t c = vc % C; const size_t v = vc / C;
+        planar[i] = inter[(v * T + f) * C + c];
+    }
+}
+// masks: per-voice graph_out silence masks (or one bus mask when rows_per_mask == 0 is not used: n_masks = 1)
+__global__ void interleave_kernel(const float* __restrict__ planar, float* __restrict__ inter, const uint64_t* __restrict__ masks,
+                                  uint32_t V, uint32_t C, uint32_t T, uint32_t block_frames) {
+    const size_t n = (size_t)V * C * T;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t c = i % C; const size_t vf = i / C; const uint32_t f = vf % T; const size_t v = vf / T;
+        // The mask handed to interleave is the last block's; silent-flagged buffers hold +0.0 anyway
+        // (util.rs:171), so applying it to the final block only is value-identical for earlier blocks.
+        const uint64_t m = masks ? masks[v] : 0ull;
+        const bool last_block = f >= ((T - 1) / block_frames) * block_frames;
+        bool silent;
+        if (C == 2) silent = (m & 3ull) == 3ull;            // interleave_stereo util.rs:129-134
+        else silent = c < 64 && ((m >> c) & 1ull);           // interleave util.rs:103-107
+        inter[i] = (silent && last_block) ? 0.0f : planar[(v * C + c) * T + f];
+    }
+}
+
+__global__ void fill_kernel(float* __restrict__ p, size_t n, float val) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = val;
+}
+
+// bus mask: V == 1 -> the voice's mask; else ALL(n_out) iff every voice is all-silent (2-port SumNode tree, sum.rs:52-56)
+__global__ void bus_mask_kernel(const uint64_t* __restrict__ gout_mask, uint32_t V, uint32_t n_out, uint64_t* __restrict__ bus_mask) {
+    __shared__ int any_audible;
+    if (threadIdx.x == 0) any_audible = 0;
+    __syncthreads();
+    const uint64_t all = all_silent_mask(n_out);
+    for (uint32_t v = threadIdx.x; v < V; v += blockDim.x) if ((gout_mask[v] & all) != all) any_audible = 1;
+    __syncthreads();
+    if (threadIdx.x == 0) *bus_mask = (V == 1) ? gout_mask[0] : (any_audible ? 0ull : all);
+}
+
+// =============================================================================================
+// launchers
+// =============================================================================================
+static inline unsigned grid_for(size_t n) { size_t b = (n + 255) / 256; return (unsigned)(b < 148u * 16u ? b : 148u * 16u); }
+#define FW_LAUNCH_CHECK() do { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return e_; } while (0)
+
+cudaError_t launch_control(const ControlArgs& a, cudaStream_t st) {
+    const uint32_t threads = 128, blocks = (a.num_voices + threads - 1) / threads;
+    control_kernel<<<blocks, threads, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+template <int VEC, int CIN>
+static cudaError_t launch_chain_t(const ChainArgs& a, bool bus, cudaStream_t st) {
+    dim3 grid((a.frames + 32 * VEC - 1) / (32 * VEC), (a.num_voices + kVPC - 1) / kVPC);
+    if (bus) chain_kernel<VEC, CIN, true><<<grid, kWarps * 32, 0, st>>>(a);
+    else chain_kernel<VEC, CIN, false><<<grid, kWarps * 32, 0, st>>>(a);
+    return cudaGetLastError();
+}
+cudaError_t launch_chain(const ChainArgs& a, bool bus, cudaStream_t st) {
+    const bool vec4 = (a.frames % 4 == 0) && (a.block_frames % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.in) | reinterpret_cast<uintptr_t>(a.out)) % 16 == 0);
+    if (a.prog.c_in == 2) return vec4 ? launch_chain_t<4, 2>(a, bus, st) : launch_chain_t<1, 2>(a, bus, st);
+    return vec4 ? launch_chain_t<4, 1>(a, bus, st) : launch_chain_t<1, 1>(a, bus, st);
+}
+uint32_t chain_voice_groups(uint32_t num_voices) { return (num_voices + kVPC - 1) / kVPC; }
+
+cudaError_t launch_combine(const float* pin, float* pout, uint32_t n_in, uint32_t rows, uint32_t T, cudaStream_t st) {
+    const bool vec4 = (T % 4 == 0) && ((reinterpret_cast<uintptr_t>(pin) | reinterpret_cast<uintptr_t>(pout)) % 16 == 0);
+    const uint32_t n_out = (n_in + 15) / 16;
+    if (vec4) { dim3 grid((T / 4 + 127) / 128, rows, n_out); combine_kernel<4><<<grid, 128, 0, st>>>(pin, pout, n_in, rows, T); }
+    else { dim3 grid((T + 127) / 128, rows, n_out); combine_kernel<1><<<grid, 128, 0, st>>>(pin, pout, n_in, rows, T); }
+    return cudaGetLastError();
+}
+cudaError_t launch_deinterleave(const float* inter, float* planar, uint32_t V, uint32_t C, uint32_t T, cudaStream_t st) {
+    const size_t n = (size_t)V * C * T; if (n == 0) return cudaSuccess;
+    deinterleave_kernel<<<grid_for(n), 256, 0, st>>>(inter, planar, V, C, T);
+    return cudaGetLastError();
+}
+cudaError_t launch_interleave(const float* planar, float* inter, const uint64_t* masks, uint32_t V, uint32_t C, uint32_t T, uint32_t block_frames, cudaStream_t st) {
+    const size_t n = (size_t)V * C * T; if (n == 0) return cudaSuccess;
+    interleave_kernel<<<grid_for(n), 256, 0, st>>>(planar, inter, masks, V, C, T, block_frames);
+    return cudaGetLastError();
+}
+cudaError_t launch_fill(float* p, size_t n, float val, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    fill_kernel<<<grid_for(n), 256, 0, st>>>(p, n, val);
+    return cudaGetLastError();
+}
+cudaError_t launch_bus_mask(const uint64_t* gout_mask, uint32_t V, uint32_t n_out, uint64_t* bus_mask, cudaStream_t st) {
+    bus_mask_kernel<<<1, 256, 0, st>>>(gout_mask, V, n_out, bus_mask);
+    return cudaGetLastError();
+}
+
+}  // namespace fw

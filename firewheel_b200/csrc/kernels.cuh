@@ -1,0 +1,20 @@
+// kernels.cuh — launchers for kernels.cu (all asynchronous on the given stream).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+
+#include "plan.hpp"
+
+namespace fw {
+cudaError_t launch_control(const ControlArgs& a, cudaStream_t st);
+cudaError_t launch_chain(const ChainArgs& a, bool bus, cudaStream_t st);
+uint32_t chain_voice_groups(uint32_t num_voices);  // partial buses produced by the bus variant
+cudaError_t launch_combine(const float* pin, float* pout, uint32_t n_in, uint32_t rows, uint32_t T, cudaStream_t st);
+cudaError_t launch_deinterleave(const float* inter, float* planar, uint32_t V, uint32_t C, uint32_t T, cudaStream_t st);
+cudaError_t launch_interleave(const float* planar, float* inter, const uint64_t* masks, uint32_t V, uint32_t C, uint32_t T,
+                              uint32_t block_frames, cudaStream_t st);
+cudaError_t launch_fill(float* p, size_t n, float val, cudaStream_t st);
+cudaError_t launch_bus_mask(const uint64_t* gout_mask, uint32_t V, uint32_t n_out, uint64_t* bus_mask, cudaStream_t st);
+}  // namespace fw

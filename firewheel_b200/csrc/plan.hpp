@@ -1,0 +1,69 @@
+// plan.hpp — PODs shared by the host lowering and the sm_100a kernels.
+//
+// A compiled voice graph is lowered to
+//   * CtlTables  — the schedule as the CONTROL kernel sees it: one thread per voice walks the
+//                  scheduled nodes per block and restates the reference's per-block control logic
+//                  (silence flags schedule.rs:305-341, ParamSmoother state machine smoother.rs:115-194,
+//                  gain's early-outs volume.rs:94-108), emitting one small record per (voice, block);
+//   * ChainProgram — the DATA plane: a linear chain of pointwise node bodies fused into one
+//                  streaming kernel, optionally ending in the master-bus tree sum.
+#pragma once
+#include <cstdint>
+
+namespace fw {
+
+constexpr int kMaxChainOps = 16;
+constexpr int kMaxSmoothers = 16;   // 2 mode bits each in a 32-bit record word
+constexpr int kMaxCtlNodes = 64;
+constexpr int kMaxCtlPorts = 512;
+
+enum SmStatus : uint32_t { SM_INACTIVE = 0, SM_ACTIVE = 1, SM_DEACTIVATING = 2 };   // smoother.rs:29-39
+enum RecMode : uint32_t { REC_CONST = 0, REC_CLEAR = 1, REC_CURVE = 2 };
+
+enum ChainOpKind : uint32_t { OP_GAIN = 0, OP_PAN = 1, OP_CLIP = 2, OP_M2S = 3, OP_S2M = 4 };
+struct ChainOp { uint32_t kind; int32_t sm0, sm1; float f0; };
+struct ChainProgram { uint32_t n_ops, c_in, c_out, pad; ChainOp ops[kMaxChainOps]; };
+
+struct CtlNode {
+    uint8_t kind, n_in, n_out, pad;
+    uint16_t in_off, out_off;   // into in_buf / in_clear / out_buf
+    int16_t sm0, sm1;           // smoother indices (-1: none)
+};
+struct CtlTables {
+    uint32_t n_nodes, n_smoothers, n_buffers, pad;
+    CtlNode nodes[kMaxCtlNodes];
+    uint8_t in_buf[kMaxCtlPorts], in_clear[kMaxCtlPorts], out_buf[kMaxCtlPorts];
+    // per-smoother state (SoA over voices, owned by the node's device state) and its target parameter
+    float* sm_input[kMaxSmoothers];
+    float* sm_last[kMaxSmoothers];
+    uint32_t* sm_status[kMaxSmoothers];
+    const float* sm_target[kMaxSmoothers];
+};
+
+// Per-call record buffers written by the control kernel, read by the data kernels.
+//   modes[k][v]          2 bits per smoother
+//   vals[k][s][v]        constant value of smoother s in block k (REC_CONST)
+//   curves[k][s][v][F]   gain curve (REC_CURVE)
+//   steady_k[v]          blocks >= steady_k[v] reuse the record of block steady_k[v]
+struct Records {
+    uint32_t* modes; float* vals; float* curves; uint32_t* steady_k; uint64_t* gout_mask; uint32_t* error;
+    uint32_t kt_max, n_smoothers;
+};
+
+struct ControlArgs {
+    const CtlTables* tables;
+    Records rec;
+    uint64_t* flags;       // [V] buffer_silence_flags bitset (schedule.rs:170), persists across calls
+    uint32_t num_voices, frames, block_frames;
+    float a, b, eps;       // smoother.rs:99-100,22
+};
+
+struct ChainArgs {
+    const float* in;       // [V][c_in][T]
+    float* out;            // bus: partial bus [G][c_out][T]; else [V][c_out][T]
+    uint32_t num_voices, frames, block_frames, zero_first_block;
+    Records rec;
+    ChainProgram prog;
+};
+
+}  // namespace fw

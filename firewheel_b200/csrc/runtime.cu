@@ -1,0 +1,806 @@
+// runtime.cu — product runtime behind include/fw_b200.h.
+//
+//   fw_ctx        main-thread side (FirewheelGraphCtx context.rs:29): graph edits, parameter stores,
+//                 compile + lowering + device allocation in update(), plan hand-off.
+//   fw_processor  stream side (FirewheelProcessor processor.rs:18): adopts plans from the ring, snapshots
+//                 parameters, enqueues the control + data kernels on its CUDA stream. It never allocates
+//                 graph state; only I/O staging grows to a high-water mark.
+//   Plan          ScheduleHeapData analogue (schedule.rs:128-150): schedule + device tables + record buffers.
+//   NodeDeviceState  the device-resident "processor counterpart" of a node (Box<dyn AudioNodeProcessor>):
+//                 parameter mirrors and per-voice state; survives schedule swaps like processors do
+//                 (processor.rs:176-197) and is released on the main thread (graph.rs:644-669).
+//
+// There is no CPU fallback anywhere in this file: without a CUDA device activate() fails.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/fw_b200.h"
+#include "graph.hpp"
+#include "kernels.cuh"
+#include "plan.hpp"
+
+namespace fw {
+
+static thread_local std::string g_dev_err;
+static bool cuda_ok(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return true;
+    g_dev_err = std::string(what) + ": " + cudaGetErrorString(e);
+    return false;
+}
+#define FW_CUDA(call) fw::cuda_ok((call), #call)
+
+template <class T> static T* dev_alloc(size_t n, bool zero = true) {
+    void* p = nullptr;
+    if (n == 0) n = 1;
+    if (!FW_CUDA(cudaMalloc(&p, n * sizeof(T)))) return nullptr;
+    if (zero) cudaMemset(p, 0, n * sizeof(T));
+    return static_cast<T*>(p);
+}
+
+// wait-free SPSC ring (rtrb::RingBuffer, context.rs:61-64), capacity 16
+template <class T, size_t N = 16> struct Spsc {
+    T slots[N + 1];
+    std::atomic<size_t> head{0}, tail{0};
+    bool push(const T& v) {
+        size_t t = tail.load(std::memory_order_relaxed), n = (t + 1) % (N + 1);
+        if (n == head.load(std::memory_order_acquire)) return false;
+        slots[t] = v; tail.store(n, std::memory_order_release); return true;
+    }
+    bool pop(T* out) {
+        size_t h = head.load(std::memory_order_relaxed);
+        if (h == tail.load(std::memory_order_acquire)) return false;
+        *out = slots[h]; head.store((h + 1) % (N + 1), std::memory_order_release); return true;
+    }
+};
+
+struct NodeDeviceState {
+    int device = 0; uint32_t kind = 0, V = 0, n_sm = 0;
+    std::shared_ptr<NodeParams> params;
+    uint64_t uploaded_version = 0;
+    float* d_target[2] = {nullptr, nullptr};      // volume: raw_gain; pan: gain_l, gain_r
+    float* sm_input[2] = {nullptr, nullptr};
+    float* sm_last[2] = {nullptr, nullptr};
+    uint32_t* sm_status[2] = {nullptr, nullptr};
+    ~NodeDeviceState() {
+        cudaSetDevice(device);
+        for (int i = 0; i < 2; ++i) { cudaFree(d_target[i]); cudaFree(sm_input[i]); cudaFree(sm_last[i]); cudaFree(sm_status[i]); }
+    }
+    const std::vector<float>& host_target(int i) const { return kind == FW_NODE_VOLUME ? params->raw_gain : (i == 0 ? params->gain_l : params->gain_r); }
+    // ParamSmoother::new(val): input = last_output = val, Inactive (smoother.rs:93-112; volume.rs:67-75)
+    bool create() {
+        n_sm = kind == FW_NODE_VOLUME ? 1 : kind == FW_NODE_PAN ? 2 : 0;
+        for (uint32_t i = 0; i < n_sm; ++i) {
+            d_target[i] = dev_alloc<float>(V); sm_input[i] = dev_alloc<float>(V); sm_last[i] = dev_alloc<float>(V); sm_status[i] = dev_alloc<uint32_t>(V);
+            if (!d_target[i] || !sm_input[i] || !sm_last[i] || !sm_status[i]) return false;
+            const float* h = host_target(i).data();
+            if (!FW_CUDA(cudaMemcpy(d_target[i], h, V * 4, cudaMemcpyHostToDevice))) return false;
+            if (!FW_CUDA(cudaMemcpy(sm_input[i], h, V * 4, cudaMemcpyHostToDevice))) return false;
+            if (!FW_CUDA(cudaMemcpy(sm_last[i], h, V * 4, cudaMemcpyHostToDevice))) return false;
+        }
+        uploaded_version = params->version;
+        return true;
+    }
+    // stream side, at call start: the relaxed atomic load of volume.rs:92, batched
+    bool snapshot_params(cudaStream_t st) {
+        const uint64_t ver = params->version;
+        if (ver == uploaded_version) return true;
+        for (uint32_t i = 0; i < n_sm; ++i)
+            if (!FW_CUDA(cudaMemcpyAsync(d_target[i], host_target(i).data(), V * 4, cudaMemcpyHostToDevice, st))) return false;
+        uploaded_version = ver;
+        return true;
+    }
+};
+
+struct Plan {
+    int device = 0;
+    Schedule sched;
+    std::vector<std::shared_ptr<NodeDeviceState>> states;   // keeps every referenced node state alive
+    std::vector<Id> nodes_to_remove;
+    CtlTables* d_tables = nullptr; uint64_t* d_flags = nullptr;
+    ChainProgram prog{}; bool bus = false; uint32_t n_sm = 0, c_in = 0, c_out = 0, num_voices = 0, block_frames = 0;
+    Records rec{};
+    uint64_t* d_bus_mask = nullptr;
+    ~Plan() {
+        cudaSetDevice(device);
+        cudaFree(d_tables); cudaFree(d_flags); cudaFree(rec.modes); cudaFree(rec.vals); cudaFree(rec.curves);
+        cudaFree(rec.steady_k); cudaFree(rec.gout_mask); cudaFree(rec.error); cudaFree(d_bus_mask);
+    }
+};
+
+struct CtxToProc { int kind = 0; Plan* plan = nullptr; };                 // 0 NewSchedule, 1 Stop (processor.rs:265-268)
+struct ProcToCtx { int kind = 0; Plan* plan = nullptr; void* user_cx = nullptr; };  // 0 ReturnSchedule, 1 Dropped (:270-277)
+struct Channels { Spsc<CtxToProc> to_proc; Spsc<ProcToCtx> to_ctx; };
+
+}  // namespace fw
+
+using namespace fw;
+
+struct fw_ctx {
+    fw_graph_config cfg{};
+    std::unique_ptr<Graph> graph;
+    std::map<uint64_t, std::shared_ptr<NodeDeviceState>> node_states;  // activated nodes by packed id
+    std::string last_error;
+    Schedule dbg_schedule; bool dbg_valid = false;
+    // ActiveState (context.rs:17-27)
+    bool active = false; std::shared_ptr<Channels> ch; uint32_t sample_rate = 0, max_block_frames = 0, n_in = 0, n_out = 0;
+};
+
+struct fw_processor {
+    int device = 0; cudaStream_t stream = nullptr; cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::shared_ptr<Channels> ch; void* user_cx = nullptr;
+    Plan* plan = nullptr; bool running = true; bool pending_zero_first = false;
+    uint32_t num_voices = 0, max_block_frames = 0, n_in = 0, n_out = 0; bool bus = false;
+    float sm_a = 0, sm_b = 0, sm_eps = 0;
+    uint64_t launches = 0;
+    // I/O staging (high-water mark)
+    float *d_in = nullptr, *d_out = nullptr, *d_inter = nullptr, *d_part[2] = {nullptr, nullptr}, *d_flush = nullptr;
+    size_t cap_in = 0, cap_out = 0, cap_inter = 0, cap_part[2] = {0, 0};
+    uint64_t* h_masks = nullptr; uint32_t* h_err = nullptr;  // pinned
+    // optional per-kernel-class timing (CUDA events on `stream`)
+    bool profiling = false; std::vector<cudaEvent_t> prof_ev; std::vector<int> prof_class; size_t prof_used = 0;
+};
+
+struct ProfScope {  // brackets the launches of one kernel class with a pair of events
+    fw_processor* p; bool on;
+    ProfScope(fw_processor* p_, int cls) : p(p_), on(false) {
+        if (!p->profiling || p->prof_used + 2 > p->prof_ev.size()) return;
+        on = true; p->prof_class[p->prof_used / 2] = cls;
+        cudaEventRecord(p->prof_ev[p->prof_used], p->stream);
+    }
+    ~ProfScope() { if (on) { cudaEventRecord(p->prof_ev[p->prof_used + 1], p->stream); p->prof_used += 2; } }
+};
+
+// =============================================================================================
+// lowering: schedule -> control tables + fused chain program
+// =============================================================================================
+static bool lower(fw_ctx* c, const Schedule& s, Plan* plan, std::string* why) {
+    Graph& g = *c->graph;
+    const size_t n = s.nodes.size();
+    if (n < 2 || n > (size_t)kMaxCtlNodes) { *why = "schedule too long for the device control tables"; return false; }
+    if (s.num_buffers > 64) { *why = "more than 64 buffers in one voice graph"; return false; }
+    CtlTables tb{};
+    tb.n_nodes = (uint32_t)n; tb.n_buffers = s.num_buffers;
+    uint32_t off_in = 0, off_out = 0, n_sm = 0;
+    std::vector<int> sm_of_node(n, -1);
+    for (size_t i = 0; i < n; ++i) {
+        const SchedNode& sn = s.nodes[i];
+        NodeRec* nr = g.node(sn.id);
+        CtlNode& cn = tb.nodes[i];
+        cn.kind = (uint8_t)nr->params->kind; cn.n_in = (uint8_t)sn.in.size(); cn.n_out = (uint8_t)sn.out.size();
+        cn.in_off = (uint16_t)off_in; cn.out_off = (uint16_t)off_out; cn.sm0 = cn.sm1 = -1;
+        if (off_in + sn.in.size() > (size_t)kMaxCtlPorts || off_out + sn.out.size() > (size_t)kMaxCtlPorts) { *why = "too many ports"; return false; }
+        for (const InAssign& a : sn.in) { tb.in_buf[off_in] = (uint8_t)a.buffer; tb.in_clear[off_in] = a.should_clear; ++off_in; }
+        for (const OutAssign& a : sn.out) tb.out_buf[off_out++] = (uint8_t)a.buffer;
+        auto it = c->node_states.find(sn.id.pack());
+        if (it == c->node_states.end()) { *why = "internal: node without device state"; return false; }
+        std::shared_ptr<NodeDeviceState> st = it->second;
+        plan->states.push_back(st);
+        if (st->n_sm) {
+            if (n_sm + st->n_sm > (uint32_t)kMaxSmoothers) { *why = "more than 16 smoothed parameters in one voice graph"; return false; }
+            sm_of_node[i] = (int)n_sm;
+            cn.sm0 = (int16_t)n_sm; if (st->n_sm == 2) cn.sm1 = (int16_t)(n_sm + 1);
+            for (uint32_t k = 0; k < st->n_sm; ++k) {
+                tb.sm_input[n_sm] = st->sm_input[k]; tb.sm_last[n_sm] = st->sm_last[k]; tb.sm_status[n_sm] = st->sm_status[k]; tb.sm_target[n_sm] = st->d_target[k];
+                ++n_sm;
+            }
+        }
+    }
+    tb.n_smoothers = n_sm;
+
+    // ---- data plane: a linear chain graph_in -> n1 -> ... -> nk -> graph_out, port i to port i ----
+    ChainProgram pr{};
+    const SchedNode& gin = s.nodes.front();
+    const SchedNode& gout = s.nodes.back();
+    uint32_t width = (uint32_t)gin.out.size();
+    if (width != c->n_in) { *why = "stream input channels must equal the graph_in port count on the device path"; return false; }
+    if (gout.in.size() != c->n_out) { *why = "stream output channels must equal the graph_out port count on the device path"; return false; }
+    if (width < 1 || width > 2) { *why = "the fused chain supports 1 or 2 channels (generic per-node lowering not built yet)"; return false; }
+    pr.c_in = width;
+    Id prev = gin.id;
+    auto fed_by_prev = [&](const SchedNode& sn, uint32_t w) {
+        if (sn.in.size() != w) return false;
+        for (uint32_t p = 0; p < w; ++p) if (sn.in[p].should_clear || sn.in[p].producer != prev || sn.in[p].producer_port != p) return false;
+        return true;
+    };
+    for (size_t i = 1; i + 1 < n; ++i) {
+        const SchedNode& sn = s.nodes[i];
+        NodeRec* nr = g.node(sn.id);
+        if (!fed_by_prev(sn, width)) { *why = "voice graph is not a linear port-to-port chain (generic per-node lowering not built yet)"; return false; }
+        if (pr.n_ops >= (uint32_t)kMaxChainOps) { *why = "chain longer than 16 nodes"; return false; }
+        ChainOp op{}; op.sm0 = op.sm1 = -1;
+        switch (nr->params->kind) {
+            case FW_NODE_VOLUME: op.kind = OP_GAIN; op.sm0 = sm_of_node[i]; break;
+            case FW_NODE_PAN: op.kind = OP_PAN; op.sm0 = sm_of_node[i]; op.sm1 = sm_of_node[i] + 1; break;
+            case FW_NODE_HARD_CLIP: op.kind = OP_CLIP; op.f0 = nr->params->threshold_gain; break;
+            case FW_NODE_MONO_TO_STEREO: op.kind = OP_M2S; break;
+            case FW_NODE_STEREO_TO_MONO: op.kind = OP_S2M; break;
+            case FW_NODE_SUM:
+                if (sn.in.size() == sn.out.size()) continue;  // 1-port sum == copy (sum.rs:58-65): no data op
+                *why = "SumNode with more than one port inside a voice chain (generic per-node lowering not built yet)"; return false;
+            default: *why = std::string("node kind '") + node_debug_name(nr->params->kind) + "' has no device lowering yet"; return false;
+        }
+        if (sn.out.size() < 1 || sn.out.size() > 2) { *why = "the fused chain supports 1 or 2 channels"; return false; }
+        if (nr->params->kind != FW_NODE_SUM) pr.ops[pr.n_ops++] = op;
+        width = (uint32_t)sn.out.size();
+        prev = sn.id;
+    }
+    if (!fed_by_prev(gout, width)) { *why = "graph_out is not fed port-to-port by the end of the chain"; return false; }
+    pr.c_out = width;
+    plan->prog = pr; plan->n_sm = n_sm; plan->c_in = pr.c_in; plan->c_out = pr.c_out;
+
+    // ---- device allocations (main thread) ----
+    const uint32_t V = c->cfg.num_voices, F = c->max_block_frames;
+    plan->num_voices = V; plan->block_frames = F; plan->bus = c->cfg.master_bus != 0;
+    plan->d_tables = dev_alloc<CtlTables>(1, false);
+    plan->d_flags = dev_alloc<uint64_t>(V);
+    Records& r = plan->rec;
+    r.n_smoothers = n_sm;
+    r.kt_max = n_sm ? (8192u + F - 1) / F + 3u : 2u;  // longest ramp: ln(4/1e-6)*480 < 8192 samples, then settle/stall
+    r.modes = dev_alloc<uint32_t>((size_t)r.kt_max * V);
+    r.vals = dev_alloc<float>((size_t)r.kt_max * (n_sm ? n_sm : 1) * V);
+    r.curves = dev_alloc<float>((size_t)r.kt_max * n_sm * V * F, false);
+    r.steady_k = dev_alloc<uint32_t>(V);
+    r.gout_mask = dev_alloc<uint64_t>(V);
+    r.error = dev_alloc<uint32_t>(1);
+    plan->d_bus_mask = dev_alloc<uint64_t>(1);
+    if (!plan->d_tables || !plan->d_flags || !r.modes || !r.vals || !r.curves || !r.steady_k || !r.gout_mask || !r.error || !plan->d_bus_mask) { *why = g_dev_err; return false; }
+    if (!FW_CUDA(cudaMemcpy(plan->d_tables, &tb, sizeof(tb), cudaMemcpyHostToDevice))) { *why = g_dev_err; return false; }
+    return true;
+}
+
+static std::shared_ptr<NodeParams> params_from_desc(const fw_node_desc* d, uint32_t V) {
+    auto p = std::make_shared<NodeParams>();
+    p->kind = d->kind; p->num_voices = V;
+    switch (d->kind) {
+        case FW_NODE_DUMMY: case FW_NODE_SUM: case FW_NODE_MONO_TO_STEREO: case FW_NODE_STEREO_TO_MONO: break;
+        case FW_NODE_VOLUME: {  // volume.rs:16-24
+            float pct = std::fmax(d->f0, 0.0f), n = std::fmax(pct, 0.0f) * (1.0f / 100.0f);
+            p->percent.assign(V, pct); p->raw_gain.assign(V, n * n);
+            break;
+        }
+        case FW_NODE_HARD_CLIP:  // hard_clip.rs:8-12, util.rs:21-27
+            p->threshold_gain = d->f0 <= -100.0f ? 0.0f : std::pow(10.0f, 0.05f * d->f0);
+            break;
+        case FW_NODE_PAN: {
+            double pp = std::fmin(std::fmax((double)d->f0, -1.0), 1.0), th = (pp + 1.0) * (M_PI / 4.0);
+            p->pan.assign(V, d->f0); p->gain_l.assign(V, (float)std::cos(th)); p->gain_r.assign(V, (float)std::sin(th));
+            break;
+        }
+        case FW_NODE_BIQUAD:
+            p->num_stages = d->u0 > 8 ? 8 : d->u0;
+            p->coeffs.assign((size_t)V * p->num_stages * 5, 0.0f);
+            for (size_t i = 0; i < (size_t)V * p->num_stages; ++i) p->coeffs[i * 5] = 1.0f;
+            break;
+        case FW_NODE_DELAY: p->delay = d->u0; break;
+        case FW_NODE_CONV_REVERB:
+            if (!d->data || d->data_len < (uint64_t)d->u0 * d->u1) return nullptr;
+            p->ir_len = d->u0; p->ir_channels = d->u1; p->ir.assign(d->data, d->data + (size_t)d->u0 * d->u1);
+            break;
+        default: return nullptr;
+    }
+    return p;
+}
+
+static void ctx_drain(fw_ctx* c, bool* dropped, void** cx) {  // context.rs:213-234
+    if (!c->active) return;
+    ProcToCtx m;
+    while (c->ch->to_ctx.pop(&m)) {
+        if (m.kind == 0) { delete m.plan; }  // on_schedule_returned: removed processors are released here, on the main thread
+        else { delete m.plan; *dropped = true; *cx = m.user_cx; }
+    }
+}
+static void ctx_graph_deactivate(fw_ctx* c) {  // graph.rs:671-689
+    c->node_states.clear();
+    c->graph->nodes_removed_since_compile.clear();
+    c->graph->mark_dirty();
+    c->graph->nodes_to_activate.clear();
+    c->graph->each_node([&](Id id, NodeRec& r) { r.activated = false; c->graph->nodes_to_activate.push_back(id); });
+}
+
+extern "C" {
+
+void fw_graph_config_default(fw_graph_config* c) { *c = fw_graph_config{0, 2, 64, 256, 1, 0, 0, 0}; }
+
+fw_ctx* fw_ctx_new(const fw_graph_config* cfg) {
+    if (!cfg || cfg->num_voices == 0 || cfg->num_graph_inputs > 64 || cfg->num_graph_outputs > 64) { g_dev_err = "bad graph config"; return nullptr; }
+    auto* c = new fw_ctx();
+    c->cfg = *cfg;
+    c->graph = std::make_unique<Graph>(cfg->num_graph_inputs, cfg->num_graph_outputs, cfg->num_voices);
+    return c;
+}
+void fw_ctx_free(fw_ctx* c) {
+    if (!c) return;
+    if (c->active) { bool d = false; void* cx = nullptr; ctx_drain(c, &d, &cx); }
+    c->node_states.clear();
+    delete c;
+}
+const char* fw_ctx_last_error(fw_ctx* c) { return c ? c->last_error.c_str() : "null context"; }
+fw_node_id fw_graph_in_node(fw_ctx* c) { return c->graph->graph_in().pack(); }
+fw_node_id fw_graph_out_node(fw_ctx* c) { return c->graph->graph_out().pack(); }
+
+fw_node_id fw_graph_add_node(fw_ctx* c, uint32_t ni, uint32_t no, const fw_node_desc* d) {
+    if (!c || !d || ni > 64 || no > 64) return FW_ID_DANGLING;
+    auto p = params_from_desc(d, c->cfg.num_voices);
+    if (!p) { c->last_error = "bad node description"; return FW_ID_DANGLING; }
+    return c->graph->add_node(ni, no, std::move(p)).pack();
+}
+static void write_ids(const std::vector<Id>& v, uint64_t* out, uint32_t cap, uint32_t* n) {
+    if (n) *n = (uint32_t)v.size();
+    for (size_t i = 0; i < v.size() && i < cap && out; ++i) out[i] = v[i].pack();
+}
+int fw_graph_remove_node(fw_ctx* c, fw_node_id node, fw_edge_id* removed, uint32_t cap, uint32_t* n_removed) {
+    std::vector<Id> rm;
+    if (!c->graph->remove_node(Id::unpack(node), &rm)) { if (n_removed) *n_removed = 0; return -1; }
+    write_ids(rm, removed, cap, n_removed);
+    return 0;
+}
+int fw_graph_set_num_inputs(fw_ctx* c, fw_node_id node, uint32_t n, fw_edge_id* removed, uint32_t cap, uint32_t* n_removed) {
+    std::vector<Id> rm;
+    if (n > 64 || !c->graph->set_num_inputs(Id::unpack(node), n, &rm)) { if (n_removed) *n_removed = 0; return -1; }
+    write_ids(rm, removed, cap, n_removed);
+    return 0;
+}
+int fw_graph_set_num_outputs(fw_ctx* c, fw_node_id node, uint32_t n, fw_edge_id* removed, uint32_t cap, uint32_t* n_removed) {
+    std::vector<Id> rm;
+    if (n > 64 || !c->graph->set_num_outputs(Id::unpack(node), n, &rm)) { if (n_removed) *n_removed = 0; return -1; }
+    write_ids(rm, removed, cap, n_removed);
+    return 0;
+}
+int fw_graph_connect(fw_ctx* c, fw_node_id src, uint32_t sp, fw_node_id dst, uint32_t dp, int check, fw_edge_id* out_edge, fw_node_id* err_node, uint32_t* err_port) {
+    Id e;
+    int rc = c->graph->connect(Id::unpack(src), sp, Id::unpack(dst), dp, check != 0, &e);
+    if (rc == FW_EDGE_OK) { if (out_edge) *out_edge = e.pack(); return rc; }
+    if (err_node) {
+        switch (rc) {
+            case FW_EDGE_SRC_NODE_NOT_FOUND: case FW_EDGE_OUT_PORT_OUT_OF_RANGE: *err_node = src; break;
+            case FW_EDGE_DST_NODE_NOT_FOUND: case FW_EDGE_IN_PORT_OUT_OF_RANGE: case FW_EDGE_INPUT_PORT_ALREADY_CONNECTED: *err_node = dst; break;
+            default: *err_node = FW_ID_DANGLING;
+        }
+    }
+    if (err_port) *err_port = rc == FW_EDGE_OUT_PORT_OUT_OF_RANGE ? sp : dp;
+    return rc;
+}
+int fw_graph_disconnect(fw_ctx* c, fw_node_id s, uint32_t sp, fw_node_id d, uint32_t dp) { return c->graph->disconnect(Id::unpack(s), sp, Id::unpack(d), dp); }
+int fw_graph_disconnect_by_edge_id(fw_ctx* c, fw_edge_id e) { return c->graph->disconnect_edge(Id::unpack(e)); }
+int fw_graph_edge(fw_ctx* c, fw_edge_id e, fw_edge_info* out) {
+    const EdgeRec* r = c->graph->edge(Id::unpack(e));
+    if (!r) return 0;
+    if (out) *out = fw_edge_info{r->id.pack(), r->src.pack(), r->dst.pack(), r->src_port, r->dst_port};
+    return 1;
+}
+int fw_graph_node_info(fw_ctx* c, fw_node_id node, fw_node_info* out) {
+    NodeRec* r = c->graph->node(Id::unpack(node));
+    if (!r) return 0;
+    if (out) {
+        std::memset(out, 0, sizeof(*out));
+        out->num_inputs = r->num_inputs; out->num_outputs = r->num_outputs; out->kind = r->params->kind;
+        node_supported_ports(r->params->kind, &out->num_min_supported_inputs, &out->num_max_supported_inputs, &out->num_min_supported_outputs, &out->num_max_supported_outputs);
+        const char* name = r->id == c->graph->graph_in() ? "graph_in" : r->id == c->graph->graph_out() ? "graph_out" : node_debug_name(r->params->kind);
+        std::strncpy(out->debug_name, name, sizeof(out->debug_name) - 1);
+    }
+    return 1;
+}
+uint32_t fw_graph_num_nodes(fw_ctx* c) { return c->graph->num_nodes(); }
+uint32_t fw_graph_num_edges(fw_ctx* c) { return c->graph->num_edges(); }
+uint32_t fw_graph_nodes(fw_ctx* c, fw_node_id* out, uint32_t cap) { uint32_t n = 0; c->graph->each_node([&](Id id, NodeRec&) { if (out && n < cap) out[n] = id.pack(); ++n; }); return n; }
+uint32_t fw_graph_edges(fw_ctx* c, fw_edge_id* out, uint32_t cap) { uint32_t n = 0; c->graph->each_edge([&](Id id, EdgeRec&) { if (out && n < cap) out[n] = id.pack(); ++n; }); return n; }
+int fw_graph_cycle_detected(fw_ctx* c) { return c->graph->cycle_detected(); }
+void fw_graph_reset(fw_ctx* c) { c->graph->reset(); }
+int fw_graph_needs_compile(fw_ctx* c) { return c->graph->needs_compile(); }
+
+int fw_graph_compile_internal(fw_ctx* c, uint32_t mbf) {
+    c->dbg_valid = false;
+    if (mbf == 0) return FW_COMPILE_NODE_ACTIVATION_FAILED;
+    CompileError e = c->graph->compile_schedule(mbf, &c->dbg_schedule);
+    c->dbg_valid = e.code == FW_COMPILE_OK;
+    return e.code;
+}
+uint32_t fw_schedule_len(fw_ctx* c) { return c->dbg_valid ? (uint32_t)c->dbg_schedule.nodes.size() : 0; }
+uint32_t fw_schedule_num_buffers(fw_ctx* c) { return c->dbg_valid ? c->dbg_schedule.num_buffers : 0; }
+int fw_schedule_node(fw_ctx* c, uint32_t i, fw_scheduled_node* out) {
+    if (!c->dbg_valid || i >= c->dbg_schedule.nodes.size() || !out) return 0;
+    const SchedNode& sn = c->dbg_schedule.nodes[i];
+    std::memset(out, 0, sizeof(*out));
+    out->id = sn.id.pack(); out->num_inputs = (uint32_t)sn.in.size(); out->num_outputs = (uint32_t)sn.out.size();
+    for (size_t k = 0; k < sn.in.size() && k < 64; ++k) { out->in_buffer[k] = sn.in[k].buffer; out->in_should_clear[k] = sn.in[k].should_clear; }
+    for (size_t k = 0; k < sn.out.size() && k < 64; ++k) out->out_buffer[k] = sn.out[k].buffer;
+    return 1;
+}
+
+}  // extern "C"
+// ---- parameters -----------------------------------------------------------------------------
+static NodeParams* params_of(fw_ctx* c, fw_node_id node, uint32_t kind) {
+    NodeRec* r = c->graph->node(Id::unpack(node));
+    return (r && r->params->kind == kind) ? r->params.get() : nullptr;
+}
+template <class F> static int for_voices(NodeParams* p, uint32_t voice, F&& f) {
+    if (!p) return -1;
+    if (voice == FW_ALL_VOICES) { for (uint32_t v = 0; v < p->num_voices; ++v) f(v); }
+    else if (voice < p->num_voices) f(voice);
+    else return -1;
+    p->version += 1;
+    return 0;
+}
+extern "C" {
+int fw_volume_set_percent_volume(fw_ctx* c, fw_node_id node, uint32_t voice, float pct) {  // volume.rs:28-34, range.rs:32-35
+    NodeParams* p = params_of(c, node, FW_NODE_VOLUME);
+    return for_voices(p, voice, [&](uint32_t v) { float n = std::fmax(pct, 0.0f) * (1.0f / 100.0f); p->raw_gain[v] = n * n; p->percent[v] = std::fmax(pct, 0.0f); });
+}
+int fw_volume_set_percent_volumes(fw_ctx* c, fw_node_id node, const float* pct, uint32_t n) {
+    NodeParams* p = params_of(c, node, FW_NODE_VOLUME);
+    if (!p || n != p->num_voices) return -1;
+    for (uint32_t v = 0; v < n; ++v) { float x = std::fmax(pct[v], 0.0f) * (1.0f / 100.0f); p->raw_gain[v] = x * x; p->percent[v] = std::fmax(pct[v], 0.0f); }
+    p->version += 1;
+    return 0;
+}
+static void pan_gains(float pan, float* gl, float* gr) {
+    double pp = std::fmin(std::fmax((double)pan, -1.0), 1.0), th = (pp + 1.0) * (M_PI / 4.0);
+    *gl = (float)std::cos(th); *gr = (float)std::sin(th);
+}
+int fw_pan_set_pan(fw_ctx* c, fw_node_id node, uint32_t voice, float pan) {
+    NodeParams* p = params_of(c, node, FW_NODE_PAN);
+    return for_voices(p, voice, [&](uint32_t v) { p->pan[v] = pan; pan_gains(pan, &p->gain_l[v], &p->gain_r[v]); });
+}
+int fw_pan_set_pans(fw_ctx* c, fw_node_id node, const float* pan, uint32_t n) {
+    NodeParams* p = params_of(c, node, FW_NODE_PAN);
+    if (!p || n != p->num_voices) return -1;
+    for (uint32_t v = 0; v < n; ++v) { p->pan[v] = pan[v]; pan_gains(pan[v], &p->gain_l[v], &p->gain_r[v]); }
+    p->version += 1;
+    return 0;
+}
+int fw_pan_set_gains(fw_ctx* c, fw_node_id node, uint32_t voice, float gl, float gr) {
+    NodeParams* p = params_of(c, node, FW_NODE_PAN);
+    return for_voices(p, voice, [&](uint32_t v) { p->gain_l[v] = gl; p->gain_r[v] = gr; });
+}
+int fw_biquad_set_coeffs(fw_ctx* c, fw_node_id node, uint32_t voice, uint32_t stage, const float* k) {
+    NodeParams* p = params_of(c, node, FW_NODE_BIQUAD);
+    if (!p || stage >= p->num_stages) return -1;
+    return for_voices(p, voice, [&](uint32_t v) { std::memcpy(&p->coeffs[((size_t)v * p->num_stages + stage) * 5], k, 5 * sizeof(float)); });
+}
+int fw_biquad_set_all_coeffs(fw_ctx* c, fw_node_id node, const float* k, uint32_t nv, uint32_t ns) {
+    NodeParams* p = params_of(c, node, FW_NODE_BIQUAD);
+    if (!p || nv != p->num_voices || ns != p->num_stages) return -1;
+    std::memcpy(p->coeffs.data(), k, (size_t)nv * ns * 5 * sizeof(float));
+    p->version += 1;
+    return 0;
+}
+void fw_biquad_design_rbj(uint32_t type, double fc, double q, double gain_db, double sr, float* out) {  // RBJ cookbook, f64 -> f32
+    const double w0 = 2.0 * M_PI * fc / sr, cw = std::cos(w0), sw = std::sin(w0), alpha = sw / (2.0 * q), A = std::pow(10.0, gain_db / 40.0);
+    double b0, b1, b2, a0, a1, a2;
+    switch (type) {
+        case 0: b0 = (1 - cw) / 2; b1 = 1 - cw; b2 = (1 - cw) / 2; a0 = 1 + alpha; a1 = -2 * cw; a2 = 1 - alpha; break;
+        case 1: b0 = (1 + cw) / 2; b1 = -(1 + cw); b2 = (1 + cw) / 2; a0 = 1 + alpha; a1 = -2 * cw; a2 = 1 - alpha; break;
+        case 2: b0 = alpha; b1 = 0; b2 = -alpha; a0 = 1 + alpha; a1 = -2 * cw; a2 = 1 - alpha; break;
+        case 3: b0 = 1; b1 = -2 * cw; b2 = 1; a0 = 1 + alpha; a1 = -2 * cw; a2 = 1 - alpha; break;
+        case 4: b0 = 1 + alpha * A; b1 = -2 * cw; b2 = 1 - alpha * A; a0 = 1 + alpha / A; a1 = -2 * cw; a2 = 1 - alpha / A; break;
+        case 5: { const double s = 2 * std::sqrt(A) * alpha;
+            b0 = A * ((A + 1) - (A - 1) * cw + s); b1 = 2 * A * ((A - 1) - (A + 1) * cw); b2 = A * ((A + 1) - (A - 1) * cw - s);
+            a0 = (A + 1) + (A - 1) * cw + s; a1 = -2 * ((A - 1) + (A + 1) * cw); a2 = (A + 1) + (A - 1) * cw - s; break; }
+        default: { const double s = 2 * std::sqrt(A) * alpha;
+            b0 = A * ((A + 1) + (A - 1) * cw + s); b1 = -2 * A * ((A - 1) + (A + 1) * cw); b2 = A * ((A + 1) + (A - 1) * cw - s);
+            a0 = (A + 1) - (A - 1) * cw + s; a1 = 2 * ((A - 1) - (A + 1) * cw); a2 = (A + 1) - (A - 1) * cw - s; break; }
+    }
+    out[0] = (float)(b0 / a0); out[1] = (float)(b1 / a0); out[2] = (float)(b2 / a0); out[3] = (float)(a1 / a0); out[4] = (float)(a2 / a0);
+}
+
+// ---- lifecycle --------------------------------------------------------------------------------
+int fw_ctx_activate(fw_ctx* c, uint32_t sr, uint32_t n_in, uint32_t n_out, uint32_t mbf, void* user_cx, fw_processor** out) {
+    if (!c || !out || sr == 0 || mbf == 0 || n_in > 64 || n_out > 64) { if (c) c->last_error = "bad activate arguments"; return -1; }
+    if (c->active) return 1;  // context.rs:57-59
+    int ndev = 0;
+    if (!FW_CUDA(cudaGetDeviceCount(&ndev)) || c->cfg.device < 0 || c->cfg.device >= ndev) {
+        c->last_error = "no CUDA device " + std::to_string(c->cfg.device) + " (firewheel-b200 has no CPU fallback): " + g_dev_err;
+        return -1;
+    }
+    if (!FW_CUDA(cudaSetDevice(c->cfg.device))) { c->last_error = g_dev_err; return -1; }
+    auto* p = new fw_processor();
+    p->device = c->cfg.device;
+    bool ok = FW_CUDA(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    for (int i = 0; ok && i < 4; ++i) ok = FW_CUDA(cudaEventCreate(&p->ev[i]));
+    ok = ok && FW_CUDA(cudaMallocHost(&p->h_masks, sizeof(uint64_t) * (c->cfg.num_voices + 1))) && FW_CUDA(cudaMallocHost(&p->h_err, sizeof(uint32_t)));
+    if (!ok) { c->last_error = g_dev_err; delete p; return -1; }
+    c->ch = std::make_shared<Channels>();
+    c->active = true; c->sample_rate = sr; c->max_block_frames = mbf; c->n_in = n_in; c->n_out = n_out;
+    p->ch = c->ch; p->user_cx = user_cx; p->num_voices = c->cfg.num_voices; p->max_block_frames = mbf; p->n_in = n_in; p->n_out = n_out;
+    p->bus = c->cfg.master_bus != 0;
+    // SmootherConfig::default + ParamSmoother::new (smoother.rs:18-25,99-100); host libm, once
+    p->sm_b = std::exp(-1.0f / ((10.0f / 1000.0f) * (float)sr)); p->sm_a = 1.0f - p->sm_b; p->sm_eps = 0.00001f;
+    *out = p;
+    return 0;
+}
+int fw_ctx_is_activated(fw_ctx* c) { return c->active; }
+
+int fw_ctx_update(fw_ctx* c, fw_update_status* out) {  // context.rs:93-148
+    fw_update_status st{}; st.kind = FW_UPDATE_INACTIVE; st.error_node = FW_ID_DANGLING;
+    auto done = [&] { if (out) *out = st; return 0; };
+    if (!c->active) return done();
+    bool dropped = false; void* cx = nullptr;
+    ctx_drain(c, &dropped, &cx);
+    if (dropped) { ctx_graph_deactivate(c); c->active = false; c->ch.reset(); st.kind = FW_UPDATE_DEACTIVATED; st.returned_user_cx = cx; return done(); }
+    st.kind = FW_UPDATE_ACTIVE;
+    if (!c->graph->needs_compile()) return done();
+    cudaSetDevice(c->cfg.device);
+    auto plan = std::make_unique<Plan>();
+    plan->device = c->cfg.device;
+    CompileError e = c->graph->compile_schedule(c->max_block_frames, &plan->sched);
+    if (e.code != FW_COMPILE_OK) { st.graph_error = e.code; st.error_node = e.node.pack(); st.error_port = e.port; return done(); }
+    // activate new nodes in queue order (graph.rs:593-612); a failure rolls back this round's activations
+    std::vector<uint64_t> created;
+    for (Id id : c->graph->nodes_to_activate) {
+        NodeRec* r = c->graph->node(id);
+        if (!r) continue;
+        std::string msg = node_check_activation(*r->params, r->num_inputs, r->num_outputs);
+        std::shared_ptr<NodeDeviceState> ds;
+        if (msg.empty()) {
+            ds = std::make_shared<NodeDeviceState>();
+            ds->device = c->cfg.device; ds->kind = r->params->kind; ds->V = c->cfg.num_voices; ds->params = r->params;
+            if (!ds->create()) msg = "device allocation failed: " + g_dev_err;
+        }
+        if (!msg.empty()) {
+            for (uint64_t k : created) c->node_states.erase(k);
+            st.graph_error = FW_COMPILE_NODE_ACTIVATION_FAILED; st.error_node = id.pack(); c->last_error = msg;
+            return done();
+        }
+        c->node_states[id.pack()] = ds; created.push_back(id.pack());
+    }
+    std::string why;
+    if (!lower(c, plan->sched, plan.get(), &why)) {
+        for (uint64_t k : created) c->node_states.erase(k);
+        st.graph_error = FW_COMPILE_UNSUPPORTED_ON_DEVICE; c->last_error = why;
+        return done();
+    }
+    plan->nodes_to_remove = c->graph->nodes_removed_since_compile;
+    for (Id id : plan->nodes_to_remove) c->node_states.erase(id.pack());  // the outgoing plan still holds them until it is returned
+    c->graph->clear_dirty(); c->graph->nodes_to_activate.clear(); c->graph->nodes_removed_since_compile.clear();
+    cudaDeviceSynchronize();  // tables and initial state are resident before the stream side can see the plan
+    CtxToProc m; m.kind = 0; m.plan = plan.get();
+    if (c->ch->to_proc.push(m)) plan.release();
+    else std::fprintf(stderr, "firewheel-b200: failed to send new schedule: message channel is full\n");  // context.rs:128-136
+    return done();
+}
+
+void* fw_ctx_deactivate(fw_ctx* c, int stream_is_running) {  // context.rs:162-211
+    if (!c->active) return nullptr;
+    using clock = std::chrono::steady_clock;
+    const auto start = clock::now();
+    bool dropped = false; void* cx = nullptr;
+    if (stream_is_running) {
+        CtxToProc m; m.kind = 1;
+        while (!c->ch->to_proc.push(m)) {
+            std::this_thread::sleep_for(std::chrono::milliseconds(2));
+            if (clock::now() - start > std::chrono::seconds(3)) { dropped = true; break; }
+        }
+    }
+    while (!dropped) {
+        ctx_drain(c, &dropped, &cx);
+        if (!dropped) {
+            std::this_thread::sleep_for(std::chrono::milliseconds(2));
+            if (clock::now() - start > std::chrono::seconds(3)) dropped = true;
+        }
+    }
+    ctx_graph_deactivate(c);
+    c->active = false; c->ch.reset();
+    return cx;
+}
+
+// ---- stream side --------------------------------------------------------------------------------
+static void proc_poll(fw_processor* p) {  // processor.rs:167-206
+    CtxToProc m;
+    while (p->ch->to_proc.pop(&m)) {
+        if (m.kind == 1) { p->running = false; continue; }
+        if (p->plan) {
+            ProcToCtx r; r.kind = 0; r.plan = p->plan;
+            cudaStreamSynchronize(p->stream);  // the old plan's buffers may still be in flight
+            p->ch->to_ctx.push(r);
+            p->pending_zero_first = true;  // Q11: the swap happens after this block's inputs were written to the old pool
+        }
+        p->plan = m.plan;
+    }
+}
+static bool ensure(float** buf, size_t* cap, size_t n) {
+    if (n <= *cap) return true;
+    cudaFree(*buf); *buf = nullptr; *cap = 0;
+    void* q = nullptr;
+    if (!FW_CUDA(cudaMalloc(&q, n * sizeof(float)))) return false;
+    *buf = static_cast<float*>(q); *cap = n;
+    return true;
+}
+
+// Enqueue one call (frames = K blocks) on device buffers. d_in [V][c_in][T]; d_out [V][c_out][T] or bus [c_out][T].
+static int proc_enqueue(fw_processor* p, const float* d_in, float* d_out, uint32_t n_in, uint32_t n_out, uint64_t frames64) {
+    if (frames64 > 0x7fffffffull) return FW_PROC_BAD_ARGS;
+    const uint32_t T = (uint32_t)frames64, V = p->num_voices;
+    const size_t out_elems = (size_t)(p->bus ? 1 : V) * n_out * T;
+    cudaSetDevice(p->device);
+    auto silence = [&] { if (out_elems) { launch_fill(d_out, out_elems, 0.0f, p->stream); p->launches++; } };
+    if (!p->running) { silence(); return FW_PROC_DROP_PROCESSOR; }                   // processor.rs:71-74
+    if (!p->plan) { proc_poll(p); p->pending_zero_first = false; if (!p->running) { silence(); return FW_PROC_DROP_PROCESSOR; } }  // :76-84
+    if (!p->plan || T == 0) { silence(); return FW_PROC_OK; }                        // :86-89
+    proc_poll(p);                                                                    // process_block :214
+    if (!p->running) { silence(); return FW_PROC_DROP_PROCESSOR; }
+    Plan& pl = *p->plan;
+    if (n_in != pl.c_in || n_out != pl.c_out) { g_dev_err = "channel counts do not match the compiled graph"; return FW_PROC_BAD_ARGS; }
+    for (auto& st : pl.states) if (!st->snapshot_params(p->stream)) return FW_PROC_DEVICE_ERROR;
+
+    ControlArgs ca{};
+    ca.tables = pl.d_tables; ca.rec = pl.rec; ca.flags = pl.d_flags; ca.num_voices = V; ca.frames = T; ca.block_frames = pl.block_frames;
+    ca.a = p->sm_a; ca.b = p->sm_b; ca.eps = p->sm_eps;
+    { ProfScope ps(p, 0); if (!FW_CUDA(launch_control(ca, p->stream))) return FW_PROC_DEVICE_ERROR; }
+    p->launches++;
+
+    ChainArgs xa{};
+    xa.in = d_in; xa.num_voices = V; xa.frames = T; xa.block_frames = pl.block_frames; xa.zero_first_block = p->pending_zero_first ? 1u : 0u;
+    xa.rec = pl.rec; xa.prog = pl.prog;
+    p->pending_zero_first = false;
+    if (!pl.bus) {
+        xa.out = d_out;
+        { ProfScope ps(p, 1); if (!FW_CUDA(launch_chain(xa, false, p->stream))) return FW_PROC_DEVICE_ERROR; }
+        p->launches++;
+    } else {
+        uint32_t n = chain_voice_groups(V);
+        if (n == 1) { xa.out = d_out; }
+        else {
+            const size_t need = (size_t)n * n_out * T;
+            if (!ensure(&p->d_part[0], &p->cap_part[0], need) || !ensure(&p->d_part[1], &p->cap_part[1], (size_t)((n + 15) / 16) * n_out * T)) return FW_PROC_DEVICE_ERROR;
+            xa.out = p->d_part[0];
+        }
+        { ProfScope ps(p, 1); if (!FW_CUDA(launch_chain(xa, true, p->stream))) return FW_PROC_DEVICE_ERROR; }
+        p->launches++;
+        ProfScope ps2(p, 2);
+        int cur = 0;
+        while (n > 1) {
+            const uint32_t n_next = (n + 15) / 16;
+            float* dst = n_next == 1 ? d_out : p->d_part[cur ^ 1];
+            if (!FW_CUDA(launch_combine(p->d_part[cur], dst, n, n_out, T, p->stream))) return FW_PROC_DEVICE_ERROR;
+            p->launches++;
+            n = n_next; cur ^= 1;
+        }
+    }
+    return FW_PROC_OK;
+}
+
+static uint64_t bus_mask_from(const uint64_t* masks, uint32_t V, uint32_t n_out) {
+    if (V == 1) return masks[0];
+    const uint64_t all = n_out >= 64 ? ~0ull : ((1ull << n_out) - 1ull);
+    for (uint32_t v = 0; v < V; ++v) if ((masks[v] & all) != all) return 0;
+    return all;
+}
+
+int fw_processor_process_planar_device(fw_processor* p, const float* d_in, float* d_out, uint32_t n_in, uint32_t n_out, uint64_t frames, double, uint32_t) {
+    if (!p) return FW_PROC_BAD_ARGS;
+    return proc_enqueue(p, d_in, d_out, n_in, n_out, frames);
+}
+
+int fw_processor_process_planar(fw_processor* p, const float* in, float* out, uint32_t n_in, uint32_t n_out, uint64_t frames, double, uint32_t, uint64_t* out_mask) {
+    if (!p) return FW_PROC_BAD_ARGS;
+    cudaSetDevice(p->device);
+    const uint32_t V = p->num_voices;
+    const size_t in_elems = (size_t)V * n_in * frames, out_elems = (size_t)(p->bus ? 1 : V) * n_out * frames;
+    if (out_mask) *out_mask = 0;
+    if (!ensure(&p->d_in, &p->cap_in, in_elems) || !ensure(&p->d_out, &p->cap_out, out_elems)) return FW_PROC_DEVICE_ERROR;
+    if (in_elems && !FW_CUDA(cudaMemcpyAsync(p->d_in, in, in_elems * 4, cudaMemcpyHostToDevice, p->stream))) return FW_PROC_DEVICE_ERROR;
+    int rc = proc_enqueue(p, p->d_in, p->d_out, n_in, n_out, frames);
+    if (rc < 0) return rc;
+    if (out_elems && !FW_CUDA(cudaMemcpyAsync(out, p->d_out, out_elems * 4, cudaMemcpyDeviceToHost, p->stream))) return FW_PROC_DEVICE_ERROR;
+    const bool ran = rc == FW_PROC_OK && p->plan && frames > 0;
+    if (ran) {
+        cudaMemcpyAsync(p->h_masks, p->plan->rec.gout_mask, sizeof(uint64_t) * V, cudaMemcpyDeviceToHost, p->stream);
+        cudaMemcpyAsync(p->h_err, p->plan->rec.error, sizeof(uint32_t), cudaMemcpyDeviceToHost, p->stream);
+    }
+    if (!FW_CUDA(cudaStreamSynchronize(p->stream))) return FW_PROC_DEVICE_ERROR;
+    if (ran) {
+        if (*p->h_err) { g_dev_err = "control pass overflowed its transient-block budget"; return FW_PROC_DEVICE_ERROR; }
+        if (out_mask) *out_mask = p->bus ? bus_mask_from(p->h_masks, V, n_out) : p->h_masks[0];
+    }
+    return rc;
+}
+
+int fw_processor_process_interleaved(fw_processor* p, const float* in, float* out, uint32_t n_in, uint32_t n_out, uint64_t frames, double, uint32_t) {
+    if (!p) return FW_PROC_BAD_ARGS;
+    cudaSetDevice(p->device);
+    const uint32_t V = p->num_voices, Vo = p->bus ? 1 : V;
+    const size_t in_elems = (size_t)V * n_in * frames, out_elems = (size_t)Vo * n_out * frames;
+    const size_t inter_elems = in_elems > out_elems ? in_elems : out_elems;
+    if (!ensure(&p->d_in, &p->cap_in, in_elems) || !ensure(&p->d_out, &p->cap_out, out_elems) || !ensure(&p->d_inter, &p->cap_inter, inter_elems)) return FW_PROC_DEVICE_ERROR;
+    if (in_elems) {
+        if (!FW_CUDA(cudaMemcpyAsync(p->d_inter, in, in_elems * 4, cudaMemcpyHostToDevice, p->stream))) return FW_PROC_DEVICE_ERROR;
+        if (!FW_CUDA(launch_deinterleave(p->d_inter, p->d_in, V, n_in, (uint32_t)frames, p->stream))) return FW_PROC_DEVICE_ERROR;
+        p->launches++;
+    }
+    int rc = proc_enqueue(p, p->d_in, p->d_out, n_in, n_out, frames);
+    if (rc < 0) return rc;
+    if (out_elems) {
+        const bool ran = rc == FW_PROC_OK && p->plan && frames > 0;
+        const uint64_t* masks = nullptr;
+        if (ran) {
+            if (p->bus) { launch_bus_mask(p->plan->rec.gout_mask, V, n_out, p->plan->d_bus_mask, p->stream); p->launches++; masks = p->plan->d_bus_mask; }
+            else masks = p->plan->rec.gout_mask;
+        }
+        if (!FW_CUDA(launch_interleave(p->d_out, p->d_inter, masks, Vo, n_out, (uint32_t)frames, p->max_block_frames, p->stream))) return FW_PROC_DEVICE_ERROR;
+        p->launches++;
+        if (!FW_CUDA(cudaMemcpyAsync(out, p->d_inter, out_elems * 4, cudaMemcpyDeviceToHost, p->stream))) return FW_PROC_DEVICE_ERROR;
+    }
+    if (!FW_CUDA(cudaStreamSynchronize(p->stream))) return FW_PROC_DEVICE_ERROR;
+    return rc;
+}
+
+void fw_processor_free(fw_processor* p) {  // Drop processor.rs:251-263
+    if (!p) return;
+    cudaSetDevice(p->device);
+    cudaStreamSynchronize(p->stream);
+    ProcToCtx m; m.kind = 1; m.plan = p->plan; m.user_cx = p->user_cx;
+    if (!p->ch->to_ctx.push(m)) delete p->plan;
+    cudaFree(p->d_in); cudaFree(p->d_out); cudaFree(p->d_inter); cudaFree(p->d_part[0]); cudaFree(p->d_part[1]); cudaFree(p->d_flush);
+    cudaFreeHost(p->h_masks); cudaFreeHost(p->h_err);
+    for (auto& e : p->ev) if (e) cudaEventDestroy(e);
+    for (auto& e : p->prof_ev) if (e) cudaEventDestroy(e);
+    cudaStreamDestroy(p->stream);
+    delete p;
+}
+
+// ---- device plumbing ----------------------------------------------------------------------------
+int fw_device_count(void) { int n = 0; if (!FW_CUDA(cudaGetDeviceCount(&n))) return 0; return n; }
+const char* fw_last_device_error(void) { return g_dev_err.c_str(); }
+void* fw_dev_malloc(int device, uint64_t bytes) { void* p = nullptr; if (!FW_CUDA(cudaSetDevice(device)) || !FW_CUDA(cudaMalloc(&p, bytes))) return nullptr; return p; }
+void fw_dev_free(int device, void* p) { cudaSetDevice(device); cudaFree(p); }
+void* fw_host_alloc_pinned(uint64_t bytes) { void* p = nullptr; if (!FW_CUDA(cudaMallocHost(&p, bytes))) return nullptr; return p; }
+void fw_host_free_pinned(void* p) { cudaFreeHost(p); }
+int fw_processor_h2d(fw_processor* p, void* dst, const void* src, uint64_t bytes) { cudaSetDevice(p->device); return FW_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, p->stream)) ? 0 : -1; }
+int fw_processor_d2h(fw_processor* p, void* dst, const void* src, uint64_t bytes) { cudaSetDevice(p->device); return FW_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, p->stream)) ? 0 : -1; }
+int fw_processor_sync(fw_processor* p) {
+    cudaSetDevice(p->device);
+    if (!FW_CUDA(cudaStreamSynchronize(p->stream))) return -1;
+    if (p->plan) { uint32_t e = 0; cudaMemcpy(&e, p->plan->rec.error, 4, cudaMemcpyDeviceToHost); if (e) { g_dev_err = "control pass overflowed its transient-block budget"; return -1; } }
+    return 0;
+}
+int fw_processor_event_record(fw_processor* p, int slot) { if (slot < 0 || slot > 3) return -1; cudaSetDevice(p->device); return FW_CUDA(cudaEventRecord(p->ev[slot], p->stream)) ? 0 : -1; }
+float fw_processor_event_elapsed_ms(fw_processor* p, int a, int b) {
+    float ms = -1.0f; cudaSetDevice(p->device);
+    if (!FW_CUDA(cudaEventSynchronize(p->ev[b])) || !FW_CUDA(cudaEventElapsedTime(&ms, p->ev[a], p->ev[b]))) return -1.0f;
+    return ms;
+}
+uint64_t fw_processor_kernel_launches(fw_processor* p) { return p->launches; }
+int fw_processor_profile(fw_processor* p, int enable) {
+    cudaSetDevice(p->device);
+    if (enable && p->prof_ev.empty()) {
+        p->prof_ev.resize(2 * 4096); p->prof_class.assign(4096, 0);
+        for (auto& e : p->prof_ev) if (!FW_CUDA(cudaEventCreate(&e))) return -1;
+    }
+    p->profiling = enable != 0; p->prof_used = 0;
+    return 0;
+}
+int fw_processor_profile_read(fw_processor* p, double* ms4, uint64_t* n4) {
+    cudaSetDevice(p->device);
+    if (!FW_CUDA(cudaStreamSynchronize(p->stream))) return -1;
+    for (int i = 0; i < 4; ++i) { ms4[i] = 0.0; n4[i] = 0; }
+    for (size_t i = 0; i + 1 < p->prof_used; i += 2) {
+        float ms = 0.0f;
+        if (!FW_CUDA(cudaEventElapsedTime(&ms, p->prof_ev[i], p->prof_ev[i + 1]))) return -1;
+        const int cls = p->prof_class[i / 2] & 3;
+        ms4[cls] += ms; n4[cls] += 1;
+    }
+    p->prof_used = 0;
+    return 0;
+}
+int fw_processor_l2_flush(fw_processor* p) {
+    cudaSetDevice(p->device);
+    const size_t n = (size_t)64 << 20;  // 256 MiB of f32 > 126 MB L2
+    if (!p->d_flush) { void* q = nullptr; if (!FW_CUDA(cudaMalloc(&q, n * 4))) return -1; p->d_flush = static_cast<float*>(q); }
+    if (!FW_CUDA(launch_fill(p->d_flush, n, 1.0f, p->stream))) return -1;
+    return 0;
+}
+int fw_comm_unique_id(uint8_t*) { g_dev_err = "multi-GPU master bus not built yet"; return -1; }
+int fw_processor_comm_init(fw_processor*, int, int, const uint8_t*) { g_dev_err = "multi-GPU master bus not built yet"; return -1; }
+
+}  // extern "C"

@@ -325,6 +325,18 @@ class FirewheelProcessor:
     def kernel_launches(self):
         return self._lib.processor_kernel_launches(self._h)
 
+    def profile(self, enable):
+        return self._lib.processor_profile(self._h, int(enable))
+
+    def profile_read(self):
+        """-> (ms[4], launches[4]) for classes control / chain / combine / temporal, then resets."""
+        ms = (C.c_double * 4)()
+        n = (C.c_uint64 * 4)()
+        rc = self._lib.processor_profile_read(self._h, ms, n)
+        if rc != 0:
+            raise RuntimeError("profile_read failed")
+        return list(ms), list(n)
+
     def l2_flush(self):
         return self._lib.processor_l2_flush(self._h)
 

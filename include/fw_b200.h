@@ -240,6 +240,10 @@ FW_EXPORT int FW_FN(processor_sync)(fw_processor* p);
 FW_EXPORT int FW_FN(processor_event_record)(fw_processor* p, int slot);
 FW_EXPORT float FW_FN(processor_event_elapsed_ms)(fw_processor* p, int slot_start, int slot_stop);
 FW_EXPORT uint64_t FW_FN(processor_kernel_launches)(fw_processor* p); /* kernels launched so far */
+/* Per-kernel-class device timing with CUDA events on the launching stream.
+ * classes: 0 control, 1 fused chain (+bus), 2 bus combine, 3 temporal (biquad/delay/reverb). */
+FW_EXPORT int FW_FN(processor_profile)(fw_processor* p, int enable);
+FW_EXPORT int FW_FN(processor_profile_read)(fw_processor* p, double* ms_by_class4, uint64_t* launches_by_class4);
 FW_EXPORT int FW_FN(processor_l2_flush)(fw_processor* p);             /* writes a >L2 scratch buffer */
 
 /* ---- multi-GPU master bus (voices sharded by rank) --------------------------- */

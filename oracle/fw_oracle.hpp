@@ -744,6 +744,8 @@ class CompiledSchedule {  // schedule.rs:166-344
   public:
     std::vector<ScheduledNode> schedule; std::vector<float> buffers; std::vector<uint8_t> buffer_silence_flags;
     size_t num_buffers = 0, max_block_frames = 0;
+    // scratch for the ArrayVec<_, 64> the reference keeps on the stack (schedule.rs:223,265,296-297): no per-block allocation
+    std::vector<const float*> scratch_in_; std::vector<float*> scratch_out_;
     CompiledSchedule(std::vector<ScheduledNode> s, size_t nb, size_t mbf)
         : schedule(std::move(s)), buffers(nb * mbf, 0.0f), buffer_silence_flags(nb, 0), num_buffers(nb), max_block_frames(mbf) {}
     float* buffer_slice(size_t buffer_index) { return buffers.data() + buffer_index * max_block_frames; }  // :347-379
@@ -751,7 +753,7 @@ class CompiledSchedule {  // schedule.rs:166-344
     template <class F> void prepare_graph_inputs(size_t frames, size_t num_stream_inputs, F&& fill_inputs) {  // :213-253
         frames = std::min(frames, max_block_frames);
         ScheduledNode& gin = schedule.front();
-        std::vector<float*> inputs;
+        std::vector<float*>& inputs = scratch_out_; inputs.clear();
         size_t fill_len = std::min(num_stream_inputs, gin.output_buffers.size());
         for (size_t i = 0; i < fill_len; ++i) inputs.push_back(buffer_slice(gin.output_buffers[i].buffer_index));
         SilenceMask m = fill_inputs(inputs, frames);
@@ -765,7 +767,7 @@ class CompiledSchedule {  // schedule.rs:166-344
     template <class F> void read_graph_outputs(size_t frames, size_t num_stream_outputs, F&& read_outputs) {  // :255-287
         frames = std::min(frames, max_block_frames);
         ScheduledNode& gout = schedule.back();
-        std::vector<const float*> outputs; SilenceMask m = SilenceMask::none();
+        std::vector<const float*>& outputs = scratch_in_; outputs.clear(); SilenceMask m = SilenceMask::none();
         size_t read_len = std::min(num_stream_outputs, gout.input_buffers.size());
         for (size_t i = 0; i < read_len; ++i) {
             size_t bi = gout.input_buffers[i].buffer_index;
@@ -776,7 +778,7 @@ class CompiledSchedule {  // schedule.rs:166-344
     }
     template <class F> void process(size_t frames, F&& proc) {  // :289-343
         frames = std::min(frames, max_block_frames);
-        std::vector<const float*> inputs; std::vector<float*> outputs;
+        std::vector<const float*>& inputs = scratch_in_; std::vector<float*>& outputs = scratch_out_;
         for (ScheduledNode& sn : schedule) {
             SilenceMask in_mask = SilenceMask::none();
             inputs.clear(); outputs.clear();

@@ -309,32 +309,43 @@ void* fwo_ctx_deactivate(fw_ctx* c, int stream_is_running) {
 
 // ---- hot path --------------------------------------------------------------------------------
 namespace {
-struct BusItem { std::vector<float> buf; SilenceMask mask; };  // [n_out][bf]
-
-// Balanced tree of 2-port SumNodes over `items` (n_out channels each); returns the root.
-BusItem master_bus_tree(std::vector<BusItem> level, size_t n_out, size_t bf) {
-    SumNodeProcessor sum2(2);
-    while (level.size() > 1) {
-        std::vector<BusItem> next;
-        for (size_t i = 0; i + 1 < level.size(); i += 2) {
-            BusItem o; o.buf.assign(n_out * bf, 0.0f);
-            std::vector<const float*> in; std::vector<float*> out; SilenceMask in_mask = SilenceMask::none();
-            for (size_t port = 0; port < 2; ++port) for (size_t ch = 0; ch < n_out; ++ch) {
-                const BusItem& s = level[i + port];
-                in.push_back(s.buf.data() + ch * bf);
-                if (s.mask.is_channel_silent(ch)) in_mask.set_channel(port * n_out + ch, true);
-            }
-            for (size_t ch = 0; ch < n_out; ++ch) out.push_back(o.buf.data() + ch * bf);
-            SilenceMask om = SilenceMask::none();
-            sum2.process(bf, in, out, ProcInfo{in_mask, &om, 0.0, 0, nullptr});
-            o.mask = om;
-            next.push_back(std::move(o));
-        }
-        if (level.size() & 1) next.push_back(std::move(level.back()));
-        level = std::move(next);
+// Balanced tree of 2-port SumNodes (sum.rs:69-81) over V leaves of n_out channels x bf frames, evaluated in a
+// preallocated arena: nodes [0,V) are the voices' graph_out buffers, internal nodes are appended behind them.
+struct BusArena {
+    std::vector<float> buf; std::vector<SilenceMask> mask; size_t n_out = 0, mbf = 0;
+    std::vector<const float*> in; std::vector<float*> out; std::vector<size_t> level, next;
+    void reserve(size_t V, size_t n_out_, size_t mbf_) {
+        if (buf.size() < 2 * V * n_out_ * mbf_ || n_out != n_out_ || mbf != mbf_) { buf.assign(2 * V * n_out_ * mbf_, 0.0f); mask.assign(2 * V, SilenceMask::none()); }
+        n_out = n_out_; mbf = mbf_;
     }
-    return std::move(level[0]);
-}
+    float* node(size_t i) { return buf.data() + i * n_out * mbf; }
+    size_t reduce(size_t V, size_t bf) {  // returns the root node index
+        SumNodeProcessor sum2(2);
+        level.resize(V); for (size_t v = 0; v < V; ++v) level[v] = v;
+        size_t next_free = V;
+        while (level.size() > 1) {
+            next.clear();
+            for (size_t i = 0; i + 1 < level.size(); i += 2) {
+                const size_t o = next_free++;
+                in.clear(); out.clear(); SilenceMask in_mask = SilenceMask::none();
+                for (size_t port = 0; port < 2; ++port) for (size_t ch = 0; ch < n_out; ++ch) {
+                    const size_t s = level[i + port];
+                    in.push_back(node(s) + ch * mbf);
+                    if (mask[s].is_channel_silent(ch)) in_mask.set_channel(port * n_out + ch, true);
+                }
+                for (size_t ch = 0; ch < n_out; ++ch) out.push_back(node(o) + ch * mbf);
+                SilenceMask om = SilenceMask::none();
+                sum2.process(bf, in, out, ProcInfo{in_mask, &om, 0.0, 0, nullptr});
+                mask[o] = om;
+                next.push_back(o);
+            }
+            if (level.size() & 1) next.push_back(level.back());  // unpaired: carried up (1-port SumNode copy, sum.rs:58-65)
+            level.swap(next);
+        }
+        return level[0];
+    }
+};
+thread_local BusArena g_arena;
 }  // namespace
 
 int fwo_processor_process_planar(fw_processor* p, const float* input, float* output, uint32_t n_in, uint32_t n_out, uint64_t frames,
@@ -343,37 +354,36 @@ int fwo_processor_process_planar(fw_processor* p, const float* input, float* out
     size_t V = p->procs.size(); bool bus = p->ctx->cfg.master_bus != 0;
     size_t mbf = p->max_block_frames; int rc = FW_PROC_OK;
     if (out_mask) *out_mask = 0;
-    std::vector<const float*> in_ptrs(n_in); std::vector<float*> out_ptrs(n_out);
-    std::vector<BusItem> items;
+    const float* in_ptrs[64]; float* out_ptrs[64];
+    BusArena& ar = g_arena;
+    if (bus) ar.reserve(V, n_out, mbf);
     size_t done = 0;
     // frames == 0 still polls messages like processor.rs:76-89
     do {
         size_t bf = std::min<size_t>(frames - done, mbf);
-        if (bus) { items.assign(V, BusItem{}); }
         for (size_t v = 0; v < V; ++v) {
             for (uint32_t c = 0; c < n_in; ++c) in_ptrs[c] = input + ((size_t)v * n_in + c) * frames + done;
             uint64_t m = 0; ProcessorStatus st;
             if (bus) {
-                items[v].buf.assign((size_t)n_out * bf, 0.0f);
-                for (uint32_t c = 0; c < n_out; ++c) out_ptrs[c] = items[v].buf.data() + (size_t)c * bf;
-                st = p->procs[v]->process_planar(in_ptrs.data(), out_ptrs.data(), n_in, n_out, bf, t, status, &m);
-                items[v].mask = SilenceMask{m};
+                for (uint32_t c = 0; c < n_out; ++c) out_ptrs[c] = ar.node(v) + (size_t)c * mbf;
+                st = p->procs[v]->process_planar(in_ptrs, out_ptrs, n_in, n_out, bf, t, status, &m);
+                ar.mask[v] = SilenceMask{m};
             } else {
                 for (uint32_t c = 0; c < n_out; ++c) out_ptrs[c] = output + ((size_t)v * n_out + c) * frames + done;
-                st = p->procs[v]->process_planar(in_ptrs.data(), out_ptrs.data(), n_in, n_out, bf, t, status, &m);
+                st = p->procs[v]->process_planar(in_ptrs, out_ptrs, n_in, n_out, bf, t, status, &m);
                 if (out_mask && v == 0) *out_mask = m;
             }
             if (st == ProcessorStatus::DropProcessor) rc = FW_PROC_DROP_PROCESSOR;
-        }
-        if (bus && bf > 0) {
-            BusItem root = master_bus_tree(std::move(items), n_out, bf);
-            for (uint32_t c = 0; c < n_out; ++c) std::memcpy(output + (size_t)c * frames + done, root.buf.data() + (size_t)c * bf, bf * sizeof(float));
-            if (out_mask) *out_mask = root.mask.bits;
         }
         if (rc != FW_PROC_OK) {  // processor.rs:71-74,150-155: zero-fill what was not produced
             size_t rows = bus ? n_out : V * n_out;
             for (size_t r = 0; r < rows; ++r) for (size_t i = done; i < frames; ++i) output[r * frames + i] = 0.0f;
             break;
+        }
+        if (bus && bf > 0) {
+            size_t root = ar.reduce(V, bf);
+            for (uint32_t c = 0; c < n_out; ++c) std::memcpy(output + (size_t)c * frames + done, ar.node(root) + (size_t)c * mbf, bf * sizeof(float));
+            if (out_mask) *out_mask = ar.mask[root].bits;
         }
         done += bf;
     } while (done < frames);
@@ -428,6 +438,8 @@ int fwo_processor_event_record(fw_processor*, int) { return -1; }
 float fwo_processor_event_elapsed_ms(fw_processor*, int, int) { return -1.0f; }
 uint64_t fwo_processor_kernel_launches(fw_processor*) { return 0; }
 int fwo_processor_l2_flush(fw_processor*) { return -1; }
+int fwo_processor_profile(fw_processor*, int) { return -1; }
+int fwo_processor_profile_read(fw_processor*, double*, uint64_t*) { return -1; }
 int fwo_comm_unique_id(uint8_t*) { return -1; }
 int fwo_processor_comm_init(fw_processor*, int, int, const uint8_t*) { return -1; }
 

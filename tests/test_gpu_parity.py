@@ -1,0 +1,166 @@
+"""GPU parity: the CUDA product against the CPU oracle on the same seeded inputs, through the C ABI.
+Bar: bit-exact (f32 bit patterns, including the sign of zero) and identical silence masks."""
+import numpy as np
+import pytest
+
+from conftest import synth
+from firewheel_b200 import HardClipNode, MonoToStereoNode, PanNode, StereoToMonoNode, SumNode, VolumeNode
+from helpers import assert_bit_exact, chain, f32, run_planar
+
+pytestmark = pytest.mark.gpu
+
+
+def both(gpu, oracle, build, calls, n_out, master_bus=False):
+    """build(lib) -> (cx, proc, ids); calls: list of (x, pre) where pre(cx, ids) may retune parameters."""
+    outs = []
+    for lib in (gpu, oracle):
+        cx, proc, ids = build(lib)
+        res = []
+        for x, pre in calls:
+            if pre:
+                pre(cx, ids)
+            res.append(run_planar(proc, x, n_out, master_bus))
+        outs.append(res)
+        proc.free()
+        cx.update()
+        cx.free()
+    for i, ((yg, mg), (yo, mo)) in enumerate(zip(*outs)):
+        assert_bit_exact(yg, yo, f"call {i}")
+        assert mg == mo, f"call {i}: silence mask {mg:#x} != {mo:#x}"
+    return outs[0]
+
+
+def vol_pan(V, master_bus, max_block, pct, pan):
+    def setup(cx, ids):
+        cx.graph.set_percent_volume(ids[0], pct)
+        cx.graph.set_pan(ids[1], pan)
+    return lambda lib: chain(lib, 2, [(lambda: VolumeNode(100.0), 2, 2), (lambda: PanNode(0.0), 2, 2)], voices=V,
+                             master_bus=master_bus, max_block=max_block, setup=setup)
+
+
+@pytest.mark.parametrize("V,bus", [(1, False), (3, False), (70, False), (1, True), (2, True), (7, True), (64, True), (65, True), (130, True), (1024, True)])
+def test_gain_pan_chain_constant(gpu, oracle, V, bus):
+    rng = np.random.default_rng(V)
+    pct = rng.uniform(25, 100, V).astype(f32)
+    pan = rng.uniform(-1, 1, V).astype(f32)
+    T = 256 * 3
+    x = synth((V, 2, T), 100 + V)
+    both(gpu, oracle, vol_pan(V, bus, 256, pct, pan), [(x, None), (x[:, :, :256].copy(), None)], 2, bus)
+
+
+@pytest.mark.parametrize("F,T", [(256, 256 * 2 + 4), (256, 777), (100, 1000), (64, 640), (128, 131), (4, 64), (255, 1020)])
+def test_block_shapes_and_ragged_tails(gpu, oracle, F, T):
+    V = 5
+    pct = np.linspace(30, 150, V).astype(f32)
+    pan = np.linspace(-1, 1, V).astype(f32)
+    x = synth((V, 2, T), F * 7 + T)
+    both(gpu, oracle, vol_pan(V, True, F, pct, pan), [(x, None)], 2, True)
+    both(gpu, oracle, vol_pan(V, False, F, pct, pan), [(x, None)], 2, False)
+
+
+def test_ramps_settle_stall_and_mute(gpu, oracle):
+    V, F = 9, 256
+    pct0 = np.array([100, 100, 100, 50, 0, 100, 200, 100, 30], f32)
+    pct1 = np.array([0, 50, 100, 100, 100, 25, 100, 0.05, 30], f32)   # to-mute, down, unchanged, up (stalls), from-mute, ...
+    pan0 = np.zeros(V, f32)
+    pan1 = np.linspace(-1, 1, V).astype(f32)
+    x = -np.abs(synth((V, 2, F * 30), 7)) - f32(0.01)
+
+    def retune(cx, ids):
+        cx.graph.set_percent_volume(ids[0], pct1)
+        cx.graph.set_pan(ids[1], pan1)
+
+    def back(cx, ids):
+        cx.graph.set_percent_volume(ids[0], pct0)
+
+    calls = [(x[:, :, :F * 2].copy(), None), (x, retune), (x[:, :, :F * 4].copy(), None), (x, back), (x[:, :, :F].copy(), None)]
+    both(gpu, oracle, vol_pan(V, False, F, pct0, pan0), calls, 2, False)
+    both(gpu, oracle, vol_pan(V, True, F, pct0, pan0), calls, 2, True)
+
+
+def test_all_muted_bus_is_silent(gpu, oracle):
+    V = 4
+    (y, m), = both(gpu, oracle, vol_pan(V, True, 256, np.zeros(V, f32), np.zeros(V, f32)), [(synth((V, 2, 512), 3), None)], 2, True)
+    assert m == 0b11 and not np.any(np.signbit(y))
+
+
+def test_clip_mono_stereo_chains(gpu, oracle):
+    x1 = synth((6, 1, 900), 11)
+    both(gpu, oracle, lambda lib: chain(lib, 1, [(MonoToStereoNode, 1, 2), (lambda: VolumeNode(70.0), 2, 2), (lambda: HardClipNode(-9.0), 2, 2)], voices=6), [(x1, None)], 2)
+    x2 = synth((6, 2, 900), 12)
+    both(gpu, oracle, lambda lib: chain(lib, 2, [(lambda: HardClipNode(-3.0), 2, 2), (StereoToMonoNode, 2, 1), (lambda: VolumeNode(120.0), 1, 1)], voices=6, master_bus=True), [(x2, None)], 1, True)
+    both(gpu, oracle, lambda lib: chain(lib, 2, [(SumNode, 2, 2)], voices=3), [(x2[:3].copy(), None)], 2)  # 1-port sum == copy
+    both(gpu, oracle, lambda lib: chain(lib, 2, [], voices=3), [(x2[:3].copy(), None)], 2)  # graph_in -> graph_out
+
+
+def test_interleaved_entry_point(gpu, oracle):
+    V, T = 3, 700
+    x = synth((V, T, 2), 21)
+    res = []
+    for lib in (gpu, oracle):
+        for bus in (False, True):
+            cx, proc, ids = vol_pan(V, bus, 256, np.array([50, 0, 150], f32), np.array([-0.5, 0, 0.5], f32))(lib)
+            out = np.full((T, 2) if bus else (V, T, 2), np.nan, f32)
+            assert proc.process_interleaved(x, out, 2, 2, T) == 0
+            res.append(out)
+            proc.free(); cx.update(); cx.free()
+    assert_bit_exact(res[0], res[2], "interleaved per-voice")
+    assert_bit_exact(res[1], res[3], "interleaved bus")
+
+
+def test_schedule_swap_first_block_reads_zero_inputs(gpu, oracle):  # Q11
+    V, F = 3, 128
+    x = synth((V, 2, 4 * F), 31)
+    outs = []
+    for lib in (gpu, oracle):
+        cx, proc, (vol,) = chain(lib, 2, [(lambda: VolumeNode(100.0), 2, 2)], voices=V, max_block=F)
+        g = cx.graph
+        y0 = run_planar(proc, x, 2)
+        clip = g.add_node(2, 2, HardClipNode(-12.0))
+        for c in range(2):
+            assert g.disconnect(vol, c, g.graph_out_node(), c)
+            g.connect(vol, c, clip, c, False)
+            g.connect(clip, c, g.graph_out_node(), c, False)
+        assert cx.update().graph_error is None
+        y1 = run_planar(proc, x, 2)
+        y2 = run_planar(proc, x, 2)
+        g.remove_node(clip)
+        for c in range(2):
+            g.connect(vol, c, g.graph_out_node(), c, False)
+        assert cx.update().graph_error is None
+        y3 = run_planar(proc, x, 2)
+        outs.append((y0, y1, y2, y3))
+        proc.free(); cx.update(); cx.free()
+    for (a, ma), (b, mb) in zip(*outs):
+        assert_bit_exact(a, b)
+        assert ma == mb
+    assert np.all(outs[0][1][0][:, :, :F] == 0) and np.any(outs[0][1][0][:, :, F:] != 0)
+
+
+def test_config2_full_size_blocks(gpu, oracle):
+    """BASELINE config[1]: 1024 stereo voices, gain -> pan -> sum, 256-frame blocks (8 blocks here)."""
+    V, F, K = 1024, 256, 8
+    rng = np.random.default_rng(2)
+    pct = (25 + 75 * rng.random(V)).astype(f32)
+    pan = rng.uniform(-1, 1, V).astype(f32)
+    x = synth((V, 2, F * K), 99)
+    (y, m), = both(gpu, oracle, vol_pan(V, True, F, pct, pan), [(x, None)], 2, True)
+    assert m == 0 and np.all(np.isfinite(y))
+
+
+def test_unsupported_topology_fails_loudly(gpu):
+    from firewheel_b200 import AudioGraphConfig, FirewheelGraphCtx
+    cx = FirewheelGraphCtx(gpu, AudioGraphConfig(num_graph_inputs=4, num_graph_outputs=2))
+    g = cx.graph
+    s = g.add_node(4, 2, SumNode())
+    for i in range(4):
+        g.connect(g.graph_in_node(), i, s, i, False)
+    for c in range(2):
+        g.connect(s, c, g.graph_out_node(), c, False)
+    proc = cx.activate(48000, 4, 2, 256)
+    st = cx.update()
+    assert st.graph_error is not None and st.graph_error.kind == "UnsupportedOnDevice"
+    out = np.full((1, 2, 256), np.nan, f32)
+    rc, _ = proc.process_planar(synth((1, 4, 256), 1), out, 4, 2, 256)
+    assert rc == 0 and np.all(out == 0)  # no schedule => silence (processor.rs:86-89), never a CPU fallback
+    proc.free()
