@@ -6,6 +6,8 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
+#include <utility>
 
 #include "../../include/fw_b200.h"
 #include "kernels.cuh"
@@ -23,6 +25,11 @@ namespace fw {
 //   HardClip masks      hard_clip.rs:60-93
 // Only state transitions and gain curves are computed here; no sample data is touched.
 // =============================================================================================
+// Programmatic dependent launch (sm_90+): a kernel launched with the PDL attribute may start while its
+// predecessor in the stream is still running; it must not touch the predecessor's results before pdl_wait().
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 struct SmLocal { float input, last; uint32_t status; };
 
 __device__ __forceinline__ uint64_t all_silent_mask(uint32_t n) { return n >= 64 ? ~0ull : ((1ull << n) - 1ull); }
@@ -64,6 +71,8 @@ __device__ __forceinline__ uint32_t sm_set_and_process(SmLocal& s, float val, ui
 }
 
 __global__ void __launch_bounds__(128) control_kernel(ControlArgs a) {
+    pdl_launch_dependents();  // the data kernel may start loading samples now; it waits for us before reading records
+    pdl_wait();               // the previous call's data kernels still read the record buffers we are about to rewrite
     const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t V = a.num_voices;
     if (v >= V) return;
@@ -75,7 +84,9 @@ __global__ void __launch_bounds__(128) control_kernel(ControlArgs a) {
     for (uint32_t s = 0; s < NS; ++s) { sm[s].input = tb.sm_input[s][v]; sm[s].last = tb.sm_last[s][v]; sm[s].status = tb.sm_status[s][v]; }
     uint64_t flags = a.flags[v];
     uint64_t gout_mask = 0;
-    uint32_t steady = 0xffffffffu, k = 0;
+    uint32_t steady = 0xffffffffu, k = 0, last_modes = 0;
+    float last_vals[kMaxSmoothers];
+    for (uint32_t s = 0; s < NS; ++s) last_vals[s] = 0.0f;
 
     for (; k < n_blocks; ++k) {
         if (k >= a.rec.kt_max) { *a.rec.error = 1; break; }
@@ -109,7 +120,7 @@ __global__ void __launch_bounds__(128) control_kernel(ControlArgs a) {
                             out_mask = in_mask;  // volume.rs:110
                         }
                         modes |= m << (2 * nd.sm0);
-                        a.rec.vals[(size_t)(k * NS + nd.sm0) * V + v] = cv;
+                        a.rec.vals[(size_t)(k * NS + nd.sm0) * V + v] = cv; last_vals[nd.sm0] = cv;
                     }
                     break;
                 }
@@ -124,11 +135,11 @@ __global__ void __launch_bounds__(128) control_kernel(ControlArgs a) {
                         uint32_t m = sm_set_and_process(sm[nd.sm0], gl, frames, a.a, a.b, a.eps,
                                                         a.rec.curves + ((size_t)(k * NS + nd.sm0) * V + v) * F, &cv, &smoothing, changed);
                         modes |= m << (2 * nd.sm0);
-                        a.rec.vals[(size_t)(k * NS + nd.sm0) * V + v] = cv;
+                        a.rec.vals[(size_t)(k * NS + nd.sm0) * V + v] = cv; last_vals[nd.sm0] = cv;
                         m = sm_set_and_process(sm[nd.sm1], gr, frames, a.a, a.b, a.eps,
                                                a.rec.curves + ((size_t)(k * NS + nd.sm1) * V + v) * F, &cv, &smoothing, changed);
                         modes |= m << (2 * nd.sm1);
-                        a.rec.vals[(size_t)(k * NS + nd.sm1) * V + v] = cv;
+                        a.rec.vals[(size_t)(k * NS + nd.sm1) * V + v] = cv; last_vals[nd.sm1] = cv;
                         out_mask = in_mask;
                     }
                     break;
@@ -156,10 +167,13 @@ __global__ void __launch_bounds__(128) control_kernel(ControlArgs a) {
             }
         }
         a.rec.modes[(size_t)k * V + v] = modes;
+        last_modes = modes;
         if (!changed) { steady = k; break; }  // nothing moved: every later block replays this record
     }
     if (steady == 0xffffffffu) steady = (k == 0 ? 0 : min(k, n_blocks) - 1);
     a.rec.steady_k[v] = steady;
+    a.rec.st_modes[v] = last_modes;  // the record of block `steady`, flattened
+    for (uint32_t s = 0; s < NS; ++s) a.rec.st_vals[(size_t)s * V + v] = last_vals[s];
     a.rec.gout_mask[v] = gout_mask;
     for (uint32_t s = 0; s < NS; ++s) { tb.sm_input[s][v] = sm[s].input; tb.sm_last[s][v] = sm[s].last; tb.sm_status[s][v] = sm[s].status; }
     a.flags[v] = flags;
@@ -258,112 +272,199 @@ __device__ __forceinline__ void apply_chain(const ChainArgs& a, const RecView& r
     }
 }
 
-constexpr int kVPW = 8, kWarps = 8, kVPC = kVPW * kWarps;
+constexpr int kVPC = 64;  // voices per CTA (one partial bus per CTA in the bus variant)
 
-template <int VEC, int CIN, bool BUS>
-__global__ void __launch_bounds__(kWarps * 32) chain_kernel(ChainArgs a) {
+template <int VEC, int CIN, bool BUS, int kVPW, int kWarps, int kMinBlocks>
+__global__ void __launch_bounds__(kWarps * 32, kMinBlocks) chain_kernel(ChainArgs a) {
+    static_assert(kVPW * kWarps == kVPC, "a CTA owns 64 voices");
+    pdl_launch_dependents();
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t T = a.frames, V = a.num_voices, F = a.block_frames, NS = a.rec.n_smoothers;
     const uint32_t c_out = a.prog.c_out;
-    const uint32_t t = (blockIdx.x * 32u + lane) * VEC;
+    constexpr uint32_t kTile = 32u * VEC;
+    const uint32_t t = blockIdx.x * kTile + lane * VEC;
     const bool t_ok = t < T;
     const uint32_t vcta = blockIdx.y * kVPC, v0 = vcta + warp * kVPW;
     const uint32_t k = t_ok ? t / F : 0;
     const uint32_t t_in_block = t - k * F;
-    const bool zero_in = a.zero_first_block && k == 0;  // Q11: first block after a schedule swap reads a fresh (zero) pool
+    // FULL: every voice and every frame of this CTA's tile exists and nothing is zeroed: no bounds checks at all
+    const bool full = (vcta + kVPC <= V) && ((blockIdx.x + 1u) * kTile <= T) && !a.zero_first_block;
 
-    // ---- issue every load of this thread up front -------------------------------------------
+    // ---- issue every sample load of this thread up front (independent of the control kernel) --------
     float x[kVPW][2][VEC];
+    if (full) {
+        const float* p = a.in + (size_t)v0 * CIN * T + t;
 #pragma unroll
-    for (int j = 0; j < kVPW; ++j) {
-        const uint32_t v = v0 + j;
+        for (int j = 0; j < kVPW; ++j) {
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
+            for (int c = 0; c < CIN; ++c) { VecT<VEC>::load(p, x[j][c]); p += T; }
+            if (CIN == 1) {
 #pragma unroll
-            for (int i = 0; i < VEC; ++i) x[j][c][i] = 0.0f;
-            if (c < CIN && t_ok && v < V && !zero_in) VecT<VEC>::load(a.in + ((size_t)v * CIN + c) * T + t, x[j][c]);
+                for (int i = 0; i < VEC; ++i) x[j][1][i] = 0.0f;
+            }
+        }
+    } else {
+        const bool zero_in = a.zero_first_block && k == 0;  // Q11: first block after a schedule swap reads a fresh (zero) pool
+#pragma unroll
+        for (int j = 0; j < kVPW; ++j) {
+            const uint32_t v = v0 + j;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) x[j][c][i] = 0.0f;
+                if (c < CIN && t_ok && v < V && !zero_in) VecT<VEC>::load(a.in + ((size_t)v * CIN + c) * T + t, x[j][c]);
+            }
         }
     }
 
-    // ---- records: staged once per CTA when the whole tile lies in one block ------------------
-    __shared__ uint32_t s_kk[kVPC], s_modes[kVPC];
-    __shared__ float s_vals[kMaxSmoothers][kVPC];
-    const bool cta_uniform = (F % (32u * VEC)) == 0u;  // tile never straddles a block boundary
+    pdl_wait();  // records written by the control kernel of this call are visible from here on
+
+    // ---- per-warp record staging: one independent load per voice, no CTA-wide barrier ---------------
+    // Steady voices (block >= steady_k[v], all smoothers REC_CONST) take the fast path; a warp that owns any
+    // transient / CLEAR / CURVE voice, or a tile that straddles block boundaries, takes the generic path.
+    __shared__ float s_wv[kWarps][kMaxSmoothers][kVPW];
+    const bool cta_uniform = (F % kTile) == 0u;
+    bool warp_fast = false;
     if (cta_uniform) {
-        const uint32_t kb = (blockIdx.x * 32u * VEC) / F;
-        if (threadIdx.x < kVPC) {
-            const uint32_t v = vcta + threadIdx.x;
-            uint32_t kk = 0, md = 0;
-            if (v < V) { kk = min(kb, a.rec.steady_k[v]); md = a.rec.modes[(size_t)kk * V + v]; }
-            s_kk[threadIdx.x] = kk; s_modes[threadIdx.x] = md;
+        const uint32_t kb = (blockIdx.x * kTile) / F;
+        uint32_t special = 0;
+        if (lane < kVPW && v0 + lane < V) special = (kb < a.rec.steady_k[v0 + lane]) || (a.rec.st_modes[v0 + lane] != 0u);
+        for (uint32_t i = lane; i < NS * kVPW; i += 32u) {
+            const uint32_t s = i / kVPW, j = i % kVPW;
+            s_wv[warp][s][j] = (v0 + j < V) ? a.rec.st_vals[(size_t)s * V + v0 + j] : 0.0f;
         }
-        __syncthreads();
-        for (uint32_t i = threadIdx.x; i < NS * kVPC; i += blockDim.x) {
-            const uint32_t s = i / kVPC, vl = i % kVPC, v = vcta + vl;
-            s_vals[s][vl] = v < V ? a.rec.vals[(size_t)(s_kk[vl] * NS + s) * V + v] : 0.0f;
-        }
-        __syncthreads();
+        warp_fast = !__any_sync(0xffffffffu, special);
+        __syncwarp();
     }
 
+    if (warp_fast) {
+        // ops outermost (one uniform decode per op), the warp's voices innermost; multipliers are smem broadcasts
+#pragma unroll 1
+        for (uint32_t o = 0; o < a.prog.n_ops; ++o) {
+            const ChainOp op = a.prog.ops[o];
+            if (op.kind == OP_GAIN) {  // volume.rs:123-126
 #pragma unroll
-    for (int j = 0; j < kVPW; ++j) {
-        const uint32_t v = v0 + j;
-        if (v < V && t_ok) {
-            RecView r;
-            if (cta_uniform) {
-                const uint32_t vl = warp * kVPW + j;
-                r.kk = s_kk[vl]; r.modes = s_modes[vl]; r.vals = &s_vals[0][vl]; r.stride = kVPC;
-            } else {
+                for (int j = 0; j < kVPW; ++j) {
+                    const float g = s_wv[warp][op.sm0][j];
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) { x[j][0][i] = __fmul_rn(x[j][0][i], g); x[j][1][i] = __fmul_rn(x[j][1][i], g); }
+                }
+            } else if (op.kind == OP_PAN) {
+#pragma unroll
+                for (int j = 0; j < kVPW; ++j) {
+                    const float gl = s_wv[warp][op.sm0][j], gr = s_wv[warp][op.sm1][j];
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) { x[j][0][i] = __fmul_rn(x[j][0][i], gl); x[j][1][i] = __fmul_rn(x[j][1][i], gr); }
+                }
+            } else if (op.kind == OP_CLIP) {  // hard_clip.rs:70-76
+                const float th = op.f0;
+#pragma unroll
+                for (int j = 0; j < kVPW; ++j)
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) { x[j][0][i] = fmaxf(fminf(x[j][0][i], th), -th); x[j][1][i] = fmaxf(fminf(x[j][1][i], th), -th); }
+            } else if (op.kind == OP_M2S) {  // mono_to_stereo.rs:46-48
+#pragma unroll
+                for (int j = 0; j < kVPW; ++j)
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) x[j][1][i] = x[j][0][i];
+            } else if (op.kind == OP_S2M) {  // stereo_to_mono.rs:49-54
+#pragma unroll
+                for (int j = 0; j < kVPW; ++j)
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) x[j][0][i] = __fmul_rn(__fadd_rn(x[j][0][i], x[j][1][i]), 0.5f);
+            }
+        }
+    } else {
+        // rare: park the tile in local memory and run the generic per-voice interpreter over it
+        float xs[kVPW][2][VEC];
+#pragma unroll
+        for (int j = 0; j < kVPW; ++j)
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) xs[j][c][i] = x[j][c][i];
+#pragma unroll 1
+        for (int j = 0; j < kVPW; ++j) {  // xs is indexed dynamically on purpose: it lives in local memory
+            const uint32_t v = v0 + j;
+            if (v < V && t_ok) {
+                RecView r;
                 r.kk = min(k, a.rec.steady_k[v]); r.modes = a.rec.modes[(size_t)r.kk * V + v];
                 r.vals = a.rec.vals + (size_t)r.kk * NS * V + v; r.stride = V;
-            }
-            apply_chain<VEC>(a, r, v, t_in_block, x[j]);
-            if (!BUS) {
-#pragma unroll
-                for (int c = 0; c < 2; ++c) if (c < c_out) VecT<VEC>::store(a.out + ((size_t)v * c_out + c) * T + t, x[j][c]);
+                apply_chain<VEC>(a, r, v, t_in_block, xs[j]);
             }
         }
+#pragma unroll
+        for (int j = 0; j < kVPW; ++j)
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) x[j][c][i] = xs[j][c][i];
     }
 
-    if (BUS) {
-        // Balanced tree over voices: (2i, 2i+1) per level; a right operand that lies beyond the last voice
-        // is skipped (the 1-port SumNode copy, sum.rs:58-65). Levels 1-3 in registers per thread.
-#define FW_COMB(dst, rhs, rhs_first_voice)                                                    \
-    if ((rhs_first_voice) < V) {                                                              \
-        _Pragma("unroll") for (int c = 0; c < 2; ++c) _Pragma("unroll") for (int i = 0; i < VEC; ++i) \
-            dst[c][i] = __fadd_rn(dst[c][i], rhs[c][i]);                                      \
-    }
-        FW_COMB(x[0], x[1], v0 + 1) FW_COMB(x[2], x[3], v0 + 3) FW_COMB(x[4], x[5], v0 + 5) FW_COMB(x[6], x[7], v0 + 7)
-        FW_COMB(x[0], x[2], v0 + 2) FW_COMB(x[4], x[6], v0 + 6)
-        FW_COMB(x[0], x[4], v0 + 4)
-        // Levels 4-6 across the CTA's 8 warps through shared memory (each lane owns its own frames).
+    if (!BUS) {
+        if (full) {
+            float* q = a.out + (size_t)v0 * c_out * T + t;
+#pragma unroll
+            for (int j = 0; j < kVPW; ++j)
+#pragma unroll
+                for (int c = 0; c < 2; ++c) if (c < c_out) { VecT<VEC>::store(q, x[j][c]); q += T; }
+        } else {
+#pragma unroll
+            for (int j = 0; j < kVPW; ++j) {
+                const uint32_t v = v0 + j;
+                if (v < V && t_ok) {
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) if (c < c_out) VecT<VEC>::store(a.out + ((size_t)v * c_out + c) * T + t, x[j][c]);
+                }
+            }
+        }
+    } else {
+        // Balanced tree over voices: (2i, 2i+1) per level; a right operand that lies beyond the last voice is
+        // skipped (the 1-port SumNode copy, sum.rs:58-65). log2(kVPW) levels in registers per thread.
+#pragma unroll
+        for (int step = 1; step < kVPW; step <<= 1)
+#pragma unroll
+            for (int j = 0; j + step < kVPW; j += 2 * step)
+                if (full || v0 + j + step < V) {
+#pragma unroll
+                    for (int c = 0; c < 2; ++c)
+#pragma unroll
+                        for (int i = 0; i < VEC; ++i) x[j][c][i] = __fadd_rn(x[j][c][i], x[j + step][c][i]);
+                }
+        // Remaining log2(kWarps) levels through shared memory; each lane owns its own frames. Producer warps
+        // arrive on a named barrier and leave; warp c (< c_out) waits, finishes channel c and stores it.
         __shared__ float s_red[kWarps][2][32 * VEC];
 #pragma unroll
         for (int c = 0; c < 2; ++c)
 #pragma unroll
             for (int i = 0; i < VEC; ++i) s_red[warp][c][lane * VEC + i] = x[0][c][i];
-        __syncthreads();
-        if (warp == 0 && t_ok) {
-            float p[kWarps][2][VEC];
+        if (warp >= c_out) { asm volatile("bar.arrive 1, %0;" ::"n"(kWarps * 32) : "memory"); return; }
+        asm volatile("bar.sync 1, %0;" ::"n"(kWarps * 32) : "memory");
+        if (t_ok) {
+            const uint32_t c = warp;
+            float p[kWarps][VEC];
 #pragma unroll
             for (int w = 0; w < kWarps; ++w)
 #pragma unroll
-                for (int c = 0; c < 2; ++c)
+                for (int i = 0; i < VEC; ++i) p[w][i] = s_red[w][c][lane * VEC + i];
 #pragma unroll
-                    for (int i = 0; i < VEC; ++i) p[w][c][i] = s_red[w][c][lane * VEC + i];
-            FW_COMB(p[0], p[1], vcta + 1 * kVPW) FW_COMB(p[2], p[3], vcta + 3 * kVPW) FW_COMB(p[4], p[5], vcta + 5 * kVPW) FW_COMB(p[6], p[7], vcta + 7 * kVPW)
-            FW_COMB(p[0], p[2], vcta + 2 * kVPW) FW_COMB(p[4], p[6], vcta + 6 * kVPW)
-            FW_COMB(p[0], p[4], vcta + 4 * kVPW)
+            for (int step = 1; step < kWarps; step <<= 1)
 #pragma unroll
-            for (int c = 0; c < 2; ++c) if (c < c_out) VecT<VEC>::store(a.out + ((size_t)blockIdx.y * c_out + c) * T + t, p[0][c]);
+                for (int w = 0; w + step < kWarps; w += 2 * step)
+                    if (full || vcta + (w + step) * kVPW < V) {
+#pragma unroll
+                        for (int i = 0; i < VEC; ++i) p[w][i] = __fadd_rn(p[w][i], p[w + step][i]);
+                    }
+            VecT<VEC>::store(a.out + ((size_t)blockIdx.y * c_out + c) * T + t, p[0]);
         }
-#undef FW_COMB
     }
 }
 
 // K-combine: radix-16 levels of the same balanced tree over partial buses [n_in][rows][T] -> [ceil(n_in/16)][rows][T].
 template <int VEC>
 __global__ void __launch_bounds__(128) combine_kernel(const float* __restrict__ pin, float* __restrict__ pout, uint32_t n_in, uint32_t rows, uint32_t T) {
+    pdl_launch_dependents();
+    pdl_wait();  // the partial buses come from the preceding kernel
     const uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
     if (t >= T) return;
     const uint32_t row = blockIdx.y, g = blockIdx.z, p0 = g * 16u;
@@ -432,18 +533,45 @@ __global__ void bus_mask_kernel(const uint64_t* __restrict__ gout_mask, uint32_t
 static inline unsigned grid_for(size_t n) { size_t b = (n + 255) / 256; return (unsigned)(b < 148u * 16u ? b : 148u * 16u); }
 #define FW_LAUNCH_CHECK() do { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return e_; } while (0)
 
-cudaError_t launch_control(const ControlArgs& a, cudaStream_t st) {
-    const uint32_t threads = 128, blocks = (a.num_voices + threads - 1) / threads;
-    control_kernel<<<blocks, threads, 0, st>>>(a);
-    return cudaGetLastError();
+// All three per-call kernels are launched with programmatic stream serialization: each begins with
+// griddepcontrol.launch_dependents and reads its predecessor's results only after griddepcontrol.wait.
+template <class... KArgs, class... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
+cudaError_t launch_control(const ControlArgs& a, cudaStream_t st) {
+    const uint32_t threads = 128, blocks = (a.num_voices + threads - 1) / threads;
+    return launch_pdl(control_kernel, dim3(blocks), dim3(threads), st, a);
+}
+
+static int chain_variant() {  // A/B knob for tuning runs; the default is what ships
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("FW_CHAIN_VARIANT"); v = e ? atoi(e) : 0; }
+    return v;
+}
+template <int VEC, int CIN, int VPW, int WARPS, int MINB>
+static cudaError_t launch_chain_v(const ChainArgs& a, bool bus, cudaStream_t st) {
+    dim3 grid((a.frames + 32 * VEC - 1) / (32 * VEC), (a.num_voices + kVPC - 1) / kVPC);
+    if (bus) return launch_pdl(chain_kernel<VEC, CIN, true, VPW, WARPS, MINB>, grid, dim3(WARPS * 32), st, a);
+    return launch_pdl(chain_kernel<VEC, CIN, false, VPW, WARPS, MINB>, grid, dim3(WARPS * 32), st, a);
+}
 template <int VEC, int CIN>
 static cudaError_t launch_chain_t(const ChainArgs& a, bool bus, cudaStream_t st) {
-    dim3 grid((a.frames + 32 * VEC - 1) / (32 * VEC), (a.num_voices + kVPC - 1) / kVPC);
-    if (bus) chain_kernel<VEC, CIN, true><<<grid, kWarps * 32, 0, st>>>(a);
-    else chain_kernel<VEC, CIN, false><<<grid, kWarps * 32, 0, st>>>(a);
-    return cudaGetLastError();
+    if (VEC == 4) {
+        switch (chain_variant()) {
+            case 1: return launch_chain_v<VEC, CIN, 4, 16, 2>(a, bus, st);
+            case 2: return launch_chain_v<VEC, CIN, 8, 8, 3>(a, bus, st);
+            default: break;
+        }
+    }
+    return launch_chain_v<VEC, CIN, 8, 8, 2>(a, bus, st);
 }
 cudaError_t launch_chain(const ChainArgs& a, bool bus, cudaStream_t st) {
     const bool vec4 = (a.frames % 4 == 0) && (a.block_frames % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.in) | reinterpret_cast<uintptr_t>(a.out)) % 16 == 0);
@@ -455,9 +583,8 @@ uint32_t chain_voice_groups(uint32_t num_voices) { return (num_voices + kVPC - 1
 cudaError_t launch_combine(const float* pin, float* pout, uint32_t n_in, uint32_t rows, uint32_t T, cudaStream_t st) {
     const bool vec4 = (T % 4 == 0) && ((reinterpret_cast<uintptr_t>(pin) | reinterpret_cast<uintptr_t>(pout)) % 16 == 0);
     const uint32_t n_out = (n_in + 15) / 16;
-    if (vec4) { dim3 grid((T / 4 + 127) / 128, rows, n_out); combine_kernel<4><<<grid, 128, 0, st>>>(pin, pout, n_in, rows, T); }
-    else { dim3 grid((T + 127) / 128, rows, n_out); combine_kernel<1><<<grid, 128, 0, st>>>(pin, pout, n_in, rows, T); }
-    return cudaGetLastError();
+    if (vec4) return launch_pdl(combine_kernel<4>, dim3((T / 4 + 127) / 128, rows, n_out), dim3(128), st, pin, pout, n_in, rows, T);
+    return launch_pdl(combine_kernel<1>, dim3((T + 127) / 128, rows, n_out), dim3(128), st, pin, pout, n_in, rows, T);
 }
 cudaError_t launch_deinterleave(const float* inter, float* planar, uint32_t V, uint32_t C, uint32_t T, cudaStream_t st) {
     const size_t n = (size_t)V * C * T; if (n == 0) return cudaSuccess;

@@ -45,8 +45,10 @@ struct CtlTables {
 //   vals[k][s][v]        constant value of smoother s in block k (REC_CONST)
 //   curves[k][s][v][F]   gain curve (REC_CURVE)
 //   steady_k[v]          blocks >= steady_k[v] reuse the record of block steady_k[v]
+//   st_modes[v], st_vals[s][v]  that steady record, flattened so the data kernels reach it with one independent load
 struct Records {
     uint32_t* modes; float* vals; float* curves; uint32_t* steady_k; uint64_t* gout_mask; uint32_t* error;
+    uint32_t* st_modes; float* st_vals;
     uint32_t kt_max, n_smoothers;
 };
 

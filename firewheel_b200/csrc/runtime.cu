@@ -115,6 +115,7 @@ struct Plan {
         cudaSetDevice(device);
         cudaFree(d_tables); cudaFree(d_flags); cudaFree(rec.modes); cudaFree(rec.vals); cudaFree(rec.curves);
         cudaFree(rec.steady_k); cudaFree(rec.gout_mask); cudaFree(rec.error); cudaFree(d_bus_mask);
+        cudaFree(rec.st_modes); cudaFree(rec.st_vals);
     }
 };
 
@@ -226,7 +227,7 @@ static bool lower(fw_ctx* c, const Schedule& s, Plan* plan, std::string* why) {
             case FW_NODE_MONO_TO_STEREO: op.kind = OP_M2S; break;
             case FW_NODE_STEREO_TO_MONO: op.kind = OP_S2M; break;
             case FW_NODE_SUM:
-                if (sn.in.size() == sn.out.size()) continue;  // 1-port sum == copy (sum.rs:58-65): no data op
+                if (sn.in.size() == sn.out.size()) { prev = sn.id; continue; }  // 1-port sum == copy (sum.rs:58-65): no data op
                 *why = "SumNode with more than one port inside a voice chain (generic per-node lowering not built yet)"; return false;
             default: *why = std::string("node kind '") + node_debug_name(nr->params->kind) + "' has no device lowering yet"; return false;
         }
@@ -252,9 +253,11 @@ static bool lower(fw_ctx* c, const Schedule& s, Plan* plan, std::string* why) {
     r.curves = dev_alloc<float>((size_t)r.kt_max * n_sm * V * F, false);
     r.steady_k = dev_alloc<uint32_t>(V);
     r.gout_mask = dev_alloc<uint64_t>(V);
+    r.st_modes = dev_alloc<uint32_t>(V);
+    r.st_vals = dev_alloc<float>((size_t)(n_sm ? n_sm : 1) * V);
     r.error = dev_alloc<uint32_t>(1);
     plan->d_bus_mask = dev_alloc<uint64_t>(1);
-    if (!plan->d_tables || !plan->d_flags || !r.modes || !r.vals || !r.curves || !r.steady_k || !r.gout_mask || !r.error || !plan->d_bus_mask) { *why = g_dev_err; return false; }
+    if (!plan->d_tables || !plan->d_flags || !r.modes || !r.vals || !r.curves || !r.steady_k || !r.gout_mask || !r.error || !plan->d_bus_mask || !r.st_modes || !r.st_vals) { *why = g_dev_err; return false; }
     if (!FW_CUDA(cudaMemcpy(plan->d_tables, &tb, sizeof(tb), cudaMemcpyHostToDevice))) { *why = g_dev_err; return false; }
     return true;
 }
