@@ -252,16 +252,20 @@ def run_b200(args, rank, world, local_rank):
     clocks = ClockSampler(local_rank)
     clocks.start()
     launches0 = proc.kernel_launches()
-    proc.profile(True)
     proc.event_record(0)
     for _ in range(args.steps):
         assert proc.process_planar_device(d_in, d_out, C, C, T) == 0
     proc.event_record(1)
     barrier()
     ms_total = max_over_ranks(proc.event_elapsed_ms(0, 1))
+    launches = proc.kernel_launches() - launches0
+    # second pass, same steps, with a CUDA-event pair around every kernel class (these events serialise the
+    # programmatic-dependent-launch overlap, so they stay out of the headline pass)
+    proc.profile(True)
+    for _ in range(args.steps):
+        assert proc.process_planar_device(d_in, d_out, C, C, T) == 0
     prof_ms, prof_n = proc.profile_read()
     proc.profile(False)
-    launches = proc.kernel_launches() - launches0
     clk = clocks.stop()
     ms_per_step = ms_total / args.steps
     samples_per_step = V * C * T * world
@@ -298,7 +302,7 @@ def run_b200(args, rank, world, local_rank):
             traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "chain_kernel<4,2,true> (gain->pan->bus tree)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "chain_kernel<VEC=4,CIN=2,BUS,4 voices/warp,16 warps> (gain->pan->bus tree)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "kernel_ms": chain_ms,
                 "algorithmic_bytes_per_launch": algo_bytes,
                 "step_share": {"control_ms": prof_ms[0] / max(prof_n[0], 1), "chain_ms": chain_ms, "combine_ms": prof_ms[2] / max(prof_n[2], 1)}}

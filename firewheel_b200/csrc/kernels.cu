@@ -70,13 +70,13 @@ __device__ __forceinline__ uint32_t sm_set_and_process(SmLocal& s, float val, ui
     return REC_CURVE;
 }
 
-__global__ void __launch_bounds__(128) control_kernel(ControlArgs a) {
+__global__ void __launch_bounds__(128) control_kernel(const __grid_constant__ ControlArgs a) {
     pdl_launch_dependents();  // the data kernel may start loading samples now; it waits for us before reading records
     pdl_wait();               // the previous call's data kernels still read the record buffers we are about to rewrite
     const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t V = a.num_voices;
     if (v >= V) return;
-    const CtlTables& tb = *a.tables;
+    const CtlTables& tb = a.tables;
     const uint32_t NS = tb.n_smoothers, F = a.block_frames;
     const uint32_t n_blocks = (a.frames + F - 1) / F;
 
@@ -566,9 +566,9 @@ template <int VEC, int CIN>
 static cudaError_t launch_chain_t(const ChainArgs& a, bool bus, cudaStream_t st) {
     if (VEC == 4) {
         switch (chain_variant()) {
-            case 1: return launch_chain_v<VEC, CIN, 4, 16, 2>(a, bus, st);
+            case 1: return launch_chain_v<VEC, CIN, 8, 8, 2>(a, bus, st);
             case 2: return launch_chain_v<VEC, CIN, 8, 8, 3>(a, bus, st);
-            default: break;
+            default: return launch_chain_v<VEC, CIN, 4, 16, 2>(a, bus, st);  // 64 regs, 2 x 512 threads per SM
         }
     }
     return launch_chain_v<VEC, CIN, 8, 8, 2>(a, bus, st);

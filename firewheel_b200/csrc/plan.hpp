@@ -53,7 +53,7 @@ struct Records {
 };
 
 struct ControlArgs {
-    const CtlTables* tables;
+    CtlTables tables;      // by value: read through the constant bank (2.8 KB of kernel parameters)
     Records rec;
     uint64_t* flags;       // [V] buffer_silence_flags bitset (schedule.rs:170), persists across calls
     uint32_t num_voices, frames, block_frames;

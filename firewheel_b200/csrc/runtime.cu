@@ -107,13 +107,13 @@ struct Plan {
     Schedule sched;
     std::vector<std::shared_ptr<NodeDeviceState>> states;   // keeps every referenced node state alive
     std::vector<Id> nodes_to_remove;
-    CtlTables* d_tables = nullptr; uint64_t* d_flags = nullptr;
+    CtlTables tables{}; uint64_t* d_flags = nullptr;
     ChainProgram prog{}; bool bus = false; uint32_t n_sm = 0, c_in = 0, c_out = 0, num_voices = 0, block_frames = 0;
     Records rec{};
     uint64_t* d_bus_mask = nullptr;
     ~Plan() {
         cudaSetDevice(device);
-        cudaFree(d_tables); cudaFree(d_flags); cudaFree(rec.modes); cudaFree(rec.vals); cudaFree(rec.curves);
+        cudaFree(d_flags); cudaFree(rec.modes); cudaFree(rec.vals); cudaFree(rec.curves);
         cudaFree(rec.steady_k); cudaFree(rec.gout_mask); cudaFree(rec.error); cudaFree(d_bus_mask);
         cudaFree(rec.st_modes); cudaFree(rec.st_vals);
     }
@@ -243,7 +243,6 @@ static bool lower(fw_ctx* c, const Schedule& s, Plan* plan, std::string* why) {
     // ---- device allocations (main thread) ----
     const uint32_t V = c->cfg.num_voices, F = c->max_block_frames;
     plan->num_voices = V; plan->block_frames = F; plan->bus = c->cfg.master_bus != 0;
-    plan->d_tables = dev_alloc<CtlTables>(1, false);
     plan->d_flags = dev_alloc<uint64_t>(V);
     Records& r = plan->rec;
     r.n_smoothers = n_sm;
@@ -257,8 +256,8 @@ static bool lower(fw_ctx* c, const Schedule& s, Plan* plan, std::string* why) {
     r.st_vals = dev_alloc<float>((size_t)(n_sm ? n_sm : 1) * V);
     r.error = dev_alloc<uint32_t>(1);
     plan->d_bus_mask = dev_alloc<uint64_t>(1);
-    if (!plan->d_tables || !plan->d_flags || !r.modes || !r.vals || !r.curves || !r.steady_k || !r.gout_mask || !r.error || !plan->d_bus_mask || !r.st_modes || !r.st_vals) { *why = g_dev_err; return false; }
-    if (!FW_CUDA(cudaMemcpy(plan->d_tables, &tb, sizeof(tb), cudaMemcpyHostToDevice))) { *why = g_dev_err; return false; }
+    if (!plan->d_flags || !r.modes || !r.vals || !r.curves || !r.steady_k || !r.gout_mask || !r.error || !plan->d_bus_mask || !r.st_modes || !r.st_vals) { *why = g_dev_err; return false; }
+    plan->tables = tb;
     return true;
 }
 
@@ -637,7 +636,7 @@ static int proc_enqueue(fw_processor* p, const float* d_in, float* d_out, uint32
     for (auto& st : pl.states) if (!st->snapshot_params(p->stream)) return FW_PROC_DEVICE_ERROR;
 
     ControlArgs ca{};
-    ca.tables = pl.d_tables; ca.rec = pl.rec; ca.flags = pl.d_flags; ca.num_voices = V; ca.frames = T; ca.block_frames = pl.block_frames;
+    ca.tables = pl.tables; ca.rec = pl.rec; ca.flags = pl.d_flags; ca.num_voices = V; ca.frames = T; ca.block_frames = pl.block_frames;
     ca.a = p->sm_a; ca.b = p->sm_b; ca.eps = p->sm_eps;
     { ProfScope ps(p, 0); if (!FW_CUDA(launch_control(ca, p->stream))) return FW_PROC_DEVICE_ERROR; }
     p->launches++;
