@@ -290,7 +290,9 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) chain_kernel(ChainArg
     // FULL: every voice and every frame of this CTA's tile exists and nothing is zeroed: no bounds checks at all
     const bool full = (vcta + kVPC <= V) && ((blockIdx.x + 1u) * kTile <= T) && !a.zero_first_block;
 
-    // ---- issue every sample load of this thread up front (independent of the control kernel) --------
+    // ---- issue every sample load of this thread up front (independent of the control kernel, unless this stage
+    //      consumes the output of the preceding kernel) -------------------------------------------------
+    if (a.in_from_prev_kernel) pdl_wait();
     float x[kVPW][2][VEC];
     if (full) {
         const float* p = a.in + (size_t)v0 * CIN * T + t;
@@ -542,7 +544,8 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, c
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    static const bool no_pdl = getenv("FW_NO_PDL") != nullptr;  // A/B knob
+    cfg.attrs = attr; cfg.numAttrs = no_pdl ? 0 : 1;
     return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 

@@ -17,4 +17,6 @@ cudaError_t launch_interleave(const float* planar, float* inter, const uint64_t*
                               uint32_t block_frames, cudaStream_t st);
 cudaError_t launch_fill(float* p, size_t n, float val, cudaStream_t st);
 cudaError_t launch_bus_mask(const uint64_t* gout_mask, uint32_t V, uint32_t n_out, uint64_t* bus_mask, cudaStream_t st);
+cudaError_t launch_temporal(const TemporalArgs& a, cudaStream_t st);
+bool temporal_fast_path(const TemporalArgs& a);
 }  // namespace fw

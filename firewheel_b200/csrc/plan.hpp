@@ -64,8 +64,18 @@ struct ChainArgs {
     const float* in;       // [V][c_in][T]
     float* out;            // bus: partial bus [G][c_out][T]; else [V][c_out][T]
     uint32_t num_voices, frames, block_frames, zero_first_block;
+    uint32_t in_from_prev_kernel, pad0, pad1, pad2;  // `in` is produced by the preceding kernel: wait before the loads
     Records rec;
     ChainProgram prog;
+};
+
+// One pass of the temporal kernel over R = voices * channels rows of T frames.
+struct TemporalArgs {
+    const float* in; float* out;   // [R][T]
+    uint32_t R, C, T, zero_first;  // zero_first: leading frames read as 0.0 (Q11)
+    uint32_t ns; const float* coeffs;  // biquad: [R / C][ns][5] = {b0,b1,b2,a1,a2}; ns == 0: no biquad
+    float* state;                  // [R][8][2] = {s1, s2}
+    uint32_t D; float* ring; uint32_t pos;  // delay: ring [R][D], D == 0: no delay
 };
 
 }  // namespace fw

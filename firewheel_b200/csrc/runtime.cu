@@ -13,6 +13,7 @@
 // There is no CPU fallback anywhere in this file: without a CUDA device activate() fails.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <cmath>
@@ -72,9 +73,16 @@ struct NodeDeviceState {
     float* sm_input[2] = {nullptr, nullptr};
     float* sm_last[2] = {nullptr, nullptr};
     uint32_t* sm_status[2] = {nullptr, nullptr};
+    // temporal nodes: `channels` rows per voice
+    uint32_t channels = 0;
+    float* d_coeffs = nullptr;   // biquad [V][ns][5]
+    float* d_state = nullptr;    // biquad [V*channels][8][2]
+    float* d_ring = nullptr;     // delay  [V*channels][D]
+    uint32_t ring_pos = 0;       // stream-side cursor into the ring
     ~NodeDeviceState() {
         cudaSetDevice(device);
         for (int i = 0; i < 2; ++i) { cudaFree(d_target[i]); cudaFree(sm_input[i]); cudaFree(sm_last[i]); cudaFree(sm_status[i]); }
+        cudaFree(d_coeffs); cudaFree(d_state); cudaFree(d_ring);
     }
     const std::vector<float>& host_target(int i) const { return kind == FW_NODE_VOLUME ? params->raw_gain : (i == 0 ? params->gain_l : params->gain_r); }
     // ParamSmoother::new(val): input = last_output = val, Inactive (smoother.rs:93-112; volume.rs:67-75)
@@ -88,6 +96,15 @@ struct NodeDeviceState {
             if (!FW_CUDA(cudaMemcpy(sm_input[i], h, V * 4, cudaMemcpyHostToDevice))) return false;
             if (!FW_CUDA(cudaMemcpy(sm_last[i], h, V * 4, cudaMemcpyHostToDevice))) return false;
         }
+        if (kind == FW_NODE_BIQUAD) {
+            d_coeffs = dev_alloc<float>((size_t)V * params->num_stages * 5, false);
+            d_state = dev_alloc<float>((size_t)V * channels * 8 * 2);  // zero state
+            if (!d_coeffs || !d_state) return false;
+            if (params->num_stages && !FW_CUDA(cudaMemcpy(d_coeffs, params->coeffs.data(), params->coeffs.size() * 4, cudaMemcpyHostToDevice))) return false;
+        } else if (kind == FW_NODE_DELAY && params->delay) {
+            d_ring = dev_alloc<float>((size_t)V * channels * params->delay);  // zero-initialised ring
+            if (!d_ring) return false;
+        }
         uploaded_version = params->version;
         return true;
     }
@@ -97,6 +114,8 @@ struct NodeDeviceState {
         if (ver == uploaded_version) return true;
         for (uint32_t i = 0; i < n_sm; ++i)
             if (!FW_CUDA(cudaMemcpyAsync(d_target[i], host_target(i).data(), V * 4, cudaMemcpyHostToDevice, st))) return false;
+        if (kind == FW_NODE_BIQUAD && params->num_stages &&
+            !FW_CUDA(cudaMemcpyAsync(d_coeffs, params->coeffs.data(), params->coeffs.size() * 4, cudaMemcpyHostToDevice, st))) return false;
         uploaded_version = ver;
         return true;
     }
@@ -108,7 +127,11 @@ struct Plan {
     std::vector<std::shared_ptr<NodeDeviceState>> states;   // keeps every referenced node state alive
     std::vector<Id> nodes_to_remove;
     CtlTables tables{}; uint64_t* d_flags = nullptr;
-    ChainProgram prog{}; bool bus = false; uint32_t n_sm = 0, c_in = 0, c_out = 0, num_voices = 0, block_frames = 0;
+    // data plane: stages run in order; pointwise stages are fused chain programs, temporal stages own state
+    struct Stage { int kind = 0; /* 0 pointwise, 1 temporal */ ChainProgram prog{}; uint32_t c_in = 0, c_out = 0;
+                   std::shared_ptr<NodeDeviceState> biquad, delay; };
+    std::vector<Stage> stages;
+    bool bus = false; uint32_t n_sm = 0, c_in = 0, c_out = 0, num_voices = 0, block_frames = 0;
     Records rec{};
     uint64_t* d_bus_mask = nullptr;
     ~Plan() {
@@ -147,6 +170,7 @@ struct fw_processor {
     // I/O staging (high-water mark)
     float *d_in = nullptr, *d_out = nullptr, *d_inter = nullptr, *d_part[2] = {nullptr, nullptr}, *d_flush = nullptr;
     size_t cap_in = 0, cap_out = 0, cap_inter = 0, cap_part[2] = {0, 0};
+    float* d_tmp[2] = {nullptr, nullptr}; size_t cap_tmp[2] = {0, 0};  // inter-stage scratch
     uint64_t* h_masks = nullptr; uint32_t* h_err = nullptr;  // pinned
     // optional per-kernel-class timing (CUDA events on `stream`)
     bool profiling = false; std::vector<cudaEvent_t> prof_ev; std::vector<int> prof_class; size_t prof_used = 0;
@@ -200,27 +224,49 @@ static bool lower(fw_ctx* c, const Schedule& s, Plan* plan, std::string* why) {
     tb.n_smoothers = n_sm;
 
     // ---- data plane: a linear chain graph_in -> n1 -> ... -> nk -> graph_out, port i to port i ----
-    ChainProgram pr{};
     const SchedNode& gin = s.nodes.front();
     const SchedNode& gout = s.nodes.back();
     uint32_t width = (uint32_t)gin.out.size();
     if (width != c->n_in) { *why = "stream input channels must equal the graph_in port count on the device path"; return false; }
     if (gout.in.size() != c->n_out) { *why = "stream output channels must equal the graph_out port count on the device path"; return false; }
     if (width < 1 || width > 2) { *why = "the fused chain supports 1 or 2 channels (generic per-node lowering not built yet)"; return false; }
-    pr.c_in = width;
+    plan->c_in = width;
     Id prev = gin.id;
     auto fed_by_prev = [&](const SchedNode& sn, uint32_t w) {
         if (sn.in.size() != w) return false;
         for (uint32_t p = 0; p < w; ++p) if (sn.in[p].should_clear || sn.in[p].producer != prev || sn.in[p].producer_port != p) return false;
         return true;
     };
+    Plan::Stage cur; cur.kind = 0; cur.prog.c_in = width; cur.c_in = width;
+    bool cur_open = true;  // a pointwise stage is being accumulated
+    auto close_pointwise = [&](bool force) {
+        if (cur_open && (cur.prog.n_ops > 0 || force)) { cur.prog.c_out = width; cur.c_out = width; plan->stages.push_back(cur); }
+        cur = Plan::Stage{}; cur.kind = 0; cur.prog.c_in = width; cur.c_in = width; cur_open = true;
+    };
     for (size_t i = 1; i + 1 < n; ++i) {
         const SchedNode& sn = s.nodes[i];
         NodeRec* nr = g.node(sn.id);
         if (!fed_by_prev(sn, width)) { *why = "voice graph is not a linear port-to-port chain (generic per-node lowering not built yet)"; return false; }
-        if (pr.n_ops >= (uint32_t)kMaxChainOps) { *why = "chain longer than 16 nodes"; return false; }
+        if (sn.out.size() < 1 || sn.out.size() > 2) { *why = "the fused chain supports 1 or 2 channels"; return false; }
+        const uint32_t kind = nr->params->kind;
+        if (kind == FW_NODE_BIQUAD || kind == FW_NODE_DELAY) {
+            std::shared_ptr<NodeDeviceState> st = c->node_states[sn.id.pack()];
+            // a delay directly after a biquad joins its pass; anything else opens a new temporal stage
+            if (kind == FW_NODE_DELAY && !plan->stages.empty() && plan->stages.back().kind == 1 && !plan->stages.back().delay &&
+                plan->stages.back().biquad && cur.prog.n_ops == 0) {
+                plan->stages.back().delay = st;
+            } else {
+                close_pointwise(false);
+                Plan::Stage ts; ts.kind = 1; ts.c_in = ts.c_out = width;
+                if (kind == FW_NODE_BIQUAD) ts.biquad = st; else ts.delay = st;
+                plan->stages.push_back(ts);
+            }
+            prev = sn.id;
+            continue;
+        }
+        if (cur.prog.n_ops >= (uint32_t)kMaxChainOps) { *why = "more than 16 pointwise nodes in a row"; return false; }
         ChainOp op{}; op.sm0 = op.sm1 = -1;
-        switch (nr->params->kind) {
+        switch (kind) {
             case FW_NODE_VOLUME: op.kind = OP_GAIN; op.sm0 = sm_of_node[i]; break;
             case FW_NODE_PAN: op.kind = OP_PAN; op.sm0 = sm_of_node[i]; op.sm1 = sm_of_node[i] + 1; break;
             case FW_NODE_HARD_CLIP: op.kind = OP_CLIP; op.f0 = nr->params->threshold_gain; break;
@@ -229,16 +275,17 @@ static bool lower(fw_ctx* c, const Schedule& s, Plan* plan, std::string* why) {
             case FW_NODE_SUM:
                 if (sn.in.size() == sn.out.size()) { prev = sn.id; continue; }  // 1-port sum == copy (sum.rs:58-65): no data op
                 *why = "SumNode with more than one port inside a voice chain (generic per-node lowering not built yet)"; return false;
-            default: *why = std::string("node kind '") + node_debug_name(nr->params->kind) + "' has no device lowering yet"; return false;
+            default: *why = std::string("node kind '") + node_debug_name(kind) + "' has no device lowering yet"; return false;
         }
-        if (sn.out.size() < 1 || sn.out.size() > 2) { *why = "the fused chain supports 1 or 2 channels"; return false; }
-        if (nr->params->kind != FW_NODE_SUM) pr.ops[pr.n_ops++] = op;
+        cur.prog.ops[cur.prog.n_ops++] = op;
         width = (uint32_t)sn.out.size();
         prev = sn.id;
     }
     if (!fed_by_prev(gout, width)) { *why = "graph_out is not fed port-to-port by the end of the chain"; return false; }
-    pr.c_out = width;
-    plan->prog = pr; plan->n_sm = n_sm; plan->c_in = pr.c_in; plan->c_out = pr.c_out;
+    // the last stage must be pointwise when the master bus follows it, and a plan is never empty
+    const bool bus = c->cfg.master_bus != 0;
+    close_pointwise(plan->stages.empty() || (bus && cur.prog.n_ops == 0 && plan->stages.back().kind == 1));
+    plan->n_sm = n_sm; plan->c_out = width;
 
     // ---- device allocations (main thread) ----
     const uint32_t V = c->cfg.num_voices, F = c->max_block_frames;
@@ -546,7 +593,7 @@ int fw_ctx_update(fw_ctx* c, fw_update_status* out) {  // context.rs:93-148
         std::shared_ptr<NodeDeviceState> ds;
         if (msg.empty()) {
             ds = std::make_shared<NodeDeviceState>();
-            ds->device = c->cfg.device; ds->kind = r->params->kind; ds->V = c->cfg.num_voices; ds->params = r->params;
+            ds->device = c->cfg.device; ds->kind = r->params->kind; ds->V = c->cfg.num_voices; ds->params = r->params; ds->channels = r->num_inputs;
             if (!ds->create()) msg = "device allocation failed: " + g_dev_err;
         }
         if (!msg.empty()) {
@@ -641,33 +688,60 @@ static int proc_enqueue(fw_processor* p, const float* d_in, float* d_out, uint32
     { ProfScope ps(p, 0); if (!FW_CUDA(launch_control(ca, p->stream))) return FW_PROC_DEVICE_ERROR; }
     p->launches++;
 
-    ChainArgs xa{};
-    xa.in = d_in; xa.num_voices = V; xa.frames = T; xa.block_frames = pl.block_frames; xa.zero_first_block = p->pending_zero_first ? 1u : 0u;
-    xa.rec = pl.rec; xa.prog = pl.prog;
+    // ---- data plane: run the stages in order; intermediates ping-pong through [V][ch][T] scratch ----
+    const size_t n_stages = pl.stages.size();
+    if (n_stages > 1) {
+        const size_t need = (size_t)V * 2 * T;
+        if (!ensure(&p->d_tmp[0], &p->cap_tmp[0], need) || (n_stages > 2 && !ensure(&p->d_tmp[1], &p->cap_tmp[1], need))) return FW_PROC_DEVICE_ERROR;
+    }
+    const uint32_t zero_first_frames = p->pending_zero_first ? std::min(pl.block_frames, T) : 0u;  // Q11
     p->pending_zero_first = false;
-    if (!pl.bus) {
-        xa.out = d_out;
-        { ProfScope ps(p, 1); if (!FW_CUDA(launch_chain(xa, false, p->stream))) return FW_PROC_DEVICE_ERROR; }
-        p->launches++;
-    } else {
-        uint32_t n = chain_voice_groups(V);
-        if (n == 1) { xa.out = d_out; }
-        else {
-            const size_t need = (size_t)n * n_out * T;
-            if (!ensure(&p->d_part[0], &p->cap_part[0], need) || !ensure(&p->d_part[1], &p->cap_part[1], (size_t)((n + 15) / 16) * n_out * T)) return FW_PROC_DEVICE_ERROR;
-            xa.out = p->d_part[0];
-        }
-        { ProfScope ps(p, 1); if (!FW_CUDA(launch_chain(xa, true, p->stream))) return FW_PROC_DEVICE_ERROR; }
-        p->launches++;
-        ProfScope ps2(p, 2);
-        int cur = 0;
-        while (n > 1) {
-            const uint32_t n_next = (n + 15) / 16;
-            float* dst = n_next == 1 ? d_out : p->d_part[cur ^ 1];
-            if (!FW_CUDA(launch_combine(p->d_part[cur], dst, n, n_out, T, p->stream))) return FW_PROC_DEVICE_ERROR;
+    const float* src = d_in;
+    for (size_t si = 0; si < n_stages; ++si) {
+        const Plan::Stage& sg = pl.stages[si];
+        const bool last = si + 1 == n_stages;
+        float* dst = last ? d_out : p->d_tmp[si & 1];
+        if (sg.kind == 1) {
+            TemporalArgs ta{};
+            ta.in = src; ta.out = dst; ta.R = V * sg.c_in; ta.C = sg.c_in; ta.T = T; ta.zero_first = si == 0 ? zero_first_frames : 0u;
+            if (sg.biquad) { ta.ns = sg.biquad->params->num_stages; ta.coeffs = sg.biquad->d_coeffs; ta.state = sg.biquad->d_state; }
+            if (sg.delay && sg.delay->params->delay) {
+                ta.D = sg.delay->params->delay; ta.ring = sg.delay->d_ring; ta.pos = sg.delay->ring_pos;
+                sg.delay->ring_pos = (uint32_t)(((uint64_t)sg.delay->ring_pos + T) % ta.D);
+            }
+            { ProfScope ps(p, 3); if (!FW_CUDA(launch_temporal(ta, p->stream))) return FW_PROC_DEVICE_ERROR; }
             p->launches++;
-            n = n_next; cur ^= 1;
+            src = dst;
+            continue;
         }
+        ChainArgs xa{};
+        xa.in = src; xa.num_voices = V; xa.frames = T; xa.block_frames = pl.block_frames; xa.zero_first_block = (si == 0 && zero_first_frames) ? 1u : 0u;
+        xa.rec = pl.rec; xa.prog = sg.prog; xa.in_from_prev_kernel = si > 0 ? 1u : 0u;
+        if (!(last && pl.bus)) {
+            xa.out = dst;
+            { ProfScope ps(p, 1); if (!FW_CUDA(launch_chain(xa, false, p->stream))) return FW_PROC_DEVICE_ERROR; }
+            p->launches++;
+        } else {
+            uint32_t n = chain_voice_groups(V);
+            if (n == 1) { xa.out = d_out; }
+            else {
+                const size_t need = (size_t)n * n_out * T;
+                if (!ensure(&p->d_part[0], &p->cap_part[0], need) || !ensure(&p->d_part[1], &p->cap_part[1], (size_t)((n + 15) / 16) * n_out * T)) return FW_PROC_DEVICE_ERROR;
+                xa.out = p->d_part[0];
+            }
+            { ProfScope ps(p, 1); if (!FW_CUDA(launch_chain(xa, true, p->stream))) return FW_PROC_DEVICE_ERROR; }
+            p->launches++;
+            ProfScope ps2(p, 2);
+            int cur = 0;
+            while (n > 1) {
+                const uint32_t n_next = (n + 15) / 16;
+                float* cdst = n_next == 1 ? d_out : p->d_part[cur ^ 1];
+                if (!FW_CUDA(launch_combine(p->d_part[cur], cdst, n, n_out, T, p->stream))) return FW_PROC_DEVICE_ERROR;
+                p->launches++;
+                n = n_next; cur ^= 1;
+            }
+        }
+        src = dst;
     }
     return FW_PROC_OK;
 }
@@ -743,7 +817,7 @@ void fw_processor_free(fw_processor* p) {  // Drop processor.rs:251-263
     cudaStreamSynchronize(p->stream);
     ProcToCtx m; m.kind = 1; m.plan = p->plan; m.user_cx = p->user_cx;
     if (!p->ch->to_ctx.push(m)) delete p->plan;
-    cudaFree(p->d_in); cudaFree(p->d_out); cudaFree(p->d_inter); cudaFree(p->d_part[0]); cudaFree(p->d_part[1]); cudaFree(p->d_flush);
+    cudaFree(p->d_in); cudaFree(p->d_out); cudaFree(p->d_inter); cudaFree(p->d_part[0]); cudaFree(p->d_part[1]); cudaFree(p->d_flush); cudaFree(p->d_tmp[0]); cudaFree(p->d_tmp[1]);
     cudaFreeHost(p->h_masks); cudaFreeHost(p->h_err);
     for (auto& e : p->ev) if (e) cudaEventDestroy(e);
     for (auto& e : p->prof_ev) if (e) cudaEventDestroy(e);

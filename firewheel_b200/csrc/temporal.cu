@@ -1,0 +1,308 @@
+// temporal.cu — sm_100a kernels for the nodes that carry state along time: biquad cascade and
+// integer delay line (a12), fused into one pass per voice-channel row.
+//
+// These nodes are serial recurrences whose results must match the f32 oracle bit for bit, so the op order is the
+// oracle's (oracle/fw_oracle.hpp BiquadProcessor / DelayProcessor), spelled with __fmul_rn/__fadd_rn/__fsub_rn:
+//     y = (b0*x) + s1;   s1 = ((b1*x) - (a1*y)) + s2;   s2 = (b2*x) - (a2*y)
+// Rows (voice-channels) are independent but few (8192 in config 3), and each row is a serial recurrence, so the
+// fast kernel spreads the STAGES of a row over adjacent lanes (see biquad_delay_lanes).
+// Algorithmic bytes per mono-sample: in 4 + out 4 (+ ring read 4 + ring write 4 with a delay) = 8 / 16.
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdlib>
+#include <type_traits>
+#include <utility>
+
+#include "kernels.cuh"
+#include "plan.hpp"
+
+namespace fw {
+
+__device__ __forceinline__ void t_pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void t_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void cp_async16(float4* smem_dst, const float* gsrc) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+constexpr int kStateStages = 8;  // state layout [row][8][2] regardless of the cascade length
+
+// Fast path: stage-parallel lanes, one self-contained warp per 32/L rows.
+//   * A row (voice-channel) is owned by L consecutive lanes; lane s runs biquad stage s. Lane s hands its y to lane
+//     s+1 with shfl_up and is skewed by TWO iterations per stage (lane s works on sample n-2s), so the shuffle
+//     issued in iteration n is first consumed in iteration n+2: its latency never sits on the recurrence.
+//     Same arithmetic per stage as the oracle, only interleaved differently => bit-identical.
+//   * Each warp stages its own rows: tiles are [rows][8 x float4] per 32-frame chunk with an XOR swizzle on the
+//     16-byte granule (granule g of row r lives at g ^ (r & 7)), so cooperative 16-byte cp.async / STG.128 move
+//     full 128-byte row segments and the per-row LDS.128 / STS.128 of the stage lanes are bank-conflict free.
+//     Warps never meet at a CTA barrier (only __syncwarp), so they drift freely and cover each other's stalls.
+//   * x tiles: 4-deep cp.async pipeline; old-ring tiles: 3-deep; y tiles: double-buffered by chunk parity and
+//     flushed (coalesced) two chunks later to the ring (DELAY) or to `out`. With a delay, `out` is the old ring chunk.
+// Requires T % 32 == 0, zero_first % 32 == 0 and, with a delay, D % 32 == 0, pos % 32 == 0, D >= 160 (an old-ring
+// chunk is read two chunks ahead and must already hold the y flushed D/32 chunks earlier).
+template <int NS, int L, bool DELAY, int RPL>
+__global__ void __launch_bounds__(32) biquad_delay_lanes(TemporalArgs a) {
+    // RPL rows per lane: each lane runs stage s of RPL independent rows, so a lone warp per scheduler has RPL
+    // interleaved recurrences to fill the FP32 pipe latency (measured: 1 row/lane 0.50 ms).
+    constexpr int RSET = 32 / L, ROWS = RPL * RSET, PER = RPL * 8 / L, LAG = NS > 0 ? 2 * (NS - 1) : 0;
+    static_assert(NS <= L && (L == 1 || L == 2 || L == 4 || L == 8), "lanes per row");
+    // No early launch_dependents here: this kernel is issue-bound, and dependents parked at griddepcontrol.wait
+    // cost it issue slots (measured: 0.92 vs 0.64 ms per step). The implicit trigger at exit is enough.
+    t_pdl_wait();  // `in` is produced by the previous kernel of this call
+    const uint32_t lane = threadIdx.x, s = lane % L;
+    const uint32_t row0 = blockIdx.x * ROWS, R = a.R, T = a.T, D = a.D;
+    const bool is_first = s == 0, is_last = NS == 0 ? s == 0 : s == (uint32_t)(NS > 0 ? NS - 1 : 0);
+    __shared__ float4 xt[4][ROWS][8];
+    __shared__ float4 rt[DELAY ? 3 : 1][ROWS][8];
+    __shared__ float4 yt[2][ROWS][8];
+
+    uint32_t row_l[RPL], rsw[RPL]; bool lane_ok[RPL], last_ok[RPL];
+    float b0[RPL], b1[RPL], b2[RPL], a1[RPL], a2[RPL], s1[RPL], s2[RPL], q0[RPL], q1[RPL], yb[RPL][4];
+#pragma unroll
+    for (int j = 0; j < RPL; ++j) {
+        row_l[j] = j * RSET + lane / L; rsw[j] = row_l[j] & 7u;
+        const uint32_t r = row0 + row_l[j];
+        lane_ok[j] = r < R && (NS == 0 ? s == 0 : s < (uint32_t)NS);
+        last_ok[j] = is_last && lane_ok[j];
+        b0[j] = b1[j] = b2[j] = a1[j] = a2[j] = s1[j] = s2[j] = q0[j] = q1[j] = 0.0f;
+        yb[j][0] = yb[j][1] = yb[j][2] = yb[j][3] = 0.0f;
+        if (NS > 0 && lane_ok[j]) {
+            const float* k = a.coeffs + ((size_t)(r / a.C) * NS + s) * 5;
+            b0[j] = k[0]; b1[j] = k[1]; b2[j] = k[2]; a1[j] = k[3]; a2[j] = k[4];
+            s1[j] = a.state[((size_t)r * kStateStages + s) * 2]; s2[j] = a.state[((size_t)r * kStateStages + s) * 2 + 1];
+        }
+    }
+
+    // cooperative copies: lane handles PER (row, granule) pairs of every tile
+    const float* in_p[PER]; float* out_p[PER]; float* ring_p[PER]; uint32_t sw[PER]; bool ok[PER];
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        const uint32_t idx = lane + 32u * i, rr = idx >> 3, g = idx & 7u;
+        ok[i] = row0 + rr < R;
+        const size_t row = ok[i] ? row0 + rr : 0;
+        in_p[i] = a.in + row * T + g * 4u;
+        out_p[i] = a.out + row * T + g * 4u;
+        ring_p[i] = DELAY ? a.ring + row * D + g * 4u : nullptr;
+        sw[i] = rr * 8u + (g ^ (rr & 7u));  // float4 index inside a tile
+    }
+    const uint32_t nch = T / 32u;
+    auto issue = [&](uint32_t chx, uint32_t chr) {  // x tile of chunk chx and old-ring tile of chunk chr, one commit group
+        if (chx < nch) {
+#pragma unroll
+            for (int i = 0; i < PER; ++i) if (ok[i]) cp_async16(&xt[chx & 3u][0][0] + sw[i], in_p[i] + chx * 32u);
+        }
+        if (DELAY && chr < nch) {
+            const uint32_t base = (a.pos + chr * 32u) % D;
+#pragma unroll
+            for (int i = 0; i < PER; ++i) if (ok[i]) cp_async16(&rt[chr % 3u][0][0] + sw[i], ring_p[i] + base);
+        }
+        cp_async_commit();  // always one group per call so wait_group counts stay uniform
+    };
+    auto flush_y = [&](uint32_t ch) {  // y tile of chunk ch -> ring (DELAY) or out, coalesced
+        const uint32_t base = DELAY ? (a.pos + ch * 32u) % D : 0u;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) if (ok[i]) {
+            const float4 v = (&yt[ch & 1u][0][0])[sw[i]];
+            if (DELAY) *reinterpret_cast<float4*>(ring_p[i] + base) = v;
+            else __stcs(reinterpret_cast<float4*>(out_p[i] + ch * 32u), v);
+        }
+    };
+
+    // One skewed iteration of all RPL rows; gi = global iteration index, u4 = gi & 3 (compile-time when unrolled).
+    // q0/q1: inter-stage pipeline — the value shuffled in iteration n is the input of iteration n+2.
+    // CHECK = true (first chunk, zeroed chunks, drain): stage s is live only while its sample n = gi - 2s is in [0, T).
+    // CHECK = false (every other chunk): all stages are live; lanes that own no stage run on garbage that is never stored.
+    // per-lane swizzled granule offsets of this lane's row(s) inside a tile row: granule c lives at c ^ (row & 7)
+    uint32_t goff[RPL][8];
+#pragma unroll
+    for (int j = 0; j < RPL; ++j)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) goff[j][c] = (uint32_t)c ^ rsw[j];
+    const float4* xbase[RPL]; float4* ybase[RPL][2];  // refreshed per chunk: x tile row, y tile rows of this / the previous chunk
+    auto body = [&](auto check, uint32_t gi, const float (&x)[RPL], int u4, int n4) {
+        constexpr bool CHECK = decltype(check)::value;
+        const bool in_range = CHECK ? (gi - 2u * s) < T : true;  // unsigned compare: also false during warm-up (gi < 2s)
+        const int slot = (u4 - LAG) & 3;  // the last stage emits sample m = gi - LAG; (gi - LAG) & 3 == (u4 - LAG) & 3
+#pragma unroll
+        for (int j = 0; j < RPL; ++j) {
+            const bool active = CHECK ? (lane_ok[j] && in_range) : true;
+            float y;
+            if (NS == 0) {
+                y = x[j];
+            } else {
+                const float xi = is_first ? x[j] : q0[j];
+                y = __fadd_rn(__fmul_rn(b0[j], xi), s1[j]);
+                const float n1 = __fadd_rn(__fsub_rn(__fmul_rn(b1[j], xi), __fmul_rn(a1[j], y)), s2[j]);
+                const float n2 = __fsub_rn(__fmul_rn(b2[j], xi), __fmul_rn(a2[j], y));
+                if (!CHECK || active) { s1[j] = n1; s2[j] = n2; }
+                q0[j] = q1[j];
+                q1[j] = __shfl_up_sync(0xffffffffu, y, 1);
+            }
+            yb[j][slot] = y;
+            if (slot == 3 && (CHECK ? (is_last && active) : last_ok[j])) {
+                // m = gi - LAG lies in this chunk iff n4 * 4 + u4 >= LAG (all compile-time); granule (m >> 2) & 7
+                const int ml = n4 * 4 + u4 - LAG;
+                ybase[j][ml >= 0 ? 0 : 1][goff[j][(ml >> 2) & 7]] = make_float4(yb[j][0], yb[j][1], yb[j][2], yb[j][3]);
+            }
+        }
+    };
+    auto chunk = [&](auto check, uint32_t ch, bool zero_in) {
+#pragma unroll
+        for (int j = 0; j < RPL; ++j) {
+            xbase[j] = &xt[ch & 3u][row_l[j]][0];
+            ybase[j][0] = &yt[ch & 1u][row_l[j]][0];
+            ybase[j][1] = &yt[(ch + 1u) & 1u][row_l[j]][0];
+        }
+        float4 xnext[RPL];  // software-pipelined: the LDS.128 for step n4+1 is issued before step n4 is consumed
+#pragma unroll
+        for (int j = 0; j < RPL; ++j) xnext[j] = xbase[j][goff[j][0]];
+#pragma unroll
+        for (uint32_t n4 = 0; n4 < 8u; ++n4) {
+            float4 xq[RPL];  // every lane of a row reads the same granule (broadcast); only stage 0 uses it
+#pragma unroll
+            for (int j = 0; j < RPL; ++j) {
+                xq[j] = xnext[j];
+                if (n4 + 1u < 8u) xnext[j] = xbase[j][goff[j][(n4 + 1u) & 7u]];
+                if (decltype(check)::value && zero_in) xq[j] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            }
+            const uint32_t gi = ch * 32u + n4 * 4u;
+            float x[RPL];
+#pragma unroll
+            for (int j = 0; j < RPL; ++j) x[j] = xq[j].x;
+            body(check, gi, x, 0, (int)n4);
+#pragma unroll
+            for (int j = 0; j < RPL; ++j) x[j] = xq[j].y;
+            body(check, gi + 1u, x, 1, (int)n4);
+#pragma unroll
+            for (int j = 0; j < RPL; ++j) x[j] = xq[j].z;
+            body(check, gi + 2u, x, 2, (int)n4);
+#pragma unroll
+            for (int j = 0; j < RPL; ++j) x[j] = xq[j].w;
+            body(check, gi + 3u, x, 3, (int)n4);
+        }
+    };
+
+    // groups: G(-3) = {x0}, G(-2) = {x1, ring0}, G(-1) = {x2, ring1}, G(ch) = {x(ch+3), ring(ch+2)}
+    issue(0, nch); issue(1, 0); issue(2, 1);
+    for (uint32_t ch = 0; ch < nch; ++ch) {
+        __syncwarp();  // every lane is done with x tile ch-1, ring tile ch-1 and the y tile about to be flushed
+        if (ch >= 2u) flush_y(ch - 2u);
+        __syncwarp();  // order the flush's ring stores before the ring loads issued next (they may alias when D is small)
+        issue(ch + 3u, ch + 2u);
+        cp_async_wait<2>();  // groups up to G(ch-2) have landed: x tile ch and old-ring tile ch
+        __syncwarp();
+        if (DELAY) {
+#pragma unroll
+            for (int i = 0; i < PER; ++i) if (ok[i]) __stcs(reinterpret_cast<float4*>(out_p[i] + ch * 32u), (&rt[ch % 3u][0][0])[sw[i]]);
+        }
+        const bool zero_in = ch * 32u < a.zero_first;  // Q11 (chunk-uniform)
+        if (ch == 0 || zero_in) chunk(std::true_type{}, ch, zero_in);  // warm-up: stage s starts at iteration 2s
+        else chunk(std::false_type{}, ch, false);
+    }
+    if (nch > 0) {
+        const float zx[RPL] = {};
+#pragma unroll
+        for (int j = 0; j < RPL; ++j) { ybase[j][0] = &yt[nch & 1u][row_l[j]][0]; ybase[j][1] = &yt[(nch + 1u) & 1u][row_l[j]][0]; }
+#pragma unroll
+        for (int it = 0; it < ((LAG + 3) & ~3); ++it) body(std::true_type{}, T + it, zx, it & 3, it >> 2);  // drain (T % 4 == 0)
+        __syncwarp();
+        if (nch >= 2u) flush_y(nch - 2u);
+        flush_y(nch - 1u);
+    }
+    cp_async_wait<0>();
+#pragma unroll
+    for (int j = 0; j < RPL; ++j) {
+        if (NS > 0 && lane_ok[j]) {
+            const uint32_t r = row0 + row_l[j];
+            a.state[((size_t)r * kStateStages + s) * 2] = s1[j];
+            a.state[((size_t)r * kStateStages + s) * 2 + 1] = s2[j];
+        }
+    }
+}
+
+// Generic path: any T, D, pos. One thread per row, scalar, unskewed. Bit-identical results (same per-stage op order).
+__global__ void __launch_bounds__(64) biquad_delay_generic(TemporalArgs a) {
+    t_pdl_wait();
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= a.R) return;
+    const uint32_t NS = a.ns, T = a.T, D = a.D;
+    float b0[kStateStages], b1[kStateStages], b2[kStateStages], a1[kStateStages], a2[kStateStages], s1[kStateStages], s2[kStateStages];
+    for (uint32_t s = 0; s < NS; ++s) {
+        const float* k = a.coeffs + ((size_t)(r / a.C) * NS + s) * 5;
+        b0[s] = k[0]; b1[s] = k[1]; b2[s] = k[2]; a1[s] = k[3]; a2[s] = k[4];
+        s1[s] = a.state[((size_t)r * kStateStages + s) * 2]; s2[s] = a.state[((size_t)r * kStateStages + s) * 2 + 1];
+    }
+    const float* in = a.in + (size_t)r * T;
+    float* out = a.out + (size_t)r * T;
+    float* ring = D ? a.ring + (size_t)r * D : nullptr;
+    uint32_t p = D ? a.pos % D : 0;
+    for (uint32_t n = 0; n < T; ++n) {
+        float x = n < a.zero_first ? 0.0f : in[n];
+        for (uint32_t s = 0; s < NS; ++s) {
+            const float y = __fadd_rn(__fmul_rn(b0[s], x), s1[s]);
+            s1[s] = __fadd_rn(__fsub_rn(__fmul_rn(b1[s], x), __fmul_rn(a1[s], y)), s2[s]);
+            s2[s] = __fsub_rn(__fmul_rn(b2[s], x), __fmul_rn(a2[s], y));
+            x = y;
+        }
+        if (D) { const float d = ring[p]; ring[p] = x; x = d; p = p + 1 == D ? 0 : p + 1; }
+        out[n] = x;
+    }
+    for (uint32_t s = 0; s < NS; ++s) { a.state[((size_t)r * kStateStages + s) * 2] = s1[s]; a.state[((size_t)r * kStateStages + s) * 2 + 1] = s2[s]; }
+}
+
+// Temporal kernels are launched in plain stream order: measured on config 3, programmatic dependent launch made
+// the step 0.62 ms instead of 0.51 ms (dependents parked at griddepcontrol.wait compete with an issue-bound kernel).
+template <class... KArgs, class... Args>
+static cudaError_t launch_pdl_t(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cfg.attrs = nullptr; cfg.numAttrs = 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
+template <int NS, int L>
+static cudaError_t launch_lanes(const TemporalArgs& a, cudaStream_t st) {
+    static const int rpl_knob = getenv("FW_TEMPORAL_RPL") ? atoi(getenv("FW_TEMPORAL_RPL")) : 1;  // A/B knob (2 rows/lane measured slower: 0.59 vs 0.50 ms)
+    if constexpr (L > 1) {
+        if (rpl_knob != 1) {
+            constexpr uint32_t rows_per_warp = 2 * 32 / L;
+            const dim3 grid((a.R + rows_per_warp - 1) / rows_per_warp), block(32);
+            if (a.D) return launch_pdl_t(biquad_delay_lanes<NS, L, true, 2>, grid, block, st, a);
+            return launch_pdl_t(biquad_delay_lanes<NS, L, false, 2>, grid, block, st, a);
+        }
+    }
+    constexpr uint32_t rows_per_warp = 32 / L;
+    const dim3 grid((a.R + rows_per_warp - 1) / rows_per_warp), block(32);
+    if (a.D) return launch_pdl_t(biquad_delay_lanes<NS, L, true, 1>, grid, block, st, a);
+    return launch_pdl_t(biquad_delay_lanes<NS, L, false, 1>, grid, block, st, a);
+}
+
+bool temporal_fast_path(const TemporalArgs& a) {
+    if (a.T == 0 || a.T % 32u || a.zero_first % 32u) return false;
+    if ((reinterpret_cast<uintptr_t>(a.in) | reinterpret_cast<uintptr_t>(a.out) | reinterpret_cast<uintptr_t>(a.ring)) % 16u) return false;
+    if (a.D && (a.D % 32u || a.pos % 32u || a.D < 160u)) return false;
+    return true;
+}
+
+cudaError_t launch_temporal(const TemporalArgs& a, cudaStream_t st) {
+    if (a.R == 0 || a.T == 0) return cudaSuccess;
+    if (temporal_fast_path(a)) {
+        switch (a.ns) {
+            case 0: return launch_lanes<0, 1>(a, st);
+            case 1: return launch_lanes<1, 1>(a, st);
+            case 2: return launch_lanes<2, 2>(a, st);
+            case 3: return launch_lanes<3, 4>(a, st);
+            case 4: return launch_lanes<4, 4>(a, st);
+            case 5: return launch_lanes<5, 8>(a, st);
+            case 6: return launch_lanes<6, 8>(a, st);
+            case 7: return launch_lanes<7, 8>(a, st);
+            default: return launch_lanes<8, 8>(a, st);
+        }
+    }
+    return launch_pdl_t(biquad_delay_generic, dim3((a.R + 63) / 64), dim3(64), st, a);
+}
+
+}  // namespace fw

@@ -164,3 +164,59 @@ def test_unsupported_topology_fails_loudly(gpu):
     rc, _ = proc.process_planar(synth((1, 4, 256), 1), out, 4, 2, 256)
     assert rc == 0 and np.all(out == 0)  # no schedule => silence (processor.rs:86-89), never a CPU fallback
     proc.free()
+
+
+# ---- temporal nodes: biquad cascade + delay line (spec ours; parity = bit-exact vs the f32 oracle) ------------
+def biquad_coeffs(lib, V, ns, seed):
+    from firewheel_b200 import design_rbj
+    rng = np.random.default_rng(seed)
+    k = np.zeros((V, ns, 5), f32)
+    for v in range(V):
+        for s in range(ns):
+            k[v, s] = design_rbj(lib, [0, 4, 1, 5][s % 4], 200.0 * (2.0 ** rng.uniform(0, 5.3)), rng.uniform(0.5, 2.0), rng.uniform(-6, 6), 48000)
+    return k
+
+
+def temporal_chain(gpu, V, ns, D, F, pre=(), post=(), bus=False):
+    from firewheel_b200 import BiquadNode, DelayNode
+    nodes = list(pre)
+    if ns is not None:
+        nodes.append((lambda: BiquadNode(ns), 2, 2))
+    if D is not None:
+        nodes.append((lambda: DelayNode(D), 2, 2))
+    nodes += list(post)
+    bq_index = len(pre) if ns is not None else None
+    coeffs = biquad_coeffs(gpu, V, ns, 7 * V + (ns or 0)) if ns else None
+
+    def setup(cx, ids):
+        if ns:
+            cx.graph.set_biquad_coeffs(ids[bq_index], coeffs)
+    return lambda lib: chain(lib, 2, nodes, voices=V, master_bus=bus, max_block=F, setup=setup)
+
+
+@pytest.mark.parametrize("ns,D,F,T", [(4, 12000, 512, 2048), (4, 96, 256, 1024), (1, None, 128, 512), (8, 128, 64, 640), (2, 3200, 512, 1024),
+                                      (None, 160, 256, 512), (None, 0, 256, 512),            # delay only; delay(0) == copy
+                                      (4, 300, 256, 1000), (3, 50, 100, 777), (4, 12000, 512, 36)])  # generic path: ragged T / D
+def test_biquad_delay(gpu, oracle, ns, D, F, T):
+    V = 19
+    x = synth((V, 2, T), 500 + T + (ns or 0))
+    calls = [(x, None), (x[:, :, ::-1].copy(), None), (x, None)]  # three calls: filter state and ring carry across calls
+    both(gpu, oracle, temporal_chain(gpu, V, ns, D, F), calls, 2)
+
+
+def test_mixed_pointwise_and_temporal_stages(gpu, oracle):
+    V, F, T = 70, 256, 1024
+    pre = [(lambda: VolumeNode(80.0), 2, 2)]
+    post = [(lambda: PanNode(0.25), 2, 2), (lambda: HardClipNode(-1.0), 2, 2)]
+    x = synth((V, 2, T), 77)
+    both(gpu, oracle, temporal_chain(gpu, V, 4, 480, F, pre, post, bus=True), [(x, None), (x, None)], 2, True)
+    both(gpu, oracle, temporal_chain(gpu, V, 2, None, F, pre, post, bus=False), [(x, None)], 2, False)
+    # temporal stage last with a master bus: an empty pointwise stage carries the bus
+    both(gpu, oracle, temporal_chain(gpu, V, 4, 96, F, pre, (), bus=True), [(x, None), (x, None)], 2, True)
+
+
+def test_config3_shape(gpu, oracle):
+    """BASELINE config[2] shape at reduced voice count: 4-stage biquad cascade + 12000-frame delay, 512-frame blocks."""
+    V, F, K = 256, 512, 26  # 13312 frames > D: the ring wraps inside one call
+    x = synth((V, 2, F * K), 3)
+    both(gpu, oracle, temporal_chain(gpu, V, 4, 12000, F), [(x, None), (x[:, :, :F * 2].copy(), None)], 2)
