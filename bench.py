@@ -237,6 +237,19 @@ def run_b200(args, rank, world, local_rank):
     V, C, F, KB = w["voices"], w["ch"], w["block"], w["blocks"]
     T = F * KB
     cx, proc = build_graph(fw, lib, args.workload, V, F, local_rank, 1000 + rank)
+    if dist and w["bus"]:
+        # the master bus crosses ranks inside the product: NCCL all-gather of the per-rank buses over NVLink, then the
+        # top levels of the balanced tree in rank order (bit-identical on every rank)
+        import ctypes as _ct
+        ids = [bytes(128)]
+        if rank == 0:
+            buf = (_ct.c_uint8 * 128)()
+            if lib.comm_unique_id(buf) != 0:
+                raise RuntimeError("ncclGetUniqueId failed: " + lib.last_device_error().decode())
+            ids = [bytes(buf)]
+        dist.broadcast_object_list(ids, src=0)
+        if proc.comm_init(rank, world, ids[0]) != 0:
+            raise RuntimeError("ncclCommInitRank failed: " + lib.last_device_error().decode())
     in_bytes = V * C * T * 4
     out_bytes = C * T * 4 if w["bus"] else in_bytes
 
@@ -352,7 +365,7 @@ def run_b200(args, rank, world, local_rank):
                 "dtype": "f32", "data": "synthetic",
                 "config": {"workload": w["desc"], "voices_per_gpu": V, "channels": C, "block_frames": F, "blocks_per_step": KB,
                            "l2": f"inputs larger than L2 ({in_bytes >> 20} MiB per GPU per step)", "layout": "planar [voice][ch][frame]",
-                           "parallelism": f"voices sharded over {world} rank(s)"},
+                           "parallelism": f"voices sharded over {world} rank(s)" + ("; master bus = NCCL all-gather + rank-ordered tree" if (world > 1 and w["bus"]) else "")},
                 "clocks": clk,
                 "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": in_bytes * world, "d2h_bytes_per_step": out_bytes * world,
                         "steps": e2e_steps, "ms_per_step": e2e_s * 1e3, "api": "fw_processor_process_planar (pinned host buffers)"},

@@ -12,6 +12,7 @@
 //
 // There is no CPU fallback anywhere in this file: without a CUDA device activate() fails.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <atomic>
@@ -142,6 +143,32 @@ struct Plan {
     }
 };
 
+// NCCL, resolved at run time with dlopen("libnccl.so.2"): no link-time dependency, and inside a process that
+// already loaded torch's bundled NCCL the same copy is reused (same soname). Only the master-bus exchange uses it.
+struct NcclUniqueId { char internal[128]; };
+struct NcclApi {
+    void* handle = nullptr;
+    int (*GetUniqueId)(NcclUniqueId*) = nullptr;
+    int (*CommInitRank)(void**, int, NcclUniqueId, int) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool load() {
+        if (handle) return true;
+        for (const char* name : {"libnccl.so.2", "libnccl.so"}) { handle = dlopen(name, RTLD_NOW | RTLD_GLOBAL); if (handle) break; }
+        if (!handle) { g_dev_err = std::string("dlopen(libnccl.so.2) failed: ") + dlerror(); return false; }
+        GetUniqueId = reinterpret_cast<decltype(GetUniqueId)>(dlsym(handle, "ncclGetUniqueId"));
+        CommInitRank = reinterpret_cast<decltype(CommInitRank)>(dlsym(handle, "ncclCommInitRank"));
+        AllGather = reinterpret_cast<decltype(AllGather)>(dlsym(handle, "ncclAllGather"));
+        CommDestroy = reinterpret_cast<decltype(CommDestroy)>(dlsym(handle, "ncclCommDestroy"));
+        GetErrorString = reinterpret_cast<decltype(GetErrorString)>(dlsym(handle, "ncclGetErrorString"));
+        if (!GetUniqueId || !CommInitRank || !AllGather || !CommDestroy || !GetErrorString) { g_dev_err = "libnccl lacks an expected symbol"; return false; }
+        return true;
+    }
+    bool ok(int rc, const char* what) { if (rc == 0) return true; g_dev_err = std::string(what) + ": " + GetErrorString(rc); return false; }
+};
+static NcclApi g_nccl;
+
 struct CtxToProc { int kind = 0; Plan* plan = nullptr; };                 // 0 NewSchedule, 1 Stop (processor.rs:265-268)
 struct ProcToCtx { int kind = 0; Plan* plan = nullptr; void* user_cx = nullptr; };  // 0 ReturnSchedule, 1 Dropped (:270-277)
 struct Channels { Spsc<CtxToProc> to_proc; Spsc<ProcToCtx> to_ctx; };
@@ -171,6 +198,9 @@ struct fw_processor {
     float *d_in = nullptr, *d_out = nullptr, *d_inter = nullptr, *d_part[2] = {nullptr, nullptr}, *d_flush = nullptr;
     size_t cap_in = 0, cap_out = 0, cap_inter = 0, cap_part[2] = {0, 0};
     float* d_tmp[2] = {nullptr, nullptr}; size_t cap_tmp[2] = {0, 0};  // inter-stage scratch
+    // multi-GPU master bus: voices shard by rank; the per-rank buses are all-gathered and tree-summed in rank order
+    void* nccl_comm = nullptr; int rank = 0, world = 1;
+    float *d_bus_local = nullptr, *d_gather = nullptr; size_t cap_bus_local = 0, cap_gather = 0;
     uint64_t* h_masks = nullptr; uint32_t* h_err = nullptr;  // pinned
     // optional per-kernel-class timing (CUDA events on `stream`)
     bool profiling = false; std::vector<cudaEvent_t> prof_ev; std::vector<int> prof_class; size_t prof_used = 0;
@@ -723,7 +753,12 @@ static int proc_enqueue(fw_processor* p, const float* d_in, float* d_out, uint32
             p->launches++;
         } else {
             uint32_t n = chain_voice_groups(V);
-            if (n == 1) { xa.out = d_out; }
+            float* bus_dst = d_out;  // this rank's bus; with several ranks it is gathered and tree-summed below
+            if (p->world > 1) {
+                if (!ensure(&p->d_bus_local, &p->cap_bus_local, (size_t)n_out * T) || !ensure(&p->d_gather, &p->cap_gather, (size_t)p->world * n_out * T)) return FW_PROC_DEVICE_ERROR;
+                bus_dst = p->d_bus_local;
+            }
+            if (n == 1) { xa.out = bus_dst; }
             else {
                 const size_t need = (size_t)n * n_out * T;
                 if (!ensure(&p->d_part[0], &p->cap_part[0], need) || !ensure(&p->d_part[1], &p->cap_part[1], (size_t)((n + 15) / 16) * n_out * T)) return FW_PROC_DEVICE_ERROR;
@@ -735,10 +770,18 @@ static int proc_enqueue(fw_processor* p, const float* d_in, float* d_out, uint32
             int cur = 0;
             while (n > 1) {
                 const uint32_t n_next = (n + 15) / 16;
-                float* cdst = n_next == 1 ? d_out : p->d_part[cur ^ 1];
+                float* cdst = n_next == 1 ? bus_dst : p->d_part[cur ^ 1];
                 if (!FW_CUDA(launch_combine(p->d_part[cur], cdst, n, n_out, T, p->stream))) return FW_PROC_DEVICE_ERROR;
                 p->launches++;
                 n = n_next; cur ^= 1;
+            }
+            if (p->world > 1) {
+                // Exchange step: all-gather the per-rank buses over NVLink, then the top log2(world) levels of
+                // the same balanced tree in rank order on every rank — bit-identical on all ranks, unlike ncclAllReduce.
+                if (!g_nccl.ok(g_nccl.AllGather(p->d_bus_local, p->d_gather, (size_t)n_out * T, /*ncclFloat32*/ 7, p->nccl_comm, p->stream), "ncclAllGather")) return FW_PROC_DEVICE_ERROR;
+                p->launches++;
+                if (!FW_CUDA(launch_combine(p->d_gather, d_out, (uint32_t)p->world, n_out, T, p->stream))) return FW_PROC_DEVICE_ERROR;
+                p->launches++;
             }
         }
         src = dst;
@@ -817,7 +860,8 @@ void fw_processor_free(fw_processor* p) {  // Drop processor.rs:251-263
     cudaStreamSynchronize(p->stream);
     ProcToCtx m; m.kind = 1; m.plan = p->plan; m.user_cx = p->user_cx;
     if (!p->ch->to_ctx.push(m)) delete p->plan;
-    cudaFree(p->d_in); cudaFree(p->d_out); cudaFree(p->d_inter); cudaFree(p->d_part[0]); cudaFree(p->d_part[1]); cudaFree(p->d_flush); cudaFree(p->d_tmp[0]); cudaFree(p->d_tmp[1]);
+    cudaFree(p->d_in); cudaFree(p->d_out); cudaFree(p->d_inter); cudaFree(p->d_part[0]); cudaFree(p->d_part[1]); cudaFree(p->d_flush); cudaFree(p->d_tmp[0]); cudaFree(p->d_tmp[1]); cudaFree(p->d_bus_local); cudaFree(p->d_gather);
+    if (p->nccl_comm) g_nccl.CommDestroy(p->nccl_comm);
     cudaFreeHost(p->h_masks); cudaFreeHost(p->h_err);
     for (auto& e : p->ev) if (e) cudaEventDestroy(e);
     for (auto& e : p->prof_ev) if (e) cudaEventDestroy(e);
@@ -876,7 +920,22 @@ int fw_processor_l2_flush(fw_processor* p) {
     if (!FW_CUDA(launch_fill(p->d_flush, n, 1.0f, p->stream))) return -1;
     return 0;
 }
-int fw_comm_unique_id(uint8_t*) { g_dev_err = "multi-GPU master bus not built yet"; return -1; }
-int fw_processor_comm_init(fw_processor*, int, int, const uint8_t*) { g_dev_err = "multi-GPU master bus not built yet"; return -1; }
+int fw_comm_unique_id(uint8_t* id128) {
+    if (!id128 || !g_nccl.load()) return -1;
+    NcclUniqueId id;
+    if (!g_nccl.ok(g_nccl.GetUniqueId(&id), "ncclGetUniqueId")) return -1;
+    std::memcpy(id128, id.internal, 128);
+    return 0;
+}
+int fw_processor_comm_init(fw_processor* p, int rank, int world, const uint8_t* id128) {
+    if (!p || !id128 || world < 1 || world > 16 || rank < 0 || rank >= world) { g_dev_err = "bad comm arguments (1 <= world <= 16)"; return -1; }
+    if (world == 1) { p->rank = 0; p->world = 1; return 0; }
+    if (!g_nccl.load()) return -1;
+    cudaSetDevice(p->device);
+    NcclUniqueId id; std::memcpy(id.internal, id128, 128);
+    if (!g_nccl.ok(g_nccl.CommInitRank(&p->nccl_comm, world, id, rank), "ncclCommInitRank")) return -1;
+    p->rank = rank; p->world = world;
+    return 0;
+}
 
 }  // extern "C"
