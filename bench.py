@@ -227,6 +227,10 @@ def run_b200(args, rank, world, local_rank):
         raise RuntimeError("no CUDA device for this rank: " + lib.last_device_error().decode())
     dist = None
     if world > 1:
+        # NCCL prints its version banner on stdout at NCCL_DEBUG >= VERSION; keep stdout for the single JSON line
+        os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+            os.environ["NCCL_DEBUG"] = "NONE"
         import torch
         import torch.distributed as dist_mod
         torch.cuda.set_device(local_rank)

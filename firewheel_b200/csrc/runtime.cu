@@ -201,6 +201,8 @@ struct fw_processor {
     // multi-GPU master bus: voices shard by rank; the per-rank buses are all-gathered and tree-summed in rank order
     void* nccl_comm = nullptr; int rank = 0, world = 1;
     float *d_bus_local = nullptr, *d_gather = nullptr; size_t cap_bus_local = 0, cap_gather = 0;
+    // the exchange runs on a side stream so that it overlaps the next call's control + chain kernels
+    cudaStream_t side = nullptr; cudaEvent_t ev_bus_ready = nullptr, ev_exchange_done = nullptr; bool exchange_pending = false;
     uint64_t* h_masks = nullptr; uint32_t* h_err = nullptr;  // pinned
     // optional per-kernel-class timing (CUDA events on `stream`)
     bool profiling = false; std::vector<cudaEvent_t> prof_ev; std::vector<int> prof_class; size_t prof_used = 0;
@@ -674,6 +676,11 @@ void* fw_ctx_deactivate(fw_ctx* c, int stream_is_running) {  // context.rs:162-2
 }
 
 // ---- stream side --------------------------------------------------------------------------------
+// make the main stream wait for an outstanding master-bus exchange (side stream)
+static void join_side(fw_processor* p) {
+    if (p->exchange_pending) { cudaStreamWaitEvent(p->stream, p->ev_exchange_done, 0); p->exchange_pending = false; }
+}
+
 static void proc_poll(fw_processor* p) {  // processor.rs:167-206
     CtxToProc m;
     while (p->ch->to_proc.pop(&m)) {
@@ -755,6 +762,7 @@ static int proc_enqueue(fw_processor* p, const float* d_in, float* d_out, uint32
             uint32_t n = chain_voice_groups(V);
             float* bus_dst = d_out;  // this rank's bus; with several ranks it is gathered and tree-summed below
             if (p->world > 1) {
+                if ((size_t)n_out * T > p->cap_bus_local || (size_t)p->world * n_out * T > p->cap_gather) join_side(p);  // about to reallocate
                 if (!ensure(&p->d_bus_local, &p->cap_bus_local, (size_t)n_out * T) || !ensure(&p->d_gather, &p->cap_gather, (size_t)p->world * n_out * T)) return FW_PROC_DEVICE_ERROR;
                 bus_dst = p->d_bus_local;
             }
@@ -764,6 +772,7 @@ static int proc_enqueue(fw_processor* p, const float* d_in, float* d_out, uint32
                 if (!ensure(&p->d_part[0], &p->cap_part[0], need) || !ensure(&p->d_part[1], &p->cap_part[1], (size_t)((n + 15) / 16) * n_out * T)) return FW_PROC_DEVICE_ERROR;
                 xa.out = p->d_part[0];
             }
+            if (p->world > 1 && n == 1) join_side(p);  // the chain kernel writes d_bus_local directly
             { ProfScope ps(p, 1); if (!FW_CUDA(launch_chain(xa, true, p->stream))) return FW_PROC_DEVICE_ERROR; }
             p->launches++;
             ProfScope ps2(p, 2);
@@ -771,6 +780,7 @@ static int proc_enqueue(fw_processor* p, const float* d_in, float* d_out, uint32
             while (n > 1) {
                 const uint32_t n_next = (n + 15) / 16;
                 float* cdst = n_next == 1 ? bus_dst : p->d_part[cur ^ 1];
+                if (p->world > 1 && n_next == 1) join_side(p);  // d_bus_local is still being read by the previous exchange
                 if (!FW_CUDA(launch_combine(p->d_part[cur], cdst, n, n_out, T, p->stream))) return FW_PROC_DEVICE_ERROR;
                 p->launches++;
                 n = n_next; cur ^= 1;
@@ -778,10 +788,14 @@ static int proc_enqueue(fw_processor* p, const float* d_in, float* d_out, uint32
             if (p->world > 1) {
                 // Exchange step: all-gather the per-rank buses over NVLink, then the top log2(world) levels of
                 // the same balanced tree in rank order on every rank — bit-identical on all ranks, unlike ncclAllReduce.
-                if (!g_nccl.ok(g_nccl.AllGather(p->d_bus_local, p->d_gather, (size_t)n_out * T, /*ncclFloat32*/ 7, p->nccl_comm, p->stream), "ncclAllGather")) return FW_PROC_DEVICE_ERROR;
+                cudaEventRecord(p->ev_bus_ready, p->stream);
+                cudaStreamWaitEvent(p->side, p->ev_bus_ready, 0);
+                if (!g_nccl.ok(g_nccl.AllGather(p->d_bus_local, p->d_gather, (size_t)n_out * T, /*ncclFloat32*/ 7, p->nccl_comm, p->side), "ncclAllGather")) return FW_PROC_DEVICE_ERROR;
                 p->launches++;
-                if (!FW_CUDA(launch_combine(p->d_gather, d_out, (uint32_t)p->world, n_out, T, p->stream))) return FW_PROC_DEVICE_ERROR;
+                if (!FW_CUDA(launch_combine(p->d_gather, d_out, (uint32_t)p->world, n_out, T, p->side))) return FW_PROC_DEVICE_ERROR;
                 p->launches++;
+                cudaEventRecord(p->ev_exchange_done, p->side);
+                p->exchange_pending = true;
             }
         }
         src = dst;
@@ -811,6 +825,7 @@ int fw_processor_process_planar(fw_processor* p, const float* in, float* out, ui
     if (in_elems && !FW_CUDA(cudaMemcpyAsync(p->d_in, in, in_elems * 4, cudaMemcpyHostToDevice, p->stream))) return FW_PROC_DEVICE_ERROR;
     int rc = proc_enqueue(p, p->d_in, p->d_out, n_in, n_out, frames);
     if (rc < 0) return rc;
+    join_side(p);
     if (out_elems && !FW_CUDA(cudaMemcpyAsync(out, p->d_out, out_elems * 4, cudaMemcpyDeviceToHost, p->stream))) return FW_PROC_DEVICE_ERROR;
     const bool ran = rc == FW_PROC_OK && p->plan && frames > 0;
     if (ran) {
@@ -839,6 +854,7 @@ int fw_processor_process_interleaved(fw_processor* p, const float* in, float* ou
     }
     int rc = proc_enqueue(p, p->d_in, p->d_out, n_in, n_out, frames);
     if (rc < 0) return rc;
+    join_side(p);
     if (out_elems) {
         const bool ran = rc == FW_PROC_OK && p->plan && frames > 0;
         const uint64_t* masks = nullptr;
@@ -857,7 +873,9 @@ int fw_processor_process_interleaved(fw_processor* p, const float* in, float* ou
 void fw_processor_free(fw_processor* p) {  // Drop processor.rs:251-263
     if (!p) return;
     cudaSetDevice(p->device);
+    join_side(p);
     cudaStreamSynchronize(p->stream);
+    if (p->side) { cudaStreamSynchronize(p->side); cudaStreamDestroy(p->side); cudaEventDestroy(p->ev_bus_ready); cudaEventDestroy(p->ev_exchange_done); }
     ProcToCtx m; m.kind = 1; m.plan = p->plan; m.user_cx = p->user_cx;
     if (!p->ch->to_ctx.push(m)) delete p->plan;
     cudaFree(p->d_in); cudaFree(p->d_out); cudaFree(p->d_inter); cudaFree(p->d_part[0]); cudaFree(p->d_part[1]); cudaFree(p->d_flush); cudaFree(p->d_tmp[0]); cudaFree(p->d_tmp[1]); cudaFree(p->d_bus_local); cudaFree(p->d_gather);
@@ -880,11 +898,12 @@ int fw_processor_h2d(fw_processor* p, void* dst, const void* src, uint64_t bytes
 int fw_processor_d2h(fw_processor* p, void* dst, const void* src, uint64_t bytes) { cudaSetDevice(p->device); return FW_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, p->stream)) ? 0 : -1; }
 int fw_processor_sync(fw_processor* p) {
     cudaSetDevice(p->device);
+    join_side(p);
     if (!FW_CUDA(cudaStreamSynchronize(p->stream))) return -1;
     if (p->plan) { uint32_t e = 0; cudaMemcpy(&e, p->plan->rec.error, 4, cudaMemcpyDeviceToHost); if (e) { g_dev_err = "control pass overflowed its transient-block budget"; return -1; } }
     return 0;
 }
-int fw_processor_event_record(fw_processor* p, int slot) { if (slot < 0 || slot > 3) return -1; cudaSetDevice(p->device); return FW_CUDA(cudaEventRecord(p->ev[slot], p->stream)) ? 0 : -1; }
+int fw_processor_event_record(fw_processor* p, int slot) { if (slot < 0 || slot > 3) return -1; cudaSetDevice(p->device); join_side(p); return FW_CUDA(cudaEventRecord(p->ev[slot], p->stream)) ? 0 : -1; }
 float fw_processor_event_elapsed_ms(fw_processor* p, int a, int b) {
     float ms = -1.0f; cudaSetDevice(p->device);
     if (!FW_CUDA(cudaEventSynchronize(p->ev[b])) || !FW_CUDA(cudaEventElapsedTime(&ms, p->ev[a], p->ev[b]))) return -1.0f;
@@ -934,6 +953,8 @@ int fw_processor_comm_init(fw_processor* p, int rank, int world, const uint8_t* 
     cudaSetDevice(p->device);
     NcclUniqueId id; std::memcpy(id.internal, id128, 128);
     if (!g_nccl.ok(g_nccl.CommInitRank(&p->nccl_comm, world, id, rank), "ncclCommInitRank")) return -1;
+    if (!FW_CUDA(cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking)) || !FW_CUDA(cudaEventCreateWithFlags(&p->ev_bus_ready, cudaEventDisableTiming)) ||
+        !FW_CUDA(cudaEventCreateWithFlags(&p->ev_exchange_done, cudaEventDisableTiming))) return -1;
     p->rank = rank; p->world = world;
     return 0;
 }
