@@ -42,6 +42,9 @@ WORKLOADS = {
     "c3": dict(voices=4096, ch=2, block=512, blocks=32, bus=False, bytes_per_sample=16.0, kernel_class=3,
                kernel="biquad_delay_fast<NS=4,DELAY> (4-stage biquad cascade + 12000-frame delay ring)",
                desc="c3: 4096 stereo voices/GPU, 4-stage biquad cascade + 12000-frame delay line, 512-frame blocks, 32 blocks/step"),
+    "c4": dict(voices=256, ch=2, block=512, blocks=16, bus=False, bytes_per_sample=8.0, kernel_class=3, ir_len=48000,
+               kernel="reverb_gemm_kernel (tcgen05.mma kind::f16 M128 N256 K16, TMEM accumulators, TMA 128B-swizzle operands)",
+               desc="c4: 256 stereo voices/GPU, FIR convolutional reverb, 48000-tap stereo IR, bf16 tcgen05, 512-frame blocks, 16 blocks/step"),
 }
 
 
@@ -76,6 +79,12 @@ def build_graph(fw, lib, workload, V, block, device, seed):
         nodes = [g.add_node(2, 2, fw.VolumeNode(100.0)), g.add_node(2, 2, fw.PanNode(0.0))]
         g.set_percent_volume(nodes[0], pct)
         g.set_pan(nodes[1], pan)
+    elif workload == "c4":
+        L = w["ir_len"]
+        rng = np.random.default_rng(0x1200)
+        ir = rng.standard_normal((2, L)) * np.exp(-6.9 * np.arange(L) / L)
+        ir = (ir / np.sqrt((ir ** 2).sum(axis=1, keepdims=True))).astype(F32)
+        nodes = [g.add_node(2, 2, fw.ConvReverbNode(ir))]
     else:
         nodes = [g.add_node(2, 2, fw.BiquadNode(4)), g.add_node(2, 2, fw.DelayNode(12000))]
         g.set_biquad_coeffs(nodes[0], biquad_params(fw, lib, V, seed))
@@ -207,6 +216,8 @@ def run_reference(args, rank, world):
     n_blocks = 32  # bounded sample of the step (the full step is w["blocks"] blocks)
     if args.workload == "c3":
         n_blocks = 4
+    if args.workload == "c4":
+        V, n_blocks = max(cores, 2) * 1, 1  # direct-form FIR on the CPU: 96 kflop per output sample
     val, sec_per_step = oracle_rate(V, w["block"], n_blocks, cores, steps=args.steps, warmup=args.warmup, workload=args.workload)
     sample = f"{V} voices x {n_blocks} of {w['blocks']} blocks per step, {cores} replica threads over disjoint voice ranges"
     line = {"impl": "reference", "metric": "mono_equiv_samples_per_sec", "value": val, "unit": "samples/s", "n_gpus": args.gpus,
@@ -346,9 +357,14 @@ def run_b200(args, rank, world, local_rank):
             traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": w["kernel"], "achieved": achieved, "peak": peak, "unit": "GB/s",
+    if args.workload == "c4":  # tensor-pipe roofline: dense direct-form count 2*L flop per output sample
+        pk = ROOT / "MEASURED_PEAKS.json"
+        peak, peak_src = (float(json.loads(pk.read_text())["bf16_tflops"]), "measured (MEASURED_PEAKS.json bf16_tflops, burst)") if pk.exists() else (1590.0, "fallback (B200_PROFILING.md 1.59 PFLOP/s)")
+        flops = 2.0 * w["ir_len"] * V * C * T
+        achieved = flops / (chain_ms * 1e-3) / 1e12 if chain_ms > 0 else 0.0
+    roofline = {"bound": "hbm" if args.workload != "c4" else "tensor", "kernel": w["kernel"], "achieved": achieved, "peak": peak, "unit": "GB/s" if args.workload != "c4" else "TFLOP/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "kernel_ms": chain_ms,
-                "algorithmic_bytes_per_launch": algo_bytes,
+                "algorithmic_bytes_per_launch": algo_bytes, "algorithmic_flops_per_launch": (2.0 * w["ir_len"] * V * C * T) if args.workload == "c4" else None,
                 "step_share": {"control_ms": prof_ms[0] / max(prof_n[0], 1), "chain_ms": prof_ms[1] / max(prof_n[1], 1),
                                "combine_ms": prof_ms[2] / max(prof_n[2], 1), "temporal_ms": prof_ms[3] / max(prof_n[3], 1)}}
 
@@ -356,12 +372,18 @@ def run_b200(args, rank, world, local_rank):
     if rank == 0:
         n_blocks = 64
         n_blocks = 64 if args.workload == "c2" else 2
-        rate, sec = oracle_rate(V, F, n_blocks, 1, steps=1, warmup=0, workload=args.workload)
-        if sec < 2.0:  # size the sample towards ~10 s of CPU work
+        Vc = V if args.workload != "c4" else 2  # the direct-form FIR oracle needs ~0.2 s per voice-block
+        if args.workload == "c4":
+            n_blocks = 1
+        rate, sec = oracle_rate(Vc, F, n_blocks, 1, steps=1, warmup=0, workload=args.workload)
+        if sec < 2.0 and args.workload != "c4":  # size the sample towards ~10 s of CPU work
             n_blocks = int(min(KB * 8, max(n_blocks, n_blocks * 10.0 / max(sec, 1e-3))))
-            rate, sec = oracle_rate(V, F, n_blocks, 1, steps=1, warmup=0, workload=args.workload)
+            rate, sec = oracle_rate(Vc, F, n_blocks, 1, steps=1, warmup=0, workload=args.workload)
+        elif args.workload == "c4" and sec < 5.0:
+            Vc = int(min(64, max(2, Vc * 10.0 / max(sec, 1e-3))))
+            rate, sec = oracle_rate(Vc, F, n_blocks, 1, steps=1, warmup=0, workload=args.workload)
         cpu = {"value": rate, "unit": "samples/s", "cores": 1, "kind": "port",
-               "sample": f"{V} voices x {n_blocks} blocks of {F} frames, 1 thread (the reference's execution model), {sec:.1f} s"}
+               "sample": f"{Vc} voices x {n_blocks} blocks of {F} frames, 1 thread (the reference's execution model), {sec:.1f} s"}
 
     if rank == 0:
         line = {"metric": "mono_equiv_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
@@ -390,7 +412,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))  # c2 is the headline (BASELINE configs[1])
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -5,6 +5,8 @@
 #include <cstddef>
 #include <cstdint>
 
+#include <string>
+
 #include "plan.hpp"
 
 namespace fw {
@@ -19,4 +21,8 @@ cudaError_t launch_fill(float* p, size_t n, float val, cudaStream_t st);
 cudaError_t launch_bus_mask(const uint64_t* gout_mask, uint32_t V, uint32_t n_out, uint64_t* bus_mask, cudaStream_t st);
 cudaError_t launch_temporal(const TemporalArgs& a, cudaStream_t st);
 bool temporal_fast_path(const TemporalArgs& a);
+uint32_t reverb_kpad(uint32_t L);
+uint32_t reverb_hist(uint32_t L);
+cudaError_t launch_reverb_build(const float* d_ir, void* d_bt, uint32_t L, uint32_t ir_ch, cudaStream_t st);
+cudaError_t launch_reverb(const ReverbCall& rc, cudaStream_t st, std::string* err);
 }  // namespace fw

@@ -78,4 +78,12 @@ struct TemporalArgs {
     uint32_t D; float* ring; uint32_t pos;  // delay: ring [R][D], D == 0: no delay
 };
 
+// One call of the FIR reverb (reverb.cu): history roll + bf16 conversion, then the tcgen05 GEMM.
+struct ReverbCall {
+    const float* in; float* out;        // [V][C][T] f32
+    const void* xh_old; void* xh_new;   // bf16 sample history [C*V][pitch]: H history samples, then the call's block
+    const void* bt;                     // bf16 Toeplitz expansion of the IR [ir_ch][256][kpad]
+    uint32_t V, C, T, L, ir_ch, t_old, pitch, zero_first;
+};
+
 }  // namespace fw

@@ -1,0 +1,288 @@
+// reverb.cu — FIR convolutional reverb as a bf16 tcgen05 GEMM with TMEM accumulators.
+//
+//   y[v][n] = sum_{k<L} bf16(h_c[k]) * bf16(x[v][n-k])          (per IR channel c; products exact, fp32 accumulate)
+//
+// For one IR channel all voices share h, so a tile of outputs is a plain GEMM with a long reduction:
+//   D[128 voices][256 frames] = A[128][K] * Bt[256][K]^T,   K = L + 255 (padded to 64)
+//   A[v][j]  = xh[row v][H + n0 - Lr + j]         a TMA window of the bf16 sample history, K-major as stored;
+//                                                 Lr = roundup(L-1, 8) keeps every box start 16-byte aligned (TMA rule)
+//   Bt[i][j] = h[Lr - (j - i)]  (0 <= Lr-(j-i) < L)  Toeplitz expansion of the reversed IR, built ONCE per IR (12 MB per
+//                                                 channel for L = 48000) and then L2-resident: it is the same for
+//                                                 every time tile and every voice tile.
+// The band is (L / K) = 99.5 % dense, so the GEMM does no meaningful wasted work.
+//
+// Kernel anatomy (one CTA per output tile, 256 threads, 1 CTA/SM):
+//   warp 0   TMA producer   cp.async.bulk.tensor.2d -> 128B-swizzled smem stages, mbarrier expect_tx
+//   warp 1   MMA issuer     one elected thread: 4 x tcgen05.mma.kind::f16 (M128 N256 K16) per 64-wide k-block,
+//                           tcgen05.commit frees the stage / signals the epilogue
+//   warp 2   TMEM allocator (256 columns)
+//   warps 4-7 epilogue      tcgen05.ld 32x32b.x32 -> registers -> predicated 16-byte stores of y
+// 4 stages x (16 KB A + 32 KB B) = 192 KB of shared memory.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+
+#include "kernels.cuh"
+#include "plan.hpp"
+
+namespace fw {
+
+constexpr uint32_t RV_BM = 128, RV_BN = 256, RV_BK = 64, RV_STAGES = 4;
+constexpr uint32_t RV_A_BYTES = RV_BM * RV_BK * 2, RV_B_BYTES = RV_BN * RV_BK * 2;
+constexpr uint32_t RV_SMEM_BYTES = RV_STAGES * (RV_A_BYTES + RV_B_BYTES) + 1024 /*align*/ + 256 /*barriers*/;
+
+// ---------------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int32_t x, int32_t y) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(smem_dst)), "l"(tm), "r"(smem_u32(bar)), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void tcgen05_alloc(uint32_t* smem_result, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tcgen05_dealloc(uint32_t taddr, uint32_t cols) { asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory"); }
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tcgen05_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tcgen05_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+          "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+          "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
+// UMMA shared-memory descriptor, K-major operand, 128-byte swizzle: rows at 128 B pitch, 8-row groups at SBO = 1024 B,
+// LBO = 1 (unused for swizzled K-major), descriptor version 1 (sm_100), layout type 2 = SWIZZLE_128B.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3ffffu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024u >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// Instruction descriptor, kind::f16: D = F32, A = B = BF16, both K-major, N >> 3 at bit 17, M >> 4 at bit 24.
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N) { return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24); }
+
+// ---------------------------------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------------------------------
+// Bt[c][i][j] = bf16(h_c[Lr-(j-i)]) where 0 <= Lr-(j-i) < L, else 0.    [ir_ch][256][Kpad]
+__global__ void reverb_build_toeplitz(const float* __restrict__ ir, __nv_bfloat16* __restrict__ bt, uint32_t L, uint32_t Lr, uint32_t ir_ch, uint32_t kpad) {
+    const size_t n = (size_t)ir_ch * RV_BN * kpad;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t j = idx % kpad; const size_t ci = idx / kpad; const uint32_t i = ci % RV_BN, c = (uint32_t)(ci / RV_BN);
+        float v = 0.0f;
+        const int64_t k = (int64_t)Lr - ((int64_t)j - (int64_t)i);
+        if (k >= 0 && k < (int64_t)L) v = ir[(size_t)c * L + (size_t)k];
+        bt[idx] = __float2bfloat16_rn(v);
+    }
+}
+
+// xh_new[c*V + v][0..H) = tail of xh_old (the H most recent samples of the previous call); [H..H+T) = bf16(in[v][c][*])
+__global__ void reverb_prepare(const float* __restrict__ in, const __nv_bfloat16* __restrict__ xh_old, __nv_bfloat16* __restrict__ xh_new,
+                               uint32_t V, uint32_t C, uint32_t T, uint32_t H, uint32_t t_old, uint32_t pitch, uint32_t zero_first) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const uint32_t row = blockIdx.y;  // c * V + v
+    const uint32_t c = row / V, v = row % V;
+    const __nv_bfloat16* src_old = xh_old + (size_t)row * pitch + t_old;  // H valid samples precede column H + t_old ... start at t_old
+    __nv_bfloat16* dst = xh_new + (size_t)row * pitch;
+    const float* x = in + ((size_t)v * C + c) * T;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < H + T; i += gridDim.x * blockDim.x)
+        dst[i] = i < H ? src_old[i] : __float2bfloat16_rn((i - H) < zero_first ? 0.0f : x[i - H]);
+}
+
+struct ReverbGemmArgs {
+    float* out;                   // [V][C][T]
+    uint32_t V, C, T, Lr, H, ir_ch, num_kb, debug;
+};
+
+__global__ void __launch_bounds__(256, 1) reverb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const ReverbGemmArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));  // SWIZZLE_128B wants 1024-byte tiles
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + RV_STAGES * RV_A_BYTES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + RV_STAGES * (RV_A_BYTES + RV_B_BYTES));
+    uint64_t* empty_bar = full_bar + RV_STAGES;
+    uint64_t* tmem_full_bar = empty_bar + RV_STAGES;
+    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t nt = blockIdx.x, mt = blockIdx.y, c = blockIdx.z;
+    const uint32_t n0 = nt * RV_BN, v0 = mt * RV_BM;
+    const uint32_t num_kb = a.num_kb;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_b) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (uint32_t s = 0; s < RV_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) tcgen05_alloc(tmem_base_slot, RV_BN);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_base_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        asm volatile("griddepcontrol.wait;" ::: "memory");  // the history buffer is written by reverb_prepare just before us
+        if (lane == 0) {
+            const int32_t col_a0 = (int32_t)(a.H + n0) - (int32_t)a.Lr;  // multiple of 8 elements = 16 bytes
+            const int32_t row_a = (int32_t)(c * a.V + v0), row_b = (int32_t)((c % a.ir_ch) * RV_BN);
+            for (uint32_t kb = 0; kb < num_kb; ++kb) {
+                const uint32_t s = kb % RV_STAGES, ph = (kb / RV_STAGES) & 1u;
+                mbar_wait(&empty_bar[s], ph ^ 1u);
+                if (a.debug & 2u) { mbar_expect_tx(&full_bar[s], 0); continue; }
+                mbar_expect_tx(&full_bar[s], RV_A_BYTES + RV_B_BYTES);
+                tma_load_2d(smem_a + s * RV_A_BYTES, &tm_a, &full_bar[s], col_a0 + (int32_t)(kb * RV_BK), row_a);
+                tma_load_2d(smem_b + s * RV_B_BYTES, &tm_b, &full_bar[s], (int32_t)(kb * RV_BK), row_b);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one elected lane) =====
+        constexpr uint32_t idesc = umma_idesc_bf16(RV_BM, RV_BN);
+        for (uint32_t kb = 0; kb < num_kb; ++kb) {
+            const uint32_t s = kb % RV_STAGES, ph = (kb / RV_STAGES) & 1u;
+            mbar_wait(&full_bar[s], ph);
+            tcgen05_fence_after();
+            if (elect_one()) {
+                const uint64_t adesc = umma_desc_sw128(smem_u32(smem_a + s * RV_A_BYTES));
+                const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_b + s * RV_B_BYTES));
+#pragma unroll
+                for (uint32_t k = 0; k < RV_BK / 16; ++k)  // +32 bytes per K=16 step inside the 128-byte swizzle atom
+                    if (!(a.debug & 1u)) tcgen05_mma_f16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+                tcgen05_commit(&empty_bar[s]);                       // smem stage free once these MMAs retire
+                if (kb + 1 == num_kb) tcgen05_commit(tmem_full_bar);  // accumulator complete
+            }
+            __syncwarp();
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: TMEM -> registers -> global =====
+        const uint32_t q = warp & 3u;  // a warp may only touch TMEM lanes [32q, 32q+32)
+        mbar_wait(tmem_full_bar, 0);
+        tcgen05_fence_after();
+        const uint32_t v = v0 + q * 32u + lane;
+        float* dst_row = a.out + ((size_t)v * a.C + c) * a.T + n0;
+#pragma unroll 1
+        for (uint32_t col = 0; col < RV_BN; col += 32) {
+            uint32_t r[32];
+            if (a.debug & 4u) { for (int i = 0; i < 32; ++i) r[i] = 0; } else
+            tcgen05_ld_32x32b_x32(tmem_base + ((q * 32u) << 16) + col, r);
+            if (v < a.V) {
+                if (n0 + col + 32 <= a.T && (a.T & 3u) == 0) {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4)
+                        __stcs(reinterpret_cast<float4*>(dst_row + col + i), make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]), __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3])));
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) if (n0 + col + i < a.T) dst_row[col + i] = __uint_as_float(r[i]);
+                }
+            }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 2) tcgen05_dealloc(tmem_base, RV_BN);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr; cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess) fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+static bool make_map_bf16_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_elems, uint32_t box_inner, uint32_t box_outer) {
+    EncodeTiledFn fn = encode_tiled();
+    if (!fn) return false;
+    const cuuint64_t dims[2] = {inner, outer};
+    const cuuint64_t strides[1] = {pitch_elems * 2};
+    const cuuint32_t box[2] = {box_inner, box_outer};
+    const cuuint32_t estr[2] = {1, 1};
+    return fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static uint32_t reverb_lr(uint32_t L) { return ((L - 1 + 7) / 8) * 8; }
+uint32_t reverb_kpad(uint32_t L) { return ((reverb_lr(L) + RV_BN + RV_BK - 1) / RV_BK) * RV_BK; }
+uint32_t reverb_hist(uint32_t L) { return ((L - 1 + 63) / 64) * 64; }  // history samples kept in front of each call's block
+
+cudaError_t launch_reverb_build(const float* d_ir, void* d_bt, uint32_t L, uint32_t ir_ch, cudaStream_t st) {
+    const size_t n = (size_t)ir_ch * RV_BN * reverb_kpad(L);
+    reverb_build_toeplitz<<<(unsigned)((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096), 256, 0, st>>>(d_ir, static_cast<__nv_bfloat16*>(d_bt), L, reverb_lr(L), ir_ch, reverb_kpad(L));
+    return cudaGetLastError();
+}
+
+// One call: roll the history, convert the block to bf16, run the GEMM. xh_old/xh_new: [C*V][pitch] bf16.
+cudaError_t launch_reverb(const ReverbCall& rc, cudaStream_t st, std::string* err) {
+    const uint32_t H = reverb_hist(rc.L), kpad = reverb_kpad(rc.L);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(reverb_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RV_SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    {
+        dim3 grid((H + rc.T + 255) / 256 < 64 ? (H + rc.T + 255) / 256 : 64, rc.C * rc.V);
+        reverb_prepare<<<grid, 256, 0, st>>>(rc.in, static_cast<const __nv_bfloat16*>(rc.xh_old), static_cast<__nv_bfloat16*>(rc.xh_new), rc.V, rc.C, rc.T, H, rc.t_old,
+                                            rc.pitch, rc.zero_first);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    CUtensorMap tm_a, tm_b;
+    if (!make_map_bf16_2d(&tm_a, rc.xh_new, (uint64_t)H + rc.T, (uint64_t)rc.C * rc.V, rc.pitch, RV_BK, RV_BM) ||
+        !make_map_bf16_2d(&tm_b, rc.bt, kpad, (uint64_t)rc.ir_ch * RV_BN, kpad, RV_BK, RV_BN)) {
+        if (err) *err = "cuTensorMapEncodeTiled failed";
+        return cudaErrorInvalidValue;
+    }
+    static const uint32_t dbg = getenv("FW_REVERB_DEBUG") ? (uint32_t)atoi(getenv("FW_REVERB_DEBUG")) : 0u;
+    ReverbGemmArgs ga{rc.out, rc.V, rc.C, rc.T, reverb_lr(rc.L), H, rc.ir_ch, kpad / RV_BK, dbg};
+    dim3 grid((rc.T + RV_BN - 1) / RV_BN, (rc.V + RV_BM - 1) / RV_BM, rc.C);
+    reverb_gemm_kernel<<<grid, 256, RV_SMEM_BYTES, st>>>(tm_a, tm_b, ga);
+    return cudaGetLastError();
+}
+
+}  // namespace fw

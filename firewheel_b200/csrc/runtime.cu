@@ -80,10 +80,13 @@ struct NodeDeviceState {
     float* d_state = nullptr;    // biquad [V*channels][8][2]
     float* d_ring = nullptr;     // delay  [V*channels][D]
     uint32_t ring_pos = 0;       // stream-side cursor into the ring
+    // conv reverb: Toeplitz-expanded IR and the ping-pong bf16 sample history (reverb.cu)
+    void* d_bt = nullptr; void* d_xh[2] = {nullptr, nullptr}; uint32_t xh_cur = 0, xh_t_old = 0, xh_pitch = 0;
+    static constexpr uint32_t kReverbMaxFrames = 65536;  // longest call the history buffers are sized for
     ~NodeDeviceState() {
         cudaSetDevice(device);
         for (int i = 0; i < 2; ++i) { cudaFree(d_target[i]); cudaFree(sm_input[i]); cudaFree(sm_last[i]); cudaFree(sm_status[i]); }
-        cudaFree(d_coeffs); cudaFree(d_state); cudaFree(d_ring);
+        cudaFree(d_coeffs); cudaFree(d_state); cudaFree(d_ring); cudaFree(d_bt); cudaFree(d_xh[0]); cudaFree(d_xh[1]);
     }
     const std::vector<float>& host_target(int i) const { return kind == FW_NODE_VOLUME ? params->raw_gain : (i == 0 ? params->gain_l : params->gain_r); }
     // ParamSmoother::new(val): input = last_output = val, Inactive (smoother.rs:93-112; volume.rs:67-75)
@@ -105,6 +108,18 @@ struct NodeDeviceState {
         } else if (kind == FW_NODE_DELAY && params->delay) {
             d_ring = dev_alloc<float>((size_t)V * channels * params->delay);  // zero-initialised ring
             if (!d_ring) return false;
+        } else if (kind == FW_NODE_CONV_REVERB) {
+            const uint32_t L = params->ir_len, ich = params->ir_channels, kpad = reverb_kpad(L);
+            xh_pitch = reverb_hist(L) + kReverbMaxFrames;
+            d_bt = dev_alloc<uint16_t>((size_t)ich * 256 * kpad, false);
+            d_xh[0] = dev_alloc<uint16_t>((size_t)V * channels * xh_pitch);  // zero history
+            d_xh[1] = dev_alloc<uint16_t>((size_t)V * channels * xh_pitch);
+            float* d_ir = dev_alloc<float>((size_t)ich * L, false);
+            if (!d_bt || !d_xh[0] || !d_xh[1] || !d_ir) { cudaFree(d_ir); return false; }
+            bool ok = FW_CUDA(cudaMemcpy(d_ir, params->ir.data(), (size_t)ich * L * 4, cudaMemcpyHostToDevice)) &&
+                      FW_CUDA(launch_reverb_build(d_ir, d_bt, L, ich, nullptr)) && FW_CUDA(cudaDeviceSynchronize());
+            cudaFree(d_ir);
+            if (!ok) return false;
         }
         uploaded_version = params->version;
         return true;
@@ -130,7 +145,7 @@ struct Plan {
     CtlTables tables{}; uint64_t* d_flags = nullptr;
     // data plane: stages run in order; pointwise stages are fused chain programs, temporal stages own state
     struct Stage { int kind = 0; /* 0 pointwise, 1 temporal */ ChainProgram prog{}; uint32_t c_in = 0, c_out = 0;
-                   std::shared_ptr<NodeDeviceState> biquad, delay; };
+                   std::shared_ptr<NodeDeviceState> biquad, delay, reverb; };  // kind 2: reverb
     std::vector<Stage> stages;
     bool bus = false; uint32_t n_sm = 0, c_in = 0, c_out = 0, num_voices = 0, block_frames = 0;
     Records rec{};
@@ -281,6 +296,13 @@ static bool lower(fw_ctx* c, const Schedule& s, Plan* plan, std::string* why) {
         if (!fed_by_prev(sn, width)) { *why = "voice graph is not a linear port-to-port chain (generic per-node lowering not built yet)"; return false; }
         if (sn.out.size() < 1 || sn.out.size() > 2) { *why = "the fused chain supports 1 or 2 channels"; return false; }
         const uint32_t kind = nr->params->kind;
+        if (kind == FW_NODE_CONV_REVERB) {
+            close_pointwise(false);
+            Plan::Stage ts; ts.kind = 2; ts.c_in = ts.c_out = width; ts.reverb = c->node_states[sn.id.pack()];
+            plan->stages.push_back(ts);
+            prev = sn.id;
+            continue;
+        }
         if (kind == FW_NODE_BIQUAD || kind == FW_NODE_DELAY) {
             std::shared_ptr<NodeDeviceState> st = c->node_states[sn.id.pack()];
             // a delay directly after a biquad joins its pass; anything else opens a new temporal stage
@@ -316,7 +338,7 @@ static bool lower(fw_ctx* c, const Schedule& s, Plan* plan, std::string* why) {
     if (!fed_by_prev(gout, width)) { *why = "graph_out is not fed port-to-port by the end of the chain"; return false; }
     // the last stage must be pointwise when the master bus follows it, and a plan is never empty
     const bool bus = c->cfg.master_bus != 0;
-    close_pointwise(plan->stages.empty() || (bus && cur.prog.n_ops == 0 && plan->stages.back().kind == 1));
+    close_pointwise(plan->stages.empty() || (bus && cur.prog.n_ops == 0 && plan->stages.back().kind != 0));
     plan->n_sm = n_sm; plan->c_out = width;
 
     // ---- device allocations (main thread) ----
@@ -738,6 +760,20 @@ static int proc_enqueue(fw_processor* p, const float* d_in, float* d_out, uint32
         const Plan::Stage& sg = pl.stages[si];
         const bool last = si + 1 == n_stages;
         float* dst = last ? d_out : p->d_tmp[si & 1];
+        if (sg.kind == 2) {
+            NodeDeviceState& rs = *sg.reverb;
+            if (T > NodeDeviceState::kReverbMaxFrames) { g_dev_err = "conv reverb: more than 65536 frames in one call"; return FW_PROC_BAD_ARGS; }
+            ReverbCall rc{};
+            rc.in = src; rc.out = dst; rc.xh_old = rs.d_xh[rs.xh_cur]; rc.xh_new = rs.d_xh[rs.xh_cur ^ 1u]; rc.bt = rs.d_bt;
+            rc.V = V; rc.C = sg.c_in; rc.T = T; rc.L = rs.params->ir_len; rc.ir_ch = rs.params->ir_channels; rc.t_old = rs.xh_t_old; rc.pitch = rs.xh_pitch;
+            rc.zero_first = si == 0 ? zero_first_frames : 0u;
+            std::string rerr;
+            { ProfScope ps(p, 3); if (!FW_CUDA(launch_reverb(rc, p->stream, &rerr))) { if (!rerr.empty()) g_dev_err = rerr; return FW_PROC_DEVICE_ERROR; } }
+            p->launches += 2;
+            rs.xh_cur ^= 1u; rs.xh_t_old = T;
+            src = dst;
+            continue;
+        }
         if (sg.kind == 1) {
             TemporalArgs ta{};
             ta.in = src; ta.out = dst; ta.R = V * sg.c_in; ta.C = sg.c_in; ta.T = T; ta.zero_first = si == 0 ? zero_first_frames : 0u;

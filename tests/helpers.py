@@ -34,7 +34,7 @@ def run_planar(proc, x, n_out, master_bus=False):
     V, n_in, T = x.shape
     out = np.full((n_out, T) if master_bus else (V, n_out, T), np.nan, dtype=f32)
     rc, mask = proc.process_planar(np.ascontiguousarray(x), out, n_in, n_out, T)
-    assert rc == 0, rc
+    assert rc == 0, (rc, proc._lib.last_device_error())
     return out, mask
 
 

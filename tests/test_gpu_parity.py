@@ -220,3 +220,64 @@ def test_config3_shape(gpu, oracle):
     V, F, K = 256, 512, 26  # 13312 frames > D: the ring wraps inside one call
     x = synth((V, 2, F * K), 3)
     both(gpu, oracle, temporal_chain(gpu, V, 4, 12000, F), [(x, None), (x[:, :, :F * 2].copy(), None)], 2)
+
+
+# ---- FIR convolutional reverb (spec ours): bf16 operands, fp32 tensor-core accumulation -----------------------
+def reverb_ir(L, ch, seed):
+    rng = np.random.default_rng(seed)
+    h = rng.standard_normal((ch, L)) * np.exp(-6.9 * np.arange(L) / L)
+    h /= np.sqrt((h ** 2).sum(axis=1, keepdims=True))
+    return h.astype(f32)
+
+
+def norm_max_err(got, ref):
+    return float(np.max(np.abs(got.astype(np.float64) - ref.astype(np.float64))) / np.max(np.abs(ref)))
+
+
+@pytest.mark.parametrize("L,V,T,F", [(200, 5, 512, 256), (1000, 130, 1024, 512), (4096, 3, 777, 128), (64, 2, 256, 256)])
+def test_conv_reverb_vs_oracle(gpu, oracle, L, V, T, F):
+    """Tolerance (north_star): normalised max error <= 1e-5 against the oracle (bf16-rounded x and h, f64 accumulate)."""
+    from firewheel_b200 import ConvReverbNode
+    ir = reverb_ir(L, 2, L)
+    x = synth((V, 2, T), 900 + L)
+    outs = []
+    for lib in (gpu, oracle):
+        cx, proc, _ = chain(lib, 2, [(lambda: ConvReverbNode(ir), 2, 2)], voices=V, max_block=F)
+        ys = [run_planar(proc, x, 2)[0], run_planar(proc, x[:, :, ::-1].copy(), 2)[0]]  # second call: history carries over
+        outs.append(ys)
+        proc.free(); cx.update(); cx.free()
+    for yg, yo in zip(*outs):
+        assert norm_max_err(yg, yo) <= 1e-5, norm_max_err(yg, yo)
+
+
+def test_conv_reverb_full_length_vs_fft(gpu, oracle):
+    """BASELINE config[3] IR length (48000 taps, stereo IR) on a few voices; reference = f64 FFT convolution of the
+    bf16-rounded operands (the direct-form oracle would take minutes at this length)."""
+    import scipy.signal
+    from firewheel_b200 import ConvReverbNode
+    L, V, T = 48000, 6, 2048
+    ir = reverb_ir(L, 2, 7)
+    x = synth((V, 2, T * 2), 31)
+    cx, proc, _ = chain(gpu, 2, [(lambda: ConvReverbNode(ir), 2, 2)], voices=V, max_block=512)
+    y = np.concatenate([run_planar(proc, np.ascontiguousarray(x[:, :, :T]), 2)[0], run_planar(proc, np.ascontiguousarray(x[:, :, T:]), 2)[0]], axis=2)
+    proc.free(); cx.update(); cx.free()
+    rb = np.vectorize(oracle.bf16_round, otypes=[f32])
+    xb, hb = rb(x).astype(np.float64), rb(ir).astype(np.float64)
+    for v in range(V):
+        for c in range(2):
+            ref = scipy.signal.fftconvolve(xb[v, c], hb[c])[: 2 * T]
+            assert norm_max_err(y[v, c], ref) <= 1e-5, (v, c, norm_max_err(y[v, c], ref))
+
+
+def test_reverb_in_a_mixed_chain_with_bus(gpu, oracle):
+    from firewheel_b200 import ConvReverbNode
+    ir = reverb_ir(300, 2, 3)
+    V, T = 70, 512
+    x = synth((V, 2, T), 5)
+    nodes = [(lambda: VolumeNode(70.0), 2, 2), (lambda: ConvReverbNode(ir), 2, 2), (lambda: PanNode(-0.3), 2, 2)]
+    outs = []
+    for lib in (gpu, oracle):
+        cx, proc, _ = chain(lib, 2, nodes, voices=V, master_bus=True, max_block=256)
+        outs.append(run_planar(proc, x, 2, True)[0])
+        proc.free(); cx.update(); cx.free()
+    assert norm_max_err(outs[0], outs[1]) <= 1e-5
