@@ -81,9 +81,9 @@ struct TemporalArgs {
 // One call of the FIR reverb (reverb.cu): history roll + bf16 conversion, then the tcgen05 GEMM.
 struct ReverbCall {
     const float* in; float* out;        // [V][C][T] f32
-    const void* xh_old; void* xh_new;   // bf16 sample history [C*V][pitch]: H history samples, then the call's block
+    void* xh;                           // bf16 sample history [C*V][pitch]; the call's block is appended at column `cursor`
     const void* bt;                     // bf16 Toeplitz expansion of the IR [ir_ch][256][kpad]
-    uint32_t V, C, T, L, ir_ch, t_old, pitch, zero_first;
+    uint32_t V, C, T, L, ir_ch, cursor, pitch, zero_first;
 };
 
 }  // namespace fw

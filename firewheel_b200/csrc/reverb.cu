@@ -112,22 +112,32 @@ __global__ void reverb_build_toeplitz(const float* __restrict__ ir, __nv_bfloat1
     }
 }
 
-// xh_new[c*V + v][0..H) = tail of xh_old (the H most recent samples of the previous call); [H..H+T) = bf16(in[v][c][*])
-__global__ void reverb_prepare(const float* __restrict__ in, const __nv_bfloat16* __restrict__ xh_old, __nv_bfloat16* __restrict__ xh_new,
-                               uint32_t V, uint32_t C, uint32_t T, uint32_t H, uint32_t t_old, uint32_t pitch, uint32_t zero_first) {
+// xh[c*V + v][cursor + t] = bf16(in[v][c][t]) for t < T: appends the call's block behind the history (8 samples per thread)
+__global__ void reverb_prepare(const float* __restrict__ in, __nv_bfloat16* __restrict__ xh, uint32_t V, uint32_t C, uint32_t T, uint32_t cursor,
+                               uint32_t pitch, uint32_t zero_first) {
     asm volatile("griddepcontrol.wait;" ::: "memory");
     const uint32_t row = blockIdx.y;  // c * V + v
     const uint32_t c = row / V, v = row % V;
-    const __nv_bfloat16* src_old = xh_old + (size_t)row * pitch + t_old;  // H valid samples precede column H + t_old ... start at t_old
-    __nv_bfloat16* dst = xh_new + (size_t)row * pitch;
+    __nv_bfloat16* dst = xh + (size_t)row * pitch + cursor;
     const float* x = in + ((size_t)v * C + c) * T;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < H + T; i += gridDim.x * blockDim.x)
-        dst[i] = i < H ? src_old[i] : __float2bfloat16_rn((i - H) < zero_first ? 0.0f : x[i - H]);
+    const bool vec = (T % 8u) == 0 && (cursor % 8u) == 0 && (pitch % 8u) == 0 && (reinterpret_cast<uintptr_t>(in) % 16u) == 0;
+    if (vec) {
+        for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) * 8u; i < T; i += gridDim.x * blockDim.x * 8u) {
+            float4 a = __ldcs(reinterpret_cast<const float4*>(x + i)), b = __ldcs(reinterpret_cast<const float4*>(x + i + 4));
+            if (i < zero_first) { a = make_float4(0.f, 0.f, 0.f, 0.f); b = a; }  // zero_first is a multiple of the block size here
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x, a.y), p1 = __floats2bfloat162_rn(a.z, a.w), p2 = __floats2bfloat162_rn(b.x, b.y), p3 = __floats2bfloat162_rn(b.z, b.w);
+            uint4 o;
+            o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1); o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
+            *reinterpret_cast<uint4*>(dst + i) = o;
+        }
+    } else {
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < T; i += gridDim.x * blockDim.x) dst[i] = __float2bfloat16_rn(i < zero_first ? 0.0f : x[i]);
+    }
 }
 
 struct ReverbGemmArgs {
     float* out;                   // [V][C][T]
-    uint32_t V, C, T, Lr, H, ir_ch, num_kb, debug;
+    uint32_t V, C, T, Lr, cursor, ir_ch, num_kb, debug;
 };
 
 __global__ void __launch_bounds__(256, 1) reverb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const ReverbGemmArgs a) {
@@ -164,7 +174,7 @@ __global__ void __launch_bounds__(256, 1) reverb_gemm_kernel(const __grid_consta
         // ===== TMA producer =====
         asm volatile("griddepcontrol.wait;" ::: "memory");  // the history buffer is written by reverb_prepare just before us
         if (lane == 0) {
-            const int32_t col_a0 = (int32_t)(a.H + n0) - (int32_t)a.Lr;  // multiple of 8 elements = 16 bytes
+            const int32_t col_a0 = (int32_t)(a.cursor + n0) - (int32_t)a.Lr;  // multiple of 8 elements = 16 bytes
             const int32_t row_a = (int32_t)(c * a.V + v0), row_b = (int32_t)((c % a.ir_ch) * RV_BN);
             for (uint32_t kb = 0; kb < num_kb; ++kb) {
                 const uint32_t s = kb % RV_STAGES, ph = (kb / RV_STAGES) & 1u;
@@ -256,9 +266,10 @@ cudaError_t launch_reverb_build(const float* d_ir, void* d_bt, uint32_t L, uint3
     return cudaGetLastError();
 }
 
-// One call: roll the history, convert the block to bf16, run the GEMM. xh_old/xh_new: [C*V][pitch] bf16.
+// One call: append the block (bf16) behind the history at `cursor`, run the GEMM over windows ending in it.
+// The caller owns the cursor policy (compaction when the buffer is full); cursor is a multiple of 8 and >= Lr.
 cudaError_t launch_reverb(const ReverbCall& rc, cudaStream_t st, std::string* err) {
-    const uint32_t H = reverb_hist(rc.L), kpad = reverb_kpad(rc.L);
+    const uint32_t kpad = reverb_kpad(rc.L);
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(reverb_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RV_SMEM_BYTES);
@@ -266,20 +277,20 @@ cudaError_t launch_reverb(const ReverbCall& rc, cudaStream_t st, std::string* er
         attr_set = true;
     }
     {
-        dim3 grid((H + rc.T + 255) / 256 < 64 ? (H + rc.T + 255) / 256 : 64, rc.C * rc.V);
-        reverb_prepare<<<grid, 256, 0, st>>>(rc.in, static_cast<const __nv_bfloat16*>(rc.xh_old), static_cast<__nv_bfloat16*>(rc.xh_new), rc.V, rc.C, rc.T, H, rc.t_old,
-                                            rc.pitch, rc.zero_first);
+        const uint32_t per_block = 256 * 8;
+        dim3 grid((rc.T + per_block - 1) / per_block < 32 ? (rc.T + per_block - 1) / per_block : 32, rc.C * rc.V);
+        reverb_prepare<<<grid, 256, 0, st>>>(rc.in, static_cast<__nv_bfloat16*>(rc.xh), rc.V, rc.C, rc.T, rc.cursor, rc.pitch, rc.zero_first);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }
     CUtensorMap tm_a, tm_b;
-    if (!make_map_bf16_2d(&tm_a, rc.xh_new, (uint64_t)H + rc.T, (uint64_t)rc.C * rc.V, rc.pitch, RV_BK, RV_BM) ||
+    if (!make_map_bf16_2d(&tm_a, rc.xh, (uint64_t)rc.cursor + rc.T, (uint64_t)rc.C * rc.V, rc.pitch, RV_BK, RV_BM) ||
         !make_map_bf16_2d(&tm_b, rc.bt, kpad, (uint64_t)rc.ir_ch * RV_BN, kpad, RV_BK, RV_BN)) {
         if (err) *err = "cuTensorMapEncodeTiled failed";
         return cudaErrorInvalidValue;
     }
     static const uint32_t dbg = getenv("FW_REVERB_DEBUG") ? (uint32_t)atoi(getenv("FW_REVERB_DEBUG")) : 0u;
-    ReverbGemmArgs ga{rc.out, rc.V, rc.C, rc.T, reverb_lr(rc.L), H, rc.ir_ch, kpad / RV_BK, dbg};
+    ReverbGemmArgs ga{rc.out, rc.V, rc.C, rc.T, reverb_lr(rc.L), rc.cursor, rc.ir_ch, kpad / RV_BK, dbg};
     dim3 grid((rc.T + RV_BN - 1) / RV_BN, (rc.V + RV_BM - 1) / RV_BM, rc.C);
     reverb_gemm_kernel<<<grid, 256, RV_SMEM_BYTES, st>>>(tm_a, tm_b, ga);
     return cudaGetLastError();

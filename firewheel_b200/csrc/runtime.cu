@@ -81,7 +81,7 @@ struct NodeDeviceState {
     float* d_ring = nullptr;     // delay  [V*channels][D]
     uint32_t ring_pos = 0;       // stream-side cursor into the ring
     // conv reverb: Toeplitz-expanded IR and the ping-pong bf16 sample history (reverb.cu)
-    void* d_bt = nullptr; void* d_xh[2] = {nullptr, nullptr}; uint32_t xh_cur = 0, xh_t_old = 0, xh_pitch = 0;
+    void* d_bt = nullptr; void* d_xh[2] = {nullptr, nullptr}; uint32_t xh_cur = 0, xh_cursor = 0, xh_pitch = 0;  // cursor: where the next block is appended
     static constexpr uint32_t kReverbMaxFrames = 65536;  // longest call the history buffers are sized for
     ~NodeDeviceState() {
         cudaSetDevice(device);
@@ -110,7 +110,7 @@ struct NodeDeviceState {
             if (!d_ring) return false;
         } else if (kind == FW_NODE_CONV_REVERB) {
             const uint32_t L = params->ir_len, ich = params->ir_channels, kpad = reverb_kpad(L);
-            xh_pitch = reverb_hist(L) + kReverbMaxFrames;
+            xh_pitch = reverb_hist(L) + kReverbMaxFrames; xh_cursor = reverb_hist(L);
             d_bt = dev_alloc<uint16_t>((size_t)ich * 256 * kpad, false);
             d_xh[0] = dev_alloc<uint16_t>((size_t)V * channels * xh_pitch);  // zero history
             d_xh[1] = dev_alloc<uint16_t>((size_t)V * channels * xh_pitch);
@@ -764,13 +764,20 @@ static int proc_enqueue(fw_processor* p, const float* d_in, float* d_out, uint32
             NodeDeviceState& rs = *sg.reverb;
             if (T > NodeDeviceState::kReverbMaxFrames) { g_dev_err = "conv reverb: more than 65536 frames in one call"; return FW_PROC_BAD_ARGS; }
             ReverbCall rc{};
-            rc.in = src; rc.out = dst; rc.xh_old = rs.d_xh[rs.xh_cur]; rc.xh_new = rs.d_xh[rs.xh_cur ^ 1u]; rc.bt = rs.d_bt;
-            rc.V = V; rc.C = sg.c_in; rc.T = T; rc.L = rs.params->ir_len; rc.ir_ch = rs.params->ir_channels; rc.t_old = rs.xh_t_old; rc.pitch = rs.xh_pitch;
+            const uint32_t H = reverb_hist(rs.params->ir_len);
+            if (rs.xh_cursor + T > rs.xh_pitch || (rs.xh_cursor & 7u)) {  // buffer full (or cursor off the 16-byte TMA grid after an odd-length call):
+                // carry the H most recent samples to the front of the other buffer
+                if (!FW_CUDA(cudaMemcpy2DAsync(rs.d_xh[rs.xh_cur ^ 1u], (size_t)rs.xh_pitch * 2, static_cast<const uint16_t*>(rs.d_xh[rs.xh_cur]) + (rs.xh_cursor - H),
+                                               (size_t)rs.xh_pitch * 2, (size_t)H * 2, (size_t)V * sg.c_in, cudaMemcpyDeviceToDevice, p->stream))) return FW_PROC_DEVICE_ERROR;
+                rs.xh_cur ^= 1u; rs.xh_cursor = H;
+            }
+            rc.in = src; rc.out = dst; rc.xh = rs.d_xh[rs.xh_cur]; rc.bt = rs.d_bt;
+            rc.V = V; rc.C = sg.c_in; rc.T = T; rc.L = rs.params->ir_len; rc.ir_ch = rs.params->ir_channels; rc.cursor = rs.xh_cursor; rc.pitch = rs.xh_pitch;
             rc.zero_first = si == 0 ? zero_first_frames : 0u;
             std::string rerr;
             { ProfScope ps(p, 3); if (!FW_CUDA(launch_reverb(rc, p->stream, &rerr))) { if (!rerr.empty()) g_dev_err = rerr; return FW_PROC_DEVICE_ERROR; } }
             p->launches += 2;
-            rs.xh_cur ^= 1u; rs.xh_t_old = T;
+            rs.xh_cursor += T;
             src = dst;
             continue;
         }
