@@ -45,6 +45,9 @@ WORKLOADS = {
     "c4": dict(voices=256, ch=2, block=512, blocks=16, bus=False, bytes_per_sample=8.0, kernel_class=3, ir_len=48000,
                kernel="reverb_gemm_kernel (tcgen05.mma kind::f16 M128 N256 K16, TMEM accumulators, TMA 128B-swizzle operands)",
                desc="c4: 256 stereo voices/GPU, FIR convolutional reverb, 48000-tap stereo IR, bf16 tcgen05, 512-frame blocks, 16 blocks/step"),
+    "c5": dict(voices=8192, ch=2, block=512, blocks=2, bus=True, bytes_per_sample=8.0, kernel_class=3, ir_len=48000,
+               kernel="reverb_gemm_kernel (tcgen05) + biquad_delay_lanes; chain_kernel before and after",
+               desc="c5: 8192 stereo voices/GPU (65536 over 8), gain->pan->4-stage biquad->48000-tap FIR reverb->master-bus sum, 512-frame blocks, 2 blocks/step"),
 }
 
 
@@ -79,12 +82,17 @@ def build_graph(fw, lib, workload, V, block, device, seed):
         nodes = [g.add_node(2, 2, fw.VolumeNode(100.0)), g.add_node(2, 2, fw.PanNode(0.0))]
         g.set_percent_volume(nodes[0], pct)
         g.set_pan(nodes[1], pan)
-    elif workload == "c4":
+    elif workload in ("c4", "c5"):
         L = w["ir_len"]
         rng = np.random.default_rng(0x1200)
         ir = rng.standard_normal((2, L)) * np.exp(-6.9 * np.arange(L) / L)
         ir = (ir / np.sqrt((ir ** 2).sum(axis=1, keepdims=True))).astype(F32)
         nodes = [g.add_node(2, 2, fw.ConvReverbNode(ir))]
+        if workload == "c5":
+            pct, pan = voice_params(V, seed)
+            pre = [g.add_node(2, 2, fw.VolumeNode(100.0)), g.add_node(2, 2, fw.PanNode(0.0)), g.add_node(2, 2, fw.BiquadNode(4))]
+            g.set_percent_volume(pre[0], pct); g.set_pan(pre[1], pan); g.set_biquad_coeffs(pre[2], biquad_params(fw, lib, V, seed))
+            nodes = pre + nodes
     else:
         nodes = [g.add_node(2, 2, fw.BiquadNode(4)), g.add_node(2, 2, fw.DelayNode(12000))]
         g.set_biquad_coeffs(nodes[0], biquad_params(fw, lib, V, seed))
@@ -216,7 +224,7 @@ def run_reference(args, rank, world):
     n_blocks = 32  # bounded sample of the step (the full step is w["blocks"] blocks)
     if args.workload == "c3":
         n_blocks = 4
-    if args.workload == "c4":
+    if args.workload in ("c4", "c5"):
         V, n_blocks = max(cores, 2) * 1, 1  # direct-form FIR on the CPU: 96 kflop per output sample
     val, sec_per_step = oracle_rate(V, w["block"], n_blocks, cores, steps=args.steps, warmup=args.warmup, workload=args.workload)
     sample = f"{V} voices x {n_blocks} of {w['blocks']} blocks per step, {cores} replica threads over disjoint voice ranges"
@@ -346,7 +354,7 @@ def run_b200(args, rank, world, local_rank):
     # ---- roofline of the dominant kernel (fused chain + bus), CUDA events on the launching stream ----
     peak, peak_src = peaks()
     kc = w["kernel_class"]
-    chain_ms = prof_ms[kc] / max(prof_n[kc], 1)
+    chain_ms = prof_ms[kc] / max(args.steps, 1)  # all launches of the dominant kernel class in one step
     # c2 reads V*C*T f32 and writes the C*T bus; c3 moves in + out + delay-ring read + write = 16 B/sample
     algo_bytes = 4 * C * T * (V + 1) if args.workload == "c2" else int(w["bytes_per_sample"] * V * C * T)
     achieved = algo_bytes / (chain_ms * 1e-3) / 1e9 if chain_ms > 0 else 0.0
@@ -357,14 +365,14 @@ def run_b200(args, rank, world, local_rank):
             traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    if args.workload == "c4":  # tensor-pipe roofline: dense direct-form count 2*L flop per output sample
+    if args.workload in ("c4", "c5"):  # tensor-pipe roofline: dense direct-form count 2*L flop per output sample
         pk = ROOT / "MEASURED_PEAKS.json"
         peak, peak_src = (float(json.loads(pk.read_text())["bf16_tflops"]), "measured (MEASURED_PEAKS.json bf16_tflops, burst)") if pk.exists() else (1590.0, "fallback (B200_PROFILING.md 1.59 PFLOP/s)")
         flops = 2.0 * w["ir_len"] * V * C * T
         achieved = flops / (chain_ms * 1e-3) / 1e12 if chain_ms > 0 else 0.0
-    roofline = {"bound": "hbm" if args.workload != "c4" else "tensor", "kernel": w["kernel"], "achieved": achieved, "peak": peak, "unit": "GB/s" if args.workload != "c4" else "TFLOP/s",
+    roofline = {"bound": "hbm" if args.workload not in ("c4", "c5") else "tensor", "kernel": w["kernel"], "achieved": achieved, "peak": peak, "unit": "GB/s" if args.workload not in ("c4", "c5") else "TFLOP/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "kernel_ms": chain_ms,
-                "algorithmic_bytes_per_launch": algo_bytes, "algorithmic_flops_per_launch": (2.0 * w["ir_len"] * V * C * T) if args.workload == "c4" else None,
+                "algorithmic_bytes_per_launch": algo_bytes, "algorithmic_flops_per_launch": (2.0 * w["ir_len"] * V * C * T) if args.workload in ("c4", "c5") else None,
                 "step_share": {"control_ms": prof_ms[0] / max(prof_n[0], 1), "chain_ms": prof_ms[1] / max(prof_n[1], 1),
                                "combine_ms": prof_ms[2] / max(prof_n[2], 1), "temporal_ms": prof_ms[3] / max(prof_n[3], 1)}}
 
@@ -372,14 +380,14 @@ def run_b200(args, rank, world, local_rank):
     if rank == 0:
         n_blocks = 64
         n_blocks = 64 if args.workload == "c2" else 2
-        Vc = V if args.workload != "c4" else 2  # the direct-form FIR oracle needs ~0.2 s per voice-block
-        if args.workload == "c4":
+        Vc = V if args.workload not in ("c4", "c5") else 2  # the direct-form FIR oracle needs ~0.2 s per voice-block
+        if args.workload in ("c4", "c5"):
             n_blocks = 1
         rate, sec = oracle_rate(Vc, F, n_blocks, 1, steps=1, warmup=0, workload=args.workload)
-        if sec < 2.0 and args.workload != "c4":  # size the sample towards ~10 s of CPU work
+        if sec < 2.0 and args.workload not in ("c4", "c5"):  # size the sample towards ~10 s of CPU work
             n_blocks = int(min(KB * 8, max(n_blocks, n_blocks * 10.0 / max(sec, 1e-3))))
             rate, sec = oracle_rate(Vc, F, n_blocks, 1, steps=1, warmup=0, workload=args.workload)
-        elif args.workload == "c4" and sec < 5.0:
+        elif args.workload in ("c4", "c5") and sec < 5.0:
             Vc = int(min(64, max(2, Vc * 10.0 / max(sec, 1e-3))))
             rate, sec = oracle_rate(Vc, F, n_blocks, 1, steps=1, warmup=0, workload=args.workload)
         cpu = {"value": rate, "unit": "samples/s", "cores": 1, "kind": "port",

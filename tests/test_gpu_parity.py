@@ -281,3 +281,26 @@ def test_reverb_in_a_mixed_chain_with_bus(gpu, oracle):
         outs.append(run_planar(proc, x, 2, True)[0])
         proc.free(); cx.update(); cx.free()
     assert norm_max_err(outs[0], outs[1]) <= 1e-5
+
+
+def test_config5_chain_shape(gpu, oracle):
+    """BASELINE config[4] voice graph at reduced size: gain -> pan -> 4-stage biquad -> FIR reverb -> master bus.
+    Everything up to the reverb is bit-exact, so the bus differs from the oracle only by the reverb's fp32 accumulation."""
+    from firewheel_b200 import BiquadNode, ConvReverbNode
+    V, F, T, L = 96, 256, 1024, 600
+    ir = reverb_ir(L, 2, 17)
+    co = biquad_coeffs(gpu, V, 4, 23)
+    rng = np.random.default_rng(8)
+    pct = (25 + 75 * rng.random(V)).astype(f32); pan = rng.uniform(-1, 1, V).astype(f32)
+    nodes = [(lambda: VolumeNode(100.0), 2, 2), (lambda: PanNode(0.0), 2, 2), (lambda: BiquadNode(4), 2, 2), (lambda: ConvReverbNode(ir), 2, 2)]
+
+    def setup(cx, ids):
+        cx.graph.set_percent_volume(ids[0], pct); cx.graph.set_pan(ids[1], pan); cx.graph.set_biquad_coeffs(ids[2], co)
+    x = synth((V, 2, T), 12)
+    outs = []
+    for lib in (gpu, oracle):
+        cx, proc, _ = chain(lib, 2, nodes, voices=V, master_bus=True, max_block=F, setup=setup)
+        outs.append([run_planar(proc, x, 2, True)[0], run_planar(proc, x, 2, True)[0]])
+        proc.free(); cx.update(); cx.free()
+    for yg, yo in zip(*outs):
+        assert norm_max_err(yg, yo) <= 1e-5, norm_max_err(yg, yo)
