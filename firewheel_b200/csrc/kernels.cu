@@ -87,20 +87,24 @@ __global__ void __launch_bounds__(128) control_kernel(const __grid_constant__ Co
     uint32_t steady = 0xffffffffu, k = 0, last_modes = 0;
     float last_vals[kMaxSmoothers];
     for (uint32_t s = 0; s < NS; ++s) last_vals[s] = 0.0f;
+    uint64_t last_sum_mask[kMaxSumMasks];
+    for (int s = 0; s < kMaxSumMasks; ++s) last_sum_mask[s] = 0;
 
     for (; k < n_blocks; ++k) {
         if (k >= a.rec.kt_max) { *a.rec.error = 1; break; }
         const uint32_t frames = min(F, a.frames - k * F);
-        bool changed = false;
+        bool changed = false;  // smoother state moved during this block
+        const uint64_t flags0 = flags;  // the block is a pure function of (flags, smoother state): equal at both ends => it replays
         uint32_t modes = 0;
         for (uint32_t n = 0; n < tb.n_nodes; ++n) {
             const CtlNode nd = tb.nodes[n];
             uint64_t in_mask = 0;
             for (uint32_t i = 0; i < nd.n_in; ++i) {  // schedule.rs:305-320
                 const uint64_t bit = 1ull << tb.in_buf[nd.in_off + i];
-                if (tb.in_clear[nd.in_off + i] && !(flags & bit)) { flags |= bit; changed = true; }
+                if (tb.in_clear[nd.in_off + i]) flags |= bit;
                 if (flags & bit) in_mask |= 1ull << i;
             }
+            if (nd.mask_slot) { a.rec.sum_masks[((size_t)k * a.rec.n_sum_masks + (nd.mask_slot - 1)) * V + v] = in_mask; last_sum_mask[nd.mask_slot - 1] = in_mask; }
             uint64_t out_mask = 0;  // processor.rs:233 NONE_SILENT
             switch (nd.kind) {
                 case FW_NODE_VOLUME: {
@@ -162,18 +166,18 @@ __global__ void __launch_bounds__(128) control_kernel(const __grid_constant__ Co
             if (n + 1 == tb.n_nodes) gout_mask = in_mask;  // graph_out is scheduled last (compiler.rs:291)
             for (uint32_t i = 0; i < nd.n_out; ++i) {  // schedule.rs:338-341
                 const uint64_t bit = 1ull << tb.out_buf[nd.out_off + i];
-                const uint64_t nf = (out_mask >> i) & 1ull ? (flags | bit) : (flags & ~bit);
-                if (nf != flags) { flags = nf; changed = true; }
+                flags = (out_mask >> i) & 1ull ? (flags | bit) : (flags & ~bit);
             }
         }
         a.rec.modes[(size_t)k * V + v] = modes;
         last_modes = modes;
-        if (!changed) { steady = k; break; }  // nothing moved: every later block replays this record
+        if (!changed && flags == flags0) { steady = k; break; }  // nothing moved: every later block replays this record
     }
     if (steady == 0xffffffffu) steady = (k == 0 ? 0 : min(k, n_blocks) - 1);
     a.rec.steady_k[v] = steady;
     a.rec.st_modes[v] = last_modes;  // the record of block `steady`, flattened
     for (uint32_t s = 0; s < NS; ++s) a.rec.st_vals[(size_t)s * V + v] = last_vals[s];
+    for (uint32_t s = 0; s < a.rec.n_sum_masks; ++s) a.rec.st_sum_masks[(size_t)s * V + v] = last_sum_mask[s];
     a.rec.gout_mask[v] = gout_mask;
     for (uint32_t s = 0; s < NS; ++s) { tb.sm_input[s][v] = sm[s].input; tb.sm_last[s][v] = sm[s].last; tb.sm_status[s][v] = sm[s].status; }
     a.flags[v] = flags;
@@ -295,11 +299,11 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) chain_kernel(ChainArg
     if (a.in_from_prev_kernel) pdl_wait();
     float x[kVPW][2][VEC];
     if (full) {
-        const float* p = a.in + (size_t)v0 * CIN * T + t;
+        const float* p[2] = {a.in_ch[0] + (size_t)v0 * a.in_vstride + t, a.in_ch[CIN - 1] + (size_t)v0 * a.in_vstride + t};
 #pragma unroll
         for (int j = 0; j < kVPW; ++j) {
 #pragma unroll
-            for (int c = 0; c < CIN; ++c) { VecT<VEC>::load(p, x[j][c]); p += T; }
+            for (int c = 0; c < CIN; ++c) { VecT<VEC>::load(p[c], x[j][c]); p[c] += a.in_vstride; }
             if (CIN == 1) {
 #pragma unroll
                 for (int i = 0; i < VEC; ++i) x[j][1][i] = 0.0f;
@@ -314,7 +318,7 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) chain_kernel(ChainArg
             for (int c = 0; c < 2; ++c) {
 #pragma unroll
                 for (int i = 0; i < VEC; ++i) x[j][c][i] = 0.0f;
-                if (c < CIN && t_ok && v < V && !zero_in) VecT<VEC>::load(a.in + ((size_t)v * CIN + c) * T + t, x[j][c]);
+                if (c < CIN && t_ok && v < V && !zero_in) VecT<VEC>::load(a.in_ch[c < CIN ? c : 0] + (size_t)v * a.in_vstride + t, x[j][c]);
             }
         }
     }
@@ -405,18 +409,18 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) chain_kernel(ChainArg
 
     if (!BUS) {
         if (full) {
-            float* q = a.out + (size_t)v0 * c_out * T + t;
+            float* q[2] = {a.out_ch[0] + (size_t)v0 * a.out_vstride + t, a.out_ch[1] + (size_t)v0 * a.out_vstride + t};
 #pragma unroll
             for (int j = 0; j < kVPW; ++j)
 #pragma unroll
-                for (int c = 0; c < 2; ++c) if (c < c_out) { VecT<VEC>::store(q, x[j][c]); q += T; }
+                for (int c = 0; c < 2; ++c) if (c < c_out) { VecT<VEC>::store(q[c], x[j][c]); q[c] += a.out_vstride; }
         } else {
 #pragma unroll
             for (int j = 0; j < kVPW; ++j) {
                 const uint32_t v = v0 + j;
                 if (v < V && t_ok) {
 #pragma unroll
-                    for (int c = 0; c < 2; ++c) if (c < c_out) VecT<VEC>::store(a.out + ((size_t)v * c_out + c) * T + t, x[j][c]);
+                    for (int c = 0; c < 2; ++c) if (c < c_out) VecT<VEC>::store(a.out_ch[c] + (size_t)v * a.out_vstride + t, x[j][c]);
                 }
             }
         }
@@ -460,6 +464,58 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) chain_kernel(ChainArg
             VecT<VEC>::store(a.out + ((size_t)blockIdx.y * c_out + c) * T + t, p[0]);
         }
     }
+}
+
+// K-sum: multi-port SumNode over pool buffers (generic lowering). sum.rs:52-56: all inputs flagged silent -> outputs
+// cleared to +0.0 (flagged buffers hold +-0.0, and -0.0 + -0.0 would give -0.0); sum.rs:69-110: ports 2-4 add left to
+// right unconditionally; sum.rs:111-133: ports >= 5 start from port 0 and skip ports flagged silent.
+template <int VEC>
+__global__ void __launch_bounds__(128) sum_kernel(const __grid_constant__ SumArgs a) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) * VEC, v = blockIdx.y, T = a.frames, V = a.num_voices;
+    if (t >= T) return;
+    const size_t off = (size_t)v * T + t;
+    uint64_t mask = 0;
+    if (a.mask_slot >= 0) {
+        const uint32_t k = t / a.block_frames, sk = a.rec.steady_k[v];
+        mask = k >= sk ? a.rec.st_sum_masks[(size_t)a.mask_slot * V + v] : a.rec.sum_masks[((size_t)k * a.rec.n_sum_masks + a.mask_slot) * V + v];
+    }
+    float acc[VEC];
+    if (a.mask_slot >= 0 && (mask & a.all_mask) == a.all_mask) {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) acc[i] = 0.0f;
+        VecT<VEC>::store(a.out + off, acc);
+        return;
+    }
+    VecT<VEC>::load(a.in[0] + off, acc);
+    for (uint32_t p = 1; p < a.n_ports; ++p) {
+        if (a.skip_silent && ((mask >> a.mask_bit[p]) & 1ull)) continue;
+        float x[VEC];
+        VecT<VEC>::load(a.in[p] + off, x);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) acc[i] = __fadd_rn(acc[i], x[i]);
+    }
+    VecT<VEC>::store(a.out + off, acc);
+}
+
+// K-silence-fix (generic lowering): the reference's non-fused node bodies write +0.0 to an output channel whose input
+// channel(s) are flagged silent (volume.rs:131-135, hard_clip.rs:78-82, mono_to_stereo.rs:41-44, stereo_to_mono.rs:41-47)
+// where the arithmetic on the flagged +-0.0 samples could give -0.0. Rewrites `out` with +0.0 for every (voice, block)
+// whose input mask contains all bits of `test`.
+template <int VEC>
+__global__ void __launch_bounds__(128) silence_fix_kernel(const __grid_constant__ SilenceFixArgs a) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) * VEC, v = blockIdx.y, T = a.frames, V = a.num_voices;
+    if (t >= T) return;
+    const uint32_t k = t / a.block_frames, sk = a.rec.steady_k[v];
+    const uint64_t mask = k >= sk ? a.rec.st_sum_masks[(size_t)a.mask_slot * V + v] : a.rec.sum_masks[((size_t)k * a.rec.n_sum_masks + a.mask_slot) * V + v];
+    if ((mask & a.test) != a.test) return;
+    float z[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) z[i] = 0.0f;
+    VecT<VEC>::store(a.out + (size_t)v * T + t, z);
 }
 
 // K-combine: radix-16 levels of the same balanced tree over partial buses [n_in][rows][T] -> [ceil(n_in/16)][rows][T].
@@ -577,7 +633,9 @@ static cudaError_t launch_chain_t(const ChainArgs& a, bool bus, cudaStream_t st)
     return launch_chain_v<VEC, CIN, 8, 8, 2>(a, bus, st);
 }
 cudaError_t launch_chain(const ChainArgs& a, bool bus, cudaStream_t st) {
-    const bool vec4 = (a.frames % 4 == 0) && (a.block_frames % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.in) | reinterpret_cast<uintptr_t>(a.out)) % 16 == 0);
+    const uintptr_t al = reinterpret_cast<uintptr_t>(a.in_ch[0]) | reinterpret_cast<uintptr_t>(a.in_ch[1]) | reinterpret_cast<uintptr_t>(a.out_ch[0]) |
+                         reinterpret_cast<uintptr_t>(a.out_ch[1]) | reinterpret_cast<uintptr_t>(a.out) | (uintptr_t)((a.in_vstride | a.out_vstride) * 4);
+    const bool vec4 = (a.frames % 4 == 0) && (a.block_frames % 4 == 0) && (al % 16 == 0);
     if (a.prog.c_in == 2) return vec4 ? launch_chain_t<4, 2>(a, bus, st) : launch_chain_t<1, 2>(a, bus, st);
     return vec4 ? launch_chain_t<4, 1>(a, bus, st) : launch_chain_t<1, 1>(a, bus, st);
 }
@@ -588,6 +646,18 @@ cudaError_t launch_combine(const float* pin, float* pout, uint32_t n_in, uint32_
     const uint32_t n_out = (n_in + 15) / 16;
     if (vec4) return launch_pdl(combine_kernel<4>, dim3((T / 4 + 127) / 128, rows, n_out), dim3(128), st, pin, pout, n_in, rows, T);
     return launch_pdl(combine_kernel<1>, dim3((T + 127) / 128, rows, n_out), dim3(128), st, pin, pout, n_in, rows, T);
+}
+cudaError_t launch_sum(const SumArgs& a, cudaStream_t st) {
+    uintptr_t al = reinterpret_cast<uintptr_t>(a.out);
+    for (uint32_t p = 0; p < a.n_ports; ++p) al |= reinterpret_cast<uintptr_t>(a.in[p]);
+    const bool vec4 = (a.frames % 4 == 0) && (a.block_frames % 4 == 0) && (al % 16 == 0);
+    if (vec4) return launch_pdl(sum_kernel<4>, dim3((a.frames / 4 + 127) / 128, a.num_voices), dim3(128), st, a);
+    return launch_pdl(sum_kernel<1>, dim3((a.frames + 127) / 128, a.num_voices), dim3(128), st, a);
+}
+cudaError_t launch_silence_fix(const SilenceFixArgs& a, cudaStream_t st) {
+    const bool vec4 = (a.frames % 4 == 0) && (a.block_frames % 4 == 0) && (reinterpret_cast<uintptr_t>(a.out) % 16 == 0);
+    if (vec4) return launch_pdl(silence_fix_kernel<4>, dim3((a.frames / 4 + 127) / 128, a.num_voices), dim3(128), st, a);
+    return launch_pdl(silence_fix_kernel<1>, dim3((a.frames + 127) / 128, a.num_voices), dim3(128), st, a);
 }
 cudaError_t launch_deinterleave(const float* inter, float* planar, uint32_t V, uint32_t C, uint32_t T, cudaStream_t st) {
     const size_t n = (size_t)V * C * T; if (n == 0) return cudaSuccess;

@@ -16,6 +16,7 @@ constexpr int kMaxChainOps = 16;
 constexpr int kMaxSmoothers = 16;   // 2 mode bits each in a 32-bit record word
 constexpr int kMaxCtlNodes = 64;
 constexpr int kMaxCtlPorts = 512;
+constexpr int kMaxSumMasks = 32;    // generic lowering: nodes whose data-plane body depends on the per-block input silence mask
 
 enum SmStatus : uint32_t { SM_INACTIVE = 0, SM_ACTIVE = 1, SM_DEACTIVATING = 2 };   // smoother.rs:29-39
 enum RecMode : uint32_t { REC_CONST = 0, REC_CLEAR = 1, REC_CURVE = 2 };
@@ -25,7 +26,7 @@ struct ChainOp { uint32_t kind; int32_t sm0, sm1; float f0; };
 struct ChainProgram { uint32_t n_ops, c_in, c_out, pad; ChainOp ops[kMaxChainOps]; };
 
 struct CtlNode {
-    uint8_t kind, n_in, n_out, pad;
+    uint8_t kind, n_in, n_out, mask_slot;  // mask_slot: 1 + index into Records::sum_masks, 0 = none
     uint16_t in_off, out_off;   // into in_buf / in_clear / out_buf
     int16_t sm0, sm1;           // smoother indices (-1: none)
 };
@@ -49,6 +50,8 @@ struct CtlTables {
 struct Records {
     uint32_t* modes; float* vals; float* curves; uint32_t* steady_k; uint64_t* gout_mask; uint32_t* error;
     uint32_t* st_modes; float* st_vals;
+    uint64_t* sum_masks; uint64_t* st_sum_masks;  // [k][slot][v] and the steady record [slot][v]
+    uint32_t n_sum_masks, pad_;
     uint32_t kt_max, n_smoothers;
 };
 
@@ -61,8 +64,11 @@ struct ControlArgs {
 };
 
 struct ChainArgs {
-    const float* in;       // [V][c_in][T]
-    float* out;            // bus: partial bus [G][c_out][T]; else [V][c_out][T]
+    // Channel c of voice v starts at in_ch[c] + v * in_vstride (floats). A staged chain reads [V][c_in][T]
+    // (in_ch[c] = base + c*T, in_vstride = c_in*T); the generic lowering reads pool buffers [V][T] (in_vstride = T).
+    const float* in_ch[2]; float* out_ch[2];
+    uint64_t in_vstride, out_vstride;
+    float* out;            // bus variant only: partial bus [G][c_out][T]
     uint32_t num_voices, frames, block_frames, zero_first_block;
     uint32_t in_from_prev_kernel, pad0, pad1, pad2;  // `in` is produced by the preceding kernel: wait before the loads
     Records rec;
@@ -76,6 +82,7 @@ struct TemporalArgs {
     uint32_t ns; const float* coeffs;  // biquad: [R / C][ns][5] = {b0,b1,b2,a1,a2}; ns == 0: no biquad
     float* state;                  // [R][8][2] = {s1, s2}
     uint32_t D; float* ring; uint32_t pos;  // delay: ring [R][D], D == 0: no delay
+    uint32_t srow_mul, srow_add;   // state / ring row of data row r = r * srow_mul + srow_add (1, 0 for [V][C][T] input)
 };
 
 // One call of the FIR reverb (reverb.cu): history roll + bf16 conversion, then the tcgen05 GEMM.
@@ -84,6 +91,25 @@ struct ReverbCall {
     void* xh;                           // bf16 sample history [C*V][pitch]; the call's block is appended at column `cursor`
     const void* bt;                     // bf16 Toeplitz expansion of the IR [ir_ch][256][kpad]
     uint32_t V, C, T, L, ir_ch, cursor, pitch, zero_first;
+    uint32_t chan_base;                 // history rows / IR channel of data channel c are (chan_base + c)
+};
+
+// Multi-port SumNode on pool buffers (sum.rs:69-133): out = in[0] + in[1] + ... strictly left to right.
+struct SumArgs {
+    const float* in[64]; float* out;   // rows [V][T]
+    uint8_t mask_bit[64];              // input index (port * n_out + ch) of in[p] inside the node's silence mask
+    uint32_t n_ports, num_voices, frames, block_frames;
+    int32_t mask_slot;                 // index into Records::sum_masks
+    uint32_t skip_silent;              // ports >= 5: silent ports are skipped (sum.rs:118-131)
+    uint64_t all_mask;                 // all node inputs: every bit set -> outputs cleared (sum.rs:52-56)
+    Records rec;
+};
+
+// Rewrite one pool buffer with +0.0 wherever the node's input silence mask contains `test` (see silence_fix_kernel).
+struct SilenceFixArgs {
+    float* out; uint64_t test;
+    uint32_t num_voices, frames, block_frames; int32_t mask_slot;
+    Records rec;
 };
 
 }  // namespace fw

@@ -114,11 +114,11 @@ __global__ void reverb_build_toeplitz(const float* __restrict__ ir, __nv_bfloat1
 
 // xh[c*V + v][cursor + t] = bf16(in[v][c][t]) for t < T: appends the call's block behind the history (8 samples per thread)
 __global__ void reverb_prepare(const float* __restrict__ in, __nv_bfloat16* __restrict__ xh, uint32_t V, uint32_t C, uint32_t T, uint32_t cursor,
-                               uint32_t pitch, uint32_t zero_first) {
+                               uint32_t pitch, uint32_t zero_first, uint32_t chan_base) {
     asm volatile("griddepcontrol.wait;" ::: "memory");
     const uint32_t row = blockIdx.y;  // c * V + v
     const uint32_t c = row / V, v = row % V;
-    __nv_bfloat16* dst = xh + (size_t)row * pitch + cursor;
+    __nv_bfloat16* dst = xh + ((size_t)chan_base * V + row) * pitch + cursor;
     const float* x = in + ((size_t)v * C + c) * T;
     const bool vec = (T % 8u) == 0 && (cursor % 8u) == 0 && (pitch % 8u) == 0 && (reinterpret_cast<uintptr_t>(in) % 16u) == 0;
     if (vec) {
@@ -137,7 +137,7 @@ __global__ void reverb_prepare(const float* __restrict__ in, __nv_bfloat16* __re
 
 struct ReverbGemmArgs {
     float* out;                   // [V][C][T]
-    uint32_t V, C, T, Lr, cursor, ir_ch, num_kb, debug;
+    uint32_t V, C, T, Lr, cursor, ir_ch, num_kb, debug, chan_base;
 };
 
 __global__ void __launch_bounds__(256, 1) reverb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const ReverbGemmArgs a) {
@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(256, 1) reverb_gemm_kernel(const __grid_consta
         asm volatile("griddepcontrol.wait;" ::: "memory");  // the history buffer is written by reverb_prepare just before us
         if (lane == 0) {
             const int32_t col_a0 = (int32_t)(a.cursor + n0) - (int32_t)a.Lr;  // multiple of 8 elements = 16 bytes
-            const int32_t row_a = (int32_t)(c * a.V + v0), row_b = (int32_t)((c % a.ir_ch) * RV_BN);
+            const int32_t row_a = (int32_t)((a.chan_base + c) * a.V + v0), row_b = (int32_t)(((a.chan_base + c) % a.ir_ch) * RV_BN);
             for (uint32_t kb = 0; kb < num_kb; ++kb) {
                 const uint32_t s = kb % RV_STAGES, ph = (kb / RV_STAGES) & 1u;
                 mbar_wait(&empty_bar[s], ph ^ 1u);
@@ -279,18 +279,18 @@ cudaError_t launch_reverb(const ReverbCall& rc, cudaStream_t st, std::string* er
     {
         const uint32_t per_block = 256 * 8;
         dim3 grid((rc.T + per_block - 1) / per_block < 32 ? (rc.T + per_block - 1) / per_block : 32, rc.C * rc.V);
-        reverb_prepare<<<grid, 256, 0, st>>>(rc.in, static_cast<__nv_bfloat16*>(rc.xh), rc.V, rc.C, rc.T, rc.cursor, rc.pitch, rc.zero_first);
+        reverb_prepare<<<grid, 256, 0, st>>>(rc.in, static_cast<__nv_bfloat16*>(rc.xh), rc.V, rc.C, rc.T, rc.cursor, rc.pitch, rc.zero_first, rc.chan_base);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }
     CUtensorMap tm_a, tm_b;
-    if (!make_map_bf16_2d(&tm_a, rc.xh, (uint64_t)rc.cursor + rc.T, (uint64_t)rc.C * rc.V, rc.pitch, RV_BK, RV_BM) ||
+    if (!make_map_bf16_2d(&tm_a, rc.xh, (uint64_t)rc.cursor + rc.T, (uint64_t)(rc.chan_base + rc.C) * rc.V, rc.pitch, RV_BK, RV_BM) ||
         !make_map_bf16_2d(&tm_b, rc.bt, kpad, (uint64_t)rc.ir_ch * RV_BN, kpad, RV_BK, RV_BN)) {
         if (err) *err = "cuTensorMapEncodeTiled failed";
         return cudaErrorInvalidValue;
     }
     static const uint32_t dbg = getenv("FW_REVERB_DEBUG") ? (uint32_t)atoi(getenv("FW_REVERB_DEBUG")) : 0u;
-    ReverbGemmArgs ga{rc.out, rc.V, rc.C, rc.T, reverb_lr(rc.L), rc.cursor, rc.ir_ch, kpad / RV_BK, dbg};
+    ReverbGemmArgs ga{rc.out, rc.V, rc.C, rc.T, reverb_lr(rc.L), rc.cursor, rc.ir_ch, kpad / RV_BK, dbg, rc.chan_base};
     dim3 grid((rc.T + RV_BN - 1) / RV_BN, (rc.V + RV_BM - 1) / RV_BM, rc.C);
     reverb_gemm_kernel<<<grid, 256, RV_SMEM_BYTES, st>>>(tm_a, tm_b, ga);
     return cudaGetLastError();

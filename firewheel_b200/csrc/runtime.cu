@@ -147,6 +147,10 @@ struct Plan {
     struct Stage { int kind = 0; /* 0 pointwise, 1 temporal */ ChainProgram prog{}; uint32_t c_in = 0, c_out = 0;
                    std::shared_ptr<NodeDeviceState> biquad, delay, reverb; };  // kind 2: reverb
     std::vector<Stage> stages;
+    // generic lowering (arbitrary DAG of built-in nodes): one launch group per scheduled node over pool buffers [buffer][V][T]
+    struct GNode { uint32_t kind = 0; std::vector<uint32_t> in_buf, out_buf; std::vector<uint8_t> in_clear; int sm0 = -1, sm1 = -1, mask_slot = -1;
+                   float f0 = 0.0f; std::shared_ptr<NodeDeviceState> st; };
+    bool generic = false; std::vector<GNode> gnodes; uint32_t num_buffers = 0;
     bool bus = false; uint32_t n_sm = 0, c_in = 0, c_out = 0, num_voices = 0, block_frames = 0;
     Records rec{};
     uint64_t* d_bus_mask = nullptr;
@@ -154,7 +158,7 @@ struct Plan {
         cudaSetDevice(device);
         cudaFree(d_flags); cudaFree(rec.modes); cudaFree(rec.vals); cudaFree(rec.curves);
         cudaFree(rec.steady_k); cudaFree(rec.gout_mask); cudaFree(rec.error); cudaFree(d_bus_mask);
-        cudaFree(rec.st_modes); cudaFree(rec.st_vals);
+        cudaFree(rec.st_modes); cudaFree(rec.st_vals); cudaFree(rec.sum_masks); cudaFree(rec.st_sum_masks);
     }
 };
 
@@ -213,6 +217,7 @@ struct fw_processor {
     float *d_in = nullptr, *d_out = nullptr, *d_inter = nullptr, *d_part[2] = {nullptr, nullptr}, *d_flush = nullptr;
     size_t cap_in = 0, cap_out = 0, cap_inter = 0, cap_part[2] = {0, 0};
     float* d_tmp[2] = {nullptr, nullptr}; size_t cap_tmp[2] = {0, 0};  // inter-stage scratch
+    float* d_pool = nullptr; size_t cap_pool = 0;  // generic lowering: [buffer][V][T]
     // multi-GPU master bus: voices shard by rank; the per-rank buses are all-gathered and tree-summed in rank order
     void* nccl_comm = nullptr; int rank = 0, world = 1;
     float *d_bus_local = nullptr, *d_gather = nullptr; size_t cap_bus_local = 0, cap_gather = 0;
@@ -269,14 +274,18 @@ static bool lower(fw_ctx* c, const Schedule& s, Plan* plan, std::string* why) {
         }
     }
     tb.n_smoothers = n_sm;
+    uint32_t n_sum_masks = 0;  // generic lowering only: nodes whose data-plane body needs the per-block input silence mask
 
-    // ---- data plane: a linear chain graph_in -> n1 -> ... -> nk -> graph_out, port i to port i ----
     const SchedNode& gin = s.nodes.front();
     const SchedNode& gout = s.nodes.back();
-    uint32_t width = (uint32_t)gin.out.size();
-    if (width != c->n_in) { *why = "stream input channels must equal the graph_in port count on the device path"; return false; }
+    if (gin.out.size() != c->n_in) { *why = "stream input channels must equal the graph_in port count on the device path"; return false; }
     if (gout.in.size() != c->n_out) { *why = "stream output channels must equal the graph_out port count on the device path"; return false; }
-    if (width < 1 || width > 2) { *why = "the fused chain supports 1 or 2 channels (generic per-node lowering not built yet)"; return false; }
+    plan->c_in = (uint32_t)gin.out.size(); plan->c_out = (uint32_t)gout.in.size();
+
+    // ---- data plane, first choice: a linear chain graph_in -> n1 -> ... -> nk -> graph_out, port i to port i, fused into stages ----
+    auto chain_lower = [&]() -> bool {
+    uint32_t width = (uint32_t)gin.out.size();
+    if (width < 1 || width > 2) { *why = "the fused chain supports 1 or 2 channels"; return false; }
     plan->c_in = width;
     Id prev = gin.id;
     auto fed_by_prev = [&](const SchedNode& sn, uint32_t w) {
@@ -339,7 +348,40 @@ static bool lower(fw_ctx* c, const Schedule& s, Plan* plan, std::string* why) {
     // the last stage must be pointwise when the master bus follows it, and a plan is never empty
     const bool bus = c->cfg.master_bus != 0;
     close_pointwise(plan->stages.empty() || (bus && cur.prog.n_ops == 0 && plan->stages.back().kind != 0));
-    plan->n_sm = n_sm; plan->c_out = width;
+    plan->c_out = width;
+    return true;
+    };  // chain_lower
+
+    // ---- data plane, general case: the reference's own buffer assignment on device, one launch group per scheduled node ----
+    auto generic_lower = [&]() -> bool {
+        plan->stages.clear(); plan->generic = true; plan->num_buffers = s.num_buffers;
+        if (c->cfg.master_bus && gout.in.size() > 2) { *why = "master bus over more than 2 graph_out channels"; return false; }
+        for (size_t i = 0; i < n; ++i) {
+            const SchedNode& sn = s.nodes[i];
+            NodeRec* nr = g.node(sn.id);
+            Plan::GNode gn; gn.kind = nr->params->kind; gn.st = c->node_states[sn.id.pack()];
+            for (const InAssign& a : sn.in) { gn.in_buf.push_back(a.buffer); gn.in_clear.push_back(a.should_clear); }
+            for (const OutAssign& a : sn.out) gn.out_buf.push_back(a.buffer);
+            gn.sm0 = sm_of_node[i]; gn.sm1 = gn.kind == FW_NODE_PAN ? sm_of_node[i] + 1 : -1;
+            gn.f0 = nr->params->threshold_gain;
+            const bool endpoint = i == 0 || i + 1 == n;
+            // bodies that branch on the input silence mask (see silence_fix_kernel / sum_kernel)
+            const bool needs_mask = !endpoint && !sn.out.empty() &&
+                ((gn.kind == FW_NODE_SUM && sn.in.size() != sn.out.size()) || gn.kind == FW_NODE_HARD_CLIP || (gn.kind == FW_NODE_VOLUME && sn.in.size() != 2) ||
+                 gn.kind == FW_NODE_MONO_TO_STEREO || gn.kind == FW_NODE_STEREO_TO_MONO);
+            if (needs_mask) {
+                if (n_sum_masks >= (uint32_t)kMaxSumMasks) { *why = "more than 32 mask-dependent nodes in one voice graph"; return false; }
+                gn.mask_slot = (int)n_sum_masks; tb.nodes[i].mask_slot = (uint8_t)(++n_sum_masks);
+            }
+            if (gn.kind == FW_NODE_DUMMY && !endpoint && !sn.out.empty()) { *why = "a DummyAudioNode inside the graph leaves its outputs stale in the reference (dummy.rs:34-41): not reproducible on the device"; return false; }
+            if (gn.kind == FW_NODE_MONO_TO_STEREO && (sn.in.size() != 1 || sn.out.size() != 2)) { *why = "MonoToStereoNode must be 1 -> 2"; return false; }
+            if (gn.kind == FW_NODE_STEREO_TO_MONO && (sn.in.size() != 2 || sn.out.size() != 1)) { *why = "StereoToMonoNode must be 2 -> 1"; return false; }
+            plan->gnodes.push_back(std::move(gn));
+        }
+        return true;
+    };
+    if (!chain_lower()) { if (!generic_lower()) return false; }
+    plan->n_sm = n_sm;
 
     // ---- device allocations (main thread) ----
     const uint32_t V = c->cfg.num_voices, F = c->max_block_frames;
@@ -347,7 +389,7 @@ static bool lower(fw_ctx* c, const Schedule& s, Plan* plan, std::string* why) {
     plan->d_flags = dev_alloc<uint64_t>(V);
     Records& r = plan->rec;
     r.n_smoothers = n_sm;
-    r.kt_max = n_sm ? (8192u + F - 1) / F + 3u : 2u;  // longest ramp: ln(4/1e-6)*480 < 8192 samples, then settle/stall
+    r.kt_max = n_sm ? (8192u + F - 1) / F + 3u : 4u;  // longest ramp: ln(4/1e-6)*480 < 8192 samples, then settle/stall
     r.modes = dev_alloc<uint32_t>((size_t)r.kt_max * V);
     r.vals = dev_alloc<float>((size_t)r.kt_max * (n_sm ? n_sm : 1) * V);
     r.curves = dev_alloc<float>((size_t)r.kt_max * n_sm * V * F, false);
@@ -355,9 +397,12 @@ static bool lower(fw_ctx* c, const Schedule& s, Plan* plan, std::string* why) {
     r.gout_mask = dev_alloc<uint64_t>(V);
     r.st_modes = dev_alloc<uint32_t>(V);
     r.st_vals = dev_alloc<float>((size_t)(n_sm ? n_sm : 1) * V);
+    r.n_sum_masks = n_sum_masks;
+    r.sum_masks = dev_alloc<uint64_t>((size_t)r.kt_max * (n_sum_masks ? n_sum_masks : 1) * V);
+    r.st_sum_masks = dev_alloc<uint64_t>((size_t)(n_sum_masks ? n_sum_masks : 1) * V);
     r.error = dev_alloc<uint32_t>(1);
     plan->d_bus_mask = dev_alloc<uint64_t>(1);
-    if (!plan->d_flags || !r.modes || !r.vals || !r.curves || !r.steady_k || !r.gout_mask || !r.error || !plan->d_bus_mask || !r.st_modes || !r.st_vals) { *why = g_dev_err; return false; }
+    if (!plan->d_flags || !r.modes || !r.vals || !r.curves || !r.steady_k || !r.gout_mask || !r.error || !plan->d_bus_mask || !r.st_modes || !r.st_vals || !r.sum_masks || !r.st_sum_masks) { *why = g_dev_err; return false; }
     plan->tables = tb;
     return true;
 }
@@ -725,6 +770,198 @@ static bool ensure(float** buf, size_t* cap, size_t n) {
     return true;
 }
 
+// Last stage with a master bus: the chain kernel (BUS variant) reduces 64 voices per CTA into partial buses, the combine
+// kernel finishes the tree, and with several ranks the per-rank buses are exchanged.
+static int run_bus_stage(fw_processor* p, ChainArgs& xa, uint32_t n_out, uint32_t T, float* d_out) {
+    const uint32_t V = p->num_voices;
+    uint32_t n = chain_voice_groups(V);
+    float* bus_dst = d_out;  // this rank's bus; with several ranks it is gathered and tree-summed below
+    if (p->world > 1) {
+        if ((size_t)n_out * T > p->cap_bus_local || (size_t)p->world * n_out * T > p->cap_gather) join_side(p);  // about to reallocate
+        if (!ensure(&p->d_bus_local, &p->cap_bus_local, (size_t)n_out * T) || !ensure(&p->d_gather, &p->cap_gather, (size_t)p->world * n_out * T)) return FW_PROC_DEVICE_ERROR;
+        bus_dst = p->d_bus_local;
+    }
+    if (n == 1) { xa.out = bus_dst; }
+    else {
+        const size_t need = (size_t)n * n_out * T;
+        if (!ensure(&p->d_part[0], &p->cap_part[0], need) || !ensure(&p->d_part[1], &p->cap_part[1], (size_t)((n + 15) / 16) * n_out * T)) return FW_PROC_DEVICE_ERROR;
+        xa.out = p->d_part[0];
+    }
+    if (p->world > 1 && n == 1) join_side(p);  // the chain kernel writes d_bus_local directly
+    { ProfScope ps(p, 1); if (!FW_CUDA(launch_chain(xa, true, p->stream))) return FW_PROC_DEVICE_ERROR; }
+    p->launches++;
+    ProfScope ps2(p, 2);
+    int cur = 0;
+    while (n > 1) {
+        const uint32_t n_next = (n + 15) / 16;
+        float* cdst = n_next == 1 ? bus_dst : p->d_part[cur ^ 1];
+        if (p->world > 1 && n_next == 1) join_side(p);  // d_bus_local is still being read by the previous exchange
+        if (!FW_CUDA(launch_combine(p->d_part[cur], cdst, n, n_out, T, p->stream))) return FW_PROC_DEVICE_ERROR;
+        p->launches++;
+        n = n_next; cur ^= 1;
+    }
+    if (p->world > 1) {
+        // Exchange step: all-gather the per-rank buses over NVLink, then the top log2(world) levels of
+        // the same balanced tree in rank order on every rank — bit-identical on all ranks, unlike ncclAllReduce.
+        cudaEventRecord(p->ev_bus_ready, p->stream);
+        cudaStreamWaitEvent(p->side, p->ev_bus_ready, 0);
+        if (!g_nccl.ok(g_nccl.AllGather(p->d_bus_local, p->d_gather, (size_t)n_out * T, /*ncclFloat32*/ 7, p->nccl_comm, p->side), "ncclAllGather")) return FW_PROC_DEVICE_ERROR;
+        p->launches++;
+        if (!FW_CUDA(launch_combine(p->d_gather, d_out, (uint32_t)p->world, n_out, T, p->side))) return FW_PROC_DEVICE_ERROR;
+        p->launches++;
+        cudaEventRecord(p->ev_exchange_done, p->side);
+        p->exchange_pending = true;
+    }
+    return FW_PROC_OK;
+}
+
+// Generic lowering at run time: walk the scheduled nodes (compiler.rs order) over the pool [buffer][V][T]. Buffer reuse
+// is the reference's (compiler.rs:302-412): it is valid for any execution that respects the schedule order, and each
+// node here finishes all K blocks before the next node starts.
+static int enqueue_generic(fw_processor* p, Plan& pl, const float* d_in, float* d_out, uint32_t T, uint32_t zero_first_frames) {
+    const uint32_t V = p->num_voices, n_in = pl.c_in, n_out = pl.c_out;
+    const size_t BS = (size_t)V * T;  // floats per pool buffer
+    if (!ensure(&p->d_pool, &p->cap_pool, (size_t)pl.num_buffers * BS)) return FW_PROC_DEVICE_ERROR;
+    auto buf = [&](uint32_t b) { return p->d_pool + (size_t)b * BS; };
+    // one pointwise launch: up to 2 channels, arbitrary channel pointers
+    auto pointwise = [&](const ChainProgram& prog, const float* i0, const float* i1, uint64_t ivs, float* o0, float* o1, uint64_t ovs, bool first) -> bool {
+        ChainArgs xa{};
+        xa.in_ch[0] = i0; xa.in_ch[1] = i1 ? i1 : i0; xa.out_ch[0] = o0; xa.out_ch[1] = o1 ? o1 : o0;
+        xa.in_vstride = ivs; xa.out_vstride = ovs; xa.out = nullptr;
+        xa.num_voices = V; xa.frames = T; xa.block_frames = pl.block_frames; xa.zero_first_block = (first && zero_first_frames) ? 1u : 0u;
+        xa.rec = pl.rec; xa.prog = prog; xa.in_from_prev_kernel = first ? 0u : 1u;
+        ProfScope ps(p, 1);
+        if (!FW_CUDA(launch_chain(xa, false, p->stream))) return false;
+        p->launches++;
+        return true;
+    };
+    auto prog1 = [&](int kind, uint32_t ci, uint32_t co, int sm0, int sm1, float f0) {
+        ChainProgram pr{}; pr.c_in = ci; pr.c_out = co; pr.n_ops = kind < 0 ? 0u : 1u;
+        if (kind >= 0) { pr.ops[0].kind = (uint32_t)kind; pr.ops[0].sm0 = sm0; pr.ops[0].sm1 = sm1; pr.ops[0].f0 = f0; }
+        return pr;
+    };
+    // channel-wise op over matching in/out channel lists, two channels per launch
+    auto per_channel = [&](const Plan::GNode& gn, int kind) -> bool {
+        const size_t nc = std::min(gn.in_buf.size(), gn.out_buf.size());
+        for (size_t c = 0; c < nc; c += 2) {
+            const bool two = c + 1 < nc;
+            if (!pointwise(prog1(kind, two ? 2 : 1, two ? 2 : 1, gn.sm0, gn.sm1, gn.f0), buf(gn.in_buf[c]), two ? buf(gn.in_buf[c + 1]) : nullptr, T,
+                           buf(gn.out_buf[c]), two ? buf(gn.out_buf[c + 1]) : nullptr, T, false)) return false;
+        }
+        return true;
+    };
+    auto silence_fix = [&](const Plan::GNode& gn, size_t out_ch, uint64_t test) -> bool {
+        if (gn.mask_slot < 0) return true;
+        SilenceFixArgs fa{};
+        fa.out = buf(gn.out_buf[out_ch]); fa.test = test; fa.num_voices = V; fa.frames = T; fa.block_frames = pl.block_frames; fa.mask_slot = gn.mask_slot; fa.rec = pl.rec;
+        ProfScope ps(p, 1);
+        if (!FW_CUDA(launch_silence_fix(fa, p->stream))) return false;
+        p->launches++;
+        return true;
+    };
+    const size_t N = pl.gnodes.size();
+    for (size_t i = 0; i < N; ++i) {
+        Plan::GNode& gn = pl.gnodes[i];
+        for (size_t k = 0; k < gn.in_buf.size(); ++k)  // unconnected inputs are cleared every block (schedule.rs:310-313)
+            if (gn.in_clear[k]) { if (!FW_CUDA(launch_fill(buf(gn.in_buf[k]), BS, 0.0f, p->stream))) return FW_PROC_DEVICE_ERROR; p->launches++; }
+        if (i == 0) {  // graph_in: stream channels -> pool (prepare_graph_inputs, schedule.rs:213-253)
+            for (size_t c = 0; c < gn.out_buf.size(); c += 2) {
+                const bool two = c + 1 < gn.out_buf.size();
+                if (!pointwise(prog1(-1, two ? 2 : 1, two ? 2 : 1, -1, -1, 0.f), d_in + c * T, two ? d_in + (c + 1) * T : nullptr, (uint64_t)n_in * T,
+                               buf(gn.out_buf[c]), two ? buf(gn.out_buf[c + 1]) : nullptr, T, true)) return FW_PROC_DEVICE_ERROR;
+            }
+            continue;
+        }
+        if (i + 1 == N) {  // graph_out: pool -> stream channels / master bus (read_graph_outputs, schedule.rs:255-287)
+            if (pl.bus) {
+                ChainArgs xa{};
+                xa.in_ch[0] = buf(gn.in_buf[0]); xa.in_ch[1] = buf(gn.in_buf[n_out > 1 ? 1 : 0]); xa.in_vstride = T;
+                xa.num_voices = V; xa.frames = T; xa.block_frames = pl.block_frames; xa.rec = pl.rec; xa.prog = prog1(-1, n_out, n_out, -1, -1, 0.f); xa.in_from_prev_kernel = 1;
+                const int brc = run_bus_stage(p, xa, n_out, T, d_out);
+                if (brc != FW_PROC_OK) return brc;
+            } else {
+                for (size_t c = 0; c < gn.in_buf.size(); c += 2) {
+                    const bool two = c + 1 < gn.in_buf.size();
+                    if (!pointwise(prog1(-1, two ? 2 : 1, two ? 2 : 1, -1, -1, 0.f), buf(gn.in_buf[c]), two ? buf(gn.in_buf[c + 1]) : nullptr, T,
+                                   d_out + c * T, two ? d_out + (c + 1) * T : nullptr, (uint64_t)n_out * T, false)) return FW_PROC_DEVICE_ERROR;
+                }
+            }
+            continue;
+        }
+        switch (gn.kind) {
+            case FW_NODE_DUMMY: break;  // no outputs (rejected otherwise)
+            case FW_NODE_VOLUME: case FW_NODE_HARD_CLIP:
+                if (!per_channel(gn, gn.kind == FW_NODE_VOLUME ? OP_GAIN : OP_CLIP)) return FW_PROC_DEVICE_ERROR;
+                for (size_t c = 0; gn.mask_slot >= 0 && c < gn.out_buf.size(); ++c) if (!silence_fix(gn, c, 1ull << c)) return FW_PROC_DEVICE_ERROR;
+                break;
+            case FW_NODE_PAN:
+                if (!pointwise(prog1(OP_PAN, 2, 2, gn.sm0, gn.sm1, 0.f), buf(gn.in_buf[0]), buf(gn.in_buf[1]), T, buf(gn.out_buf[0]), buf(gn.out_buf[1]), T, false)) return FW_PROC_DEVICE_ERROR;
+                break;
+            case FW_NODE_MONO_TO_STEREO:
+                if (!pointwise(prog1(OP_M2S, 1, 2, -1, -1, 0.f), buf(gn.in_buf[0]), nullptr, T, buf(gn.out_buf[0]), buf(gn.out_buf[1]), T, false)) return FW_PROC_DEVICE_ERROR;
+                if (!silence_fix(gn, 0, 1ull) || !silence_fix(gn, 1, 1ull)) return FW_PROC_DEVICE_ERROR;
+                break;
+            case FW_NODE_STEREO_TO_MONO:
+                if (!pointwise(prog1(OP_S2M, 2, 1, -1, -1, 0.f), buf(gn.in_buf[0]), buf(gn.in_buf[1]), T, buf(gn.out_buf[0]), nullptr, T, false)) return FW_PROC_DEVICE_ERROR;
+                if (!silence_fix(gn, 0, 3ull)) return FW_PROC_DEVICE_ERROR;
+                break;
+            case FW_NODE_SUM: {
+                const size_t no = gn.out_buf.size(), ports = no ? gn.in_buf.size() / no : 0;
+                if (ports <= 1) { if (!per_channel(gn, -1)) return FW_PROC_DEVICE_ERROR; break; }  // copy (sum.rs:58-65)
+                for (size_t c = 0; c < no; ++c) {
+                    SumArgs sa{};
+                    for (size_t q = 0; q < ports; ++q) { sa.in[q] = buf(gn.in_buf[q * no + c]); sa.mask_bit[q] = (uint8_t)(q * no + c); }
+                    sa.out = buf(gn.out_buf[c]); sa.n_ports = (uint32_t)ports; sa.num_voices = V; sa.frames = T; sa.block_frames = pl.block_frames;
+                    sa.mask_slot = gn.mask_slot; sa.skip_silent = ports >= 5 ? 1u : 0u;
+                    sa.all_mask = gn.in_buf.size() >= 64 ? ~0ull : (1ull << gn.in_buf.size()) - 1ull; sa.rec = pl.rec;
+                    ProfScope ps(p, 1);
+                    if (!FW_CUDA(launch_sum(sa, p->stream))) return FW_PROC_DEVICE_ERROR;
+                    p->launches++;
+                }
+                break;
+            }
+            case FW_NODE_BIQUAD: case FW_NODE_DELAY: {
+                NodeDeviceState& st = *gn.st;
+                const uint32_t nc = (uint32_t)gn.in_buf.size(), D = gn.kind == FW_NODE_DELAY ? st.params->delay : 0u;
+                for (uint32_t c = 0; c < nc; ++c) {
+                    TemporalArgs ta{};
+                    ta.in = buf(gn.in_buf[c]); ta.out = buf(gn.out_buf[c]); ta.R = V; ta.C = 1; ta.T = T; ta.srow_mul = nc; ta.srow_add = c;
+                    if (gn.kind == FW_NODE_BIQUAD) { ta.ns = st.params->num_stages; ta.coeffs = st.d_coeffs; ta.state = st.d_state; }
+                    else if (D) { ta.D = D; ta.ring = st.d_ring; ta.pos = st.ring_pos; }
+                    ProfScope ps(p, 3);
+                    if (!FW_CUDA(launch_temporal(ta, p->stream))) return FW_PROC_DEVICE_ERROR;
+                    p->launches++;
+                }
+                if (D) st.ring_pos = (uint32_t)(((uint64_t)st.ring_pos + T) % D);
+                break;
+            }
+            case FW_NODE_CONV_REVERB: {
+                NodeDeviceState& rs = *gn.st;
+                if (T > NodeDeviceState::kReverbMaxFrames) { g_dev_err = "conv reverb: more than 65536 frames in one call"; return FW_PROC_BAD_ARGS; }
+                const uint32_t nc = (uint32_t)gn.in_buf.size(), H = reverb_hist(rs.params->ir_len);
+                if (rs.xh_cursor + T > rs.xh_pitch || (rs.xh_cursor & 7u)) {
+                    if (!FW_CUDA(cudaMemcpy2DAsync(rs.d_xh[rs.xh_cur ^ 1u], (size_t)rs.xh_pitch * 2, static_cast<const uint16_t*>(rs.d_xh[rs.xh_cur]) + (rs.xh_cursor - H),
+                                                   (size_t)rs.xh_pitch * 2, (size_t)H * 2, (size_t)V * nc, cudaMemcpyDeviceToDevice, p->stream))) return FW_PROC_DEVICE_ERROR;
+                    rs.xh_cur ^= 1u; rs.xh_cursor = H;
+                }
+                for (uint32_t c = 0; c < nc; ++c) {
+                    ReverbCall rc{};
+                    rc.in = buf(gn.in_buf[c]); rc.out = buf(gn.out_buf[c]); rc.xh = rs.d_xh[rs.xh_cur]; rc.bt = rs.d_bt;
+                    rc.V = V; rc.C = 1; rc.T = T; rc.L = rs.params->ir_len; rc.ir_ch = rs.params->ir_channels; rc.cursor = rs.xh_cursor; rc.pitch = rs.xh_pitch; rc.chan_base = c;
+                    std::string rerr;
+                    ProfScope ps(p, 3);
+                    if (!FW_CUDA(launch_reverb(rc, p->stream, &rerr))) { if (!rerr.empty()) g_dev_err = rerr; return FW_PROC_DEVICE_ERROR; }
+                    p->launches += 2;
+                }
+                rs.xh_cursor += T;
+                break;
+            }
+            default: g_dev_err = "generic lowering: unknown node kind"; return FW_PROC_DEVICE_ERROR;
+        }
+    }
+    return FW_PROC_OK;
+}
+
 // Enqueue one call (frames = K blocks) on device buffers. d_in [V][c_in][T]; d_out [V][c_out][T] or bus [c_out][T].
 static int proc_enqueue(fw_processor* p, const float* d_in, float* d_out, uint32_t n_in, uint32_t n_out, uint64_t frames64) {
     if (frames64 > 0x7fffffffull) return FW_PROC_BAD_ARGS;
@@ -747,6 +984,11 @@ static int proc_enqueue(fw_processor* p, const float* d_in, float* d_out, uint32
     { ProfScope ps(p, 0); if (!FW_CUDA(launch_control(ca, p->stream))) return FW_PROC_DEVICE_ERROR; }
     p->launches++;
 
+    if (pl.generic) {
+        const uint32_t zff = p->pending_zero_first ? std::min(pl.block_frames, T) : 0u;  // Q11
+        p->pending_zero_first = false;
+        return enqueue_generic(p, pl, d_in, d_out, T, zff);
+    }
     // ---- data plane: run the stages in order; intermediates ping-pong through [V][ch][T] scratch ----
     const size_t n_stages = pl.stages.size();
     if (n_stages > 1) {
@@ -773,7 +1015,7 @@ static int proc_enqueue(fw_processor* p, const float* d_in, float* d_out, uint32
             }
             rc.in = src; rc.out = dst; rc.xh = rs.d_xh[rs.xh_cur]; rc.bt = rs.d_bt;
             rc.V = V; rc.C = sg.c_in; rc.T = T; rc.L = rs.params->ir_len; rc.ir_ch = rs.params->ir_channels; rc.cursor = rs.xh_cursor; rc.pitch = rs.xh_pitch;
-            rc.zero_first = si == 0 ? zero_first_frames : 0u;
+            rc.zero_first = si == 0 ? zero_first_frames : 0u; rc.chan_base = 0;
             std::string rerr;
             { ProfScope ps(p, 3); if (!FW_CUDA(launch_reverb(rc, p->stream, &rerr))) { if (!rerr.empty()) g_dev_err = rerr; return FW_PROC_DEVICE_ERROR; } }
             p->launches += 2;
@@ -784,6 +1026,7 @@ static int proc_enqueue(fw_processor* p, const float* d_in, float* d_out, uint32
         if (sg.kind == 1) {
             TemporalArgs ta{};
             ta.in = src; ta.out = dst; ta.R = V * sg.c_in; ta.C = sg.c_in; ta.T = T; ta.zero_first = si == 0 ? zero_first_frames : 0u;
+            ta.srow_mul = 1; ta.srow_add = 0;
             if (sg.biquad) { ta.ns = sg.biquad->params->num_stages; ta.coeffs = sg.biquad->d_coeffs; ta.state = sg.biquad->d_state; }
             if (sg.delay && sg.delay->params->delay) {
                 ta.D = sg.delay->params->delay; ta.ring = sg.delay->d_ring; ta.pos = sg.delay->ring_pos;
@@ -795,51 +1038,20 @@ static int proc_enqueue(fw_processor* p, const float* d_in, float* d_out, uint32
             continue;
         }
         ChainArgs xa{};
-        xa.in = src; xa.num_voices = V; xa.frames = T; xa.block_frames = pl.block_frames; xa.zero_first_block = (si == 0 && zero_first_frames) ? 1u : 0u;
+        for (uint32_t c = 0; c < 2; ++c) {  // staged chains read / write [V][ch][T]
+            xa.in_ch[c] = src + (size_t)(c < sg.prog.c_in ? c : 0) * T;
+            xa.out_ch[c] = dst + (size_t)(c < sg.prog.c_out ? c : 0) * T;
+        }
+        xa.in_vstride = (uint64_t)sg.prog.c_in * T; xa.out_vstride = (uint64_t)sg.prog.c_out * T;
+        xa.num_voices = V; xa.frames = T; xa.block_frames = pl.block_frames; xa.zero_first_block = (si == 0 && zero_first_frames) ? 1u : 0u;
         xa.rec = pl.rec; xa.prog = sg.prog; xa.in_from_prev_kernel = si > 0 ? 1u : 0u;
         if (!(last && pl.bus)) {
-            xa.out = dst;
+            xa.out = nullptr;
             { ProfScope ps(p, 1); if (!FW_CUDA(launch_chain(xa, false, p->stream))) return FW_PROC_DEVICE_ERROR; }
             p->launches++;
         } else {
-            uint32_t n = chain_voice_groups(V);
-            float* bus_dst = d_out;  // this rank's bus; with several ranks it is gathered and tree-summed below
-            if (p->world > 1) {
-                if ((size_t)n_out * T > p->cap_bus_local || (size_t)p->world * n_out * T > p->cap_gather) join_side(p);  // about to reallocate
-                if (!ensure(&p->d_bus_local, &p->cap_bus_local, (size_t)n_out * T) || !ensure(&p->d_gather, &p->cap_gather, (size_t)p->world * n_out * T)) return FW_PROC_DEVICE_ERROR;
-                bus_dst = p->d_bus_local;
-            }
-            if (n == 1) { xa.out = bus_dst; }
-            else {
-                const size_t need = (size_t)n * n_out * T;
-                if (!ensure(&p->d_part[0], &p->cap_part[0], need) || !ensure(&p->d_part[1], &p->cap_part[1], (size_t)((n + 15) / 16) * n_out * T)) return FW_PROC_DEVICE_ERROR;
-                xa.out = p->d_part[0];
-            }
-            if (p->world > 1 && n == 1) join_side(p);  // the chain kernel writes d_bus_local directly
-            { ProfScope ps(p, 1); if (!FW_CUDA(launch_chain(xa, true, p->stream))) return FW_PROC_DEVICE_ERROR; }
-            p->launches++;
-            ProfScope ps2(p, 2);
-            int cur = 0;
-            while (n > 1) {
-                const uint32_t n_next = (n + 15) / 16;
-                float* cdst = n_next == 1 ? bus_dst : p->d_part[cur ^ 1];
-                if (p->world > 1 && n_next == 1) join_side(p);  // d_bus_local is still being read by the previous exchange
-                if (!FW_CUDA(launch_combine(p->d_part[cur], cdst, n, n_out, T, p->stream))) return FW_PROC_DEVICE_ERROR;
-                p->launches++;
-                n = n_next; cur ^= 1;
-            }
-            if (p->world > 1) {
-                // Exchange step: all-gather the per-rank buses over NVLink, then the top log2(world) levels of
-                // the same balanced tree in rank order on every rank — bit-identical on all ranks, unlike ncclAllReduce.
-                cudaEventRecord(p->ev_bus_ready, p->stream);
-                cudaStreamWaitEvent(p->side, p->ev_bus_ready, 0);
-                if (!g_nccl.ok(g_nccl.AllGather(p->d_bus_local, p->d_gather, (size_t)n_out * T, /*ncclFloat32*/ 7, p->nccl_comm, p->side), "ncclAllGather")) return FW_PROC_DEVICE_ERROR;
-                p->launches++;
-                if (!FW_CUDA(launch_combine(p->d_gather, d_out, (uint32_t)p->world, n_out, T, p->side))) return FW_PROC_DEVICE_ERROR;
-                p->launches++;
-                cudaEventRecord(p->ev_exchange_done, p->side);
-                p->exchange_pending = true;
-            }
+            const int brc = run_bus_stage(p, xa, n_out, T, d_out);
+            if (brc != FW_PROC_OK) return brc;
         }
         src = dst;
     }
@@ -921,7 +1133,7 @@ void fw_processor_free(fw_processor* p) {  // Drop processor.rs:251-263
     if (p->side) { cudaStreamSynchronize(p->side); cudaStreamDestroy(p->side); cudaEventDestroy(p->ev_bus_ready); cudaEventDestroy(p->ev_exchange_done); }
     ProcToCtx m; m.kind = 1; m.plan = p->plan; m.user_cx = p->user_cx;
     if (!p->ch->to_ctx.push(m)) delete p->plan;
-    cudaFree(p->d_in); cudaFree(p->d_out); cudaFree(p->d_inter); cudaFree(p->d_part[0]); cudaFree(p->d_part[1]); cudaFree(p->d_flush); cudaFree(p->d_tmp[0]); cudaFree(p->d_tmp[1]); cudaFree(p->d_bus_local); cudaFree(p->d_gather);
+    cudaFree(p->d_in); cudaFree(p->d_out); cudaFree(p->d_inter); cudaFree(p->d_part[0]); cudaFree(p->d_part[1]); cudaFree(p->d_flush); cudaFree(p->d_tmp[0]); cudaFree(p->d_tmp[1]); cudaFree(p->d_bus_local); cudaFree(p->d_gather); cudaFree(p->d_pool);
     if (p->nccl_comm) g_nccl.CommDestroy(p->nccl_comm);
     cudaFreeHost(p->h_masks); cudaFreeHost(p->h_err);
     for (auto& e : p->ev) if (e) cudaEventDestroy(e);

@@ -72,7 +72,8 @@ __global__ void __launch_bounds__(32) biquad_delay_lanes(TemporalArgs a) {
         if (NS > 0 && lane_ok[j]) {
             const float* k = a.coeffs + ((size_t)(r / a.C) * NS + s) * 5;
             b0[j] = k[0]; b1[j] = k[1]; b2[j] = k[2]; a1[j] = k[3]; a2[j] = k[4];
-            s1[j] = a.state[((size_t)r * kStateStages + s) * 2]; s2[j] = a.state[((size_t)r * kStateStages + s) * 2 + 1];
+            const size_t sr = (size_t)r * a.srow_mul + a.srow_add;
+            s1[j] = a.state[(sr * kStateStages + s) * 2]; s2[j] = a.state[(sr * kStateStages + s) * 2 + 1];
         }
     }
 
@@ -85,7 +86,7 @@ __global__ void __launch_bounds__(32) biquad_delay_lanes(TemporalArgs a) {
         const size_t row = ok[i] ? row0 + rr : 0;
         in_p[i] = a.in + row * T + g * 4u;
         out_p[i] = a.out + row * T + g * 4u;
-        ring_p[i] = DELAY ? a.ring + row * D + g * 4u : nullptr;
+        ring_p[i] = DELAY ? a.ring + (row * a.srow_mul + a.srow_add) * D + g * 4u : nullptr;
         sw[i] = rr * 8u + (g ^ (rr & 7u));  // float4 index inside a tile
     }
     const uint32_t nch = T / 32u;
@@ -216,9 +217,9 @@ __global__ void __launch_bounds__(32) biquad_delay_lanes(TemporalArgs a) {
 #pragma unroll
     for (int j = 0; j < RPL; ++j) {
         if (NS > 0 && lane_ok[j]) {
-            const uint32_t r = row0 + row_l[j];
-            a.state[((size_t)r * kStateStages + s) * 2] = s1[j];
-            a.state[((size_t)r * kStateStages + s) * 2 + 1] = s2[j];
+            const size_t sr = (size_t)(row0 + row_l[j]) * a.srow_mul + a.srow_add;
+            a.state[(sr * kStateStages + s) * 2] = s1[j];
+            a.state[(sr * kStateStages + s) * 2 + 1] = s2[j];
         }
     }
 }
@@ -233,11 +234,11 @@ __global__ void __launch_bounds__(64) biquad_delay_generic(TemporalArgs a) {
     for (uint32_t s = 0; s < NS; ++s) {
         const float* k = a.coeffs + ((size_t)(r / a.C) * NS + s) * 5;
         b0[s] = k[0]; b1[s] = k[1]; b2[s] = k[2]; a1[s] = k[3]; a2[s] = k[4];
-        s1[s] = a.state[((size_t)r * kStateStages + s) * 2]; s2[s] = a.state[((size_t)r * kStateStages + s) * 2 + 1];
+        s1[s] = a.state[(((size_t)r * a.srow_mul + a.srow_add) * kStateStages + s) * 2]; s2[s] = a.state[(((size_t)r * a.srow_mul + a.srow_add) * kStateStages + s) * 2 + 1];
     }
     const float* in = a.in + (size_t)r * T;
     float* out = a.out + (size_t)r * T;
-    float* ring = D ? a.ring + (size_t)r * D : nullptr;
+    float* ring = D ? a.ring + ((size_t)r * a.srow_mul + a.srow_add) * D : nullptr;
     uint32_t p = D ? a.pos % D : 0;
     for (uint32_t n = 0; n < T; ++n) {
         float x = n < a.zero_first ? 0.0f : in[n];
@@ -250,7 +251,7 @@ __global__ void __launch_bounds__(64) biquad_delay_generic(TemporalArgs a) {
         if (D) { const float d = ring[p]; ring[p] = x; x = d; p = p + 1 == D ? 0 : p + 1; }
         out[n] = x;
     }
-    for (uint32_t s = 0; s < NS; ++s) { a.state[((size_t)r * kStateStages + s) * 2] = s1[s]; a.state[((size_t)r * kStateStages + s) * 2 + 1] = s2[s]; }
+    for (uint32_t s = 0; s < NS; ++s) { const size_t sr = (size_t)r * a.srow_mul + a.srow_add; a.state[(sr * kStateStages + s) * 2] = s1[s]; a.state[(sr * kStateStages + s) * 2 + 1] = s2[s]; }
 }
 
 // Temporal kernels are launched in plain stream order: measured on config 3, programmatic dependent launch made

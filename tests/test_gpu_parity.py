@@ -149,20 +149,21 @@ def test_config2_full_size_blocks(gpu, oracle):
 
 
 def test_unsupported_topology_fails_loudly(gpu):
-    from firewheel_b200 import AudioGraphConfig, FirewheelGraphCtx
-    cx = FirewheelGraphCtx(gpu, AudioGraphConfig(num_graph_inputs=4, num_graph_outputs=2))
+    """A DummyAudioNode with outputs inside the graph leaves stale buffer contents behind in the reference (dummy.rs:34-41);
+    the device path refuses the graph instead of inventing a result — and never falls back to a CPU path."""
+    from firewheel_b200 import AudioGraphConfig, DummyAudioNode, FirewheelGraphCtx
+    cx = FirewheelGraphCtx(gpu, AudioGraphConfig(num_graph_inputs=2, num_graph_outputs=2))
     g = cx.graph
-    s = g.add_node(4, 2, SumNode())
-    for i in range(4):
-        g.connect(g.graph_in_node(), i, s, i, False)
+    d = g.add_node(2, 2, DummyAudioNode())
     for c in range(2):
-        g.connect(s, c, g.graph_out_node(), c, False)
-    proc = cx.activate(48000, 4, 2, 256)
+        g.connect(g.graph_in_node(), c, d, c, False)
+        g.connect(d, c, g.graph_out_node(), c, False)
+    proc = cx.activate(48000, 2, 2, 256)
     st = cx.update()
     assert st.graph_error is not None and st.graph_error.kind == "UnsupportedOnDevice"
     out = np.full((1, 2, 256), np.nan, f32)
-    rc, _ = proc.process_planar(synth((1, 4, 256), 1), out, 4, 2, 256)
-    assert rc == 0 and np.all(out == 0)  # no schedule => silence (processor.rs:86-89), never a CPU fallback
+    rc, _ = proc.process_planar(synth((1, 2, 256), 1), out, 2, 2, 256)
+    assert rc == 0 and np.all(out == 0)  # no schedule => silence (processor.rs:86-89)
     proc.free()
 
 
