@@ -112,4 +112,17 @@ struct SilenceFixArgs {
     Records rec;
 };
 
+// Master-bus exchange over peer memory (exchange.cu). Pointers indexed by rank are the IPC-mapped mailboxes.
+struct BusPushArgs {
+    const float* pin; uint32_t n_in, rows, T;   // partial buses [n_in <= 16][rows][T] of this rank
+    float* data[16]; uint32_t* ready[16];       // per destination rank: slot storage and ready words
+    const uint32_t* ack_local; uint32_t* counter; uint32_t* push_done; uint32_t* error;
+    uint32_t world, me, epoch, cap;             // cap: floats per slot
+};
+struct BusRecvArgs {
+    const float* data_local; float* out; uint32_t rows, T;
+    uint32_t* ack[16]; uint32_t* counter;
+    uint32_t world, me, epoch, cap;
+};
+
 }  // namespace fw

@@ -223,6 +223,9 @@ struct fw_processor {
     float *d_bus_local = nullptr, *d_gather = nullptr; size_t cap_bus_local = 0, cap_gather = 0;
     // the exchange runs on a side stream so that it overlaps the next call's control + chain kernels
     cudaStream_t side = nullptr; cudaEvent_t ev_bus_ready = nullptr, ev_exchange_done = nullptr; bool exchange_pending = false;
+    // peer-memory exchange (exchange.cu): IPC-mapped mailboxes of all ranks; falls back to the NCCL all-gather when off
+    struct P2P { bool on = false; uint8_t* base[16] = {}; size_t cap = 0; uint32_t epoch = 0; uint32_t* counters = nullptr;
+                 float* part[2][2] = {}; size_t cap_part[2][2] = {}; } p2p;
     uint64_t* h_masks = nullptr; uint32_t* h_err = nullptr;  // pinned
     // optional per-kernel-class timing (CUDA events on `stream`)
     bool profiling = false; std::vector<cudaEvent_t> prof_ev; std::vector<int> prof_class; size_t prof_used = 0;
@@ -755,6 +758,7 @@ static void proc_poll(fw_processor* p) {  // processor.rs:167-206
         if (p->plan) {
             ProcToCtx r; r.kind = 0; r.plan = p->plan;
             cudaStreamSynchronize(p->stream);  // the old plan's buffers may still be in flight
+            if (p->side) cudaStreamSynchronize(p->side);
             p->ch->to_ctx.push(r);
             p->pending_zero_first = true;  // Q11: the swap happens after this block's inputs were written to the old pool
         }
@@ -772,9 +776,51 @@ static bool ensure(float** buf, size_t* cap, size_t n) {
 
 // Last stage with a master bus: the chain kernel (BUS variant) reduces 64 voices per CTA into partial buses, the combine
 // kernel finishes the tree, and with several ranks the per-rank buses are exchanged.
+static constexpr size_t kMailHeader = 256;  // ready[2][16] u32 at +0, ack[2][16] u32 at +128, slots at +256
 static int run_bus_stage(fw_processor* p, ChainArgs& xa, uint32_t n_out, uint32_t T, float* d_out) {
     const uint32_t V = p->num_voices;
     uint32_t n = chain_voice_groups(V);
+    const bool p2p = p->world > 1 && p->p2p.on && (size_t)n_out * T <= p->p2p.cap;
+    if (p2p) {
+        // Main stream: chain -> partial buses (+ radix-16 levels while more than 16 remain). Side stream (high priority):
+        // K-push = last tree level fused with the NVLink stores, K-wait, K-recv. The partial buffers alternate with the
+        // epoch parity, so the whole exchange of call e overlaps control + chain of call e + 1.
+        fw_processor::P2P& x = p->p2p;
+        const uint32_t epoch = ++x.epoch;
+        const int s = (int)(epoch & 1u);
+        if (!ensure(&x.part[s][0], &x.cap_part[s][0], (size_t)n * n_out * T) || (n > 16 && !ensure(&x.part[s][1], &x.cap_part[s][1], (size_t)((n + 15) / 16) * n_out * T))) return FW_PROC_DEVICE_ERROR;
+        xa.out = x.part[s][0];
+        { ProfScope ps(p, 1); if (!FW_CUDA(launch_chain(xa, true, p->stream))) return FW_PROC_DEVICE_ERROR; }
+        p->launches++;
+        int cur = 0;
+        {
+            ProfScope ps2(p, 2);
+            while (n > 16) {
+                if (!FW_CUDA(launch_combine(x.part[s][cur], x.part[s][cur ^ 1], n, n_out, T, p->stream))) return FW_PROC_DEVICE_ERROR;
+                p->launches++;
+                n = (n + 15) / 16; cur ^= 1;
+            }
+        }
+        // device-side hand-over instead of events (an event record between kernels would break the PDL chain)
+        if (!FW_CUDA(launch_bus_signal(x.counters + 2, x.counters + 3, epoch, xa.rec.error, p->stream))) return FW_PROC_DEVICE_ERROR;
+        if (!FW_CUDA(launch_bus_wait(x.counters + 2, 1, epoch, xa.rec.error, p->side))) return FW_PROC_DEVICE_ERROR;
+        BusPushArgs pa{};
+        pa.pin = x.part[s][cur]; pa.n_in = n; pa.rows = n_out; pa.T = T;
+        for (int r = 0; r < p->world; ++r) { pa.data[r] = reinterpret_cast<float*>(x.base[r] + kMailHeader); pa.ready[r] = reinterpret_cast<uint32_t*>(x.base[r]); }
+        pa.ack_local = reinterpret_cast<const uint32_t*>(x.base[p->rank] + 128); pa.counter = x.counters; pa.push_done = x.counters + 3; pa.error = xa.rec.error;
+        pa.world = (uint32_t)p->world; pa.me = (uint32_t)p->rank; pa.epoch = epoch; pa.cap = (uint32_t)x.cap;
+        if (!FW_CUDA(launch_bus_push(pa, p->side))) return FW_PROC_DEVICE_ERROR;
+        if (!FW_CUDA(launch_bus_wait(reinterpret_cast<const uint32_t*>(x.base[p->rank]) + s * 16, (uint32_t)p->world, epoch, xa.rec.error, p->side))) return FW_PROC_DEVICE_ERROR;
+        BusRecvArgs ra{};
+        ra.data_local = reinterpret_cast<const float*>(x.base[p->rank] + kMailHeader); ra.out = d_out; ra.rows = n_out; ra.T = T;
+        for (int r = 0; r < p->world; ++r) ra.ack[r] = reinterpret_cast<uint32_t*>(x.base[r] + 128);
+        ra.counter = x.counters + 1; ra.world = (uint32_t)p->world; ra.me = (uint32_t)p->rank; ra.epoch = epoch; ra.cap = (uint32_t)x.cap;
+        if (!FW_CUDA(launch_bus_recv(ra, p->side))) return FW_PROC_DEVICE_ERROR;
+        p->launches += 5;
+        cudaEventRecord(p->ev_exchange_done, p->side);
+        p->exchange_pending = true;
+        return FW_PROC_OK;
+    }
     float* bus_dst = d_out;  // this rank's bus; with several ranks it is gathered and tree-summed below
     if (p->world > 1) {
         if ((size_t)n_out * T > p->cap_bus_local || (size_t)p->world * n_out * T > p->cap_gather) join_side(p);  // about to reallocate
@@ -962,6 +1008,72 @@ static int enqueue_generic(fw_processor* p, Plan& pl, const float* d_in, float* 
     return FW_PROC_OK;
 }
 
+// Peer-memory mailboxes for the bus exchange: allocate, exchange CUDA IPC handles through the communicator, map all peers.
+// Any rank failing turns the feature off on ALL ranks (they then use the NCCL all-gather): decided by a second all-gather.
+static bool p2p_setup(fw_processor* p) {
+    const char* mode = getenv("FW_EXCHANGE");
+    const bool want = !(mode && std::strcmp(mode, "nccl") == 0);
+    const int W = p->world, me = p->rank;
+    size_t cap = 262144;  // floats per slot: 2 channels x 131072 frames
+    if (const char* e = getenv("FW_P2P_SLOT_FLOATS")) { const long long v = atoll(e); if (v >= 1024) cap = (size_t)v & ~(size_t)3; }
+    const size_t bytes = kMailHeader + (size_t)2 * W * cap * sizeof(float);
+    struct Msg { cudaIpcMemHandle_t h; uint32_t ok; uint32_t pad[15]; };
+    static_assert(sizeof(Msg) == 128, "IPC handle message");
+    std::vector<Msg> all((size_t)W);
+    Msg mine{}; uint8_t* local = nullptr;
+    bool ok = want;
+    if (ok && cudaMalloc(&local, bytes) != cudaSuccess) { cudaGetLastError(); ok = false; local = nullptr; }
+    if (ok) { cudaMemset(local, 0, bytes); if (cudaIpcGetMemHandle(&mine.h, local) != cudaSuccess) { cudaGetLastError(); ok = false; } }
+    mine.ok = ok ? 1u : 0u;
+    Msg* d_msg = nullptr;
+    if (!FW_CUDA(cudaMalloc(&d_msg, sizeof(Msg) * W))) return false;
+    auto gather = [&]() -> bool {
+        cudaMemcpy(d_msg + me, &mine, sizeof(Msg), cudaMemcpyHostToDevice);
+        cudaDeviceSynchronize();
+        if (!g_nccl.ok(g_nccl.AllGather(d_msg + me, d_msg, sizeof(Msg), /*ncclInt8*/ 0, p->nccl_comm, p->side), "ncclAllGather(ipc handles)")) return false;
+        if (!FW_CUDA(cudaStreamSynchronize(p->side))) return false;
+        return FW_CUDA(cudaMemcpy(all.data(), d_msg, sizeof(Msg) * W, cudaMemcpyDeviceToHost));
+    };
+    if (!gather()) { cudaFree(d_msg); return false; }
+    for (int r = 0; r < W; ++r) ok = ok && all[r].ok;
+    if (ok) {
+        for (int r = 0; r < W && ok; ++r) {
+            if (r == me) { p->p2p.base[r] = local; continue; }
+            void* ptr = nullptr;
+            if (cudaIpcOpenMemHandle(&ptr, all[r].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
+            p->p2p.base[r] = static_cast<uint8_t*>(ptr);
+        }
+    }
+    mine.ok = ok ? 1u : 0u;  // second round: did every rank map every peer?
+    if (!gather()) { cudaFree(d_msg); return false; }
+    cudaFree(d_msg);
+    for (int r = 0; r < W; ++r) ok = ok && all[r].ok;
+    if (!ok) {
+        for (int r = 0; r < W; ++r) { if (r != me && p->p2p.base[r]) cudaIpcCloseMemHandle(p->p2p.base[r]); p->p2p.base[r] = nullptr; }
+        if (local) cudaFree(local);
+        if (want && me == 0) std::fprintf(stderr, "[firewheel_b200] peer-memory bus exchange unavailable (CUDA IPC / peer access); using the NCCL all-gather\n");
+        return true;
+    }
+    p->p2p.counters = dev_alloc<uint32_t>(4);  // push counter, recv counter, chain_done, push_done
+    p->p2p.cap = cap; p->p2p.epoch = 0; p->p2p.on = true;
+    return true;
+}
+
+// All ranks must have drained their streams before any mailbox is unmapped or freed: peers write acknowledgements into it.
+static void p2p_teardown(fw_processor* p) {
+    if (!p->p2p.on) return;
+    uint8_t* d_b = nullptr;
+    if (cudaMalloc(&d_b, 16 * p->world) == cudaSuccess) {
+        g_nccl.AllGather(d_b + 16 * p->rank, d_b, 16, /*ncclInt8*/ 0, p->nccl_comm, p->side);  // barrier
+        cudaStreamSynchronize(p->side);
+        cudaFree(d_b);
+    }
+    for (int r = 0; r < p->world; ++r) if (r != p->rank && p->p2p.base[r]) cudaIpcCloseMemHandle(p->p2p.base[r]);
+    cudaFree(p->p2p.base[p->rank]); cudaFree(p->p2p.counters);
+    for (int q = 0; q < 2; ++q) { cudaFree(p->p2p.part[q][0]); cudaFree(p->p2p.part[q][1]); }
+    p->p2p.on = false;
+}
+
 // Enqueue one call (frames = K blocks) on device buffers. d_in [V][c_in][T]; d_out [V][c_out][T] or bus [c_out][T].
 static int proc_enqueue(fw_processor* p, const float* d_in, float* d_out, uint32_t n_in, uint32_t n_out, uint64_t frames64) {
     if (frames64 > 0x7fffffffull) return FW_PROC_BAD_ARGS;
@@ -1089,7 +1201,7 @@ int fw_processor_process_planar(fw_processor* p, const float* in, float* out, ui
     }
     if (!FW_CUDA(cudaStreamSynchronize(p->stream))) return FW_PROC_DEVICE_ERROR;
     if (ran) {
-        if (*p->h_err) { g_dev_err = "control pass overflowed its transient-block budget"; return FW_PROC_DEVICE_ERROR; }
+        if (*p->h_err) { g_dev_err = *p->h_err == 2 ? "master-bus exchange timed out waiting for a peer rank" : "control pass overflowed its transient-block budget"; return FW_PROC_DEVICE_ERROR; }
         if (out_mask) *out_mask = p->bus ? bus_mask_from(p->h_masks, V, n_out) : p->h_masks[0];
     }
     return rc;
@@ -1130,7 +1242,7 @@ void fw_processor_free(fw_processor* p) {  // Drop processor.rs:251-263
     cudaSetDevice(p->device);
     join_side(p);
     cudaStreamSynchronize(p->stream);
-    if (p->side) { cudaStreamSynchronize(p->side); cudaStreamDestroy(p->side); cudaEventDestroy(p->ev_bus_ready); cudaEventDestroy(p->ev_exchange_done); }
+    if (p->side) { cudaStreamSynchronize(p->side); p2p_teardown(p); cudaStreamDestroy(p->side); cudaEventDestroy(p->ev_bus_ready); cudaEventDestroy(p->ev_exchange_done); }
     ProcToCtx m; m.kind = 1; m.plan = p->plan; m.user_cx = p->user_cx;
     if (!p->ch->to_ctx.push(m)) delete p->plan;
     cudaFree(p->d_in); cudaFree(p->d_out); cudaFree(p->d_inter); cudaFree(p->d_part[0]); cudaFree(p->d_part[1]); cudaFree(p->d_flush); cudaFree(p->d_tmp[0]); cudaFree(p->d_tmp[1]); cudaFree(p->d_bus_local); cudaFree(p->d_gather); cudaFree(p->d_pool);
@@ -1208,9 +1320,12 @@ int fw_processor_comm_init(fw_processor* p, int rank, int world, const uint8_t* 
     cudaSetDevice(p->device);
     NcclUniqueId id; std::memcpy(id.internal, id128, 128);
     if (!g_nccl.ok(g_nccl.CommInitRank(&p->nccl_comm, world, id, rank), "ncclCommInitRank")) return -1;
-    if (!FW_CUDA(cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking)) || !FW_CUDA(cudaEventCreateWithFlags(&p->ev_bus_ready, cudaEventDisableTiming)) ||
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);  // the exchange must not queue behind the next call's chain CTAs
+    if (!FW_CUDA(cudaStreamCreateWithPriority(&p->side, cudaStreamNonBlocking, prio_hi)) || !FW_CUDA(cudaEventCreateWithFlags(&p->ev_bus_ready, cudaEventDisableTiming)) ||
         !FW_CUDA(cudaEventCreateWithFlags(&p->ev_exchange_done, cudaEventDisableTiming))) return -1;
     p->rank = rank; p->world = world;
+    if (!p2p_setup(p)) return -1;
     return 0;
 }
 
