@@ -12,7 +12,12 @@ FW_MAX_PORTS = 64
 
 # fw_node_kind
 NODE_DUMMY, NODE_VOLUME, NODE_SUM, NODE_MONO_TO_STEREO, NODE_STEREO_TO_MONO, NODE_HARD_CLIP = range(6)
-NODE_PAN, NODE_BIQUAD, NODE_DELAY, NODE_CONV_REVERB = 6, 7, 8, 9
+NODE_PAN, NODE_BIQUAD, NODE_DELAY, NODE_CONV_REVERB, NODE_SAMPLER = 6, 7, 8, 9, 10
+
+# fw_sample_format / fw_loop_mode / fw_sampler_status
+SAMPLE_F32_PLANAR, SAMPLE_F32_INTERLEAVED, SAMPLE_I16_INTERLEAVED, SAMPLE_U16_INTERLEAVED, SAMPLE_I16_PLANAR, SAMPLE_U16_PLANAR = range(6)
+LOOP_NONE, LOOP_FULL, LOOP_RANGE_SECS = 0, 1, 2
+SAMPLER_ERRORS = {-1: "NotASampler", -2: "RingFull", -3: "NotActivated", -4: "BadArgs"}
 
 # fw_add_edge_error / fw_compile_error names, index = code
 ADD_EDGE_ERRORS = ["Ok", "SrcNodeNotFound", "DstNodeNotFound", "InPortOutOfRange", "OutPortOutOfRange",
@@ -101,6 +106,15 @@ SIGNATURES = {
     "biquad_set_coeffs": (_i32, [_vp, _u64, _u32, _u32, _pf]),
     "biquad_set_all_coeffs": (_i32, [_vp, _u64, _pf, _u32, _u32]),
     "biquad_design_rbj": (None, [_u32, _f64, _f64, _f64, _f64, _pf]),
+    "sample_resource_create": (_u32, [_vp, _u32, _u32, _u64, _vp]),
+    "sampler_set_sample": (_i32, [_vp, _u64, _u32, _u32, _i32]),
+    "sampler_play": (_i32, [_vp, _u64, _u32]),
+    "sampler_pause": (_i32, [_vp, _u64, _u32]),
+    "sampler_stop": (_i32, [_vp, _u64, _u32]),
+    "sampler_set_playhead": (_i32, [_vp, _u64, _u32, _f64]),
+    "sampler_set_loop_range": (_i32, [_vp, _u64, _u32, _u32, _f64, _f64]),
+    "sampler_set_percent_volume": (_i32, [_vp, _u64, _u32, _f32]),
+    "sampler_is_playing": (_i32, [_vp, _u64, _u32]),
     "ctx_activate": (_i32, [_vp, _u32, _u32, _u32, _u32, _vp, C.POINTER(_vp)]),
     "ctx_is_activated": (_i32, [_vp]),
     "ctx_update": (_i32, [_vp, C.POINTER(UpdateStatusC)]),

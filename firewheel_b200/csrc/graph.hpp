@@ -15,6 +15,7 @@
 #include <cstring>
 #include <deque>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <unordered_map>
 #include <unordered_set>
@@ -93,6 +94,14 @@ struct NodeParams {
     // conv reverb
     uint32_t ir_len = 0, ir_channels = 0;
     std::vector<float> ir;  // [ch][len] f32 (rounded to bf16 on the device side)
+    // sampler (sampler.rs:46-181): node-side state per voice + the node -> processor message ring. `percent` / `raw_gain`
+    // above double as the sampler's volume (sampler.rs:49-50). The stream side drains `smp_msgs` at call start.
+    struct SamplerMsg { uint32_t voice, kind, a; uint64_t x, y; };
+    bool smp_active = false;               // ActiveState is Some (sampler.rs:198-215)
+    std::vector<uint8_t> smp_playing;      // SamplerNode::playing (sampler.rs:51)
+    std::mutex smp_mu;                     // guards the two members below (main thread pushes, stream thread drains)
+    std::vector<SamplerMsg> smp_msgs;      // push order
+    std::vector<uint16_t> smp_pending;     // queued messages per voice (ring capacity 128, sampler.rs:14)
 };
 
 const char* node_debug_name(uint32_t kind);

@@ -70,6 +70,56 @@ __device__ __forceinline__ uint32_t sm_set_and_process(SmLocal& s, float val, ui
     return REC_CURVE;
 }
 
+// ---- SamplerNode control (sampler.rs:331-516) ----
+struct SmpLocal { uint32_t playing, flags, res, last_play; uint64_t playhead, ls, le; };
+
+// the message drain of sampler.rs:331-414, for one voice
+__device__ __forceinline__ void smp_apply_messages(SmpLocal& q, const SamplerCtl& sc, uint32_t v) {
+    if (sc.n_msgs == 0) return;
+    for (uint32_t i = sc.msg_off[v]; i < sc.msg_off[v + 1]; ++i) {
+        const SamplerMsgDev m = sc.msgs[i];
+        const uint64_t loop_start_or_zero = (q.flags & 1u) ? q.ls : 0ull;
+        switch (m.kind) {
+            case SMSG_SET_SAMPLE:  // :333-364
+                q.res = m.a;
+                if ((q.flags & 3u) == 3u && q.res != 0 && q.res <= sc.n_res) { q.ls = 0; q.le = sc.res_tab[q.res - 1].frames; }  // update_sample :269-281
+                if (m.x) { q.playhead = loop_start_or_zero; q.playing = 0; }
+                break;
+            case SMSG_PLAY: q.playing = 1; break;    // :365-371
+            case SMSG_PAUSE: q.playing = 0; break;   // :372-378
+            case SMSG_STOP: q.playhead = loop_start_or_zero; q.playing = 0; break;  // :379-391
+            case SMSG_SET_PLAYHEAD: q.playhead = m.x; break;  // :392-399
+            default:  // SMSG_SET_LOOP :400-412
+                if (m.a == 0) { q.flags = 0; break; }
+                if (m.a == 1) { q.flags = 3u; q.ls = 0; q.le = (q.res != 0 && q.res <= sc.n_res) ? sc.res_tab[q.res - 1].frames : 0ull; }
+                else { q.flags = 1u; q.ls = m.x; q.le = m.y; }
+                if (q.playhead >= q.ls && q.playhead < q.le) q.playhead = q.ls;
+                break;
+        }
+    }
+}
+
+// the playing branch of sampler.rs:445-516: advances the playhead by one block, says what the block plays.
+// Returns false when the block is cleared instead (non-looping sample already at its end).
+__device__ __forceinline__ bool smp_step(SmpLocal& q, uint64_t len, uint32_t frames, SmpRec* r, bool& changed) {
+    if (q.flags & 1u) {  // :445-484
+        if (q.playhead >= q.le) q.playhead = q.ls;
+        const uint64_t left = q.le - q.playhead;
+        const uint32_t first = left < (uint64_t)frames ? (uint32_t)left : frames;
+        r->p0 = q.playhead; r->first = first;
+        if (first < frames) { q.playhead = q.ls + (frames - first); r->mode = SMP_PLAY_WRAP; }
+        else { q.playhead += frames; r->mode = SMP_PLAY; }
+        return true;
+    }
+    if (q.playhead >= len) { q.playing = 0; changed = true; r->p0 = 0; r->first = 0; r->mode = SMP_CLEAR; return false; }  // :486-497
+    const uint64_t left = len - q.playhead;
+    const uint32_t copy = left < (uint64_t)frames ? (uint32_t)left : frames;
+    r->p0 = q.playhead; r->first = copy;
+    if (copy < frames) { q.playing = 0; q.playhead = 0; changed = true; r->mode = SMP_PLAY_ZERO_TAIL; }  // :503-513
+    else { q.playhead += frames; r->mode = SMP_PLAY; }
+    return true;
+}
+
 __global__ void __launch_bounds__(128) control_kernel(const __grid_constant__ ControlArgs a) {
     pdl_launch_dependents();  // the data kernel may start loading samples now; it waits for us before reading records
     pdl_wait();               // the previous call's data kernels still read the record buffers we are about to rewrite
@@ -77,24 +127,51 @@ __global__ void __launch_bounds__(128) control_kernel(const __grid_constant__ Co
     const uint32_t V = a.num_voices;
     if (v >= V) return;
     const CtlTables& tb = a.tables;
-    const uint32_t NS = tb.n_smoothers, F = a.block_frames;
+    const uint32_t NS = tb.n_smoothers, F = a.block_frames, NSMP = tb.n_samplers;
     const uint32_t n_blocks = (a.frames + F - 1) / F;
+    uint16_t* slot_of = const_cast<uint16_t*>(a.rec.slot_of);
 
     SmLocal sm[kMaxSmoothers];
     for (uint32_t s = 0; s < NS; ++s) { sm[s].input = tb.sm_input[s][v]; sm[s].last = tb.sm_last[s][v]; sm[s].status = tb.sm_status[s][v]; }
+    SmpLocal sl[kMaxSamplers];
+    for (uint32_t s = 0; s < NSMP; ++s) {
+        const SamplerCtl& sc = tb.smp[s];
+        sl[s].playing = sc.playing[v]; sl[s].playhead = sc.playhead[v]; sl[s].flags = sc.loop_flags[v]; sl[s].ls = sc.loop_start[v]; sl[s].le = sc.loop_end[v];
+        sl[s].res = sc.res[v]; sl[s].last_play = 0;
+        smp_apply_messages(sl[s], sc, v);
+    }
     uint64_t flags = a.flags[v];
     uint64_t gout_mask = 0;
-    uint32_t steady = 0xffffffffu, k = 0, last_modes = 0;
+    uint32_t steady = 0xffffffffu, k = 0, last_modes = 0, slot = 0;
+    bool steady_mode = false;
     float last_vals[kMaxSmoothers];
     for (uint32_t s = 0; s < NS; ++s) last_vals[s] = 0.0f;
     uint64_t last_sum_mask[kMaxSumMasks];
     for (int s = 0; s < kMaxSumMasks; ++s) last_sum_mask[s] = 0;
 
     for (; k < n_blocks; ++k) {
-        if (k >= a.rec.kt_max) { *a.rec.error = 1; break; }
         const uint32_t frames = min(F, a.frames - k * F);
-        bool changed = false;  // smoother state moved during this block
-        const uint64_t flags0 = flags;  // the block is a pure function of (flags, smoother state): equal at both ends => it replays
+        if (steady_mode) {
+            // Nothing but sampler playheads moves. The block replays the steady record unless a non-looping sample
+            // reaches its end in it (sampler.rs:486-513), which starts a new transient.
+            bool evt = false;
+            for (uint32_t s = 0; s < NSMP; ++s)
+                if (sl[s].last_play && !(sl[s].flags & 1u) && sl[s].playhead + frames > tb.smp[s].res_tab[sl[s].res - 1].frames) evt = true;
+            if (!evt) {
+                for (uint32_t s = 0; s < NSMP; ++s) {
+                    SmpRec r; r.p0 = 0; r.first = 0; r.mode = SMP_CLEAR;
+                    bool dummy = false;
+                    if (sl[s].last_play) smp_step(sl[s], tb.smp[s].res_tab[sl[s].res - 1].frames, frames, &r, dummy);
+                    tb.smp[s].rec[(size_t)k * V + v] = r;
+                }
+                slot_of[(size_t)k * V + v] = (uint16_t)slot;
+                continue;
+            }
+            steady_mode = false; steady = 0xffffffffu; ++slot;
+        }
+        if (slot >= a.rec.kt_max) { *a.rec.error = 1; break; }
+        bool changed = false;  // smoother / sampler transport state moved during this block
+        const uint64_t flags0 = flags;  // the block is a pure function of (flags, that state): equal at both ends => it replays
         uint32_t modes = 0;
         for (uint32_t n = 0; n < tb.n_nodes; ++n) {
             const CtlNode nd = tb.nodes[n];
@@ -104,7 +181,7 @@ __global__ void __launch_bounds__(128) control_kernel(const __grid_constant__ Co
                 if (tb.in_clear[nd.in_off + i]) flags |= bit;
                 if (flags & bit) in_mask |= 1ull << i;
             }
-            if (nd.mask_slot) { a.rec.sum_masks[((size_t)k * a.rec.n_sum_masks + (nd.mask_slot - 1)) * V + v] = in_mask; last_sum_mask[nd.mask_slot - 1] = in_mask; }
+            if (nd.mask_slot) { a.rec.sum_masks[((size_t)slot * a.rec.n_sum_masks + (nd.mask_slot - 1)) * V + v] = in_mask; last_sum_mask[nd.mask_slot - 1] = in_mask; }
             uint64_t out_mask = 0;  // processor.rs:233 NONE_SILENT
             switch (nd.kind) {
                 case FW_NODE_VOLUME: {
@@ -116,7 +193,7 @@ __global__ void __launch_bounds__(128) control_kernel(const __grid_constant__ Co
                         out_mask = all_silent_mask(nd.n_out);
                     } else {
                         float cv; bool smoothing;
-                        float* curve = a.rec.curves + ((size_t)(k * NS + nd.sm0) * V + v) * F;
+                        float* curve = a.rec.curves + ((size_t)(slot * NS + nd.sm0) * V + v) * F;
                         uint32_t m = sm_set_and_process(s, g, frames, a.a, a.b, a.eps, curve, &cv, &smoothing, changed);
                         if (!smoothing && cv < 0.00001f) {  // volume.rs:104-108
                             m = REC_CLEAR; out_mask = all_silent_mask(nd.n_out);
@@ -124,7 +201,7 @@ __global__ void __launch_bounds__(128) control_kernel(const __grid_constant__ Co
                             out_mask = in_mask;  // volume.rs:110
                         }
                         modes |= m << (2 * nd.sm0);
-                        a.rec.vals[(size_t)(k * NS + nd.sm0) * V + v] = cv; last_vals[nd.sm0] = cv;
+                        a.rec.vals[(size_t)(slot * NS + nd.sm0) * V + v] = cv; last_vals[nd.sm0] = cv;
                     }
                     break;
                 }
@@ -137,15 +214,37 @@ __global__ void __launch_bounds__(128) control_kernel(const __grid_constant__ Co
                     } else {
                         float cv; bool smoothing;
                         uint32_t m = sm_set_and_process(sm[nd.sm0], gl, frames, a.a, a.b, a.eps,
-                                                        a.rec.curves + ((size_t)(k * NS + nd.sm0) * V + v) * F, &cv, &smoothing, changed);
+                                                        a.rec.curves + ((size_t)(slot * NS + nd.sm0) * V + v) * F, &cv, &smoothing, changed);
                         modes |= m << (2 * nd.sm0);
-                        a.rec.vals[(size_t)(k * NS + nd.sm0) * V + v] = cv; last_vals[nd.sm0] = cv;
+                        a.rec.vals[(size_t)(slot * NS + nd.sm0) * V + v] = cv; last_vals[nd.sm0] = cv;
                         m = sm_set_and_process(sm[nd.sm1], gr, frames, a.a, a.b, a.eps,
-                                               a.rec.curves + ((size_t)(k * NS + nd.sm1) * V + v) * F, &cv, &smoothing, changed);
+                                               a.rec.curves + ((size_t)(slot * NS + nd.sm1) * V + v) * F, &cv, &smoothing, changed);
                         modes |= m << (2 * nd.sm1);
-                        a.rec.vals[(size_t)(k * NS + nd.sm1) * V + v] = cv; last_vals[nd.sm1] = cv;
+                        a.rec.vals[(size_t)(slot * NS + nd.sm1) * V + v] = cv; last_vals[nd.sm1] = cv;
                         out_mask = in_mask;
                     }
+                    break;
+                }
+                case FW_NODE_SAMPLER: {  // sampler.rs:416-559
+                    SmpLocal& q = sl[nd.sm1];
+                    const SamplerCtl& sc = tb.smp[nd.sm1];
+                    SmpRec r; r.p0 = 0; r.first = 0; r.mode = SMP_CLEAR;
+                    bool play = false; uint32_t sch = 0;
+                    if (q.res != 0 && q.res <= sc.n_res && q.playing) {
+                        const ResDesc rd = sc.res_tab[q.res - 1];
+                        sch = rd.channels;
+                        float cv; bool smoothing;
+                        float* curve = a.rec.curves + ((size_t)(slot * NS + nd.sm0) * V + v) * F;
+                        const uint32_t m = sm_set_and_process(sm[nd.sm0], tb.sm_target[nd.sm0][v], frames, a.a, a.b, a.eps, curve, &cv, &smoothing, changed);  // :432-433
+                        modes |= m << (2 * nd.sm0);
+                        a.rec.vals[(size_t)(slot * NS + nd.sm0) * V + v] = cv; last_vals[nd.sm0] = cv;
+                        if (smoothing || !(cv < 0.00001f)) play = smp_step(q, rd.frames, frames, &r, changed);  // :437-443 muted => clear, playhead stays
+                    }
+                    if (!play) out_mask = all_silent_mask(nd.n_out);
+                    else if (nd.n_out > sch && !(nd.n_out == 2 && sch == 1))  // :545-559: channels past the sample's are zeroed and flagged
+                        out_mask = all_silent_mask(nd.n_out) & ~all_silent_mask(sch);
+                    q.last_play = play ? 1u : 0u;
+                    sc.rec[(size_t)k * V + v] = r;
                     break;
                 }
                 case FW_NODE_SUM:  // sum.rs:52-65; the unrolled / generic sums never write the mask (Q7)
@@ -169,9 +268,16 @@ __global__ void __launch_bounds__(128) control_kernel(const __grid_constant__ Co
                 flags = (out_mask >> i) & 1ull ? (flags | bit) : (flags & ~bit);
             }
         }
-        a.rec.modes[(size_t)k * V + v] = modes;
+        a.rec.modes[(size_t)slot * V + v] = modes;
         last_modes = modes;
-        if (!changed && flags == flags0) { steady = k; break; }  // nothing moved: every later block replays this record
+        if (slot_of) slot_of[(size_t)k * V + v] = (uint16_t)slot;
+        if (!changed && flags == flags0) {  // nothing moved: later blocks replay this record
+            steady = k;
+            if (NSMP == 0) break;
+            steady_mode = true;
+        } else {
+            ++slot;
+        }
     }
     if (steady == 0xffffffffu) steady = (k == 0 ? 0 : min(k, n_blocks) - 1);
     a.rec.steady_k[v] = steady;
@@ -180,6 +286,10 @@ __global__ void __launch_bounds__(128) control_kernel(const __grid_constant__ Co
     for (uint32_t s = 0; s < a.rec.n_sum_masks; ++s) a.rec.st_sum_masks[(size_t)s * V + v] = last_sum_mask[s];
     a.rec.gout_mask[v] = gout_mask;
     for (uint32_t s = 0; s < NS; ++s) { tb.sm_input[s][v] = sm[s].input; tb.sm_last[s][v] = sm[s].last; tb.sm_status[s][v] = sm[s].status; }
+    for (uint32_t s = 0; s < NSMP; ++s) {
+        const SamplerCtl& sc = tb.smp[s];
+        sc.playing[v] = sl[s].playing; sc.playhead[v] = sl[s].playhead; sc.loop_flags[v] = sl[s].flags; sc.loop_start[v] = sl[s].ls; sc.loop_end[v] = sl[s].le; sc.res[v] = sl[s].res;
+    }
     a.flags[v] = flags;
 }
 
@@ -206,6 +316,12 @@ template <> struct VecT<1> {
     static __device__ __forceinline__ void load_ca(const float* p, float (&x)[1]) { x[0] = __ldg(p); }
     static __device__ __forceinline__ void store(float* p, const float (&x)[1]) { __stcs(p, x[0]); }
 };
+
+// record slot of block k of voice v (see Records::slot_of)
+__device__ __forceinline__ uint32_t rec_slot(const Records& r, uint32_t v, uint32_t k, uint32_t V) {
+    if (r.slot_of != nullptr) return r.slot_of[(size_t)k * V + v];
+    return min(k, r.steady_k[v]);
+}
 
 struct RecView {  // per-voice record access, either from the CTA's smem stage or straight from global
     uint32_t kk, modes;
@@ -394,7 +510,7 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) chain_kernel(ChainArg
             const uint32_t v = v0 + j;
             if (v < V && t_ok) {
                 RecView r;
-                r.kk = min(k, a.rec.steady_k[v]); r.modes = a.rec.modes[(size_t)r.kk * V + v];
+                r.kk = rec_slot(a.rec, v, k, V); r.modes = a.rec.modes[(size_t)r.kk * V + v];
                 r.vals = a.rec.vals + (size_t)r.kk * NS * V + v; r.stride = V;
                 apply_chain<VEC>(a, r, v, t_in_block, xs[j]);
             }
@@ -479,7 +595,7 @@ __global__ void __launch_bounds__(128) sum_kernel(const __grid_constant__ SumArg
     uint64_t mask = 0;
     if (a.mask_slot >= 0) {
         const uint32_t k = t / a.block_frames, sk = a.rec.steady_k[v];
-        mask = k >= sk ? a.rec.st_sum_masks[(size_t)a.mask_slot * V + v] : a.rec.sum_masks[((size_t)k * a.rec.n_sum_masks + a.mask_slot) * V + v];
+        mask = k >= sk ? a.rec.st_sum_masks[(size_t)a.mask_slot * V + v] : a.rec.sum_masks[((size_t)rec_slot(a.rec, v, k, V) * a.rec.n_sum_masks + a.mask_slot) * V + v];
     }
     float acc[VEC];
     if (a.mask_slot >= 0 && (mask & a.all_mask) == a.all_mask) {
@@ -510,12 +626,69 @@ __global__ void __launch_bounds__(128) silence_fix_kernel(const __grid_constant_
     const uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) * VEC, v = blockIdx.y, T = a.frames, V = a.num_voices;
     if (t >= T) return;
     const uint32_t k = t / a.block_frames, sk = a.rec.steady_k[v];
-    const uint64_t mask = k >= sk ? a.rec.st_sum_masks[(size_t)a.mask_slot * V + v] : a.rec.sum_masks[((size_t)k * a.rec.n_sum_masks + a.mask_slot) * V + v];
+    const uint64_t mask = k >= sk ? a.rec.st_sum_masks[(size_t)a.mask_slot * V + v] : a.rec.sum_masks[((size_t)rec_slot(a.rec, v, k, V) * a.rec.n_sum_masks + a.mask_slot) * V + v];
     if ((mask & a.test) != a.test) return;
     float z[VEC];
 #pragma unroll
     for (int i = 0; i < VEC; ++i) z[i] = 0.0f;
     VecT<VEC>::store(a.out + (size_t)v * T + t, z);
+}
+
+// K-sampler: SamplerNode data plane (sampler.rs:445-559 + sample_resource.rs:337-456). One thread = VEC frames of one
+// (voice, output channel); what the block plays comes from the control kernel's SmpRec, the samples straight from the
+// resource in HBM (converted per sample_resource.rs:337-345), times the node's gain record.
+__device__ __forceinline__ float smp_fetch(const ResDesc& d, uint32_t ch, uint64_t pos) {
+    if (pos >= d.frames) return 0.0f;  // the reference panics on this slice bound; defined as 0.0 here and in the oracle
+    switch (d.fmt) {
+        case FW_SAMPLE_F32_PLANAR: return static_cast<const float*>(d.data)[(size_t)ch * d.frames + pos];
+        case FW_SAMPLE_F32_INTERLEAVED: return static_cast<const float*>(d.data)[pos * d.channels + ch];
+        case FW_SAMPLE_I16_INTERLEAVED: return __fmul_rn((float)static_cast<const int16_t*>(d.data)[pos * d.channels + ch], 1.0f / 32767.0f);
+        case FW_SAMPLE_U16_INTERLEAVED: return __fsub_rn(__fmul_rn((float)static_cast<const uint16_t*>(d.data)[pos * d.channels + ch], 2.0f / 65535.0f), 1.0f);
+        case FW_SAMPLE_I16_PLANAR: return __fmul_rn((float)static_cast<const int16_t*>(d.data)[(size_t)ch * d.frames + pos], 1.0f / 32767.0f);
+        default: return __fsub_rn(__fmul_rn((float)static_cast<const uint16_t*>(d.data)[(size_t)ch * d.frames + pos], 2.0f / 65535.0f), 1.0f);
+    }
+}
+template <int VEC>
+__global__ void __launch_bounds__(128) sampler_kernel(const __grid_constant__ SamplerArgs a) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) * VEC, v = blockIdx.y, c = blockIdx.z, T = a.frames, V = a.num_voices, F = a.block_frames;
+    if (t >= T) return;
+    const uint32_t k = t / F, f0 = t - k * F;
+    const SmpRec r = a.srec[(size_t)k * V + v];
+    float y[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) y[i] = 0.0f;
+    float* dst = a.out[c] + (size_t)v * a.out_vstride + t;
+    if (r.mode == SMP_CLEAR) { VecT<VEC>::store(dst, y); return; }  // clear_all_outputs
+    const ResDesc d = a.res_tab[a.res[v] - 1];
+    const uint32_t filled = min(a.n_out, d.channels);
+    uint32_t src_ch = c;
+    if (c >= filled) {
+        if (a.n_out == 2 && d.channels == 1) src_ch = 0;              // :546-551 mono sample, stereo node: duplicate
+        else { VecT<VEC>::store(dst, y); return; }                    // :552-558 zeroed (and flagged by the control kernel)
+    }
+    const uint32_t kk = rec_slot(a.rec, v, k, V), NS = a.rec.n_smoothers;
+    const uint32_t m = (a.rec.modes[(size_t)kk * V + v] >> (2 * a.sm)) & 3u;
+    float g[VEC];
+    if (m == REC_CURVE) {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) g[i] = a.rec.curves[((size_t)(kk * NS + a.sm) * V + v) * F + f0 + i];
+    } else {
+        const float gc = a.rec.vals[(size_t)(kk * NS + a.sm) * V + v];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) g[i] = gc;
+    }
+    const uint64_t wrap = r.mode == SMP_PLAY_WRAP ? a.loop_start[v] : 0ull;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+        const uint32_t f = f0 + i;
+        float x = 0.0f;  // ZERO_TAIL: frames past the sample's end (:509-511)
+        if (f < r.first) x = smp_fetch(d, src_ch, r.p0 + f);
+        else if (r.mode == SMP_PLAY_WRAP) x = smp_fetch(d, src_ch, wrap + (f - r.first));
+        y[i] = __fmul_rn(x, g[i]);  // :522-543
+    }
+    VecT<VEC>::store(dst, y);
 }
 
 // K-combine: radix-16 levels of the same balanced tree over partial buses [n_in][rows][T] -> [ceil(n_in/16)][rows][T].
@@ -653,6 +826,14 @@ cudaError_t launch_sum(const SumArgs& a, cudaStream_t st) {
     const bool vec4 = (a.frames % 4 == 0) && (a.block_frames % 4 == 0) && (al % 16 == 0);
     if (vec4) return launch_pdl(sum_kernel<4>, dim3((a.frames / 4 + 127) / 128, a.num_voices), dim3(128), st, a);
     return launch_pdl(sum_kernel<1>, dim3((a.frames + 127) / 128, a.num_voices), dim3(128), st, a);
+}
+cudaError_t launch_sampler(const SamplerArgs& a, cudaStream_t st) {
+    if (a.n_out == 0 || a.num_voices == 0 || a.frames == 0) return cudaSuccess;
+    uintptr_t al = 0;
+    for (uint32_t c = 0; c < a.n_out; ++c) al |= reinterpret_cast<uintptr_t>(a.out[c]);
+    const bool vec4 = (a.frames % 4 == 0) && (a.block_frames % 4 == 0) && (al % 16 == 0) && (a.out_vstride % 4 == 0);
+    if (vec4) return launch_pdl(sampler_kernel<4>, dim3((a.frames / 4 + 127) / 128, a.num_voices, a.n_out), dim3(128), st, a);
+    return launch_pdl(sampler_kernel<1>, dim3((a.frames + 127) / 128, a.num_voices, a.n_out), dim3(128), st, a);
 }
 cudaError_t launch_silence_fix(const SilenceFixArgs& a, cudaStream_t st) {
     const bool vec4 = (a.frames % 4 == 0) && (a.block_frames % 4 == 0) && (reinterpret_cast<uintptr_t>(a.out) % 16 == 0);

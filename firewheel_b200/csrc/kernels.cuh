@@ -14,6 +14,7 @@ cudaError_t launch_control(const ControlArgs& a, cudaStream_t st);
 cudaError_t launch_chain(const ChainArgs& a, bool bus, cudaStream_t st);
 uint32_t chain_voice_groups(uint32_t num_voices);  // partial buses produced by the bus variant
 cudaError_t launch_sum(const SumArgs& a, cudaStream_t st);
+cudaError_t launch_sampler(const SamplerArgs& a, cudaStream_t st);
 cudaError_t launch_silence_fix(const SilenceFixArgs& a, cudaStream_t st);
 cudaError_t launch_combine(const float* pin, float* pout, uint32_t n_in, uint32_t rows, uint32_t T, cudaStream_t st);
 cudaError_t launch_deinterleave(const float* inter, float* planar, uint32_t V, uint32_t C, uint32_t T, cudaStream_t st);

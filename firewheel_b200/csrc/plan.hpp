@@ -18,6 +18,8 @@ constexpr int kMaxCtlNodes = 64;
 constexpr int kMaxCtlPorts = 512;
 constexpr int kMaxSumMasks = 32;    // generic lowering: nodes whose data-plane body depends on the per-block input silence mask
 
+constexpr int kMaxSamplers = 4;     // SamplerNodes per voice graph
+
 enum SmStatus : uint32_t { SM_INACTIVE = 0, SM_ACTIVE = 1, SM_DEACTIVATING = 2 };   // smoother.rs:29-39
 enum RecMode : uint32_t { REC_CONST = 0, REC_CLEAR = 1, REC_CURVE = 2 };
 
@@ -28,13 +30,34 @@ struct ChainProgram { uint32_t n_ops, c_in, c_out, pad; ChainOp ops[kMaxChainOps
 struct CtlNode {
     uint8_t kind, n_in, n_out, mask_slot;  // mask_slot: 1 + index into Records::sum_masks, 0 = none
     uint16_t in_off, out_off;   // into in_buf / in_clear / out_buf
-    int16_t sm0, sm1;           // smoother indices (-1: none)
+    int16_t sm0, sm1;           // smoother indices (-1: none); SamplerNode: sm1 = index into CtlTables::smp
+};
+
+// ---- SamplerNode (sampler.rs:283-560) on the device ----
+// Sample resources (sample_resource.rs): one descriptor per uploaded resource; handles are index + 1.
+struct ResDesc { const void* data; uint64_t frames; uint32_t channels, fmt; };  // fmt: fw_sample_format
+// NodeToProcessorMsg (sampler.rs:21-28) with seconds already converted to frames on the host (pure f64 arithmetic)
+enum SmpMsgKind : uint32_t { SMSG_SET_SAMPLE = 0, SMSG_PLAY = 1, SMSG_PAUSE = 2, SMSG_STOP = 3, SMSG_SET_PLAYHEAD = 4, SMSG_SET_LOOP = 5 };
+struct SamplerMsgDev { uint32_t kind, a; uint64_t x, y; };  // SET_SAMPLE: a = handle, x = stop_playback; SET_PLAYHEAD: x = frame; SET_LOOP: a = fw_loop_mode, x = start, y = end
+// What one block of one voice plays: frames [0, first) come from resource frames p0.., the rest from the loop start
+// (WRAP), or is zero (ZERO_TAIL, the sample ended), sampler.rs:445-516. CLEAR: clear_all_outputs.
+enum SmpMode : uint32_t { SMP_CLEAR = 0, SMP_PLAY = 1, SMP_PLAY_WRAP = 2, SMP_PLAY_ZERO_TAIL = 3 };
+struct SmpRec { uint64_t p0; uint32_t first, mode; };
+struct SamplerCtl {
+    // per-voice processor state (SamplerProcessor fields sampler.rs:283-297), persistent across calls
+    uint32_t* playing; uint64_t* playhead; uint32_t* loop_flags;  // bit0: loop_range.is_some(), bit1: full_range
+    uint64_t* loop_start; uint64_t* loop_end; uint32_t* res;      // res: resource handle, 0 = None
+    // per call
+    const ResDesc* res_tab; const SamplerMsgDev* msgs; const uint32_t* msg_off;  // messages of voice v: [msg_off[v], msg_off[v+1])
+    SmpRec* rec;                                                   // [block][voice]
+    uint32_t n_res, n_msgs, n_out, pad;
 };
 struct CtlTables {
     uint32_t n_nodes, n_smoothers, n_buffers, pad;
     CtlNode nodes[kMaxCtlNodes];
     uint8_t in_buf[kMaxCtlPorts], in_clear[kMaxCtlPorts], out_buf[kMaxCtlPorts];
     // per-smoother state (SoA over voices, owned by the node's device state) and its target parameter
+    SamplerCtl smp[kMaxSamplers]; uint32_t n_samplers, pad2;
     float* sm_input[kMaxSmoothers];
     float* sm_last[kMaxSmoothers];
     uint32_t* sm_status[kMaxSmoothers];
@@ -53,6 +76,20 @@ struct Records {
     uint64_t* sum_masks; uint64_t* st_sum_masks;  // [k][slot][v] and the steady record [slot][v]
     uint32_t n_sum_masks, pad_;
     uint32_t kt_max, n_smoothers;
+    // Graphs with SamplerNodes: a sample that ends mid-call starts a new transient, so "record of block k" is no longer
+    // min(k, steady_k): slot_of[k][v] names the record slot explicitly (null for graphs without samplers). steady_k[v] is
+    // then the first block of the FINAL steady phase, and st_modes / st_vals its record, so the chain kernel's fast path
+    // still applies.
+    const uint16_t* slot_of;
+};
+
+// SamplerNode data plane: out[c] + v * out_vstride is channel c of voice v ([T] floats).
+struct SamplerArgs {
+    float* out[64]; uint64_t out_vstride;
+    uint32_t n_out, num_voices, frames, block_frames;
+    const SmpRec* srec; const uint32_t* res; const uint64_t* loop_start; const ResDesc* res_tab;
+    int32_t sm, pad;   // the node's gain smoother
+    Records rec;
 };
 
 struct ControlArgs {

@@ -66,6 +66,29 @@ template <class T, size_t N = 16> struct Spsc {
     }
 };
 
+// Sample resources of one context ("Arc<dyn SampleResource>", sample_resource.rs): uploaded once, referenced by handle.
+struct ResTable {
+    int device = 0; std::mutex mu;
+    std::vector<ResDesc> host; std::vector<void*> allocs;  // descriptors and the device copies of the sample data
+    ResDesc* d_tab = nullptr; std::vector<void*> retired;   // device table (re-built on every add; old ones stay valid for in-flight calls)
+    ~ResTable() { cudaSetDevice(device); for (void* q : allocs) cudaFree(q); for (void* q : retired) cudaFree(q); cudaFree(d_tab); }
+    uint32_t add(uint32_t fmt, uint32_t channels, uint64_t frames, const void* data) {
+        const size_t bytes = (size_t)channels * frames * (fmt <= FW_SAMPLE_F32_INTERLEAVED ? 4 : 2);
+        cudaSetDevice(device);
+        void* d = nullptr;
+        if (!FW_CUDA(cudaMalloc(&d, bytes)) || !FW_CUDA(cudaMemcpy(d, data, bytes, cudaMemcpyHostToDevice))) { cudaFree(d); return 0; }
+        std::lock_guard<std::mutex> lk(mu);
+        allocs.push_back(d); host.push_back(ResDesc{d, frames, channels, fmt});
+        ResDesc* nt = nullptr;
+        if (!FW_CUDA(cudaMalloc(&nt, sizeof(ResDesc) * host.size())) || !FW_CUDA(cudaMemcpy(nt, host.data(), sizeof(ResDesc) * host.size(), cudaMemcpyHostToDevice))) { cudaFree(nt); host.pop_back(); return 0; }
+        if (d_tab) retired.push_back(d_tab);
+        d_tab = nt;
+        return (uint32_t)host.size();
+    }
+    void snapshot(const ResDesc** tab, uint32_t* n) { std::lock_guard<std::mutex> lk(mu); *tab = d_tab; *n = (uint32_t)host.size(); }
+    bool frames_of(uint32_t handle, uint64_t* frames) { std::lock_guard<std::mutex> lk(mu); if (handle == 0 || handle > host.size()) return false; *frames = host[handle - 1].frames; return true; }
+};
+
 struct NodeDeviceState {
     int device = 0; uint32_t kind = 0, V = 0, n_sm = 0;
     std::shared_ptr<NodeParams> params;
@@ -83,15 +106,24 @@ struct NodeDeviceState {
     // conv reverb: Toeplitz-expanded IR and the ping-pong bf16 sample history (reverb.cu)
     void* d_bt = nullptr; void* d_xh[2] = {nullptr, nullptr}; uint32_t xh_cur = 0, xh_cursor = 0, xh_pitch = 0;  // cursor: where the next block is appended
     static constexpr uint32_t kReverbMaxFrames = 65536;  // longest call the history buffers are sized for
+    // sampler: per-voice SamplerProcessor state (sampler.rs:283-297) + this call's messages / resource table / block records
+    std::shared_ptr<ResTable> res_table;
+    uint32_t* d_playing = nullptr; uint64_t* d_playhead = nullptr; uint32_t* d_loop_flags = nullptr; uint64_t* d_loop_start = nullptr; uint64_t* d_loop_end = nullptr; uint32_t* d_res = nullptr;
+    SamplerMsgDev* d_msgs = nullptr; size_t cap_msgs = 0; uint32_t* d_msg_off = nullptr; uint32_t cur_n_msgs = 0;
+    const ResDesc* cur_tab = nullptr; uint32_t cur_n_res = 0;
+    SmpRec* d_srec = nullptr; size_t cap_srec = 0;
+    std::vector<SamplerMsgDev> h_msgs; std::vector<uint32_t> h_off; std::vector<NodeParams::SamplerMsg> h_drain;
     ~NodeDeviceState() {
         cudaSetDevice(device);
         for (int i = 0; i < 2; ++i) { cudaFree(d_target[i]); cudaFree(sm_input[i]); cudaFree(sm_last[i]); cudaFree(sm_status[i]); }
         cudaFree(d_coeffs); cudaFree(d_state); cudaFree(d_ring); cudaFree(d_bt); cudaFree(d_xh[0]); cudaFree(d_xh[1]);
+        cudaFree(d_playing); cudaFree(d_playhead); cudaFree(d_loop_flags); cudaFree(d_loop_start); cudaFree(d_loop_end); cudaFree(d_res);
+        cudaFree(d_msgs); cudaFree(d_msg_off); cudaFree(d_srec);
     }
-    const std::vector<float>& host_target(int i) const { return kind == FW_NODE_VOLUME ? params->raw_gain : (i == 0 ? params->gain_l : params->gain_r); }
+    const std::vector<float>& host_target(int i) const { return (kind == FW_NODE_VOLUME || kind == FW_NODE_SAMPLER) ? params->raw_gain : (i == 0 ? params->gain_l : params->gain_r); }
     // ParamSmoother::new(val): input = last_output = val, Inactive (smoother.rs:93-112; volume.rs:67-75)
     bool create() {
-        n_sm = kind == FW_NODE_VOLUME ? 1 : kind == FW_NODE_PAN ? 2 : 0;
+        n_sm = (kind == FW_NODE_VOLUME || kind == FW_NODE_SAMPLER) ? 1 : kind == FW_NODE_PAN ? 2 : 0;
         for (uint32_t i = 0; i < n_sm; ++i) {
             d_target[i] = dev_alloc<float>(V); sm_input[i] = dev_alloc<float>(V); sm_last[i] = dev_alloc<float>(V); sm_status[i] = dev_alloc<uint32_t>(V);
             if (!d_target[i] || !sm_input[i] || !sm_last[i] || !sm_status[i]) return false;
@@ -121,11 +153,44 @@ struct NodeDeviceState {
             cudaFree(d_ir);
             if (!ok) return false;
         }
+        if (kind == FW_NODE_SAMPLER) {  // SamplerProcessor::new (sampler.rs:300-320): not playing, playhead 0, no loop, no sample
+            d_playing = dev_alloc<uint32_t>(V); d_playhead = dev_alloc<uint64_t>(V); d_loop_flags = dev_alloc<uint32_t>(V);
+            d_loop_start = dev_alloc<uint64_t>(V); d_loop_end = dev_alloc<uint64_t>(V); d_res = dev_alloc<uint32_t>(V); d_msg_off = dev_alloc<uint32_t>((size_t)V + 1);
+            if (!d_playing || !d_playhead || !d_loop_flags || !d_loop_start || !d_loop_end || !d_res || !d_msg_off) return false;
+            std::lock_guard<std::mutex> lk(params->smp_mu);
+            params->smp_active = true;  // activate() creates the rings (sampler.rs:204-212)
+            params->smp_msgs.clear(); std::fill(params->smp_pending.begin(), params->smp_pending.end(), (uint16_t)0);
+        }
         uploaded_version = params->version;
         return true;
     }
+    // stream side, first block of a call: drain the node -> processor ring (sampler.rs:331) into device memory, grouped by
+    // voice (stable: per-voice order is push order), and pin the resource table this call reads
+    bool snapshot_sampler(cudaStream_t st) {
+        h_drain.clear();
+        {
+            std::lock_guard<std::mutex> lk(params->smp_mu);
+            if (!params->smp_msgs.empty()) { h_drain.swap(params->smp_msgs); std::fill(params->smp_pending.begin(), params->smp_pending.end(), (uint16_t)0); }
+        }
+        res_table->snapshot(&cur_tab, &cur_n_res);
+        cur_n_msgs = (uint32_t)h_drain.size();
+        if (cur_n_msgs == 0) return true;
+        std::stable_sort(h_drain.begin(), h_drain.end(), [](const NodeParams::SamplerMsg& x, const NodeParams::SamplerMsg& y) { return x.voice < y.voice; });
+        h_msgs.resize(cur_n_msgs); h_off.assign((size_t)V + 1, 0);
+        for (uint32_t i = 0; i < cur_n_msgs; ++i) { const auto& m = h_drain[i]; h_msgs[i] = SamplerMsgDev{m.kind, m.a, m.x, m.y}; h_off[m.voice + 1]++; }
+        for (uint32_t v = 0; v < V; ++v) h_off[v + 1] += h_off[v];
+        if (cur_n_msgs > cap_msgs) {
+            cudaStreamSynchronize(st); cudaFree(d_msgs); d_msgs = nullptr; cap_msgs = 0;
+            const size_t want = std::max<size_t>(cur_n_msgs, 1024);
+            if (!FW_CUDA(cudaMalloc(&d_msgs, want * sizeof(SamplerMsgDev)))) return false;
+            cap_msgs = want;
+        }
+        return FW_CUDA(cudaMemcpyAsync(d_msgs, h_msgs.data(), cur_n_msgs * sizeof(SamplerMsgDev), cudaMemcpyHostToDevice, st)) &&
+               FW_CUDA(cudaMemcpyAsync(d_msg_off, h_off.data(), ((size_t)V + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    }
     // stream side, at call start: the relaxed atomic load of volume.rs:92, batched
     bool snapshot_params(cudaStream_t st) {
+        if (kind == FW_NODE_SAMPLER && !snapshot_sampler(st)) return false;
         const uint64_t ver = params->version;
         if (ver == uploaded_version) return true;
         for (uint32_t i = 0; i < n_sm; ++i)
@@ -151,6 +216,7 @@ struct Plan {
     struct GNode { uint32_t kind = 0; std::vector<uint32_t> in_buf, out_buf; std::vector<uint8_t> in_clear; int sm0 = -1, sm1 = -1, mask_slot = -1;
                    float f0 = 0.0f; std::shared_ptr<NodeDeviceState> st; };
     bool generic = false; std::vector<GNode> gnodes; uint32_t num_buffers = 0;
+    std::vector<std::shared_ptr<NodeDeviceState>> samplers;  // index = CtlTables::smp index
     bool bus = false; uint32_t n_sm = 0, c_in = 0, c_out = 0, num_voices = 0, block_frames = 0;
     Records rec{};
     uint64_t* d_bus_mask = nullptr;
@@ -201,6 +267,7 @@ struct fw_ctx {
     std::unique_ptr<Graph> graph;
     std::map<uint64_t, std::shared_ptr<NodeDeviceState>> node_states;  // activated nodes by packed id
     std::string last_error;
+    std::shared_ptr<ResTable> res;  // sample resources (created lazily)
     Schedule dbg_schedule; bool dbg_valid = false;
     // ActiveState (context.rs:17-27)
     bool active = false; std::shared_ptr<Channels> ch; uint32_t sample_rate = 0, max_block_frames = 0, n_in = 0, n_out = 0;
@@ -218,6 +285,7 @@ struct fw_processor {
     size_t cap_in = 0, cap_out = 0, cap_inter = 0, cap_part[2] = {0, 0};
     float* d_tmp[2] = {nullptr, nullptr}; size_t cap_tmp[2] = {0, 0};  // inter-stage scratch
     float* d_pool = nullptr; size_t cap_pool = 0;  // generic lowering: [buffer][V][T]
+    uint16_t* d_slot_of = nullptr; size_t cap_slot_of = 0;  // sampler graphs: record slot per (block, voice)
     // multi-GPU master bus: voices shard by rank; the per-rank buses are all-gathered and tree-summed in rank order
     void* nccl_comm = nullptr; int rank = 0, world = 1;
     float *d_bus_local = nullptr, *d_gather = nullptr; size_t cap_bus_local = 0, cap_gather = 0;
@@ -225,7 +293,8 @@ struct fw_processor {
     cudaStream_t side = nullptr; cudaEvent_t ev_bus_ready = nullptr, ev_exchange_done = nullptr; bool exchange_pending = false;
     // peer-memory exchange (exchange.cu): IPC-mapped mailboxes of all ranks; falls back to the NCCL all-gather when off
     struct P2P { bool on = false; uint8_t* base[16] = {}; size_t cap = 0; uint32_t epoch = 0; uint32_t* counters = nullptr;
-                 float* part[2][2] = {}; size_t cap_part[2][2] = {}; } p2p;
+                 float* part[2][2] = {}; size_t cap_part[2][2] = {};
+                 bool use_events = true; cudaEvent_t ev_done[2] = {}; bool done_valid[2] = {false, false}; } p2p;
     uint64_t* h_masks = nullptr; uint32_t* h_err = nullptr;  // pinned
     // optional per-kernel-class timing (CUDA events on `stream`)
     bool profiling = false; std::vector<cudaEvent_t> prof_ev; std::vector<int> prof_class; size_t prof_used = 0;
@@ -277,6 +346,16 @@ static bool lower(fw_ctx* c, const Schedule& s, Plan* plan, std::string* why) {
         }
     }
     tb.n_smoothers = n_sm;
+    for (size_t i = 0; i < n; ++i) {  // SamplerNodes: per-voice transport state lives in the node's device state
+        if (tb.nodes[i].kind != FW_NODE_SAMPLER) continue;
+        if (tb.n_samplers >= (uint32_t)kMaxSamplers) { *why = "more than 4 SamplerNodes in one voice graph"; return false; }
+        std::shared_ptr<NodeDeviceState> st = c->node_states[s.nodes[i].id.pack()];
+        SamplerCtl& sc = tb.smp[tb.n_samplers];
+        sc.playing = st->d_playing; sc.playhead = st->d_playhead; sc.loop_flags = st->d_loop_flags; sc.loop_start = st->d_loop_start; sc.loop_end = st->d_loop_end; sc.res = st->d_res;
+        sc.n_out = (uint32_t)s.nodes[i].out.size();
+        tb.nodes[i].sm1 = (int16_t)tb.n_samplers++;
+        plan->samplers.push_back(st);
+    }
     uint32_t n_sum_masks = 0;  // generic lowering only: nodes whose data-plane body needs the per-block input silence mask
 
     const SchedNode& gin = s.nodes.front();
@@ -393,6 +472,7 @@ static bool lower(fw_ctx* c, const Schedule& s, Plan* plan, std::string* why) {
     Records& r = plan->rec;
     r.n_smoothers = n_sm;
     r.kt_max = n_sm ? (8192u + F - 1) / F + 3u : 4u;  // longest ramp: ln(4/1e-6)*480 < 8192 samples, then settle/stall
+    r.kt_max += 8u * (uint32_t)plan->samplers.size();  // every sample that ends mid-call opens a short transient of its own
     r.modes = dev_alloc<uint32_t>((size_t)r.kt_max * V);
     r.vals = dev_alloc<float>((size_t)r.kt_max * (n_sm ? n_sm : 1) * V);
     r.curves = dev_alloc<float>((size_t)r.kt_max * n_sm * V * F, false);
@@ -418,6 +498,12 @@ static std::shared_ptr<NodeParams> params_from_desc(const fw_node_desc* d, uint3
         case FW_NODE_VOLUME: {  // volume.rs:16-24
             float pct = std::fmax(d->f0, 0.0f), n = std::fmax(pct, 0.0f) * (1.0f / 100.0f);
             p->percent.assign(V, pct); p->raw_gain.assign(V, n * n);
+            break;
+        }
+        case FW_NODE_SAMPLER: {  // sampler.rs:56-66
+            float pct = std::fmax(d->f0, 0.0f), n = std::fmax(pct, 0.0f) * (1.0f / 100.0f);
+            p->percent.assign(V, pct); p->raw_gain.assign(V, n * n);
+            p->smp_playing.assign(V, 0); p->smp_pending.assign(V, 0);
             break;
         }
         case FW_NODE_HARD_CLIP:  // hard_clip.rs:8-12, util.rs:21-27
@@ -539,6 +625,7 @@ int fw_graph_node_info(fw_ctx* c, fw_node_id node, fw_node_info* out) {
         node_supported_ports(r->params->kind, &out->num_min_supported_inputs, &out->num_max_supported_inputs, &out->num_min_supported_outputs, &out->num_max_supported_outputs);
         const char* name = r->id == c->graph->graph_in() ? "graph_in" : r->id == c->graph->graph_out() ? "graph_out" : node_debug_name(r->params->kind);
         std::strncpy(out->debug_name, name, sizeof(out->debug_name) - 1);
+        out->updates = r->params->kind == FW_NODE_SAMPLER;  // sampler.rs:193
     }
     return 1;
 }
@@ -583,7 +670,74 @@ template <class F> static int for_voices(NodeParams* p, uint32_t voice, F&& f) {
     p->version += 1;
     return 0;
 }
+// `(secs * sample_rate).round() as u64` (sampler.rs:250-251,394): saturating float -> int cast, NaN -> 0
+static uint64_t secs_to_frame(double secs, uint32_t sample_rate) {
+    const double f = std::round(secs * (double)sample_rate);
+    if (!(f > 0.0)) return 0;
+    if (f >= 18446744073709551616.0) return UINT64_MAX;
+    return (uint64_t)f;
+}
+// push one message for the selected voices; `gate(v)` mirrors the node-side `playing` checks (sampler.rs:82-136)
+template <class G> static int sampler_push(fw_ctx* c, fw_node_id node, uint32_t voice, NodeParams::SamplerMsg m, G&& gate) {
+    NodeParams* p = c ? params_of(c, node, FW_NODE_SAMPLER) : nullptr;
+    if (!p || (voice != FW_ALL_VOICES && voice >= p->num_voices)) return FW_SAMPLER_NOT_A_SAMPLER;
+    std::lock_guard<std::mutex> lk(p->smp_mu);
+    if (!p->smp_active) return FW_SAMPLER_NOT_ACTIVATED;
+    int rc = FW_SAMPLER_OK;
+    const uint32_t v0 = voice == FW_ALL_VOICES ? 0 : voice, v1 = voice == FW_ALL_VOICES ? p->num_voices : voice + 1;
+    for (uint32_t v = v0; v < v1; ++v) {
+        if (!gate(*p, v, /*probe=*/true)) continue;
+        if (p->smp_pending[v] >= 128) { rc = FW_SAMPLER_RING_FULL; continue; }  // rtrb push Err (sampler.rs:14)
+        m.voice = v; p->smp_msgs.push_back(m); p->smp_pending[v]++;
+        gate(*p, v, /*probe=*/false);
+    }
+    return rc;
+}
+static bool gate_always(NodeParams&, uint32_t, bool) { return true; }
 extern "C" {
+// ---- sample resources + SamplerNode (sampler.rs:46-181) --------------------------------------
+uint32_t fw_sample_resource_create(fw_ctx* c, uint32_t format, uint32_t channels, uint64_t frames, const void* data) {
+    if (!c || !data || format > FW_SAMPLE_U16_PLANAR || channels == 0 || channels > 64 || frames == 0) return 0;
+    if (!c->res) { c->res = std::make_shared<ResTable>(); c->res->device = c->cfg.device; }
+    return c->res->add(format, channels, frames, data);
+}
+int fw_sampler_set_sample(fw_ctx* c, fw_node_id node, uint32_t voice, uint32_t res, int stop_playback) {
+    uint64_t frames = 0;
+    if (!c || !c->res || !c->res->frames_of(res, &frames)) return FW_SAMPLER_BAD_ARGS;
+    return sampler_push(c, node, voice, NodeParams::SamplerMsg{0, SMSG_SET_SAMPLE, res, stop_playback ? 1ull : 0ull, 0}, gate_always);
+}
+int fw_sampler_play(fw_ctx* c, fw_node_id node, uint32_t voice) {
+    return sampler_push(c, node, voice, NodeParams::SamplerMsg{0, SMSG_PLAY, 0, 0, 0},
+                        [](NodeParams& p, uint32_t v, bool probe) { if (probe) return !p.smp_playing[v]; p.smp_playing[v] = 1; return true; });
+}
+int fw_sampler_pause(fw_ctx* c, fw_node_id node, uint32_t voice) {
+    return sampler_push(c, node, voice, NodeParams::SamplerMsg{0, SMSG_PAUSE, 0, 0, 0},
+                        [](NodeParams& p, uint32_t v, bool probe) { if (probe) return (bool)p.smp_playing[v]; p.smp_playing[v] = 0; return true; });
+}
+int fw_sampler_stop(fw_ctx* c, fw_node_id node, uint32_t voice) {
+    return sampler_push(c, node, voice, NodeParams::SamplerMsg{0, SMSG_STOP, 0, 0, 0},
+                        [](NodeParams& p, uint32_t v, bool probe) { if (probe) return (bool)p.smp_playing[v]; p.smp_playing[v] = 0; return true; });
+}
+int fw_sampler_set_playhead(fw_ctx* c, fw_node_id node, uint32_t voice, double secs) {
+    if (!c) return FW_SAMPLER_NOT_A_SAMPLER;
+    return sampler_push(c, node, voice, NodeParams::SamplerMsg{0, SMSG_SET_PLAYHEAD, 0, secs_to_frame(secs, c->sample_rate), 0}, gate_always);
+}
+int fw_sampler_set_loop_range(fw_ctx* c, fw_node_id node, uint32_t voice, uint32_t mode, double s, double e) {
+    if (!c || mode > FW_LOOP_RANGE_SECS) return FW_SAMPLER_BAD_ARGS;
+    const uint64_t fs = mode == FW_LOOP_RANGE_SECS ? secs_to_frame(s, c->sample_rate) : 0, fe = mode == FW_LOOP_RANGE_SECS ? secs_to_frame(e, c->sample_rate) : 0;
+    if (mode == FW_LOOP_RANGE_SECS && c->active && !(fs < fe)) return FW_SAMPLER_BAD_ARGS;
+    return sampler_push(c, node, voice, NodeParams::SamplerMsg{0, SMSG_SET_LOOP, mode, fs, fe}, gate_always);
+}
+int fw_sampler_set_percent_volume(fw_ctx* c, fw_node_id node, uint32_t voice, float pct) {  // sampler.rs:174-180
+    NodeParams* p = c ? params_of(c, node, FW_NODE_SAMPLER) : nullptr;
+    return for_voices(p, voice, [&](uint32_t v) { float n = std::fmax(pct, 0.0f) * (1.0f / 100.0f); p->raw_gain[v] = n * n; p->percent[v] = std::fmax(pct, 0.0f); }) == 0 ? FW_SAMPLER_OK : FW_SAMPLER_NOT_A_SAMPLER;
+}
+int fw_sampler_is_playing(fw_ctx* c, fw_node_id node, uint32_t voice) {
+    NodeParams* p = c ? params_of(c, node, FW_NODE_SAMPLER) : nullptr;
+    if (!p || voice >= p->num_voices) return FW_SAMPLER_NOT_A_SAMPLER;
+    return p->smp_playing[voice] ? 1 : 0;
+}
+
 int fw_volume_set_percent_volume(fw_ctx* c, fw_node_id node, uint32_t voice, float pct) {  // volume.rs:28-34, range.rs:32-35
     NodeParams* p = params_of(c, node, FW_NODE_VOLUME);
     return for_voices(p, voice, [&](uint32_t v) { float n = std::fmax(pct, 0.0f) * (1.0f / 100.0f); p->raw_gain[v] = n * n; p->percent[v] = std::fmax(pct, 0.0f); });
@@ -696,6 +850,7 @@ int fw_ctx_update(fw_ctx* c, fw_update_status* out) {  // context.rs:93-148
         if (msg.empty()) {
             ds = std::make_shared<NodeDeviceState>();
             ds->device = c->cfg.device; ds->kind = r->params->kind; ds->V = c->cfg.num_voices; ds->params = r->params; ds->channels = r->num_inputs;
+            if (ds->kind == FW_NODE_SAMPLER) { if (!c->res) { c->res = std::make_shared<ResTable>(); c->res->device = c->cfg.device; } ds->res_table = c->res; }
             if (!ds->create()) msg = "device allocation failed: " + g_dev_err;
         }
         if (!msg.empty()) {
@@ -788,6 +943,7 @@ static int run_bus_stage(fw_processor* p, ChainArgs& xa, uint32_t n_out, uint32_
         fw_processor::P2P& x = p->p2p;
         const uint32_t epoch = ++x.epoch;
         const int s = (int)(epoch & 1u);
+        if (x.use_events && x.done_valid[s]) cudaStreamWaitEvent(p->stream, x.ev_done[s], 0);  // K-push(e - 2) has read part[s]
         if (!ensure(&x.part[s][0], &x.cap_part[s][0], (size_t)n * n_out * T) || (n > 16 && !ensure(&x.part[s][1], &x.cap_part[s][1], (size_t)((n + 15) / 16) * n_out * T))) return FW_PROC_DEVICE_ERROR;
         xa.out = x.part[s][0];
         { ProfScope ps(p, 1); if (!FW_CUDA(launch_chain(xa, true, p->stream))) return FW_PROC_DEVICE_ERROR; }
@@ -801,22 +957,30 @@ static int run_bus_stage(fw_processor* p, ChainArgs& xa, uint32_t n_out, uint32_
                 n = (n + 15) / 16; cur ^= 1;
             }
         }
-        // device-side hand-over instead of events (an event record between kernels would break the PDL chain)
-        if (!FW_CUDA(launch_bus_signal(x.counters + 2, x.counters + 3, epoch, xa.rec.error, p->stream))) return FW_PROC_DEVICE_ERROR;
-        if (!FW_CUDA(launch_bus_wait(x.counters + 2, 1, epoch, xa.rec.error, p->side))) return FW_PROC_DEVICE_ERROR;
+        // Hand-over main -> side. Events (default) cost the PDL overlap of the next control kernel (an event record between
+        // two kernels serialises them); FW_P2P_HANDOVER=signal keeps the PDL chain with a device-word hand-over instead.
+        if (x.use_events) {
+            cudaEventRecord(p->ev_bus_ready, p->stream);
+            cudaStreamWaitEvent(p->side, p->ev_bus_ready, 0);
+        } else {
+            if (!FW_CUDA(launch_bus_signal(x.counters + 2, x.counters + 3, epoch, xa.rec.error, p->stream))) return FW_PROC_DEVICE_ERROR;
+            if (!FW_CUDA(launch_bus_wait(x.counters + 2, 1, epoch, xa.rec.error, p->side))) return FW_PROC_DEVICE_ERROR;
+            p->launches += 2;
+        }
         BusPushArgs pa{};
         pa.pin = x.part[s][cur]; pa.n_in = n; pa.rows = n_out; pa.T = T;
         for (int r = 0; r < p->world; ++r) { pa.data[r] = reinterpret_cast<float*>(x.base[r] + kMailHeader); pa.ready[r] = reinterpret_cast<uint32_t*>(x.base[r]); }
         pa.ack_local = reinterpret_cast<const uint32_t*>(x.base[p->rank] + 128); pa.counter = x.counters; pa.push_done = x.counters + 3; pa.error = xa.rec.error;
         pa.world = (uint32_t)p->world; pa.me = (uint32_t)p->rank; pa.epoch = epoch; pa.cap = (uint32_t)x.cap;
         if (!FW_CUDA(launch_bus_push(pa, p->side))) return FW_PROC_DEVICE_ERROR;
+        if (x.use_events) { cudaEventRecord(x.ev_done[s], p->side); x.done_valid[s] = true; }
         if (!FW_CUDA(launch_bus_wait(reinterpret_cast<const uint32_t*>(x.base[p->rank]) + s * 16, (uint32_t)p->world, epoch, xa.rec.error, p->side))) return FW_PROC_DEVICE_ERROR;
         BusRecvArgs ra{};
         ra.data_local = reinterpret_cast<const float*>(x.base[p->rank] + kMailHeader); ra.out = d_out; ra.rows = n_out; ra.T = T;
         for (int r = 0; r < p->world; ++r) ra.ack[r] = reinterpret_cast<uint32_t*>(x.base[r] + 128);
         ra.counter = x.counters + 1; ra.world = (uint32_t)p->world; ra.me = (uint32_t)p->rank; ra.epoch = epoch; ra.cap = (uint32_t)x.cap;
         if (!FW_CUDA(launch_bus_recv(ra, p->side))) return FW_PROC_DEVICE_ERROR;
-        p->launches += 5;
+        p->launches += 3;
         cudaEventRecord(p->ev_exchange_done, p->side);
         p->exchange_pending = true;
         return FW_PROC_OK;
@@ -936,6 +1100,17 @@ static int enqueue_generic(fw_processor* p, Plan& pl, const float* d_in, float* 
         }
         switch (gn.kind) {
             case FW_NODE_DUMMY: break;  // no outputs (rejected otherwise)
+            case FW_NODE_SAMPLER: {
+                NodeDeviceState& st = *gn.st;
+                SamplerArgs sa{};
+                for (size_t c = 0; c < gn.out_buf.size(); ++c) sa.out[c] = buf(gn.out_buf[c]);
+                sa.out_vstride = T; sa.n_out = (uint32_t)gn.out_buf.size(); sa.num_voices = V; sa.frames = T; sa.block_frames = pl.block_frames;
+                sa.srec = st.d_srec; sa.res = st.d_res; sa.loop_start = st.d_loop_start; sa.res_tab = st.cur_tab; sa.sm = gn.sm0; sa.rec = pl.rec;
+                ProfScope ps(p, 1);
+                if (!FW_CUDA(launch_sampler(sa, p->stream))) return FW_PROC_DEVICE_ERROR;
+                p->launches++;
+                break;
+            }
             case FW_NODE_VOLUME: case FW_NODE_HARD_CLIP:
                 if (!per_channel(gn, gn.kind == FW_NODE_VOLUME ? OP_GAIN : OP_CLIP)) return FW_PROC_DEVICE_ERROR;
                 for (size_t c = 0; gn.mask_slot >= 0 && c < gn.out_buf.size(); ++c) if (!silence_fix(gn, c, 1ull << c)) return FW_PROC_DEVICE_ERROR;
@@ -1055,6 +1230,8 @@ static bool p2p_setup(fw_processor* p) {
         return true;
     }
     p->p2p.counters = dev_alloc<uint32_t>(4);  // push counter, recv counter, chain_done, push_done
+    { const char* h = getenv("FW_P2P_HANDOVER"); p->p2p.use_events = !(h && std::strcmp(h, "signal") == 0); }
+    for (auto& e : p->p2p.ev_done) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     p->p2p.cap = cap; p->p2p.epoch = 0; p->p2p.on = true;
     return true;
 }
@@ -1070,7 +1247,7 @@ static void p2p_teardown(fw_processor* p) {
     }
     for (int r = 0; r < p->world; ++r) if (r != p->rank && p->p2p.base[r]) cudaIpcCloseMemHandle(p->p2p.base[r]);
     cudaFree(p->p2p.base[p->rank]); cudaFree(p->p2p.counters);
-    for (int q = 0; q < 2; ++q) { cudaFree(p->p2p.part[q][0]); cudaFree(p->p2p.part[q][1]); }
+    for (int q = 0; q < 2; ++q) { cudaFree(p->p2p.part[q][0]); cudaFree(p->p2p.part[q][1]); if (p->p2p.ev_done[q]) cudaEventDestroy(p->p2p.ev_done[q]); }
     p->p2p.on = false;
 }
 
@@ -1090,8 +1267,29 @@ static int proc_enqueue(fw_processor* p, const float* d_in, float* d_out, uint32
     if (n_in != pl.c_in || n_out != pl.c_out) { g_dev_err = "channel counts do not match the compiled graph"; return FW_PROC_BAD_ARGS; }
     for (auto& st : pl.states) if (!st->snapshot_params(p->stream)) return FW_PROC_DEVICE_ERROR;
 
+    if (!pl.samplers.empty()) {  // per-call buffers of sampler graphs: record slot per (block, voice), block records per sampler
+        const size_t KV = (size_t)((T + pl.block_frames - 1) / pl.block_frames) * V;
+        if (KV > p->cap_slot_of) {
+            cudaStreamSynchronize(p->stream); cudaFree(p->d_slot_of); p->d_slot_of = nullptr; p->cap_slot_of = 0;
+            if (!FW_CUDA(cudaMalloc(&p->d_slot_of, KV * sizeof(uint16_t)))) return FW_PROC_DEVICE_ERROR;
+            p->cap_slot_of = KV;
+        }
+        pl.rec.slot_of = p->d_slot_of;
+        for (auto& st : pl.samplers) {
+            if (KV > st->cap_srec) {
+                cudaStreamSynchronize(p->stream); cudaFree(st->d_srec); st->d_srec = nullptr; st->cap_srec = 0;
+                if (!FW_CUDA(cudaMalloc(&st->d_srec, KV * sizeof(SmpRec)))) return FW_PROC_DEVICE_ERROR;
+                st->cap_srec = KV;
+            }
+        }
+    }
     ControlArgs ca{};
-    ca.tables = pl.tables; ca.rec = pl.rec; ca.flags = pl.d_flags; ca.num_voices = V; ca.frames = T; ca.block_frames = pl.block_frames;
+    ca.tables = pl.tables; ca.rec = pl.rec;
+    for (size_t i = 0; i < pl.samplers.size(); ++i) {
+        NodeDeviceState& st = *pl.samplers[i];
+        SamplerCtl& sc = ca.tables.smp[i];
+        sc.res_tab = st.cur_tab; sc.n_res = st.cur_n_res; sc.msgs = st.d_msgs; sc.msg_off = st.d_msg_off; sc.n_msgs = st.cur_n_msgs; sc.rec = st.d_srec;
+    } ca.flags = pl.d_flags; ca.num_voices = V; ca.frames = T; ca.block_frames = pl.block_frames;
     ca.a = p->sm_a; ca.b = p->sm_b; ca.eps = p->sm_eps;
     { ProfScope ps(p, 0); if (!FW_CUDA(launch_control(ca, p->stream))) return FW_PROC_DEVICE_ERROR; }
     p->launches++;
@@ -1245,7 +1443,7 @@ void fw_processor_free(fw_processor* p) {  // Drop processor.rs:251-263
     if (p->side) { cudaStreamSynchronize(p->side); p2p_teardown(p); cudaStreamDestroy(p->side); cudaEventDestroy(p->ev_bus_ready); cudaEventDestroy(p->ev_exchange_done); }
     ProcToCtx m; m.kind = 1; m.plan = p->plan; m.user_cx = p->user_cx;
     if (!p->ch->to_ctx.push(m)) delete p->plan;
-    cudaFree(p->d_in); cudaFree(p->d_out); cudaFree(p->d_inter); cudaFree(p->d_part[0]); cudaFree(p->d_part[1]); cudaFree(p->d_flush); cudaFree(p->d_tmp[0]); cudaFree(p->d_tmp[1]); cudaFree(p->d_bus_local); cudaFree(p->d_gather); cudaFree(p->d_pool);
+    cudaFree(p->d_in); cudaFree(p->d_out); cudaFree(p->d_inter); cudaFree(p->d_part[0]); cudaFree(p->d_part[1]); cudaFree(p->d_flush); cudaFree(p->d_tmp[0]); cudaFree(p->d_tmp[1]); cudaFree(p->d_bus_local); cudaFree(p->d_gather); cudaFree(p->d_pool); cudaFree(p->d_slot_of);
     if (p->nccl_comm) g_nccl.CommDestroy(p->nccl_comm);
     cudaFreeHost(p->h_masks); cudaFreeHost(p->h_err);
     for (auto& e : p->ev) if (e) cudaEventDestroy(e);

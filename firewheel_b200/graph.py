@@ -118,6 +118,18 @@ def ConvReverbNode(ir):
     return _Node(K.NODE_CONV_REVERB, u=(ir.shape[1], ir.shape[0], 0), data=ir)
 
 
+def SamplerNode(percent_volume):  # sampler.rs:56
+    return _Node(K.NODE_SAMPLER, f=(float(percent_volume), 0.0, 0.0, 0.0))
+
+
+class SamplerError(Exception):
+    """Err(()) of the SamplerNode setters (sampler.rs:67-169), with the reason the C ABI reports."""
+
+    def __init__(self, code):
+        self.code, self.kind = code, K.SAMPLER_ERRORS.get(code, str(code))
+        super().__init__(self.kind)
+
+
 @dataclass
 class AudioGraphConfig:  # graph.rs:91-107 + batching
     num_graph_inputs: int = 0
@@ -279,6 +291,63 @@ class AudioGraph:
                 self._chk(self._lib.biquad_set_coeffs(self._ctx, node_id, voice, s, a[s].ctypes.data), "biquad")
         else:  # [voice][stage][5]
             self._chk(self._lib.biquad_set_all_coeffs(self._ctx, node_id, a.ctypes.data, a.shape[0], a.shape[1]), "biquad")
+
+
+    # ---- sample resources + SamplerNode (sample_resource.rs, sampler.rs:46-181) ----
+    _FORMATS = {("float32", False): K.SAMPLE_F32_PLANAR, ("float32", True): K.SAMPLE_F32_INTERLEAVED,
+                ("int16", True): K.SAMPLE_I16_INTERLEAVED, ("uint16", True): K.SAMPLE_U16_INTERLEAVED,
+                ("int16", False): K.SAMPLE_I16_PLANAR, ("uint16", False): K.SAMPLE_U16_PLANAR}
+
+    def create_sample_resource(self, data, interleaved=False):
+        """data: [frames][channels] when interleaved, else [channels][frames]; dtype float32 / int16 / uint16."""
+        a = np.ascontiguousarray(data)
+        if a.ndim == 1:
+            a = a[:, None] if interleaved else a[None, :]
+        fmt = self._FORMATS[(a.dtype.name, bool(interleaved))]
+        frames, channels = (a.shape[0], a.shape[1]) if interleaved else (a.shape[1], a.shape[0])
+        h = self._lib.sample_resource_create(self._ctx, fmt, channels, frames, a.ctypes.data)
+        if h == 0:
+            raise ValueError("bad sample resource")
+        return h
+
+    def _smp(self, rc):
+        if rc != 0:
+            raise SamplerError(rc)
+
+    def sampler_set_sample(self, node_id, resource, stop_playback, voice=K.FW_ALL_VOICES):  # sampler.rs:67
+        self._smp(self._lib.sampler_set_sample(self._ctx, node_id, voice, resource, int(bool(stop_playback))))
+
+    def sampler_play(self, node_id, voice=K.FW_ALL_VOICES):  # sampler.rs:82
+        self._smp(self._lib.sampler_play(self._ctx, node_id, voice))
+
+    def sampler_pause(self, node_id, voice=K.FW_ALL_VOICES):  # sampler.rs:101
+        self._smp(self._lib.sampler_pause(self._ctx, node_id, voice))
+
+    def sampler_stop(self, node_id, voice=K.FW_ALL_VOICES):  # sampler.rs:120
+        self._smp(self._lib.sampler_stop(self._ctx, node_id, voice))
+
+    def sampler_set_playhead(self, node_id, playhead_secs, voice=K.FW_ALL_VOICES):  # sampler.rs:139
+        self._smp(self._lib.sampler_set_playhead(self._ctx, node_id, voice, float(playhead_secs)))
+
+    def sampler_set_loop_range(self, node_id, loop_range, voice=K.FW_ALL_VOICES):  # sampler.rs:153
+        """loop_range: None | "full" | (start_secs, end_secs)  — Option<LoopRange> (sampler.rs:16-19)."""
+        if loop_range is None:
+            mode, s, e = K.LOOP_NONE, 0.0, 0.0
+        elif isinstance(loop_range, str):
+            mode, s, e = K.LOOP_FULL, 0.0, 0.0
+        else:
+            mode, (s, e) = K.LOOP_RANGE_SECS, loop_range
+        self._smp(self._lib.sampler_set_loop_range(self._ctx, node_id, voice, mode, float(s), float(e)))
+
+    def sampler_set_percent_volume(self, node_id, percent, voice=K.FW_ALL_VOICES):  # sampler.rs:174
+        if np.ndim(percent) == 0:
+            self._smp(self._lib.sampler_set_percent_volume(self._ctx, node_id, voice, float(percent)))
+        else:
+            for v, pc in enumerate(np.asarray(percent, dtype=np.float32)):
+                self._smp(self._lib.sampler_set_percent_volume(self._ctx, node_id, v, float(pc)))
+
+    def sampler_is_playing(self, node_id, voice=0):  # sampler.rs:163
+        return self._lib.sampler_is_playing(self._ctx, node_id, voice) == 1
 
 
 def design_rbj(lib, ftype, fc, q, gain_db, sample_rate):

@@ -75,8 +75,24 @@ enum fw_node_kind {
     FW_NODE_PAN = 6,            /* spec ours  f0 = pan in [-1,1] */
     FW_NODE_BIQUAD = 7,         /* spec ours (a11)  u0 = num_stages (<= 8) */
     FW_NODE_DELAY = 8,          /* spec ours (a12)  u0 = delay in frames */
-    FW_NODE_CONV_REVERB = 9     /* spec ours (a14)  u0 = ir_len, u1 = ir_channels, data = IR [ch][len] */
+    FW_NODE_CONV_REVERB = 9,    /* spec ours (a14)  u0 = ir_len, u1 = ir_channels, data = IR [ch][len] */
+    FW_NODE_SAMPLER = 10        /* basic_nodes/sampler.rs  f0 = percent_volume; 0 inputs, 1..64 outputs */
 };
+/* SampleResource implementations (firewheel-core/src/sample_resource.rs:28-335). Interleaved data is [frame][ch],
+ * planar ("Vec<Vec<T>>") is [ch][frame]. */
+enum fw_sample_format {
+    FW_SAMPLE_F32_PLANAR = 0,       /* Vec<Vec<f32>>            :249-266 */
+    FW_SAMPLE_F32_INTERLEAVED = 1,  /* InterleavedResourceF32   :142-197 */
+    FW_SAMPLE_I16_INTERLEAVED = 2,  /* InterleavedResourceI16   :28-83,  pcm_i16_to_f32 :337 */
+    FW_SAMPLE_U16_INTERLEAVED = 3,  /* InterleavedResourceU16   :85-140, pcm_u16_to_f32 :342 */
+    FW_SAMPLE_I16_PLANAR = 4,       /* Vec<Vec<i16>>            :199-222 */
+    FW_SAMPLE_U16_PLANAR = 5        /* Vec<Vec<u16>>            :224-247 */
+};
+/* LoopRange (sampler.rs:16-19) as passed to sampler_set_loop_range */
+enum fw_loop_mode { FW_LOOP_NONE = 0, FW_LOOP_FULL = 1, FW_LOOP_RANGE_SECS = 2 };
+/* sampler_* return codes: Ok(()) => 0; Err(()) from a full message ring (capacity 128, sampler.rs:14) => -2 */
+enum fw_sampler_status { FW_SAMPLER_OK = 0, FW_SAMPLER_NOT_A_SAMPLER = -1, FW_SAMPLER_RING_FULL = -2,
+                         FW_SAMPLER_NOT_ACTIVATED = -3 /* the reference hits todo!() */, FW_SAMPLER_BAD_ARGS = -4 };
 typedef struct fw_node_desc {
     uint32_t kind;
     uint32_t u0, u1, u2;
@@ -198,6 +214,25 @@ FW_EXPORT int FW_FN(biquad_set_coeffs)(fw_ctx* ctx, fw_node_id node, uint32_t vo
 FW_EXPORT int FW_FN(biquad_set_all_coeffs)(fw_ctx* ctx, fw_node_id node, const float* coeffs, uint32_t n_voices, uint32_t n_stages);
 /* RBJ cookbook design, f64 -> f32, host only. type: 0 lowpass 1 highpass 2 bandpass 3 notch 4 peaking 5 lowshelf 6 highshelf */
 FW_EXPORT void FW_FN(biquad_design_rbj)(uint32_t type, double fc, double q, double gain_db, double sample_rate, float* coeffs5);
+
+/* ---- sample resources + SamplerNode (sample_resource.rs, sampler.rs:46-233) ---------------
+ * A resource is uploaded once ("Arc<...>": shared by any number of voices and nodes) and lives until ctx_free.
+ * Returns a handle >= 1, or 0 on bad arguments. `data` holds channels * frames elements of the format's type. */
+FW_EXPORT uint32_t FW_FN(sample_resource_create)(fw_ctx* ctx, uint32_t format, uint32_t channels, uint64_t frames,
+                                                 const void* data);
+/* Messages to the processor side (sampler.rs:21-28); `voice` may be FW_ALL_VOICES. They are drained at the first
+ * block of the next process call, in order (sampler.rs:331-414). */
+FW_EXPORT int FW_FN(sampler_set_sample)(fw_ctx* ctx, fw_node_id node, uint32_t voice, uint32_t resource,
+                                        int stop_playback);                         /* sampler.rs:67 */
+FW_EXPORT int FW_FN(sampler_play)(fw_ctx* ctx, fw_node_id node, uint32_t voice);    /* sampler.rs:82 */
+FW_EXPORT int FW_FN(sampler_pause)(fw_ctx* ctx, fw_node_id node, uint32_t voice);   /* sampler.rs:101 */
+FW_EXPORT int FW_FN(sampler_stop)(fw_ctx* ctx, fw_node_id node, uint32_t voice);    /* sampler.rs:120 */
+FW_EXPORT int FW_FN(sampler_set_playhead)(fw_ctx* ctx, fw_node_id node, uint32_t voice, double playhead_secs); /* :139 */
+/* mode: fw_loop_mode; RANGE_SECS needs round(start*sr) < round(end*sr) (the reference underflows otherwise) */
+FW_EXPORT int FW_FN(sampler_set_loop_range)(fw_ctx* ctx, fw_node_id node, uint32_t voice, uint32_t mode,
+                                            double start_secs, double end_secs);    /* sampler.rs:153 */
+FW_EXPORT int FW_FN(sampler_set_percent_volume)(fw_ctx* ctx, fw_node_id node, uint32_t voice, float percent); /* :174 */
+FW_EXPORT int FW_FN(sampler_is_playing)(fw_ctx* ctx, fw_node_id node, uint32_t voice); /* node-side flag, sampler.rs:163 */
 
 /* ---- lifecycle (context.rs:46-211) ------------------------------------------------------- */
 /* 0 => *out_processor set (Some); 1 => already active (None) */

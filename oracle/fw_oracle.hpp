@@ -717,6 +717,174 @@ struct ConvReverbNode : AudioNode {
     }
 };
 
+// ---------------------------------------------------------------------------
+// firewheel-core/src/sample_resource.rs:1-456 — sample resources (the sampler's data source)
+// ---------------------------------------------------------------------------
+inline float pcm_i16_to_f32(int16_t s) { return (float)s * (1.0f / (float)INT16_MAX); }            // :337-340
+inline float pcm_u16_to_f32(uint16_t s) { return ((float)s * (2.0f / (float)UINT16_MAX)) - 1.0f; }  // :342-345
+enum class SampleFormat : uint32_t { F32Planar = 0, F32Interleaved = 1, I16Interleaved = 2, U16Interleaved = 3, I16Planar = 4, U16Planar = 5 };
+// One struct stands for the twelve `impl SampleResource` blocks (:33-335): interleaved data is [frame][ch], planar is
+// [ch][frame]. All of fill_buffers_interleaved (:348-401, mono / stereo / generic loops), fill_buffers_deinterleaved
+// (:404-439) and fill_buffers_deinterleaved_f32 (:442-456) reduce to: buffer c < min(buffers, channels) receives
+// convert(data[c][start_frame + i]). A read past the end of the data panics in the reference (slice bounds); here it
+// yields 0.0 — the one place this restatement defines behaviour the reference does not have.
+struct SampleResource {
+    SampleFormat fmt = SampleFormat::F32Planar; size_t channels = 1; uint64_t frames = 0;
+    std::vector<float> f32; std::vector<int16_t> i16; std::vector<uint16_t> u16;
+    size_t num_channels() const { return channels; }
+    uint64_t len_frames() const { return frames; }
+    float at(size_t ch, uint64_t frame) const {
+        if (frame >= frames) return 0.0f;
+        switch (fmt) {
+            case SampleFormat::F32Planar: return f32[ch * frames + frame];
+            case SampleFormat::F32Interleaved: return f32[frame * channels + ch];
+            case SampleFormat::I16Interleaved: return pcm_i16_to_f32(i16[frame * channels + ch]);
+            case SampleFormat::U16Interleaved: return pcm_u16_to_f32(u16[frame * channels + ch]);
+            case SampleFormat::I16Planar: return pcm_i16_to_f32(i16[ch * frames + frame]);
+            default: return pcm_u16_to_f32(u16[ch * frames + frame]);
+        }
+    }
+    void fill_buffers(const std::vector<float*>& buffers, size_t r0, size_t r1, uint64_t start_frame) const {  // :20-25
+        size_t n = std::min(buffers.size(), channels);
+        for (size_t c = 0; c < n; ++c) for (size_t i = r0; i < r1; ++i) buffers[c][i] = at(c, start_frame + (i - r0));
+    }
+};
+
+// ---------------------------------------------------------------------------
+// basic_nodes/sampler.rs:14-577
+// ---------------------------------------------------------------------------
+constexpr size_t SAMPLER_CHANNEL_CAPACITY = 128;  // :14
+struct SamplerMsg {  // NodeToProcessorMsg :21-28
+    enum Kind : uint32_t { SetSample = 0, Play = 1, Pause = 2, Stop = 3, SetPlayheadSecs = 4, SetLoopRange = 5 } kind;
+    explicit SamplerMsg(Kind k) : kind(k) {}
+    std::shared_ptr<const SampleResource> sample; bool stop_playback = false;
+    double secs = 0.0;                                  // SetPlayheadSecs
+    uint32_t loop_mode = 0; double loop_start = 0.0, loop_end = 0.0;  // SetLoopRange: 0 None, 1 Full, 2 RangeSecs
+};
+struct SamplerShared {  // what the node and its processor share: the atomic gain and the two rings
+    float raw_gain = 0.0f;
+    std::deque<SamplerMsg> to_processor;                               // rtrb ring, capacity 128
+    std::deque<std::shared_ptr<const SampleResource>> from_processor;  // ReturnSample
+};
+// `(secs * sample_rate).round() as u64` (:250-251,:394): Rust float->int casts saturate, NaN -> 0
+inline uint64_t secs_to_frame(double secs, uint32_t sample_rate) {
+    double f = std::round(secs * (double)sample_rate);
+    if (!(f > 0.0)) return 0;
+    if (f >= 18446744073709551616.0) return UINT64_MAX;
+    return (uint64_t)f;
+}
+struct ProcLoopRange {  // :235-281
+    uint64_t start = 0, end = 0; bool full_range = false;
+    static ProcLoopRange make(uint32_t mode, double s, double e, uint32_t sample_rate, const std::shared_ptr<const SampleResource>& sample) {
+        ProcLoopRange r;
+        if (mode == 1) { r.start = 0; r.end = sample ? sample->len_frames() : 0; r.full_range = true; }
+        else { r.start = secs_to_frame(s, sample_rate); r.end = secs_to_frame(e, sample_rate); r.full_range = false; }
+        return r;
+    }
+    void update_sample(const std::shared_ptr<const SampleResource>& sample) { if (!sample || !full_range) return; start = 0; end = sample->len_frames(); }
+    bool contains(uint64_t p) const { return p >= start && p < end; }
+};
+struct SamplerProcessor : AudioNodeProcessor {
+    std::shared_ptr<SamplerShared> sh; ParamSmoother gain_smoother; bool playing = false; uint32_t sample_rate; uint64_t playhead = 0;
+    bool has_loop = false; ProcLoopRange loop_range; std::shared_ptr<const SampleResource> sample;
+    SamplerProcessor(std::shared_ptr<SamplerShared> s, uint32_t sr, size_t mbf) : sh(std::move(s)), gain_smoother(sh->raw_gain, sr, mbf), sample_rate(sr) {}
+    ~SamplerProcessor() override { if (sample) sh->from_processor.push_back(sample); }  // :562-570
+    uint64_t loop_start_or_zero() const { return has_loop ? loop_range.start : 0; }
+    void process(size_t frames, const std::vector<const float*>&, const std::vector<float*>& outputs, ProcInfo pi) override {
+        while (!sh->to_processor.empty()) {  // :331-414
+            SamplerMsg m = std::move(sh->to_processor.front()); sh->to_processor.pop_front();
+            switch (m.kind) {
+                case SamplerMsg::SetSample:
+                    if (sample) sh->from_processor.push_back(sample);
+                    sample = m.sample;
+                    if (has_loop) loop_range.update_sample(sample);
+                    if (m.stop_playback) { playhead = loop_start_or_zero(); if (playing) playing = false; }
+                    break;
+                case SamplerMsg::Play: if (!playing) playing = true; break;
+                case SamplerMsg::Pause: if (playing) playing = false; break;
+                case SamplerMsg::Stop: playhead = loop_start_or_zero(); if (playing) playing = false; break;
+                case SamplerMsg::SetPlayheadSecs: { uint64_t p = secs_to_frame(m.secs, sample_rate); if (p != playhead) playhead = p; break; }
+                case SamplerMsg::SetLoopRange:
+                    has_loop = m.loop_mode != 0;
+                    if (has_loop) { loop_range = ProcLoopRange::make(m.loop_mode, m.loop_start, m.loop_end, sample_rate, sample); if (loop_range.contains(playhead)) playhead = loop_range.start; }
+                    break;
+            }
+        }
+        if (!sample) { clear_all_outputs(frames, outputs, pi.out_silence_mask); return; }   // :416-422
+        if (!playing) { clear_all_outputs(frames, outputs, pi.out_silence_mask); return; }  // :424-430
+        float raw_gain = sh->raw_gain;
+        SmoothedOutput gain = gain_smoother.set_and_process(raw_gain, frames);  // :432-433
+        // :435 assert_eq!(gain.values.len(), frames) panics for a short block while the smoother is inactive (Q1); a
+        // panic is not a result, so short blocks are processed like full ones here.
+        if (!gain.is_smoothing() && gain.values[0] < 0.00001f) { clear_all_outputs(frames, outputs, pi.out_silence_mask); return; }  // :437-443
+        if (has_loop) {  // :445-484
+            if (playhead >= loop_range.end) playhead = loop_range.start;
+            uint64_t frames_left = loop_range.end - playhead;
+            size_t first_copy_frames = (size_t)std::min<uint64_t>(frames, frames_left);
+            sample->fill_buffers(outputs, 0, first_copy_frames, playhead);
+            if (first_copy_frames < frames) {
+                playhead = loop_range.start;
+                size_t second_copy_frames = frames - first_copy_frames;
+                sample->fill_buffers(outputs, first_copy_frames, frames, playhead);
+                playhead += second_copy_frames;
+            } else {
+                playhead += frames;
+            }
+        } else {  // :485-516
+            if (playhead >= sample->len_frames()) { playing = false; clear_all_outputs(frames, outputs, pi.out_silence_mask); return; }
+            size_t copy_frames = (size_t)std::min<uint64_t>(frames, sample->len_frames() - playhead);
+            sample->fill_buffers(outputs, 0, copy_frames, playhead);
+            if (copy_frames < frames) {
+                playing = false; playhead = 0;
+                for (float* o : outputs) for (size_t i = copy_frames; i < frames; ++i) o[i] = 0.0f;
+            } else {
+                playhead += frames;
+            }
+        }
+        size_t sample_channels = sample->num_channels();
+        if (outputs.size() >= 2 && sample_channels == 2) {  // :522-533
+            for (size_t i = 0; i < frames; ++i) { outputs[0][i] *= gain[i]; outputs[1][i] *= gain[i]; }
+        } else {  // :534-543
+            size_t n = std::min(outputs.size(), sample_channels);
+            for (size_t c = 0; c < n; ++c) for (size_t i = 0; i < frames; ++i) outputs[c][i] *= gain[i];
+        }
+        if (outputs.size() > sample_channels) {  // :545-559
+            if (outputs.size() == 2 && sample_channels == 1) {
+                std::memcpy(outputs[1], outputs[0], frames * sizeof(float));
+            } else {
+                for (size_t c = sample_channels; c < outputs.size(); ++c) { for (size_t i = 0; i < frames; ++i) outputs[c][i] = 0.0f; pi.out_silence_mask->set_channel(c, true); }
+            }
+        }
+    }
+};
+struct SamplerNode : AudioNode {  // :46-233
+    std::shared_ptr<SamplerShared> sh; bool active = false; float percent_volume; bool playing = false;
+    explicit SamplerNode(float percent) : sh(std::make_shared<SamplerShared>()) {
+        percent = std::fmax(percent, 0.0f); sh->raw_gain = percent_volume_to_raw_gain(percent); percent_volume = percent;
+    }
+    // 0 ok, -2 ring full (push Err), -3 not activated (the reference hits todo!() there)
+    int push(SamplerMsg m) {
+        if (!active) return -3;
+        if (sh->to_processor.size() >= SAMPLER_CHANNEL_CAPACITY) return -2;
+        sh->to_processor.push_back(std::move(m)); return 0;
+    }
+    int set_sample(std::shared_ptr<const SampleResource> s, bool stop_playback) { SamplerMsg m(SamplerMsg::SetSample); m.sample = std::move(s); m.stop_playback = stop_playback; return push(std::move(m)); }
+    int play() { if (playing) return 0; int rc = push(SamplerMsg(SamplerMsg::Play)); if (rc == 0) playing = true; return rc; }     // :82-98
+    int pause() { if (!playing) return 0; int rc = push(SamplerMsg(SamplerMsg::Pause)); if (rc == 0) playing = false; return rc; }  // :101-117
+    int stop() { if (!playing) return 0; int rc = push(SamplerMsg(SamplerMsg::Stop)); if (rc == 0) playing = false; return rc; }    // :120-136
+    int set_playhead(double secs) { SamplerMsg m(SamplerMsg::SetPlayheadSecs); m.secs = secs; return push(std::move(m)); }
+    int set_loop_range(uint32_t mode, double s, double e) { SamplerMsg m(SamplerMsg::SetLoopRange); m.loop_mode = mode; m.loop_start = s; m.loop_end = e; return push(std::move(m)); }
+    void set_percent_volume(float p) { sh->raw_gain = percent_volume_to_raw_gain(p); percent_volume = std::fmax(p, 0.0f); }  // :174-180
+    const char* debug_name() const override { return "beep_test"; }  // Q8 :186
+    AudioNodeInfo info() const override { AudioNodeInfo i; i.num_min_supported_outputs = 1; i.num_max_supported_outputs = 64; i.updates = true; return i; }  // :189-196
+    std::unique_ptr<AudioNodeProcessor> activate(uint32_t sr, size_t mbf, size_t, size_t, std::string*) override {  // :198-221
+        sh->to_processor.clear(); sh->from_processor.clear();
+        active = true;
+        return std::make_unique<SamplerProcessor>(sh, sr, mbf);
+    }
+    void update() override { if (active) sh->from_processor.clear(); }  // :223-232
+};
+
 // ===========================================================================
 // firewheel-graph: graph.rs, graph/compiler.rs, graph/compiler/schedule.rs,
 // graph/error.rs, processor.rs, context.rs
@@ -1215,6 +1383,7 @@ class FirewheelGraphCtx {  // context.rs:29-243
         return std::make_unique<FirewheelProcessor>(ch_, graph.current_node_capacity(), n_in, n_out, max_block_frames, user_cx);
     }
     bool is_activated() const { return active_; }
+    uint32_t sample_rate() const { return active_ ? sample_rate_ : 0; }
     UpdateStatus update() {  // :93-148
         UpdateStatus st;
         graph.update();

@@ -24,6 +24,7 @@ struct fw_ctx {
     std::unique_ptr<CompiledSchedule> dbg_schedule;
     std::string last_error;
     fw_processor* live_processor = nullptr;
+    std::vector<std::shared_ptr<const SampleResource>> resources;  // handle - 1
 };
 struct fw_processor {
     fw_ctx* ctx;
@@ -45,6 +46,7 @@ static std::unique_ptr<AudioNode> make_node(const fw_node_desc* d) {
         case FW_NODE_CONV_REVERB:
             if (!d->data || d->data_len < (uint64_t)d->u0 * d->u1) return nullptr;
             return std::make_unique<ConvReverbNode>(d->data, d->u0, d->u1);
+        case FW_NODE_SAMPLER: return std::make_unique<SamplerNode>(d->f0);
         default: return nullptr;
     }
 }
@@ -58,6 +60,7 @@ static uint32_t kind_of(const AudioNode* n) {
     if (dynamic_cast<const BiquadNode*>(n)) return FW_NODE_BIQUAD;
     if (dynamic_cast<const DelayNode*>(n)) return FW_NODE_DELAY;
     if (dynamic_cast<const ConvReverbNode*>(n)) return FW_NODE_CONV_REVERB;
+    if (dynamic_cast<const SamplerNode*>(n)) return FW_NODE_SAMPLER;
     return FW_NODE_DUMMY;
 }
 template <class F> static void each_voice(fw_ctx* c, uint32_t voice, F&& f) {
@@ -69,6 +72,16 @@ static void write_edges(const std::vector<EdgeID>& rm, fw_edge_id* out, uint32_t
     for (size_t i = 0; i < rm.size() && i < cap && out; ++i) out[i] = pack(rm[i].idx);
 }
 
+template <class F> static int each_sampler(fw_ctx* c, fw_node_id node, uint32_t voice, F&& f) {
+    if (!c || (voice != FW_ALL_VOICES && voice >= c->voices.size())) return FW_SAMPLER_NOT_A_SAMPLER;
+    int rc = FW_SAMPLER_NOT_A_SAMPLER; bool first = true;
+    each_voice(c, voice, [&](FirewheelGraphCtx& v) {
+        auto* n = dynamic_cast<SamplerNode*>(v.graph.node(nid(node)));
+        int r = n ? f(*n) : FW_SAMPLER_NOT_A_SAMPLER;
+        if (first || r != 0) { if (first || rc == 0) rc = r; first = false; }
+    });
+    return rc;
+}
 extern "C" {
 
 void fwo_graph_config_default(fw_graph_config* c) { *c = fw_graph_config{0, 2, 64, 256, 1, 0, 0, 0}; }
@@ -273,6 +286,41 @@ void fwo_biquad_design_rbj(uint32_t type, double fc, double q, double gain_db, d
             a0 = (A + 1) - (A - 1) * cw + s; a1 = 2 * ((A - 1) - (A + 1) * cw); a2 = (A + 1) - (A - 1) * cw - s; break; }
     }
     out[0] = (float)(b0 / a0); out[1] = (float)(b1 / a0); out[2] = (float)(b2 / a0); out[3] = (float)(a1 / a0); out[4] = (float)(a2 / a0);
+}
+
+// ---- sample resources + sampler messages ---------------------------------------------------------
+uint32_t fwo_sample_resource_create(fw_ctx* c, uint32_t format, uint32_t channels, uint64_t frames, const void* data) {
+    if (!c || !data || format > 5 || channels == 0 || channels > 64 || frames == 0) return 0;
+    auto r = std::make_shared<SampleResource>();
+    r->fmt = (SampleFormat)format; r->channels = channels; r->frames = frames;
+    const size_t n = (size_t)channels * frames;
+    if (format <= 1) r->f32.assign((const float*)data, (const float*)data + n);
+    else if (format == 2 || format == 4) r->i16.assign((const int16_t*)data, (const int16_t*)data + n);
+    else r->u16.assign((const uint16_t*)data, (const uint16_t*)data + n);
+    c->resources.push_back(std::move(r));
+    return (uint32_t)c->resources.size();
+}
+int fwo_sampler_set_sample(fw_ctx* c, fw_node_id node, uint32_t voice, uint32_t res, int stop_playback) {
+    if (!c || res == 0 || res > c->resources.size()) return FW_SAMPLER_BAD_ARGS;
+    return each_sampler(c, node, voice, [&](SamplerNode& n) { return n.set_sample(c->resources[res - 1], stop_playback != 0); });
+}
+int fwo_sampler_play(fw_ctx* c, fw_node_id node, uint32_t voice) { return each_sampler(c, node, voice, [](SamplerNode& n) { return n.play(); }); }
+int fwo_sampler_pause(fw_ctx* c, fw_node_id node, uint32_t voice) { return each_sampler(c, node, voice, [](SamplerNode& n) { return n.pause(); }); }
+int fwo_sampler_stop(fw_ctx* c, fw_node_id node, uint32_t voice) { return each_sampler(c, node, voice, [](SamplerNode& n) { return n.stop(); }); }
+int fwo_sampler_set_playhead(fw_ctx* c, fw_node_id node, uint32_t voice, double secs) { return each_sampler(c, node, voice, [&](SamplerNode& n) { return n.set_playhead(secs); }); }
+int fwo_sampler_set_loop_range(fw_ctx* c, fw_node_id node, uint32_t voice, uint32_t mode, double s, double e) {
+    if (mode > 2) return FW_SAMPLER_BAD_ARGS;
+    if (mode == 2 && c && !c->voices.empty()) {
+        const uint32_t sr = c->voices[0]->sample_rate();
+        if (sr && !(secs_to_frame(s, sr) < secs_to_frame(e, sr))) return FW_SAMPLER_BAD_ARGS;
+    }
+    return each_sampler(c, node, voice, [&](SamplerNode& n) { return n.set_loop_range(mode, s, e); });
+}
+int fwo_sampler_set_percent_volume(fw_ctx* c, fw_node_id node, uint32_t voice, float pct) { return each_sampler(c, node, voice, [&](SamplerNode& n) { n.set_percent_volume(pct); return 0; }); }
+int fwo_sampler_is_playing(fw_ctx* c, fw_node_id node, uint32_t voice) {
+    if (!c || voice >= c->voices.size()) return FW_SAMPLER_NOT_A_SAMPLER;
+    auto* n = dynamic_cast<SamplerNode*>(c->voices[voice]->graph.node(nid(node)));
+    return n ? (n->playing ? 1 : 0) : FW_SAMPLER_NOT_A_SAMPLER;
 }
 
 // ---- lifecycle -------------------------------------------------------------------------------
