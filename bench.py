@@ -48,7 +48,12 @@ WORKLOADS = {
     "c5": dict(voices=8192, ch=2, block=512, blocks=2, bus=True, bytes_per_sample=8.0, kernel_class=3, ir_len=48000,
                kernel="reverb_gemm_kernel (tcgen05) + biquad_delay_lanes; chain_kernel before and after",
                desc="c5: 8192 stereo voices/GPU (65536 over 8), gain->pan->4-stage biquad->48000-tap FIR reverb->master-bus sum, 512-frame blocks, 2 blocks/step"),
+    # config 5 with its real source: every voice is a looping SamplerNode reading an f32 stereo sample resource in HBM
+    "c5s": dict(voices=8192, ch=2, block=512, blocks=2, bus=True, bytes_per_sample=8.0, kernel_class=3, ir_len=48000, src="sampler",
+                kernel="reverb_gemm_kernel (tcgen05) + biquad_delay_lanes; sampler_kernel source, chain_kernel before and after",
+                desc="c5s: 8192 looping stereo sampler voices/GPU (256 two-second f32 resources, 188 MiB in HBM) -> gain->pan->4-stage biquad->48000-tap FIR reverb->master-bus sum, 512-frame blocks, 2 blocks/step"),
 }
+REVERB_WORKLOADS = ("c4", "c5", "c5s")
 
 
 def synth(shape, seed):
@@ -75,20 +80,21 @@ def biquad_params(fw, lib, V, seed):
 def build_graph(fw, lib, workload, V, block, device, seed):
     """The voice graph of a workload, on `lib` (the CUDA product, or the CPU oracle for the baseline legs)."""
     w = WORKLOADS[workload]
-    cx = fw.FirewheelGraphCtx(lib, fw.AudioGraphConfig(num_graph_inputs=2, num_graph_outputs=2, num_voices=V, master_bus=w["bus"], device=device))
+    sampler_src = w.get("src") == "sampler"
+    cx = fw.FirewheelGraphCtx(lib, fw.AudioGraphConfig(num_graph_inputs=0 if sampler_src else 2, num_graph_outputs=2, num_voices=V, master_bus=w["bus"], device=device))
     g = cx.graph
     if workload == "c2":
         pct, pan = voice_params(V, seed)
         nodes = [g.add_node(2, 2, fw.VolumeNode(100.0)), g.add_node(2, 2, fw.PanNode(0.0))]
         g.set_percent_volume(nodes[0], pct)
         g.set_pan(nodes[1], pan)
-    elif workload in ("c4", "c5"):
+    elif workload in REVERB_WORKLOADS:
         L = w["ir_len"]
         rng = np.random.default_rng(0x1200)
         ir = rng.standard_normal((2, L)) * np.exp(-6.9 * np.arange(L) / L)  # SURVEY §8d
         ir = (ir / np.sqrt((ir ** 2).sum(axis=1, keepdims=True))).astype(F32)
         nodes = [g.add_node(2, 2, fw.ConvReverbNode(ir))]
-        if workload == "c5":
+        if workload in ("c5", "c5s"):
             pct, pan = voice_params(V, seed)
             pre = [g.add_node(2, 2, fw.VolumeNode(100.0)), g.add_node(2, 2, fw.PanNode(0.0)), g.add_node(2, 2, fw.BiquadNode(4))]
             g.set_percent_volume(pre[0], pct); g.set_pan(pre[1], pan); g.set_biquad_coeffs(pre[2], biquad_params(fw, lib, V, seed))
@@ -96,17 +102,31 @@ def build_graph(fw, lib, workload, V, block, device, seed):
     else:
         nodes = [g.add_node(2, 2, fw.BiquadNode(4)), g.add_node(2, 2, fw.DelayNode(12000))]
         g.set_biquad_coeffs(nodes[0], biquad_params(fw, lib, V, seed))
-    prev = g.graph_in_node()
+    smp = None
+    if sampler_src:
+        smp = g.add_node(0, 2, fw.SamplerNode(100.0))
+        prev = smp
+    else:
+        prev = g.graph_in_node()
     for n in nodes + [g.graph_out_node()]:
         for c in range(2):
             g.connect(prev, c, n, c, False)
         prev = n
-    proc = cx.activate(SR, 2, 2, block)
+    proc = cx.activate(SR, 0 if sampler_src else 2, 2, block)
     if proc is None:
         raise RuntimeError("activate failed")
     st = cx.update()
     if st.graph_error is not None:
         raise RuntimeError(f"compile failed: {st.graph_error} {cx.last_error()}")
+    if sampler_src:
+        # 256 two-second stereo f32 resources (188 MiB: larger than L2); voice v loops resource v % n_res from its own offset
+        n_res = min(256, V)
+        handles = [g.create_sample_resource(synth((2, 2 * SR), 0x5A000000 + seed * 4096 + r)) for r in range(n_res)]
+        for v in range(V):
+            g.sampler_set_sample(smp, handles[v % n_res], True, voice=v)
+            g.sampler_set_loop_range(smp, "full", voice=v)
+            g.sampler_set_playhead(smp, ((v // n_res) * 2731 % (2 * SR)) / SR, voice=v)
+        g.sampler_play(smp)
     return cx, proc
 
 
@@ -185,13 +205,13 @@ def oracle_rate(V, block, n_blocks, threads, seed=7, steps=1, warmup=0, workload
         if hi <= lo:
             continue
         cx, proc = build_graph(fw, lib, workload, hi - lo, block, 0, seed * 100 + i)
-        x = synth((hi - lo, 2, T), seed * 1000 + i)
+        x = synth((hi - lo, 0 if WORKLOADS[workload].get("src") == "sampler" else 2, T), seed * 1000 + i)
         out = np.zeros((2, T) if bus else (hi - lo, 2, T), F32)
         parts.append((cx, proc, x, out))
 
     def run(p):
         cx, proc, x, out = p
-        rc, _ = proc.process_planar(x, out, 2, 2, T)
+        rc, _ = proc.process_planar(x, out, x.shape[1], 2, T)
         assert rc == 0
 
     def one_step():
@@ -224,7 +244,7 @@ def run_reference(args, rank, world):
     n_blocks = 32  # bounded sample of the step (the full step is w["blocks"] blocks)
     if args.workload == "c3":
         n_blocks = 4
-    if args.workload in ("c4", "c5"):
+    if args.workload in REVERB_WORKLOADS:
         V, n_blocks = max(cores, 2) * 1, 1  # direct-form FIR on the CPU: 96 kflop per output sample
     val, sec_per_step = oracle_rate(V, w["block"], n_blocks, cores, steps=args.steps, warmup=args.warmup, workload=args.workload)
     sample = f"{V} voices x {n_blocks} of {w['blocks']} blocks per step, {cores} replica threads over disjoint voice ranges"
@@ -273,24 +293,27 @@ def run_b200(args, rank, world, local_rank):
         dist.broadcast_object_list(ids, src=0)
         if proc.comm_init(rank, world, ids[0]) != 0:
             raise RuntimeError("ncclCommInitRank failed: " + lib.last_device_error().decode())
-    in_bytes = V * C * T * 4
-    out_bytes = C * T * 4 if w["bus"] else in_bytes
+    Cin = 0 if w.get("src") == "sampler" else C  # sampler voices read their sample resources from HBM, not a stream input
+    in_bytes = V * Cin * T * 4
+    out_bytes = C * T * 4 if w["bus"] else V * C * T * 4
 
     # synthetic input straight into pinned host memory, then resident in HBM
-    h_in = lib.host_alloc_pinned(in_bytes)
+    h_in = lib.host_alloc_pinned(in_bytes) if in_bytes else 0
     h_out = lib.host_alloc_pinned(out_bytes)
-    if not h_in or not h_out:
+    if (in_bytes and not h_in) or not h_out:
         raise RuntimeError("pinned allocation failed")
     import ctypes
-    x = np.ctypeslib.as_array(ctypes.cast(h_in, ctypes.POINTER(ctypes.c_float)), shape=(V, C, T))
-    chunk = 64
-    for v0 in range(0, V, chunk):
-        x[v0:v0 + chunk] = synth((min(chunk, V - v0), C, T), 0xF17E0000 + rank * 65536 + v0)
+    if in_bytes:
+        x = np.ctypeslib.as_array(ctypes.cast(h_in, ctypes.POINTER(ctypes.c_float)), shape=(V, C, T))
+        chunk = 64
+        for v0 in range(0, V, chunk):
+            x[v0:v0 + chunk] = synth((min(chunk, V - v0), C, T), 0xF17E0000 + rank * 65536 + v0)
     y = np.ctypeslib.as_array(ctypes.cast(h_out, ctypes.POINTER(ctypes.c_float)), shape=(C, T) if w["bus"] else (V, C, T))
-    d_in, d_out = lib.dev_malloc(local_rank, in_bytes), lib.dev_malloc(local_rank, out_bytes)
-    if not d_in or not d_out:
+    d_in, d_out = (lib.dev_malloc(local_rank, in_bytes) if in_bytes else 0), lib.dev_malloc(local_rank, out_bytes)
+    if (in_bytes and not d_in) or not d_out:
         raise RuntimeError("device allocation failed: " + lib.last_device_error().decode())
-    proc.h2d(d_in, h_in, in_bytes)
+    if in_bytes:
+        proc.h2d(d_in, h_in, in_bytes)
     proc.sync()
 
     def barrier():
@@ -308,14 +331,14 @@ def run_b200(args, rank, world, local_rank):
 
     # ---- device-timed pass (inputs resident in HBM) ----
     for _ in range(max(args.warmup, 3)):
-        assert proc.process_planar_device(d_in, d_out, C, C, T) == 0
+        assert proc.process_planar_device(d_in, d_out, Cin, C, T) == 0
     barrier()
     clocks = ClockSampler(local_rank)
     clocks.start()
     launches0 = proc.kernel_launches()
     proc.event_record(0)
     for _ in range(args.steps):
-        assert proc.process_planar_device(d_in, d_out, C, C, T) == 0
+        assert proc.process_planar_device(d_in, d_out, Cin, C, T) == 0
     proc.event_record(1)
     barrier()
     ms_total = max_over_ranks(proc.event_elapsed_ms(0, 1))
@@ -324,7 +347,7 @@ def run_b200(args, rank, world, local_rank):
     # programmatic-dependent-launch overlap, so they stay out of the headline pass)
     proc.profile(True)
     for _ in range(args.steps):
-        assert proc.process_planar_device(d_in, d_out, C, C, T) == 0
+        assert proc.process_planar_device(d_in, d_out, Cin, C, T) == 0
     prof_ms, prof_n = proc.profile_read()
     proc.profile(False)
     clk = clocks.stop()
@@ -340,12 +363,12 @@ def run_b200(args, rank, world, local_rank):
     # ---- end-to-end pass: host buffers through the C-ABI call, H2D + D2H inside the timed region ----
     e2e_steps = min(args.steps, 10)
     for _ in range(2):
-        rc, _ = proc.process_planar(h_in, h_out, C, C, T)
+        rc, _ = proc.process_planar(h_in, h_out, Cin, C, T)
         assert rc == 0
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        rc, _ = proc.process_planar(h_in, h_out, C, C, T)
+        rc, _ = proc.process_planar(h_in, h_out, Cin, C, T)
         assert rc == 0
     proc.sync()
     e2e_s = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
@@ -365,14 +388,14 @@ def run_b200(args, rank, world, local_rank):
             traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    if args.workload in ("c4", "c5"):  # tensor-pipe roofline: dense direct-form count 2*L flop per output sample
+    if args.workload in REVERB_WORKLOADS:  # tensor-pipe roofline: dense direct-form count 2*L flop per output sample
         pk = ROOT / "MEASURED_PEAKS.json"
         peak, peak_src = (float(json.loads(pk.read_text())["bf16_tflops"]), "measured (MEASURED_PEAKS.json bf16_tflops, burst)") if pk.exists() else (1590.0, "fallback (B200_PROFILING.md 1.59 PFLOP/s)")
         flops = 2.0 * w["ir_len"] * V * C * T
         achieved = flops / (chain_ms * 1e-3) / 1e12 if chain_ms > 0 else 0.0
-    roofline = {"bound": "hbm" if args.workload not in ("c4", "c5") else "tensor", "kernel": w["kernel"], "achieved": achieved, "peak": peak, "unit": "GB/s" if args.workload not in ("c4", "c5") else "TFLOP/s",
+    roofline = {"bound": "hbm" if args.workload not in REVERB_WORKLOADS else "tensor", "kernel": w["kernel"], "achieved": achieved, "peak": peak, "unit": "GB/s" if args.workload not in REVERB_WORKLOADS else "TFLOP/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "kernel_ms": chain_ms,
-                "algorithmic_bytes_per_launch": algo_bytes, "algorithmic_flops_per_launch": (2.0 * w["ir_len"] * V * C * T) if args.workload in ("c4", "c5") else None,
+                "algorithmic_bytes_per_launch": algo_bytes, "algorithmic_flops_per_launch": (2.0 * w["ir_len"] * V * C * T) if args.workload in REVERB_WORKLOADS else None,
                 "step_share": {"control_ms": prof_ms[0] / max(prof_n[0], 1), "chain_ms": prof_ms[1] / max(prof_n[1], 1),
                                "combine_ms": prof_ms[2] / max(prof_n[2], 1), "temporal_ms": prof_ms[3] / max(prof_n[3], 1)}}
 
@@ -380,14 +403,14 @@ def run_b200(args, rank, world, local_rank):
     if rank == 0:
         n_blocks = 64
         n_blocks = 64 if args.workload == "c2" else 2
-        Vc = V if args.workload not in ("c4", "c5") else 2  # the direct-form FIR oracle needs ~0.2 s per voice-block
-        if args.workload in ("c4", "c5"):
+        Vc = V if args.workload not in REVERB_WORKLOADS else 2  # the direct-form FIR oracle needs ~0.2 s per voice-block
+        if args.workload in REVERB_WORKLOADS:
             n_blocks = 1
         rate, sec = oracle_rate(Vc, F, n_blocks, 1, steps=1, warmup=0, workload=args.workload)
-        if sec < 2.0 and args.workload not in ("c4", "c5"):  # size the sample towards ~10 s of CPU work
+        if sec < 2.0 and args.workload not in REVERB_WORKLOADS:  # size the sample towards ~10 s of CPU work
             n_blocks = int(min(KB * 8, max(n_blocks, n_blocks * 10.0 / max(sec, 1e-3))))
             rate, sec = oracle_rate(Vc, F, n_blocks, 1, steps=1, warmup=0, workload=args.workload)
-        elif args.workload in ("c4", "c5") and sec < 5.0:
+        elif args.workload in REVERB_WORKLOADS and sec < 5.0:
             Vc = int(min(64, max(2, Vc * 10.0 / max(sec, 1e-3))))
             rate, sec = oracle_rate(Vc, F, n_blocks, 1, steps=1, warmup=0, workload=args.workload)
         cpu = {"value": rate, "unit": "samples/s", "cores": 1, "kind": "port",
@@ -398,8 +421,8 @@ def run_b200(args, rank, world, local_rank):
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
                 "config": {"workload": w["desc"], "voices_per_gpu": V, "channels": C, "block_frames": F, "blocks_per_step": KB,
-                           "l2": f"inputs larger than L2 ({in_bytes >> 20} MiB per GPU per step)", "layout": "planar [voice][ch][frame]",
-                           "parallelism": f"voices sharded over {world} rank(s)" + ("; master bus = NCCL all-gather + rank-ordered tree" if (world > 1 and w["bus"]) else "")},
+                           "l2": (f"inputs larger than L2 ({in_bytes >> 20} MiB per GPU per step)" if in_bytes else "sample pool larger than L2 (188 MiB per GPU), every voice at its own offset"), "layout": "planar [voice][ch][frame]",
+                           "parallelism": f"voices sharded over {world} rank(s)" + ("; master bus = peer-memory (NVLink) exchange + rank-ordered tree, FW_EXCHANGE=nccl selects ncclAllGather" if (world > 1 and w["bus"]) else "")},
                 "clocks": clk,
                 "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": in_bytes * world, "d2h_bytes_per_step": out_bytes * world,
                         "steps": e2e_steps, "ms_per_step": e2e_s * 1e3, "api": "fw_processor_process_planar (pinned host buffers)"},

@@ -210,7 +210,7 @@ struct Plan {
     CtlTables tables{}; uint64_t* d_flags = nullptr;
     // data plane: stages run in order; pointwise stages are fused chain programs, temporal stages own state
     struct Stage { int kind = 0; /* 0 pointwise, 1 temporal */ ChainProgram prog{}; uint32_t c_in = 0, c_out = 0;
-                   std::shared_ptr<NodeDeviceState> biquad, delay, reverb; };  // kind 2: reverb
+                   std::shared_ptr<NodeDeviceState> biquad, delay, reverb, sampler; int sampler_sm = -1; };  // kind 2: reverb, kind 3: sampler head
     std::vector<Stage> stages;
     // generic lowering (arbitrary DAG of built-in nodes): one launch group per scheduled node over pool buffers [buffer][V][T]
     struct GNode { uint32_t kind = 0; std::vector<uint32_t> in_buf, out_buf; std::vector<uint8_t> in_clear; int sm0 = -1, sm1 = -1, mask_slot = -1;
@@ -367,9 +367,16 @@ static bool lower(fw_ctx* c, const Schedule& s, Plan* plan, std::string* why) {
     // ---- data plane, first choice: a linear chain graph_in -> n1 -> ... -> nk -> graph_out, port i to port i, fused into stages ----
     auto chain_lower = [&]() -> bool {
     uint32_t width = (uint32_t)gin.out.size();
-    if (width < 1 || width > 2) { *why = "the fused chain supports 1 or 2 channels"; return false; }
-    plan->c_in = width;
     Id prev = gin.id;
+    size_t first = 1;
+    if (width == 0 && n >= 3 && tb.nodes[1].kind == FW_NODE_SAMPLER && s.nodes[1].in.empty() && s.nodes[1].out.size() >= 1 && s.nodes[1].out.size() <= 2) {
+        // no stream inputs: a SamplerNode heads the chain (BASELINE config 5: sampler -> gain -> pan -> ... -> bus)
+        Plan::Stage hs; hs.kind = 3; hs.c_in = 0; hs.c_out = (uint32_t)s.nodes[1].out.size(); hs.sampler = c->node_states[s.nodes[1].id.pack()]; hs.sampler_sm = sm_of_node[1];
+        plan->stages.push_back(hs);
+        width = hs.c_out; prev = s.nodes[1].id; first = 2;
+    }
+    if (width < 1 || width > 2) { *why = "the fused chain supports 1 or 2 channels"; return false; }
+    plan->c_in = (uint32_t)gin.out.size();
     auto fed_by_prev = [&](const SchedNode& sn, uint32_t w) {
         if (sn.in.size() != w) return false;
         for (uint32_t p = 0; p < w; ++p) if (sn.in[p].should_clear || sn.in[p].producer != prev || sn.in[p].producer_port != p) return false;
@@ -381,7 +388,7 @@ static bool lower(fw_ctx* c, const Schedule& s, Plan* plan, std::string* why) {
         if (cur_open && (cur.prog.n_ops > 0 || force)) { cur.prog.c_out = width; cur.c_out = width; plan->stages.push_back(cur); }
         cur = Plan::Stage{}; cur.kind = 0; cur.prog.c_in = width; cur.c_in = width; cur_open = true;
     };
-    for (size_t i = 1; i + 1 < n; ++i) {
+    for (size_t i = first; i + 1 < n; ++i) {
         const SchedNode& sn = s.nodes[i];
         NodeRec* nr = g.node(sn.id);
         if (!fed_by_prev(sn, width)) { *why = "voice graph is not a linear port-to-port chain (generic per-node lowering not built yet)"; return false; }
@@ -1312,6 +1319,17 @@ static int proc_enqueue(fw_processor* p, const float* d_in, float* d_out, uint32
         const Plan::Stage& sg = pl.stages[si];
         const bool last = si + 1 == n_stages;
         float* dst = last ? d_out : p->d_tmp[si & 1];
+        if (sg.kind == 3) {  // SamplerNode heading the chain: writes [V][c_out][T]
+            NodeDeviceState& st = *sg.sampler;
+            SamplerArgs sa{};
+            for (uint32_t c = 0; c < sg.c_out; ++c) sa.out[c] = dst + (size_t)c * T;
+            sa.out_vstride = (uint64_t)sg.c_out * T; sa.n_out = sg.c_out; sa.num_voices = V; sa.frames = T; sa.block_frames = pl.block_frames;
+            sa.srec = st.d_srec; sa.res = st.d_res; sa.loop_start = st.d_loop_start; sa.res_tab = st.cur_tab; sa.sm = sg.sampler_sm; sa.rec = pl.rec;
+            { ProfScope ps(p, 1); if (!FW_CUDA(launch_sampler(sa, p->stream))) return FW_PROC_DEVICE_ERROR; }
+            p->launches++;
+            src = dst;
+            continue;
+        }
         if (sg.kind == 2) {
             NodeDeviceState& rs = *sg.reverb;
             if (T > NodeDeviceState::kReverbMaxFrames) { g_dev_err = "conv reverb: more than 65536 frames in one call"; return FW_PROC_BAD_ARGS; }

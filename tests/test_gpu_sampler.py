@@ -28,7 +28,7 @@ def make_resources(g, seed=0):
     }
 
 
-def run_scenario(lib, V, n_out, F, steps, bus=False, post=None, n_graph_out=None):
+def run_scenario(lib, V, n_out, F, steps, bus=False, post=None, n_graph_out=None, stray=False):
     n_graph_out = n_graph_out or n_out
     cx = FirewheelGraphCtx(lib, AudioGraphConfig(num_graph_inputs=0, num_graph_outputs=n_graph_out, num_voices=V, master_bus=bus))
     g = cx.graph
@@ -38,6 +38,8 @@ def run_scenario(lib, V, n_out, F, steps, bus=False, post=None, n_graph_out=None
         last = post(g, smp, ids)
     for c in range(n_graph_out):
         g.connect(last, c, g.graph_out_node(), c, False)
+    if stray:  # an unconnected node makes the graph a non-chain: the generic per-node lowering runs instead of the fused one
+        g.add_node(1, 1, VolumeNode(100.0))
     proc = cx.activate(SR, 0, n_graph_out, F)
     st = cx.update()
     assert st.kind == "Active" and st.graph_error is None, (st, cx.last_error())
@@ -108,6 +110,7 @@ def test_transport_messages_and_loops(gpu, oracle):
 
     steps = [(a0, 5 * F), (a1, 7 * F), (a2, 6 * F + 17), (a3, 9 * F), (None, 20 * F), (None, 3)]
     both(gpu, oracle, V, 2, F, steps)
+    both(gpu, oracle, V, 2, F, steps, stray=True)
 
 
 def test_muted_sampler_keeps_its_playhead(gpu, oracle):
@@ -122,8 +125,8 @@ def test_muted_sampler_keeps_its_playhead(gpu, oracle):
     both(gpu, oracle, V, 2, F, [(a0, 3 * F), (a1, 4 * F), (None, 6 * F)])
 
 
-@pytest.mark.parametrize("bus", [False, True])
-def test_sampler_feeding_a_voice_graph(gpu, oracle, bus):
+@pytest.mark.parametrize("bus,stray", [(False, False), (True, False), (False, True), (True, True)])
+def test_sampler_feeding_a_voice_graph(gpu, oracle, bus, stray):
     """Config-5 shape in miniature: sampler -> gain -> pan (-> master bus); the sample ends mid-call, so the gain node sees
     its input go silent (smoother reset, cleared outputs) in the middle of a call."""
     V, F = 70, 64
@@ -154,7 +157,7 @@ def test_sampler_feeding_a_voice_graph(gpu, oracle, bus):
     def a2(g, ids, res):
         g.sampler_play(ids["smp"])
 
-    both(gpu, oracle, V, 2, F, [(a0, 12 * F), (a1, 30 * F), (a2, 8 * F), (None, 40 * F)], bus=bus, post=post)
+    both(gpu, oracle, V, 2, F, [(a0, 12 * F), (a1, 30 * F), (a2, 8 * F), (None, 40 * F)], bus=bus, post=post, stray=stray)
 
 
 def test_two_samplers_summed(gpu, oracle):
@@ -171,3 +174,14 @@ def test_two_samplers_summed(gpu, oracle):
     def a1(g, ids, res):
         g.sampler_play(ids["smp2"])
     both(gpu, oracle, V, 2, F, [(a0, 10 * F), (a1, 80 * F), (None, 10 * F)], post=post)
+
+
+# the oracle's known-answer tests (hand-derived from the reference source) hold for the device path as well
+import test_sampler_oracle as kat  # noqa: E402
+
+
+@pytest.mark.parametrize("fn", [kat.test_pcm_conversions, kat.test_one_shot_end_and_zero_tail, kat.test_loop_wrap_inside_and_across_blocks,
+                                kat.test_channel_mapping_and_masks, kat.test_message_semantics, kat.test_ring_capacity_and_activation],
+                         ids=lambda f: f.__name__)
+def test_known_answers_on_device(gpu, fn):
+    fn(gpu)
