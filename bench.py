@@ -400,7 +400,7 @@ def run_b200(args, rank, world, local_rank):
                                "combine_ms": prof_ms[2] / max(prof_n[2], 1), "temporal_ms": prof_ms[3] / max(prof_n[3], 1)}}
 
     cpu = None
-    if rank == 0:
+    if rank == 0 and not os.environ.get("FW_BENCH_SKIP_CPU"):  # (experiments on multi-GPU boxes skip the 10 s CPU leg)
         n_blocks = 64
         n_blocks = 64 if args.workload == "c2" else 2
         Vc = V if args.workload not in REVERB_WORKLOADS else 2  # the direct-form FIR oracle needs ~0.2 s per voice-block
@@ -422,7 +422,7 @@ def run_b200(args, rank, world, local_rank):
                 "dtype": "f32", "data": "synthetic",
                 "config": {"workload": w["desc"], "voices_per_gpu": V, "channels": C, "block_frames": F, "blocks_per_step": KB,
                            "l2": (f"inputs larger than L2 ({in_bytes >> 20} MiB per GPU per step)" if in_bytes else "sample pool larger than L2 (188 MiB per GPU), every voice at its own offset"), "layout": "planar [voice][ch][frame]",
-                           "parallelism": f"voices sharded over {world} rank(s)" + ("; master bus = peer-memory (NVLink) exchange + rank-ordered tree, FW_EXCHANGE=nccl selects ncclAllGather" if (world > 1 and w["bus"]) else "")},
+                           "parallelism": f"voices sharded over {world} rank(s)" + (("; master bus = peer-memory (NVLink) push + rank-ordered tree" if os.environ.get("FW_EXCHANGE") == "p2p" else "; master bus = NCCL all-gather on a high-priority side stream + rank-ordered tree") if (world > 1 and w["bus"]) else "")},
                 "clocks": clk,
                 "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": in_bytes * world, "d2h_bytes_per_step": out_bytes * world,
                         "steps": e2e_steps, "ms_per_step": e2e_s * 1e3, "api": "fw_processor_process_planar (pinned host buffers)"},

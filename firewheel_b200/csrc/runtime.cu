@@ -1193,8 +1193,10 @@ static int enqueue_generic(fw_processor* p, Plan& pl, const float* d_in, float* 
 // Peer-memory mailboxes for the bus exchange: allocate, exchange CUDA IPC handles through the communicator, map all peers.
 // Any rank failing turns the feature off on ALL ranks (they then use the NCCL all-gather): decided by a second all-gather.
 static bool p2p_setup(fw_processor* p) {
+    // Default: the NCCL all-gather on the high-priority side stream — measured faster at 8 GPUs (0.113 ms/step vs 0.119 /
+    // 0.126 for the two peer-memory hand-overs, profiles/r01_bench_c2_n8_*.json). FW_EXCHANGE=p2p selects the peer-memory path.
     const char* mode = getenv("FW_EXCHANGE");
-    const bool want = !(mode && std::strcmp(mode, "nccl") == 0);
+    const bool want = mode && std::strcmp(mode, "p2p") == 0;
     const int W = p->world, me = p->rank;
     size_t cap = 262144;  // floats per slot: 2 channels x 131072 frames
     if (const char* e = getenv("FW_P2P_SLOT_FLOATS")) { const long long v = atoll(e); if (v >= 1024) cap = (size_t)v & ~(size_t)3; }
