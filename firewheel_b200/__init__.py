@@ -12,7 +12,8 @@ from . import _capi
 from ._capi import FW_ALL_VOICES, FW_ID_DANGLING  # noqa: F401
 from .graph import (AddEdgeError, AudioGraphConfig, BiquadNode, CompileGraphError, ConvReverbNode, DelayNode,  # noqa: F401
                     DummyAudioNode, EdgeID, FirewheelGraphCtx, FirewheelProcessor, HardClipNode, MonoToStereoNode,
-                    NodeID, PanNode, SamplerError, SamplerNode, StereoToMonoNode, SumNode, UpdateStatus, VolumeNode, design_rbj)
+                    NodeID, PanNode, ResamplerNode, SamplerError, SamplerNode, StereoToMonoNode, SumNode, SvfNode, UpdateStatus, VolumeNode,
+                    design_rbj, design_resampler, design_svf)
 
 REPO_ROOT = Path(__file__).resolve().parent.parent
 LIB_PATH = Path(__file__).resolve().parent / "lib" / "libfirewheel_b200.so"

@@ -12,7 +12,7 @@ FW_MAX_PORTS = 64
 
 # fw_node_kind
 NODE_DUMMY, NODE_VOLUME, NODE_SUM, NODE_MONO_TO_STEREO, NODE_STEREO_TO_MONO, NODE_HARD_CLIP = range(6)
-NODE_PAN, NODE_BIQUAD, NODE_DELAY, NODE_CONV_REVERB, NODE_SAMPLER = 6, 7, 8, 9, 10
+NODE_PAN, NODE_BIQUAD, NODE_DELAY, NODE_CONV_REVERB, NODE_SAMPLER, NODE_SVF, NODE_RESAMPLER = 6, 7, 8, 9, 10, 11, 12
 
 # fw_sample_format / fw_loop_mode / fw_sampler_status
 SAMPLE_F32_PLANAR, SAMPLE_F32_INTERLEAVED, SAMPLE_I16_INTERLEAVED, SAMPLE_U16_INTERLEAVED, SAMPLE_I16_PLANAR, SAMPLE_U16_PLANAR = range(6)
@@ -106,6 +106,12 @@ SIGNATURES = {
     "biquad_set_coeffs": (_i32, [_vp, _u64, _u32, _u32, _pf]),
     "biquad_set_all_coeffs": (_i32, [_vp, _u64, _pf, _u32, _u32]),
     "biquad_design_rbj": (None, [_u32, _f64, _f64, _f64, _f64, _pf]),
+    "svf_set_coeffs": (_i32, [_vp, _u64, _u32, _u32, _pf]),
+    "svf_set_all_coeffs": (_i32, [_vp, _u64, _pf, _u32, _u32]),
+    "svf_design": (None, [_u32, _f64, _f64, _f64, _pf]),
+    "resampler_set": (_i32, [_vp, _u64, _u32, _u32, _u64, _i32, _i32]),
+    "resampler_seek": (_i32, [_vp, _u64, _u32, _u64]),
+    "resampler_design": (None, [_u32, _u32, _f64, _f64, _pf]),
     "sample_resource_create": (_u32, [_vp, _u32, _u32, _u64, _vp]),
     "sampler_set_sample": (_i32, [_vp, _u64, _u32, _u32, _i32]),
     "sampler_play": (_i32, [_vp, _u64, _u32]),

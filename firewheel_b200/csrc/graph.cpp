@@ -18,6 +18,8 @@ const char* node_debug_name(uint32_t kind) {
         case FW_NODE_BIQUAD: return "biquad";
         case FW_NODE_DELAY: return "delay";
         case FW_NODE_CONV_REVERB: return "conv_reverb";
+        case FW_NODE_SVF: return "svf";
+        case FW_NODE_RESAMPLER: return "resampler";
         case FW_NODE_SAMPLER: return "beep_test";              // Q8: sampler.rs:186 really says that
         default: return "unknown";
     }
@@ -29,7 +31,7 @@ void node_supported_ports(uint32_t kind, uint32_t* mi, uint32_t* xi, uint32_t* m
         case FW_NODE_MONO_TO_STEREO: *mi = 1; *xi = 1; *mo = 2; *xo = 2; break;   // mono_to_stereo.rs:10-18
         case FW_NODE_STEREO_TO_MONO: *mi = 2; *xi = 2; *mo = 1; *xo = 1; break;   // stereo_to_mono.rs:10-18
         case FW_NODE_PAN: *mi = 2; *xi = 2; *mo = 2; *xo = 2; break;
-        case FW_NODE_SAMPLER: *mi = 0; *xi = 0; *mo = 1; *xo = 64; break;         // sampler.rs:189-196
+        case FW_NODE_SAMPLER: case FW_NODE_RESAMPLER: *mi = 0; *xi = 0; *mo = 1; *xo = 64; break;         // sampler.rs:189-196
         default: *mi = 1; *xi = 64; *mo = 1; *xo = 64; break;                      // volume.rs:46-54 et al.
     }
 }
@@ -54,6 +56,13 @@ std::string node_check_activation(const NodeParams& p, uint32_t ni, uint32_t no)
             break;
         case FW_NODE_DELAY:
             if (ni != no) return "The number of inputs on a DelayNode must equal the number of outputs. " + got();
+            break;
+        case FW_NODE_SVF:
+            if (ni != no) return "The number of inputs on an SvfNode must equal the number of outputs. " + got();
+            break;
+        case FW_NODE_RESAMPLER:
+            if (no == 0 || p.rs_phases == 0 || p.rs_phases > 1024 || (p.rs_phases & (p.rs_phases - 1)) || p.rs_taps < 2 || p.rs_taps > 64 || (p.rs_taps & 1))
+                return "A ResamplerNode needs >= 1 output, a power-of-two phase count <= 1024 and an even tap count <= 64.";
             break;
         case FW_NODE_CONV_REVERB:
             if (ni != no || p.ir_len == 0 || p.ir_channels == 0)

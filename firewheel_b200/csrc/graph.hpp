@@ -94,6 +94,11 @@ struct NodeParams {
     // conv reverb
     uint32_t ir_len = 0, ir_channels = 0;
     std::vector<float> ir;  // [ch][len] f32 (rounded to bf16 on the device side)
+    // svf (spec ours): [voice][stage][6] = {a1, a2, a3, m0, m1, m2}; num_stages above
+    std::vector<float> svf_coeffs;
+    // polyphase resampler (spec ours): table [phases][taps] + per-voice transport (guarded by smp_mu)
+    uint32_t rs_phases = 0, rs_taps = 0; std::vector<float> rs_table;
+    std::vector<uint32_t> rs_res, rs_flags; std::vector<uint64_t> rs_step, rs_seek; std::vector<uint8_t> rs_seek_flag; bool rs_seek_any = false;
     // sampler (sampler.rs:46-181): node-side state per voice + the node -> processor message ring. `percent` / `raw_gain`
     // above double as the sampler's volume (sampler.rs:49-50). The stream side drains `smp_msgs` at call start.
     struct SamplerMsg { uint32_t voice, kind, a; uint64_t x, y; };

@@ -247,6 +247,13 @@ __global__ void __launch_bounds__(128) control_kernel(const __grid_constant__ Co
                     sc.rec[(size_t)k * V + v] = r;
                     break;
                 }
+                case FW_NODE_RESAMPLER: {  // spec ours: cleared + flagged when not playing / no resource; surplus channels as the sampler's
+                    const RsCtl& rc = tb.rs[nd.sm1];
+                    const uint32_t r = rc.res[v];
+                    if (!(rc.flags[v] & 1u) || r == 0 || r > rc.n_res) out_mask = all_silent_mask(nd.n_out);
+                    else { const uint32_t sch = rc.res_tab[r - 1].channels; if (nd.n_out > sch && !(nd.n_out == 2 && sch == 1)) out_mask = all_silent_mask(nd.n_out) & ~all_silent_mask(sch); }
+                    break;
+                }
                 case FW_NODE_SUM:  // sum.rs:52-65; the unrolled / generic sums never write the mask (Q7)
                     if (all_channels_silent(in_mask, nd.n_in)) out_mask = all_silent_mask(nd.n_out);
                     else if (nd.n_in == nd.n_out) out_mask = in_mask;
@@ -691,6 +698,43 @@ __global__ void __launch_bounds__(128) sampler_kernel(const __grid_constant__ Sa
     VecT<VEC>::store(dst, y);
 }
 
+// K-resampler: polyphase windowed-sinc sample player (spec in include/fw_b200.h). One thread = one output
+// frame of one (voice, channel): the read position is analytic (pos + n * step, Q32.32), so frames are independent.
+// Accumulation order (taps ascending, separate multiply and add) matches the oracle bit for bit.
+__global__ void resampler_begin_kernel(uint64_t* pos, const uint64_t* seek, uint32_t* seek_flag, uint32_t V) {
+    const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v < V && seek_flag[v]) { pos[v] = seek[v] << 32; seek_flag[v] = 0; }
+}
+__global__ void resampler_end_kernel(uint64_t* pos, const uint64_t* step, const uint32_t* flags, const uint32_t* res, uint32_t V, uint32_t frames) {
+    const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v < V && (flags[v] & 1u) && res[v] != 0) pos[v] += (uint64_t)frames * step[v];
+}
+__global__ void __launch_bounds__(128) resampler_kernel(const __grid_constant__ ResamplerArgs a) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y, c = blockIdx.z;
+    if (n >= a.frames) return;
+    float* dst = a.out[c] + (size_t)v * a.out_vstride + n;
+    const uint32_t r = a.res[v], fl = a.flags[v];
+    if (!(fl & 1u) || r == 0) { *dst = 0.0f; return; }
+    const ResDesc d = a.res_tab[r - 1];
+    uint32_t src_ch = c;
+    if (c >= min(a.n_out, d.channels)) {
+        if (a.n_out == 2 && d.channels == 1) src_ch = 0;
+        else { *dst = 0.0f; return; }
+    }
+    const uint64_t p = a.pos[v] + (uint64_t)n * a.step[v];
+    const int64_t len = (int64_t)d.frames, i0 = (int64_t)(p >> 32) - (int64_t)(a.taps / 2 - 1);
+    const float* h = a.table + (size_t)((uint32_t)(p & 0xffffffffull) >> a.phase_shift) * a.taps;
+    float y = 0.0f;
+    for (uint32_t t = 0; t < a.taps; ++t) {
+        int64_t idx = i0 + (int64_t)t;
+        float x = 0.0f;
+        if (fl & 2u) { idx %= len; if (idx < 0) idx += len; x = smp_fetch(d, src_ch, (uint64_t)idx); }
+        else if (idx >= 0 && idx < len) x = smp_fetch(d, src_ch, (uint64_t)idx);
+        y = __fadd_rn(y, __fmul_rn(__ldg(h + t), x));
+    }
+    *dst = y;
+}
+
 // K-combine: radix-16 levels of the same balanced tree over partial buses [n_in][rows][T] -> [ceil(n_in/16)][rows][T].
 template <int VEC>
 __global__ void __launch_bounds__(128) combine_kernel(const float* __restrict__ pin, float* __restrict__ pout, uint32_t n_in, uint32_t rows, uint32_t T) {
@@ -834,6 +878,17 @@ cudaError_t launch_sampler(const SamplerArgs& a, cudaStream_t st) {
     const bool vec4 = (a.frames % 4 == 0) && (a.block_frames % 4 == 0) && (al % 16 == 0) && (a.out_vstride % 4 == 0);
     if (vec4) return launch_pdl(sampler_kernel<4>, dim3((a.frames / 4 + 127) / 128, a.num_voices, a.n_out), dim3(128), st, a);
     return launch_pdl(sampler_kernel<1>, dim3((a.frames + 127) / 128, a.num_voices, a.n_out), dim3(128), st, a);
+}
+cudaError_t launch_resampler_begin(uint64_t* pos, const uint64_t* seek, uint32_t* seek_flag, uint32_t V, cudaStream_t st) {
+    resampler_begin_kernel<<<(V + 127) / 128, 128, 0, st>>>(pos, seek, seek_flag, V);
+    return cudaGetLastError();
+}
+cudaError_t launch_resampler(const ResamplerArgs& a, uint64_t* pos, cudaStream_t st) {
+    if (a.n_out && a.num_voices && a.frames) {
+        resampler_kernel<<<dim3((a.frames + 127) / 128, a.num_voices, a.n_out), 128, 0, st>>>(a);
+        resampler_end_kernel<<<(a.num_voices + 127) / 128, 128, 0, st>>>(pos, a.step, a.flags, a.res, a.num_voices, a.frames);
+    }
+    return cudaGetLastError();
 }
 cudaError_t launch_silence_fix(const SilenceFixArgs& a, cudaStream_t st) {
     const bool vec4 = (a.frames % 4 == 0) && (a.block_frames % 4 == 0) && (reinterpret_cast<uintptr_t>(a.out) % 16 == 0);

@@ -43,6 +43,8 @@ struct SamplerMsgDev { uint32_t kind, a; uint64_t x, y; };  // SET_SAMPLE: a = h
 // (WRAP), or is zero (ZERO_TAIL, the sample ended), sampler.rs:445-516. CLEAR: clear_all_outputs.
 enum SmpMode : uint32_t { SMP_CLEAR = 0, SMP_PLAY = 1, SMP_PLAY_WRAP = 2, SMP_PLAY_ZERO_TAIL = 3 };
 struct SmpRec { uint64_t p0; uint32_t first, mode; };
+// polyphase resampler player (spec ours): what the control kernel needs for the silence flags (constant within a call)
+struct RsCtl { const uint32_t* flags; const uint32_t* res; const ResDesc* res_tab; uint32_t n_res, n_out; };  // flags: bit0 playing, bit1 loop
 struct SamplerCtl {
     // per-voice processor state (SamplerProcessor fields sampler.rs:283-297), persistent across calls
     uint32_t* playing; uint64_t* playhead; uint32_t* loop_flags;  // bit0: loop_range.is_some(), bit1: full_range
@@ -57,7 +59,8 @@ struct CtlTables {
     CtlNode nodes[kMaxCtlNodes];
     uint8_t in_buf[kMaxCtlPorts], in_clear[kMaxCtlPorts], out_buf[kMaxCtlPorts];
     // per-smoother state (SoA over voices, owned by the node's device state) and its target parameter
-    SamplerCtl smp[kMaxSamplers]; uint32_t n_samplers, pad2;
+    SamplerCtl smp[kMaxSamplers]; uint32_t n_samplers, n_resamplers;
+    RsCtl rs[kMaxSamplers];
     float* sm_input[kMaxSmoothers];
     float* sm_last[kMaxSmoothers];
     uint32_t* sm_status[kMaxSmoothers];
@@ -120,6 +123,7 @@ struct TemporalArgs {
     float* state;                  // [R][8][2] = {s1, s2}
     uint32_t D; float* ring; uint32_t pos;  // delay: ring [R][D], D == 0: no delay
     uint32_t srow_mul, srow_add;   // state / ring row of data row r = r * srow_mul + srow_add (1, 0 for [V][C][T] input)
+    uint32_t svf, pad;             // 1: `coeffs` holds SVF stages [R / C][ns][6] and the recurrence is the SVF's
 };
 
 // One call of the FIR reverb (reverb.cu): history roll + bf16 conversion, then the tcgen05 GEMM.
@@ -160,6 +164,14 @@ struct BusRecvArgs {
     const float* data_local; float* out; uint32_t rows, T;
     uint32_t* ack[16]; uint32_t* counter;
     uint32_t world, me, epoch, cap;
+};
+
+// Polyphase resampler data plane (spec in include/fw_b200.h). out[c] + v * out_vstride is channel c of voice v.
+struct ResamplerArgs {
+    float* out[64]; uint64_t out_vstride;
+    uint32_t n_out, num_voices, frames, taps;
+    uint32_t phase_shift, pad;
+    const float* table; const uint64_t* pos; const uint64_t* step; const uint32_t* flags; const uint32_t* res; const ResDesc* res_tab;
 };
 
 }  // namespace fw

@@ -106,6 +106,10 @@ struct NodeDeviceState {
     // conv reverb: Toeplitz-expanded IR and the ping-pong bf16 sample history (reverb.cu)
     void* d_bt = nullptr; void* d_xh[2] = {nullptr, nullptr}; uint32_t xh_cur = 0, xh_cursor = 0, xh_pitch = 0;  // cursor: where the next block is appended
     static constexpr uint32_t kReverbMaxFrames = 65536;  // longest call the history buffers are sized for
+    // polyphase resampler: table + per-voice transport mirrors + the device-resident Q32.32 position
+    float* d_rs_table = nullptr; uint32_t* d_rs_res = nullptr; uint32_t* d_rs_flags = nullptr; uint64_t* d_rs_step = nullptr;
+    uint64_t* d_rs_seek = nullptr; uint32_t* d_rs_seek_flag = nullptr; uint64_t* d_rs_pos = nullptr; bool rs_seek_uploaded = false;
+    std::vector<uint32_t> h_rs_seek_flag;
     // sampler: per-voice SamplerProcessor state (sampler.rs:283-297) + this call's messages / resource table / block records
     std::shared_ptr<ResTable> res_table;
     uint32_t* d_playing = nullptr; uint64_t* d_playhead = nullptr; uint32_t* d_loop_flags = nullptr; uint64_t* d_loop_start = nullptr; uint64_t* d_loop_end = nullptr; uint32_t* d_res = nullptr;
@@ -119,6 +123,7 @@ struct NodeDeviceState {
         cudaFree(d_coeffs); cudaFree(d_state); cudaFree(d_ring); cudaFree(d_bt); cudaFree(d_xh[0]); cudaFree(d_xh[1]);
         cudaFree(d_playing); cudaFree(d_playhead); cudaFree(d_loop_flags); cudaFree(d_loop_start); cudaFree(d_loop_end); cudaFree(d_res);
         cudaFree(d_msgs); cudaFree(d_msg_off); cudaFree(d_srec);
+        cudaFree(d_rs_table); cudaFree(d_rs_res); cudaFree(d_rs_flags); cudaFree(d_rs_step); cudaFree(d_rs_seek); cudaFree(d_rs_seek_flag); cudaFree(d_rs_pos);
     }
     const std::vector<float>& host_target(int i) const { return (kind == FW_NODE_VOLUME || kind == FW_NODE_SAMPLER) ? params->raw_gain : (i == 0 ? params->gain_l : params->gain_r); }
     // ParamSmoother::new(val): input = last_output = val, Inactive (smoother.rs:93-112; volume.rs:67-75)
@@ -152,6 +157,21 @@ struct NodeDeviceState {
                       FW_CUDA(launch_reverb_build(d_ir, d_bt, L, ich, nullptr)) && FW_CUDA(cudaDeviceSynchronize());
             cudaFree(d_ir);
             if (!ok) return false;
+        }
+        if (kind == FW_NODE_SVF) {
+            d_coeffs = dev_alloc<float>((size_t)V * params->num_stages * 6, false);
+            d_state = dev_alloc<float>((size_t)V * channels * 8 * 2);  // zero state
+            if (!d_coeffs || !d_state) return false;
+            if (params->num_stages && !FW_CUDA(cudaMemcpy(d_coeffs, params->svf_coeffs.data(), params->svf_coeffs.size() * 4, cudaMemcpyHostToDevice))) return false;
+        }
+        if (kind == FW_NODE_RESAMPLER) {
+            d_rs_table = dev_alloc<float>(params->rs_table.size(), false);
+            d_rs_res = dev_alloc<uint32_t>(V); d_rs_flags = dev_alloc<uint32_t>(V); d_rs_step = dev_alloc<uint64_t>(V);
+            d_rs_seek = dev_alloc<uint64_t>(V); d_rs_seek_flag = dev_alloc<uint32_t>(V); d_rs_pos = dev_alloc<uint64_t>(V);
+            if (!d_rs_table || !d_rs_res || !d_rs_flags || !d_rs_step || !d_rs_seek || !d_rs_seek_flag || !d_rs_pos) return false;
+            if (!FW_CUDA(cudaMemcpy(d_rs_table, params->rs_table.data(), params->rs_table.size() * 4, cudaMemcpyHostToDevice))) return false;
+            uploaded_version = 0;  // transport arrays go up with the first snapshot
+            return true;
         }
         if (kind == FW_NODE_SAMPLER) {  // SamplerProcessor::new (sampler.rs:300-320): not playing, playhead 0, no loop, no sample
             d_playing = dev_alloc<uint32_t>(V); d_playhead = dev_alloc<uint64_t>(V); d_loop_flags = dev_alloc<uint32_t>(V);
@@ -191,12 +211,33 @@ struct NodeDeviceState {
     // stream side, at call start: the relaxed atomic load of volume.rs:92, batched
     bool snapshot_params(cudaStream_t st) {
         if (kind == FW_NODE_SAMPLER && !snapshot_sampler(st)) return false;
+        if (kind == FW_NODE_RESAMPLER) {
+            res_table->snapshot(&cur_tab, &cur_n_res);
+            std::lock_guard<std::mutex> lk(params->smp_mu);
+            rs_seek_uploaded = false;
+            if (params->rs_seek_any) {  // seeks take effect at the start of this call
+                h_rs_seek_flag.assign(params->rs_seek_flag.begin(), params->rs_seek_flag.end());
+                if (!FW_CUDA(cudaMemcpyAsync(d_rs_seek, params->rs_seek.data(), (size_t)V * 8, cudaMemcpyHostToDevice, st)) ||
+                    !FW_CUDA(cudaMemcpyAsync(d_rs_seek_flag, h_rs_seek_flag.data(), (size_t)V * 4, cudaMemcpyHostToDevice, st))) return false;
+                std::fill(params->rs_seek_flag.begin(), params->rs_seek_flag.end(), (uint8_t)0); params->rs_seek_any = false;
+                rs_seek_uploaded = true;
+            }
+            if (params->version != uploaded_version) {
+                if (!FW_CUDA(cudaMemcpyAsync(d_rs_res, params->rs_res.data(), (size_t)V * 4, cudaMemcpyHostToDevice, st)) ||
+                    !FW_CUDA(cudaMemcpyAsync(d_rs_flags, params->rs_flags.data(), (size_t)V * 4, cudaMemcpyHostToDevice, st)) ||
+                    !FW_CUDA(cudaMemcpyAsync(d_rs_step, params->rs_step.data(), (size_t)V * 8, cudaMemcpyHostToDevice, st))) return false;
+                uploaded_version = params->version;
+            }
+            return true;
+        }
         const uint64_t ver = params->version;
         if (ver == uploaded_version) return true;
         for (uint32_t i = 0; i < n_sm; ++i)
             if (!FW_CUDA(cudaMemcpyAsync(d_target[i], host_target(i).data(), V * 4, cudaMemcpyHostToDevice, st))) return false;
         if (kind == FW_NODE_BIQUAD && params->num_stages &&
             !FW_CUDA(cudaMemcpyAsync(d_coeffs, params->coeffs.data(), params->coeffs.size() * 4, cudaMemcpyHostToDevice, st))) return false;
+        if (kind == FW_NODE_SVF && params->num_stages &&
+            !FW_CUDA(cudaMemcpyAsync(d_coeffs, params->svf_coeffs.data(), params->svf_coeffs.size() * 4, cudaMemcpyHostToDevice, st))) return false;
         uploaded_version = ver;
         return true;
     }
@@ -210,13 +251,14 @@ struct Plan {
     CtlTables tables{}; uint64_t* d_flags = nullptr;
     // data plane: stages run in order; pointwise stages are fused chain programs, temporal stages own state
     struct Stage { int kind = 0; /* 0 pointwise, 1 temporal */ ChainProgram prog{}; uint32_t c_in = 0, c_out = 0;
-                   std::shared_ptr<NodeDeviceState> biquad, delay, reverb, sampler; int sampler_sm = -1; };  // kind 2: reverb, kind 3: sampler head
+                   std::shared_ptr<NodeDeviceState> biquad, delay, reverb, sampler, svf; int sampler_sm = -1; };  // kind 2: reverb, kind 3: sampler head
     std::vector<Stage> stages;
     // generic lowering (arbitrary DAG of built-in nodes): one launch group per scheduled node over pool buffers [buffer][V][T]
     struct GNode { uint32_t kind = 0; std::vector<uint32_t> in_buf, out_buf; std::vector<uint8_t> in_clear; int sm0 = -1, sm1 = -1, mask_slot = -1;
                    float f0 = 0.0f; std::shared_ptr<NodeDeviceState> st; };
     bool generic = false; std::vector<GNode> gnodes; uint32_t num_buffers = 0;
     std::vector<std::shared_ptr<NodeDeviceState>> samplers;  // index = CtlTables::smp index
+    std::vector<std::shared_ptr<NodeDeviceState>> resamplers;  // index = CtlTables::rs index
     bool bus = false; uint32_t n_sm = 0, c_in = 0, c_out = 0, num_voices = 0, block_frames = 0;
     Records rec{};
     uint64_t* d_bus_mask = nullptr;
@@ -356,6 +398,15 @@ static bool lower(fw_ctx* c, const Schedule& s, Plan* plan, std::string* why) {
         tb.nodes[i].sm1 = (int16_t)tb.n_samplers++;
         plan->samplers.push_back(st);
     }
+    for (size_t i = 0; i < n; ++i) {
+        if (tb.nodes[i].kind != FW_NODE_RESAMPLER) continue;
+        if (tb.n_resamplers >= (uint32_t)kMaxSamplers) { *why = "more than 4 ResamplerNodes in one voice graph"; return false; }
+        std::shared_ptr<NodeDeviceState> st = c->node_states[s.nodes[i].id.pack()];
+        RsCtl& rc = tb.rs[tb.n_resamplers];
+        rc.flags = st->d_rs_flags; rc.res = st->d_rs_res; rc.n_out = (uint32_t)s.nodes[i].out.size();
+        tb.nodes[i].sm1 = (int16_t)tb.n_resamplers++;
+        plan->resamplers.push_back(st);
+    }
     uint32_t n_sum_masks = 0;  // generic lowering only: nodes whose data-plane body needs the per-block input silence mask
 
     const SchedNode& gin = s.nodes.front();
@@ -397,6 +448,13 @@ static bool lower(fw_ctx* c, const Schedule& s, Plan* plan, std::string* why) {
         if (kind == FW_NODE_CONV_REVERB) {
             close_pointwise(false);
             Plan::Stage ts; ts.kind = 2; ts.c_in = ts.c_out = width; ts.reverb = c->node_states[sn.id.pack()];
+            plan->stages.push_back(ts);
+            prev = sn.id;
+            continue;
+        }
+        if (kind == FW_NODE_SVF) {
+            close_pointwise(false);
+            Plan::Stage ts; ts.kind = 1; ts.c_in = ts.c_out = width; ts.svf = c->node_states[sn.id.pack()];
             plan->stages.push_back(ts);
             prev = sn.id;
             continue;
@@ -527,6 +585,16 @@ static std::shared_ptr<NodeParams> params_from_desc(const fw_node_desc* d, uint3
             for (size_t i = 0; i < (size_t)V * p->num_stages; ++i) p->coeffs[i * 5] = 1.0f;
             break;
         case FW_NODE_DELAY: p->delay = d->u0; break;
+        case FW_NODE_SVF:
+            p->num_stages = d->u0 > 8 ? 8 : d->u0;
+            p->svf_coeffs.assign((size_t)V * p->num_stages * 6, 0.0f);
+            for (size_t i = 0; i < (size_t)V * p->num_stages; ++i) { p->svf_coeffs[i * 6] = 1.0f; p->svf_coeffs[i * 6 + 3] = 1.0f; }  // identity
+            break;
+        case FW_NODE_RESAMPLER:
+            if (!d->data || d->u0 == 0 || d->u1 == 0 || d->data_len < (uint64_t)d->u0 * d->u1) return nullptr;
+            p->rs_phases = d->u0; p->rs_taps = d->u1; p->rs_table.assign(d->data, d->data + (size_t)d->u0 * d->u1);
+            p->rs_res.assign(V, 0); p->rs_flags.assign(V, 0); p->rs_step.assign(V, 1ull << 32); p->rs_seek.assign(V, 0); p->rs_seek_flag.assign(V, 0);
+            break;
         case FW_NODE_CONV_REVERB:
             if (!d->data || d->data_len < (uint64_t)d->u0 * d->u1) return nullptr;
             p->ir_len = d->u0; p->ir_channels = d->u1; p->ir.assign(d->data, d->data + (size_t)d->u0 * d->u1);
@@ -702,6 +770,59 @@ template <class G> static int sampler_push(fw_ctx* c, fw_node_id node, uint32_t 
 }
 static bool gate_always(NodeParams&, uint32_t, bool) { return true; }
 extern "C" {
+// ---- SVF + polyphase resampler (spec ours) ----------------------------------------------------
+int fw_svf_set_coeffs(fw_ctx* c, fw_node_id node, uint32_t voice, uint32_t stage, const float* k) {
+    NodeParams* p = params_of(c, node, FW_NODE_SVF);
+    if (!p || !k || stage >= p->num_stages) return -1;
+    return for_voices(p, voice, [&](uint32_t v) { std::memcpy(&p->svf_coeffs[((size_t)v * p->num_stages + stage) * 6], k, 6 * sizeof(float)); });
+}
+int fw_svf_set_all_coeffs(fw_ctx* c, fw_node_id node, const float* k, uint32_t nv, uint32_t ns) {
+    NodeParams* p = params_of(c, node, FW_NODE_SVF);
+    if (!p || !k || nv != p->num_voices || ns != p->num_stages) return -1;
+    std::memcpy(p->svf_coeffs.data(), k, (size_t)nv * ns * 6 * sizeof(float));
+    p->version += 1;
+    return 0;
+}
+void fw_svf_design(uint32_t type, double fc, double q, double sr, float* out) {
+    const double g = std::tan(M_PI * fc / sr), k = 1.0 / q;
+    const double a1 = 1.0 / (1.0 + g * (g + k)), a2 = g * a1, a3 = g * a2;
+    double m0 = 0, m1 = 0, m2 = 1;
+    switch (type) {
+        case 1: m0 = 0; m1 = 1; m2 = 0; break;
+        case 2: m0 = 1; m1 = -k; m2 = -1; break;
+        case 3: m0 = 1; m1 = -k; m2 = 0; break;
+        case 4: m0 = 1; m1 = -k; m2 = -2; break;
+        case 5: m0 = 1; m1 = -2 * k; m2 = 0; break;
+        default: break;
+    }
+    out[0] = (float)a1; out[1] = (float)a2; out[2] = (float)a3; out[3] = (float)m0; out[4] = (float)m1; out[5] = (float)m2;
+}
+int fw_resampler_set(fw_ctx* c, fw_node_id node, uint32_t voice, uint32_t res, uint64_t step, int playing, int loop) {
+    NodeParams* p = c ? params_of(c, node, FW_NODE_RESAMPLER) : nullptr;
+    uint64_t frames = 0;
+    if (!p || (res != 0 && (!c->res || !c->res->frames_of(res, &frames)))) return -1;
+    std::lock_guard<std::mutex> lk(p->smp_mu);
+    return for_voices(p, voice, [&](uint32_t v) { p->rs_res[v] = res; p->rs_step[v] = step; p->rs_flags[v] = (playing ? 1u : 0u) | (loop ? 2u : 0u); });
+}
+int fw_resampler_seek(fw_ctx* c, fw_node_id node, uint32_t voice, uint64_t pos_frames) {
+    NodeParams* p = c ? params_of(c, node, FW_NODE_RESAMPLER) : nullptr;
+    if (!p) return -1;
+    std::lock_guard<std::mutex> lk(p->smp_mu);
+    const int rc = for_voices(p, voice, [&](uint32_t v) { p->rs_seek[v] = pos_frames; p->rs_seek_flag[v] = 1; });
+    if (rc == 0) p->rs_seek_any = true;
+    return rc;
+}
+static double bessel_i0(double x) { double s = 1.0, t = 1.0; for (int k = 1; k < 64; ++k) { t *= (x / (2.0 * k)) * (x / (2.0 * k)); s += t; if (t < 1e-18 * s) break; } return s; }
+void fw_resampler_design(uint32_t P, uint32_t T, double cutoff, double beta, float* table) {
+    const double half = (double)T / 2.0, i0b = bessel_i0(beta);
+    for (uint32_t ph = 0; ph < P; ++ph) for (uint32_t t = 0; t < T; ++t) {
+        const double x = (double)t - (half - 1.0) - (double)ph / (double)P;
+        const double sn = x == 0.0 ? 1.0 : std::sin(M_PI * cutoff * x) / (M_PI * cutoff * x);
+        const double r = x / half, w = std::fabs(r) >= 1.0 ? 0.0 : bessel_i0(beta * std::sqrt(1.0 - r * r)) / i0b;
+        table[(size_t)ph * T + t] = (float)(cutoff * sn * w);
+    }
+}
+
 // ---- sample resources + SamplerNode (sampler.rs:46-181) --------------------------------------
 uint32_t fw_sample_resource_create(fw_ctx* c, uint32_t format, uint32_t channels, uint64_t frames, const void* data) {
     if (!c || !data || format > FW_SAMPLE_U16_PLANAR || channels == 0 || channels > 64 || frames == 0) return 0;
@@ -857,7 +978,7 @@ int fw_ctx_update(fw_ctx* c, fw_update_status* out) {  // context.rs:93-148
         if (msg.empty()) {
             ds = std::make_shared<NodeDeviceState>();
             ds->device = c->cfg.device; ds->kind = r->params->kind; ds->V = c->cfg.num_voices; ds->params = r->params; ds->channels = r->num_inputs;
-            if (ds->kind == FW_NODE_SAMPLER) { if (!c->res) { c->res = std::make_shared<ResTable>(); c->res->device = c->cfg.device; } ds->res_table = c->res; }
+            if (ds->kind == FW_NODE_SAMPLER || ds->kind == FW_NODE_RESAMPLER) { if (!c->res) { c->res = std::make_shared<ResTable>(); c->res->device = c->cfg.device; } ds->res_table = c->res; }
             if (!ds->create()) msg = "device allocation failed: " + g_dev_err;
         }
         if (!msg.empty()) {
@@ -1148,6 +1269,33 @@ static int enqueue_generic(fw_processor* p, Plan& pl, const float* d_in, float* 
                 }
                 break;
             }
+            case FW_NODE_RESAMPLER: {
+                NodeDeviceState& st = *gn.st;
+                if (st.rs_seek_uploaded) { if (!FW_CUDA(launch_resampler_begin(st.d_rs_pos, st.d_rs_seek, st.d_rs_seek_flag, V, p->stream))) return FW_PROC_DEVICE_ERROR; p->launches++; st.rs_seek_uploaded = false; }
+                ResamplerArgs ra{};
+                for (size_t c = 0; c < gn.out_buf.size(); ++c) ra.out[c] = buf(gn.out_buf[c]);
+                ra.out_vstride = T; ra.n_out = (uint32_t)gn.out_buf.size(); ra.num_voices = V; ra.frames = T; ra.taps = st.params->rs_taps;
+                uint32_t lg = 0; while ((1u << lg) < st.params->rs_phases) ++lg;
+                ra.phase_shift = 32 - lg;
+                ra.table = st.d_rs_table; ra.pos = st.d_rs_pos; ra.step = st.d_rs_step; ra.flags = st.d_rs_flags; ra.res = st.d_rs_res; ra.res_tab = st.cur_tab;
+                ProfScope ps(p, 3);
+                if (!FW_CUDA(launch_resampler(ra, st.d_rs_pos, p->stream))) return FW_PROC_DEVICE_ERROR;
+                p->launches += 2;
+                break;
+            }
+            case FW_NODE_SVF: {
+                NodeDeviceState& st = *gn.st;
+                const uint32_t nc = (uint32_t)gn.in_buf.size();
+                for (uint32_t c = 0; c < nc; ++c) {
+                    TemporalArgs ta{};
+                    ta.in = buf(gn.in_buf[c]); ta.out = buf(gn.out_buf[c]); ta.R = V; ta.C = 1; ta.T = T; ta.srow_mul = nc; ta.srow_add = c;
+                    ta.svf = 1; ta.ns = st.params->num_stages; ta.coeffs = st.d_coeffs; ta.state = st.d_state;
+                    ProfScope ps(p, 3);
+                    if (!FW_CUDA(launch_temporal(ta, p->stream))) return FW_PROC_DEVICE_ERROR;
+                    p->launches++;
+                }
+                break;
+            }
             case FW_NODE_BIQUAD: case FW_NODE_DELAY: {
                 NodeDeviceState& st = *gn.st;
                 const uint32_t nc = (uint32_t)gn.in_buf.size(), D = gn.kind == FW_NODE_DELAY ? st.params->delay : 0u;
@@ -1294,6 +1442,7 @@ static int proc_enqueue(fw_processor* p, const float* d_in, float* d_out, uint32
     }
     ControlArgs ca{};
     ca.tables = pl.tables; ca.rec = pl.rec;
+    for (size_t i = 0; i < pl.resamplers.size(); ++i) { ca.tables.rs[i].res_tab = pl.resamplers[i]->cur_tab; ca.tables.rs[i].n_res = pl.resamplers[i]->cur_n_res; }
     for (size_t i = 0; i < pl.samplers.size(); ++i) {
         NodeDeviceState& st = *pl.samplers[i];
         SamplerCtl& sc = ca.tables.smp[i];
@@ -1358,6 +1507,7 @@ static int proc_enqueue(fw_processor* p, const float* d_in, float* d_out, uint32
             ta.in = src; ta.out = dst; ta.R = V * sg.c_in; ta.C = sg.c_in; ta.T = T; ta.zero_first = si == 0 ? zero_first_frames : 0u;
             ta.srow_mul = 1; ta.srow_add = 0;
             if (sg.biquad) { ta.ns = sg.biquad->params->num_stages; ta.coeffs = sg.biquad->d_coeffs; ta.state = sg.biquad->d_state; }
+            if (sg.svf) { ta.svf = 1; ta.ns = sg.svf->params->num_stages; ta.coeffs = sg.svf->d_coeffs; ta.state = sg.svf->d_state; }
             if (sg.delay && sg.delay->params->delay) {
                 ta.D = sg.delay->params->delay; ta.ring = sg.delay->d_ring; ta.pos = sg.delay->ring_pos;
                 sg.delay->ring_pos = (uint32_t)(((uint64_t)sg.delay->ring_pos + T) % ta.D);

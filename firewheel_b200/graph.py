@@ -118,6 +118,16 @@ def ConvReverbNode(ir):
     return _Node(K.NODE_CONV_REVERB, u=(ir.shape[1], ir.shape[0], 0), data=ir)
 
 
+def SvfNode(num_stages):
+    return _Node(K.NODE_SVF, u=(int(num_stages), 0, 0))
+
+
+def ResamplerNode(table):
+    """table: [phases][taps] float32 (see design_resampler)."""
+    table = np.ascontiguousarray(table, dtype=np.float32)
+    return _Node(K.NODE_RESAMPLER, u=(table.shape[0], table.shape[1], 0), data=table)
+
+
 def SamplerNode(percent_volume):  # sampler.rs:56
     return _Node(K.NODE_SAMPLER, f=(float(percent_volume), 0.0, 0.0, 0.0))
 
@@ -293,6 +303,23 @@ class AudioGraph:
             self._chk(self._lib.biquad_set_all_coeffs(self._ctx, node_id, a.ctypes.data, a.shape[0], a.shape[1]), "biquad")
 
 
+    def set_svf_coeffs(self, node_id, coeffs, voice=K.FW_ALL_VOICES):
+        """coeffs: [stage][6] for the selected voices, or [voice][stage][6]; rows {a1, a2, a3, m0, m1, m2}."""
+        a = np.ascontiguousarray(coeffs, dtype=np.float32)
+        if a.ndim == 2:
+            for s in range(a.shape[0]):
+                self._chk(self._lib.svf_set_coeffs(self._ctx, node_id, voice, s, a[s].ctypes.data), "svf")
+        else:
+            self._chk(self._lib.svf_set_all_coeffs(self._ctx, node_id, a.ctypes.data, a.shape[0], a.shape[1]), "svf")
+
+    def resampler_set(self, node_id, resource, ratio=None, step_q32=None, playing=True, loop=False, voice=K.FW_ALL_VOICES):
+        """ratio: source frames advanced per output frame (Q32.32 on the wire)."""
+        step = int(step_q32) if step_q32 is not None else int(round(float(ratio) * 4294967296.0))
+        self._chk(self._lib.resampler_set(self._ctx, node_id, voice, int(resource), step, int(bool(playing)), int(bool(loop))), "resampler")
+
+    def resampler_seek(self, node_id, pos_frames, voice=K.FW_ALL_VOICES):
+        self._chk(self._lib.resampler_seek(self._ctx, node_id, voice, int(pos_frames)), "resampler")
+
     # ---- sample resources + SamplerNode (sample_resource.rs, sampler.rs:46-181) ----
     _FORMATS = {("float32", False): K.SAMPLE_F32_PLANAR, ("float32", True): K.SAMPLE_F32_INTERLEAVED,
                 ("int16", True): K.SAMPLE_I16_INTERLEAVED, ("uint16", True): K.SAMPLE_U16_INTERLEAVED,
@@ -348,6 +375,18 @@ class AudioGraph:
 
     def sampler_is_playing(self, node_id, voice=0):  # sampler.rs:163
         return self._lib.sampler_is_playing(self._ctx, node_id, voice) == 1
+
+
+def design_svf(lib, ftype, fc, q, sample_rate):
+    out = np.zeros(6, dtype=np.float32)
+    lib.svf_design(int(ftype), float(fc), float(q), float(sample_rate), out.ctypes.data)
+    return out
+
+
+def design_resampler(lib, phases=256, taps=32, cutoff=1.0, beta=9.0):
+    out = np.zeros((phases, taps), dtype=np.float32)
+    lib.resampler_design(int(phases), int(taps), float(cutoff), float(beta), out.ctypes.data)
+    return out
 
 
 def design_rbj(lib, ftype, fc, q, gain_db, sample_rate):

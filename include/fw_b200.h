@@ -76,7 +76,10 @@ enum fw_node_kind {
     FW_NODE_BIQUAD = 7,         /* spec ours (a11)  u0 = num_stages (<= 8) */
     FW_NODE_DELAY = 8,          /* spec ours (a12)  u0 = delay in frames */
     FW_NODE_CONV_REVERB = 9,    /* spec ours (a14)  u0 = ir_len, u1 = ir_channels, data = IR [ch][len] */
-    FW_NODE_SAMPLER = 10        /* basic_nodes/sampler.rs  f0 = percent_volume; 0 inputs, 1..64 outputs */
+    FW_NODE_SAMPLER = 10,       /* basic_nodes/sampler.rs  f0 = percent_volume; 0 inputs, 1..64 outputs */
+    FW_NODE_SVF = 11,           /* spec ours (a11)  u0 = num_stages (<= 8): trapezoidal state-variable filter cascade */
+    FW_NODE_RESAMPLER = 12      /* spec ours (a13)  polyphase-resampling sample player: u0 = phases P (power of two, <= 1024),
+                                   u1 = taps T (even, <= 64), data = Kaiser-windowed-sinc table [P][T]; 0 inputs, 1..64 outputs */
 };
 /* SampleResource implementations (firewheel-core/src/sample_resource.rs:28-335). Interleaved data is [frame][ch],
  * planar ("Vec<Vec<T>>") is [ch][frame]. */
@@ -214,6 +217,26 @@ FW_EXPORT int FW_FN(biquad_set_coeffs)(fw_ctx* ctx, fw_node_id node, uint32_t vo
 FW_EXPORT int FW_FN(biquad_set_all_coeffs)(fw_ctx* ctx, fw_node_id node, const float* coeffs, uint32_t n_voices, uint32_t n_stages);
 /* RBJ cookbook design, f64 -> f32, host only. type: 0 lowpass 1 highpass 2 bandpass 3 notch 4 peaking 5 lowshelf 6 highshelf */
 FW_EXPORT void FW_FN(biquad_design_rbj)(uint32_t type, double fc, double q, double gain_db, double sample_rate, float* coeffs5);
+
+/* SVF (spec ours — DESIGN.md): per stage coeffs6 = {a1, a2, a3, m0, m1, m2}; per channel and stage, with
+ * state (ic1, ic2):  v3 = x - ic2;  v1 = a1*ic1 + a2*v3;  v2 = ic2 + (a2*ic1 + a3*v3);  ic1 = 2*v1 - ic1;  ic2 = 2*v2 - ic2;
+ * y = m0*x + (m1*v1 + m2*v2)   — every product and sum a single rounded f32 operation, in this order. */
+FW_EXPORT int FW_FN(svf_set_coeffs)(fw_ctx* ctx, fw_node_id node, uint32_t voice, uint32_t stage, const float* coeffs6);
+FW_EXPORT int FW_FN(svf_set_all_coeffs)(fw_ctx* ctx, fw_node_id node, const float* coeffs, uint32_t n_voices, uint32_t n_stages);
+/* Simper/Cytomic design in f64 -> f32, host only: g = tan(pi*fc/sr), k = 1/q.
+ * type: 0 lowpass 1 bandpass 2 highpass 3 notch 4 peak 5 allpass */
+FW_EXPORT void FW_FN(svf_design)(uint32_t type, double fc, double q, double sample_rate, float* coeffs6);
+
+/* Polyphase resampler (spec ours — DESIGN.md). Per voice: a Q32.32 position `pos` and step `step`;
+ * output frame n of a call reads at p = pos + n*step:  i = p >> 32,  phase = (p & 0xffffffff) >> (32 - log2 P),
+ * y = sum_{t=0}^{T-1} table[phase][t] * x[i + t - (T/2 - 1)]   (t ascending, separate f32 multiply and add),
+ * x = 0 outside [0, frames) or, with `loop`, indices taken modulo frames. After the call pos += frames_in_call * step.
+ * Channel mapping as in the SamplerNode. Not playing / no resource => cleared and flagged. */
+FW_EXPORT int FW_FN(resampler_set)(fw_ctx* ctx, fw_node_id node, uint32_t voice, uint32_t resource, uint64_t step_q32,
+                                   int playing, int loop);
+FW_EXPORT int FW_FN(resampler_seek)(fw_ctx* ctx, fw_node_id node, uint32_t voice, uint64_t pos_frames); /* next call starts here */
+/* h[p][t] = cutoff * sinc(cutoff * (t - (T/2 - 1) - p/P)) * kaiser(beta), f64 -> f32; host only */
+FW_EXPORT void FW_FN(resampler_design)(uint32_t phases, uint32_t taps, double cutoff, double beta, float* table);
 
 /* ---- sample resources + SamplerNode (sample_resource.rs, sampler.rs:46-233) ---------------
  * A resource is uploaded once ("Arc<...>": shared by any number of voices and nodes) and lives until ctx_free.

@@ -885,6 +885,103 @@ struct SamplerNode : AudioNode {  // :46-233
     void update() override { if (active) sh->from_processor.clear(); }  // :223-232
 };
 
+// ---------------------------------------------------------------------------
+// SVF cascade (spec ours; parity unpinned by the reference): Simper/Cytomic trapezoidal
+// state-variable filter. coeffs per stage {a1, a2, a3, m0, m1, m2}; op order as written (include/fw_b200.h).
+// ---------------------------------------------------------------------------
+struct SvfCoeffs { float a1 = 1, a2 = 0, a3 = 0, m0 = 1, m1 = 0, m2 = 0; };  // identity: y = x
+struct SvfParams { uint32_t num_stages = 0; SvfCoeffs st[MAX_BIQUAD_STAGES]; };
+struct SvfProcessor : AudioNodeProcessor {
+    std::shared_ptr<SvfParams> params; std::vector<float> ic;  // [ch][stage][2]
+    SvfProcessor(std::shared_ptr<SvfParams> p, size_t channels) : params(std::move(p)), ic(channels * MAX_BIQUAD_STAGES * 2, 0.0f) {}
+    void process(size_t frames, const std::vector<const float*>& inputs, const std::vector<float*>& outputs, ProcInfo) override {
+        size_t n = std::min(inputs.size(), outputs.size());
+        for (size_t c = 0; c < n; ++c) {
+            float* st = &ic[c * MAX_BIQUAD_STAGES * 2];
+            for (size_t i = 0; i < frames; ++i) {
+                float x = inputs[c][i];
+                for (uint32_t s = 0; s < params->num_stages; ++s) {
+                    const SvfCoeffs& k = params->st[s];
+                    float& ic1 = st[s * 2]; float& ic2 = st[s * 2 + 1];
+                    float v3 = x - ic2;
+                    float v1 = (k.a1 * ic1) + (k.a2 * v3);
+                    float v2 = ic2 + ((k.a2 * ic1) + (k.a3 * v3));
+                    ic1 = (2.0f * v1) - ic1;
+                    ic2 = (2.0f * v2) - ic2;
+                    x = (k.m0 * x) + ((k.m1 * v1) + (k.m2 * v2));
+                }
+                outputs[c][i] = x;
+            }
+        }
+    }
+};
+struct SvfNode : AudioNode {
+    std::shared_ptr<SvfParams> params;
+    explicit SvfNode(uint32_t ns) : params(std::make_shared<SvfParams>()) { params->num_stages = std::min<uint32_t>(ns, MAX_BIQUAD_STAGES); }
+    const char* debug_name() const override { return "svf"; }
+    AudioNodeInfo info() const override { return AudioNodeInfo{1, 64, 1, 64, false}; }
+    std::unique_ptr<AudioNodeProcessor> activate(uint32_t, size_t, size_t ni, size_t no, std::string* err) override {
+        if (ni != no) { if (err) *err = "The number of inputs on an SvfNode must equal the number of outputs. Got num_inputs: " + std::to_string(ni) + ", num_outputs: " + std::to_string(no); return nullptr; }
+        return std::make_unique<SvfProcessor>(params, ni);
+    }
+};
+
+// ---------------------------------------------------------------------------
+// Polyphase resampler (spec ours; parity unpinned): a sample player with a Q32.32 position and step
+// reading a SampleResource through a P-phase, T-tap windowed-sinc table. Semantics: include/fw_b200.h.
+// ---------------------------------------------------------------------------
+struct ResamplerShared {
+    std::vector<float> table; uint32_t phases = 0, taps = 0, phase_shift = 32;
+    std::shared_ptr<const SampleResource> sample; uint64_t step = 1ull << 32; bool playing = false, loop = false;
+    bool seek_pending = false; uint64_t seek_frames = 0;
+};
+struct ResamplerProcessor : AudioNodeProcessor {
+    std::shared_ptr<ResamplerShared> sh; uint64_t pos = 0;
+    explicit ResamplerProcessor(std::shared_ptr<ResamplerShared> s) : sh(std::move(s)) {}
+    void process(size_t frames, const std::vector<const float*>&, const std::vector<float*>& outputs, ProcInfo pi) override {
+        if (sh->seek_pending) { pos = sh->seek_frames << 32; sh->seek_pending = false; }
+        if (!sh->sample || !sh->playing) { clear_all_outputs(frames, outputs, pi.out_silence_mask); return; }
+        const SampleResource& smp = *sh->sample;
+        const int64_t len = (int64_t)smp.len_frames(); const size_t sch = smp.num_channels(), T = sh->taps;
+        const size_t filled = std::min(outputs.size(), sch);
+        for (size_t c = 0; c < filled; ++c) {
+            for (size_t n = 0; n < frames; ++n) {
+                const uint64_t p = pos + (uint64_t)n * sh->step;
+                const int64_t i0 = (int64_t)(p >> 32) - (int64_t)(T / 2 - 1);
+                const float* h = &sh->table[(size_t)((uint32_t)(p & 0xffffffffull) >> sh->phase_shift) * T];
+                float y = 0.0f;
+                for (size_t t = 0; t < T; ++t) {
+                    int64_t idx = i0 + (int64_t)t; float x;
+                    if (sh->loop) { idx %= len; if (idx < 0) idx += len; x = smp.at(c, (uint64_t)idx); }
+                    else x = (idx >= 0 && idx < len) ? smp.at(c, (uint64_t)idx) : 0.0f;
+                    y = y + (h[t] * x);
+                }
+                outputs[c][n] = y;
+            }
+        }
+        if (outputs.size() > sch) {
+            if (outputs.size() == 2 && sch == 1) std::memcpy(outputs[1], outputs[0], frames * sizeof(float));
+            else for (size_t c = sch; c < outputs.size(); ++c) { for (size_t i = 0; i < frames; ++i) outputs[c][i] = 0.0f; pi.out_silence_mask->set_channel(c, true); }
+        }
+        pos += (uint64_t)frames * sh->step;
+    }
+};
+struct ResamplerNode : AudioNode {
+    std::shared_ptr<ResamplerShared> sh;
+    ResamplerNode(const float* table, uint32_t phases, uint32_t taps) : sh(std::make_shared<ResamplerShared>()) {
+        sh->phases = phases; sh->taps = taps; sh->table.assign(table, table + (size_t)phases * taps);
+        uint32_t lg = 0; while ((1u << lg) < phases) ++lg;
+        sh->phase_shift = 32 - lg;
+    }
+    const char* debug_name() const override { return "resampler"; }
+    AudioNodeInfo info() const override { AudioNodeInfo i; i.num_min_supported_outputs = 1; i.num_max_supported_outputs = 64; return i; }
+    std::unique_ptr<AudioNodeProcessor> activate(uint32_t, size_t, size_t, size_t no, std::string* err) override {
+        const uint32_t P = sh->phases, T = sh->taps;
+        if (no == 0 || P == 0 || P > 1024 || (P & (P - 1)) || T < 2 || T > 64 || (T & 1)) { if (err) *err = "A ResamplerNode needs >= 1 output, a power-of-two phase count <= 1024 and an even tap count <= 64."; return nullptr; }
+        return std::make_unique<ResamplerProcessor>(sh);
+    }
+};
+
 // ===========================================================================
 // firewheel-graph: graph.rs, graph/compiler.rs, graph/compiler/schedule.rs,
 // graph/error.rs, processor.rs, context.rs

@@ -47,6 +47,10 @@ static std::unique_ptr<AudioNode> make_node(const fw_node_desc* d) {
             if (!d->data || d->data_len < (uint64_t)d->u0 * d->u1) return nullptr;
             return std::make_unique<ConvReverbNode>(d->data, d->u0, d->u1);
         case FW_NODE_SAMPLER: return std::make_unique<SamplerNode>(d->f0);
+        case FW_NODE_SVF: return std::make_unique<SvfNode>(d->u0);
+        case FW_NODE_RESAMPLER:
+            if (!d->data || d->data_len < (uint64_t)d->u0 * d->u1) return nullptr;
+            return std::make_unique<ResamplerNode>(d->data, d->u0, d->u1);
         default: return nullptr;
     }
 }
@@ -61,6 +65,8 @@ static uint32_t kind_of(const AudioNode* n) {
     if (dynamic_cast<const DelayNode*>(n)) return FW_NODE_DELAY;
     if (dynamic_cast<const ConvReverbNode*>(n)) return FW_NODE_CONV_REVERB;
     if (dynamic_cast<const SamplerNode*>(n)) return FW_NODE_SAMPLER;
+    if (dynamic_cast<const SvfNode*>(n)) return FW_NODE_SVF;
+    if (dynamic_cast<const ResamplerNode*>(n)) return FW_NODE_RESAMPLER;
     return FW_NODE_DUMMY;
 }
 template <class F> static void each_voice(fw_ctx* c, uint32_t voice, F&& f) {
@@ -286,6 +292,57 @@ void fwo_biquad_design_rbj(uint32_t type, double fc, double q, double gain_db, d
             a0 = (A + 1) - (A - 1) * cw + s; a1 = 2 * ((A - 1) - (A + 1) * cw); a2 = (A + 1) - (A - 1) * cw - s; break; }
     }
     out[0] = (float)(b0 / a0); out[1] = (float)(b1 / a0); out[2] = (float)(b2 / a0); out[3] = (float)(a1 / a0); out[4] = (float)(a2 / a0);
+}
+
+// ---- SVF + polyphase resampler (spec ours) ----------------------------------------------------
+int fwo_svf_set_coeffs(fw_ctx* c, fw_node_id node, uint32_t voice, uint32_t stage, const float* k) {
+    int ok = -1;
+    each_voice(c, voice, [&](FirewheelGraphCtx& v) {
+        if (auto* n = dynamic_cast<SvfNode*>(v.graph.node(nid(node)))) if (stage < n->params->num_stages) { n->params->st[stage] = SvfCoeffs{k[0], k[1], k[2], k[3], k[4], k[5]}; ok = 0; }
+    });
+    return ok;
+}
+int fwo_svf_set_all_coeffs(fw_ctx* c, fw_node_id node, const float* k, uint32_t nv, uint32_t ns) {
+    if (nv != c->voices.size()) return -1;
+    for (uint32_t v = 0; v < nv; ++v) for (uint32_t s = 0; s < ns; ++s) if (fwo_svf_set_coeffs(c, node, v, s, k + ((size_t)v * ns + s) * 6) != 0) return -1;
+    return 0;
+}
+void fwo_svf_design(uint32_t type, double fc, double q, double sr, float* out) {
+    const double g = std::tan(M_PI * fc / sr), k = 1.0 / q;
+    const double a1 = 1.0 / (1.0 + g * (g + k)), a2 = g * a1, a3 = g * a2;
+    double m0 = 0, m1 = 0, m2 = 1;  // lowpass
+    switch (type) {
+        case 1: m0 = 0; m1 = 1; m2 = 0; break;          // bandpass
+        case 2: m0 = 1; m1 = -k; m2 = -1; break;        // highpass
+        case 3: m0 = 1; m1 = -k; m2 = 0; break;         // notch
+        case 4: m0 = 1; m1 = -k; m2 = -2; break;        // peak
+        case 5: m0 = 1; m1 = -2 * k; m2 = 0; break;     // allpass
+        default: break;
+    }
+    out[0] = (float)a1; out[1] = (float)a2; out[2] = (float)a3; out[3] = (float)m0; out[4] = (float)m1; out[5] = (float)m2;
+}
+int fwo_resampler_set(fw_ctx* c, fw_node_id node, uint32_t voice, uint32_t res, uint64_t step, int playing, int loop) {
+    if (!c || res > c->resources.size()) return -1;
+    int ok = -1;
+    each_voice(c, voice, [&](FirewheelGraphCtx& v) {
+        if (auto* n = dynamic_cast<ResamplerNode*>(v.graph.node(nid(node)))) { n->sh->sample = res ? c->resources[res - 1] : nullptr; n->sh->step = step; n->sh->playing = playing != 0; n->sh->loop = loop != 0; ok = 0; }
+    });
+    return ok;
+}
+int fwo_resampler_seek(fw_ctx* c, fw_node_id node, uint32_t voice, uint64_t pos_frames) {
+    int ok = -1;
+    each_voice(c, voice, [&](FirewheelGraphCtx& v) { if (auto* n = dynamic_cast<ResamplerNode*>(v.graph.node(nid(node)))) { n->sh->seek_pending = true; n->sh->seek_frames = pos_frames; ok = 0; } });
+    return ok;
+}
+static double bessel_i0(double x) { double s = 1.0, t = 1.0; for (int k = 1; k < 64; ++k) { t *= (x / (2.0 * k)) * (x / (2.0 * k)); s += t; if (t < 1e-18 * s) break; } return s; }
+void fwo_resampler_design(uint32_t P, uint32_t T, double cutoff, double beta, float* table) {
+    const double half = (double)T / 2.0, i0b = bessel_i0(beta);
+    for (uint32_t p = 0; p < P; ++p) for (uint32_t t = 0; t < T; ++t) {
+        const double x = (double)t - (half - 1.0) - (double)p / (double)P;   // distance of tap t from the fractional read point
+        const double s = x == 0.0 ? 1.0 : std::sin(M_PI * cutoff * x) / (M_PI * cutoff * x);
+        const double r = x / half, w = std::fabs(r) >= 1.0 ? 0.0 : bessel_i0(beta * std::sqrt(1.0 - r * r)) / i0b;
+        table[(size_t)p * T + t] = (float)(cutoff * s * w);
+    }
 }
 
 // ---- sample resources + sampler messages ---------------------------------------------------------
