@@ -123,7 +123,8 @@ struct TemporalArgs {
     float* state;                  // [R][8][2] = {s1, s2}
     uint32_t D; float* ring; uint32_t pos;  // delay: ring [R][D], D == 0: no delay
     uint32_t srow_mul, srow_add;   // state / ring row of data row r = r * srow_mul + srow_add (1, 0 for [V][C][T] input)
-    uint32_t svf, pad;             // 1: `coeffs` holds SVF stages [R / C][ns][6] and the recurrence is the SVF's
+    uint32_t svf;                  // 1: `coeffs` holds SVF stages [R / C][ns][6] and the recurrence is the SVF's
+    uint32_t row_base;             // lanes kernel: first row of CTA 0 (the ragged last CTA is launched on its own)
 };
 
 // One call of the FIR reverb (reverb.cu): history roll + bf16 conversion, then the tcgen05 GEMM.

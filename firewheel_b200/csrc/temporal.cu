@@ -43,7 +43,9 @@ constexpr int kStateStages = 8;  // state layout [row][8][2] regardless of the c
 //     flushed (coalesced) two chunks later to the ring (DELAY) or to `out`. With a delay, `out` is the old ring chunk.
 // Requires T % 32 == 0, zero_first % 32 == 0 and, with a delay, D % 32 == 0, pos % 32 == 0, D >= 160 (an old-ring
 // chunk is read two chunks ahead and must already hold the y flushed D/32 chunks earlier).
-template <int NS, int L, bool DELAY, int RPL>
+//   * FULL = true: every row of the CTA exists (the host launches the ragged last CTA separately with FULL = false), so the
+//     cooperative copies carry no per-lane predicates or branches.
+template <int NS, int L, bool DELAY, int RPL, bool FULL>
 __global__ void __launch_bounds__(32) biquad_delay_lanes(TemporalArgs a) {
     // RPL rows per lane: each lane runs stage s of RPL independent rows, so a lone warp per scheduler has RPL
     // interleaved recurrences to fill the FP32 pipe latency (measured: 1 row/lane 0.50 ms).
@@ -53,7 +55,7 @@ __global__ void __launch_bounds__(32) biquad_delay_lanes(TemporalArgs a) {
     // cost it issue slots (measured: 0.92 vs 0.64 ms per step). The implicit trigger at exit is enough.
     t_pdl_wait();  // `in` is produced by the previous kernel of this call
     const uint32_t lane = threadIdx.x, s = lane % L;
-    const uint32_t row0 = blockIdx.x * ROWS, R = a.R, T = a.T, D = a.D;
+    const uint32_t row0 = a.row_base + blockIdx.x * ROWS, R = a.R, T = a.T, D = a.D;
     const bool is_first = s == 0, is_last = NS == 0 ? s == 0 : s == (uint32_t)(NS > 0 ? NS - 1 : 0);
     __shared__ float4 xt[4][ROWS][8];
     __shared__ float4 rt[DELAY ? 3 : 1][ROWS][8];
@@ -65,7 +67,7 @@ __global__ void __launch_bounds__(32) biquad_delay_lanes(TemporalArgs a) {
     for (int j = 0; j < RPL; ++j) {
         row_l[j] = j * RSET + lane / L; rsw[j] = row_l[j] & 7u;
         const uint32_t r = row0 + row_l[j];
-        lane_ok[j] = r < R && (NS == 0 ? s == 0 : s < (uint32_t)NS);
+        lane_ok[j] = (FULL || r < R) && (NS == 0 ? s == 0 : s < (uint32_t)NS);
         last_ok[j] = is_last && lane_ok[j];
         b0[j] = b1[j] = b2[j] = a1[j] = a2[j] = s1[j] = s2[j] = q0[j] = q1[j] = 0.0f;
         yb[j][0] = yb[j][1] = yb[j][2] = yb[j][3] = 0.0f;
@@ -82,7 +84,7 @@ __global__ void __launch_bounds__(32) biquad_delay_lanes(TemporalArgs a) {
 #pragma unroll
     for (int i = 0; i < PER; ++i) {
         const uint32_t idx = lane + 32u * i, rr = idx >> 3, g = idx & 7u;
-        ok[i] = row0 + rr < R;
+        ok[i] = FULL || row0 + rr < R;
         const size_t row = ok[i] ? row0 + rr : 0;
         in_p[i] = a.in + row * T + g * 4u;
         out_p[i] = a.out + row * T + g * 4u;
@@ -90,26 +92,33 @@ __global__ void __launch_bounds__(32) biquad_delay_lanes(TemporalArgs a) {
         sw[i] = rr * 8u + (g ^ (rr & 7u));  // float4 index inside a tile
     }
     const uint32_t nch = T / 32u;
+    // Ring offsets and tile slots advance incrementally (ring chunks are issued, consumed and flushed strictly in order):
+    // a runtime `% D` costs ~20 dependent instructions through MUFU.RCP, three times per chunk, on a one-warp critical path
+    // (measured on config 3: 0.506 -> 0.467 ms per step).
+    uint32_t ring_issue_off = DELAY ? a.pos % D : 0u, ring_flush_off = ring_issue_off;  // (pos + 32 * chunk) % D
+    uint32_t ring_issue_slot = 0, ring_use_slot = 0;                                   // chunk % 3
+    auto advance = [&](uint32_t& off) { off += 32u; if (off >= D) off -= D; };
     auto issue = [&](uint32_t chx, uint32_t chr) {  // x tile of chunk chx and old-ring tile of chunk chr, one commit group
         if (chx < nch) {
 #pragma unroll
-            for (int i = 0; i < PER; ++i) if (ok[i]) cp_async16(&xt[chx & 3u][0][0] + sw[i], in_p[i] + chx * 32u);
+            for (int i = 0; i < PER; ++i) if (FULL || ok[i]) cp_async16(&xt[chx & 3u][0][0] + sw[i], in_p[i] + chx * 32u);
         }
         if (DELAY && chr < nch) {
-            const uint32_t base = (a.pos + chr * 32u) % D;
 #pragma unroll
-            for (int i = 0; i < PER; ++i) if (ok[i]) cp_async16(&rt[chr % 3u][0][0] + sw[i], ring_p[i] + base);
+            for (int i = 0; i < PER; ++i) if (FULL || ok[i]) cp_async16(&rt[ring_issue_slot][0][0] + sw[i], ring_p[i] + ring_issue_off);
+            advance(ring_issue_off);
+            ring_issue_slot = ring_issue_slot == 2u ? 0u : ring_issue_slot + 1u;
         }
         cp_async_commit();  // always one group per call so wait_group counts stay uniform
     };
-    auto flush_y = [&](uint32_t ch) {  // y tile of chunk ch -> ring (DELAY) or out, coalesced
-        const uint32_t base = DELAY ? (a.pos + ch * 32u) % D : 0u;
+    auto flush_y = [&](uint32_t ch) {  // y tile of chunk ch -> ring (DELAY) or out, coalesced; called for ch = 0, 1, 2, ... in order
 #pragma unroll
-        for (int i = 0; i < PER; ++i) if (ok[i]) {
+        for (int i = 0; i < PER; ++i) if (FULL || ok[i]) {
             const float4 v = (&yt[ch & 1u][0][0])[sw[i]];
-            if (DELAY) *reinterpret_cast<float4*>(ring_p[i] + base) = v;
+            if (DELAY) *reinterpret_cast<float4*>(ring_p[i] + ring_flush_off) = v;
             else __stcs(reinterpret_cast<float4*>(out_p[i] + ch * 32u), v);
         }
+        if (DELAY) advance(ring_flush_off);
     };
 
     // One skewed iteration of all RPL rows; gi = global iteration index, u4 = gi & 3 (compile-time when unrolled).
@@ -197,7 +206,8 @@ __global__ void __launch_bounds__(32) biquad_delay_lanes(TemporalArgs a) {
         __syncwarp();
         if (DELAY) {
 #pragma unroll
-            for (int i = 0; i < PER; ++i) if (ok[i]) __stcs(reinterpret_cast<float4*>(out_p[i] + ch * 32u), (&rt[ch % 3u][0][0])[sw[i]]);
+            for (int i = 0; i < PER; ++i) if (FULL || ok[i]) __stcs(reinterpret_cast<float4*>(out_p[i] + ch * 32u), (&rt[ring_use_slot][0][0])[sw[i]]);
+            ring_use_slot = ring_use_slot == 2u ? 0u : ring_use_slot + 1u;
         }
         const bool zero_in = ch * 32u < a.zero_first;  // Q11 (chunk-uniform)
         if (ch == 0 || zero_in) chunk(std::true_type{}, ch, zero_in);  // warm-up: stage s starts at iteration 2s
@@ -294,21 +304,27 @@ static cudaError_t launch_pdl_t(void (*kernel)(KArgs...), dim3 grid, dim3 block,
     return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
+template <int NS, int L, bool DELAY, int RPL>
+static cudaError_t launch_lanes_split(const TemporalArgs& a, cudaStream_t st) {
+    constexpr uint32_t rows_per_warp = RPL * 32 / L;
+    const uint32_t n_full = a.R / rows_per_warp;
+    if (n_full) {
+        cudaError_t e = launch_pdl_t(biquad_delay_lanes<NS, L, DELAY, RPL, true>, dim3(n_full), dim3(32), st, a);
+        if (e != cudaSuccess) return e;
+    }
+    if (a.R % rows_per_warp) {  // ragged tail: one predicated CTA
+        TemporalArgs t = a; t.row_base = n_full * rows_per_warp;
+        return launch_pdl_t(biquad_delay_lanes<NS, L, DELAY, RPL, false>, dim3(1), dim3(32), st, t);
+    }
+    return cudaSuccess;
+}
 template <int NS, int L>
 static cudaError_t launch_lanes(const TemporalArgs& a, cudaStream_t st) {
     static const int rpl_knob = getenv("FW_TEMPORAL_RPL") ? atoi(getenv("FW_TEMPORAL_RPL")) : 1;  // A/B knob (2 rows/lane measured slower: 0.59 vs 0.50 ms)
     if constexpr (L > 1) {
-        if (rpl_knob != 1) {
-            constexpr uint32_t rows_per_warp = 2 * 32 / L;
-            const dim3 grid((a.R + rows_per_warp - 1) / rows_per_warp), block(32);
-            if (a.D) return launch_pdl_t(biquad_delay_lanes<NS, L, true, 2>, grid, block, st, a);
-            return launch_pdl_t(biquad_delay_lanes<NS, L, false, 2>, grid, block, st, a);
-        }
+        if (rpl_knob != 1) return a.D ? launch_lanes_split<NS, L, true, 2>(a, st) : launch_lanes_split<NS, L, false, 2>(a, st);
     }
-    constexpr uint32_t rows_per_warp = 32 / L;
-    const dim3 grid((a.R + rows_per_warp - 1) / rows_per_warp), block(32);
-    if (a.D) return launch_pdl_t(biquad_delay_lanes<NS, L, true, 1>, grid, block, st, a);
-    return launch_pdl_t(biquad_delay_lanes<NS, L, false, 1>, grid, block, st, a);
+    return a.D ? launch_lanes_split<NS, L, true, 1>(a, st) : launch_lanes_split<NS, L, false, 1>(a, st);
 }
 
 bool temporal_fast_path(const TemporalArgs& a) {
