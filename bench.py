@@ -40,7 +40,7 @@ WORKLOADS = {
                kernel="chain_kernel<VEC=4,CIN=2,BUS,4 voices/warp,16 warps> (gain->pan->bus tree)",
                desc="c2: 1024 stereo voices/GPU, gain->pan->master-bus sum, 256-frame blocks, 256 blocks/step"),
     "c3": dict(voices=4096, ch=2, block=512, blocks=32, bus=False, bytes_per_sample=16.0, kernel_class=3,
-               kernel="biquad_delay_fast<NS=4,DELAY> (4-stage biquad cascade + 12000-frame delay ring)",
+               kernel="biquad_delay_lanes<NS=4,L=4,DELAY,FULL> (4-stage biquad cascade + 12000-frame delay ring, stage-parallel lanes)",
                desc="c3: 4096 stereo voices/GPU, 4-stage biquad cascade + 12000-frame delay line, 512-frame blocks, 32 blocks/step"),
     "c4": dict(voices=256, ch=2, block=512, blocks=16, bus=False, bytes_per_sample=8.0, kernel_class=3, ir_len=48000,
                kernel="reverb_gemm_kernel (tcgen05.mma kind::f16 M128 N256 K16, TMEM accumulators, TMA 128B-swizzle operands)",
