@@ -129,6 +129,10 @@ SIGNATURES = {
     "processor_process_planar": (_i32, [_vp, _pf, _pf, _u32, _u32, _u64, _f64, _u32, _pu64]),
     "processor_process_planar_device": (_i32, [_vp, _pf, _pf, _u32, _u32, _u64, _f64, _u32]),
     "processor_free": (None, [_vp]),
+    "stream_open": (_vp, [_vp, _u32, _u32, _u32, _u32]),
+    "stream_pull": (C.c_int64, [_vp, _vp, _u64, _pu32, C.POINTER(C.c_double)]),
+    "stream_frames_ready": (_u64, [_vp]),
+    "stream_close": (None, [_vp]),
     "device_count": (_i32, []),
     "last_device_error": (C.c_char_p, []),
     "dev_malloc": (_vp, [_i32, _u64]),

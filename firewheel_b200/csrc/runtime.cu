@@ -17,6 +17,7 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -1674,6 +1675,87 @@ int fw_processor_l2_flush(fw_processor* p) {
     if (!FW_CUDA(launch_fill(p->d_flush, n, 1.0f, p->stream))) return -1;
     return 0;
 }
+// ---- pull-style stream backend -------------------------------------------------------
+struct fw_stream {
+    fw_processor* p = nullptr; uint32_t n_out = 0, period = 0, n_periods = 0, sample_rate = 0;
+    std::vector<float> ring;                                    // [n_periods][period][n_out]
+    std::atomic<uint64_t> produced{0}, consumed{0};             // periods
+    std::atomic<uint32_t> pending_status{0};                    // flags for the next rendered period (OUTPUT_UNDERFLOW)
+    std::atomic<bool> stop{false}, dropped{false};
+    uint64_t cursor = 0, frames_delivered = 0;                  // consumer side
+    std::mutex mu; std::condition_variable cv; std::thread th;
+};
+static void stream_producer(fw_stream* s) {
+    uint64_t frames_rendered = 0;
+    while (!s->stop.load(std::memory_order_acquire)) {
+        const uint64_t prod = s->produced.load(std::memory_order_relaxed);
+        if (prod - s->consumed.load(std::memory_order_acquire) >= s->n_periods) {  // ring full: sleep until the consumer frees a period
+            std::unique_lock<std::mutex> lk(s->mu);
+            s->cv.wait_for(lk, std::chrono::milliseconds(1));
+            continue;
+        }
+        float* dst = s->ring.data() + (size_t)(prod % s->n_periods) * s->period * s->n_out;
+        const uint32_t status = s->pending_status.exchange(0, std::memory_order_acq_rel);
+        const int rc = fw_processor_process_interleaved(s->p, nullptr, dst, 0, s->n_out, s->period, (double)frames_rendered / (double)s->sample_rate, status);
+        if (rc != FW_PROC_OK) {  // DropProcessor (lib.rs:440-448) or a device error: this period is silence, and so is everything after it
+            if (rc < 0) std::fill(dst, dst + (size_t)s->period * s->n_out, 0.0f);
+            s->dropped.store(true, std::memory_order_release);
+            s->produced.store(prod + 1, std::memory_order_release);
+            return;
+        }
+        frames_rendered += s->period;
+        s->produced.store(prod + 1, std::memory_order_release);
+    }
+}
+fw_stream* fw_stream_open(fw_processor* p, uint32_t n_out, uint32_t sample_rate, uint32_t period_frames, uint32_t ring_periods) {
+    if (!p || n_out == 0 || n_out > 64 || sample_rate == 0 || period_frames == 0 || ring_periods < 2) { g_dev_err = "bad stream arguments"; return nullptr; }
+    if (!p->bus && p->num_voices != 1) { g_dev_err = "a stream needs one output: num_voices == 1 or master_bus == 1"; return nullptr; }
+    auto* s = new fw_stream();
+    s->p = p; s->n_out = n_out; s->period = period_frames; s->n_periods = ring_periods; s->sample_rate = sample_rate;
+    s->ring.assign((size_t)ring_periods * period_frames * n_out, 0.0f);
+    s->th = std::thread(stream_producer, s);
+    return s;
+}
+int64_t fw_stream_pull(fw_stream* s, float* out, uint64_t frames, uint32_t* status, double* stream_time_secs) {
+    if (!s || (!out && frames)) return -1;
+    if (status) *status = 0;
+    if (stream_time_secs) *stream_time_secs = (double)s->frames_delivered / (double)s->sample_rate;
+    uint64_t done = 0;
+    while (done < frames) {
+        const uint64_t cons = s->consumed.load(std::memory_order_relaxed);
+        if (cons == s->produced.load(std::memory_order_acquire)) {
+            if (s->dropped.load(std::memory_order_acquire)) {  // no processor any more: silence, not an underflow
+                std::fill(out + done * s->n_out, out + frames * s->n_out, 0.0f);
+                s->frames_delivered += frames - done;
+                return (int64_t)frames;
+            }
+            std::fill(out + done * s->n_out, out + frames * s->n_out, 0.0f);  // underflow: the consumer outran the producer
+            s->pending_status.fetch_or(FW_STREAM_OUTPUT_UNDERFLOW, std::memory_order_acq_rel);
+            if (status) *status |= FW_STREAM_OUTPUT_UNDERFLOW;
+            break;
+        }
+        const uint64_t n = std::min<uint64_t>(s->period - s->cursor, frames - done);
+        const float* src = s->ring.data() + ((size_t)(cons % s->n_periods) * s->period + s->cursor) * s->n_out;
+        std::memcpy(out + done * s->n_out, src, (size_t)n * s->n_out * sizeof(float));
+        done += n; s->cursor += n;
+        if (s->cursor == s->period) { s->cursor = 0; s->consumed.store(cons + 1, std::memory_order_release); s->cv.notify_one(); }
+    }
+    s->frames_delivered += done;
+    return (int64_t)done;
+}
+uint64_t fw_stream_frames_ready(fw_stream* s) {
+    if (!s) return 0;
+    const uint64_t periods = s->produced.load(std::memory_order_acquire) - s->consumed.load(std::memory_order_relaxed);
+    return periods * s->period - (periods ? s->cursor : 0);
+}
+void fw_stream_close(fw_stream* s) {
+    if (!s) return;
+    s->stop.store(true, std::memory_order_release);
+    s->cv.notify_all();
+    if (s->th.joinable()) s->th.join();
+    delete s;
+}
+
 int fw_comm_unique_id(uint8_t* id128) {
     if (!id128 || !g_nccl.load()) return -1;
     NcclUniqueId id;

@@ -395,6 +395,28 @@ def design_rbj(lib, ftype, fc, q, gain_db, sample_rate):
     return out
 
 
+class Stream:
+    """Pull-style backend (the role of firewheel-cpal's DataCallback, crates/firewheel-cpal/src/lib.rs:378-449)."""
+
+    def __init__(self, lib, handle, n_out):
+        self._lib, self._h, self.n_out = lib, handle, n_out
+
+    def frames_ready(self):
+        return self._lib.stream_frames_ready(self._h)
+
+    def pull(self, frames):
+        """-> (interleaved [frames][n_out] float32, frames delivered, status bits, stream_time_secs)"""
+        out = np.full((frames, self.n_out), np.nan, dtype=np.float32)
+        st, t = C.c_uint32(0), C.c_double(0.0)
+        n = self._lib.stream_pull(self._h, out.ctypes.data, frames, C.byref(st), C.byref(t))
+        return out, n, st.value, t.value
+
+    def close(self):
+        if self._h:
+            self._lib.stream_close(self._h)
+            self._h = None
+
+
 class FirewheelProcessor:
     """processor.rs:18 — owned by the stream side; `free()` is Drop."""
 
@@ -447,6 +469,10 @@ class FirewheelProcessor:
 
     def l2_flush(self):
         return self._lib.processor_l2_flush(self._h)
+
+    def open_stream(self, num_out_channels, sample_rate, period_frames, ring_periods=4):
+        h = self._lib.stream_open(self._h, num_out_channels, sample_rate, period_frames, ring_periods)
+        return Stream(self._lib, h, num_out_channels) if h else None
 
     def comm_init(self, rank, world_size, id128):
         buf = (C.c_uint8 * 128).from_buffer_copy(bytes(id128))

@@ -284,6 +284,23 @@ FW_EXPORT int FW_FN(processor_process_planar_device)(fw_processor* p, const floa
                                                      uint64_t frames, double stream_time_secs, uint32_t stream_status);
 FW_EXPORT void FW_FN(processor_free)(fw_processor* p);                              /* Drop processor.rs:251 */
 
+/* ---- pull-style stream backend (product only; replaces firewheel-cpal's DataCallback, crates/firewheel-cpal/src/lib.rs:378-449)
+ * cpal calls the processor from its device callback; here a producer thread renders `period_frames` at a time, ahead of
+ * the consumer, into a host ring of `ring_periods` periods, and the consumer PULLS interleaved frames. Like cpal (lib.rs:177)
+ * the stream has no input channels. stream_time_secs handed to the graph is the sample clock (frames rendered / sample
+ * rate). A pull that finds the ring empty zero-fills the rest, reports FW_STREAM_OUTPUT_UNDERFLOW, and the next rendered
+ * period carries that flag in its stream_status (lib.rs:424-428). After DropProcessor pulls deliver silence (lib.rs:446-448).
+ * Requires one output stream per context: num_voices == 1 or master_bus == 1. While a stream is open the processor must not
+ * be driven through process_* by anyone else. */
+typedef struct fw_stream fw_stream;
+FW_EXPORT fw_stream* FW_FN(stream_open)(fw_processor* p, uint32_t num_out_channels, uint32_t sample_rate, uint32_t period_frames,
+                                        uint32_t ring_periods);
+/* returns the frames delivered (<= frames; the rest of `out` is zero-filled); *status gets fw_stream_status bits;
+ * *stream_time_secs = frames delivered before this pull / sample_rate */
+FW_EXPORT int64_t FW_FN(stream_pull)(fw_stream* s, float* out_interleaved, uint64_t frames, uint32_t* status, double* stream_time_secs);
+FW_EXPORT uint64_t FW_FN(stream_frames_ready)(fw_stream* s);
+FW_EXPORT void FW_FN(stream_close)(fw_stream* s);   /* joins the producer thread; the processor stays alive */
+
 /* ---- device plumbing for drivers and benchmarks (product only; oracle returns errors) --- */
 FW_EXPORT int FW_FN(device_count)(void);
 FW_EXPORT const char* FW_FN(last_device_error)(void);

@@ -587,4 +587,11 @@ FW_EXPORT void fwo_interleave(const float* planar, uint32_t n_ch_in, uint32_t fr
     else interleave(ch, frames, interleaved, (size_t)frames * n_interleaved, n_interleaved, use_mask ? &m : nullptr);
 }
 
+// The pull-style stream backend is product plumbing (a host thread around process_interleaved): not restated here.
+struct fw_stream;
+fw_stream* fwo_stream_open(fw_processor*, uint32_t, uint32_t, uint32_t, uint32_t) { return nullptr; }
+int64_t fwo_stream_pull(fw_stream*, float*, uint64_t, uint32_t*, double*) { return -1; }
+uint64_t fwo_stream_frames_ready(fw_stream*) { return 0; }
+void fwo_stream_close(fw_stream*) {}
+
 }  // extern "C"
