@@ -45,7 +45,9 @@ constexpr int kStateStages = 8;  // state layout [row][8][2] regardless of the c
 // chunk is read two chunks ahead and must already hold the y flushed D/32 chunks earlier).
 //   * FULL = true: every row of the CTA exists (the host launches the ragged last CTA separately with FULL = false), so the
 //     cooperative copies carry no per-lane predicates or branches.
-template <int NS, int L, bool DELAY, int RPL, bool FULL>
+//   * SVF = true: the per-stage update is the trapezoidal SVF's (include/fw_b200.h) instead of the TDF-II biquad's; the lane /
+//     tile / pipeline machinery is identical. Coefficient rows are then 6 floats {a1, a2, a3, m0, m1, m2}, state {ic1, ic2}.
+template <int NS, int L, bool DELAY, int RPL, bool FULL, bool SVF = false>
 __global__ void __launch_bounds__(32) biquad_delay_lanes(TemporalArgs a) {
     // RPL rows per lane: each lane runs stage s of RPL independent rows, so a lone warp per scheduler has RPL
     // interleaved recurrences to fill the FP32 pipe latency (measured: 1 row/lane 0.50 ms).
@@ -62,18 +64,19 @@ __global__ void __launch_bounds__(32) biquad_delay_lanes(TemporalArgs a) {
     __shared__ float4 yt[2][ROWS][8];
 
     uint32_t row_l[RPL], rsw[RPL]; bool lane_ok[RPL], last_ok[RPL];
-    float b0[RPL], b1[RPL], b2[RPL], a1[RPL], a2[RPL], s1[RPL], s2[RPL], q0[RPL], q1[RPL], yb[RPL][4];
+    float b0[RPL], b1[RPL], b2[RPL], a1[RPL], a2[RPL], c5[RPL], s1[RPL], s2[RPL], q0[RPL], q1[RPL], yb[RPL][4];
 #pragma unroll
     for (int j = 0; j < RPL; ++j) {
         row_l[j] = j * RSET + lane / L; rsw[j] = row_l[j] & 7u;
         const uint32_t r = row0 + row_l[j];
         lane_ok[j] = (FULL || r < R) && (NS == 0 ? s == 0 : s < (uint32_t)NS);
         last_ok[j] = is_last && lane_ok[j];
-        b0[j] = b1[j] = b2[j] = a1[j] = a2[j] = s1[j] = s2[j] = q0[j] = q1[j] = 0.0f;
+        b0[j] = b1[j] = b2[j] = a1[j] = a2[j] = c5[j] = s1[j] = s2[j] = q0[j] = q1[j] = 0.0f;
         yb[j][0] = yb[j][1] = yb[j][2] = yb[j][3] = 0.0f;
         if (NS > 0 && lane_ok[j]) {
-            const float* k = a.coeffs + ((size_t)(r / a.C) * NS + s) * 5;
+            const float* k = a.coeffs + ((size_t)(r / a.C) * NS + s) * (SVF ? 6 : 5);
             b0[j] = k[0]; b1[j] = k[1]; b2[j] = k[2]; a1[j] = k[3]; a2[j] = k[4];
+            if (SVF) c5[j] = k[5];
             const size_t sr = (size_t)r * a.srow_mul + a.srow_add;
             s1[j] = a.state[(sr * kStateStages + s) * 2]; s2[j] = a.state[(sr * kStateStages + s) * 2 + 1];
         }
@@ -144,9 +147,19 @@ __global__ void __launch_bounds__(32) biquad_delay_lanes(TemporalArgs a) {
                 y = x[j];
             } else {
                 const float xi = is_first ? x[j] : q0[j];
-                y = __fadd_rn(__fmul_rn(b0[j], xi), s1[j]);
-                const float n1 = __fadd_rn(__fsub_rn(__fmul_rn(b1[j], xi), __fmul_rn(a1[j], y)), s2[j]);
-                const float n2 = __fsub_rn(__fmul_rn(b2[j], xi), __fmul_rn(a2[j], y));
+                float n1, n2;
+                if (SVF) {  // (b0, b1, b2, a1, a2, c5) hold (a1, a2, a3, m0, m1, m2); (s1, s2) hold (ic1, ic2)
+                    const float v3 = __fsub_rn(xi, s2[j]);
+                    const float v1 = __fadd_rn(__fmul_rn(b0[j], s1[j]), __fmul_rn(b1[j], v3));
+                    const float v2 = __fadd_rn(s2[j], __fadd_rn(__fmul_rn(b1[j], s1[j]), __fmul_rn(b2[j], v3)));
+                    n1 = __fsub_rn(__fmul_rn(2.0f, v1), s1[j]);
+                    n2 = __fsub_rn(__fmul_rn(2.0f, v2), s2[j]);
+                    y = __fadd_rn(__fmul_rn(a1[j], xi), __fadd_rn(__fmul_rn(a2[j], v1), __fmul_rn(c5[j], v2)));
+                } else {
+                    y = __fadd_rn(__fmul_rn(b0[j], xi), s1[j]);
+                    n1 = __fadd_rn(__fsub_rn(__fmul_rn(b1[j], xi), __fmul_rn(a1[j], y)), s2[j]);
+                    n2 = __fsub_rn(__fmul_rn(b2[j], xi), __fmul_rn(a2[j], y));
+                }
                 if (!CHECK || active) { s1[j] = n1; s2[j] = n2; }
                 q0[j] = q1[j];
                 q1[j] = __shfl_up_sync(0xffffffffu, y, 1);
@@ -304,17 +317,17 @@ static cudaError_t launch_pdl_t(void (*kernel)(KArgs...), dim3 grid, dim3 block,
     return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
-template <int NS, int L, bool DELAY, int RPL>
+template <int NS, int L, bool DELAY, int RPL, bool SVF = false>
 static cudaError_t launch_lanes_split(const TemporalArgs& a, cudaStream_t st) {
     constexpr uint32_t rows_per_warp = RPL * 32 / L;
     const uint32_t n_full = a.R / rows_per_warp;
     if (n_full) {
-        cudaError_t e = launch_pdl_t(biquad_delay_lanes<NS, L, DELAY, RPL, true>, dim3(n_full), dim3(32), st, a);
+        cudaError_t e = launch_pdl_t(biquad_delay_lanes<NS, L, DELAY, RPL, true, SVF>, dim3(n_full), dim3(32), st, a);
         if (e != cudaSuccess) return e;
     }
     if (a.R % rows_per_warp) {  // ragged tail: one predicated CTA
         TemporalArgs t = a; t.row_base = n_full * rows_per_warp;
-        return launch_pdl_t(biquad_delay_lanes<NS, L, DELAY, RPL, false>, dim3(1), dim3(32), st, t);
+        return launch_pdl_t(biquad_delay_lanes<NS, L, DELAY, RPL, false, SVF>, dim3(1), dim3(32), st, t);
     }
     return cudaSuccess;
 }
@@ -336,7 +349,21 @@ bool temporal_fast_path(const TemporalArgs& a) {
 
 cudaError_t launch_temporal(const TemporalArgs& a, cudaStream_t st) {
     if (a.R == 0 || a.T == 0) return cudaSuccess;
-    if (a.svf) return launch_pdl_t(svf_generic, dim3((a.R + 63) / 64), dim3(64), st, a);
+    if (a.svf) {
+        if (a.ns >= 1 && a.D == 0 && temporal_fast_path(a)) {
+            switch (a.ns) {
+                case 1: return launch_lanes_split<1, 1, false, 1, true>(a, st);
+                case 2: return launch_lanes_split<2, 2, false, 1, true>(a, st);
+                case 3: return launch_lanes_split<3, 4, false, 1, true>(a, st);
+                case 4: return launch_lanes_split<4, 4, false, 1, true>(a, st);
+                case 5: return launch_lanes_split<5, 8, false, 1, true>(a, st);
+                case 6: return launch_lanes_split<6, 8, false, 1, true>(a, st);
+                case 7: return launch_lanes_split<7, 8, false, 1, true>(a, st);
+                default: return launch_lanes_split<8, 8, false, 1, true>(a, st);
+            }
+        }
+        return launch_pdl_t(svf_generic, dim3((a.R + 63) / 64), dim3(64), st, a);
+    }
     if (temporal_fast_path(a)) {
         switch (a.ns) {
             case 0: return launch_lanes<0, 1>(a, st);

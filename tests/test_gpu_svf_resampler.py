@@ -35,7 +35,8 @@ def compare(gpu, oracle, build, calls, n_out, bus=False):
     return outs[0]
 
 
-@pytest.mark.parametrize("ns,F,T,bus", [(1, 256, 1024, False), (3, 64, 777, False), (8, 128, 512, True), (2, 100, 1000, True)])
+@pytest.mark.parametrize("ns,F,T,bus", [(1, 256, 1024, False), (3, 64, 777, False), (8, 128, 512, True), (2, 100, 1000, True),
+                                        (4, 128, 480, False), (5, 256, 2048, True), (2, 64, 4096, False), (3, 32, 96, False)])  # T % 32 == 0: the lanes kernel
 def test_svf_in_a_chain(gpu, oracle, ns, F, T, bus):
     V = 37
     co = svf_coeffs(gpu, V, ns, 10 + ns)
