@@ -245,3 +245,28 @@ def test_fanout_shares_one_buffer_and_reuse(lib):  # compiler.rs:387-399, :123-1
     assert sa.input_buffers[0][0] == sb.input_buffers[0][0] == find(schedule, gin).output_buffers[0]
     assert nb == 3  # in, a.out, b.out — the shared input cannot be recycled before b has run
     assert sa.output_buffers[0] != sb.output_buffers[0]
+
+
+def test_node_info_of_every_built_in_kind_matches(oracle, product):
+    """AudioNodeInfo (node.rs:57-79) + debug_name of every built-in node kind: the product's host tables against the oracle's
+    restated nodes (no GPU needed: nothing is activated)."""
+    import numpy as np
+    from firewheel_b200 import (AudioGraphConfig, BiquadNode, ConvReverbNode, DelayNode, DummyAudioNode, FirewheelGraphCtx, HardClipNode,
+                                MonoToStereoNode, PanNode, ResamplerNode, SamplerNode, StereoToMonoNode, SumNode, SvfNode, VolumeNode)
+    table = np.zeros((64, 16), np.float32)
+    kinds = [(DummyAudioNode, 3, 2), (lambda: VolumeNode(50.0), 2, 2), (SumNode, 4, 2), (MonoToStereoNode, 1, 2), (StereoToMonoNode, 2, 1),
+             (lambda: HardClipNode(-3.0), 2, 2), (lambda: PanNode(0.5), 2, 2), (lambda: BiquadNode(3), 2, 2), (lambda: DelayNode(100), 1, 1),
+             (lambda: ConvReverbNode(np.ones((1, 8), np.float32)), 2, 2), (lambda: SamplerNode(90.0), 0, 2), (lambda: SvfNode(2), 2, 2),
+             (lambda: ResamplerNode(table), 0, 1)]
+    infos = []
+    for lib in (oracle, product):
+        cx = FirewheelGraphCtx(lib, AudioGraphConfig(num_graph_inputs=2, num_graph_outputs=2))
+        g = cx.graph
+        rows = []
+        for mk, ni, no in kinds:
+            i = g.node_info(g.add_node(ni, no, mk()))
+            rows.append((i.kind, i.num_inputs, i.num_outputs, i.num_min_supported_inputs, i.num_max_supported_inputs,
+                         i.num_min_supported_outputs, i.num_max_supported_outputs, i.updates, i.debug_name))
+        infos.append(rows)
+        cx.free()
+    assert infos[0] == infos[1]

@@ -113,3 +113,17 @@ def test_resampler_loop_and_channel_mapping(oracle):
     y, m = run(proc, np.zeros((1, 0, 128), f32), 3)
     assert np.all(y == 0) and m == 0b111
     proc.free(); cx.update(); cx.free()
+
+
+def test_host_design_helpers_agree_between_product_and_oracle(oracle, product):
+    """The design helpers are host-only f64 code on both sides of the parity boundary; tests hand the same table / coefficients
+    to both anyway, but the helpers themselves must agree bit for bit (no GPU needed)."""
+    from firewheel_b200 import design_rbj
+    for args in [(256, 32, 1.0, 9.0), (64, 16, 0.45, 6.5), (1024, 64, 0.9, 12.0)]:
+        assert np.array_equal(design_resampler(oracle, *args).view(np.uint32), design_resampler(product, *args).view(np.uint32)), args
+    for ftype in range(6):
+        for fc, q in [(80.0, 0.5), (1234.5, 0.707), (15000.0, 8.0)]:
+            assert np.array_equal(design_svf(oracle, ftype, fc, q, SR).view(np.uint32), design_svf(product, ftype, fc, q, SR).view(np.uint32))
+    for ftype in range(7):
+        a, b = design_rbj(oracle, ftype, 997.0, 1.3, 4.5, SR), design_rbj(product, ftype, 997.0, 1.3, 4.5, SR)
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
