@@ -443,7 +443,7 @@ static bool lower(fw_ctx* c, const Schedule& s, Plan* plan, std::string* why) {
     for (size_t i = first; i + 1 < n; ++i) {
         const SchedNode& sn = s.nodes[i];
         NodeRec* nr = g.node(sn.id);
-        if (!fed_by_prev(sn, width)) { *why = "voice graph is not a linear port-to-port chain (generic per-node lowering not built yet)"; return false; }
+        if (!fed_by_prev(sn, width)) { *why = "voice graph is not a linear port-to-port chain"; return false; }
         if (sn.out.size() < 1 || sn.out.size() > 2) { *why = "the fused chain supports 1 or 2 channels"; return false; }
         const uint32_t kind = nr->params->kind;
         if (kind == FW_NODE_CONV_REVERB) {
@@ -485,7 +485,7 @@ static bool lower(fw_ctx* c, const Schedule& s, Plan* plan, std::string* why) {
             case FW_NODE_STEREO_TO_MONO: op.kind = OP_S2M; break;
             case FW_NODE_SUM:
                 if (sn.in.size() == sn.out.size()) { prev = sn.id; continue; }  // 1-port sum == copy (sum.rs:58-65): no data op
-                *why = "SumNode with more than one port inside a voice chain (generic per-node lowering not built yet)"; return false;
+                *why = "SumNode with more than one port inside a voice chain"; return false;
             default: *why = std::string("node kind '") + node_debug_name(kind) + "' has no device lowering yet"; return false;
         }
         cur.prog.ops[cur.prog.n_ops++] = op;
