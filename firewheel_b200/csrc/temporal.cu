@@ -47,8 +47,20 @@ constexpr int kStateStages = 8;  // state layout [row][8][2] regardless of the c
 //     cooperative copies carry no per-lane predicates or branches.
 //   * SVF = true: the per-stage update is the trapezoidal SVF's (include/fw_b200.h) instead of the TDF-II biquad's; the lane /
 //     tile / pipeline machinery is identical. Coefficient rows are then 6 floats {a1, a2, a3, m0, m1, m2}, state {ic1, ic2}.
-template <int NS, int L, bool DELAY, int RPL, bool FULL, bool SVF = false>
-__global__ void __launch_bounds__(32) biquad_delay_lanes(TemporalArgs a) {
+//   * WS = 1 (opt-in, FW_TEMPORAL_WS=1; compiled but NOT yet validated or measured on hardware — the round's GPU budget ran
+//     out): warp-specialised CTAs of two warps. One warp runs only the recurrence (the 11-instruction-per-sample chunk body),
+//     the other moves the tiles (cp.async loads, coalesced flushes, the delay's out copy) — the ~110 instructions of per-chunk
+//     bookkeeping that today share the compute warp's single instruction stream. Hand-over through named barriers
+//     READY[parity] (mover arrives, compute syncs) and DONE[parity] (compute arrives, mover syncs); y tiles get four slots
+//     so that a flush never meets the chunk being computed. Roles alternate with the CTA index to spread compute warps
+//     over the SM's schedulers.
+__device__ __forceinline__ void named_bar_sync(uint32_t id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(uint32_t id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
+template <int NS, int L, bool DELAY, int RPL, bool FULL, bool SVF = false, int WS = 0>
+__global__ void __launch_bounds__(WS ? 64 : 32) biquad_delay_lanes(TemporalArgs a) {
+    static_assert(!WS || (RPL == 1 && FULL), "the warp-specialised variant covers full CTAs with one row per lane");
+    constexpr uint32_t YM = WS ? 3u : 1u;            // y tile slots - 1
+    constexpr uint32_t kReady = 1, kDone = 3;         // named barriers kReady + parity, kDone + parity
     // RPL rows per lane: each lane runs stage s of RPL independent rows, so a lone warp per scheduler has RPL
     // interleaved recurrences to fill the FP32 pipe latency (measured: 1 row/lane 0.50 ms).
     constexpr int RSET = 32 / L, ROWS = RPL * RSET, PER = RPL * 8 / L, LAG = NS > 0 ? 2 * (NS - 1) : 0;
@@ -56,12 +68,13 @@ __global__ void __launch_bounds__(32) biquad_delay_lanes(TemporalArgs a) {
     // No early launch_dependents here: this kernel is issue-bound, and dependents parked at griddepcontrol.wait
     // cost it issue slots (measured: 0.92 vs 0.64 ms per step). The implicit trigger at exit is enough.
     t_pdl_wait();  // `in` is produced by the previous kernel of this call
-    const uint32_t lane = threadIdx.x, s = lane % L;
+    const uint32_t lane = threadIdx.x & 31u, s = lane % L;
+    const bool ws_mover = WS && (((threadIdx.x >> 5) ^ (blockIdx.x & 1u)) != 0u);  // the other warp computes
     const uint32_t row0 = a.row_base + blockIdx.x * ROWS, R = a.R, T = a.T, D = a.D;
     const bool is_first = s == 0, is_last = NS == 0 ? s == 0 : s == (uint32_t)(NS > 0 ? NS - 1 : 0);
     __shared__ float4 xt[4][ROWS][8];
     __shared__ float4 rt[DELAY ? 3 : 1][ROWS][8];
-    __shared__ float4 yt[2][ROWS][8];
+    __shared__ float4 yt[WS ? 4 : 2][ROWS][8];
 
     uint32_t row_l[RPL], rsw[RPL]; bool lane_ok[RPL], last_ok[RPL];
     float b0[RPL], b1[RPL], b2[RPL], a1[RPL], a2[RPL], c5[RPL], s1[RPL], s2[RPL], q0[RPL], q1[RPL], yb[RPL][4];
@@ -117,7 +130,7 @@ __global__ void __launch_bounds__(32) biquad_delay_lanes(TemporalArgs a) {
     auto flush_y = [&](uint32_t ch) {  // y tile of chunk ch -> ring (DELAY) or out, coalesced; called for ch = 0, 1, 2, ... in order
 #pragma unroll
         for (int i = 0; i < PER; ++i) if (FULL || ok[i]) {
-            const float4 v = (&yt[ch & 1u][0][0])[sw[i]];
+            const float4 v = (&yt[ch & YM][0][0])[sw[i]];
             if (DELAY) *reinterpret_cast<float4*>(ring_p[i] + ring_flush_off) = v;
             else __stcs(reinterpret_cast<float4*>(out_p[i] + ch * 32u), v);
         }
@@ -176,8 +189,8 @@ __global__ void __launch_bounds__(32) biquad_delay_lanes(TemporalArgs a) {
 #pragma unroll
         for (int j = 0; j < RPL; ++j) {
             xbase[j] = &xt[ch & 3u][row_l[j]][0];
-            ybase[j][0] = &yt[ch & 1u][row_l[j]][0];
-            ybase[j][1] = &yt[(ch + 1u) & 1u][row_l[j]][0];
+            ybase[j][0] = &yt[ch & YM][row_l[j]][0];
+            ybase[j][1] = &yt[(ch + YM) & YM][row_l[j]][0];
         }
         float4 xnext[RPL];  // software-pipelined: the LDS.128 for step n4+1 is issued before step n4 is consumed
 #pragma unroll
@@ -208,35 +221,80 @@ __global__ void __launch_bounds__(32) biquad_delay_lanes(TemporalArgs a) {
         }
     };
 
-    // groups: G(-3) = {x0}, G(-2) = {x1, ring0}, G(-1) = {x2, ring1}, G(ch) = {x(ch+3), ring(ch+2)}
-    issue(0, nch); issue(1, 0); issue(2, 1);
-    for (uint32_t ch = 0; ch < nch; ++ch) {
-        __syncwarp();  // every lane is done with x tile ch-1, ring tile ch-1 and the y tile about to be flushed
-        if (ch >= 2u) flush_y(ch - 2u);
-        __syncwarp();  // order the flush's ring stores before the ring loads issued next (they may alias when D is small)
-        issue(ch + 3u, ch + 2u);
-        cp_async_wait<2>();  // groups up to G(ch-2) have landed: x tile ch and old-ring tile ch
-        __syncwarp();
-        if (DELAY) {
+    if (WS && ws_mover) {
+        // ---- mover warp: groups G(-3) = {x0}, G(-2) = {x1, ring0}, G(-1) = {x2, ring1}, G(ch) = {x(ch+3), ring(ch+2)} ----
+        issue(0, nch); issue(1, 0); issue(2, 1);
+        for (uint32_t ch = 0; ch < nch; ++ch) {
+            cp_async_wait<1>();                       // everything but G(ch-1) has landed: x tile ch and old-ring tile ch
+            __syncwarp();
+            named_bar_arrive(kReady + (ch & 1u));     // tiles of chunk ch are ready; never more than one chunk ahead per parity
+            if (ch >= 1u) named_bar_sync(kDone + ((ch - 1u) & 1u));  // compute finished chunk ch-1: y tile ch-2 is complete, x slot (ch+3)&3 is free
+            if (ch >= 2u) flush_y(ch - 2u);
+            __syncwarp();
+            issue(ch + 3u, ch + 2u);
+            if (DELAY) {
 #pragma unroll
-            for (int i = 0; i < PER; ++i) if (FULL || ok[i]) __stcs(reinterpret_cast<float4*>(out_p[i] + ch * 32u), (&rt[ring_use_slot][0][0])[sw[i]]);
-            ring_use_slot = ring_use_slot == 2u ? 0u : ring_use_slot + 1u;
+                for (int i = 0; i < PER; ++i) __stcs(reinterpret_cast<float4*>(out_p[i] + ch * 32u), (&rt[ring_use_slot][0][0])[sw[i]]);
+                ring_use_slot = ring_use_slot == 2u ? 0u : ring_use_slot + 1u;
+            }
         }
-        const bool zero_in = ch * 32u < a.zero_first;  // Q11 (chunk-uniform)
-        if (ch == 0 || zero_in) chunk(std::true_type{}, ch, zero_in);  // warm-up: stage s starts at iteration 2s
-        else chunk(std::false_type{}, ch, false);
+        if (nch > 0) {
+            named_bar_sync(kDone + ((nch - 1u) & 1u));  // last chunk done
+            if (nch >= 2u) flush_y(nch - 2u);
+            named_bar_sync(kDone + (nch & 1u));          // drain done: tile nch-1 holds its lagged samples
+            flush_y(nch - 1u);
+        }
+        cp_async_wait<0>();
+        return;
     }
-    if (nch > 0) {
-        const float zx[RPL] = {};
+    if (WS) {
+        // ---- compute warp ----
+        for (uint32_t ch = 0; ch < nch; ++ch) {
+            named_bar_sync(kReady + (ch & 1u));
+            const bool zero_in = ch * 32u < a.zero_first;  // Q11 (chunk-uniform)
+            if (ch == 0 || zero_in) chunk(std::true_type{}, ch, zero_in);
+            else chunk(std::false_type{}, ch, false);
+            named_bar_arrive(kDone + (ch & 1u));
+        }
+        if (nch > 0) {
+            const float zx[RPL] = {};
 #pragma unroll
-        for (int j = 0; j < RPL; ++j) { ybase[j][0] = &yt[nch & 1u][row_l[j]][0]; ybase[j][1] = &yt[(nch + 1u) & 1u][row_l[j]][0]; }
+            for (int j = 0; j < RPL; ++j) { ybase[j][0] = &yt[nch & YM][row_l[j]][0]; ybase[j][1] = &yt[(nch + YM) & YM][row_l[j]][0]; }
 #pragma unroll
-        for (int it = 0; it < ((LAG + 3) & ~3); ++it) body(std::true_type{}, T + it, zx, it & 3, it >> 2);  // drain (T % 4 == 0)
-        __syncwarp();
-        if (nch >= 2u) flush_y(nch - 2u);
-        flush_y(nch - 1u);
+            for (int it = 0; it < ((LAG + 3) & ~3); ++it) body(std::true_type{}, T + it, zx, it & 3, it >> 2);  // drain (T % 4 == 0)
+            named_bar_arrive(kDone + (nch & 1u));
+        }
+    } else {
+        // groups: G(-3) = {x0}, G(-2) = {x1, ring0}, G(-1) = {x2, ring1}, G(ch) = {x(ch+3), ring(ch+2)}
+        issue(0, nch); issue(1, 0); issue(2, 1);
+        for (uint32_t ch = 0; ch < nch; ++ch) {
+            __syncwarp();  // every lane is done with x tile ch-1, ring tile ch-1 and the y tile about to be flushed
+            if (ch >= 2u) flush_y(ch - 2u);
+            __syncwarp();  // order the flush's ring stores before the ring loads issued next (they may alias when D is small)
+            issue(ch + 3u, ch + 2u);
+            cp_async_wait<2>();  // groups up to G(ch-2) have landed: x tile ch and old-ring tile ch
+            __syncwarp();
+            if (DELAY) {
+    #pragma unroll
+                for (int i = 0; i < PER; ++i) if (FULL || ok[i]) __stcs(reinterpret_cast<float4*>(out_p[i] + ch * 32u), (&rt[ring_use_slot][0][0])[sw[i]]);
+                ring_use_slot = ring_use_slot == 2u ? 0u : ring_use_slot + 1u;
+            }
+            const bool zero_in = ch * 32u < a.zero_first;  // Q11 (chunk-uniform)
+            if (ch == 0 || zero_in) chunk(std::true_type{}, ch, zero_in);  // warm-up: stage s starts at iteration 2s
+            else chunk(std::false_type{}, ch, false);
+        }
+        if (nch > 0) {
+            const float zx[RPL] = {};
+    #pragma unroll
+            for (int j = 0; j < RPL; ++j) { ybase[j][0] = &yt[nch & YM][row_l[j]][0]; ybase[j][1] = &yt[(nch + YM) & YM][row_l[j]][0]; }
+    #pragma unroll
+            for (int it = 0; it < ((LAG + 3) & ~3); ++it) body(std::true_type{}, T + it, zx, it & 3, it >> 2);  // drain (T % 4 == 0)
+            __syncwarp();
+            if (nch >= 2u) flush_y(nch - 2u);
+            flush_y(nch - 1u);
+        }
     }
-    cp_async_wait<0>();
+    if (!WS) cp_async_wait<0>();
 #pragma unroll
     for (int j = 0; j < RPL; ++j) {
         if (NS > 0 && lane_ok[j]) {
@@ -321,8 +379,15 @@ template <int NS, int L, bool DELAY, int RPL, bool SVF = false>
 static cudaError_t launch_lanes_split(const TemporalArgs& a, cudaStream_t st) {
     constexpr uint32_t rows_per_warp = RPL * 32 / L;
     const uint32_t n_full = a.R / rows_per_warp;
+    static const int ws_knob = getenv("FW_TEMPORAL_WS") ? atoi(getenv("FW_TEMPORAL_WS")) : 0;  // opt-in, see the kernel's comment
     if (n_full) {
-        cudaError_t e = launch_pdl_t(biquad_delay_lanes<NS, L, DELAY, RPL, true, SVF>, dim3(n_full), dim3(32), st, a);
+        cudaError_t e;
+        if constexpr (RPL == 1 && L >= 2) {
+            e = ws_knob ? launch_pdl_t(biquad_delay_lanes<NS, L, DELAY, 1, true, SVF, 1>, dim3(n_full), dim3(64), st, a)
+                        : launch_pdl_t(biquad_delay_lanes<NS, L, DELAY, RPL, true, SVF>, dim3(n_full), dim3(32), st, a);
+        } else {
+            e = launch_pdl_t(biquad_delay_lanes<NS, L, DELAY, RPL, true, SVF>, dim3(n_full), dim3(32), st, a);
+        }
         if (e != cudaSuccess) return e;
     }
     if (a.R % rows_per_warp) {  // ragged tail: one predicated CTA
