@@ -1,5 +1,15 @@
 // kernels.cu — sm_100a kernels for the per-block audio-graph DSP path.
 //
+//   control_kernel       K-ctl        per-voice control pass: silence flags, smoothers, sampler transport -> records
+//   chain_kernel         K-chain      fused pointwise voice chain (+ master-bus tree), the HBM-bound headline kernel
+//   sum_kernel           K-sum        multi-port SumNode on pool buffers (generic lowering)
+//   silence_fix_kernel   K-fix        +0.0 where the reference's non-fused bodies clear flagged channels (generic lowering)
+//   sampler_kernel       K-sampler    SamplerNode: resource fetch + conversion + gain
+//   resampler_*_kernel   K-resampler  polyphase windowed-sinc sample player (+ seek / advance helpers)
+//   combine_kernel       K-combine    radix-16 levels of the bus tree over partial buses
+//   (de)interleave, fill, bus_mask    stream boundary and small helpers
+// temporal.cu holds the biquad / SVF / delay kernels, reverb.cu the tcgen05 FIR GEMM, exchange.cu the peer-memory bus exchange.
+//
 // Bit-exactness rules: this TU is compiled with --fmad=false, -ftz=false,
 // -prec-div=true; recurrences additionally spell out __fmul_rn/__fadd_rn. Sum order equals the
 // graph's association order: no atomics, no order-agnostic shuffles on sample data.
