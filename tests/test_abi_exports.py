@@ -31,3 +31,15 @@ def test_header_ctypes_table_and_both_libraries_agree(oracle, product):
     # the product must not reach into the oracle: no fwo_ symbol, no dependency on its library
     needed = subprocess.run(["readelf", "-d", product.path], capture_output=True, text=True).stdout
     assert "fw_oracle" not in needed and not exported(product.path, "fwo_")
+
+
+def test_c_host_example_builds_against_the_header_and_links(product, tmp_path):
+    """examples/host.c is the binding a maintainer would write: C99, include/fw_b200.h only, linked against the product library.
+    Without a GPU it builds the graph, prints the compiled schedule and stops — the product has no CPU fallback."""
+    exe = tmp_path / "host"
+    lib_dir = Path(product.path).parent
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-I", str(ROOT / "include"), str(ROOT / "examples" / "host.c"), "-o", str(exe),
+                    "-L", str(lib_dir), "-lfirewheel_b200", "-lm", f"-Wl,-rpath,{lib_dir}"], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert "schedule: 4 nodes" in r.stdout and "beep_test" in r.stdout and "volume" in r.stdout
