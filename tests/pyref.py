@@ -4,7 +4,8 @@ oracle where the reference itself cannot be built (no Rust toolchain): small cas
 
 Covers: the executor loop and its silence flags (schedule.rs:213-343), ParamSmoother (smoother.rs:93-205), VolumeNode
 (volume.rs:85-144), SumNode (sum.rs:42-135), MonoToStereo / StereoToMono (mono_to_stereo.rs:34-49, stereo_to_mono.rs:34-55),
-HardClip (hard_clip.rs:52-94), clear_all_outputs (util.rs:165-175). The schedule (node order, buffer indices, should_clear) is
+HardClip (hard_clip.rs:52-94), clear_all_outputs (util.rs:165-175), SamplerNode with its message drain and the sample-resource
+conversions (sampler.rs:283-560, sample_resource.rs:337-456). The schedule (node order, buffer indices, should_clear) is
 taken from the library under test through `compile_internal` — the compiler has its own equivalence test."""
 import math
 
@@ -151,8 +152,9 @@ class StereoToMono:  # stereo_to_mono.rs:34-55
         return 0
 
 
-def db_to_gain_clamped(db):  # util.rs:21-27
-    return ZERO if f32(db) <= f32(-100.0) else f32(math.pow(10.0, 0.05 * float(f32(db)))) if False else f32(np.power(f32(10.0), f32(0.05) * f32(db)))
+def db_to_gain_clamped(db):  # util.rs:21-27: if db <= -100 { 0 } else { 10^(0.05 * db) }, in f32
+    db = f32(db)
+    return ZERO if db <= f32(-100.0) else f32(np.power(f32(10.0), f32(0.05) * db))
 
 
 class HardClip:  # hard_clip.rs:8-94
@@ -224,3 +226,114 @@ class Executor:
                 y[i, done:done + frames] = self.buffers[b, :frames]
             done += frames
         return y, mask
+
+
+# ---- SamplerNode (sampler.rs:283-560) + sample resources (sample_resource.rs:337-456) --------------------------------------
+def pcm_i16_to_f32(s):  # sample_resource.rs:337-340
+    return f32(s) * (f32(1.0) / f32(32767.0))
+
+
+def pcm_u16_to_f32(s):  # sample_resource.rs:342-345
+    return (f32(s) * (f32(2.0) / f32(65535.0))) - f32(1.0)
+
+
+class Resource:
+    """data: [channels][frames] float32 / int16 / uint16 (layout does not matter to the restatement: fill_buffers reads
+    channel c, frame f whichever way the resource stores it, sample_resource.rs:348-456)."""
+
+    def __init__(self, data):
+        self.data = np.asarray(data)
+        self.channels, self.frames = self.data.shape
+        self.conv = {np.dtype(np.float32): f32, np.dtype(np.int16): pcm_i16_to_f32, np.dtype(np.uint16): pcm_u16_to_f32}[self.data.dtype]
+
+    def fill_buffers(self, buffers, r0, r1, start_frame):
+        for c in range(min(len(buffers), self.channels)):
+            for i in range(r0, r1):
+                f = start_frame + (i - r0)
+                buffers[c][i] = self.conv(self.data[c, f]) if f < self.frames else ZERO  # past the end: the reference panics; defined as 0.0
+
+
+def secs_to_frame(secs, sr):  # `(secs * sr as f64).round() as u64`, saturating (sampler.rs:250-251, 394)
+    f = math.floor(abs(secs * sr) + 0.5) * (1 if secs >= 0 else -1)  # f64::round: half away from zero
+    return 0 if not f > 0 else int(f)
+
+
+class Sampler:
+    def __init__(self, percent, sr, mbf):
+        self.raw_gain = percent_to_raw_gain(max(f32(percent), ZERO))
+        self.sm = Smoother(self.raw_gain, sr, mbf)
+        self.sr, self.playing, self.playhead, self.loop, self.sample, self.msgs = sr, False, 0, None, None, []
+
+    def set_percent(self, p):
+        self.raw_gain = percent_to_raw_gain(p)
+
+    def loop_start_or_zero(self):
+        return self.loop[0] if self.loop else 0
+
+    def process(self, frames, inputs, outputs, in_mask):
+        for m in self.msgs:  # sampler.rs:331-414
+            kind = m[0]
+            if kind == "set_sample":
+                self.sample = m[1]
+                if self.loop and self.loop[2]:
+                    self.loop = [0, self.sample.frames, True]
+                if m[2]:
+                    self.playhead = self.loop_start_or_zero(); self.playing = False
+            elif kind == "play":
+                self.playing = True
+            elif kind == "pause":
+                self.playing = False
+            elif kind == "stop":
+                self.playhead = self.loop_start_or_zero(); self.playing = False
+            elif kind == "playhead":
+                self.playhead = secs_to_frame(m[1], self.sr)
+            else:  # ("loop", None | "full" | (start, end))
+                if m[1] is None:
+                    self.loop = None
+                else:
+                    self.loop = [0, self.sample.frames if self.sample else 0, True] if m[1] == "full" else [secs_to_frame(m[1][0], self.sr), secs_to_frame(m[1][1], self.sr), False]
+                    if self.loop[0] <= self.playhead < self.loop[1]:
+                        self.playhead = self.loop[0]
+        self.msgs = []
+        if self.sample is None or not self.playing:  # :416-430
+            return clear_all_outputs(frames, outputs)
+        gain, smoothing = self.sm.set_and_process(self.raw_gain, frames)
+        if not smoothing and gain[0] < f32(0.00001):  # :437-443
+            return clear_all_outputs(frames, outputs)
+        smp = self.sample
+        if self.loop:  # :445-484
+            if self.playhead >= self.loop[1]:
+                self.playhead = self.loop[0]
+            first = min(frames, self.loop[1] - self.playhead)
+            smp.fill_buffers(outputs, 0, first, self.playhead)
+            if first < frames:
+                self.playhead = self.loop[0]
+                smp.fill_buffers(outputs, first, frames, self.playhead)
+                self.playhead += frames - first
+            else:
+                self.playhead += frames
+        else:  # :485-516
+            if self.playhead >= smp.frames:
+                self.playing = False
+                return clear_all_outputs(frames, outputs)
+            copy = min(frames, smp.frames - self.playhead)
+            smp.fill_buffers(outputs, 0, copy, self.playhead)
+            if copy < frames:
+                self.playing = False; self.playhead = 0
+                for o in outputs:
+                    o[copy:frames] = ZERO
+            else:
+                self.playhead += frames
+        sch = smp.channels
+        for c in range(min(len(outputs), sch)):  # :522-543 (the stereo loop is the same arithmetic)
+            for i in range(frames):
+                outputs[c][i] = outputs[c][i] * gain[i]
+        mask = 0
+        if len(outputs) > sch:  # :545-559
+            if len(outputs) == 2 and sch == 1:
+                outputs[1][:frames] = outputs[0][:frames]
+            else:
+                for c in range(sch, len(outputs)):
+                    outputs[c][:frames] = ZERO
+                    mask |= 1 << c
+        return mask

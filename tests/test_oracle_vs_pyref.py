@@ -78,3 +78,62 @@ def test_oracle_equals_the_python_restatement(oracle, seed):
         assert np.array_equal(out[0].view(np.uint32), want.view(np.uint32)), (seed, call, np.argwhere(out[0].view(np.uint32) != want.view(np.uint32))[:3])
         assert mask == want_mask, (seed, call, hex(mask), hex(want_mask))
     proc.free(); cx.update(); cx.free()
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_sampler_oracle_equals_the_python_restatement(oracle, seed):
+    """SamplerNode under random transport: resources of every sample type, set_sample / play / pause / stop / set_playhead /
+    loop ranges / volume changes between calls, samples ending and loops wrapping inside blocks."""
+    from firewheel_b200 import SamplerNode
+    rng = np.random.default_rng(500 + seed)
+    F, n_out = int(rng.choice([8, 16, 20])), int(rng.integers(1, 4))
+    cx = FirewheelGraphCtx(oracle, AudioGraphConfig(num_graph_inputs=0, num_graph_outputs=n_out))
+    g = cx.graph
+    smp = g.add_node(0, n_out, SamplerNode(100.0))
+    for c in range(n_out):
+        g.connect(smp, c, g.graph_out_node(), c, False)
+    sched, nb = g.compile_internal(F)
+    py_s = pyref.Sampler(100.0, SR, F)
+    py = {int(g.graph_in_node()): pyref.Dummy(), int(g.graph_out_node()): pyref.Dummy(), int(smp): py_s}
+    ex = pyref.Executor([(int(s.id), s.input_buffers, s.output_buffers) for s in sched], nb, F, py)
+    proc = cx.activate(SR, 0, n_out, F)
+    assert cx.update().graph_error is None
+    datas = [synth((2, 50), seed), synth((1, 37), seed + 1), rng.integers(-32768, 32768, size=(2, 64)).astype(np.int16),
+             rng.integers(0, 65536, size=(1, 45)).astype(np.uint16), synth((3, 29), seed + 2)]
+    res = [(g.create_sample_resource(d), pyref.Resource(d)) for d in datas]
+    node_playing = False  # SamplerNode::playing (sampler.rs:51): play / pause / stop are filtered on the node side
+    for call in range(10):
+        for _ in range(int(rng.integers(0, 4))):
+            op = rng.choice(["set_sample", "play", "pause", "stop", "playhead", "loop_none", "loop_full", "loop_range", "volume"])
+            if op == "set_sample":
+                h, r = res[int(rng.integers(len(res)))]; stop = bool(rng.integers(2))
+                g.sampler_set_sample(smp, h, stop); py_s.msgs.append(("set_sample", r, stop))
+            elif op == "play":
+                g.sampler_play(smp)
+                if not node_playing:
+                    py_s.msgs.append(("play",)); node_playing = True
+            elif op in ("pause", "stop"):
+                getattr(g, "sampler_" + op)(smp)
+                if node_playing:
+                    py_s.msgs.append((op,)); node_playing = False
+            elif op == "playhead":
+                secs = float(rng.integers(0, 70)) / SR
+                g.sampler_set_playhead(smp, secs); py_s.msgs.append(("playhead", secs))
+            elif op == "loop_none":
+                g.sampler_set_loop_range(smp, None); py_s.msgs.append(("loop", None))
+            elif op == "loop_full":
+                g.sampler_set_loop_range(smp, "full"); py_s.msgs.append(("loop", "full"))
+            elif op == "loop_range":
+                a = int(rng.integers(0, 20)); b = a + int(rng.integers(3, 25))   # may reach past short samples: zeros there
+                g.sampler_set_loop_range(smp, (a / SR, b / SR)); py_s.msgs.append(("loop", (a / SR, b / SR)))
+            else:
+                pct = float(rng.choice([0.0, 50.0, 100.0]))
+                g.sampler_set_percent_volume(smp, pct); py_s.set_percent(pct)
+        T = int(rng.choice([F, 2 * F, 3 * F]))  # whole blocks (Q1: the reference asserts on short blocks while the smoother idles)
+        out = np.full((1, n_out, T), np.nan, f32)
+        rc, mask = proc.process_planar(np.zeros((1, 0, T), f32), out, 0, n_out, T)
+        assert rc == 0
+        want, want_mask = ex.process(np.zeros((0, T), f32), n_out)
+        assert np.array_equal(out[0].view(np.uint32), want.view(np.uint32)), (seed, call)
+        assert mask == want_mask, (seed, call, hex(mask), hex(want_mask))
+    proc.free(); cx.update(); cx.free()
