@@ -14,15 +14,22 @@
 //     percent_volume_to_raw_gain, Volume/Sum/MonoToStereo/StereoToMono/HardClip
 //     processors, AudioGraph, the compiler (Kahn sort + buffer allocator),
 //     CompiledSchedule::{prepare_graph_inputs,process,read_graph_outputs},
-//     FirewheelProcessor::process_interleaved, FirewheelGraphCtx.
+//     FirewheelProcessor::process_interleaved, FirewheelGraphCtx, SamplerNode /
+//     SamplerProcessor and the SampleResource implementations.
 //     The reference's only tests are 5 *structural* schedule tests
 //     (schedule.rs:407,451,539,662,685); all five are re-run against this file
-//     in tests/test_oracle_structural.py. The reference holds NO numeric golden
-//     vectors, so numeric parity is anchored on the restated formulas plus
-//     hand-derived known answers (tests/test_oracle_kat.py).
+//     in tests/test_structural.py. The reference holds NO numeric golden
+//     vectors, so numeric parity is anchored on (i) the restated formulas plus
+//     hand-derived known answers (tests/test_oracle_kat.py, tests/test_sampler_oracle.py),
+//     (ii) a second, independent restatement of the executor, the smoother, the
+//     pinned nodes and the sampler in pure Python (tests/pyref.py) that must agree
+//     with this file bit for bit on random graphs (tests/test_oracle_vs_pyref.py),
+//     (iii) committed golden vectors (tests/golden/).
 //   * PARITY UNPINNED (no reference code or tests exist; the spec below IS the
-//     definition): PanNode, BiquadNode, DelayNode, ConvReverbNode. They follow
-//     SURVEY.md §8 a10-a14 and are cross-checked against scipy in tests.
+//     definition): PanNode, BiquadNode, SvfNode, DelayNode, ResamplerNode,
+//     ConvReverbNode. They follow SURVEY.md §8 a10-a14 and are cross-checked
+//     against scipy / closed forms (tests/test_oracle_kat.py,
+//     tests/test_svf_resampler_oracle.py).
 //   * thunderdome 0.6.1 (generational arena; absent from /root/reference, a
 //     Cargo dependency: crates/firewheel-graph/Cargo.toml:21) is restated from
 //     its published algorithm: LIFO free list, generation bumped on slot reuse,
