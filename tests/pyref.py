@@ -227,6 +227,44 @@ class Executor:
             done += frames
         return y, mask
 
+    def process_interleaved(self, x, n_out):  # processor.rs:93-150 with util.rs:43-147; x: [T][n_in] -> [T][n_out]
+        T, n_in = x.shape
+        y = np.zeros((T, n_out), f32)
+        done = 0
+        while done < T:
+            frames = min(T - done, self.mbf)
+            gin_outs = self.sched[0][2]
+            fill = min(n_in, len(gin_outs))
+            for i in range(fill):  # deinterleave (util.rs:43-87); its stale-buffer silence mask (Q4) is overwritten by graph_in below
+                self.buffers[gin_outs[i], :frames] = x[done:done + frames, i]
+            for b in gin_outs[fill:]:
+                self.buffers[b, :frames] = ZERO
+                self.flags[b] = True
+            for key, ins, outs in self.sched:
+                in_mask = 0
+                for i, (b, clear) in enumerate(ins):
+                    if clear:
+                        self.buffers[b, :frames] = ZERO
+                        self.flags[b] = True
+                    if self.flags[b]:
+                        in_mask |= 1 << i
+                out_mask = self.procs[key].process(frames, [self.buffers[b] for b, _ in ins], [self.buffers[b] for b in outs], in_mask)
+                for i, b in enumerate(outs):
+                    self.flags[b] = bool((out_mask >> i) & 1)
+            gout_ins = self.sched[-1][1]
+            chans = [gout_ins[i][0] for i in range(min(n_out, len(gout_ins)))]
+            mask = sum(1 << i for i, b in enumerate(chans) if self.flags[b])
+            blk = y[done:done + frames]
+            if len(chans) == 2 and n_out == 2:  # interleave_stereo (util.rs:123-147): zeros only if BOTH channels are flagged
+                if mask & 3 != 3:
+                    blk[:, 0] = self.buffers[chans[0], :frames]; blk[:, 1] = self.buffers[chans[1], :frames]
+            else:  # interleave (util.rs:90-120): zero-fill, then every channel that is not flagged
+                for i, b in enumerate(chans):
+                    if not (mask >> i) & 1:
+                        blk[:, i] = self.buffers[b, :frames]
+            done += frames
+        return y
+
 
 # ---- SamplerNode (sampler.rs:283-560) + sample resources (sample_resource.rs:337-456) --------------------------------------
 def pcm_i16_to_f32(s):  # sample_resource.rs:337-340

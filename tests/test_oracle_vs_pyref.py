@@ -137,3 +137,24 @@ def test_sampler_oracle_equals_the_python_restatement(oracle, seed):
         assert np.array_equal(out[0].view(np.uint32), want.view(np.uint32)), (seed, call)
         assert mask == want_mask, (seed, call, hex(mask), hex(want_mask))
     proc.free(); cx.update(); cx.free()
+
+
+@pytest.mark.parametrize("seed", range(16, 28))
+def test_interleaved_entry_point_equals_the_python_restatement(oracle, seed):
+    """process_interleaved (processor.rs:61-165): deinterleave, block loop, and the two interleave flavours with their different
+    treatment of flagged channels (util.rs:90-147)."""
+    F = int(np.random.default_rng(seed).choice([8, 16]))
+    cx, proc, n_in, n_out, ex, py, vols = build(oracle, seed, F)
+    rng = np.random.default_rng(900 + seed)
+    for call in range(4):
+        if call == 2:
+            for nid in vols:
+                pct = float(rng.choice([0.0, 60.0]))
+                cx.graph.set_percent_volume(nid, pct); py[int(nid)].set_percent(pct)
+        T = int(rng.choice([F, 2 * F + 3]))
+        x = np.ascontiguousarray(synth((T, n_in), 11 * seed + call))
+        out = np.full((T, n_out), np.nan, f32)
+        assert proc.process_interleaved(x, out, n_in, n_out, T) == 0
+        want = ex.process_interleaved(x, n_out)
+        assert np.array_equal(out.view(np.uint32), want.view(np.uint32)), (seed, call)
+    proc.free(); cx.update(); cx.free()
