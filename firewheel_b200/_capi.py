@@ -150,6 +150,7 @@ SIGNATURES = {
     "processor_profile_read": (_i32, [_vp, C.c_void_p, C.c_void_p]),
     "comm_unique_id": (_i32, [C.c_void_p]),
     "processor_comm_init": (_i32, [_vp, _i32, _i32, C.c_void_p]),
+    "processor_comm_allgather": (_i32, [_vp, C.c_void_p, C.c_void_p, _u64]),
 }
 
 

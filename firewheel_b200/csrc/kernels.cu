@@ -606,7 +606,7 @@ template <int VEC>
 __global__ void __launch_bounds__(128) sum_kernel(const __grid_constant__ SumArgs a) {
     pdl_launch_dependents();
     pdl_wait();
-    const uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) * VEC, v = blockIdx.y, T = a.frames, V = a.num_voices;
+    const uint32_t t = (blockIdx.y * blockDim.x + threadIdx.x) * VEC, v = blockIdx.x, T = a.frames, V = a.num_voices;  // voices on grid.x (no 65535 cap)
     if (t >= T) return;
     const size_t off = (size_t)v * T + t;
     uint64_t mask = 0;
@@ -640,7 +640,7 @@ template <int VEC>
 __global__ void __launch_bounds__(128) silence_fix_kernel(const __grid_constant__ SilenceFixArgs a) {
     pdl_launch_dependents();
     pdl_wait();
-    const uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) * VEC, v = blockIdx.y, T = a.frames, V = a.num_voices;
+    const uint32_t t = (blockIdx.y * blockDim.x + threadIdx.x) * VEC, v = blockIdx.x, T = a.frames, V = a.num_voices;  // voices on grid.x (no 65535 cap)
     if (t >= T) return;
     const uint32_t k = t / a.block_frames, sk = a.rec.steady_k[v];
     const uint64_t mask = k >= sk ? a.rec.st_sum_masks[(size_t)a.mask_slot * V + v] : a.rec.sum_masks[((size_t)rec_slot(a.rec, v, k, V) * a.rec.n_sum_masks + a.mask_slot) * V + v];
@@ -669,7 +669,7 @@ template <int VEC>
 __global__ void __launch_bounds__(128) sampler_kernel(const __grid_constant__ SamplerArgs a) {
     pdl_launch_dependents();
     pdl_wait();
-    const uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) * VEC, v = blockIdx.y, c = blockIdx.z, T = a.frames, V = a.num_voices, F = a.block_frames;
+    const uint32_t t = (blockIdx.y * blockDim.x + threadIdx.x) * VEC, v = blockIdx.x, c = blockIdx.z, T = a.frames, V = a.num_voices, F = a.block_frames;
     if (t >= T) return;
     const uint32_t k = t / F, f0 = t - k * F;
     const SmpRec r = a.srec[(size_t)k * V + v];
@@ -720,7 +720,7 @@ __global__ void resampler_end_kernel(uint64_t* pos, const uint64_t* step, const 
     if (v < V && (flags[v] & 1u) && res[v] != 0) pos[v] += (uint64_t)frames * step[v];
 }
 __global__ void __launch_bounds__(128) resampler_kernel(const __grid_constant__ ResamplerArgs a) {
-    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y, c = blockIdx.z;
+    const uint32_t n = blockIdx.y * blockDim.x + threadIdx.x, v = blockIdx.x, c = blockIdx.z;
     if (n >= a.frames) return;
     float* dst = a.out[c] + (size_t)v * a.out_vstride + n;
     const uint32_t r = a.res[v], fl = a.flags[v];
@@ -878,16 +878,16 @@ cudaError_t launch_sum(const SumArgs& a, cudaStream_t st) {
     uintptr_t al = reinterpret_cast<uintptr_t>(a.out);
     for (uint32_t p = 0; p < a.n_ports; ++p) al |= reinterpret_cast<uintptr_t>(a.in[p]);
     const bool vec4 = (a.frames % 4 == 0) && (a.block_frames % 4 == 0) && (al % 16 == 0);
-    if (vec4) return launch_pdl(sum_kernel<4>, dim3((a.frames / 4 + 127) / 128, a.num_voices), dim3(128), st, a);
-    return launch_pdl(sum_kernel<1>, dim3((a.frames + 127) / 128, a.num_voices), dim3(128), st, a);
+    if (vec4) return launch_pdl(sum_kernel<4>, dim3(a.num_voices, (a.frames / 4 + 127) / 128), dim3(128), st, a);
+    return launch_pdl(sum_kernel<1>, dim3(a.num_voices, (a.frames + 127) / 128), dim3(128), st, a);
 }
 cudaError_t launch_sampler(const SamplerArgs& a, cudaStream_t st) {
     if (a.n_out == 0 || a.num_voices == 0 || a.frames == 0) return cudaSuccess;
     uintptr_t al = 0;
     for (uint32_t c = 0; c < a.n_out; ++c) al |= reinterpret_cast<uintptr_t>(a.out[c]);
     const bool vec4 = (a.frames % 4 == 0) && (a.block_frames % 4 == 0) && (al % 16 == 0) && (a.out_vstride % 4 == 0);
-    if (vec4) return launch_pdl(sampler_kernel<4>, dim3((a.frames / 4 + 127) / 128, a.num_voices, a.n_out), dim3(128), st, a);
-    return launch_pdl(sampler_kernel<1>, dim3((a.frames + 127) / 128, a.num_voices, a.n_out), dim3(128), st, a);
+    if (vec4) return launch_pdl(sampler_kernel<4>, dim3(a.num_voices, (a.frames / 4 + 127) / 128, a.n_out), dim3(128), st, a);
+    return launch_pdl(sampler_kernel<1>, dim3(a.num_voices, (a.frames + 127) / 128, a.n_out), dim3(128), st, a);
 }
 cudaError_t launch_resampler_begin(uint64_t* pos, const uint64_t* seek, uint32_t* seek_flag, uint32_t V, cudaStream_t st) {
     resampler_begin_kernel<<<(V + 127) / 128, 128, 0, st>>>(pos, seek, seek_flag, V);
@@ -895,15 +895,15 @@ cudaError_t launch_resampler_begin(uint64_t* pos, const uint64_t* seek, uint32_t
 }
 cudaError_t launch_resampler(const ResamplerArgs& a, uint64_t* pos, cudaStream_t st) {
     if (a.n_out && a.num_voices && a.frames) {
-        resampler_kernel<<<dim3((a.frames + 127) / 128, a.num_voices, a.n_out), 128, 0, st>>>(a);
+        resampler_kernel<<<dim3(a.num_voices, (a.frames + 127) / 128, a.n_out), 128, 0, st>>>(a);
         resampler_end_kernel<<<(a.num_voices + 127) / 128, 128, 0, st>>>(pos, a.step, a.flags, a.res, a.num_voices, a.frames);
     }
     return cudaGetLastError();
 }
 cudaError_t launch_silence_fix(const SilenceFixArgs& a, cudaStream_t st) {
     const bool vec4 = (a.frames % 4 == 0) && (a.block_frames % 4 == 0) && (reinterpret_cast<uintptr_t>(a.out) % 16 == 0);
-    if (vec4) return launch_pdl(silence_fix_kernel<4>, dim3((a.frames / 4 + 127) / 128, a.num_voices), dim3(128), st, a);
-    return launch_pdl(silence_fix_kernel<1>, dim3((a.frames + 127) / 128, a.num_voices), dim3(128), st, a);
+    if (vec4) return launch_pdl(silence_fix_kernel<4>, dim3(a.num_voices, (a.frames / 4 + 127) / 128), dim3(128), st, a);
+    return launch_pdl(silence_fix_kernel<1>, dim3(a.num_voices, (a.frames + 127) / 128), dim3(128), st, a);
 }
 cudaError_t launch_deinterleave(const float* inter, float* planar, uint32_t V, uint32_t C, uint32_t T, cudaStream_t st) {
     const size_t n = (size_t)V * C * T; if (n == 0) return cudaSuccess;

@@ -32,6 +32,7 @@ cudaError_t launch_temporal(const TemporalArgs& a, cudaStream_t st);
 bool temporal_fast_path(const TemporalArgs& a);
 uint32_t reverb_kpad(uint32_t L);
 uint32_t reverb_hist(uint32_t L);
+uint32_t reverb_grid_max();   // CTAs of the persistent GEMM grid (= SMs)
 cudaError_t launch_reverb_build(const float* d_ir, void* d_bt, uint32_t L, uint32_t ir_ch, cudaStream_t st);
 cudaError_t launch_reverb(const ReverbCall& rc, cudaStream_t st, std::string* err);
 }  // namespace fw

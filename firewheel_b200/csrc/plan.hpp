@@ -117,7 +117,7 @@ struct ChainArgs {
 
 // One pass of the temporal kernel over R = voices * channels rows of T frames.
 struct TemporalArgs {
-    const float* in; float* out;   // [R][T]
+    const float* in; float* out;   // [R][in_pitch] / [R][out_pitch], T frames used
     uint32_t R, C, T, zero_first;  // zero_first: leading frames read as 0.0 (Q11)
     uint32_t ns; const float* coeffs;  // biquad: [R / C][ns][5] = {b0,b1,b2,a1,a2}; ns == 0: no biquad
     float* state;                  // [R][8][2] = {s1, s2}
@@ -125,6 +125,8 @@ struct TemporalArgs {
     uint32_t srow_mul, srow_add;   // state / ring row of data row r = r * srow_mul + srow_add (1, 0 for [V][C][T] input)
     uint32_t svf;                  // 1: `coeffs` holds SVF stages [R / C][ns][6] and the recurrence is the SVF's
     uint32_t row_base;             // lanes kernel: first row of CTA 0 (the ragged last CTA is launched on its own)
+    uint32_t in_pitch, out_pitch;  // floats between rows of `in` / `out` (0: T). A call chunk is a column window of longer rows.
+    float k_one, k_negzero, k_negone, k_two;  // set by launch_temporal: opaque constants of the packed kernel's exact-fma spelling
 };
 
 // One call of the FIR reverb (reverb.cu): history roll + bf16 conversion, then the tcgen05 GEMM.
@@ -134,6 +136,7 @@ struct ReverbCall {
     const void* bt;                     // bf16 Toeplitz expansion of the IR [ir_ch][256][kpad]
     uint32_t V, C, T, L, ir_ch, cursor, pitch, zero_first;
     uint32_t chan_base;                 // history rows / IR channel of data channel c are (chan_base + c)
+    uint32_t in_pitch, out_pitch;       // floats between (voice, channel) rows of in / out (0: T)
 };
 
 // Multi-port SumNode on pool buffers (sum.rs:69-133): out = in[0] + in[1] + ... strictly left to right.

@@ -3,7 +3,7 @@
 //   y[v][n] = sum_{k<L} bf16(h_c[k]) * bf16(x[v][n-k])          (per IR channel c; products exact, fp32 accumulate)
 //
 // For one IR channel all voices share h, so a tile of outputs is a plain GEMM with a long reduction:
-//   D[128 voices][256 frames] = A[128][K] * Bt[256][K]^T,   K = L + 255 (padded to 64)
+//   D[128 voices][BN frames] = A[128][K] * Bt[BN][K]^T,   K = L + BN - 1 (padded to 64), BN in {256, 224, 192, 128}
 //   A[v][j]  = xh[row v][H + n0 - Lr + j]         a TMA window of the bf16 sample history, K-major as stored;
 //                                                 Lr = roundup(L-1, 8) keeps every box start 16-byte aligned (TMA rule)
 //   Bt[i][j] = h[Lr - (j - i)]  (0 <= Lr-(j-i) < L)  Toeplitz expansion of the reversed IR, built ONCE per IR (12 MB per
@@ -11,12 +11,12 @@
 //                                                 every time tile and every voice tile.
 // The band is (L / K) = 99.5 % dense, so the GEMM does no meaningful wasted work.
 //
-// Kernel anatomy (one CTA per output tile, 256 threads, 1 CTA/SM):
+// Kernel anatomy (persistent grid, one CTA per SM, tiles strided by the grid; 256 threads):
 //   warp 0   TMA producer   cp.async.bulk.tensor.2d -> 128B-swizzled smem stages, mbarrier expect_tx
 //   warp 1   MMA issuer     one elected thread: 4 x tcgen05.mma.kind::f16 (M128 N256 K16) per 64-wide k-block,
 //                           tcgen05.commit frees the stage / signals the epilogue
-//   warp 2   TMEM allocator (256 columns)
-//   warps 4-7 epilogue      tcgen05.ld 32x32b.x32 -> registers -> predicated 16-byte stores of y
+//   warp 2   TMEM allocator (512 columns = two accumulators: a segment's epilogue overlaps the next segment's MMAs)
+//   warps 4-7 epilogue      tcgen05.ld 32x32b.x32 -> registers -> 16-byte stores of y
 // 4 stages x (16 KB A + 32 KB B) = 192 KB of shared memory.
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -113,16 +113,16 @@ __global__ void reverb_build_toeplitz(const float* __restrict__ ir, __nv_bfloat1
 }
 
 // xh[c*V + v][cursor + t] = bf16(in[v][c][t]) for t < T: appends the call's block behind the history (8 samples per thread)
-__global__ void reverb_prepare(const float* __restrict__ in, __nv_bfloat16* __restrict__ xh, uint32_t V, uint32_t C, uint32_t T, uint32_t cursor,
+__global__ void reverb_prepare(const float* __restrict__ in, __nv_bfloat16* __restrict__ xh, uint32_t V, uint32_t C, uint32_t T, uint32_t in_pitch, uint32_t cursor,
                                uint32_t pitch, uint32_t zero_first, uint32_t chan_base) {
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    const uint32_t row = blockIdx.y;  // c * V + v
+    const uint32_t row = blockIdx.x;  // c * V + v (rows on grid.x: no 65535 cap)
     const uint32_t c = row / V, v = row % V;
     __nv_bfloat16* dst = xh + ((size_t)chan_base * V + row) * pitch + cursor;
-    const float* x = in + ((size_t)v * C + c) * T;
-    const bool vec = (T % 8u) == 0 && (cursor % 8u) == 0 && (pitch % 8u) == 0 && (reinterpret_cast<uintptr_t>(in) % 16u) == 0;
+    const float* x = in + ((size_t)v * C + c) * in_pitch;
+    const bool vec = (T % 8u) == 0 && (in_pitch % 4u) == 0 && (cursor % 8u) == 0 && (pitch % 8u) == 0 && (reinterpret_cast<uintptr_t>(in) % 16u) == 0;
     if (vec) {
-        for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) * 8u; i < T; i += gridDim.x * blockDim.x * 8u) {
+        for (uint32_t i = (blockIdx.y * blockDim.x + threadIdx.x) * 8u; i < T; i += gridDim.y * blockDim.x * 8u) {
             float4 a = __ldcs(reinterpret_cast<const float4*>(x + i)), b = __ldcs(reinterpret_cast<const float4*>(x + i + 4));
             if (i < zero_first) { a = make_float4(0.f, 0.f, 0.f, 0.f); b = a; }  // zero_first is a multiple of the block size here
             __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x, a.y), p1 = __floats2bfloat162_rn(a.z, a.w), p2 = __floats2bfloat162_rn(b.x, b.y), p3 = __floats2bfloat162_rn(b.z, b.w);
@@ -131,29 +131,41 @@ __global__ void reverb_prepare(const float* __restrict__ in, __nv_bfloat16* __re
             *reinterpret_cast<uint4*>(dst + i) = o;
         }
     } else {
-        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < T; i += gridDim.x * blockDim.x) dst[i] = __float2bfloat16_rn(i < zero_first ? 0.0f : x[i]);
+        for (uint32_t i = blockIdx.y * blockDim.x + threadIdx.x; i < T; i += gridDim.y * blockDim.x) dst[i] = __float2bfloat16_rn(i < zero_first ? 0.0f : x[i]);
     }
 }
 
 struct ReverbGemmArgs {
-    float* out;                   // [V][C][T]
-    uint32_t V, C, T, Lr, cursor, ir_ch, num_kb, debug, chan_base;
+    float* out;                   // row (v * C + c) at out + row * out_pitch
+    uint32_t out_pitch, V, C, T, Lr, cursor, ir_ch, num_kb, chan_base;
+    uint32_t tiles_n, tiles_m, total_tiles;  // output tiles along frames / voices (per channel); tiles_n * tiles_m * C
 };
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
+
+// Persistent grid, one CTA per SM: CTA g computes tiles g, g + G, g + 2G, ... each over the whole reduction. All CTAs walk
+// the k-blocks of their tiles IN STEP, and the Toeplitz operand B depends only on (channel, k-block): at any moment the whole
+// chip reads the same few B blocks, so B streams through L2 once instead of living there. (A stream-K split that gives every
+// SM an equal k-range was measured on config 4 and lost badly for exactly that reason — 0.39 ms against 0.28 ms — the CTAs
+// then sit at 148 different k-offsets and B + the sample history no longer fit L2.) SM coverage comes from the tile width
+// instead: BN is chosen per call among 256 / 224 / 192 / 128 frames so that the tile count fills whole waves of SMs (config 4:
+// 37 x 2 x 2 = 148 tiles of 224 frames on 148 SMs, instead of 128 tiles of 256). Two TMEM accumulators: the epilogue of a tile
+// overlaps the next tile's MMAs.
+template <uint32_t BN>
 __global__ void __launch_bounds__(256, 1) reverb_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const ReverbGemmArgs a) {
+    constexpr uint32_t B_BYTES = BN * RV_BK * 2;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));  // SWIZZLE_128B wants 1024-byte tiles
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + RV_STAGES * RV_A_BYTES;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + RV_STAGES * (RV_A_BYTES + RV_B_BYTES));
     uint64_t* empty_bar = full_bar + RV_STAGES;
-    uint64_t* tmem_full_bar = empty_bar + RV_STAGES;
-    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+    uint64_t* tmem_full_bar = empty_bar + RV_STAGES;   // [2]: accumulator complete (MMA -> epilogue)
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]: accumulator drained  (epilogue -> MMA)
+    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-    const uint32_t nt = blockIdx.x, mt = blockIdx.y, c = blockIdx.z;
-    const uint32_t n0 = nt * RV_BN, v0 = mt * RV_BM;
-    const uint32_t num_kb = a.num_kb;
+    const uint32_t g = blockIdx.x, G = gridDim.x, num_kb = a.num_kb;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_a) : "memory");
@@ -161,75 +173,93 @@ __global__ void __launch_bounds__(256, 1) reverb_gemm_kernel(const __grid_consta
     }
     if (warp == 1 && lane == 0) {
         for (uint32_t s = 0; s < RV_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        mbar_init(tmem_full_bar, 1);
+        for (uint32_t b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 2) tcgen05_alloc(tmem_base_slot, RV_BN);
+    if (warp == 2) tcgen05_alloc(tmem_base_slot, 512);  // two accumulators of up to 256 columns
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_base_slot;
+    const uint32_t tiles_per_ch = a.tiles_n * a.tiles_m;
 
     if (warp == 0) {
         // ===== TMA producer =====
         asm volatile("griddepcontrol.wait;" ::: "memory");  // the history buffer is written by reverb_prepare just before us
         if (lane == 0) {
-            const int32_t col_a0 = (int32_t)(a.cursor + n0) - (int32_t)a.Lr;  // multiple of 8 elements = 16 bytes
-            const int32_t row_a = (int32_t)((a.chan_base + c) * a.V + v0), row_b = (int32_t)(((a.chan_base + c) % a.ir_ch) * RV_BN);
-            for (uint32_t kb = 0; kb < num_kb; ++kb) {
-                const uint32_t s = kb % RV_STAGES, ph = (kb / RV_STAGES) & 1u;
-                mbar_wait(&empty_bar[s], ph ^ 1u);
-                if (a.debug & 2u) { mbar_expect_tx(&full_bar[s], 0); continue; }
-                mbar_expect_tx(&full_bar[s], RV_A_BYTES + RV_B_BYTES);
-                tma_load_2d(smem_a + s * RV_A_BYTES, &tm_a, &full_bar[s], col_a0 + (int32_t)(kb * RV_BK), row_a);
-                tma_load_2d(smem_b + s * RV_B_BYTES, &tm_b, &full_bar[s], (int32_t)(kb * RV_BK), row_b);
+            uint32_t it = 0;
+            for (uint32_t t = g; t < a.total_tiles; t += G) {
+                const uint32_t c = t / tiles_per_ch, rem = t % tiles_per_ch, mt = rem / a.tiles_n, nt = rem % a.tiles_n;
+                const int32_t col_a0 = (int32_t)(a.cursor + nt * BN) - (int32_t)a.Lr;  // multiple of 8 elements = 16 bytes
+                const int32_t row_a = (int32_t)((a.chan_base + c) * a.V + mt * RV_BM), row_b = (int32_t)(((a.chan_base + c) % a.ir_ch) * RV_BN);
+                for (uint32_t kb = 0; kb < num_kb; ++kb, ++it) {
+                    const uint32_t s = it % RV_STAGES, ph = (it / RV_STAGES) & 1u;
+                    mbar_wait(&empty_bar[s], ph ^ 1u);
+                    mbar_expect_tx(&full_bar[s], RV_A_BYTES + B_BYTES);
+                    tma_load_2d(smem_a + s * RV_A_BYTES, &tm_a, &full_bar[s], col_a0 + (int32_t)(kb * RV_BK), row_a);
+                    tma_load_2d(smem_b + s * RV_B_BYTES, &tm_b, &full_bar[s], (int32_t)(kb * RV_BK), row_b);
+                }
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer (one elected lane) =====
-        constexpr uint32_t idesc = umma_idesc_bf16(RV_BM, RV_BN);
-        for (uint32_t kb = 0; kb < num_kb; ++kb) {
-            const uint32_t s = kb % RV_STAGES, ph = (kb / RV_STAGES) & 1u;
-            mbar_wait(&full_bar[s], ph);
+        constexpr uint32_t idesc = umma_idesc_bf16(RV_BM, BN);
+        uint32_t it = 0, seg = 0;
+        for (uint32_t t = g; t < a.total_tiles; t += G, ++seg) {
+            const uint32_t buf = seg & 1u;
+            mbar_wait(&tmem_empty_bar[buf], ((seg >> 1) & 1u) ^ 1u);  // the epilogue has drained this accumulator (free on first use)
             tcgen05_fence_after();
-            if (elect_one()) {
-                const uint64_t adesc = umma_desc_sw128(smem_u32(smem_a + s * RV_A_BYTES));
-                const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_b + s * RV_B_BYTES));
+            const uint32_t tmem_d = tmem_base + buf * RV_BN;
+            for (uint32_t kb = 0; kb < num_kb; ++kb, ++it) {
+                const uint32_t s = it % RV_STAGES, ph = (it / RV_STAGES) & 1u;
+                mbar_wait(&full_bar[s], ph);
+                tcgen05_fence_after();
+                if (elect_one()) {
+                    const uint64_t adesc = umma_desc_sw128(smem_u32(smem_a + s * RV_A_BYTES));
+                    const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_b + s * RV_B_BYTES));
 #pragma unroll
-                for (uint32_t k = 0; k < RV_BK / 16; ++k)  // +32 bytes per K=16 step inside the 128-byte swizzle atom
-                    if (!(a.debug & 1u)) tcgen05_mma_f16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
-                tcgen05_commit(&empty_bar[s]);                       // smem stage free once these MMAs retire
-                if (kb + 1 == num_kb) tcgen05_commit(tmem_full_bar);  // accumulator complete
+                    for (uint32_t k = 0; k < RV_BK / 16; ++k)  // +32 bytes per K=16 step inside the 128-byte swizzle atom
+                        tcgen05_mma_f16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+                    tcgen05_commit(&empty_bar[s]);                                // smem stage free once these MMAs retire
+                    if (kb + 1 == num_kb) tcgen05_commit(&tmem_full_bar[buf]);    // accumulator complete
+                }
+                __syncwarp();
             }
-            __syncwarp();
         }
     } else if (warp >= 4) {
         // ===== epilogue: TMEM -> registers -> global =====
         const uint32_t q = warp & 3u;  // a warp may only touch TMEM lanes [32q, 32q+32)
-        mbar_wait(tmem_full_bar, 0);
-        tcgen05_fence_after();
-        const uint32_t v = v0 + q * 32u + lane;
-        float* dst_row = a.out + ((size_t)v * a.C + c) * a.T + n0;
+        uint32_t seg = 0;
+        for (uint32_t t = g; t < a.total_tiles; t += G, ++seg) {
+            const uint32_t buf = seg & 1u;
+            const uint32_t c = t / tiles_per_ch, rem = t % tiles_per_ch, mt = rem / a.tiles_n, nt = rem % a.tiles_n;
+            const uint32_t n0 = nt * BN, v = mt * RV_BM + q * 32u + lane;
+            mbar_wait(&tmem_full_bar[buf], (seg >> 1) & 1u);
+            tcgen05_fence_after();
+            float* dst_row = a.out + ((size_t)v * a.C + c) * a.out_pitch + n0;
 #pragma unroll 1
-        for (uint32_t col = 0; col < RV_BN; col += 32) {
-            uint32_t r[32];
-            if (a.debug & 4u) { for (int i = 0; i < 32; ++i) r[i] = 0; } else
-            tcgen05_ld_32x32b_x32(tmem_base + ((q * 32u) << 16) + col, r);
-            if (v < a.V) {
-                if (n0 + col + 32 <= a.T && (a.T & 3u) == 0) {
+            for (uint32_t col = 0; col < BN; col += 32) {
+                uint32_t r[32];
+                tcgen05_ld_32x32b_x32(tmem_base + ((q * 32u) << 16) + buf * RV_BN + col, r);
+                if (v < a.V) {
+                    if (n0 + col + 32 <= a.T && ((a.T | a.out_pitch) & 3u) == 0) {
 #pragma unroll
-                    for (int i = 0; i < 32; i += 4)
-                        __stcs(reinterpret_cast<float4*>(dst_row + col + i), make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]), __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3])));
-                } else {
+                        for (int i = 0; i < 32; i += 4)
+                            __stcs(reinterpret_cast<float4*>(dst_row + col + i), make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]), __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3])));
+                    } else {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) if (n0 + col + i < a.T) dst_row[col + i] = __uint_as_float(r[i]);
+                        for (int i = 0; i < 32; ++i) if (n0 + col + i < a.T) dst_row[col + i] = __uint_as_float(r[i]);
+                    }
                 }
             }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
         }
     }
     tcgen05_fence_before();
     __syncthreads();
-    if (warp == 2) tcgen05_dealloc(tmem_base, RV_BN);
+    if (warp == 2) tcgen05_dealloc(tmem_base, 512);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -268,32 +298,67 @@ cudaError_t launch_reverb_build(const float* d_ir, void* d_bt, uint32_t L, uint3
 
 // One call: append the block (bf16) behind the history at `cursor`, run the GEMM over windows ending in it.
 // The caller owns the cursor policy (compaction when the buffer is full); cursor is a multiple of 8 and >= Lr.
-cudaError_t launch_reverb(const ReverbCall& rc, cudaStream_t st, std::string* err) {
-    const uint32_t kpad = reverb_kpad(rc.L);
+uint32_t reverb_grid_max() {
+    static int sms = 0;
+    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+    return (uint32_t)sms;
+}
+
+template <uint32_t BN>
+static cudaError_t launch_gemm(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const ReverbGemmArgs& ga, uint32_t grid, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(reverb_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RV_SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(reverb_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RV_SMEM_BYTES);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
+    reverb_gemm_kernel<BN><<<dim3(grid), 256, RV_SMEM_BYTES, st>>>(tm_a, tm_b, ga);
+    return cudaGetLastError();
+}
+
+// Tile width for a call: the candidate that needs the least (waves of SMs) x (tile width + a per-tile constant).
+static uint32_t reverb_pick_bn(uint32_t T, uint32_t tiles_mc, uint32_t sms) {
+    static const uint32_t cand[4] = {256, 224, 192, 128};
+    uint32_t best = 256; uint64_t best_cost = ~0ull;
+    for (uint32_t bn : cand) {
+        const uint64_t tiles = (uint64_t)((T + bn - 1) / bn) * tiles_mc, waves = (tiles + sms - 1) / sms;
+        const uint64_t cost = waves * (bn + 12u);
+        if (cost < best_cost) { best_cost = cost; best = bn; }
+    }
+    return best;
+}
+
+cudaError_t launch_reverb(const ReverbCall& rc, cudaStream_t st, std::string* err) {
+    const uint32_t in_pitch = rc.in_pitch ? rc.in_pitch : rc.T, out_pitch = rc.out_pitch ? rc.out_pitch : rc.T;
     {
         const uint32_t per_block = 256 * 8;
-        dim3 grid((rc.T + per_block - 1) / per_block < 32 ? (rc.T + per_block - 1) / per_block : 32, rc.C * rc.V);
-        reverb_prepare<<<grid, 256, 0, st>>>(rc.in, static_cast<__nv_bfloat16*>(rc.xh), rc.V, rc.C, rc.T, rc.cursor, rc.pitch, rc.zero_first, rc.chan_base);
+        dim3 grid(rc.C * rc.V, (rc.T + per_block - 1) / per_block < 32 ? (rc.T + per_block - 1) / per_block : 32);
+        reverb_prepare<<<grid, 256, 0, st>>>(rc.in, static_cast<__nv_bfloat16*>(rc.xh), rc.V, rc.C, rc.T, in_pitch, rc.cursor, rc.pitch, rc.zero_first, rc.chan_base);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }
+    const uint32_t sms = reverb_grid_max(), tiles_m = (rc.V + RV_BM - 1) / RV_BM;
+    const uint32_t bn = reverb_pick_bn(rc.T, tiles_m * rc.C, sms);
+    const uint32_t kpad = reverb_kpad(rc.L);  // pitch of the Toeplitz rows (built for the widest tile)
     CUtensorMap tm_a, tm_b;
     if (!make_map_bf16_2d(&tm_a, rc.xh, (uint64_t)rc.cursor + rc.T, (uint64_t)(rc.chan_base + rc.C) * rc.V, rc.pitch, RV_BK, RV_BM) ||
-        !make_map_bf16_2d(&tm_b, rc.bt, kpad, (uint64_t)rc.ir_ch * RV_BN, kpad, RV_BK, RV_BN)) {
+        !make_map_bf16_2d(&tm_b, rc.bt, kpad, (uint64_t)rc.ir_ch * RV_BN, kpad, RV_BK, bn)) {
         if (err) *err = "cuTensorMapEncodeTiled failed";
         return cudaErrorInvalidValue;
     }
-    static const uint32_t dbg = getenv("FW_REVERB_DEBUG") ? (uint32_t)atoi(getenv("FW_REVERB_DEBUG")) : 0u;
-    ReverbGemmArgs ga{rc.out, rc.V, rc.C, rc.T, reverb_lr(rc.L), rc.cursor, rc.ir_ch, kpad / RV_BK, dbg, rc.chan_base};
-    dim3 grid((rc.T + RV_BN - 1) / RV_BN, (rc.V + RV_BM - 1) / RV_BM, rc.C);
-    reverb_gemm_kernel<<<grid, 256, RV_SMEM_BYTES, st>>>(tm_a, tm_b, ga);
-    return cudaGetLastError();
+    ReverbGemmArgs ga{};
+    ga.out = rc.out; ga.out_pitch = out_pitch; ga.V = rc.V; ga.C = rc.C; ga.T = rc.T; ga.Lr = reverb_lr(rc.L); ga.cursor = rc.cursor; ga.ir_ch = rc.ir_ch;
+    ga.num_kb = (reverb_lr(rc.L) + bn + RV_BK - 1) / RV_BK;  // Bt[i][j] is zero for j > Lr + i: a narrower tile has a shorter reduction
+    ga.chan_base = rc.chan_base;
+    ga.tiles_n = (rc.T + bn - 1) / bn; ga.tiles_m = tiles_m; ga.total_tiles = ga.tiles_n * ga.tiles_m * rc.C;
+    if (ga.total_tiles == 0) return cudaSuccess;
+    const uint32_t G = ga.total_tiles < sms ? ga.total_tiles : sms;
+    switch (bn) {
+        case 224: return launch_gemm<224>(tm_a, tm_b, ga, G, st);
+        case 192: return launch_gemm<192>(tm_a, tm_b, ga, G, st);
+        case 128: return launch_gemm<128>(tm_a, tm_b, ga, G, st);
+        default: return launch_gemm<256>(tm_a, tm_b, ga, G, st);
+    }
 }
 
 }  // namespace fw

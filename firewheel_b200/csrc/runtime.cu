@@ -1631,7 +1631,7 @@ void fw_dev_free(int device, void* p) { cudaSetDevice(device); cudaFree(p); }
 void* fw_host_alloc_pinned(uint64_t bytes) { void* p = nullptr; if (!FW_CUDA(cudaMallocHost(&p, bytes))) return nullptr; return p; }
 void fw_host_free_pinned(void* p) { cudaFreeHost(p); }
 int fw_processor_h2d(fw_processor* p, void* dst, const void* src, uint64_t bytes) { cudaSetDevice(p->device); return FW_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, p->stream)) ? 0 : -1; }
-int fw_processor_d2h(fw_processor* p, void* dst, const void* src, uint64_t bytes) { cudaSetDevice(p->device); return FW_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, p->stream)) ? 0 : -1; }
+int fw_processor_d2h(fw_processor* p, void* dst, const void* src, uint64_t bytes) { cudaSetDevice(p->device); join_side(p); return FW_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, p->stream)) ? 0 : -1; }
 int fw_processor_sync(fw_processor* p) {
     cudaSetDevice(p->device);
     join_side(p);
@@ -1777,6 +1777,21 @@ int fw_processor_comm_init(fw_processor* p, int rank, int world, const uint8_t* 
     p->rank = rank; p->world = world;
     if (!p2p_setup(p)) return -1;
     return 0;
+}
+// Host-buffer all-gather over the processor's communicator: what a torch-free driver needs for barriers, max-over-ranks
+// timing and result cross-checks (bench.py, tests/multigpu_worker.py). Not on the audio path.
+int fw_processor_comm_allgather(fw_processor* p, const void* send, void* recv, uint64_t bytes) {
+    if (!p || !send || !recv || bytes == 0) return -1;
+    if (p->world == 1) { std::memcpy(recv, send, bytes); return 0; }
+    if (!p->nccl_comm) { g_dev_err = "comm_allgather: no communicator (call processor_comm_init first)"; return -1; }
+    cudaSetDevice(p->device);
+    uint8_t* d = nullptr;
+    if (!FW_CUDA(cudaMalloc(&d, bytes * (size_t)p->world))) return -1;
+    bool ok = FW_CUDA(cudaMemcpyAsync(d + bytes * (size_t)p->rank, send, bytes, cudaMemcpyHostToDevice, p->side)) &&
+              g_nccl.ok(g_nccl.AllGather(d + bytes * (size_t)p->rank, d, bytes, /*ncclInt8*/ 0, p->nccl_comm, p->side), "ncclAllGather(host)") &&
+              FW_CUDA(cudaMemcpyAsync(recv, d, bytes * (size_t)p->world, cudaMemcpyDeviceToHost, p->side)) && FW_CUDA(cudaStreamSynchronize(p->side));
+    cudaFree(d);
+    return ok ? 0 : -1;
 }
 
 }  // extern "C"

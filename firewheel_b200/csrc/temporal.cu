@@ -47,34 +47,33 @@ constexpr int kStateStages = 8;  // state layout [row][8][2] regardless of the c
 //     cooperative copies carry no per-lane predicates or branches.
 //   * SVF = true: the per-stage update is the trapezoidal SVF's (include/fw_b200.h) instead of the TDF-II biquad's; the lane /
 //     tile / pipeline machinery is identical. Coefficient rows are then 6 floats {a1, a2, a3, m0, m1, m2}, state {ic1, ic2}.
-//   * WS = 1 (opt-in, FW_TEMPORAL_WS=1; compiled but NOT yet validated or measured on hardware — the round's GPU budget ran
-//     out): warp-specialised CTAs of two warps. One warp runs only the recurrence (the 11-instruction-per-sample chunk body),
-//     the other moves the tiles (cp.async loads, coalesced flushes, the delay's out copy) — the ~110 instructions of per-chunk
-//     bookkeeping that today share the compute warp's single instruction stream. Hand-over through named barriers
-//     READY[parity] (mover arrives, compute syncs) and DONE[parity] (compute arrives, mover syncs); y tiles get four slots
-//     so that a flush never meets the chunk being computed. Roles alternate with the CTA index to spread compute warps
-//     over the SM's schedulers.
-__device__ __forceinline__ void named_bar_sync(uint32_t id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
-__device__ __forceinline__ void named_bar_arrive(uint32_t id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
-template <int NS, int L, bool DELAY, int RPL, bool FULL, bool SVF = false, int WS = 0>
-__global__ void __launch_bounds__(WS ? 64 : 32) biquad_delay_lanes(TemporalArgs a) {
-    static_assert(!WS || (RPL == 1 && FULL), "the warp-specialised variant covers full CTAs with one row per lane");
-    constexpr uint32_t YM = WS ? 3u : 1u;            // y tile slots - 1
-    constexpr uint32_t kReady = 1, kDone = 3;         // named barriers kReady + parity, kDone + parity
-    // RPL rows per lane: each lane runs stage s of RPL independent rows, so a lone warp per scheduler has RPL
-    // interleaved recurrences to fill the FP32 pipe latency (measured: 1 row/lane 0.50 ms).
+//   * PK = true (RPL == 2): the two rows of a lane run as ONE packed-f32x2 recurrence (Blackwell FFMA2): half the FP
+//     instructions per row and two independent chains per dependent-issue slot. ptxas contracts mul.rn.f32x2 + add.rn.f32x2
+//     into one FFMA2 even under --fmad=false (single rounding: NOT the oracle's arithmetic), so every packed operation is
+//     spelled as an exact fma against OPAQUE constants handed in through the kernel parameters: a*b = fma(a, b, -0.0),
+//     a + c = fma(a, 1.0, c), a - b = fma(b, -1.0, a). Each is bit-identical to the separately rounded scalar operation
+//     (signed zeros included), and ptxas cannot simplify what it cannot see. Result: bit-exact like the scalar lanes.
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t pk2(float lo, float hi) { f32x2_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ float lo2(f32x2_t v) { return __uint_as_float((uint32_t)(v & 0xffffffffull)); }
+__device__ __forceinline__ float hi2(f32x2_t v) { return __uint_as_float((uint32_t)(v >> 32)); }
+__device__ __forceinline__ f32x2_t fma2(f32x2_t a, f32x2_t b, f32x2_t c) { f32x2_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+template <int NS, int L, bool DELAY, int RPL, bool FULL, bool SVF = false, bool PK = false>
+__global__ void __launch_bounds__(32) biquad_delay_lanes(TemporalArgs a) {
+    static_assert(!PK || (RPL == 2 && NS > 0), "the packed variant pairs the two rows of a lane");
+    constexpr uint32_t YM = 1u;                       // y tile slots - 1
+    // RPL rows per lane: each lane runs stage s of RPL independent rows.
     constexpr int RSET = 32 / L, ROWS = RPL * RSET, PER = RPL * 8 / L, LAG = NS > 0 ? 2 * (NS - 1) : 0;
     static_assert(NS <= L && (L == 1 || L == 2 || L == 4 || L == 8), "lanes per row");
     // No early launch_dependents here: this kernel is issue-bound, and dependents parked at griddepcontrol.wait
     // cost it issue slots (measured: 0.92 vs 0.64 ms per step). The implicit trigger at exit is enough.
     t_pdl_wait();  // `in` is produced by the previous kernel of this call
     const uint32_t lane = threadIdx.x & 31u, s = lane % L;
-    const bool ws_mover = WS && (((threadIdx.x >> 5) ^ (blockIdx.x & 1u)) != 0u);  // the other warp computes
     const uint32_t row0 = a.row_base + blockIdx.x * ROWS, R = a.R, T = a.T, D = a.D;
     const bool is_first = s == 0, is_last = NS == 0 ? s == 0 : s == (uint32_t)(NS > 0 ? NS - 1 : 0);
     __shared__ float4 xt[4][ROWS][8];
     __shared__ float4 rt[DELAY ? 3 : 1][ROWS][8];
-    __shared__ float4 yt[WS ? 4 : 2][ROWS][8];
+    __shared__ float4 yt[2][ROWS][8];
 
     uint32_t row_l[RPL], rsw[RPL]; bool lane_ok[RPL], last_ok[RPL];
     float b0[RPL], b1[RPL], b2[RPL], a1[RPL], a2[RPL], c5[RPL], s1[RPL], s2[RPL], q0[RPL], q1[RPL], yb[RPL][4];
@@ -94,6 +93,16 @@ __global__ void __launch_bounds__(WS ? 64 : 32) biquad_delay_lanes(TemporalArgs 
             s1[j] = a.state[(sr * kStateStages + s) * 2]; s2[j] = a.state[(sr * kStateStages + s) * 2 + 1];
         }
     }
+    // packed copies of the coefficients / state of the lane's two rows (PK), and the opaque constants of the exact-fma spelling
+    f32x2_t B0 = 0, B1 = 0, B2 = 0, A1 = 0, A2 = 0, C5 = 0, S1 = 0, S2 = 0, K1 = 0, KN0 = 0, KN1 = 0, K2 = 0;
+    if constexpr (PK) {
+        B0 = pk2(b0[0], b0[RPL - 1]); B1 = pk2(b1[0], b1[RPL - 1]); B2 = pk2(b2[0], b2[RPL - 1]); A1 = pk2(a1[0], a1[RPL - 1]); A2 = pk2(a2[0], a2[RPL - 1]);
+        C5 = pk2(c5[0], c5[RPL - 1]); S1 = pk2(s1[0], s1[RPL - 1]); S2 = pk2(s2[0], s2[RPL - 1]);
+        K1 = pk2(a.k_one, a.k_one); KN0 = pk2(a.k_negzero, a.k_negzero); KN1 = pk2(a.k_negone, a.k_negone); K2 = pk2(a.k_two, a.k_two);
+    }
+    auto mul2 = [&](f32x2_t x, f32x2_t y) { return fma2(x, y, KN0); };   // RN(x*y): adding -0.0 changes nothing, signed zeros included
+    auto add2 = [&](f32x2_t x, f32x2_t y) { return fma2(x, K1, y); };    // RN(x+y): x*1.0 is exact
+    auto sub2 = [&](f32x2_t x, f32x2_t y) { return fma2(y, KN1, x); };   // RN(x-y): y*-1.0 is exact
 
     // cooperative copies: lane handles PER (row, granule) pairs of every tile
     const float* in_p[PER]; float* out_p[PER]; float* ring_p[PER]; uint32_t sw[PER]; bool ok[PER];
@@ -102,8 +111,8 @@ __global__ void __launch_bounds__(WS ? 64 : 32) biquad_delay_lanes(TemporalArgs 
         const uint32_t idx = lane + 32u * i, rr = idx >> 3, g = idx & 7u;
         ok[i] = FULL || row0 + rr < R;
         const size_t row = ok[i] ? row0 + rr : 0;
-        in_p[i] = a.in + row * T + g * 4u;
-        out_p[i] = a.out + row * T + g * 4u;
+        in_p[i] = a.in + row * a.in_pitch + g * 4u;
+        out_p[i] = a.out + row * a.out_pitch + g * 4u;
         ring_p[i] = DELAY ? a.ring + (row * a.srow_mul + a.srow_add) * D + g * 4u : nullptr;
         sw[i] = rr * 8u + (g ^ (rr & 7u));  // float4 index inside a tile
     }
@@ -147,11 +156,43 @@ __global__ void __launch_bounds__(WS ? 64 : 32) biquad_delay_lanes(TemporalArgs 
     for (int j = 0; j < RPL; ++j)
 #pragma unroll
         for (int c = 0; c < 8; ++c) goff[j][c] = (uint32_t)c ^ rsw[j];
-    const float4* xbase[RPL]; float4* ybase[RPL][2];  // refreshed per chunk: x tile row, y tile rows of this / the previous chunk
+    const float4* xbase[RPL] = {}; float4* ybase[RPL][2] = {};  // refreshed per chunk: x tile row, y tile rows of this / the previous chunk
     auto body = [&](auto check, uint32_t gi, const float (&x)[RPL], int u4, int n4) {
         constexpr bool CHECK = decltype(check)::value;
         const bool in_range = CHECK ? (gi - 2u * s) < T : true;  // unsigned compare: also false during warm-up (gi < 2s)
         const int slot = (u4 - LAG) & 3;  // the last stage emits sample m = gi - LAG; (gi - LAG) & 3 == (u4 - LAG) & 3
+        if constexpr (PK) {
+            // both rows of the lane in one packed recurrence (same op order per element as the scalar branch below)
+            const f32x2_t X = pk2(is_first ? x[0] : q0[0], is_first ? x[1] : q0[1]);
+            f32x2_t Y, N1, N2;
+            if (SVF) {  // (B0, B1, B2, A1, A2, C5) hold (a1, a2, a3, m0, m1, m2); (S1, S2) hold (ic1, ic2)
+                const f32x2_t v3 = sub2(X, S2);
+                const f32x2_t v1 = add2(mul2(B0, S1), mul2(B1, v3));
+                const f32x2_t v2 = add2(S2, add2(mul2(B1, S1), mul2(B2, v3)));
+                N1 = sub2(mul2(K2, v1), S1);
+                N2 = sub2(mul2(K2, v2), S2);
+                Y = add2(mul2(A1, X), add2(mul2(A2, v1), mul2(C5, v2)));
+            } else {
+                Y = add2(mul2(B0, X), S1);
+                N1 = add2(sub2(mul2(B1, X), mul2(A1, Y)), S2);
+                N2 = sub2(mul2(B2, X), mul2(A2, Y));
+            }
+            if (!CHECK) { S1 = N1; S2 = N2; }
+            else {
+                const bool act0 = lane_ok[0] && in_range, act1 = lane_ok[1] && in_range;
+                S1 = pk2(act0 ? lo2(N1) : lo2(S1), act1 ? hi2(N1) : hi2(S1));
+                S2 = pk2(act0 ? lo2(N2) : lo2(S2), act1 ? hi2(N2) : hi2(S2));
+            }
+            const float y0 = lo2(Y), y1 = hi2(Y);
+            q0[0] = q1[0]; q0[1] = q1[1];
+            q1[0] = __shfl_up_sync(0xffffffffu, y0, 1); q1[1] = __shfl_up_sync(0xffffffffu, y1, 1);
+            yb[0][slot] = y0; yb[1][slot] = y1;
+            if (slot == 3) {
+                const int ml = n4 * 4 + u4 - LAG;
+                if (CHECK ? (is_last && lane_ok[0] && in_range) : last_ok[0]) ybase[0][ml >= 0 ? 0 : 1][goff[0][(ml >> 2) & 7]] = make_float4(yb[0][0], yb[0][1], yb[0][2], yb[0][3]);
+                if (CHECK ? (is_last && lane_ok[1] && in_range) : last_ok[1]) ybase[1][ml >= 0 ? 0 : 1][goff[1][(ml >> 2) & 7]] = make_float4(yb[1][0], yb[1][1], yb[1][2], yb[1][3]);
+            }
+        } else {
 #pragma unroll
         for (int j = 0; j < RPL; ++j) {
             const bool active = CHECK ? (lane_ok[j] && in_range) : true;
@@ -183,6 +224,7 @@ __global__ void __launch_bounds__(WS ? 64 : 32) biquad_delay_lanes(TemporalArgs 
                 const int ml = n4 * 4 + u4 - LAG;
                 ybase[j][ml >= 0 ? 0 : 1][goff[j][(ml >> 2) & 7]] = make_float4(yb[j][0], yb[j][1], yb[j][2], yb[j][3]);
             }
+        }
         }
     };
     auto chunk = [&](auto check, uint32_t ch, bool zero_in) {
@@ -221,80 +263,36 @@ __global__ void __launch_bounds__(WS ? 64 : 32) biquad_delay_lanes(TemporalArgs 
         }
     };
 
-    if (WS && ws_mover) {
-        // ---- mover warp: groups G(-3) = {x0}, G(-2) = {x1, ring0}, G(-1) = {x2, ring1}, G(ch) = {x(ch+3), ring(ch+2)} ----
-        issue(0, nch); issue(1, 0); issue(2, 1);
-        for (uint32_t ch = 0; ch < nch; ++ch) {
-            cp_async_wait<1>();                       // everything but G(ch-1) has landed: x tile ch and old-ring tile ch
-            __syncwarp();
-            named_bar_arrive(kReady + (ch & 1u));     // tiles of chunk ch are ready; never more than one chunk ahead per parity
-            if (ch >= 1u) named_bar_sync(kDone + ((ch - 1u) & 1u));  // compute finished chunk ch-1: y tile ch-2 is complete, x slot (ch+3)&3 is free
-            if (ch >= 2u) flush_y(ch - 2u);
-            __syncwarp();
-            issue(ch + 3u, ch + 2u);
-            if (DELAY) {
+    // groups: G(-3) = {x0}, G(-2) = {x1, ring0}, G(-1) = {x2, ring1}, G(ch) = {x(ch+3), ring(ch+2)}
+    issue(0, nch); issue(1, 0); issue(2, 1);
+    for (uint32_t ch = 0; ch < nch; ++ch) {
+        __syncwarp();  // every lane is done with x tile ch-1, ring tile ch-1 and the y tile about to be flushed
+        if (ch >= 2u) flush_y(ch - 2u);
+        __syncwarp();  // order the flush's ring stores before the ring loads issued next (they may alias when D is small)
+        issue(ch + 3u, ch + 2u);
+        cp_async_wait<2>();  // groups up to G(ch-2) have landed: x tile ch and old-ring tile ch
+        __syncwarp();
+        if (DELAY) {
 #pragma unroll
-                for (int i = 0; i < PER; ++i) __stcs(reinterpret_cast<float4*>(out_p[i] + ch * 32u), (&rt[ring_use_slot][0][0])[sw[i]]);
-                ring_use_slot = ring_use_slot == 2u ? 0u : ring_use_slot + 1u;
-            }
+            for (int i = 0; i < PER; ++i) if (FULL || ok[i]) __stcs(reinterpret_cast<float4*>(out_p[i] + ch * 32u), (&rt[ring_use_slot][0][0])[sw[i]]);
+            ring_use_slot = ring_use_slot == 2u ? 0u : ring_use_slot + 1u;
         }
-        if (nch > 0) {
-            named_bar_sync(kDone + ((nch - 1u) & 1u));  // last chunk done
-            if (nch >= 2u) flush_y(nch - 2u);
-            named_bar_sync(kDone + (nch & 1u));          // drain done: tile nch-1 holds its lagged samples
-            flush_y(nch - 1u);
-        }
-        cp_async_wait<0>();
-        return;
+        const bool zero_in = ch * 32u < a.zero_first;  // Q11 (chunk-uniform)
+        if (ch == 0 || zero_in) chunk(std::true_type{}, ch, zero_in);  // warm-up: stage s starts at iteration 2s
+        else chunk(std::false_type{}, ch, false);
     }
-    if (WS) {
-        // ---- compute warp ----
-        for (uint32_t ch = 0; ch < nch; ++ch) {
-            named_bar_sync(kReady + (ch & 1u));
-            const bool zero_in = ch * 32u < a.zero_first;  // Q11 (chunk-uniform)
-            if (ch == 0 || zero_in) chunk(std::true_type{}, ch, zero_in);
-            else chunk(std::false_type{}, ch, false);
-            named_bar_arrive(kDone + (ch & 1u));
-        }
-        if (nch > 0) {
-            const float zx[RPL] = {};
+    if (nch > 0) {
+        const float zx[RPL] = {};
 #pragma unroll
-            for (int j = 0; j < RPL; ++j) { ybase[j][0] = &yt[nch & YM][row_l[j]][0]; ybase[j][1] = &yt[(nch + YM) & YM][row_l[j]][0]; }
+        for (int j = 0; j < RPL; ++j) { ybase[j][0] = &yt[nch & YM][row_l[j]][0]; ybase[j][1] = &yt[(nch + YM) & YM][row_l[j]][0]; }
 #pragma unroll
-            for (int it = 0; it < ((LAG + 3) & ~3); ++it) body(std::true_type{}, T + it, zx, it & 3, it >> 2);  // drain (T % 4 == 0)
-            named_bar_arrive(kDone + (nch & 1u));
-        }
-    } else {
-        // groups: G(-3) = {x0}, G(-2) = {x1, ring0}, G(-1) = {x2, ring1}, G(ch) = {x(ch+3), ring(ch+2)}
-        issue(0, nch); issue(1, 0); issue(2, 1);
-        for (uint32_t ch = 0; ch < nch; ++ch) {
-            __syncwarp();  // every lane is done with x tile ch-1, ring tile ch-1 and the y tile about to be flushed
-            if (ch >= 2u) flush_y(ch - 2u);
-            __syncwarp();  // order the flush's ring stores before the ring loads issued next (they may alias when D is small)
-            issue(ch + 3u, ch + 2u);
-            cp_async_wait<2>();  // groups up to G(ch-2) have landed: x tile ch and old-ring tile ch
-            __syncwarp();
-            if (DELAY) {
-    #pragma unroll
-                for (int i = 0; i < PER; ++i) if (FULL || ok[i]) __stcs(reinterpret_cast<float4*>(out_p[i] + ch * 32u), (&rt[ring_use_slot][0][0])[sw[i]]);
-                ring_use_slot = ring_use_slot == 2u ? 0u : ring_use_slot + 1u;
-            }
-            const bool zero_in = ch * 32u < a.zero_first;  // Q11 (chunk-uniform)
-            if (ch == 0 || zero_in) chunk(std::true_type{}, ch, zero_in);  // warm-up: stage s starts at iteration 2s
-            else chunk(std::false_type{}, ch, false);
-        }
-        if (nch > 0) {
-            const float zx[RPL] = {};
-    #pragma unroll
-            for (int j = 0; j < RPL; ++j) { ybase[j][0] = &yt[nch & YM][row_l[j]][0]; ybase[j][1] = &yt[(nch + YM) & YM][row_l[j]][0]; }
-    #pragma unroll
-            for (int it = 0; it < ((LAG + 3) & ~3); ++it) body(std::true_type{}, T + it, zx, it & 3, it >> 2);  // drain (T % 4 == 0)
-            __syncwarp();
-            if (nch >= 2u) flush_y(nch - 2u);
-            flush_y(nch - 1u);
-        }
+        for (int it = 0; it < ((LAG + 3) & ~3); ++it) body(std::true_type{}, T + it, zx, it & 3, it >> 2);  // drain (T % 4 == 0)
+        __syncwarp();
+        if (nch >= 2u) flush_y(nch - 2u);
+        flush_y(nch - 1u);
     }
-    if (!WS) cp_async_wait<0>();
+    cp_async_wait<0>();
+    if constexpr (PK) { s1[0] = lo2(S1); s1[1] = hi2(S1); s2[0] = lo2(S2); s2[1] = hi2(S2); }
 #pragma unroll
     for (int j = 0; j < RPL; ++j) {
         if (NS > 0 && lane_ok[j]) {
@@ -317,8 +315,8 @@ __global__ void __launch_bounds__(64) biquad_delay_generic(TemporalArgs a) {
         b0[s] = k[0]; b1[s] = k[1]; b2[s] = k[2]; a1[s] = k[3]; a2[s] = k[4];
         s1[s] = a.state[(((size_t)r * a.srow_mul + a.srow_add) * kStateStages + s) * 2]; s2[s] = a.state[(((size_t)r * a.srow_mul + a.srow_add) * kStateStages + s) * 2 + 1];
     }
-    const float* in = a.in + (size_t)r * T;
-    float* out = a.out + (size_t)r * T;
+    const float* in = a.in + (size_t)r * a.in_pitch;
+    float* out = a.out + (size_t)r * a.out_pitch;
     float* ring = D ? a.ring + ((size_t)r * a.srow_mul + a.srow_add) * D : nullptr;
     uint32_t p = D ? a.pos % D : 0;
     for (uint32_t n = 0; n < T; ++n) {
@@ -348,8 +346,8 @@ __global__ void __launch_bounds__(64) svf_generic(TemporalArgs a) {
         a1[s] = k[0]; a2[s] = k[1]; a3[s] = k[2]; m0[s] = k[3]; m1[s] = k[4]; m2[s] = k[5];
         ic1[s] = a.state[(sr * kStateStages + s) * 2]; ic2[s] = a.state[(sr * kStateStages + s) * 2 + 1];
     }
-    const float* in = a.in + (size_t)r * T;
-    float* out = a.out + (size_t)r * T;
+    const float* in = a.in + (size_t)r * a.in_pitch;
+    float* out = a.out + (size_t)r * a.out_pitch;
     for (uint32_t n = 0; n < T; ++n) {
         float x = n < a.zero_first ? 0.0f : in[n];
         for (uint32_t s = 0; s < NS; ++s) {
@@ -375,72 +373,83 @@ static cudaError_t launch_pdl_t(void (*kernel)(KArgs...), dim3 grid, dim3 block,
     return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
-template <int NS, int L, bool DELAY, int RPL, bool SVF = false>
-static cudaError_t launch_lanes_split(const TemporalArgs& a, cudaStream_t st) {
-    constexpr uint32_t rows_per_warp = RPL * 32 / L;
-    const uint32_t n_full = a.R / rows_per_warp;
-    static const int ws_knob = getenv("FW_TEMPORAL_WS") ? atoi(getenv("FW_TEMPORAL_WS")) : 0;  // opt-in, see the kernel's comment
-    if (n_full) {
-        cudaError_t e;
-        if constexpr (RPL == 1 && L >= 2) {
-            e = ws_knob ? launch_pdl_t(biquad_delay_lanes<NS, L, DELAY, 1, true, SVF, 1>, dim3(n_full), dim3(64), st, a)
-                        : launch_pdl_t(biquad_delay_lanes<NS, L, DELAY, RPL, true, SVF>, dim3(n_full), dim3(32), st, a);
-        } else {
-            e = launch_pdl_t(biquad_delay_lanes<NS, L, DELAY, RPL, true, SVF>, dim3(n_full), dim3(32), st, a);
+// Full CTAs of `rows_per_warp` rows + predicated one-row-per-lane CTAs for the ragged tail.
+// Packed variant (two rows per lane, FFMA2: 10.9 instead of 16.9 instructions per row and sample): chosen when even at two
+// rows per lane every scheduler of the chip (148 SMs x 4) still has two warps to interleave. With fewer rows the kernel is
+// bound by the dependent-issue latency of the recurrence, not by issue slots, and one row per lane keeps twice the warps in
+// flight (config 3, 8192 rows: packed 0.490 ms, one row per lane 0.456 ms).
+template <int NS, int L, bool DELAY, bool SVF = false>
+static cudaError_t launch_lanes(const TemporalArgs& a, cudaStream_t st) {
+    constexpr uint32_t rows1 = 32 / L;
+    bool packed = false;
+    if constexpr (L > 1 && NS > 0) packed = a.R / (2 * rows1) >= 2 * 4 * 148;  // >= 2 warps per scheduler even at two rows per lane
+    uint32_t done = 0;
+    if constexpr (L > 1 && NS > 0) {
+        if (packed) {
+            const uint32_t n_full = a.R / (2 * rows1);
+            cudaError_t e = launch_pdl_t(biquad_delay_lanes<NS, L, DELAY, 2, true, SVF, true>, dim3(n_full), dim3(32), st, a);
+            if (e != cudaSuccess) return e;
+            done = n_full * 2 * rows1;
         }
-        if (e != cudaSuccess) return e;
     }
-    if (a.R % rows_per_warp) {  // ragged tail: one predicated CTA
-        TemporalArgs t = a; t.row_base = n_full * rows_per_warp;
-        return launch_pdl_t(biquad_delay_lanes<NS, L, DELAY, RPL, false, SVF>, dim3(1), dim3(32), st, t);
+    if (!packed) {
+        const uint32_t n_full = a.R / rows1;
+        if (n_full) {
+            cudaError_t e = launch_pdl_t(biquad_delay_lanes<NS, L, DELAY, 1, true, SVF>, dim3(n_full), dim3(32), st, a);
+            if (e != cudaSuccess) return e;
+        }
+        done = n_full * rows1;
+    }
+    if (done < a.R) {  // ragged tail
+        TemporalArgs t = a; t.row_base = done;
+        return launch_pdl_t(biquad_delay_lanes<NS, L, DELAY, 1, false, SVF>, dim3((a.R - done + rows1 - 1) / rows1), dim3(32), st, t);
     }
     return cudaSuccess;
-}
-template <int NS, int L>
-static cudaError_t launch_lanes(const TemporalArgs& a, cudaStream_t st) {
-    static const int rpl_knob = getenv("FW_TEMPORAL_RPL") ? atoi(getenv("FW_TEMPORAL_RPL")) : 1;  // A/B knob (2 rows/lane measured slower: 0.59 vs 0.50 ms)
-    if constexpr (L > 1) {
-        if (rpl_knob != 1) return a.D ? launch_lanes_split<NS, L, true, 2>(a, st) : launch_lanes_split<NS, L, false, 2>(a, st);
-    }
-    return a.D ? launch_lanes_split<NS, L, true, 1>(a, st) : launch_lanes_split<NS, L, false, 1>(a, st);
 }
 
 bool temporal_fast_path(const TemporalArgs& a) {
     if (a.T == 0 || a.T % 32u || a.zero_first % 32u) return false;
     if ((reinterpret_cast<uintptr_t>(a.in) | reinterpret_cast<uintptr_t>(a.out) | reinterpret_cast<uintptr_t>(a.ring)) % 16u) return false;
+    if ((a.in_pitch | a.out_pitch) % 4u) return false;
     if (a.D && (a.D % 32u || a.pos % 32u || a.D < 160u)) return false;
     return true;
 }
 
-cudaError_t launch_temporal(const TemporalArgs& a, cudaStream_t st) {
-    if (a.R == 0 || a.T == 0) return cudaSuccess;
+cudaError_t launch_temporal(const TemporalArgs& a0, cudaStream_t st) {
+    if (a0.R == 0 || a0.T == 0) return cudaSuccess;
+    TemporalArgs a = a0;
+    if (a.in_pitch == 0) a.in_pitch = a.T;
+    if (a.out_pitch == 0) a.out_pitch = a.T;
+    a.k_one = 1.0f; a.k_negzero = -0.0f; a.k_negone = -1.0f; a.k_two = 2.0f;  // see the PK note in the kernel's comment
     if (a.svf) {
         if (a.ns >= 1 && a.D == 0 && temporal_fast_path(a)) {
             switch (a.ns) {
-                case 1: return launch_lanes_split<1, 1, false, 1, true>(a, st);
-                case 2: return launch_lanes_split<2, 2, false, 1, true>(a, st);
-                case 3: return launch_lanes_split<3, 4, false, 1, true>(a, st);
-                case 4: return launch_lanes_split<4, 4, false, 1, true>(a, st);
-                case 5: return launch_lanes_split<5, 8, false, 1, true>(a, st);
-                case 6: return launch_lanes_split<6, 8, false, 1, true>(a, st);
-                case 7: return launch_lanes_split<7, 8, false, 1, true>(a, st);
-                default: return launch_lanes_split<8, 8, false, 1, true>(a, st);
+                case 1: return launch_lanes<1, 1, false, true>(a, st);
+                case 2: return launch_lanes<2, 2, false, true>(a, st);
+                case 3: return launch_lanes<3, 4, false, true>(a, st);
+                case 4: return launch_lanes<4, 4, false, true>(a, st);
+                case 5: return launch_lanes<5, 8, false, true>(a, st);
+                case 6: return launch_lanes<6, 8, false, true>(a, st);
+                case 7: return launch_lanes<7, 8, false, true>(a, st);
+                default: return launch_lanes<8, 8, false, true>(a, st);
             }
         }
         return launch_pdl_t(svf_generic, dim3((a.R + 63) / 64), dim3(64), st, a);
     }
     if (temporal_fast_path(a)) {
+#define FW_LANES(NS_, L_) (a.D ? launch_lanes<NS_, L_, true>(a, st) : launch_lanes<NS_, L_, false>(a, st))
         switch (a.ns) {
-            case 0: return launch_lanes<0, 1>(a, st);
-            case 1: return launch_lanes<1, 1>(a, st);
-            case 2: return launch_lanes<2, 2>(a, st);
-            case 3: return launch_lanes<3, 4>(a, st);
-            case 4: return launch_lanes<4, 4>(a, st);
-            case 5: return launch_lanes<5, 8>(a, st);
-            case 6: return launch_lanes<6, 8>(a, st);
-            case 7: return launch_lanes<7, 8>(a, st);
-            default: return launch_lanes<8, 8>(a, st);
+            case 0: return FW_LANES(0, 1);
+            case 1: return FW_LANES(1, 1);
+            case 2: return FW_LANES(2, 2);
+            case 3: return FW_LANES(3, 4);
+            case 4: return FW_LANES(4, 4);
+            case 5: return FW_LANES(5, 8);
+            case 6: return FW_LANES(6, 8);
+            case 7: return FW_LANES(7, 8);
+            default: return FW_LANES(8, 8);
         }
+#undef FW_LANES
     }
     return launch_pdl_t(biquad_delay_generic, dim3((a.R + 63) / 64), dim3(64), st, a);
 }

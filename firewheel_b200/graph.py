@@ -475,8 +475,18 @@ class FirewheelProcessor:
         return Stream(self._lib, h, num_out_channels) if h else None
 
     def comm_init(self, rank, world_size, id128):
+        self.world_size = world_size
         buf = (C.c_uint8 * 128).from_buffer_copy(bytes(id128))
         return self._lib.processor_comm_init(self._h, rank, world_size, buf)
+
+    def comm_allgather(self, array):
+        """All-gather a small host array over the processor's communicator: returns shape (world, *array.shape)."""
+        a = np.ascontiguousarray(array)
+        world = max(int(getattr(self, "world_size", 1)), 1)
+        out = np.empty((world,) + a.shape, a.dtype)
+        if self._lib.processor_comm_allgather(self._h, a.ctypes.data, out.ctypes.data, a.nbytes) != 0:
+            raise RuntimeError("comm_allgather failed: " + (self._lib.last_device_error() or b"").decode())
+        return out
 
     def free(self):
         if self._h:

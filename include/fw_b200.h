@@ -324,6 +324,9 @@ FW_EXPORT int FW_FN(processor_l2_flush)(fw_processor* p);             /* writes 
 /* ---- multi-GPU master bus (voices sharded by rank) --------------------------- */
 FW_EXPORT int FW_FN(comm_unique_id)(uint8_t* id128);                  /* ncclGetUniqueId */
 FW_EXPORT int FW_FN(processor_comm_init)(fw_processor* p, int rank, int world_size, const uint8_t* id128);
+/* host-buffer all-gather over that communicator (recv holds world_size * bytes): barriers, max-over-ranks timing and
+ * cross-rank result checks of a torch-free driver; world_size == 1 copies. Not on the audio path. */
+FW_EXPORT int FW_FN(processor_comm_allgather)(fw_processor* p, const void* send, void* recv, uint64_t bytes);
 
 #ifdef __cplusplus
 }

@@ -547,6 +547,7 @@ int fwo_processor_profile(fw_processor*, int) { return -1; }
 int fwo_processor_profile_read(fw_processor*, double*, uint64_t*) { return -1; }
 int fwo_comm_unique_id(uint8_t*) { return -1; }
 int fwo_processor_comm_init(fw_processor*, int, int, const uint8_t*) { return -1; }
+int fwo_processor_comm_allgather(fw_processor*, const void*, void*, uint64_t) { return -1; }
 
 // ---- oracle-only extras for known-answer tests and the CPU baseline ---------------------------
 // ParamSmoother driven directly (smoother.rs:93-205): returns the status after the last block.

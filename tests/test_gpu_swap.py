@@ -1,35 +1,13 @@
-"""Opt-in validation of kernels that are compiled but not yet enabled by default. Skipped unless FW_VALIDATE_EXPERIMENTAL=1.
-
-* FW_TEMPORAL_WS=1 — the warp-specialised (compute warp + mover warp) variant of the temporal lanes kernel
-  (firewheel_b200/csrc/temporal.cu). The knob is read once per process, so the temporal parity tests are re-run in a child
-  process with the knob set; they compare against the oracle bit for bit, exactly as for the default kernel."""
-import os
-import subprocess
-import sys
-from pathlib import Path
-
+"""Schedule swaps on the temporal and generic lowerings (processor.rs:167-206 + Q11: the first block after a swap reads zero
+inputs; node state survives the swap like the reference's processors do). The pointwise-chain case lives in test_gpu_parity.py."""
+import numpy as np
 import pytest
 
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("FW_VALIDATE_EXPERIMENTAL") != "1", reason="opt-in: FW_VALIDATE_EXPERIMENTAL=1")]
-ROOT = Path(__file__).resolve().parent.parent
+from conftest import synth
+from firewheel_b200 import BiquadNode, DelayNode, HardClipNode, SamplerNode, SumNode, VolumeNode, design_rbj
+from helpers import assert_bit_exact, chain, f32, run_planar
 
-
-def test_warp_specialised_temporal_kernel_is_bit_exact():
-    env = dict(os.environ, FW_TEMPORAL_WS="1")
-    env.pop("FW_VALIDATE_EXPERIMENTAL")
-    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-m", "gpu", "-k", "biquad or temporal or config3 or config5 or svf or golden or full_size",
-                        str(ROOT / "tests")], env=env, capture_output=True, text=True, timeout=900)
-    assert r.returncode == 0, r.stdout[-3000:]
-
-
-# ---- schedule swaps (Q11: the first block after a swap reads zero inputs; node state survives the swap) on paths the default
-# suite covers only for the pointwise chain. Written after the round's GPU budget ran out: enable with
-# FW_VALIDATE_EXPERIMENTAL=1, then move into the default files once green. ------------------------------------------------
-import numpy as np  # noqa: E402
-
-from conftest import synth  # noqa: E402
-from firewheel_b200 import BiquadNode, DelayNode, HardClipNode, SamplerNode, SumNode, VolumeNode, design_rbj  # noqa: E402
-from helpers import assert_bit_exact, chain, f32, run_planar  # noqa: E402
+pytestmark = pytest.mark.gpu
 
 
 def _swap_scenario(lib, V, F, kind):
