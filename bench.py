@@ -43,7 +43,7 @@ sys.path.insert(0, str(ROOT / "oracle"))
 
 F32 = np.float32
 SR = 48000
-C5_TOTAL_VOICES = 65536
+C5_TOTAL_VOICES = int(os.environ.get("FW_BENCH_C5_VOICES", "65536"))  # (development override; the config is 65536)
 WORKLOADS = {
     # voices per GPU (c5: in total), channels, block frames, blocks per step
     "c1": dict(voices=1, ch=1, block=256, blocks=4096, bus=False, desc="c1: single VolumeNode, mono, 256-frame blocks (CPU plumbing, beep_test shape)"),

@@ -79,6 +79,7 @@ SIGNATURES = {
     "graph_in_node": (_u64, [_vp]),
     "graph_out_node": (_u64, [_vp]),
     "graph_add_node": (_u64, [_vp, _u32, _u32, C.POINTER(NodeDesc)]),
+    "graph_add_custom_node": (_u64, [_vp, _u32, _u32, _vp, _vp]),
     "graph_remove_node": (_i32, [_vp, _u64, _pu64, _u32, _pu32]),
     "graph_set_num_inputs": (_i32, [_vp, _u64, _u32, _pu64, _u32, _pu32]),
     "graph_set_num_outputs": (_i32, [_vp, _u64, _u32, _pu64, _u32, _pu32]),

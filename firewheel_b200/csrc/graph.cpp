@@ -21,6 +21,7 @@ const char* node_debug_name(uint32_t kind) {
         case FW_NODE_SVF: return "svf";
         case FW_NODE_RESAMPLER: return "resampler";
         case FW_NODE_SAMPLER: return "beep_test";              // Q8: sampler.rs:186 really says that
+        case FW_NODE_CUSTOM: return "custom";                  // the context reports the plugin's own debug_name()
         default: return "unknown";
     }
 }

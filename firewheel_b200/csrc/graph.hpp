@@ -75,11 +75,18 @@ class SlotTable {
     }
 };
 
+// A user node behind the plugin vtable (include/fw_b200.h fw_node_vtable): the graph's `Box<dyn AudioNode>`.
+struct CustomNode {
+    fw_node_vtable vt{}; void* node = nullptr; fw_audio_node_info info{}; std::string debug_name;
+    ~CustomNode() { if (vt.drop_node) vt.drop_node(node); }
+};
+
 // ---- node parameters (main-thread side; the stream side snapshots them at call start) -------
 struct NodeParams {
     uint32_t kind = FW_NODE_DUMMY;
     uint32_t num_voices = 1;
     uint64_t version = 1;  // bumped on every change; the device mirror re-uploads when it differs
+    std::shared_ptr<CustomNode> custom;  // kind == FW_NODE_CUSTOM
     // volume (volume.rs:8-34)
     std::vector<float> percent, raw_gain;
     // pan

@@ -277,6 +277,10 @@ __global__ void __launch_bounds__(128) control_kernel(const __grid_constant__ Co
                 case FW_NODE_HARD_CLIP:  // hard_clip.rs:60-80 leaves the mask untouched on the stereo fast path
                     if (!(nd.n_in == 2 && nd.n_out == 2 && (in_mask & 3ull) == 0)) out_mask = in_mask;
                     break;
+                case FW_NODE_CUSTOM:  // the plugin's declared out_silence_rule (include/fw_b200.h)
+                    if (nd.sm0 == FW_OUT_SILENCE_PASSTHROUGH) out_mask = in_mask & all_silent_mask(nd.n_out);
+                    else if (nd.sm0 == FW_OUT_SILENCE_ALL_IF_ALL_INPUTS && nd.n_in > 0 && all_channels_silent(in_mask, nd.n_in)) out_mask = all_silent_mask(nd.n_out);
+                    break;
                 default: break;  // dummy / graph_in / graph_out / biquad / delay / reverb: NONE_SILENT
             }
             if (n + 1 == tb.n_nodes) gout_mask = in_mask;  // graph_out is scheduled last (compiler.rs:291)
@@ -651,6 +655,16 @@ __global__ void __launch_bounds__(128) silence_fix_kernel(const __grid_constant_
     VecT<VEC>::store(a.out + (size_t)v * T + t, z);
 }
 
+// Dense per-(block, voice) input silence masks of one mask slot, for a custom node's process_device (fw_device_block::in_silence_masks).
+__global__ void __launch_bounds__(128) expand_masks_kernel(Records rec, uint32_t mask_slot, uint32_t V, uint32_t n_blocks, uint64_t* __restrict__ out) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y;
+    if (v >= V || k >= n_blocks) return;
+    out[(size_t)k * V + v] = k >= rec.steady_k[v] ? rec.st_sum_masks[(size_t)mask_slot * V + v]
+                                                  : rec.sum_masks[((size_t)rec_slot(rec, v, k, V) * rec.n_sum_masks + mask_slot) * V + v];
+}
+
 // K-sampler: SamplerNode data plane (sampler.rs:445-559 + sample_resource.rs:337-456). One thread = VEC frames of one
 // (voice, output channel); what the block plays comes from the control kernel's SmpRec, the samples straight from the
 // resource in HBM (converted per sample_resource.rs:337-345), times the node's gain record.
@@ -904,6 +918,10 @@ cudaError_t launch_silence_fix(const SilenceFixArgs& a, cudaStream_t st) {
     const bool vec4 = (a.frames % 4 == 0) && (a.block_frames % 4 == 0) && (reinterpret_cast<uintptr_t>(a.out) % 16 == 0);
     if (vec4) return launch_pdl(silence_fix_kernel<4>, dim3(a.num_voices, (a.frames / 4 + 127) / 128), dim3(128), st, a);
     return launch_pdl(silence_fix_kernel<1>, dim3(a.num_voices, (a.frames + 127) / 128), dim3(128), st, a);
+}
+cudaError_t launch_expand_masks(const Records& rec, uint32_t mask_slot, uint32_t V, uint32_t n_blocks, uint64_t* out, cudaStream_t st) {
+    if (V == 0 || n_blocks == 0) return cudaSuccess;
+    return launch_pdl(expand_masks_kernel, dim3((V + 127) / 128, n_blocks), dim3(128), st, rec, mask_slot, V, n_blocks, out);
 }
 cudaError_t launch_deinterleave(const float* inter, float* planar, uint32_t V, uint32_t C, uint32_t T, cudaStream_t st) {
     const size_t n = (size_t)V * C * T; if (n == 0) return cudaSuccess;

@@ -30,7 +30,7 @@ struct ChainProgram { uint32_t n_ops, c_in, c_out, pad; ChainOp ops[kMaxChainOps
 struct CtlNode {
     uint8_t kind, n_in, n_out, mask_slot;  // mask_slot: 1 + index into Records::sum_masks, 0 = none
     uint16_t in_off, out_off;   // into in_buf / in_clear / out_buf
-    int16_t sm0, sm1;           // smoother indices (-1: none); SamplerNode: sm1 = index into CtlTables::smp
+    int16_t sm0, sm1;           // smoother indices (-1: none); SamplerNode: sm1 = index into CtlTables::smp; custom node: sm0 = fw_out_silence_rule
 };
 
 // ---- SamplerNode (sampler.rs:283-560) on the device ----

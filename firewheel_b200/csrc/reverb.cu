@@ -26,6 +26,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <string>
+#include <utility>
 
 #include "kernels.cuh"
 #include "plan.hpp"
@@ -115,6 +116,7 @@ __global__ void reverb_build_toeplitz(const float* __restrict__ ir, __nv_bfloat1
 // xh[c*V + v][cursor + t] = bf16(in[v][c][t]) for t < T: appends the call's block behind the history (8 samples per thread)
 __global__ void reverb_prepare(const float* __restrict__ in, __nv_bfloat16* __restrict__ xh, uint32_t V, uint32_t C, uint32_t T, uint32_t in_pitch, uint32_t cursor,
                                uint32_t pitch, uint32_t zero_first, uint32_t chan_base) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the GEMM's set-up (barriers, TMEM, tensor maps) overlaps this kernel
     asm volatile("griddepcontrol.wait;" ::: "memory");
     const uint32_t row = blockIdx.x;  // c * V + v (rows on grid.x: no 65535 cap)
     const uint32_t c = row / V, v = row % V;
@@ -164,6 +166,7 @@ __global__ void __launch_bounds__(256, 1) reverb_gemm_kernel(const __grid_consta
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]: accumulator drained  (epilogue -> MMA)
     uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the next kernel's launch latency hides behind this one; it waits for our results itself
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     const uint32_t g = blockIdx.x, G = gridDim.x, num_kb = a.num_kb;
 
@@ -263,6 +266,170 @@ __global__ void __launch_bounds__(256, 1) reverb_gemm_kernel(const __grid_consta
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2): two SMs of a cluster share one 256-voice x BN-frame tile.
+// Why: the single-CTA kernel is bound by SHARED-MEMORY bandwidth, not by the tensor pipe. Per 64-wide k-block an SM writes
+// (TMA) and reads (UMMA operand fetch) A 16 KB + B BN*128 B each: 96 KB at BN = 256, i.e. 768 cycles at 128 B/clk against
+// 512 cycles of MMA (measured on config 5: 730 cycles per k-block at BN = 256, 555 at BN = 128 — the fixed A term does not
+// shrink with the tile). In a pair each SM stages its own 128 voices of A and only HALF of B (the tensor cores of both SMs
+// consume both halves), so the traffic is 64 KB per k-block = 512 cycles: level with the MMA.
+//   * cluster (2,1,1); rank 0 (leader) issues every tcgen05.mma.cta_group::2 (M = 256), both CTAs run TMA + epilogue;
+//   * full barriers live in the leader: both CTAs' TMA loads complete_tx on them (cp.async.bulk.tensor .cta_group::2);
+//   * tcgen05.commit ... multicast::cluster releases the smem stage / publishes the accumulator in BOTH CTAs;
+//   * the leader's MMA warp waits for the epilogues of both CTAs (8 warps arrive on its tmem_empty barrier, the peer's
+//     through mapa + mbarrier.arrive.shared::cluster);
+//   * cluster barrier after set-up and before tear-down (the leader's MMAs read the peer's smem and TMEM).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr uint32_t RV2_STAGES = 6;
+constexpr uint32_t RV2_B_BYTES_MAX = (RV_BN / 2) * RV_BK * 2;  // 16 KB: half of B
+constexpr uint32_t RV2_SMEM_BYTES = RV2_STAGES * (RV_A_BYTES + RV2_B_BYTES_MAX) + 1024 /*align*/ + 256 /*barriers*/;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t smem_addr, uint32_t rank) { uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank)); return r; }
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) { asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory"); }
+// TMA load into THIS CTA's smem whose completion bytes are counted on a barrier given by its shared::cluster address (the leader's)
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* tm, uint32_t bar_cluster_addr, int32_t x, int32_t y) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(smem_dst)), "l"(tm), "r"(bar_cluster_addr), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void tcgen05_alloc2(uint32_t* smem_result, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tcgen05_dealloc2(uint32_t taddr, uint32_t cols) { asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory"); }
+__device__ __forceinline__ void tcgen05_commit2(uint64_t* bar) {  // arrives on the barrier at this offset in BOTH CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tcgen05_mma2_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+template <uint32_t BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+reverb_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const ReverbGemmArgs a) {
+    constexpr uint32_t B_BYTES = (BN / 2) * RV_BK * 2;  // this CTA's half of B
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + RV2_STAGES * RV_A_BYTES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + RV2_STAGES * (RV_A_BYTES + RV2_B_BYTES_MAX));  // used in the leader
+    uint64_t* empty_bar = full_bar + RV2_STAGES;       // armed in both CTAs by the leader's multicast commit
+    uint64_t* tmem_full_bar = empty_bar + RV2_STAGES;  // [2], both CTAs
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2], used in the leader: 8 epilogue warps of the pair
+    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const uint32_t P = blockIdx.x >> 1, NP = gridDim.x >> 1, num_kb = a.num_kb;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_b) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (uint32_t s = 0; s < RV2_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (uint32_t b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) tcgen05_alloc2(tmem_base_slot, 512);
+    tcgen05_fence_before();
+    __syncthreads();
+    cluster_sync_all();  // the peer's barriers are initialised and its TMEM is allocated before anything targets them
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_base_slot;
+    const uint32_t tiles_per_ch = a.tiles_n * a.tiles_m;
+
+    if (warp == 0) {
+        // ===== TMA producer (both CTAs): own 128 voices of A, own half of B =====
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (uint32_t t = P; t < a.total_tiles; t += NP) {
+                const uint32_t c = t / tiles_per_ch, rem = t % tiles_per_ch, mt = rem / a.tiles_n, nt = rem % a.tiles_n;
+                const int32_t col_a0 = (int32_t)(a.cursor + nt * BN) - (int32_t)a.Lr;
+                const int32_t row_a = (int32_t)((a.chan_base + c) * a.V + mt * 2u * RV_BM + rank * RV_BM);
+                const int32_t row_b = (int32_t)(((a.chan_base + c) % a.ir_ch) * RV_BN + rank * (BN / 2));
+                for (uint32_t kb = 0; kb < num_kb; ++kb, ++it) {
+                    const uint32_t s = it % RV2_STAGES, ph = (it / RV2_STAGES) & 1u;
+                    mbar_wait(&empty_bar[s], ph ^ 1u);
+                    const uint32_t full_leader = mapa_rank(smem_u32(&full_bar[s]), 0);
+                    if (leader) mbar_expect_tx(&full_bar[s], 2u * (RV_A_BYTES + B_BYTES));  // the bytes of both CTAs
+                    tma_load_2d_pair(smem_a + s * RV_A_BYTES, &tm_a, full_leader, col_a0 + (int32_t)(kb * RV_BK), row_a);
+                    tma_load_2d_pair(smem_b + s * RV2_B_BYTES_MAX, &tm_b, full_leader, (int32_t)(kb * RV_BK), row_b);
+                }
+            }
+        }
+    } else if (warp == 1 && leader) {
+        // ===== MMA issuer: the leader's elected lane drives both tensor cores =====
+        constexpr uint32_t idesc = umma_idesc_bf16(2 * RV_BM, BN);
+        uint32_t it = 0, seg = 0;
+        for (uint32_t t = P; t < a.total_tiles; t += NP, ++seg) {
+            const uint32_t buf = seg & 1u;
+            mbar_wait(&tmem_empty_bar[buf], ((seg >> 1) & 1u) ^ 1u);
+            tcgen05_fence_after();
+            const uint32_t tmem_d = tmem_base + buf * RV_BN;
+            for (uint32_t kb = 0; kb < num_kb; ++kb, ++it) {
+                const uint32_t s = it % RV2_STAGES, ph = (it / RV2_STAGES) & 1u;
+                mbar_wait(&full_bar[s], ph);
+                tcgen05_fence_after();
+                if (elect_one()) {
+                    const uint64_t adesc = umma_desc_sw128(smem_u32(smem_a + s * RV_A_BYTES));
+                    const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_b + s * RV2_B_BYTES_MAX));
+#pragma unroll
+                    for (uint32_t k = 0; k < RV_BK / 16; ++k)
+                        tcgen05_mma2_f16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+                    tcgen05_commit2(&empty_bar[s]);
+                    if (kb + 1 == num_kb) tcgen05_commit2(&tmem_full_bar[buf]);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue (both CTAs): own 128 rows of the 256-row tile =====
+        const uint32_t q = warp & 3u;
+        uint32_t seg = 0;
+        for (uint32_t t = P; t < a.total_tiles; t += NP, ++seg) {
+            const uint32_t buf = seg & 1u;
+            const uint32_t c = t / tiles_per_ch, rem = t % tiles_per_ch, mt = rem / a.tiles_n, nt = rem % a.tiles_n;
+            const uint32_t n0 = nt * BN, v = mt * 2u * RV_BM + rank * RV_BM + q * 32u + lane;
+            mbar_wait(&tmem_full_bar[buf], (seg >> 1) & 1u);
+            tcgen05_fence_after();
+            float* dst_row = a.out + ((size_t)v * a.C + c) * a.out_pitch + n0;
+#pragma unroll 1
+            for (uint32_t col = 0; col < BN; col += 32) {
+                uint32_t r[32];
+                tcgen05_ld_32x32b_x32(tmem_base + ((q * 32u) << 16) + buf * RV_BN + col, r);
+                if (v < a.V) {
+                    if (n0 + col + 32 <= a.T && ((a.T | a.out_pitch) & 3u) == 0) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4)
+                            __stcs(reinterpret_cast<float4*>(dst_row + col + i), make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]), __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3])));
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) if (n0 + col + i < a.T) dst_row[col + i] = __uint_as_float(r[i]);
+                    }
+                }
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa_rank(smem_u32(&tmem_empty_bar[buf]), 0));
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    cluster_sync_all();  // nobody leaves while the pair still reads this CTA's smem / TMEM or arrives on its barriers
+    if (warp == 2) tcgen05_dealloc2(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -304,6 +471,19 @@ uint32_t reverb_grid_max() {
     return (uint32_t)sms;
 }
 
+// Programmatic dependent launch: every kernel here executes griddepcontrol.wait before it touches its predecessor's results,
+// so the stream-order chain of completions stays intact while launch latency and prologues overlap.
+template <class... KArgs, class... Args>
+static cudaError_t launch_pdl_r(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 template <uint32_t BN>
 static cudaError_t launch_gemm(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const ReverbGemmArgs& ga, uint32_t grid, cudaStream_t st) {
     static bool attr_set = false;
@@ -312,17 +492,44 @@ static cudaError_t launch_gemm(const CUtensorMap& tm_a, const CUtensorMap& tm_b,
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    reverb_gemm_kernel<BN><<<dim3(grid), 256, RV_SMEM_BYTES, st>>>(tm_a, tm_b, ga);
-    return cudaGetLastError();
+    return launch_pdl_r(reverb_gemm_kernel<BN>, dim3(grid), dim3(256), RV_SMEM_BYTES, st, tm_a, tm_b, ga);
 }
 
-// Tile width for a call: the candidate that needs the least (waves of SMs) x (tile width + a per-tile constant).
-static uint32_t reverb_pick_bn(uint32_t T, uint32_t tiles_mc, uint32_t sms) {
+template <uint32_t BN>
+static cudaError_t launch_gemm2(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const ReverbGemmArgs& ga, uint32_t pairs_max, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(reverb_gemm2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RV2_SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    const uint32_t pairs = ga.total_tiles < pairs_max ? ga.total_tiles : pairs_max;
+    return launch_pdl_r(reverb_gemm2_kernel<BN>, dim3(2 * pairs), dim3(256), RV2_SMEM_BYTES, st, tm_a, tm_b, ga);  // cluster dims are compiled in
+}
+// CTA pairs that can be co-resident (a GPC with an odd number of usable SMs strands one)
+static uint32_t reverb_pairs_max() {
+    static int pairs = 0;
+    if (!pairs) {
+        cudaFuncSetAttribute(reverb_gemm2_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RV2_SMEM_BYTES);
+        cudaLaunchConfig_t cfg{}; cfg.gridDim = dim3(2 * reverb_grid_max()); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = RV2_SMEM_BYTES;
+        cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, reverb_gemm2_kernel<256>, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = (int)reverb_grid_max() / 2; }
+        pairs = n;
+    }
+    return (uint32_t)pairs;
+}
+
+// Tile width for a call: least (waves) x (cycles per k-block). Cycles per k-block = max(MMA, shared-memory traffic at
+// 128 B/clk): one CTA per tile 4 x BN/2 against (2 x (16 KB + BN x 128 B)) / 128; a CTA pair 4 x BN/2 against (2 x (16 KB + BN x 64 B)) / 128.
+static uint32_t reverb_pick_bn(uint32_t T, uint32_t tiles_mc, uint32_t units, bool pair) {
     static const uint32_t cand[4] = {256, 224, 192, 128};
     uint32_t best = 256; uint64_t best_cost = ~0ull;
     for (uint32_t bn : cand) {
-        const uint64_t tiles = (uint64_t)((T + bn - 1) / bn) * tiles_mc, waves = (tiles + sms - 1) / sms;
-        const uint64_t cost = waves * (bn + 12u);
+        const uint64_t tiles = (uint64_t)((T + bn - 1) / bn) * tiles_mc, waves = (tiles + units - 1) / units;
+        const uint64_t mma = 2ull * bn, smem = pair ? 256ull + bn : 256ull + 2ull * bn;
+        const uint64_t cost = waves * ((mma > smem ? mma : smem) + 8u);
         if (cost < best_cost) { best_cost = cost; best = bn; }
     }
     return best;
@@ -333,16 +540,18 @@ cudaError_t launch_reverb(const ReverbCall& rc, cudaStream_t st, std::string* er
     {
         const uint32_t per_block = 256 * 8;
         dim3 grid(rc.C * rc.V, (rc.T + per_block - 1) / per_block < 32 ? (rc.T + per_block - 1) / per_block : 32);
-        reverb_prepare<<<grid, 256, 0, st>>>(rc.in, static_cast<__nv_bfloat16*>(rc.xh), rc.V, rc.C, rc.T, in_pitch, rc.cursor, rc.pitch, rc.zero_first, rc.chan_base);
-        cudaError_t e = cudaGetLastError();
+        cudaError_t e = launch_pdl_r(reverb_prepare, grid, dim3(256), 0, st, rc.in, static_cast<__nv_bfloat16*>(rc.xh), rc.V, rc.C, rc.T, in_pitch, rc.cursor, rc.pitch, rc.zero_first, rc.chan_base);
         if (e != cudaSuccess) return e;
     }
-    const uint32_t sms = reverb_grid_max(), tiles_m = (rc.V + RV_BM - 1) / RV_BM;
-    const uint32_t bn = reverb_pick_bn(rc.T, tiles_m * rc.C, sms);
+    const bool pair = rc.V > RV_BM && !(getenv("FW_REVERB_1CTA"));  /* TEMP A/B */  // a pair covers 256 voices: with 128 or fewer the second SM would idle
+    const uint32_t sms = reverb_grid_max(), tiles_m = pair ? (rc.V + 2 * RV_BM - 1) / (2 * RV_BM) : (rc.V + RV_BM - 1) / RV_BM;
+    const uint32_t units = pair ? reverb_pairs_max() : sms;
+    uint32_t bn = reverb_pick_bn(rc.T, tiles_m * rc.C, units, pair);
+    { static const int k = getenv("FW_REVERB_BN") ? atoi(getenv("FW_REVERB_BN")) : 0; if (k == 256 || k == 224 || k == 192 || k == 128) bn = (uint32_t)k; }  // TEMP A/B
     const uint32_t kpad = reverb_kpad(rc.L);  // pitch of the Toeplitz rows (built for the widest tile)
     CUtensorMap tm_a, tm_b;
     if (!make_map_bf16_2d(&tm_a, rc.xh, (uint64_t)rc.cursor + rc.T, (uint64_t)(rc.chan_base + rc.C) * rc.V, rc.pitch, RV_BK, RV_BM) ||
-        !make_map_bf16_2d(&tm_b, rc.bt, kpad, (uint64_t)rc.ir_ch * RV_BN, kpad, RV_BK, bn)) {
+        !make_map_bf16_2d(&tm_b, rc.bt, kpad, (uint64_t)rc.ir_ch * RV_BN, kpad, RV_BK, pair ? bn / 2 : bn)) {
         if (err) *err = "cuTensorMapEncodeTiled failed";
         return cudaErrorInvalidValue;
     }
@@ -352,6 +561,14 @@ cudaError_t launch_reverb(const ReverbCall& rc, cudaStream_t st, std::string* er
     ga.chan_base = rc.chan_base;
     ga.tiles_n = (rc.T + bn - 1) / bn; ga.tiles_m = tiles_m; ga.total_tiles = ga.tiles_n * ga.tiles_m * rc.C;
     if (ga.total_tiles == 0) return cudaSuccess;
+    if (pair) {
+        switch (bn) {
+            case 224: return launch_gemm2<224>(tm_a, tm_b, ga, units, st);
+            case 192: return launch_gemm2<192>(tm_a, tm_b, ga, units, st);
+            case 128: return launch_gemm2<128>(tm_a, tm_b, ga, units, st);
+            default: return launch_gemm2<256>(tm_a, tm_b, ga, units, st);
+        }
+    }
     const uint32_t G = ga.total_tiles < sms ? ga.total_tiles : sms;
     switch (bn) {
         case 224: return launch_gemm<224>(tm_a, tm_b, ga, G, st);

@@ -118,8 +118,17 @@ struct NodeDeviceState {
     const ResDesc* cur_tab = nullptr; uint32_t cur_n_res = 0;
     SmpRec* d_srec = nullptr; size_t cap_srec = 0;
     std::vector<SamplerMsgDev> h_msgs; std::vector<uint32_t> h_off; std::vector<NodeParams::SamplerMsg> h_drain;
+    // custom node (plugin vtable): the processor returned by activate() and the dense per-(block, voice) input masks handed to it
+    void* custom_proc = nullptr; bool custom_deactivate = false;  // true: released through deactivate(node, processor) (graph.rs:603-609,644-648)
+    uint64_t* d_custom_masks = nullptr; size_t cap_custom_masks = 0;
     ~NodeDeviceState() {
         cudaSetDevice(device);
+        if (params && params->custom && custom_proc) {  // main thread: plans are released in ctx_drain / ctx_free
+            const fw_node_vtable& vt = params->custom->vt;
+            if (custom_deactivate && vt.deactivate) vt.deactivate(params->custom->node, custom_proc);
+            else if (vt.drop_processor) vt.drop_processor(custom_proc);
+        }
+        cudaFree(d_custom_masks);
         for (int i = 0; i < 2; ++i) { cudaFree(d_target[i]); cudaFree(sm_input[i]); cudaFree(sm_last[i]); cudaFree(sm_status[i]); }
         cudaFree(d_coeffs); cudaFree(d_state); cudaFree(d_ring); cudaFree(d_bt); cudaFree(d_xh[0]); cudaFree(d_xh[1]);
         cudaFree(d_playing); cudaFree(d_playhead); cudaFree(d_loop_flags); cudaFree(d_loop_start); cudaFree(d_loop_end); cudaFree(d_res);
@@ -314,6 +323,7 @@ struct fw_ctx {
     Schedule dbg_schedule; bool dbg_valid = false;
     // ActiveState (context.rs:17-27)
     bool active = false; std::shared_ptr<Channels> ch; uint32_t sample_rate = 0, max_block_frames = 0, n_in = 0, n_out = 0;
+    uint32_t max_call_blocks = 1024;  // longest call (in blocks) per-call side buffers are reserved for
 };
 
 struct fw_processor {
@@ -323,6 +333,7 @@ struct fw_processor {
     uint32_t num_voices = 0, max_block_frames = 0, n_in = 0, n_out = 0; bool bus = false;
     float sm_a = 0, sm_b = 0, sm_eps = 0;
     uint64_t launches = 0;
+    double cur_stream_time = 0.0; uint32_t cur_stream_status = 0;  // ProcInfo fields of the call being enqueued (node.rs:108-114)
     // I/O staging (high-water mark)
     float *d_in = nullptr, *d_out = nullptr, *d_inter = nullptr, *d_part[2] = {nullptr, nullptr}, *d_flush = nullptr;
     size_t cap_in = 0, cap_out = 0, cap_inter = 0, cap_part[2] = {0, 0};
@@ -371,6 +382,7 @@ static bool lower(fw_ctx* c, const Schedule& s, Plan* plan, std::string* why) {
         CtlNode& cn = tb.nodes[i];
         cn.kind = (uint8_t)nr->params->kind; cn.n_in = (uint8_t)sn.in.size(); cn.n_out = (uint8_t)sn.out.size();
         cn.in_off = (uint16_t)off_in; cn.out_off = (uint16_t)off_out; cn.sm0 = cn.sm1 = -1;
+        if (nr->params->kind == FW_NODE_CUSTOM) cn.sm0 = (int16_t)nr->params->custom->info.out_silence_rule;
         if (off_in + sn.in.size() > (size_t)kMaxCtlPorts || off_out + sn.out.size() > (size_t)kMaxCtlPorts) { *why = "too many ports"; return false; }
         for (const InAssign& a : sn.in) { tb.in_buf[off_in] = (uint8_t)a.buffer; tb.in_clear[off_in] = a.should_clear; ++off_in; }
         for (const OutAssign& a : sn.out) tb.out_buf[off_out++] = (uint8_t)a.buffer;
@@ -514,9 +526,10 @@ static bool lower(fw_ctx* c, const Schedule& s, Plan* plan, std::string* why) {
             gn.f0 = nr->params->threshold_gain;
             const bool endpoint = i == 0 || i + 1 == n;
             // bodies that branch on the input silence mask (see silence_fix_kernel / sum_kernel)
-            const bool needs_mask = !endpoint && !sn.out.empty() &&
+            const bool needs_mask = !endpoint && ((gn.kind == FW_NODE_CUSTOM) || (!sn.out.empty() &&
                 ((gn.kind == FW_NODE_SUM && sn.in.size() != sn.out.size()) || gn.kind == FW_NODE_HARD_CLIP || (gn.kind == FW_NODE_VOLUME && sn.in.size() != 2) ||
-                 gn.kind == FW_NODE_MONO_TO_STEREO || gn.kind == FW_NODE_STEREO_TO_MONO);
+                 gn.kind == FW_NODE_MONO_TO_STEREO || gn.kind == FW_NODE_STEREO_TO_MONO)));
+            if (gn.kind == FW_NODE_CUSTOM && !nr->params->custom->vt.process_device) { *why = std::string("custom node '") + nr->params->custom->debug_name + "' has no process_device: it cannot run on the device (there is no CPU fallback)"; return false; }
             if (needs_mask) {
                 if (n_sum_masks >= (uint32_t)kMaxSumMasks) { *why = "more than 32 mask-dependent nodes in one voice graph"; return false; }
                 gn.mask_slot = (int)n_sum_masks; tb.nodes[i].mask_slot = (uint8_t)(++n_sum_masks);
@@ -648,6 +661,21 @@ fw_node_id fw_graph_add_node(fw_ctx* c, uint32_t ni, uint32_t no, const fw_node_
     if (!p) { c->last_error = "bad node description"; return FW_ID_DANGLING; }
     return c->graph->add_node(ni, no, std::move(p)).pack();
 }
+fw_node_id fw_graph_add_custom_node(fw_ctx* c, uint32_t ni, uint32_t no, const fw_node_vtable* vt, void* node) {  // graph.rs:201-231
+    if (!c || !vt || ni > 64 || no > 64 || !vt->debug_name || !vt->info || !vt->activate) {
+        if (vt && vt->drop_node) vt->drop_node(node);
+        if (c) c->last_error = "bad custom node (vtable needs debug_name, info and activate)";
+        return FW_ID_DANGLING;
+    }
+    auto p = std::make_shared<NodeParams>();
+    p->kind = FW_NODE_CUSTOM; p->num_voices = c->cfg.num_voices;
+    p->custom = std::make_shared<CustomNode>();
+    p->custom->vt = *vt; p->custom->node = node;
+    const char* name = vt->debug_name(node);
+    p->custom->debug_name = name ? name : "custom";
+    vt->info(node, &p->custom->info);  // `let info = node.info()` (graph.rs:210)
+    return c->graph->add_node(ni, no, std::move(p)).pack();
+}
 static void write_ids(const std::vector<Id>& v, uint64_t* out, uint32_t cap, uint32_t* n) {
     if (n) *n = (uint32_t)v.size();
     for (size_t i = 0; i < v.size() && i < cap && out; ++i) out[i] = v[i].pack();
@@ -700,8 +728,14 @@ int fw_graph_node_info(fw_ctx* c, fw_node_id node, fw_node_info* out) {
         out->num_inputs = r->num_inputs; out->num_outputs = r->num_outputs; out->kind = r->params->kind;
         node_supported_ports(r->params->kind, &out->num_min_supported_inputs, &out->num_max_supported_inputs, &out->num_min_supported_outputs, &out->num_max_supported_outputs);
         const char* name = r->id == c->graph->graph_in() ? "graph_in" : r->id == c->graph->graph_out() ? "graph_out" : node_debug_name(r->params->kind);
-        std::strncpy(out->debug_name, name, sizeof(out->debug_name) - 1);
         out->updates = r->params->kind == FW_NODE_SAMPLER;  // sampler.rs:193
+        if (r->params->custom) {
+            const fw_audio_node_info& ci = r->params->custom->info;
+            out->num_min_supported_inputs = ci.num_min_supported_inputs; out->num_max_supported_inputs = ci.num_max_supported_inputs;
+            out->num_min_supported_outputs = ci.num_min_supported_outputs; out->num_max_supported_outputs = ci.num_max_supported_outputs;
+            out->updates = ci.updates != 0; name = r->params->custom->debug_name.c_str();
+        }
+        std::strncpy(out->debug_name, name, sizeof(out->debug_name) - 1);
     }
     return 1;
 }
@@ -958,6 +992,9 @@ int fw_ctx_is_activated(fw_ctx* c) { return c->active; }
 int fw_ctx_update(fw_ctx* c, fw_update_status* out) {  // context.rs:93-148
     fw_update_status st{}; st.kind = FW_UPDATE_INACTIVE; st.error_node = FW_ID_DANGLING;
     auto done = [&] { if (out) *out = st; return 0; };
+    c->graph->each_node([&](Id, NodeRec& r) {  // self.graph.update() (context.rs:94, graph.rs:691-697)
+        if (r.params->custom && r.params->custom->info.updates && r.params->custom->vt.update) r.params->custom->vt.update(r.params->custom->node);
+    });
     if (!c->active) return done();
     bool dropped = false; void* cx = nullptr;
     ctx_drain(c, &dropped, &cx);
@@ -979,11 +1016,25 @@ int fw_ctx_update(fw_ctx* c, fw_update_status* out) {  // context.rs:93-148
         if (msg.empty()) {
             ds = std::make_shared<NodeDeviceState>();
             ds->device = c->cfg.device; ds->kind = r->params->kind; ds->V = c->cfg.num_voices; ds->params = r->params; ds->channels = r->num_inputs;
+            if (r->params->custom) {  // AudioNode::activate (node.rs:12-18)
+                char err[256] = {0};
+                void* proc_h = nullptr;
+                const int arc = r->params->custom->vt.activate(r->params->custom->node, c->sample_rate, c->max_block_frames, r->num_inputs, r->num_outputs, c->cfg.num_voices,
+                                                              c->cfg.device, &proc_h, err, (uint32_t)sizeof(err) - 1);
+                if (arc != 0 || !proc_h) msg = err[0] ? std::string(err) : std::string("custom node activation failed");
+                else {
+                    ds->custom_proc = proc_h;
+                    ds->cap_custom_masks = (size_t)c->max_call_blocks * c->cfg.num_voices;
+                    ds->d_custom_masks = dev_alloc<uint64_t>(ds->cap_custom_masks);
+                    if (!ds->d_custom_masks) msg = "device allocation failed: " + g_dev_err;
+                }
+            }
             if (ds->kind == FW_NODE_SAMPLER || ds->kind == FW_NODE_RESAMPLER) { if (!c->res) { c->res = std::make_shared<ResTable>(); c->res->device = c->cfg.device; } ds->res_table = c->res; }
             if (!ds->create()) msg = "device allocation failed: " + g_dev_err;
         }
         if (!msg.empty()) {
-            for (uint64_t k : created) c->node_states.erase(k);
+            if (ds && ds->custom_proc) ds->custom_deactivate = true;
+            for (uint64_t k : created) { auto it = c->node_states.find(k); if (it != c->node_states.end()) { it->second->custom_deactivate = true; c->node_states.erase(it); } }  // roll-back: deactivate(Some(processor)) (graph.rs:603-609)
             st.graph_error = FW_COMPILE_NODE_ACTIVATION_FAILED; st.error_node = id.pack(); c->last_error = msg;
             return done();
         }
@@ -991,12 +1042,15 @@ int fw_ctx_update(fw_ctx* c, fw_update_status* out) {  // context.rs:93-148
     }
     std::string why;
     if (!lower(c, plan->sched, plan.get(), &why)) {
-        for (uint64_t k : created) c->node_states.erase(k);
+        for (uint64_t k : created) { auto it = c->node_states.find(k); if (it != c->node_states.end()) { it->second->custom_deactivate = true; c->node_states.erase(it); } }
         st.graph_error = FW_COMPILE_UNSUPPORTED_ON_DEVICE; c->last_error = why;
         return done();
     }
     plan->nodes_to_remove = c->graph->nodes_removed_since_compile;
-    for (Id id : plan->nodes_to_remove) c->node_states.erase(id.pack());  // the outgoing plan still holds them until it is returned
+    for (Id id : plan->nodes_to_remove) {  // the outgoing plan still holds them until it is returned; then deactivate(Some(processor)) (graph.rs:644-648)
+        auto it = c->node_states.find(id.pack());
+        if (it != c->node_states.end()) { it->second->custom_deactivate = true; c->node_states.erase(it); }
+    }
     c->graph->clear_dirty(); c->graph->nodes_to_activate.clear(); c->graph->nodes_removed_since_compile.clear();
     cudaDeviceSynchronize();  // tables and initial state are resident before the stream side can see the plan
     CtxToProc m; m.kind = 0; m.plan = plan.get();
@@ -1333,6 +1387,23 @@ static int enqueue_generic(fw_processor* p, Plan& pl, const float* d_in, float* 
                 rs.xh_cursor += T;
                 break;
             }
+            case FW_NODE_CUSTOM: {  // AudioNodeProcessor::process for all voices and blocks at once (fw_node_vtable::process_device)
+                NodeDeviceState& st = *gn.st;
+                const uint32_t nb = (T + pl.block_frames - 1) / pl.block_frames;
+                if ((size_t)nb * V > st.cap_custom_masks) { g_dev_err = "custom node: call longer than the reserved mask buffer"; return FW_PROC_DEVICE_ERROR; }
+                if (!FW_CUDA(launch_expand_masks(pl.rec, (uint32_t)gn.mask_slot, V, nb, st.d_custom_masks, p->stream))) return FW_PROC_DEVICE_ERROR;
+                p->launches++;
+                const float* ins[64]; float* outs[64];
+                for (size_t c = 0; c < gn.in_buf.size(); ++c) ins[c] = buf(gn.in_buf[c]);
+                for (size_t c = 0; c < gn.out_buf.size(); ++c) outs[c] = buf(gn.out_buf[c]);
+                fw_device_block blk{};
+                blk.num_voices = V; blk.num_inputs = (uint32_t)gn.in_buf.size(); blk.num_outputs = (uint32_t)gn.out_buf.size(); blk.block_frames = pl.block_frames; blk.num_blocks = nb;
+                blk.stream_status = p->cur_stream_status; blk.frames = T; blk.in_voice_stride = T; blk.out_voice_stride = T; blk.inputs = ins; blk.outputs = outs;
+                blk.in_silence_masks = st.d_custom_masks; blk.stream_time_secs = p->cur_stream_time; blk.cuda_stream = p->stream; blk.user_cx = p->user_cx;
+                ProfScope ps(p, 1);
+                if (st.params->custom->vt.process_device(st.custom_proc, &blk) != 0) { g_dev_err = std::string("custom node '") + st.params->custom->debug_name + "': process_device failed"; return FW_PROC_DEVICE_ERROR; }
+                break;
+            }
             default: g_dev_err = "generic lowering: unknown node kind"; return FW_PROC_DEVICE_ERROR;
         }
     }
@@ -1546,13 +1617,15 @@ static uint64_t bus_mask_from(const uint64_t* masks, uint32_t V, uint32_t n_out)
     return all;
 }
 
-int fw_processor_process_planar_device(fw_processor* p, const float* d_in, float* d_out, uint32_t n_in, uint32_t n_out, uint64_t frames, double, uint32_t) {
+int fw_processor_process_planar_device(fw_processor* p, const float* d_in, float* d_out, uint32_t n_in, uint32_t n_out, uint64_t frames, double stream_time_secs, uint32_t stream_status) {
     if (!p) return FW_PROC_BAD_ARGS;
+    p->cur_stream_time = stream_time_secs; p->cur_stream_status = stream_status;
     return proc_enqueue(p, d_in, d_out, n_in, n_out, frames);
 }
 
-int fw_processor_process_planar(fw_processor* p, const float* in, float* out, uint32_t n_in, uint32_t n_out, uint64_t frames, double, uint32_t, uint64_t* out_mask) {
+int fw_processor_process_planar(fw_processor* p, const float* in, float* out, uint32_t n_in, uint32_t n_out, uint64_t frames, double stream_time_secs, uint32_t stream_status, uint64_t* out_mask) {
     if (!p) return FW_PROC_BAD_ARGS;
+    p->cur_stream_time = stream_time_secs; p->cur_stream_status = stream_status;
     cudaSetDevice(p->device);
     const uint32_t V = p->num_voices;
     const size_t in_elems = (size_t)V * n_in * frames, out_elems = (size_t)(p->bus ? 1 : V) * n_out * frames;
@@ -1576,8 +1649,9 @@ int fw_processor_process_planar(fw_processor* p, const float* in, float* out, ui
     return rc;
 }
 
-int fw_processor_process_interleaved(fw_processor* p, const float* in, float* out, uint32_t n_in, uint32_t n_out, uint64_t frames, double, uint32_t) {
+int fw_processor_process_interleaved(fw_processor* p, const float* in, float* out, uint32_t n_in, uint32_t n_out, uint64_t frames, double stream_time_secs, uint32_t stream_status) {
     if (!p) return FW_PROC_BAD_ARGS;
+    p->cur_stream_time = stream_time_secs; p->cur_stream_status = stream_status;
     cudaSetDevice(p->device);
     const uint32_t V = p->num_voices, Vo = p->bus ? 1 : V;
     const size_t in_elems = (size_t)V * n_in * frames, out_elems = (size_t)Vo * n_out * frames;

@@ -191,6 +191,14 @@ class AudioGraph:
             raise ValueError(self._lib.ctx_last_error(self._ctx).decode())
         return NodeID(nid)
 
+    def add_custom_node(self, num_inputs, num_outputs, vtable_ptr, node_ptr):
+        """add_node with a user node behind the plugin vtable (include/fw_b200.h fw_node_vtable): `vtable_ptr` / `node_ptr` are
+        raw addresses produced by the plugin library; the graph takes the node over."""
+        nid = self._lib.graph_add_custom_node(self._ctx, num_inputs, num_outputs, vtable_ptr, node_ptr)
+        if nid == K.FW_ID_DANGLING:
+            raise ValueError("bad custom node")
+        return NodeID(nid)
+
     def _removed(self, fn, *args):
         cap = 4096
         buf = (C.c_uint64 * cap)()

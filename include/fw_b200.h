@@ -78,8 +78,9 @@ enum fw_node_kind {
     FW_NODE_CONV_REVERB = 9,    /* spec ours (a14)  u0 = ir_len, u1 = ir_channels, data = IR [ch][len] */
     FW_NODE_SAMPLER = 10,       /* basic_nodes/sampler.rs  f0 = percent_volume; 0 inputs, 1..64 outputs */
     FW_NODE_SVF = 11,           /* spec ours (a11)  u0 = num_stages (<= 8): trapezoidal state-variable filter cascade */
-    FW_NODE_RESAMPLER = 12      /* spec ours (a13)  polyphase-resampling sample player: u0 = phases P (power of two, <= 1024),
+    FW_NODE_RESAMPLER = 12,     /* spec ours (a13)  polyphase-resampling sample player: u0 = phases P (power of two, <= 1024),
                                    u1 = taps T (even, <= 64), data = Kaiser-windowed-sinc table [P][T]; 0 inputs, 1..64 outputs */
+    FW_NODE_CUSTOM = 13         /* a user node behind fw_node_vtable (graph_add_custom_node); never passed in a fw_node_desc */
 };
 /* SampleResource implementations (firewheel-core/src/sample_resource.rs:28-335). Interleaved data is [frame][ch],
  * planar ("Vec<Vec<T>>") is [ch][frame]. */
@@ -103,6 +104,72 @@ typedef struct fw_node_desc {
     const float* data;
     uint64_t data_len; /* floats */
 } fw_node_desc;
+
+/* ---- the plugin boundary: trait AudioNode / trait AudioNodeProcessor (firewheel-core/src/node.rs:6-53) as a C vtable ----------
+ * A Rust `Box<dyn AudioNode>` crosses the boundary as (vtable, node). The graph owns the node: `drop_node` runs when it is
+ * removed or the context is freed (Box drop). Differences forced by batching, all stated here:
+ *   * one node object serves all `num_voices` voices: `activate` is called ONCE per activation and returns ONE processor for
+ *     all voices (the reference: one processor per node, graph.rs:596-602);
+ *   * the processor has two forms of `process`. `process` is the reference's signature plus the voice index — the CPU oracle
+ *     calls it per voice and per block. `process_device` is what the product calls: all voices and all blocks of a call at
+ *     once, device pointers, on the processor's CUDA stream; the plugin enqueues its own kernels there and returns. A node
+ *     without `process_device` cannot run on the product: the graph then fails to compile with FW_COMPILE_UNSUPPORTED_ON_DEVICE
+ *     (there is no CPU fallback);
+ *   * ProcInfo::out_silence_mask is "an optional optimization hint" (node.rs:100-106). On the device the control plane runs ahead
+ *     of the samples, so a custom node DECLARES its hint as a rule in `info` instead of computing it from data; the oracle
+ *     checks that what `process` writes equals the declared rule. FW_OUT_SILENCE_NONE (the ProcInfo default) is always valid.
+ * Calls: debug_name / info / activate / deactivate / update / drop_* on the main thread (AudioNode is not Send); process* on the
+ * stream thread (AudioNodeProcessor: Send). `deactivate(node, processor)` is called where the reference calls
+ * `deactivate(Some(processor))`: activation roll-back (graph.rs:603-609) and a node removed while active (graph.rs:644-648);
+ * otherwise a processor is dropped with `drop_processor` (the reference never sets `activated`). */
+typedef struct fw_audio_node_info { /* AudioNodeInfo node.rs:57-79 */
+    uint32_t num_min_supported_inputs, num_max_supported_inputs;
+    uint32_t num_min_supported_outputs, num_max_supported_outputs;
+    uint32_t updates;            /* call `update` from ctx_update (graph.rs:691-697) */
+    uint32_t out_silence_rule;   /* fw_out_silence_rule */
+} fw_audio_node_info;
+enum fw_out_silence_rule {
+    FW_OUT_SILENCE_NONE = 0,               /* no output is ever flagged (ProcInfo default, node.rs:104-106) */
+    FW_OUT_SILENCE_PASSTHROUGH = 1,        /* output i flagged iff input i flagged (num_inputs == num_outputs; VolumeNode's rule, volume.rs:110) */
+    FW_OUT_SILENCE_ALL_IF_ALL_INPUTS = 2   /* every output flagged iff every input is flagged (SumNode's rule, sum.rs:52-56) */
+};
+typedef struct fw_proc_info { /* ProcInfo node.rs:94-118 */
+    uint64_t in_silence_mask;
+    uint64_t* out_silence_mask;  /* starts as 0 = NONE_SILENT (processor.rs:233) */
+    double stream_time_secs;
+    uint32_t stream_status;      /* fw_stream_status bits */
+    uint32_t reserved;
+    void* user_cx;               /* cx: &mut Box<dyn Any + Send> */
+} fw_proc_info;
+/* One process_device call = every voice and every block of one process_* call (frames = num_blocks blocks of block_frames,
+ * the last one possibly shorter). Channel i of voice v is the `frames` floats at inputs[i] + v * in_voice_stride; inputs and
+ * outputs never alias (schedule.rs:365-369). in_silence_masks[k * num_voices + v] is ProcInfo::in_silence_mask of voice v in
+ * block k. Everything the plugin launches must go to `cuda_stream`. */
+typedef struct fw_device_block {
+    uint32_t num_voices, num_inputs, num_outputs, block_frames, num_blocks, stream_status;
+    uint64_t frames, in_voice_stride, out_voice_stride;
+    const float* const* inputs;  /* host array of num_inputs device pointers */
+    float* const* outputs;       /* host array of num_outputs device pointers */
+    const uint64_t* in_silence_masks; /* device */
+    double stream_time_secs;
+    void* cuda_stream;           /* cudaStream_t */
+    void* user_cx;
+} fw_device_block;
+typedef struct fw_node_vtable {
+    const char* (*debug_name)(void* node);                                               /* node.rs:7 (static lifetime) */
+    void (*info)(void* node, fw_audio_node_info* out);                                   /* node.rs:9 */
+    /* node.rs:12-18. 0 => *out_processor set; nonzero => error text in err (Box<dyn Error>). `device` is the CUDA ordinal on the
+     * product and -1 on the oracle. */
+    int (*activate)(void* node, uint32_t sample_rate, uint32_t max_block_frames, uint32_t num_inputs, uint32_t num_outputs,
+                    uint32_t num_voices, int32_t device, void** out_processor, char* err, uint32_t err_cap);
+    void (*deactivate)(void* node, void* processor_or_null);                             /* node.rs:26; takes the processor over */
+    void (*update)(void* node);                                                          /* node.rs:32 */
+    void (*drop_node)(void* node);                                                       /* Box<dyn AudioNode> drop */
+    void (*process)(void* processor, uint32_t voice, uint64_t frames, const float* const* inputs, uint32_t num_inputs,
+                    float* const* outputs, uint32_t num_outputs, fw_proc_info* info);    /* node.rs:46-52, host slices */
+    int (*process_device)(void* processor, const fw_device_block* blk);                  /* 0 on success */
+    void (*drop_processor)(void* processor);                                             /* Box<dyn AudioNodeProcessor> drop */
+} fw_node_vtable;
 
 /* AddEdgeError (graph/error.rs:14-37) */
 enum fw_add_edge_error {
@@ -174,6 +241,10 @@ FW_EXPORT fw_node_id FW_FN(graph_in_node)(fw_ctx* ctx);                         
 FW_EXPORT fw_node_id FW_FN(graph_out_node)(fw_ctx* ctx);                            /* graph.rs:194 */
 FW_EXPORT fw_node_id FW_FN(graph_add_node)(fw_ctx* ctx, uint32_t num_inputs, uint32_t num_outputs,
                                            const fw_node_desc* desc);               /* graph.rs:201 */
+/* add_node with a user node (graph.rs:201: `node: impl Into<Box<dyn AudioNode>>`). The vtable is copied; `node` is owned by
+ * the graph from here on. Returns FW_ID_DANGLING (and drops the node) on bad arguments. */
+FW_EXPORT fw_node_id FW_FN(graph_add_custom_node)(fw_ctx* ctx, uint32_t num_inputs, uint32_t num_outputs,
+                                                  const fw_node_vtable* vtable, void* node);
 /* Ok(Vec<EdgeID>) => 0 and *n_removed edges written (up to cap); Err(()) => -1 */
 FW_EXPORT int FW_FN(graph_remove_node)(fw_ctx* ctx, fw_node_id node, fw_edge_id* removed, uint32_t cap,
                                        uint32_t* n_removed);                        /* graph.rs:268 */

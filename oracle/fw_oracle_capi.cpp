@@ -10,6 +10,8 @@
 #include "fw_oracle.hpp"
 
 #include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <thread>
 
 using namespace fwo;
@@ -54,7 +56,78 @@ static std::unique_ptr<AudioNode> make_node(const fw_node_desc* d) {
         default: return nullptr;
     }
 }
+// ---- the plugin boundary (include/fw_b200.h fw_node_vtable) on the oracle: the user node behind the restated traits -----------
+// One user node object serves all voices (the batching extension): the V per-voice graphs hold adapters that share it; the
+// first adapter to be activated calls the plugin's activate() once for all voices, each adapter's processor calls the
+// reference-shaped `process` with its voice index. The declared out_silence_rule is enforced: the product's control plane
+// relies on it, so a plugin whose `process` writes a different mask is a plugin bug and trips an assert here.
+struct CustomShared {
+    fw_node_vtable vt{}; void* node = nullptr; void* proc = nullptr; uint32_t num_voices = 1; fw_audio_node_info info{}; std::string name;
+    bool deactivate_on_release = false;
+    ~CustomShared() {
+        if (proc) { if (deactivate_on_release && vt.deactivate) vt.deactivate(node, proc); else if (vt.drop_processor) vt.drop_processor(proc); }
+        if (vt.drop_node) vt.drop_node(node);
+    }
+};
+struct CustomProcessor : AudioNodeProcessor {
+    std::shared_ptr<CustomShared> sh; uint32_t voice = 0;
+    void process(size_t frames, const std::vector<const float*>& inputs, const std::vector<float*>& outputs, ProcInfo info) override {
+        uint64_t out_mask = 0;
+        fw_proc_info pi{info.in_silence_mask.bits, &out_mask, info.stream_time_secs, info.stream_status, 0, info.cx};
+        sh->vt.process(sh->proc, voice, frames, inputs.data(), (uint32_t)inputs.size(), outputs.data(), (uint32_t)outputs.size(), &pi);
+        uint64_t want = 0;
+        const SilenceMask in = info.in_silence_mask;
+        if (sh->info.out_silence_rule == FW_OUT_SILENCE_PASSTHROUGH) want = in.bits & SilenceMask::new_all_silent(outputs.size()).bits;
+        else if (sh->info.out_silence_rule == FW_OUT_SILENCE_ALL_IF_ALL_INPUTS && !inputs.empty() && in.all_channels_silent(inputs.size())) want = SilenceMask::new_all_silent(outputs.size()).bits;
+        if (out_mask != want) { std::fprintf(stderr, "fw_oracle: custom node '%s' wrote out_silence_mask %llx, its declared rule gives %llx\n", sh->name.c_str(), (unsigned long long)out_mask, (unsigned long long)want); std::abort(); }
+        *info.out_silence_mask = SilenceMask{out_mask};
+    }
+};
+struct CustomAudioNode : AudioNode {
+    std::shared_ptr<CustomShared> sh; uint32_t voice = 0;
+    const char* debug_name() const override { return sh->name.c_str(); }
+    AudioNodeInfo info() const override {
+        AudioNodeInfo i; i.num_min_supported_inputs = sh->info.num_min_supported_inputs; i.num_max_supported_inputs = sh->info.num_max_supported_inputs;
+        i.num_min_supported_outputs = sh->info.num_min_supported_outputs; i.num_max_supported_outputs = sh->info.num_max_supported_outputs; i.updates = sh->info.updates != 0;
+        return i;
+    }
+    std::unique_ptr<AudioNodeProcessor> activate(uint32_t sample_rate, size_t max_block_frames, size_t num_inputs, size_t num_outputs, std::string* err) override {
+        if (!sh->vt.process) { if (err) *err = "custom node has no host `process`: the oracle cannot run it"; return nullptr; }
+        if (!sh->proc) {
+            char msg[256] = {0};
+            void* pr = nullptr;
+            if (sh->vt.activate(sh->node, sample_rate, (uint32_t)max_block_frames, (uint32_t)num_inputs, (uint32_t)num_outputs, sh->num_voices, -1, &pr, msg, sizeof(msg) - 1) != 0 || !pr) {
+                if (err) *err = msg[0] ? msg : "custom node activation failed";
+                return nullptr;
+            }
+            sh->proc = pr;
+        }
+        auto p = std::make_unique<CustomProcessor>(); p->sh = sh; p->voice = voice;
+        return p;
+    }
+    void deactivate(std::unique_ptr<AudioNodeProcessor> p) override { if (p) sh->deactivate_on_release = true; }  // the shared processor goes with the last adapter
+    void update() override { if (voice == 0 && sh->vt.update) sh->vt.update(sh->node); }
+};
+fw_node_id fwo_graph_add_custom_node(fw_ctx* c, uint32_t ni, uint32_t no, const fw_node_vtable* vt, void* node) {
+    if (!c || !vt || ni > 64 || no > 64 || !vt->debug_name || !vt->info || !vt->activate) {
+        if (vt && vt->drop_node) vt->drop_node(node);
+        if (c) c->last_error = "bad custom node (vtable needs debug_name, info and activate)";
+        return FW_ID_DANGLING;
+    }
+    auto sh = std::make_shared<CustomShared>();
+    sh->vt = *vt; sh->node = node; sh->num_voices = (uint32_t)c->voices.size();
+    const char* nm = vt->debug_name(node); sh->name = nm ? nm : "custom";
+    vt->info(node, &sh->info);
+    fw_node_id id = FW_ID_DANGLING;
+    for (size_t v = 0; v < c->voices.size(); ++v) {
+        auto n = std::make_unique<CustomAudioNode>(); n->sh = sh; n->voice = (uint32_t)v;
+        id = pack(c->voices[v]->graph.add_node(ni, no, std::move(n)).idx);
+    }
+    return id;
+}
+
 static uint32_t kind_of(const AudioNode* n) {
+    if (dynamic_cast<const CustomAudioNode*>(n)) return FW_NODE_CUSTOM;
     if (dynamic_cast<const VolumeNode*>(n)) return FW_NODE_VOLUME;
     if (dynamic_cast<const SumNode*>(n)) return FW_NODE_SUM;
     if (dynamic_cast<const MonoToStereoNode*>(n)) return FW_NODE_MONO_TO_STEREO;

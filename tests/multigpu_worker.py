@@ -1,5 +1,6 @@
-"""Run under torchrun (one rank per GPU): voices shard by rank, the master bus crosses ranks through the product's
-NCCL all-gather + fixed-order tree. Every rank checks its result bit-for-bit against the CPU oracle's tree of trees."""
+"""Run under torchrun (one rank per GPU; torch itself is not imported): voices shard by rank, the master bus crosses ranks
+through the product's NCCL all-gather + fixed-order tree. Every rank checks its result bit-for-bit against the CPU oracle's
+tree of trees; the communicator id travels through firewheel_b200.rendezvous, verdicts through the communicator itself."""
 import os
 import sys
 from pathlib import Path
@@ -11,17 +12,14 @@ sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "oracle")); sys.pat
 
 
 def main():
-    import torch
-    import torch.distributed as dist
     import firewheel_b200 as fw
     import pyoracle
     from conftest import synth
     from firewheel_b200 import PanNode, VolumeNode
-    from firewheel_b200.sharding import tree_sum, voice_range
+    from sharding import tree_sum, voice_range
     from helpers import chain, run_planar
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
-    torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from firewheel_b200 import rendezvous
     gpu, oracle = fw.load(), pyoracle.load()
     V = int(os.environ.get("FW_TEST_VOICES", "200"))
     T, F = 1024, 256
@@ -44,14 +42,7 @@ def main():
 
     lo, hi = voice_range(V, rank, world)
     cx, proc = build(gpu, lo, hi, device=local)
-    ids = [bytes(128)]
-    if rank == 0:
-        import ctypes
-        buf = (ctypes.c_uint8 * 128)()
-        assert gpu.comm_unique_id(buf) == 0, gpu.last_device_error()
-        ids = [bytes(buf)]
-    dist.broadcast_object_list(ids, src=0)
-    assert proc.comm_init(rank, world, ids[0]) == 0, gpu.last_device_error()
+    rendezvous.init_comm(gpu, proc, rank, world)
     out = np.zeros((2, T), np.float32)
     for _ in range(2):  # two calls: staging reuse
         rc, mask = proc.process_planar(np.ascontiguousarray(x[lo:hi]), out, 2, 2, T)
@@ -67,14 +58,13 @@ def main():
         oproc.free(); ocx.update(); ocx.free()
     ref = tree_sum(parts)
     ok = np.array_equal(out.view(np.uint32), ref.view(np.uint32))
-    flag = torch.tensor([1 if ok else 0], device="cuda")
-    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    all_ok = bool(proc.comm_allgather(np.array([1 if ok else 0], np.int64)).min() == 1)
+    proc.comm_allgather(np.zeros(1, np.int64))  # barrier: nobody tears its mailbox down while a peer still runs
     proc.free(); cx.update(); cx.free()
-    dist.barrier()
-    dist.destroy_process_group()
+    rendezvous.cleanup(rank)
     if rank == 0:
-        print("multigpu parity", "OK" if int(flag.item()) == 1 else "MISMATCH", f"world={world} voices={V}")
-    sys.exit(0 if int(flag.item()) == 1 else 1)
+        print("multigpu parity", "OK" if all_ok else "MISMATCH", f"world={world} voices={V}")
+    sys.exit(0 if all_ok else 1)
 
 
 if __name__ == "__main__":

@@ -18,7 +18,7 @@ def _worker(rank, world, V, port, out_dir):
     import pyoracle
     from conftest import synth
     from firewheel_b200 import PanNode, VolumeNode
-    from firewheel_b200.sharding import tree_sum, voice_range
+    from sharding import tree_sum, voice_range
     from helpers import chain, run_planar
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -60,7 +60,7 @@ def test_sharded_bus_over_gloo(tmp_path, V):
 
 
 def test_voice_range_partitions():
-    from firewheel_b200.sharding import voice_range
+    from sharding import voice_range
     for V in (1, 7, 8, 1024, 65536):
         for w in (1, 2, 3, 8):
             spans = [voice_range(V, r, w) for r in range(w)]
