@@ -33,7 +33,7 @@ class GraphConfig(C.Structure):
     _fields_ = [("num_graph_inputs", C.c_uint32), ("num_graph_outputs", C.c_uint32),
                 ("initial_node_capacity", C.c_uint32), ("initial_edge_capacity", C.c_uint32),
                 ("num_voices", C.c_uint32), ("master_bus", C.c_uint32), ("device", C.c_int32),
-                ("reserved", C.c_uint32)]
+                ("max_call_frames", C.c_uint32)]
 
 
 class NodeDesc(C.Structure):
@@ -99,6 +99,7 @@ SIGNATURES = {
     "schedule_len": (_u32, [_vp]),
     "schedule_num_buffers": (_u32, [_vp]),
     "schedule_node": (_i32, [_vp, _u32, C.POINTER(ScheduledNodeC)]),
+    "ctx_set_event_block": (None, [_vp, _u32]),
     "volume_set_percent_volume": (_i32, [_vp, _u64, _u32, _f32]),
     "volume_set_percent_volumes": (_i32, [_vp, _u64, _pf, _u32]),
     "pan_set_pan": (_i32, [_vp, _u64, _u32, _f32]),

@@ -6,22 +6,22 @@
 //                                       pushed to every sender's mailbox
 //     data[2][world][cap] f32         slot (q, s) = sender s's bus of an epoch with parity q, [rows][T]
 //
-// Per call (epoch e, parity q = e & 1), on every rank — everything below runs on the high-priority SIDE stream, so the whole
-// exchange of call e overlaps control + chain of call e + 1 on the main stream:
-//   K-push  the LAST level of the rank-local bus tree fused with the transfer: each thread finishes its tile of the tree
-//           (<= 16 partial buses left by the chain / combine kernels) and stores it straight into slot (q, me) of all
-//           `world` mailboxes — NVLink stores for the peers, a local store for itself — so no local copy of the bus is
-//           ever written and the transfer overlaps the tree tile by tile. The last CTA to finish publishes
-//           ready[q][me] = e in every mailbox (st.release.sys).
-//   K-wait  one warp polls the local ready[q][*] words until all senders published e.
-//   K-recv  the top log2(world) levels of the same balanced tree in rank order over the local slots, written to the
-//           caller's bus buffer — every rank performs the identical additions, so all ranks hold the same bits (an
-//           NCCL all-reduce gives no such guarantee). The last CTA acknowledges: ack[q][me] = e in every mailbox.
-// K-push of epoch e + 2 reuses parity q: it first polls the local ack[q][*] words for e. Senders never wait on anything
-// but acknowledgements of an epoch two calls back, and receivers only on pushes that precede them in every rank's stream
-// order, so the protocol cannot deadlock; a poll that exceeds ~2 s raises the plan's error word instead of hanging the GPU.
-// Main and side stream hand over through device words, not events (K-signal below): an event record between two kernels
-// of the main stream would cut its programmatic-dependent-launch chain and cost ~10 us per call.
+// Per call (epoch e, parity q = e & 1), on every rank:
+//   K-push  (MAIN stream, programmatic dependent launch behind the chain / combine kernels) the LAST level of the rank-local bus
+//           tree fused with the transfer: each thread finishes its tile of the tree (<= 16 partial buses) and stores it straight
+//           into slot (q, me) of all `world` mailboxes — NVLink stores for the peers, a local store for itself — so no local copy
+//           of the bus is ever written and the transfer overlaps the tree tile by tile. The last CTA to finish publishes
+//           ready[q][me] = e in every mailbox (st.release.sys). No event is recorded on the main stream: the next call's control
+//           kernel follows K-push like any other kernel of the chain.
+//   K-wait  (SIDE stream, high priority) one warp polls the local ready[q][*] words until all senders published e.
+//   K-recv  (SIDE stream) the top log2(world) levels of the same balanced tree in rank order over the local slots, written to the
+//           caller's bus buffer — every rank performs the identical additions, so all ranks hold the same bits (an NCCL
+//           all-reduce gives no such guarantee). The last CTA acknowledges: ack[q][me] = e in every mailbox.
+// The side stream depends on the main stream only through the mailbox words, so the exchange of call e overlaps control + chain
+// of call e + 1 with no stream-level hand-over at all. K-push of epoch e + 2 reuses parity q: it first polls the local ack[q][*]
+// words for e. Senders never wait on anything but acknowledgements of an epoch two calls back, and receivers only on pushes that
+// precede them in every rank's stream order, so the protocol cannot deadlock; a poll that exceeds ~2 s raises the plan's error
+// word instead of hanging the GPU.
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -77,9 +77,11 @@ __device__ __forceinline__ void tree16(float (&p)[16][VEC], uint32_t n) {
 template <int VEC>
 __global__ void __launch_bounds__(128) bus_push_kernel(const __grid_constant__ BusPushArgs a) {
     __shared__ bool s_last;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // main stream: the next call's control kernel may start
+    asm volatile("griddepcontrol.wait;" ::: "memory");               // the partial buses come from the preceding kernel
     const uint32_t q = a.epoch & 1u;
     if (threadIdx.x < a.world) {  // slot (q, me) of every mailbox must have been consumed (epoch - 2)
-        if (a.epoch > 2 && !poll_at_least(a.ack_local + q * 16 + threadIdx.x, a.epoch - 2)) *a.error = 2;
+        if (a.epoch > 2 && !poll_at_least(a.ack_local + q * 16 + threadIdx.x, a.epoch - 2)) *a.error = a.error_value;
     }
     __syncthreads();
     const uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) * VEC, row = blockIdx.y, T = a.T;
@@ -107,22 +109,8 @@ __global__ void __launch_bounds__(128) bus_push_kernel(const __grid_constant__ B
 }
 
 // polls words[0..count) until each is >= epoch
-__global__ void __launch_bounds__(32) bus_wait_kernel(const uint32_t* words, uint32_t count, uint32_t epoch, uint32_t* error) {
-    if (threadIdx.x < count && !poll_at_least(words + threadIdx.x, epoch)) *error = 2;
-}
-
-// K-signal (main stream, launched with programmatic dependency so that the stream's PDL chain stays intact — an event
-// record between two kernels would serialise them): runs once the preceding kernel (the chain / last local combine of
-// this epoch) has completed, publishes that fact to the side stream's poller, and holds the main stream until K-push of
-// the previous epoch has released the partial buffers the NEXT call overwrites.
-__global__ void __launch_bounds__(32) bus_signal_kernel(uint32_t* chain_done, const uint32_t* push_done, uint32_t epoch, uint32_t* error) {
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (threadIdx.x == 0) {
-        __threadfence();
-        st_release_sys(chain_done, epoch);
-        if (epoch > 1 && !poll_at_least(push_done, epoch - 1)) *error = 2;
-    }
+__global__ void __launch_bounds__(32) bus_wait_kernel(const uint32_t* words, uint32_t count, uint32_t epoch, uint32_t* error, uint32_t error_value) {
+    if (threadIdx.x < count && !poll_at_least(words + threadIdx.x, epoch)) *error = error_value;
 }
 
 template <int VEC>
@@ -140,7 +128,7 @@ __global__ void __launch_bounds__(128) bus_recv_kernel(const __grid_constant__ B
             if ((uint32_t)j < a.world) V4<VEC>::load_cg(a.data_local + ((size_t)q * a.world + j) * a.cap + (size_t)row * T + t, p[j]);
         }
         tree16<VEC>(p, a.world);
-        V4<VEC>::store(a.out + (size_t)row * T + t, p[0]);
+        V4<VEC>::store(a.out + (size_t)row * a.out_pitch + t, p[0]);
     }
     __threadfence_system();
     __syncthreads();
@@ -160,24 +148,21 @@ inline bool vec4_ok(uint32_t T, uint32_t cap, const void* p0, const void* p1) {
 }  // namespace
 
 cudaError_t launch_bus_push(const BusPushArgs& a, cudaStream_t st) {
-    if (vec4_ok(a.T, a.cap, a.pin, a.data[0])) bus_push_kernel<4><<<dim3((a.T / 4 + 127) / 128, a.rows), 128, 0, st>>>(a);
-    else bus_push_kernel<1><<<dim3((a.T + 127) / 128, a.rows), 128, 0, st>>>(a);
-    return cudaGetLastError();
-}
-cudaError_t launch_bus_wait(const uint32_t* words, uint32_t count, uint32_t epoch, uint32_t* error, cudaStream_t st) {
-    bus_wait_kernel<<<1, 32, 0, st>>>(words, count, epoch, error);
-    return cudaGetLastError();
-}
-cudaError_t launch_bus_signal(uint32_t* chain_done, const uint32_t* push_done, uint32_t epoch, uint32_t* error, cudaStream_t st) {
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(1); cfg.blockDim = dim3(32); cfg.stream = st;
+    cfg.blockDim = dim3(128); cfg.stream = st;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, bus_signal_kernel, chain_done, push_done, epoch, error);
+    if (vec4_ok(a.T, a.cap, a.pin, a.data[0])) { cfg.gridDim = dim3((a.T / 4 + 127) / 128, a.rows); return cudaLaunchKernelEx(&cfg, bus_push_kernel<4>, a); }
+    cfg.gridDim = dim3((a.T + 127) / 128, a.rows);
+    return cudaLaunchKernelEx(&cfg, bus_push_kernel<1>, a);
+}
+cudaError_t launch_bus_wait(const uint32_t* words, uint32_t count, uint32_t epoch, uint32_t* error, uint32_t error_value, cudaStream_t st) {
+    bus_wait_kernel<<<1, 32, 0, st>>>(words, count, epoch, error, error_value);
+    return cudaGetLastError();
 }
 cudaError_t launch_bus_recv(const BusRecvArgs& a, cudaStream_t st) {
-    if (vec4_ok(a.T, a.cap, a.out, a.data_local)) bus_recv_kernel<4><<<dim3((a.T / 4 + 127) / 128, a.rows), 128, 0, st>>>(a);
+    if (vec4_ok(a.T, a.cap | a.out_pitch, a.out, a.data_local)) bus_recv_kernel<4><<<dim3((a.T / 4 + 127) / 128, a.rows), 128, 0, st>>>(a);
     else bus_recv_kernel<1><<<dim3((a.T + 127) / 128, a.rows), 128, 0, st>>>(a);
     return cudaGetLastError();
 }

@@ -11,6 +11,7 @@
 // are tracked with plain reference counts. The compiled result additionally carries what
 // the device lowering needs (per-port producer links).
 #pragma once
+#include <atomic>
 #include <cstdint>
 #include <cstring>
 #include <deque>
@@ -81,11 +82,29 @@ struct CustomNode {
     ~CustomNode() { if (vt.drop_node) vt.drop_node(node); }
 };
 
+// ---- main thread -> stream side commands (wait-free SPSC ring, see Channels in runtime.cu) ----------------------------
+// The reference's per-node message rings (sampler.rs:14,205-208) and relaxed-atomic parameter stores (volume.rs:29-32), with a
+// block timestamp: `block` is the offset, in blocks from the start of the next process_* call, at which the command takes
+// effect — what the reference's per-block polling (processor.rs:214, volume.rs:92, sampler.rs:331) gives a host that calls
+// once per block. The stream side splits the call there.
+struct NodeParams;
+enum CmdKind : uint32_t {
+    CMD_SAMPLER = 0,   // a = SmpMsgKind, x / y / b = payload (NodeToProcessorMsg sampler.rs:21-28)
+    CMD_TARGET = 1,    // a = smoothed-parameter index of the node (0: raw_gain / gain_l, 1: gain_r), f[0] = value
+    CMD_BIQUAD = 2,    // a = stage, f[0..4] = {b0, b1, b2, a1, a2}
+    CMD_SVF = 3,       // a = stage, f[0..5] = {a1, a2, a3, m0, m1, m2}
+    CMD_RS_SET = 4,    // b = resource, x = step (Q32.32), a = flags (bit0 playing, bit1 loop)
+    CMD_RS_SEEK = 5    // x = position in frames
+};
+struct Cmd { uint32_t kind, block, voice /* or FW_ALL_VOICES */, a, b, pad; uint64_t x, y; float f[6]; const NodeParams* node; };
+
 // ---- node parameters (main-thread side; the stream side snapshots them at call start) -------
 struct NodeParams {
     uint32_t kind = FW_NODE_DUMMY;
     uint32_t num_voices = 1;
-    uint64_t version = 1;  // bumped on every change; the device mirror re-uploads when it differs
+    // Bumped (release) after every change of the arrays below; the stream side reads it (acquire) before copying them, so a new
+    // version is never observed with older values (the relaxed atomics of volume.rs:29-32, batched over voices).
+    std::atomic<uint64_t> version{1};
     std::shared_ptr<CustomNode> custom;  // kind == FW_NODE_CUSTOM
     // volume (volume.rs:8-34)
     std::vector<float> percent, raw_gain;
@@ -103,17 +122,14 @@ struct NodeParams {
     std::vector<float> ir;  // [ch][len] f32 (rounded to bf16 on the device side)
     // svf (spec ours): [voice][stage][6] = {a1, a2, a3, m0, m1, m2}; num_stages above
     std::vector<float> svf_coeffs;
-    // polyphase resampler (spec ours): table [phases][taps] + per-voice transport (guarded by smp_mu)
+    // polyphase resampler (spec ours): table [phases][taps]; the per-voice transport travels as commands
     uint32_t rs_phases = 0, rs_taps = 0; std::vector<float> rs_table;
-    std::vector<uint32_t> rs_res, rs_flags; std::vector<uint64_t> rs_step, rs_seek; std::vector<uint8_t> rs_seek_flag; bool rs_seek_any = false;
-    // sampler (sampler.rs:46-181): node-side state per voice + the node -> processor message ring. `percent` / `raw_gain`
-    // above double as the sampler's volume (sampler.rs:49-50). The stream side drains `smp_msgs` at call start.
-    struct SamplerMsg { uint32_t voice, kind, a; uint64_t x, y; };
+    // sampler (sampler.rs:46-181): node-side state per voice (main thread only). `percent` / `raw_gain` above double as the
+    // sampler's volume (sampler.rs:49-50). Messages travel through the context's command ring.
     bool smp_active = false;               // ActiveState is Some (sampler.rs:198-215)
     std::vector<uint8_t> smp_playing;      // SamplerNode::playing (sampler.rs:51)
-    std::mutex smp_mu;                     // guards the two members below (main thread pushes, stream thread drains)
-    std::vector<SamplerMsg> smp_msgs;      // push order
-    std::vector<uint16_t> smp_pending;     // queued messages per voice (ring capacity 128, sampler.rs:14)
+    std::vector<uint16_t> smp_pending;     // messages queued per voice since the stream side last drained (ring capacity 128, sampler.rs:14)
+    std::vector<uint32_t> smp_pending_epoch;  // drain epoch `smp_pending[v]` was counted in
 };
 
 const char* node_debug_name(uint32_t kind);

@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(128) control_kernel(const __grid_constant__ Co
             }
             steady_mode = false; steady = 0xffffffffu; ++slot;
         }
-        if (slot >= a.rec.kt_max) { *a.rec.error = 1; break; }
+        if (slot >= a.rec.kt_max) { *a.rec.error = a.err_value; break; }
         bool changed = false;  // smoother / sampler transport state moved during this block
         const uint64_t flags0 = flags;  // the block is a pure function of (flags, that state): equal at both ends => it replays
         uint32_t modes = 0;
@@ -598,7 +598,7 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) chain_kernel(ChainArg
 #pragma unroll
                         for (int i = 0; i < VEC; ++i) p[w][i] = __fadd_rn(p[w][i], p[w + step][i]);
                     }
-            VecT<VEC>::store(a.out + ((size_t)blockIdx.y * c_out + c) * T + t, p[0]);
+            VecT<VEC>::store(a.out + ((size_t)blockIdx.y * c_out + c) * (a.bus_pitch ? a.bus_pitch : T) + t, p[0]);
         }
     }
 }
@@ -761,7 +761,7 @@ __global__ void __launch_bounds__(128) resampler_kernel(const __grid_constant__ 
 
 // K-combine: radix-16 levels of the same balanced tree over partial buses [n_in][rows][T] -> [ceil(n_in/16)][rows][T].
 template <int VEC>
-__global__ void __launch_bounds__(128) combine_kernel(const float* __restrict__ pin, float* __restrict__ pout, uint32_t n_in, uint32_t rows, uint32_t T) {
+__global__ void __launch_bounds__(128) combine_kernel(const float* __restrict__ pin, float* __restrict__ pout, uint32_t n_in, uint32_t rows, uint32_t T, uint32_t out_pitch) {
     pdl_launch_dependents();
     pdl_wait();  // the partial buses come from the preceding kernel
     const uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
@@ -781,7 +781,7 @@ __global__ void __launch_bounds__(128) combine_kernel(const float* __restrict__ 
 #pragma unroll
         for (int j = 0; j + step < 16; j += 2 * step) FW_COMB1(j, j + step, p0 + j + step)
 #undef FW_COMB1
-    VecT<VEC>::store(pout + ((size_t)g * rows + row) * T + t, p[0]);
+    VecT<VEC>::store(pout + ((size_t)g * rows + row) * out_pitch + t, p[0]);
 }
 
 // =============================================================================================
@@ -808,6 +808,20 @@ __global__ void interleave_kernel(const float* __restrict__ planar, float* __res
         if (C == 2) silent = (m & 3ull) == 3ull;            // interleave_stereo util.rs:129-134
         else silent = c < 64 && ((m >> c) & 1ull);           // interleave util.rs:103-107
         inter[i] = (silent && last_block) ? 0.0f : planar[(v * C + c) * T + f];
+    }
+}
+
+// Ordered small stores (timed parameter commands, plan.hpp PokeArgs): entries are applied one after the other.
+__global__ void __launch_bounds__(128) poke_kernel(const __grid_constant__ PokeArgs a) {
+    pdl_launch_dependents();
+    pdl_wait();
+    for (uint32_t i = 0; i < a.n; ++i) {
+        uint8_t* base = static_cast<uint8_t*>(a.ptr[i]);
+        for (uint32_t j = threadIdx.x; j < a.count[i]; j += blockDim.x) {
+            if (a.bytes[i] == 8) *reinterpret_cast<uint64_t*>(base + (size_t)j * a.stride_bytes[i]) = a.val[i];
+            else *reinterpret_cast<uint32_t*>(base + (size_t)j * a.stride_bytes[i]) = (uint32_t)a.val[i];
+        }
+        __syncthreads();
     }
 }
 
@@ -841,8 +855,7 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, c
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
-    static const bool no_pdl = getenv("FW_NO_PDL") != nullptr;  // A/B knob
-    cfg.attrs = attr; cfg.numAttrs = no_pdl ? 0 : 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
@@ -851,11 +864,6 @@ cudaError_t launch_control(const ControlArgs& a, cudaStream_t st) {
     return launch_pdl(control_kernel, dim3(blocks), dim3(threads), st, a);
 }
 
-static int chain_variant() {  // A/B knob for tuning runs; the default is what ships
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("FW_CHAIN_VARIANT"); v = e ? atoi(e) : 0; }
-    return v;
-}
 template <int VEC, int CIN, int VPW, int WARPS, int MINB>
 static cudaError_t launch_chain_v(const ChainArgs& a, bool bus, cudaStream_t st) {
     dim3 grid((a.frames + 32 * VEC - 1) / (32 * VEC), (a.num_voices + kVPC - 1) / kVPC);
@@ -864,29 +872,24 @@ static cudaError_t launch_chain_v(const ChainArgs& a, bool bus, cudaStream_t st)
 }
 template <int VEC, int CIN>
 static cudaError_t launch_chain_t(const ChainArgs& a, bool bus, cudaStream_t st) {
-    if (VEC == 4) {
-        switch (chain_variant()) {
-            case 1: return launch_chain_v<VEC, CIN, 8, 8, 2>(a, bus, st);
-            case 2: return launch_chain_v<VEC, CIN, 8, 8, 3>(a, bus, st);
-            default: return launch_chain_v<VEC, CIN, 4, 16, 2>(a, bus, st);  // 64 regs, 2 x 512 threads per SM
-        }
-    }
+    if (VEC == 4) return launch_chain_v<VEC, CIN, 4, 16, 2>(a, bus, st);  // 64 regs, 2 x 512 threads per SM (8/8/2 and 8/8/3 measured slower)
     return launch_chain_v<VEC, CIN, 8, 8, 2>(a, bus, st);
 }
 cudaError_t launch_chain(const ChainArgs& a, bool bus, cudaStream_t st) {
     const uintptr_t al = reinterpret_cast<uintptr_t>(a.in_ch[0]) | reinterpret_cast<uintptr_t>(a.in_ch[1]) | reinterpret_cast<uintptr_t>(a.out_ch[0]) |
-                         reinterpret_cast<uintptr_t>(a.out_ch[1]) | reinterpret_cast<uintptr_t>(a.out) | (uintptr_t)((a.in_vstride | a.out_vstride) * 4);
+                         reinterpret_cast<uintptr_t>(a.out_ch[1]) | reinterpret_cast<uintptr_t>(a.out) | (uintptr_t)((a.in_vstride | a.out_vstride | a.bus_pitch) * 4);
     const bool vec4 = (a.frames % 4 == 0) && (a.block_frames % 4 == 0) && (al % 16 == 0);
     if (a.prog.c_in == 2) return vec4 ? launch_chain_t<4, 2>(a, bus, st) : launch_chain_t<1, 2>(a, bus, st);
     return vec4 ? launch_chain_t<4, 1>(a, bus, st) : launch_chain_t<1, 1>(a, bus, st);
 }
 uint32_t chain_voice_groups(uint32_t num_voices) { return (num_voices + kVPC - 1) / kVPC; }
 
-cudaError_t launch_combine(const float* pin, float* pout, uint32_t n_in, uint32_t rows, uint32_t T, cudaStream_t st) {
-    const bool vec4 = (T % 4 == 0) && ((reinterpret_cast<uintptr_t>(pin) | reinterpret_cast<uintptr_t>(pout)) % 16 == 0);
+cudaError_t launch_combine(const float* pin, float* pout, uint32_t n_in, uint32_t rows, uint32_t T, cudaStream_t st, uint32_t out_pitch) {
+    if (out_pitch == 0) out_pitch = T;
+    const bool vec4 = (T % 4 == 0) && (out_pitch % 4 == 0) && ((reinterpret_cast<uintptr_t>(pin) | reinterpret_cast<uintptr_t>(pout)) % 16 == 0);
     const uint32_t n_out = (n_in + 15) / 16;
-    if (vec4) return launch_pdl(combine_kernel<4>, dim3((T / 4 + 127) / 128, rows, n_out), dim3(128), st, pin, pout, n_in, rows, T);
-    return launch_pdl(combine_kernel<1>, dim3((T + 127) / 128, rows, n_out), dim3(128), st, pin, pout, n_in, rows, T);
+    if (vec4) return launch_pdl(combine_kernel<4>, dim3((T / 4 + 127) / 128, rows, n_out), dim3(128), st, pin, pout, n_in, rows, T, out_pitch);
+    return launch_pdl(combine_kernel<1>, dim3((T + 127) / 128, rows, n_out), dim3(128), st, pin, pout, n_in, rows, T, out_pitch);
 }
 cudaError_t launch_sum(const SumArgs& a, cudaStream_t st) {
     uintptr_t al = reinterpret_cast<uintptr_t>(a.out);
@@ -922,6 +925,10 @@ cudaError_t launch_silence_fix(const SilenceFixArgs& a, cudaStream_t st) {
 cudaError_t launch_expand_masks(const Records& rec, uint32_t mask_slot, uint32_t V, uint32_t n_blocks, uint64_t* out, cudaStream_t st) {
     if (V == 0 || n_blocks == 0) return cudaSuccess;
     return launch_pdl(expand_masks_kernel, dim3((V + 127) / 128, n_blocks), dim3(128), st, rec, mask_slot, V, n_blocks, out);
+}
+cudaError_t launch_poke(const PokeArgs& a, cudaStream_t st) {
+    if (a.n == 0) return cudaSuccess;
+    return launch_pdl(poke_kernel, dim3(1), dim3(128), st, a);
 }
 cudaError_t launch_deinterleave(const float* inter, float* planar, uint32_t V, uint32_t C, uint32_t T, cudaStream_t st) {
     const size_t n = (size_t)V * C * T; if (n == 0) return cudaSuccess;

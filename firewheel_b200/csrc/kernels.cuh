@@ -19,15 +19,15 @@ cudaError_t launch_resampler(const ResamplerArgs& a, uint64_t* pos, cudaStream_t
 cudaError_t launch_sampler(const SamplerArgs& a, cudaStream_t st);
 cudaError_t launch_silence_fix(const SilenceFixArgs& a, cudaStream_t st);
 cudaError_t launch_expand_masks(const Records& rec, uint32_t mask_slot, uint32_t V, uint32_t n_blocks, uint64_t* out, cudaStream_t st);
-cudaError_t launch_combine(const float* pin, float* pout, uint32_t n_in, uint32_t rows, uint32_t T, cudaStream_t st);
+cudaError_t launch_combine(const float* pin, float* pout, uint32_t n_in, uint32_t rows, uint32_t T, cudaStream_t st, uint32_t out_pitch = 0);
 cudaError_t launch_deinterleave(const float* inter, float* planar, uint32_t V, uint32_t C, uint32_t T, cudaStream_t st);
 cudaError_t launch_interleave(const float* planar, float* inter, const uint64_t* masks, uint32_t V, uint32_t C, uint32_t T,
                               uint32_t block_frames, cudaStream_t st);
 cudaError_t launch_fill(float* p, size_t n, float val, cudaStream_t st);
 cudaError_t launch_bus_mask(const uint64_t* gout_mask, uint32_t V, uint32_t n_out, uint64_t* bus_mask, cudaStream_t st);
 cudaError_t launch_bus_push(const BusPushArgs& a, cudaStream_t st);
-cudaError_t launch_bus_wait(const uint32_t* words, uint32_t count, uint32_t epoch, uint32_t* error, cudaStream_t st);
-cudaError_t launch_bus_signal(uint32_t* chain_done, const uint32_t* push_done, uint32_t epoch, uint32_t* error, cudaStream_t st);
+cudaError_t launch_bus_wait(const uint32_t* words, uint32_t count, uint32_t epoch, uint32_t* error, uint32_t error_value, cudaStream_t st);
+cudaError_t launch_poke(const PokeArgs& a, cudaStream_t st);
 cudaError_t launch_bus_recv(const BusRecvArgs& a, cudaStream_t st);
 cudaError_t launch_temporal(const TemporalArgs& a, cudaStream_t st);
 bool temporal_fast_path(const TemporalArgs& a);

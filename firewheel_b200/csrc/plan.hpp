@@ -95,12 +95,16 @@ struct SamplerArgs {
     Records rec;
 };
 
+// Ordered small stores into device arrays (timed parameter commands): entry i writes `count` elements of 4 or 8 bytes.
+struct PokeArgs { void* ptr[16]; uint64_t val[16]; uint32_t count[16], stride_bytes[16]; uint8_t bytes[16]; uint32_t n; };
+
 struct ControlArgs {
     CtlTables tables;      // by value: read through the constant bank (2.8 KB of kernel parameters)
     Records rec;
     uint64_t* flags;       // [V] buffer_silence_flags bitset (schedule.rs:170), persists across calls
     uint32_t num_voices, frames, block_frames;
     float a, b, eps;       // smoother.rs:99-100,22
+    uint32_t err_value;    // written to *rec.error on a record-budget overflow: (call epoch << 4) | 1
 };
 
 struct ChainArgs {
@@ -108,7 +112,8 @@ struct ChainArgs {
     // (in_ch[c] = base + c*T, in_vstride = c_in*T); the generic lowering reads pool buffers [V][T] (in_vstride = T).
     const float* in_ch[2]; float* out_ch[2];
     uint64_t in_vstride, out_vstride;
-    float* out;            // bus variant only: partial bus [G][c_out][T]
+    float* out;            // bus variant only: partial bus [G][c_out][bus_pitch]
+    uint32_t bus_pitch, pad3;  // floats between the rows of `out` (0: frames); the caller's bus is a column window of longer rows when a call is chunked
     uint32_t num_voices, frames, block_frames, zero_first_block;
     uint32_t in_from_prev_kernel, pad0, pad1, pad2;  // `in` is produced by the preceding kernel: wait before the loads
     Records rec;
@@ -161,11 +166,11 @@ struct SilenceFixArgs {
 struct BusPushArgs {
     const float* pin; uint32_t n_in, rows, T;   // partial buses [n_in <= 16][rows][T] of this rank
     float* data[16]; uint32_t* ready[16];       // per destination rank: slot storage and ready words
-    const uint32_t* ack_local; uint32_t* counter; uint32_t* push_done; uint32_t* error;
+    const uint32_t* ack_local; uint32_t* counter; uint32_t* push_done; uint32_t* error; uint32_t error_value, pad_;
     uint32_t world, me, epoch, cap;             // cap: floats per slot
 };
 struct BusRecvArgs {
-    const float* data_local; float* out; uint32_t rows, T;
+    const float* data_local; float* out; uint32_t rows, T, out_pitch;  // out rows at out_pitch floats (the caller's bus)
     uint32_t* ack[16]; uint32_t* counter;
     uint32_t world, me, epoch, cap;
 };

@@ -67,6 +67,24 @@ template <class T, size_t N = 16> struct Spsc {
     }
 };
 
+// same, capacity chosen at run time (the command ring: sized from the voice count at activate)
+template <class T> struct DynSpsc {
+    std::unique_ptr<T[]> slots; size_t n = 0;  // n = capacity + 1
+    std::atomic<size_t> head{0}, tail{0};
+    explicit DynSpsc(size_t capacity) : slots(new T[capacity + 1]), n(capacity + 1) {}
+    size_t capacity() const { return n - 1; }
+    bool push(const T& v) {
+        const size_t t = tail.load(std::memory_order_relaxed), nx = t + 1 == n ? 0 : t + 1;
+        if (nx == head.load(std::memory_order_acquire)) return false;
+        slots[t] = v; tail.store(nx, std::memory_order_release); return true;
+    }
+    bool pop(T* out) {
+        const size_t h = head.load(std::memory_order_relaxed);
+        if (h == tail.load(std::memory_order_acquire)) return false;
+        *out = slots[h]; head.store(h + 1 == n ? 0 : h + 1, std::memory_order_release); return true;
+    }
+};
+
 // Sample resources of one context ("Arc<dyn SampleResource>", sample_resource.rs): uploaded once, referenced by handle.
 struct ResTable {
     int device = 0; std::mutex mu;
@@ -109,18 +127,14 @@ struct NodeDeviceState {
     static constexpr uint32_t kReverbMaxFrames = 65536;  // longest call the history buffers are sized for
     // polyphase resampler: table + per-voice transport mirrors + the device-resident Q32.32 position
     float* d_rs_table = nullptr; uint32_t* d_rs_res = nullptr; uint32_t* d_rs_flags = nullptr; uint64_t* d_rs_step = nullptr;
-    uint64_t* d_rs_seek = nullptr; uint32_t* d_rs_seek_flag = nullptr; uint64_t* d_rs_pos = nullptr; bool rs_seek_uploaded = false;
-    std::vector<uint32_t> h_rs_seek_flag;
+    uint64_t* d_rs_pos = nullptr;
     // sampler: per-voice SamplerProcessor state (sampler.rs:283-297) + this call's messages / resource table / block records
     std::shared_ptr<ResTable> res_table;
     uint32_t* d_playing = nullptr; uint64_t* d_playhead = nullptr; uint32_t* d_loop_flags = nullptr; uint64_t* d_loop_start = nullptr; uint64_t* d_loop_end = nullptr; uint32_t* d_res = nullptr;
-    SamplerMsgDev* d_msgs = nullptr; size_t cap_msgs = 0; uint32_t* d_msg_off = nullptr; uint32_t cur_n_msgs = 0;
+    SamplerMsgDev* d_msgs = nullptr; size_t cap_msgs = 0; uint32_t* d_msg_off = nullptr; uint32_t cur_n_msgs = 0;  // this chunk's messages on the device
     const ResDesc* cur_tab = nullptr; uint32_t cur_n_res = 0;
-    SmpRec* d_srec = nullptr; size_t cap_srec = 0;
-    std::vector<SamplerMsgDev> h_msgs; std::vector<uint32_t> h_off; std::vector<NodeParams::SamplerMsg> h_drain;
     // custom node (plugin vtable): the processor returned by activate() and the dense per-(block, voice) input masks handed to it
     void* custom_proc = nullptr; bool custom_deactivate = false;  // true: released through deactivate(node, processor) (graph.rs:603-609,644-648)
-    uint64_t* d_custom_masks = nullptr; size_t cap_custom_masks = 0;
     ~NodeDeviceState() {
         cudaSetDevice(device);
         if (params && params->custom && custom_proc) {  // main thread: plans are released in ctx_drain / ctx_free
@@ -128,12 +142,11 @@ struct NodeDeviceState {
             if (custom_deactivate && vt.deactivate) vt.deactivate(params->custom->node, custom_proc);
             else if (vt.drop_processor) vt.drop_processor(custom_proc);
         }
-        cudaFree(d_custom_masks);
         for (int i = 0; i < 2; ++i) { cudaFree(d_target[i]); cudaFree(sm_input[i]); cudaFree(sm_last[i]); cudaFree(sm_status[i]); }
         cudaFree(d_coeffs); cudaFree(d_state); cudaFree(d_ring); cudaFree(d_bt); cudaFree(d_xh[0]); cudaFree(d_xh[1]);
         cudaFree(d_playing); cudaFree(d_playhead); cudaFree(d_loop_flags); cudaFree(d_loop_start); cudaFree(d_loop_end); cudaFree(d_res);
-        cudaFree(d_msgs); cudaFree(d_msg_off); cudaFree(d_srec);
-        cudaFree(d_rs_table); cudaFree(d_rs_res); cudaFree(d_rs_flags); cudaFree(d_rs_step); cudaFree(d_rs_seek); cudaFree(d_rs_seek_flag); cudaFree(d_rs_pos);
+        cudaFree(d_msgs); cudaFree(d_msg_off); cudaFreeHost(h_msgs); cudaFreeHost(h_off); cudaFreeHost(h_cnt); if (ev_staged) cudaEventDestroy(ev_staged);
+        cudaFree(d_rs_table); cudaFree(d_rs_res); cudaFree(d_rs_flags); cudaFree(d_rs_step); cudaFree(d_rs_pos);
     }
     const std::vector<float>& host_target(int i) const { return (kind == FW_NODE_VOLUME || kind == FW_NODE_SAMPLER) ? params->raw_gain : (i == 0 ? params->gain_l : params->gain_r); }
     // ParamSmoother::new(val): input = last_output = val, Inactive (smoother.rs:93-112; volume.rs:67-75)
@@ -177,70 +190,58 @@ struct NodeDeviceState {
         if (kind == FW_NODE_RESAMPLER) {
             d_rs_table = dev_alloc<float>(params->rs_table.size(), false);
             d_rs_res = dev_alloc<uint32_t>(V); d_rs_flags = dev_alloc<uint32_t>(V); d_rs_step = dev_alloc<uint64_t>(V);
-            d_rs_seek = dev_alloc<uint64_t>(V); d_rs_seek_flag = dev_alloc<uint32_t>(V); d_rs_pos = dev_alloc<uint64_t>(V);
-            if (!d_rs_table || !d_rs_res || !d_rs_flags || !d_rs_step || !d_rs_seek || !d_rs_seek_flag || !d_rs_pos) return false;
+            d_rs_pos = dev_alloc<uint64_t>(V);
+            if (!d_rs_table || !d_rs_res || !d_rs_flags || !d_rs_step || !d_rs_pos) return false;
             if (!FW_CUDA(cudaMemcpy(d_rs_table, params->rs_table.data(), params->rs_table.size() * 4, cudaMemcpyHostToDevice))) return false;
-            uploaded_version = 0;  // transport arrays go up with the first snapshot
-            return true;
+            std::vector<uint64_t> one((size_t)V, 1ull << 32);  // step 1.0 until set; not playing, no resource (zero-initialised)
+            return FW_CUDA(cudaMemcpy(d_rs_step, one.data(), (size_t)V * 8, cudaMemcpyHostToDevice));
         }
         if (kind == FW_NODE_SAMPLER) {  // SamplerProcessor::new (sampler.rs:300-320): not playing, playhead 0, no loop, no sample
             d_playing = dev_alloc<uint32_t>(V); d_playhead = dev_alloc<uint64_t>(V); d_loop_flags = dev_alloc<uint32_t>(V);
             d_loop_start = dev_alloc<uint64_t>(V); d_loop_end = dev_alloc<uint64_t>(V); d_res = dev_alloc<uint32_t>(V); d_msg_off = dev_alloc<uint32_t>((size_t)V + 1);
             if (!d_playing || !d_playhead || !d_loop_flags || !d_loop_start || !d_loop_end || !d_res || !d_msg_off) return false;
-            std::lock_guard<std::mutex> lk(params->smp_mu);
+            if (!alloc_sampler_staging(std::max<size_t>(4096, 4 * (size_t)V))) return false;
             params->smp_active = true;  // activate() creates the rings (sampler.rs:204-212)
-            params->smp_msgs.clear(); std::fill(params->smp_pending.begin(), params->smp_pending.end(), (uint16_t)0);
+            std::fill(params->smp_pending.begin(), params->smp_pending.end(), (uint16_t)0);
         }
-        uploaded_version = params->version;
+        uploaded_version = params->version.load(std::memory_order_acquire);
         return true;
     }
-    // stream side, first block of a call: drain the node -> processor ring (sampler.rs:331) into device memory, grouped by
-    // voice (stable: per-voice order is push order), and pin the resource table this call reads
-    bool snapshot_sampler(cudaStream_t st) {
-        h_drain.clear();
-        {
-            std::lock_guard<std::mutex> lk(params->smp_mu);
-            if (!params->smp_msgs.empty()) { h_drain.swap(params->smp_msgs); std::fill(params->smp_pending.begin(), params->smp_pending.end(), (uint16_t)0); }
-        }
-        res_table->snapshot(&cur_tab, &cur_n_res);
-        cur_n_msgs = (uint32_t)h_drain.size();
-        if (cur_n_msgs == 0) return true;
-        std::stable_sort(h_drain.begin(), h_drain.end(), [](const NodeParams::SamplerMsg& x, const NodeParams::SamplerMsg& y) { return x.voice < y.voice; });
-        h_msgs.resize(cur_n_msgs); h_off.assign((size_t)V + 1, 0);
-        for (uint32_t i = 0; i < cur_n_msgs; ++i) { const auto& m = h_drain[i]; h_msgs[i] = SamplerMsgDev{m.kind, m.a, m.x, m.y}; h_off[m.voice + 1]++; }
-        for (uint32_t v = 0; v < V; ++v) h_off[v + 1] += h_off[v];
-        if (cur_n_msgs > cap_msgs) {
-            cudaStreamSynchronize(st); cudaFree(d_msgs); d_msgs = nullptr; cap_msgs = 0;
-            const size_t want = std::max<size_t>(cur_n_msgs, 1024);
-            if (!FW_CUDA(cudaMalloc(&d_msgs, want * sizeof(SamplerMsgDev)))) return false;
-            cap_msgs = want;
-        }
-        return FW_CUDA(cudaMemcpyAsync(d_msgs, h_msgs.data(), cur_n_msgs * sizeof(SamplerMsgDev), cudaMemcpyHostToDevice, st)) &&
-               FW_CUDA(cudaMemcpyAsync(d_msg_off, h_off.data(), ((size_t)V + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    // ---- stream side -------------------------------------------------------------------------------------------------------
+    // Sampler messages of one chunk, staged in pinned memory grouped by voice (stable: per-voice order is push order) and copied
+    // behind the stream; `ev_staged` says when the copy has left the pinned buffer so that the next chunk may refill it.
+    SamplerMsgDev* h_msgs = nullptr; uint32_t* h_off = nullptr; uint32_t* h_cnt = nullptr; cudaEvent_t ev_staged = nullptr; bool staged_pending = false;
+    bool alloc_sampler_staging(size_t cap) {
+        cap_msgs = cap;
+        return FW_CUDA(cudaMallocHost(&h_msgs, cap * sizeof(SamplerMsgDev))) && FW_CUDA(cudaMallocHost(&h_off, ((size_t)V + 1) * sizeof(uint32_t))) &&
+               FW_CUDA(cudaMallocHost(&h_cnt, ((size_t)V + 1) * sizeof(uint32_t))) && FW_CUDA(cudaMalloc(&d_msgs, cap * sizeof(SamplerMsgDev))) &&
+               FW_CUDA(cudaEventCreateWithFlags(&ev_staged, cudaEventDisableTiming));
     }
-    // stream side, at call start: the relaxed atomic load of volume.rs:92, batched
+    // cmds[0..n): the CMD_SAMPLER commands of this node for the chunk, in push order
+    bool stage_sampler(const Cmd* const* cmds, uint32_t n, cudaStream_t st) {
+        res_table->snapshot(&cur_tab, &cur_n_res);
+        cur_n_msgs = n;
+        if (n == 0) return true;
+        if (staged_pending) { cudaEventSynchronize(ev_staged); staged_pending = false; }  // the previous copy has read the pinned buffer (it precedes that chunk's kernels)
+        std::memset(h_cnt, 0, ((size_t)V + 1) * sizeof(uint32_t));
+        auto each_voice = [&](const Cmd& m, auto&& f) { if (m.voice == FW_ALL_VOICES) { for (uint32_t v = 0; v < V; ++v) f(v); } else if (m.voice < V) f(m.voice); };
+        uint64_t total = 0;
+        for (uint32_t i = 0; i < n; ++i) each_voice(*cmds[i], [&](uint32_t v) { h_cnt[v + 1]++; ++total; });
+        if (total > cap_msgs) { g_dev_err = "sampler message staging overflow"; return false; }
+        h_off[0] = 0;
+        for (uint32_t v = 0; v < V; ++v) h_off[v + 1] = h_off[v] + h_cnt[v + 1];
+        for (uint32_t v = 0; v <= V; ++v) h_cnt[v] = h_off[v];  // running insert positions
+        for (uint32_t i = 0; i < n; ++i) { const Cmd& m = *cmds[i]; each_voice(m, [&](uint32_t v) { h_msgs[h_cnt[v]++] = SamplerMsgDev{m.a, m.b, m.x, m.y}; }); }
+        cur_n_msgs = (uint32_t)total;
+        const bool ok = FW_CUDA(cudaMemcpyAsync(d_msgs, h_msgs, total * sizeof(SamplerMsgDev), cudaMemcpyHostToDevice, st)) &&
+                        FW_CUDA(cudaMemcpyAsync(d_msg_off, h_off, ((size_t)V + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        cudaEventRecord(ev_staged, st); staged_pending = true;
+        return ok;
+    }
+    // at call start: the relaxed atomic load of volume.rs:92, batched — re-upload the arrays whose version moved
     bool snapshot_params(cudaStream_t st) {
-        if (kind == FW_NODE_SAMPLER && !snapshot_sampler(st)) return false;
-        if (kind == FW_NODE_RESAMPLER) {
-            res_table->snapshot(&cur_tab, &cur_n_res);
-            std::lock_guard<std::mutex> lk(params->smp_mu);
-            rs_seek_uploaded = false;
-            if (params->rs_seek_any) {  // seeks take effect at the start of this call
-                h_rs_seek_flag.assign(params->rs_seek_flag.begin(), params->rs_seek_flag.end());
-                if (!FW_CUDA(cudaMemcpyAsync(d_rs_seek, params->rs_seek.data(), (size_t)V * 8, cudaMemcpyHostToDevice, st)) ||
-                    !FW_CUDA(cudaMemcpyAsync(d_rs_seek_flag, h_rs_seek_flag.data(), (size_t)V * 4, cudaMemcpyHostToDevice, st))) return false;
-                std::fill(params->rs_seek_flag.begin(), params->rs_seek_flag.end(), (uint8_t)0); params->rs_seek_any = false;
-                rs_seek_uploaded = true;
-            }
-            if (params->version != uploaded_version) {
-                if (!FW_CUDA(cudaMemcpyAsync(d_rs_res, params->rs_res.data(), (size_t)V * 4, cudaMemcpyHostToDevice, st)) ||
-                    !FW_CUDA(cudaMemcpyAsync(d_rs_flags, params->rs_flags.data(), (size_t)V * 4, cudaMemcpyHostToDevice, st)) ||
-                    !FW_CUDA(cudaMemcpyAsync(d_rs_step, params->rs_step.data(), (size_t)V * 8, cudaMemcpyHostToDevice, st))) return false;
-                uploaded_version = params->version;
-            }
-            return true;
-        }
-        const uint64_t ver = params->version;
+        if (kind == FW_NODE_RESAMPLER) { res_table->snapshot(&cur_tab, &cur_n_res); return true; }
+        const uint64_t ver = params->version.load(std::memory_order_acquire);
         if (ver == uploaded_version) return true;
         for (uint32_t i = 0; i < n_sm; ++i)
             if (!FW_CUDA(cudaMemcpyAsync(d_target[i], host_target(i).data(), V * 4, cudaMemcpyHostToDevice, st))) return false;
@@ -264,7 +265,7 @@ struct Plan {
                    std::shared_ptr<NodeDeviceState> biquad, delay, reverb, sampler, svf; int sampler_sm = -1; };  // kind 2: reverb, kind 3: sampler head
     std::vector<Stage> stages;
     // generic lowering (arbitrary DAG of built-in nodes): one launch group per scheduled node over pool buffers [buffer][V][T]
-    struct GNode { uint32_t kind = 0; std::vector<uint32_t> in_buf, out_buf; std::vector<uint8_t> in_clear; int sm0 = -1, sm1 = -1, mask_slot = -1;
+    struct GNode { uint32_t kind = 0; std::vector<uint32_t> in_buf, out_buf; std::vector<uint8_t> in_clear; int sm0 = -1, sm1 = -1, mask_slot = -1, custom_idx = -1, sampler_idx = -1;
                    float f0 = 0.0f; std::shared_ptr<NodeDeviceState> st; };
     bool generic = false; std::vector<GNode> gnodes; uint32_t num_buffers = 0;
     std::vector<std::shared_ptr<NodeDeviceState>> samplers;  // index = CtlTables::smp index
@@ -272,8 +273,20 @@ struct Plan {
     bool bus = false; uint32_t n_sm = 0, c_in = 0, c_out = 0, num_voices = 0, block_frames = 0;
     Records rec{};
     uint64_t* d_bus_mask = nullptr;
+    // Per-call scratch, sized on the main thread (lower()) for one chunk of at most `chunk_frames` frames: the stream side
+    // never allocates (processor.rs:167-206, context.rs:61-64: the reference's audio thread does not either).
+    uint32_t chunk_frames = 0, chunk_blocks = 0;
+    float* d_part[2] = {nullptr, nullptr};     // partial buses [groups][c_out][chunk] and the next radix-16 level
+    float* d_tmp[2] = {nullptr, nullptr};      // inter-stage scratch [V][2][chunk]
+    float* d_pool = nullptr;                   // generic lowering: [buffer][V][chunk]
+    uint16_t* d_slot_of = nullptr;             // sampler graphs: record slot per (block, voice)
+    std::vector<SmpRec*> d_srec;               // per SamplerNode: [block][voice]
+    std::vector<uint64_t*> d_custom_masks;     // per custom node (index = GNode::custom_idx): dense [block][voice] input masks
     ~Plan() {
         cudaSetDevice(device);
+        cudaFree(d_part[0]); cudaFree(d_part[1]); cudaFree(d_tmp[0]); cudaFree(d_tmp[1]); cudaFree(d_pool); cudaFree(d_slot_of);
+        for (SmpRec* q : d_srec) cudaFree(q);
+        for (uint64_t* q : d_custom_masks) cudaFree(q);
         cudaFree(d_flags); cudaFree(rec.modes); cudaFree(rec.vals); cudaFree(rec.curves);
         cudaFree(rec.steady_k); cudaFree(rec.gout_mask); cudaFree(rec.error); cudaFree(d_bus_mask);
         cudaFree(rec.st_modes); cudaFree(rec.st_vals); cudaFree(rec.sum_masks); cudaFree(rec.st_sum_masks);
@@ -308,7 +321,12 @@ static NcclApi g_nccl;
 
 struct CtxToProc { int kind = 0; Plan* plan = nullptr; };                 // 0 NewSchedule, 1 Stop (processor.rs:265-268)
 struct ProcToCtx { int kind = 0; Plan* plan = nullptr; void* user_cx = nullptr; };  // 0 ReturnSchedule, 1 Dropped (:270-277)
-struct Channels { Spsc<CtxToProc> to_proc; Spsc<ProcToCtx> to_ctx; };
+struct Channels {
+    Spsc<CtxToProc> to_proc; Spsc<ProcToCtx> to_ctx;
+    DynSpsc<Cmd> cmds;                        // sampler messages, timed parameter stores, resampler transport (see Cmd)
+    std::atomic<uint32_t> drain_epoch{1};     // bumped by the stream side after it emptied `cmds` (per-voice ring-full accounting)
+    explicit Channels(size_t cmd_capacity) : cmds(cmd_capacity) {}
+};
 
 }  // namespace fw
 
@@ -321,9 +339,10 @@ struct fw_ctx {
     std::string last_error;
     std::shared_ptr<ResTable> res;  // sample resources (created lazily)
     Schedule dbg_schedule; bool dbg_valid = false;
+    uint32_t event_block = 0;  // fw_ctx_set_event_block: block offset (into the next call) of the stores and messages that follow
     // ActiveState (context.rs:17-27)
     bool active = false; std::shared_ptr<Channels> ch; uint32_t sample_rate = 0, max_block_frames = 0, n_in = 0, n_out = 0;
-    uint32_t max_call_blocks = 1024;  // longest call (in blocks) per-call side buffers are reserved for
+    uint32_t max_call_frames = 0;     // longest stretch processed in one go; longer calls are chunked (fw_graph_config::max_call_frames)
 };
 
 struct fw_processor {
@@ -334,21 +353,17 @@ struct fw_processor {
     float sm_a = 0, sm_b = 0, sm_eps = 0;
     uint64_t launches = 0;
     double cur_stream_time = 0.0; uint32_t cur_stream_status = 0;  // ProcInfo fields of the call being enqueued (node.rs:108-114)
-    // I/O staging (high-water mark)
-    float *d_in = nullptr, *d_out = nullptr, *d_inter = nullptr, *d_part[2] = {nullptr, nullptr}, *d_flush = nullptr;
-    size_t cap_in = 0, cap_out = 0, cap_inter = 0, cap_part[2] = {0, 0};
-    float* d_tmp[2] = {nullptr, nullptr}; size_t cap_tmp[2] = {0, 0};  // inter-stage scratch
-    float* d_pool = nullptr; size_t cap_pool = 0;  // generic lowering: [buffer][V][T]
-    uint16_t* d_slot_of = nullptr; size_t cap_slot_of = 0;  // sampler graphs: record slot per (block, voice)
+    // I/O staging of the host-buffer entry points, allocated at activate for max_call_frames (the stream side never allocates)
+    float *d_in = nullptr, *d_out = nullptr, *d_inter = nullptr, *d_flush = nullptr;
+    uint32_t max_call_frames = 0; uint32_t call_epoch = 0, first_epoch_of_call = 0, synced_epoch = 0;
+    std::vector<Cmd> pend; size_t pend_n = 0; std::vector<const Cmd*> cmd_ptrs;  // drained commands not yet applied (preallocated at activate)
     // multi-GPU master bus: voices shard by rank; the per-rank buses are all-gathered and tree-summed in rank order
     void* nccl_comm = nullptr; int rank = 0, world = 1;
-    float *d_bus_local = nullptr, *d_gather = nullptr; size_t cap_bus_local = 0, cap_gather = 0;
+    float *d_bus_local = nullptr, *d_gather = nullptr;  // [n_out][chunk], [world][n_out][chunk]: allocated by comm_init
     // the exchange runs on a side stream so that it overlaps the next call's control + chain kernels
     cudaStream_t side = nullptr; cudaEvent_t ev_bus_ready = nullptr, ev_exchange_done = nullptr; bool exchange_pending = false;
     // peer-memory exchange (exchange.cu): IPC-mapped mailboxes of all ranks; falls back to the NCCL all-gather when off
-    struct P2P { bool on = false; uint8_t* base[16] = {}; size_t cap = 0; uint32_t epoch = 0; uint32_t* counters = nullptr;
-                 float* part[2][2] = {}; size_t cap_part[2][2] = {};
-                 bool use_events = true; cudaEvent_t ev_done[2] = {}; bool done_valid[2] = {false, false}; } p2p;
+    struct P2P { bool on = false; uint8_t* base[16] = {}; size_t cap = 0; uint32_t epoch = 0; uint32_t* counters = nullptr; } p2p;
     uint64_t* h_masks = nullptr; uint32_t* h_err = nullptr;  // pinned
     // optional per-kernel-class timing (CUDA events on `stream`)
     bool profiling = false; std::vector<cudaEvent_t> prof_ev; std::vector<int> prof_class; size_t prof_used = 0;
@@ -523,6 +538,7 @@ static bool lower(fw_ctx* c, const Schedule& s, Plan* plan, std::string* why) {
             for (const InAssign& a : sn.in) { gn.in_buf.push_back(a.buffer); gn.in_clear.push_back(a.should_clear); }
             for (const OutAssign& a : sn.out) gn.out_buf.push_back(a.buffer);
             gn.sm0 = sm_of_node[i]; gn.sm1 = gn.kind == FW_NODE_PAN ? sm_of_node[i] + 1 : -1;
+            if (gn.kind == FW_NODE_SAMPLER) gn.sampler_idx = tb.nodes[i].sm1;
             gn.f0 = nr->params->threshold_gain;
             const bool endpoint = i == 0 || i + 1 == n;
             // bodies that branch on the input silence mask (see silence_fix_kernel / sum_kernel)
@@ -550,8 +566,16 @@ static bool lower(fw_ctx* c, const Schedule& s, Plan* plan, std::string* why) {
     plan->d_flags = dev_alloc<uint64_t>(V);
     Records& r = plan->rec;
     r.n_smoothers = n_sm;
-    r.kt_max = n_sm ? (8192u + F - 1) / F + 3u : 4u;  // longest ramp: ln(4/1e-6)*480 < 8192 samples, then settle/stall
-    r.kt_max += 8u * (uint32_t)plan->samplers.size();  // every sample that ends mid-call opens a short transient of its own
+    // Longest transient a record buffer must hold: a ramp decays like b^n with tau = smooth_secs * sample_rate samples and settles at
+    // |delta| * b^n < 1e-5 (smoother.rs:99-100,179); sized for |delta| up to 1e4 (a jump of 10000 % in percent_volume): ln(1e9) tau.
+    // A chunk never has more blocks than chunk_blocks, so min() with that is enough when the chunk is shorter than the ramp.
+    {
+        const double tau = 0.01 * (double)c->sample_rate;
+        const uint32_t ramp_blocks = (uint32_t)std::ceil(20.8 * tau / (double)F) + 4u;
+        const uint32_t kc = (c->max_call_frames + F - 1) / F + 1u;
+        r.kt_max = (n_sm ? ramp_blocks : 4u) + 8u * (uint32_t)plan->samplers.size();  // every sample that ends mid-call opens a short transient of its own
+        r.kt_max = std::max(2u, std::min(r.kt_max, kc));
+    }
     r.modes = dev_alloc<uint32_t>((size_t)r.kt_max * V);
     r.vals = dev_alloc<float>((size_t)r.kt_max * (n_sm ? n_sm : 1) * V);
     r.curves = dev_alloc<float>((size_t)r.kt_max * n_sm * V * F, false);
@@ -564,6 +588,26 @@ static bool lower(fw_ctx* c, const Schedule& s, Plan* plan, std::string* why) {
     r.st_sum_masks = dev_alloc<uint64_t>((size_t)(n_sum_masks ? n_sum_masks : 1) * V);
     r.error = dev_alloc<uint32_t>(1);
     plan->d_bus_mask = dev_alloc<uint64_t>(1);
+    {   // per-call scratch for one chunk (see Plan)
+        const uint32_t Tc = c->max_call_frames, Kc = (Tc + F - 1) / F;
+        plan->chunk_frames = Tc; plan->chunk_blocks = Kc;
+        const uint32_t n_out = plan->c_out, groups = chain_voice_groups(V);
+        bool ok = true;
+        if (plan->bus) {
+            plan->d_part[0] = dev_alloc<float>((size_t)groups * n_out * Tc, false); plan->d_part[1] = dev_alloc<float>((size_t)((groups + 15) / 16) * n_out * Tc, false);
+            ok = ok && plan->d_part[0] && plan->d_part[1];
+        }
+        if (!plan->generic && plan->stages.size() > 1) { plan->d_tmp[0] = dev_alloc<float>((size_t)V * 2 * Tc, false); ok = ok && plan->d_tmp[0]; }
+        if (!plan->generic && plan->stages.size() > 2) { plan->d_tmp[1] = dev_alloc<float>((size_t)V * 2 * Tc, false); ok = ok && plan->d_tmp[1]; }
+        if (plan->generic) { plan->d_pool = dev_alloc<float>((size_t)plan->num_buffers * V * Tc, false); ok = ok && plan->d_pool; }
+        if (!plan->samplers.empty()) {
+            plan->d_slot_of = dev_alloc<uint16_t>((size_t)Kc * V); ok = ok && plan->d_slot_of;
+            for (size_t i = 0; i < plan->samplers.size(); ++i) { plan->d_srec.push_back(dev_alloc<SmpRec>((size_t)Kc * V)); ok = ok && plan->d_srec.back(); }
+        }
+        for (auto& gn : plan->gnodes) if (gn.kind == FW_NODE_CUSTOM) { gn.custom_idx = (int)plan->d_custom_masks.size(); plan->d_custom_masks.push_back(dev_alloc<uint64_t>((size_t)Kc * V)); ok = ok && plan->d_custom_masks.back(); }
+        if (!ok) { *why = "device allocation failed: " + g_dev_err; return false; }
+        r.slot_of = plan->d_slot_of;
+    }
     if (!plan->d_flags || !r.modes || !r.vals || !r.curves || !r.steady_k || !r.gout_mask || !r.error || !plan->d_bus_mask || !r.st_modes || !r.st_vals || !r.sum_masks || !r.st_sum_masks) { *why = g_dev_err; return false; }
     plan->tables = tb;
     return true;
@@ -582,7 +626,7 @@ static std::shared_ptr<NodeParams> params_from_desc(const fw_node_desc* d, uint3
         case FW_NODE_SAMPLER: {  // sampler.rs:56-66
             float pct = std::fmax(d->f0, 0.0f), n = std::fmax(pct, 0.0f) * (1.0f / 100.0f);
             p->percent.assign(V, pct); p->raw_gain.assign(V, n * n);
-            p->smp_playing.assign(V, 0); p->smp_pending.assign(V, 0);
+            p->smp_playing.assign(V, 0); p->smp_pending.assign(V, 0); p->smp_pending_epoch.assign(V, 0);
             break;
         }
         case FW_NODE_HARD_CLIP:  // hard_clip.rs:8-12, util.rs:21-27
@@ -607,7 +651,6 @@ static std::shared_ptr<NodeParams> params_from_desc(const fw_node_desc* d, uint3
         case FW_NODE_RESAMPLER:
             if (!d->data || d->u0 == 0 || d->u1 == 0 || d->data_len < (uint64_t)d->u0 * d->u1) return nullptr;
             p->rs_phases = d->u0; p->rs_taps = d->u1; p->rs_table.assign(d->data, d->data + (size_t)d->u0 * d->u1);
-            p->rs_res.assign(V, 0); p->rs_flags.assign(V, 0); p->rs_step.assign(V, 1ull << 32); p->rs_seek.assign(V, 0); p->rs_seek_flag.assign(V, 0);
             break;
         case FW_NODE_CONV_REVERB:
             if (!d->data || d->data_len < (uint64_t)d->u0 * d->u1) return nullptr;
@@ -647,7 +690,9 @@ fw_ctx* fw_ctx_new(const fw_graph_config* cfg) {
 }
 void fw_ctx_free(fw_ctx* c) {
     if (!c) return;
-    if (c->active) { bool d = false; void* cx = nullptr; ctx_drain(c, &d, &cx); }
+    if (c->active) {  // Drop for FirewheelGraphCtx (context.rs:236-242): deactivate, then release what is still queued either way
+        fw_ctx_deactivate(c, 1);
+    }
     c->node_states.clear();
     delete c;
 }
@@ -768,17 +813,28 @@ int fw_schedule_node(fw_ctx* c, uint32_t i, fw_scheduled_node* out) {
 
 }  // extern "C"
 // ---- parameters -----------------------------------------------------------------------------
+// Two paths to the stream side, neither takes a lock (context.rs:61-64, "no mutexes" DESIGN_DOC.md:37):
+//   * event block 0 (default): the store lands in the node's host arrays and bumps `version` (release); the stream side
+//     re-uploads the arrays at the start of the next call — the reference's relaxed atomic store / per-block load
+//     (volume.rs:29-32,92) for a host that calls once per block;
+//   * event block b > 0 (fw_ctx_set_event_block): the store also travels as a command that takes effect at block b of the
+//     next call (the call is split there). The arrays are updated too, without a version bump, so later full uploads agree.
 static NodeParams* params_of(fw_ctx* c, fw_node_id node, uint32_t kind) {
     NodeRec* r = c->graph->node(Id::unpack(node));
     return (r && r->params->kind == kind) ? r->params.get() : nullptr;
 }
-template <class F> static int for_voices(NodeParams* p, uint32_t voice, F&& f) {
-    if (!p) return -1;
-    if (voice == FW_ALL_VOICES) { for (uint32_t v = 0; v < p->num_voices; ++v) f(v); }
-    else if (voice < p->num_voices) f(voice);
-    else return -1;
-    p->version += 1;
-    return 0;
+static bool voice_ok(const NodeParams* p, uint32_t voice) { return p && (voice == FW_ALL_VOICES || voice < p->num_voices); }
+template <class F> static void each_voice_of(NodeParams* p, uint32_t voice, F&& f) {
+    if (voice == FW_ALL_VOICES) { for (uint32_t v = 0; v < p->num_voices; ++v) f(v); } else f(voice);
+}
+static bool push_cmd(fw_ctx* c, const Cmd& m) { return c->active && c->ch && c->ch->cmds.push(m); }
+// host-array store, then either a version bump (block 0) or a timed command
+template <class F> static int store_param(fw_ctx* c, NodeParams* p, uint32_t voice, Cmd m, F&& write_host) {
+    if (!voice_ok(p, voice)) return -1;
+    each_voice_of(p, voice, write_host);
+    if (c->event_block == 0 || !c->active) { p->version.fetch_add(1, std::memory_order_release); return 0; }
+    m.block = c->event_block; m.voice = voice; m.node = p;
+    return push_cmd(c, m) ? 0 : -2;  // -2: command ring full
 }
 // `(secs * sample_rate).round() as u64` (sampler.rs:250-251,394): saturating float -> int cast, NaN -> 0
 static uint64_t secs_to_frame(double secs, uint32_t sample_rate) {
@@ -788,34 +844,51 @@ static uint64_t secs_to_frame(double secs, uint32_t sample_rate) {
     return (uint64_t)f;
 }
 // push one message for the selected voices; `gate(v)` mirrors the node-side `playing` checks (sampler.rs:82-136)
-template <class G> static int sampler_push(fw_ctx* c, fw_node_id node, uint32_t voice, NodeParams::SamplerMsg m, G&& gate) {
+template <class G> static int sampler_push(fw_ctx* c, fw_node_id node, uint32_t voice, uint32_t kind, uint32_t b, uint64_t x, uint64_t y, G&& gate) {
     NodeParams* p = c ? params_of(c, node, FW_NODE_SAMPLER) : nullptr;
     if (!p || (voice != FW_ALL_VOICES && voice >= p->num_voices)) return FW_SAMPLER_NOT_A_SAMPLER;
-    std::lock_guard<std::mutex> lk(p->smp_mu);
-    if (!p->smp_active) return FW_SAMPLER_NOT_ACTIVATED;
+    if (!p->smp_active || !c->active) return FW_SAMPLER_NOT_ACTIVATED;
     int rc = FW_SAMPLER_OK;
+    const uint32_t epoch = c->ch->drain_epoch.load(std::memory_order_acquire);
     const uint32_t v0 = voice == FW_ALL_VOICES ? 0 : voice, v1 = voice == FW_ALL_VOICES ? p->num_voices : voice + 1;
+    bool all = voice == FW_ALL_VOICES;
+    // per-voice ring capacity 128 (sampler.rs:14): count what was queued since the stream side last drained
+    for (uint32_t v = v0; v < v1; ++v) {
+        if (p->smp_pending_epoch[v] != epoch) { p->smp_pending_epoch[v] = epoch; p->smp_pending[v] = 0; }
+        if (!gate(*p, v, /*probe=*/true) || p->smp_pending[v] >= 128) all = false;
+    }
+    Cmd m{}; m.kind = CMD_SAMPLER; m.block = c->event_block; m.a = kind; m.b = b; m.x = x; m.y = y; m.node = p;
+    if (all) {  // one command for every voice
+        m.voice = FW_ALL_VOICES;
+        if (!push_cmd(c, m)) return FW_SAMPLER_RING_FULL;
+        for (uint32_t v = v0; v < v1; ++v) { p->smp_pending[v]++; gate(*p, v, /*probe=*/false); }
+        return rc;
+    }
     for (uint32_t v = v0; v < v1; ++v) {
         if (!gate(*p, v, /*probe=*/true)) continue;
-        if (p->smp_pending[v] >= 128) { rc = FW_SAMPLER_RING_FULL; continue; }  // rtrb push Err (sampler.rs:14)
-        m.voice = v; p->smp_msgs.push_back(m); p->smp_pending[v]++;
-        gate(*p, v, /*probe=*/false);
+        if (p->smp_pending[v] >= 128) { rc = FW_SAMPLER_RING_FULL; continue; }  // rtrb push Err
+        m.voice = v;
+        if (!push_cmd(c, m)) { rc = FW_SAMPLER_RING_FULL; continue; }
+        p->smp_pending[v]++; gate(*p, v, /*probe=*/false);
     }
     return rc;
 }
 static bool gate_always(NodeParams&, uint32_t, bool) { return true; }
 extern "C" {
+void fw_ctx_set_event_block(fw_ctx* c, uint32_t block) { if (c) c->event_block = block; }
 // ---- SVF + polyphase resampler (spec ours) ----------------------------------------------------
 int fw_svf_set_coeffs(fw_ctx* c, fw_node_id node, uint32_t voice, uint32_t stage, const float* k) {
     NodeParams* p = params_of(c, node, FW_NODE_SVF);
     if (!p || !k || stage >= p->num_stages) return -1;
-    return for_voices(p, voice, [&](uint32_t v) { std::memcpy(&p->svf_coeffs[((size_t)v * p->num_stages + stage) * 6], k, 6 * sizeof(float)); });
+    Cmd m{}; m.kind = CMD_SVF; m.a = stage; std::memcpy(m.f, k, 6 * sizeof(float));
+    return store_param(c, p, voice, m, [&](uint32_t v) { std::memcpy(&p->svf_coeffs[((size_t)v * p->num_stages + stage) * 6], k, 6 * sizeof(float)); });
 }
 int fw_svf_set_all_coeffs(fw_ctx* c, fw_node_id node, const float* k, uint32_t nv, uint32_t ns) {
     NodeParams* p = params_of(c, node, FW_NODE_SVF);
     if (!p || !k || nv != p->num_voices || ns != p->num_stages) return -1;
+    if (c->event_block && c->active) { int rc = 0; for (uint32_t v = 0; v < nv; ++v) for (uint32_t s = 0; s < ns; ++s) rc |= fw_svf_set_coeffs(c, node, v, s, k + ((size_t)v * ns + s) * 6); return rc; }
     std::memcpy(p->svf_coeffs.data(), k, (size_t)nv * ns * 6 * sizeof(float));
-    p->version += 1;
+    p->version.fetch_add(1, std::memory_order_release);
     return 0;
 }
 void fw_svf_design(uint32_t type, double fc, double q, double sr, float* out) {
@@ -832,20 +905,19 @@ void fw_svf_design(uint32_t type, double fc, double q, double sr, float* out) {
     }
     out[0] = (float)a1; out[1] = (float)a2; out[2] = (float)a3; out[3] = (float)m0; out[4] = (float)m1; out[5] = (float)m2;
 }
+// resampler transport travels as commands (event block 0: the start of the next call); before activation nothing can play
 int fw_resampler_set(fw_ctx* c, fw_node_id node, uint32_t voice, uint32_t res, uint64_t step, int playing, int loop) {
     NodeParams* p = c ? params_of(c, node, FW_NODE_RESAMPLER) : nullptr;
     uint64_t frames = 0;
-    if (!p || (res != 0 && (!c->res || !c->res->frames_of(res, &frames)))) return -1;
-    std::lock_guard<std::mutex> lk(p->smp_mu);
-    return for_voices(p, voice, [&](uint32_t v) { p->rs_res[v] = res; p->rs_step[v] = step; p->rs_flags[v] = (playing ? 1u : 0u) | (loop ? 2u : 0u); });
+    if (!voice_ok(p, voice) || (res != 0 && (!c->res || !c->res->frames_of(res, &frames)))) return -1;
+    Cmd m{}; m.kind = CMD_RS_SET; m.block = c->event_block; m.voice = voice; m.a = (playing ? 1u : 0u) | (loop ? 2u : 0u); m.b = res; m.x = step; m.node = p;
+    return push_cmd(c, m) ? 0 : -2;
 }
 int fw_resampler_seek(fw_ctx* c, fw_node_id node, uint32_t voice, uint64_t pos_frames) {
     NodeParams* p = c ? params_of(c, node, FW_NODE_RESAMPLER) : nullptr;
-    if (!p) return -1;
-    std::lock_guard<std::mutex> lk(p->smp_mu);
-    const int rc = for_voices(p, voice, [&](uint32_t v) { p->rs_seek[v] = pos_frames; p->rs_seek_flag[v] = 1; });
-    if (rc == 0) p->rs_seek_any = true;
-    return rc;
+    if (!voice_ok(p, voice)) return -1;
+    Cmd m{}; m.kind = CMD_RS_SEEK; m.block = c->event_block; m.voice = voice; m.x = pos_frames; m.node = p;
+    return push_cmd(c, m) ? 0 : -2;
 }
 static double bessel_i0(double x) { double s = 1.0, t = 1.0; for (int k = 1; k < 64; ++k) { t *= (x / (2.0 * k)) * (x / (2.0 * k)); s += t; if (t < 1e-18 * s) break; } return s; }
 void fw_resampler_design(uint32_t P, uint32_t T, double cutoff, double beta, float* table) {
@@ -867,33 +939,38 @@ uint32_t fw_sample_resource_create(fw_ctx* c, uint32_t format, uint32_t channels
 int fw_sampler_set_sample(fw_ctx* c, fw_node_id node, uint32_t voice, uint32_t res, int stop_playback) {
     uint64_t frames = 0;
     if (!c || !c->res || !c->res->frames_of(res, &frames)) return FW_SAMPLER_BAD_ARGS;
-    return sampler_push(c, node, voice, NodeParams::SamplerMsg{0, SMSG_SET_SAMPLE, res, stop_playback ? 1ull : 0ull, 0}, gate_always);
+    return sampler_push(c, node, voice, SMSG_SET_SAMPLE, res, stop_playback ? 1ull : 0ull, 0, gate_always);
 }
 int fw_sampler_play(fw_ctx* c, fw_node_id node, uint32_t voice) {
-    return sampler_push(c, node, voice, NodeParams::SamplerMsg{0, SMSG_PLAY, 0, 0, 0},
+    return sampler_push(c, node, voice, SMSG_PLAY, 0, 0, 0,
                         [](NodeParams& p, uint32_t v, bool probe) { if (probe) return !p.smp_playing[v]; p.smp_playing[v] = 1; return true; });
 }
 int fw_sampler_pause(fw_ctx* c, fw_node_id node, uint32_t voice) {
-    return sampler_push(c, node, voice, NodeParams::SamplerMsg{0, SMSG_PAUSE, 0, 0, 0},
+    return sampler_push(c, node, voice, SMSG_PAUSE, 0, 0, 0,
                         [](NodeParams& p, uint32_t v, bool probe) { if (probe) return (bool)p.smp_playing[v]; p.smp_playing[v] = 0; return true; });
 }
 int fw_sampler_stop(fw_ctx* c, fw_node_id node, uint32_t voice) {
-    return sampler_push(c, node, voice, NodeParams::SamplerMsg{0, SMSG_STOP, 0, 0, 0},
+    return sampler_push(c, node, voice, SMSG_STOP, 0, 0, 0,
                         [](NodeParams& p, uint32_t v, bool probe) { if (probe) return (bool)p.smp_playing[v]; p.smp_playing[v] = 0; return true; });
 }
 int fw_sampler_set_playhead(fw_ctx* c, fw_node_id node, uint32_t voice, double secs) {
     if (!c) return FW_SAMPLER_NOT_A_SAMPLER;
-    return sampler_push(c, node, voice, NodeParams::SamplerMsg{0, SMSG_SET_PLAYHEAD, 0, secs_to_frame(secs, c->sample_rate), 0}, gate_always);
+    return sampler_push(c, node, voice, SMSG_SET_PLAYHEAD, 0, secs_to_frame(secs, c->sample_rate), 0, gate_always);
 }
 int fw_sampler_set_loop_range(fw_ctx* c, fw_node_id node, uint32_t voice, uint32_t mode, double s, double e) {
     if (!c || mode > FW_LOOP_RANGE_SECS) return FW_SAMPLER_BAD_ARGS;
     const uint64_t fs = mode == FW_LOOP_RANGE_SECS ? secs_to_frame(s, c->sample_rate) : 0, fe = mode == FW_LOOP_RANGE_SECS ? secs_to_frame(e, c->sample_rate) : 0;
     if (mode == FW_LOOP_RANGE_SECS && c->active && !(fs < fe)) return FW_SAMPLER_BAD_ARGS;
-    return sampler_push(c, node, voice, NodeParams::SamplerMsg{0, SMSG_SET_LOOP, mode, fs, fe}, gate_always);
+    return sampler_push(c, node, voice, SMSG_SET_LOOP, mode, fs, fe, gate_always);
 }
-int fw_sampler_set_percent_volume(fw_ctx* c, fw_node_id node, uint32_t voice, float pct) {  // sampler.rs:174-180
+static int set_raw_gain(fw_ctx* c, NodeParams* p, uint32_t voice, float pct) {  // volume.rs:28-34, range.rs:32-35 / sampler.rs:174-180
+    const float n = std::fmax(pct, 0.0f) * (1.0f / 100.0f), g = n * n;
+    Cmd m{}; m.kind = CMD_TARGET; m.a = 0; m.f[0] = g;
+    return store_param(c, p, voice, m, [&](uint32_t v) { p->raw_gain[v] = g; p->percent[v] = std::fmax(pct, 0.0f); });
+}
+int fw_sampler_set_percent_volume(fw_ctx* c, fw_node_id node, uint32_t voice, float pct) {
     NodeParams* p = c ? params_of(c, node, FW_NODE_SAMPLER) : nullptr;
-    return for_voices(p, voice, [&](uint32_t v) { float n = std::fmax(pct, 0.0f) * (1.0f / 100.0f); p->raw_gain[v] = n * n; p->percent[v] = std::fmax(pct, 0.0f); }) == 0 ? FW_SAMPLER_OK : FW_SAMPLER_NOT_A_SAMPLER;
+    return set_raw_gain(c, p, voice, pct) == 0 ? FW_SAMPLER_OK : FW_SAMPLER_NOT_A_SAMPLER;
 }
 int fw_sampler_is_playing(fw_ctx* c, fw_node_id node, uint32_t voice) {
     NodeParams* p = c ? params_of(c, node, FW_NODE_SAMPLER) : nullptr;
@@ -901,46 +978,53 @@ int fw_sampler_is_playing(fw_ctx* c, fw_node_id node, uint32_t voice) {
     return p->smp_playing[voice] ? 1 : 0;
 }
 
-int fw_volume_set_percent_volume(fw_ctx* c, fw_node_id node, uint32_t voice, float pct) {  // volume.rs:28-34, range.rs:32-35
-    NodeParams* p = params_of(c, node, FW_NODE_VOLUME);
-    return for_voices(p, voice, [&](uint32_t v) { float n = std::fmax(pct, 0.0f) * (1.0f / 100.0f); p->raw_gain[v] = n * n; p->percent[v] = std::fmax(pct, 0.0f); });
-}
+int fw_volume_set_percent_volume(fw_ctx* c, fw_node_id node, uint32_t voice, float pct) { return set_raw_gain(c, params_of(c, node, FW_NODE_VOLUME), voice, pct); }
 int fw_volume_set_percent_volumes(fw_ctx* c, fw_node_id node, const float* pct, uint32_t n) {
     NodeParams* p = params_of(c, node, FW_NODE_VOLUME);
     if (!p || n != p->num_voices) return -1;
+    if (c->event_block && c->active) { int rc = 0; for (uint32_t v = 0; v < n; ++v) rc |= set_raw_gain(c, p, v, pct[v]); return rc; }
     for (uint32_t v = 0; v < n; ++v) { float x = std::fmax(pct[v], 0.0f) * (1.0f / 100.0f); p->raw_gain[v] = x * x; p->percent[v] = std::fmax(pct[v], 0.0f); }
-    p->version += 1;
+    p->version.fetch_add(1, std::memory_order_release);
     return 0;
 }
 static void pan_gains(float pan, float* gl, float* gr) {
     double pp = std::fmin(std::fmax((double)pan, -1.0), 1.0), th = (pp + 1.0) * (M_PI / 4.0);
     *gl = (float)std::cos(th); *gr = (float)std::sin(th);
 }
+static int set_pan_gains(fw_ctx* c, NodeParams* p, uint32_t voice, float gl, float gr, const float* pan) {
+    if (!voice_ok(p, voice)) return -1;
+    each_voice_of(p, voice, [&](uint32_t v) { p->gain_l[v] = gl; p->gain_r[v] = gr; if (pan) p->pan[v] = *pan; });
+    if (c->event_block == 0 || !c->active) { p->version.fetch_add(1, std::memory_order_release); return 0; }
+    Cmd m{}; m.kind = CMD_TARGET; m.block = c->event_block; m.voice = voice; m.node = p;
+    m.a = 0; m.f[0] = gl; const bool ok0 = push_cmd(c, m);
+    m.a = 1; m.f[0] = gr; const bool ok1 = push_cmd(c, m);
+    return ok0 && ok1 ? 0 : -2;
+}
 int fw_pan_set_pan(fw_ctx* c, fw_node_id node, uint32_t voice, float pan) {
-    NodeParams* p = params_of(c, node, FW_NODE_PAN);
-    return for_voices(p, voice, [&](uint32_t v) { p->pan[v] = pan; pan_gains(pan, &p->gain_l[v], &p->gain_r[v]); });
+    float gl, gr; pan_gains(pan, &gl, &gr);
+    return set_pan_gains(c, params_of(c, node, FW_NODE_PAN), voice, gl, gr, &pan);
 }
 int fw_pan_set_pans(fw_ctx* c, fw_node_id node, const float* pan, uint32_t n) {
     NodeParams* p = params_of(c, node, FW_NODE_PAN);
     if (!p || n != p->num_voices) return -1;
+    if (c->event_block && c->active) { int rc = 0; for (uint32_t v = 0; v < n; ++v) rc |= fw_pan_set_pan(c, node, v, pan[v]); return rc; }
     for (uint32_t v = 0; v < n; ++v) { p->pan[v] = pan[v]; pan_gains(pan[v], &p->gain_l[v], &p->gain_r[v]); }
-    p->version += 1;
+    p->version.fetch_add(1, std::memory_order_release);
     return 0;
 }
-int fw_pan_set_gains(fw_ctx* c, fw_node_id node, uint32_t voice, float gl, float gr) {
-    NodeParams* p = params_of(c, node, FW_NODE_PAN);
-    return for_voices(p, voice, [&](uint32_t v) { p->gain_l[v] = gl; p->gain_r[v] = gr; });
-}
+int fw_pan_set_gains(fw_ctx* c, fw_node_id node, uint32_t voice, float gl, float gr) { return set_pan_gains(c, params_of(c, node, FW_NODE_PAN), voice, gl, gr, nullptr); }
 int fw_biquad_set_coeffs(fw_ctx* c, fw_node_id node, uint32_t voice, uint32_t stage, const float* k) {
     NodeParams* p = params_of(c, node, FW_NODE_BIQUAD);
-    if (!p || stage >= p->num_stages) return -1;
-    return for_voices(p, voice, [&](uint32_t v) { std::memcpy(&p->coeffs[((size_t)v * p->num_stages + stage) * 5], k, 5 * sizeof(float)); });
+    if (!p || !k || stage >= p->num_stages) return -1;
+    Cmd m{}; m.kind = CMD_BIQUAD; m.a = stage; std::memcpy(m.f, k, 5 * sizeof(float));
+    return store_param(c, p, voice, m, [&](uint32_t v) { std::memcpy(&p->coeffs[((size_t)v * p->num_stages + stage) * 5], k, 5 * sizeof(float)); });
 }
 int fw_biquad_set_all_coeffs(fw_ctx* c, fw_node_id node, const float* k, uint32_t nv, uint32_t ns) {
     NodeParams* p = params_of(c, node, FW_NODE_BIQUAD);
-    if (!p || nv != p->num_voices || ns != p->num_stages) return -1;
+    if (!p || !k || nv != p->num_voices || ns != p->num_stages) return -1;
+    if (c->event_block && c->active) { int rc = 0; for (uint32_t v = 0; v < nv; ++v) for (uint32_t s = 0; s < ns; ++s) rc |= fw_biquad_set_coeffs(c, node, v, s, k + ((size_t)v * ns + s) * 5); return rc; }
     std::memcpy(p->coeffs.data(), k, (size_t)nv * ns * 5 * sizeof(float));
-    p->version += 1;
+    p->version.fetch_add(1, std::memory_order_release);
     return 0;
 }
 void fw_biquad_design_rbj(uint32_t type, double fc, double q, double gain_db, double sr, float* out) {  // RBJ cookbook, f64 -> f32
@@ -978,10 +1062,20 @@ int fw_ctx_activate(fw_ctx* c, uint32_t sr, uint32_t n_in, uint32_t n_out, uint3
     for (int i = 0; ok && i < 4; ++i) ok = FW_CUDA(cudaEventCreate(&p->ev[i]));
     ok = ok && FW_CUDA(cudaMallocHost(&p->h_masks, sizeof(uint64_t) * (c->cfg.num_voices + 1))) && FW_CUDA(cudaMallocHost(&p->h_err, sizeof(uint32_t)));
     if (!ok) { c->last_error = g_dev_err; delete p; return -1; }
-    c->ch = std::make_shared<Channels>();
+    c->ch = std::make_shared<Channels>(std::max<size_t>(4096, 4 * (size_t)c->cfg.num_voices));
     c->active = true; c->sample_rate = sr; c->max_block_frames = mbf; c->n_in = n_in; c->n_out = n_out;
     p->ch = c->ch; p->user_cx = user_cx; p->num_voices = c->cfg.num_voices; p->max_block_frames = mbf; p->n_in = n_in; p->n_out = n_out;
     p->bus = c->cfg.master_bus != 0;
+    c->max_call_frames = c->cfg.max_call_frames ? c->cfg.max_call_frames : 64u * mbf;
+    c->max_call_frames = ((c->max_call_frames + mbf - 1) / mbf) * mbf;  // whole blocks
+    p->max_call_frames = c->max_call_frames;
+    p->pend.resize(2 * c->ch->cmds.capacity()); p->cmd_ptrs.resize(p->pend.size());
+    {
+        const size_t V = c->cfg.num_voices, Tm = p->max_call_frames;
+        const size_t in_e = V * n_in * Tm, out_e = (size_t)(p->bus ? 1 : V) * n_out * Tm;
+        p->d_in = dev_alloc<float>(in_e, false); p->d_out = dev_alloc<float>(out_e, false); p->d_inter = dev_alloc<float>(std::max(in_e, out_e), false);
+        if (!p->d_in || !p->d_out || !p->d_inter) { c->last_error = "device allocation failed (I/O staging for max_call_frames): " + g_dev_err; cudaFree(p->d_in); cudaFree(p->d_out); cudaFree(p->d_inter); delete p; c->active = false; c->ch.reset(); return -1; }
+    }
     // SmootherConfig::default + ParamSmoother::new (smoother.rs:18-25,99-100); host libm, once
     p->sm_b = std::exp(-1.0f / ((10.0f / 1000.0f) * (float)sr)); p->sm_a = 1.0f - p->sm_b; p->sm_eps = 0.00001f;
     *out = p;
@@ -1024,9 +1118,6 @@ int fw_ctx_update(fw_ctx* c, fw_update_status* out) {  // context.rs:93-148
                 if (arc != 0 || !proc_h) msg = err[0] ? std::string(err) : std::string("custom node activation failed");
                 else {
                     ds->custom_proc = proc_h;
-                    ds->cap_custom_masks = (size_t)c->max_call_blocks * c->cfg.num_voices;
-                    ds->d_custom_masks = dev_alloc<uint64_t>(ds->cap_custom_masks);
-                    if (!ds->d_custom_masks) msg = "device allocation failed: " + g_dev_err;
                 }
             }
             if (ds->kind == FW_NODE_SAMPLER || ds->kind == FW_NODE_RESAMPLER) { if (!c->res) { c->res = std::make_shared<ResTable>(); c->res->device = c->cfg.device; } ds->res_table = c->res; }
@@ -1103,63 +1194,45 @@ static void proc_poll(fw_processor* p) {  // processor.rs:167-206
         p->plan = m.plan;
     }
 }
-static bool ensure(float** buf, size_t* cap, size_t n) {
-    if (n <= *cap) return true;
-    cudaFree(*buf); *buf = nullptr; *cap = 0;
-    void* q = nullptr;
-    if (!FW_CUDA(cudaMalloc(&q, n * sizeof(float)))) return false;
-    *buf = static_cast<float*>(q); *cap = n;
-    return true;
-}
+// One chunk of a call: frames [t0, t0 + Tc) of rows that are Tfull frames long in the caller's buffers.
+struct Chunk { uint32_t t0, Tc, Tfull, zero_first; };
 
 // Last stage with a master bus: the chain kernel (BUS variant) reduces 64 voices per CTA into partial buses, the combine
-// kernel finishes the tree, and with several ranks the per-rank buses are exchanged.
+// kernel finishes the tree, and with several ranks the per-rank buses are exchanged. bus_out = the caller's
+// bus rows (pitch ck.Tfull) at the chunk's first frame.
 static constexpr size_t kMailHeader = 256;  // ready[2][16] u32 at +0, ack[2][16] u32 at +128, slots at +256
-static int run_bus_stage(fw_processor* p, ChainArgs& xa, uint32_t n_out, uint32_t T, float* d_out) {
-    const uint32_t V = p->num_voices;
+static int run_bus_stage(fw_processor* p, Plan& pl, ChainArgs& xa, uint32_t n_out, const Chunk& ck, float* bus_out) {
+    const uint32_t V = p->num_voices, T = ck.Tc;
     uint32_t n = chain_voice_groups(V);
-    const bool p2p = p->world > 1 && p->p2p.on && (size_t)n_out * T <= p->p2p.cap;
-    if (p2p) {
-        // Main stream: chain -> partial buses (+ radix-16 levels while more than 16 remain). Side stream (high priority):
-        // K-push = last tree level fused with the NVLink stores, K-wait, K-recv. The partial buffers alternate with the
-        // epoch parity, so the whole exchange of call e overlaps control + chain of call e + 1.
+    const uint32_t err_val = (p->call_epoch << 4) | 2u;
+    if (p->world > 1 && p->p2p.on) {
+        // Peer-memory exchange. MAIN stream: chain -> partial buses (+ radix-16 levels while more than 16 remain) -> K-push = the
+        // last level of the rank-local tree FUSED with the NVLink stores into every rank's mailbox (programmatic dependent launch:
+        // no event, no side-stream hand-over on the critical path; the next call's control kernel overlaps its tail). SIDE stream
+        // (high priority): K-wait polls the mailbox flags, K-recv applies the top levels of the tree in rank order and writes the
+        // caller's bus — it depends on the main stream only through those device words, so nothing is recorded on the main stream.
         fw_processor::P2P& x = p->p2p;
         const uint32_t epoch = ++x.epoch;
         const int s = (int)(epoch & 1u);
-        if (x.use_events && x.done_valid[s]) cudaStreamWaitEvent(p->stream, x.ev_done[s], 0);  // K-push(e - 2) has read part[s]
-        if (!ensure(&x.part[s][0], &x.cap_part[s][0], (size_t)n * n_out * T) || (n > 16 && !ensure(&x.part[s][1], &x.cap_part[s][1], (size_t)((n + 15) / 16) * n_out * T))) return FW_PROC_DEVICE_ERROR;
-        xa.out = x.part[s][0];
+        xa.out = pl.d_part[0]; xa.bus_pitch = 0;
         { ProfScope ps(p, 1); if (!FW_CUDA(launch_chain(xa, true, p->stream))) return FW_PROC_DEVICE_ERROR; }
         p->launches++;
         int cur = 0;
-        {
-            ProfScope ps2(p, 2);
-            while (n > 16) {
-                if (!FW_CUDA(launch_combine(x.part[s][cur], x.part[s][cur ^ 1], n, n_out, T, p->stream))) return FW_PROC_DEVICE_ERROR;
-                p->launches++;
-                n = (n + 15) / 16; cur ^= 1;
-            }
-        }
-        // Hand-over main -> side. Events (default) cost the PDL overlap of the next control kernel (an event record between
-        // two kernels serialises them); FW_P2P_HANDOVER=signal keeps the PDL chain with a device-word hand-over instead.
-        if (x.use_events) {
-            cudaEventRecord(p->ev_bus_ready, p->stream);
-            cudaStreamWaitEvent(p->side, p->ev_bus_ready, 0);
-        } else {
-            if (!FW_CUDA(launch_bus_signal(x.counters + 2, x.counters + 3, epoch, xa.rec.error, p->stream))) return FW_PROC_DEVICE_ERROR;
-            if (!FW_CUDA(launch_bus_wait(x.counters + 2, 1, epoch, xa.rec.error, p->side))) return FW_PROC_DEVICE_ERROR;
-            p->launches += 2;
+        ProfScope ps2(p, 2);
+        while (n > 16) {
+            if (!FW_CUDA(launch_combine(pl.d_part[cur], pl.d_part[cur ^ 1], n, n_out, T, p->stream))) return FW_PROC_DEVICE_ERROR;
+            p->launches++;
+            n = (n + 15) / 16; cur ^= 1;
         }
         BusPushArgs pa{};
-        pa.pin = x.part[s][cur]; pa.n_in = n; pa.rows = n_out; pa.T = T;
+        pa.pin = pl.d_part[cur]; pa.n_in = n; pa.rows = n_out; pa.T = T;
         for (int r = 0; r < p->world; ++r) { pa.data[r] = reinterpret_cast<float*>(x.base[r] + kMailHeader); pa.ready[r] = reinterpret_cast<uint32_t*>(x.base[r]); }
-        pa.ack_local = reinterpret_cast<const uint32_t*>(x.base[p->rank] + 128); pa.counter = x.counters; pa.push_done = x.counters + 3; pa.error = xa.rec.error;
+        pa.ack_local = reinterpret_cast<const uint32_t*>(x.base[p->rank] + 128); pa.counter = x.counters; pa.push_done = x.counters + 3; pa.error = xa.rec.error; pa.error_value = err_val;
         pa.world = (uint32_t)p->world; pa.me = (uint32_t)p->rank; pa.epoch = epoch; pa.cap = (uint32_t)x.cap;
-        if (!FW_CUDA(launch_bus_push(pa, p->side))) return FW_PROC_DEVICE_ERROR;
-        if (x.use_events) { cudaEventRecord(x.ev_done[s], p->side); x.done_valid[s] = true; }
-        if (!FW_CUDA(launch_bus_wait(reinterpret_cast<const uint32_t*>(x.base[p->rank]) + s * 16, (uint32_t)p->world, epoch, xa.rec.error, p->side))) return FW_PROC_DEVICE_ERROR;
+        if (!FW_CUDA(launch_bus_push(pa, p->stream))) return FW_PROC_DEVICE_ERROR;
+        if (!FW_CUDA(launch_bus_wait(reinterpret_cast<const uint32_t*>(x.base[p->rank]) + s * 16, (uint32_t)p->world, epoch, xa.rec.error, err_val, p->side))) return FW_PROC_DEVICE_ERROR;
         BusRecvArgs ra{};
-        ra.data_local = reinterpret_cast<const float*>(x.base[p->rank] + kMailHeader); ra.out = d_out; ra.rows = n_out; ra.T = T;
+        ra.data_local = reinterpret_cast<const float*>(x.base[p->rank] + kMailHeader); ra.out = bus_out; ra.rows = n_out; ra.T = T; ra.out_pitch = ck.Tfull;
         for (int r = 0; r < p->world; ++r) ra.ack[r] = reinterpret_cast<uint32_t*>(x.base[r] + 128);
         ra.counter = x.counters + 1; ra.world = (uint32_t)p->world; ra.me = (uint32_t)p->rank; ra.epoch = epoch; ra.cap = (uint32_t)x.cap;
         if (!FW_CUDA(launch_bus_recv(ra, p->side))) return FW_PROC_DEVICE_ERROR;
@@ -1168,18 +1241,11 @@ static int run_bus_stage(fw_processor* p, ChainArgs& xa, uint32_t n_out, uint32_
         p->exchange_pending = true;
         return FW_PROC_OK;
     }
-    float* bus_dst = d_out;  // this rank's bus; with several ranks it is gathered and tree-summed below
-    if (p->world > 1) {
-        if ((size_t)n_out * T > p->cap_bus_local || (size_t)p->world * n_out * T > p->cap_gather) join_side(p);  // about to reallocate
-        if (!ensure(&p->d_bus_local, &p->cap_bus_local, (size_t)n_out * T) || !ensure(&p->d_gather, &p->cap_gather, (size_t)p->world * n_out * T)) return FW_PROC_DEVICE_ERROR;
-        bus_dst = p->d_bus_local;
-    }
-    if (n == 1) { xa.out = bus_dst; }
-    else {
-        const size_t need = (size_t)n * n_out * T;
-        if (!ensure(&p->d_part[0], &p->cap_part[0], need) || !ensure(&p->d_part[1], &p->cap_part[1], (size_t)((n + 15) / 16) * n_out * T)) return FW_PROC_DEVICE_ERROR;
-        xa.out = p->d_part[0];
-    }
+    // this rank's bus: with several ranks it is gathered (NCCL) and tree-summed below, else it is the caller's bus
+    float* bus_dst = p->world > 1 ? p->d_bus_local : bus_out;
+    const uint32_t bus_pitch = p->world > 1 ? T : ck.Tfull;
+    if (n == 1) { xa.out = bus_dst; xa.bus_pitch = bus_pitch; }
+    else { xa.out = pl.d_part[0]; xa.bus_pitch = 0; }
     if (p->world > 1 && n == 1) join_side(p);  // the chain kernel writes d_bus_local directly
     { ProfScope ps(p, 1); if (!FW_CUDA(launch_chain(xa, true, p->stream))) return FW_PROC_DEVICE_ERROR; }
     p->launches++;
@@ -1187,20 +1253,21 @@ static int run_bus_stage(fw_processor* p, ChainArgs& xa, uint32_t n_out, uint32_
     int cur = 0;
     while (n > 1) {
         const uint32_t n_next = (n + 15) / 16;
-        float* cdst = n_next == 1 ? bus_dst : p->d_part[cur ^ 1];
+        float* cdst = n_next == 1 ? bus_dst : pl.d_part[cur ^ 1];
         if (p->world > 1 && n_next == 1) join_side(p);  // d_bus_local is still being read by the previous exchange
-        if (!FW_CUDA(launch_combine(p->d_part[cur], cdst, n, n_out, T, p->stream))) return FW_PROC_DEVICE_ERROR;
+        if (!FW_CUDA(launch_combine(pl.d_part[cur], cdst, n, n_out, T, p->stream, n_next == 1 ? bus_pitch : 0))) return FW_PROC_DEVICE_ERROR;
         p->launches++;
         n = n_next; cur ^= 1;
     }
     if (p->world > 1) {
-        // Exchange step: all-gather the per-rank buses over NVLink, then the top log2(world) levels of
-        // the same balanced tree in rank order on every rank — bit-identical on all ranks, unlike ncclAllReduce.
+        // NCCL exchange (used when the peer-memory mailboxes could not be set up, or FW_EXCHANGE=nccl): all-gather the per-rank buses,
+        // then the top log2(world) levels of the same balanced tree in rank order on every rank — bit-identical on all ranks, unlike
+        // ncclAllReduce. Runs on the side stream so that it overlaps the next call's control + chain.
         cudaEventRecord(p->ev_bus_ready, p->stream);
         cudaStreamWaitEvent(p->side, p->ev_bus_ready, 0);
         if (!g_nccl.ok(g_nccl.AllGather(p->d_bus_local, p->d_gather, (size_t)n_out * T, /*ncclFloat32*/ 7, p->nccl_comm, p->side), "ncclAllGather")) return FW_PROC_DEVICE_ERROR;
         p->launches++;
-        if (!FW_CUDA(launch_combine(p->d_gather, d_out, (uint32_t)p->world, n_out, T, p->side))) return FW_PROC_DEVICE_ERROR;
+        if (!FW_CUDA(launch_combine(p->d_gather, bus_out, (uint32_t)p->world, n_out, T, p->side, ck.Tfull))) return FW_PROC_DEVICE_ERROR;
         p->launches++;
         cudaEventRecord(p->ev_exchange_done, p->side);
         p->exchange_pending = true;
@@ -1208,20 +1275,19 @@ static int run_bus_stage(fw_processor* p, ChainArgs& xa, uint32_t n_out, uint32_
     return FW_PROC_OK;
 }
 
-// Generic lowering at run time: walk the scheduled nodes (compiler.rs order) over the pool [buffer][V][T]. Buffer reuse
+// Generic lowering at run time: walk the scheduled nodes (compiler.rs order) over the pool [buffer][V][Tc]. Buffer reuse
 // is the reference's (compiler.rs:302-412): it is valid for any execution that respects the schedule order, and each
-// node here finishes all K blocks before the next node starts.
-static int enqueue_generic(fw_processor* p, Plan& pl, const float* d_in, float* d_out, uint32_t T, uint32_t zero_first_frames) {
-    const uint32_t V = p->num_voices, n_in = pl.c_in, n_out = pl.c_out;
+// node here finishes all blocks of the chunk before the next node starts.
+static int enqueue_generic(fw_processor* p, Plan& pl, const float* d_in, float* d_out, const Chunk& ck) {
+    const uint32_t V = p->num_voices, n_in = pl.c_in, n_out = pl.c_out, T = ck.Tc;
     const size_t BS = (size_t)V * T;  // floats per pool buffer
-    if (!ensure(&p->d_pool, &p->cap_pool, (size_t)pl.num_buffers * BS)) return FW_PROC_DEVICE_ERROR;
-    auto buf = [&](uint32_t b) { return p->d_pool + (size_t)b * BS; };
+    auto buf = [&](uint32_t b) { return pl.d_pool + (size_t)b * BS; };
     // one pointwise launch: up to 2 channels, arbitrary channel pointers
     auto pointwise = [&](const ChainProgram& prog, const float* i0, const float* i1, uint64_t ivs, float* o0, float* o1, uint64_t ovs, bool first) -> bool {
         ChainArgs xa{};
         xa.in_ch[0] = i0; xa.in_ch[1] = i1 ? i1 : i0; xa.out_ch[0] = o0; xa.out_ch[1] = o1 ? o1 : o0;
         xa.in_vstride = ivs; xa.out_vstride = ovs; xa.out = nullptr;
-        xa.num_voices = V; xa.frames = T; xa.block_frames = pl.block_frames; xa.zero_first_block = (first && zero_first_frames) ? 1u : 0u;
+        xa.num_voices = V; xa.frames = T; xa.block_frames = pl.block_frames; xa.zero_first_block = (first && ck.zero_first) ? 1u : 0u;
         xa.rec = pl.rec; xa.prog = prog; xa.in_from_prev_kernel = first ? 0u : 1u;
         ProfScope ps(p, 1);
         if (!FW_CUDA(launch_chain(xa, false, p->stream))) return false;
@@ -1260,7 +1326,8 @@ static int enqueue_generic(fw_processor* p, Plan& pl, const float* d_in, float* 
         if (i == 0) {  // graph_in: stream channels -> pool (prepare_graph_inputs, schedule.rs:213-253)
             for (size_t c = 0; c < gn.out_buf.size(); c += 2) {
                 const bool two = c + 1 < gn.out_buf.size();
-                if (!pointwise(prog1(-1, two ? 2 : 1, two ? 2 : 1, -1, -1, 0.f), d_in + c * T, two ? d_in + (c + 1) * T : nullptr, (uint64_t)n_in * T,
+                const float* s0 = d_in + c * (size_t)ck.Tfull + ck.t0;
+                if (!pointwise(prog1(-1, two ? 2 : 1, two ? 2 : 1, -1, -1, 0.f), s0, two ? s0 + ck.Tfull : nullptr, (uint64_t)n_in * ck.Tfull,
                                buf(gn.out_buf[c]), two ? buf(gn.out_buf[c + 1]) : nullptr, T, true)) return FW_PROC_DEVICE_ERROR;
             }
             continue;
@@ -1270,13 +1337,14 @@ static int enqueue_generic(fw_processor* p, Plan& pl, const float* d_in, float* 
                 ChainArgs xa{};
                 xa.in_ch[0] = buf(gn.in_buf[0]); xa.in_ch[1] = buf(gn.in_buf[n_out > 1 ? 1 : 0]); xa.in_vstride = T;
                 xa.num_voices = V; xa.frames = T; xa.block_frames = pl.block_frames; xa.rec = pl.rec; xa.prog = prog1(-1, n_out, n_out, -1, -1, 0.f); xa.in_from_prev_kernel = 1;
-                const int brc = run_bus_stage(p, xa, n_out, T, d_out);
+                const int brc = run_bus_stage(p, pl, xa, n_out, ck, d_out + ck.t0);
                 if (brc != FW_PROC_OK) return brc;
             } else {
                 for (size_t c = 0; c < gn.in_buf.size(); c += 2) {
                     const bool two = c + 1 < gn.in_buf.size();
+                    float* o0 = d_out + c * (size_t)ck.Tfull + ck.t0;
                     if (!pointwise(prog1(-1, two ? 2 : 1, two ? 2 : 1, -1, -1, 0.f), buf(gn.in_buf[c]), two ? buf(gn.in_buf[c + 1]) : nullptr, T,
-                                   d_out + c * T, two ? d_out + (c + 1) * T : nullptr, (uint64_t)n_out * T, false)) return FW_PROC_DEVICE_ERROR;
+                                   o0, two ? o0 + ck.Tfull : nullptr, (uint64_t)n_out * ck.Tfull, false)) return FW_PROC_DEVICE_ERROR;
                 }
             }
             continue;
@@ -1288,7 +1356,7 @@ static int enqueue_generic(fw_processor* p, Plan& pl, const float* d_in, float* 
                 SamplerArgs sa{};
                 for (size_t c = 0; c < gn.out_buf.size(); ++c) sa.out[c] = buf(gn.out_buf[c]);
                 sa.out_vstride = T; sa.n_out = (uint32_t)gn.out_buf.size(); sa.num_voices = V; sa.frames = T; sa.block_frames = pl.block_frames;
-                sa.srec = st.d_srec; sa.res = st.d_res; sa.loop_start = st.d_loop_start; sa.res_tab = st.cur_tab; sa.sm = gn.sm0; sa.rec = pl.rec;
+                sa.srec = pl.d_srec[gn.sampler_idx]; sa.res = st.d_res; sa.loop_start = st.d_loop_start; sa.res_tab = st.cur_tab; sa.sm = gn.sm0; sa.rec = pl.rec;
                 ProfScope ps(p, 1);
                 if (!FW_CUDA(launch_sampler(sa, p->stream))) return FW_PROC_DEVICE_ERROR;
                 p->launches++;
@@ -1326,7 +1394,6 @@ static int enqueue_generic(fw_processor* p, Plan& pl, const float* d_in, float* 
             }
             case FW_NODE_RESAMPLER: {
                 NodeDeviceState& st = *gn.st;
-                if (st.rs_seek_uploaded) { if (!FW_CUDA(launch_resampler_begin(st.d_rs_pos, st.d_rs_seek, st.d_rs_seek_flag, V, p->stream))) return FW_PROC_DEVICE_ERROR; p->launches++; st.rs_seek_uploaded = false; }
                 ResamplerArgs ra{};
                 for (size_t c = 0; c < gn.out_buf.size(); ++c) ra.out[c] = buf(gn.out_buf[c]);
                 ra.out_vstride = T; ra.n_out = (uint32_t)gn.out_buf.size(); ra.num_voices = V; ra.frames = T; ra.taps = st.params->rs_taps;
@@ -1368,7 +1435,7 @@ static int enqueue_generic(fw_processor* p, Plan& pl, const float* d_in, float* 
             }
             case FW_NODE_CONV_REVERB: {
                 NodeDeviceState& rs = *gn.st;
-                if (T > NodeDeviceState::kReverbMaxFrames) { g_dev_err = "conv reverb: more than 65536 frames in one call"; return FW_PROC_BAD_ARGS; }
+                if (T > NodeDeviceState::kReverbMaxFrames) { g_dev_err = "conv reverb: more than 65536 frames in one chunk"; return FW_PROC_BAD_ARGS; }
                 const uint32_t nc = (uint32_t)gn.in_buf.size(), H = reverb_hist(rs.params->ir_len);
                 if (rs.xh_cursor + T > rs.xh_pitch || (rs.xh_cursor & 7u)) {
                     if (!FW_CUDA(cudaMemcpy2DAsync(rs.d_xh[rs.xh_cur ^ 1u], (size_t)rs.xh_pitch * 2, static_cast<const uint16_t*>(rs.d_xh[rs.xh_cur]) + (rs.xh_cursor - H),
@@ -1390,8 +1457,8 @@ static int enqueue_generic(fw_processor* p, Plan& pl, const float* d_in, float* 
             case FW_NODE_CUSTOM: {  // AudioNodeProcessor::process for all voices and blocks at once (fw_node_vtable::process_device)
                 NodeDeviceState& st = *gn.st;
                 const uint32_t nb = (T + pl.block_frames - 1) / pl.block_frames;
-                if ((size_t)nb * V > st.cap_custom_masks) { g_dev_err = "custom node: call longer than the reserved mask buffer"; return FW_PROC_DEVICE_ERROR; }
-                if (!FW_CUDA(launch_expand_masks(pl.rec, (uint32_t)gn.mask_slot, V, nb, st.d_custom_masks, p->stream))) return FW_PROC_DEVICE_ERROR;
+                uint64_t* masks = pl.d_custom_masks[gn.custom_idx];
+                if (!FW_CUDA(launch_expand_masks(pl.rec, (uint32_t)gn.mask_slot, V, nb, masks, p->stream))) return FW_PROC_DEVICE_ERROR;
                 p->launches++;
                 const float* ins[64]; float* outs[64];
                 for (size_t c = 0; c < gn.in_buf.size(); ++c) ins[c] = buf(gn.in_buf[c]);
@@ -1399,7 +1466,7 @@ static int enqueue_generic(fw_processor* p, Plan& pl, const float* d_in, float* 
                 fw_device_block blk{};
                 blk.num_voices = V; blk.num_inputs = (uint32_t)gn.in_buf.size(); blk.num_outputs = (uint32_t)gn.out_buf.size(); blk.block_frames = pl.block_frames; blk.num_blocks = nb;
                 blk.stream_status = p->cur_stream_status; blk.frames = T; blk.in_voice_stride = T; blk.out_voice_stride = T; blk.inputs = ins; blk.outputs = outs;
-                blk.in_silence_masks = st.d_custom_masks; blk.stream_time_secs = p->cur_stream_time; blk.cuda_stream = p->stream; blk.user_cx = p->user_cx;
+                blk.in_silence_masks = masks; blk.stream_time_secs = p->cur_stream_time; blk.cuda_stream = p->stream; blk.user_cx = p->user_cx;
                 ProfScope ps(p, 1);
                 if (st.params->custom->vt.process_device(st.custom_proc, &blk) != 0) { g_dev_err = std::string("custom node '") + st.params->custom->debug_name + "': process_device failed"; return FW_PROC_DEVICE_ERROR; }
                 break;
@@ -1413,13 +1480,12 @@ static int enqueue_generic(fw_processor* p, Plan& pl, const float* d_in, float* 
 // Peer-memory mailboxes for the bus exchange: allocate, exchange CUDA IPC handles through the communicator, map all peers.
 // Any rank failing turns the feature off on ALL ranks (they then use the NCCL all-gather): decided by a second all-gather.
 static bool p2p_setup(fw_processor* p) {
-    // Default: the NCCL all-gather on the high-priority side stream — measured faster at 8 GPUs (0.113 ms/step vs 0.119 /
-    // 0.126 for the two peer-memory hand-overs, profiles/r01_bench_c2_n8_*.json). FW_EXCHANGE=p2p selects the peer-memory path.
+    // Default: the peer-memory exchange (push fused into the last tree level on the main stream, exchange.cu). FW_EXCHANGE=nccl
+    // selects the NCCL all-gather instead; it is also what every rank falls back to when CUDA IPC / peer access is unavailable.
     const char* mode = getenv("FW_EXCHANGE");
-    const bool want = mode && std::strcmp(mode, "p2p") == 0;
+    const bool want = !(mode && std::strcmp(mode, "nccl") == 0);
     const int W = p->world, me = p->rank;
-    size_t cap = 262144;  // floats per slot: 2 channels x 131072 frames
-    if (const char* e = getenv("FW_P2P_SLOT_FLOATS")) { const long long v = atoll(e); if (v >= 1024) cap = (size_t)v & ~(size_t)3; }
+    const size_t cap = (((size_t)p->n_out * p->max_call_frames) + 3) & ~(size_t)3;  // floats per slot: one chunk of the bus
     const size_t bytes = kMailHeader + (size_t)2 * W * cap * sizeof(float);
     struct Msg { cudaIpcMemHandle_t h; uint32_t ok; uint32_t pad[15]; };
     static_assert(sizeof(Msg) == 128, "IPC handle message");
@@ -1458,9 +1524,7 @@ static bool p2p_setup(fw_processor* p) {
         if (want && me == 0) std::fprintf(stderr, "[firewheel_b200] peer-memory bus exchange unavailable (CUDA IPC / peer access); using the NCCL all-gather\n");
         return true;
     }
-    p->p2p.counters = dev_alloc<uint32_t>(4);  // push counter, recv counter, chain_done, push_done
-    { const char* h = getenv("FW_P2P_HANDOVER"); p->p2p.use_events = !(h && std::strcmp(h, "signal") == 0); }
-    for (auto& e : p->p2p.ev_done) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    p->p2p.counters = dev_alloc<uint32_t>(4);  // push counter, recv counter, (unused), push_done
     p->p2p.cap = cap; p->p2p.epoch = 0; p->p2p.on = true;
     return true;
 }
@@ -1476,86 +1540,100 @@ static void p2p_teardown(fw_processor* p) {
     }
     for (int r = 0; r < p->world; ++r) if (r != p->rank && p->p2p.base[r]) cudaIpcCloseMemHandle(p->p2p.base[r]);
     cudaFree(p->p2p.base[p->rank]); cudaFree(p->p2p.counters);
-    for (int q = 0; q < 2; ++q) { cudaFree(p->p2p.part[q][0]); cudaFree(p->p2p.part[q][1]); if (p->p2p.ev_done[q]) cudaEventDestroy(p->p2p.ev_done[q]); }
     p->p2p.on = false;
 }
 
-// Enqueue one call (frames = K blocks) on device buffers. d_in [V][c_in][T]; d_out [V][c_out][T] or bus [c_out][T].
-static int proc_enqueue(fw_processor* p, const float* d_in, float* d_out, uint32_t n_in, uint32_t n_out, uint64_t frames64) {
-    if (frames64 > 0x7fffffffull) return FW_PROC_BAD_ARGS;
-    const uint32_t T = (uint32_t)frames64, V = p->num_voices;
-    const size_t out_elems = (size_t)(p->bus ? 1 : V) * n_out * T;
-    cudaSetDevice(p->device);
-    auto silence = [&] { if (out_elems) { launch_fill(d_out, out_elems, 0.0f, p->stream); p->launches++; } };
-    if (!p->running) { silence(); return FW_PROC_DROP_PROCESSOR; }                   // processor.rs:71-74
-    if (!p->plan) { proc_poll(p); p->pending_zero_first = false; if (!p->running) { silence(); return FW_PROC_DROP_PROCESSOR; } }  // :76-84
-    if (!p->plan || T == 0) { silence(); return FW_PROC_OK; }                        // :86-89
-    proc_poll(p);                                                                    // process_block :214
-    if (!p->running) { silence(); return FW_PROC_DROP_PROCESSOR; }
-    Plan& pl = *p->plan;
-    if (n_in != pl.c_in || n_out != pl.c_out) { g_dev_err = "channel counts do not match the compiled graph"; return FW_PROC_BAD_ARGS; }
-    for (auto& st : pl.states) if (!st->snapshot_params(p->stream)) return FW_PROC_DEVICE_ERROR;
-
-    if (!pl.samplers.empty()) {  // per-call buffers of sampler graphs: record slot per (block, voice), block records per sampler
-        const size_t KV = (size_t)((T + pl.block_frames - 1) / pl.block_frames) * V;
-        if (KV > p->cap_slot_of) {
-            cudaStreamSynchronize(p->stream); cudaFree(p->d_slot_of); p->d_slot_of = nullptr; p->cap_slot_of = 0;
-            if (!FW_CUDA(cudaMalloc(&p->d_slot_of, KV * sizeof(uint16_t)))) return FW_PROC_DEVICE_ERROR;
-            p->cap_slot_of = KV;
-        }
-        pl.rec.slot_of = p->d_slot_of;
-        for (auto& st : pl.samplers) {
-            if (KV > st->cap_srec) {
-                cudaStreamSynchronize(p->stream); cudaFree(st->d_srec); st->d_srec = nullptr; st->cap_srec = 0;
-                if (!FW_CUDA(cudaMalloc(&st->d_srec, KV * sizeof(SmpRec)))) return FW_PROC_DEVICE_ERROR;
-                st->cap_srec = KV;
-            }
+// ---- timed commands (see Cmd in graph.hpp) -------------------------------------------------------------------------------
+static NodeDeviceState* state_of(Plan& pl, const NodeParams* node) {
+    for (auto& st : pl.states) if (st->params.get() == node) return st.get();
+    return nullptr;  // the node is not part of the current schedule: the command is dropped, like a message to a removed processor
+}
+struct PokeBatch {
+    PokeArgs a{}; fw_processor* p; bool ok = true;
+    explicit PokeBatch(fw_processor* p_) : p(p_) {}
+    void flush() { if (a.n) { ok = ok && FW_CUDA(launch_poke(a, p->stream)); p->launches++; a.n = 0; } }
+    void add(void* ptr, uint64_t val, uint8_t bytes, uint32_t count, uint32_t stride) {
+        if (a.n == 16) flush();
+        a.ptr[a.n] = ptr; a.val[a.n] = val; a.bytes[a.n] = bytes; a.count[a.n] = count; a.stride_bytes[a.n] = stride; ++a.n;
+    }
+    void f32(float* base, uint32_t voice, uint32_t V, size_t per_voice, size_t off, float v) {  // element `off` of voice's row (or of every voice's)
+        uint32_t bits; std::memcpy(&bits, &v, 4);
+        if (voice == FW_ALL_VOICES) add(base + off, bits, 4, V, (uint32_t)(per_voice * 4)); else add(base + (size_t)voice * per_voice + off, bits, 4, 1, 0);
+    }
+};
+// apply the commands scheduled at block `b` of this call: parameter stores become ordered device stores, sampler messages are
+// staged per node for the control kernel of the chunk that starts here
+static bool apply_commands(fw_processor* p, Plan& pl, uint32_t b) {
+    const uint32_t V = p->num_voices;
+    PokeBatch pk(p);
+    for (size_t i = 0; i < p->pend_n; ++i) {
+        const Cmd& m = p->pend[i];
+        if (m.block != b || m.kind == CMD_SAMPLER) continue;
+        NodeDeviceState* st = state_of(pl, m.node);
+        if (!st || (m.voice != FW_ALL_VOICES && m.voice >= V)) continue;
+        const uint32_t cnt = m.voice == FW_ALL_VOICES ? V : 1u; const size_t v0 = m.voice == FW_ALL_VOICES ? 0 : m.voice;
+        switch (m.kind) {
+            case CMD_TARGET: if (m.a < st->n_sm) pk.f32(st->d_target[m.a], m.voice, V, 1, 0, m.f[0]); break;
+            case CMD_BIQUAD: if (st->kind == FW_NODE_BIQUAD && m.a < st->params->num_stages) for (int k = 0; k < 5; ++k) pk.f32(st->d_coeffs, m.voice, V, (size_t)st->params->num_stages * 5, (size_t)m.a * 5 + k, m.f[k]); break;
+            case CMD_SVF: if (st->kind == FW_NODE_SVF && m.a < st->params->num_stages) for (int k = 0; k < 6; ++k) pk.f32(st->d_coeffs, m.voice, V, (size_t)st->params->num_stages * 6, (size_t)m.a * 6 + k, m.f[k]); break;
+            case CMD_RS_SET:
+                if (st->kind != FW_NODE_RESAMPLER) break;
+                pk.add(st->d_rs_res + v0, m.b, 4, cnt, 4); pk.add(st->d_rs_flags + v0, m.a, 4, cnt, 4); pk.add(st->d_rs_step + v0, m.x, 8, cnt, 8);
+                break;
+            case CMD_RS_SEEK: if (st->kind == FW_NODE_RESAMPLER) pk.add(st->d_rs_pos + v0, m.x << 32, 8, cnt, 8); break;
+            default: break;
         }
     }
+    pk.flush();
+    if (!pk.ok) return false;
+    for (auto& st : pl.samplers) {
+        uint32_t n = 0;
+        for (size_t i = 0; i < p->pend_n; ++i) { const Cmd& m = p->pend[i]; if (m.block == b && m.kind == CMD_SAMPLER && m.node == st->params.get()) p->cmd_ptrs[n++] = &m; }
+        if (!st->stage_sampler(p->cmd_ptrs.data(), n, p->stream)) return false;
+    }
+    return true;
+}
+
+// One chunk: control kernel + data plane over frames [ck.t0, ck.t0 + ck.Tc) of the caller's rows (ck.Tfull frames long).
+static int enqueue_chunk(fw_processor* p, Plan& pl, const float* d_in, float* d_out, uint32_t n_out, const Chunk& ck) {
+    const uint32_t V = p->num_voices, T = ck.Tc;
+    ++p->call_epoch;
     ControlArgs ca{};
     ca.tables = pl.tables; ca.rec = pl.rec;
     for (size_t i = 0; i < pl.resamplers.size(); ++i) { ca.tables.rs[i].res_tab = pl.resamplers[i]->cur_tab; ca.tables.rs[i].n_res = pl.resamplers[i]->cur_n_res; }
     for (size_t i = 0; i < pl.samplers.size(); ++i) {
         NodeDeviceState& st = *pl.samplers[i];
         SamplerCtl& sc = ca.tables.smp[i];
-        sc.res_tab = st.cur_tab; sc.n_res = st.cur_n_res; sc.msgs = st.d_msgs; sc.msg_off = st.d_msg_off; sc.n_msgs = st.cur_n_msgs; sc.rec = st.d_srec;
-    } ca.flags = pl.d_flags; ca.num_voices = V; ca.frames = T; ca.block_frames = pl.block_frames;
-    ca.a = p->sm_a; ca.b = p->sm_b; ca.eps = p->sm_eps;
+        sc.res_tab = st.cur_tab; sc.n_res = st.cur_n_res; sc.msgs = st.d_msgs; sc.msg_off = st.d_msg_off; sc.n_msgs = st.cur_n_msgs; sc.rec = pl.d_srec[i];
+    }
+    ca.flags = pl.d_flags; ca.num_voices = V; ca.frames = T; ca.block_frames = pl.block_frames;
+    ca.a = p->sm_a; ca.b = p->sm_b; ca.eps = p->sm_eps; ca.err_value = (p->call_epoch << 4) | 1u;
     { ProfScope ps(p, 0); if (!FW_CUDA(launch_control(ca, p->stream))) return FW_PROC_DEVICE_ERROR; }
     p->launches++;
 
-    if (pl.generic) {
-        const uint32_t zff = p->pending_zero_first ? std::min(pl.block_frames, T) : 0u;  // Q11
-        p->pending_zero_first = false;
-        return enqueue_generic(p, pl, d_in, d_out, T, zff);
-    }
-    // ---- data plane: run the stages in order; intermediates ping-pong through [V][ch][T] scratch ----
+    if (pl.generic) return enqueue_generic(p, pl, d_in, d_out, ck);
+    // ---- data plane: run the stages in order; intermediates ping-pong through [V][ch][Tc] scratch ----
     const size_t n_stages = pl.stages.size();
-    if (n_stages > 1) {
-        const size_t need = (size_t)V * 2 * T;
-        if (!ensure(&p->d_tmp[0], &p->cap_tmp[0], need) || (n_stages > 2 && !ensure(&p->d_tmp[1], &p->cap_tmp[1], need))) return FW_PROC_DEVICE_ERROR;
-    }
-    const uint32_t zero_first_frames = p->pending_zero_first ? std::min(pl.block_frames, T) : 0u;  // Q11
-    p->pending_zero_first = false;
-    const float* src = d_in;
+    const float* src = d_in ? d_in + ck.t0 : nullptr; uint32_t src_pitch = ck.Tfull;  // stage 0 reads the caller's rows
     for (size_t si = 0; si < n_stages; ++si) {
         const Plan::Stage& sg = pl.stages[si];
         const bool last = si + 1 == n_stages;
-        float* dst = last ? d_out : p->d_tmp[si & 1];
-        if (sg.kind == 3) {  // SamplerNode heading the chain: writes [V][c_out][T]
+        float* dst = last ? d_out + ck.t0 : pl.d_tmp[si & 1];
+        const uint32_t dst_pitch = last ? ck.Tfull : T;
+        if (sg.kind == 3) {  // SamplerNode heading the chain: writes [V][c_out][pitch]
             NodeDeviceState& st = *sg.sampler;
             SamplerArgs sa{};
-            for (uint32_t c = 0; c < sg.c_out; ++c) sa.out[c] = dst + (size_t)c * T;
-            sa.out_vstride = (uint64_t)sg.c_out * T; sa.n_out = sg.c_out; sa.num_voices = V; sa.frames = T; sa.block_frames = pl.block_frames;
-            sa.srec = st.d_srec; sa.res = st.d_res; sa.loop_start = st.d_loop_start; sa.res_tab = st.cur_tab; sa.sm = sg.sampler_sm; sa.rec = pl.rec;
+            for (uint32_t c = 0; c < sg.c_out; ++c) sa.out[c] = dst + (size_t)c * dst_pitch;
+            sa.out_vstride = (uint64_t)sg.c_out * dst_pitch; sa.n_out = sg.c_out; sa.num_voices = V; sa.frames = T; sa.block_frames = pl.block_frames;
+            sa.srec = pl.d_srec[0]; sa.res = st.d_res; sa.loop_start = st.d_loop_start; sa.res_tab = st.cur_tab; sa.sm = sg.sampler_sm; sa.rec = pl.rec;
             { ProfScope ps(p, 1); if (!FW_CUDA(launch_sampler(sa, p->stream))) return FW_PROC_DEVICE_ERROR; }
             p->launches++;
-            src = dst;
+            src = dst; src_pitch = dst_pitch;
             continue;
         }
         if (sg.kind == 2) {
             NodeDeviceState& rs = *sg.reverb;
-            if (T > NodeDeviceState::kReverbMaxFrames) { g_dev_err = "conv reverb: more than 65536 frames in one call"; return FW_PROC_BAD_ARGS; }
+            if (T > NodeDeviceState::kReverbMaxFrames) { g_dev_err = "conv reverb: more than 65536 frames in one chunk"; return FW_PROC_BAD_ARGS; }
             ReverbCall rc{};
             const uint32_t H = reverb_hist(rs.params->ir_len);
             if (rs.xh_cursor + T > rs.xh_pitch || (rs.xh_cursor & 7u)) {  // buffer full (or cursor off the 16-byte TMA grid after an odd-length call):
@@ -1564,19 +1642,19 @@ static int proc_enqueue(fw_processor* p, const float* d_in, float* d_out, uint32
                                                (size_t)rs.xh_pitch * 2, (size_t)H * 2, (size_t)V * sg.c_in, cudaMemcpyDeviceToDevice, p->stream))) return FW_PROC_DEVICE_ERROR;
                 rs.xh_cur ^= 1u; rs.xh_cursor = H;
             }
-            rc.in = src; rc.out = dst; rc.xh = rs.d_xh[rs.xh_cur]; rc.bt = rs.d_bt;
+            rc.in = src; rc.out = dst; rc.in_pitch = src_pitch; rc.out_pitch = dst_pitch; rc.xh = rs.d_xh[rs.xh_cur]; rc.bt = rs.d_bt;
             rc.V = V; rc.C = sg.c_in; rc.T = T; rc.L = rs.params->ir_len; rc.ir_ch = rs.params->ir_channels; rc.cursor = rs.xh_cursor; rc.pitch = rs.xh_pitch;
-            rc.zero_first = si == 0 ? zero_first_frames : 0u; rc.chan_base = 0;
+            rc.zero_first = si == 0 ? ck.zero_first : 0u; rc.chan_base = 0;
             std::string rerr;
             { ProfScope ps(p, 3); if (!FW_CUDA(launch_reverb(rc, p->stream, &rerr))) { if (!rerr.empty()) g_dev_err = rerr; return FW_PROC_DEVICE_ERROR; } }
             p->launches += 2;
             rs.xh_cursor += T;
-            src = dst;
+            src = dst; src_pitch = dst_pitch;
             continue;
         }
         if (sg.kind == 1) {
             TemporalArgs ta{};
-            ta.in = src; ta.out = dst; ta.R = V * sg.c_in; ta.C = sg.c_in; ta.T = T; ta.zero_first = si == 0 ? zero_first_frames : 0u;
+            ta.in = src; ta.out = dst; ta.in_pitch = src_pitch; ta.out_pitch = dst_pitch; ta.R = V * sg.c_in; ta.C = sg.c_in; ta.T = T; ta.zero_first = si == 0 ? ck.zero_first : 0u;
             ta.srow_mul = 1; ta.srow_add = 0;
             if (sg.biquad) { ta.ns = sg.biquad->params->num_stages; ta.coeffs = sg.biquad->d_coeffs; ta.state = sg.biquad->d_state; }
             if (sg.svf) { ta.svf = 1; ta.ns = sg.svf->params->num_stages; ta.coeffs = sg.svf->d_coeffs; ta.state = sg.svf->d_state; }
@@ -1586,28 +1664,92 @@ static int proc_enqueue(fw_processor* p, const float* d_in, float* d_out, uint32
             }
             { ProfScope ps(p, 3); if (!FW_CUDA(launch_temporal(ta, p->stream))) return FW_PROC_DEVICE_ERROR; }
             p->launches++;
-            src = dst;
+            src = dst; src_pitch = dst_pitch;
             continue;
         }
         ChainArgs xa{};
-        for (uint32_t c = 0; c < 2; ++c) {  // staged chains read / write [V][ch][T]
-            xa.in_ch[c] = src + (size_t)(c < sg.prog.c_in ? c : 0) * T;
-            xa.out_ch[c] = dst + (size_t)(c < sg.prog.c_out ? c : 0) * T;
+        for (uint32_t c = 0; c < 2; ++c) {  // staged chains read / write [V][ch][pitch]
+            xa.in_ch[c] = src + (size_t)(c < sg.prog.c_in ? c : 0) * src_pitch;
+            xa.out_ch[c] = dst + (size_t)(c < sg.prog.c_out ? c : 0) * dst_pitch;
         }
-        xa.in_vstride = (uint64_t)sg.prog.c_in * T; xa.out_vstride = (uint64_t)sg.prog.c_out * T;
-        xa.num_voices = V; xa.frames = T; xa.block_frames = pl.block_frames; xa.zero_first_block = (si == 0 && zero_first_frames) ? 1u : 0u;
+        xa.in_vstride = (uint64_t)sg.prog.c_in * src_pitch; xa.out_vstride = (uint64_t)sg.prog.c_out * dst_pitch;
+        xa.num_voices = V; xa.frames = T; xa.block_frames = pl.block_frames; xa.zero_first_block = (si == 0 && ck.zero_first) ? 1u : 0u;
         xa.rec = pl.rec; xa.prog = sg.prog; xa.in_from_prev_kernel = si > 0 ? 1u : 0u;
         if (!(last && pl.bus)) {
             xa.out = nullptr;
             { ProfScope ps(p, 1); if (!FW_CUDA(launch_chain(xa, false, p->stream))) return FW_PROC_DEVICE_ERROR; }
             p->launches++;
         } else {
-            const int brc = run_bus_stage(p, xa, n_out, T, d_out);
+            const int brc = run_bus_stage(p, pl, xa, n_out, ck, d_out + ck.t0);
             if (brc != FW_PROC_OK) return brc;
         }
-        src = dst;
+        src = dst; src_pitch = dst_pitch;
     }
     return FW_PROC_OK;
+}
+
+// One process_* call on device buffers: d_in [V][c_in][T]; d_out [V][c_out][T] or bus [c_out][T]. The call is processed as
+// consecutive chunks; a chunk boundary is (a) every plan.chunk_frames frames — the stretch device memory was reserved for —
+// and (b) every block at which a timed command takes effect. Messages from the context (new schedule, Stop; processor.rs:
+// 167-206) are polled at every chunk boundary, i.e. per block whenever the host asks for per-block control.
+static int proc_call(fw_processor* p, const float* d_in, float* d_out, uint32_t n_in, uint32_t n_out, uint64_t frames64) {
+    if (frames64 > 0x7fffffffull) return FW_PROC_BAD_ARGS;
+    const uint32_t T = (uint32_t)frames64, V = p->num_voices;
+    const size_t out_rows = (size_t)(p->bus ? 1 : V) * n_out;
+    cudaSetDevice(p->device);
+    // zero frames [t0, T) of every output row
+    auto silence_from = [&](uint32_t t0) {
+        if (!out_rows || t0 >= T) return;
+        if (t0 == 0) launch_fill(d_out, out_rows * T, 0.0f, p->stream);
+        else cudaMemset2DAsync(d_out + t0, (size_t)T * 4, 0, (size_t)(T - t0) * 4, out_rows, p->stream);
+        p->launches++;
+    };
+    if (!p->running) { silence_from(0); return FW_PROC_DROP_PROCESSOR; }                   // processor.rs:71-74
+    if (!p->plan) { proc_poll(p); p->pending_zero_first = false; if (!p->running) { silence_from(0); return FW_PROC_DROP_PROCESSOR; } }  // :76-84
+    if (!p->plan || T == 0) { silence_from(0); return FW_PROC_OK; }                        // :86-89
+    // drain the command ring (sampler.rs:331 / volume.rs:92 happen at block granularity below)
+    {
+        Cmd m;
+        bool any = false;
+        while (p->pend_n < p->pend.size() && p->ch->cmds.pop(&m)) { p->pend[p->pend_n++] = m; any = true; }
+        if (any) {
+            p->ch->drain_epoch.fetch_add(1, std::memory_order_release);
+            for (size_t i = 1; i < p->pend_n; ++i) {  // stable insertion sort by block: push order is almost always sorted already
+                if (p->pend[i].block >= p->pend[i - 1].block) continue;
+                Cmd key = p->pend[i]; size_t j = i;
+                while (j > 0 && p->pend[j - 1].block > key.block) { p->pend[j] = p->pend[j - 1]; --j; }
+                p->pend[j] = key;
+            }
+        }
+    }
+    const uint32_t F = p->max_block_frames, n_blocks = (T + F - 1) / F;
+    p->first_epoch_of_call = p->call_epoch + 1;
+    uint32_t b = 0; size_t next_cmd = 0;  // pend[next_cmd..) have block >= b
+    int rc = FW_PROC_OK;
+    while (b < n_blocks) {
+        proc_poll(p);                                                                        // process_block :214
+        if (!p->running) { silence_from(b * F); rc = FW_PROC_DROP_PROCESSOR; break; }        // :150-155
+        Plan& pl = *p->plan;
+        if (n_in != pl.c_in || n_out != pl.c_out) { g_dev_err = "channel counts do not match the compiled graph"; return FW_PROC_BAD_ARGS; }
+        if (b == 0) for (auto& st : pl.states) if (!st->snapshot_params(p->stream)) return FW_PROC_DEVICE_ERROR;
+        while (next_cmd < p->pend_n && p->pend[next_cmd].block < b) ++next_cmd;
+        const bool have_cmds = next_cmd < p->pend_n && p->pend[next_cmd].block == b;
+        if (have_cmds || !pl.samplers.empty()) { if (!apply_commands(p, pl, b)) return FW_PROC_DEVICE_ERROR; }
+        size_t nc = next_cmd; while (nc < p->pend_n && p->pend[nc].block == b) ++nc;
+        uint32_t b_end = std::min(n_blocks, b + pl.chunk_blocks);
+        if (nc < p->pend_n && p->pend[nc].block < b_end) b_end = p->pend[nc].block;          // the next timed command splits the call
+        next_cmd = nc;
+        Chunk ck{b * F, std::min(T, b_end * F) - b * F, T, 0};
+        if (p->pending_zero_first) { ck.zero_first = std::min(pl.block_frames, ck.Tc); p->pending_zero_first = false; }  // Q11
+        const int erc = enqueue_chunk(p, pl, d_in, d_out, n_out, ck);
+        if (erc != FW_PROC_OK) return erc;
+        b = b_end;
+    }
+    // commands beyond this call stay queued, their block offsets re-based to the next call
+    size_t keep = 0;
+    for (size_t i = 0; i < p->pend_n; ++i) if (p->pend[i].block >= n_blocks) { Cmd m = p->pend[i]; m.block -= n_blocks; p->pend[keep++] = m; }
+    p->pend_n = keep;
+    return rc;
 }
 
 static uint64_t bus_mask_from(const uint64_t* masks, uint32_t V, uint32_t n_out) {
@@ -1620,7 +1762,16 @@ static uint64_t bus_mask_from(const uint64_t* masks, uint32_t V, uint32_t n_out)
 int fw_processor_process_planar_device(fw_processor* p, const float* d_in, float* d_out, uint32_t n_in, uint32_t n_out, uint64_t frames, double stream_time_secs, uint32_t stream_status) {
     if (!p) return FW_PROC_BAD_ARGS;
     p->cur_stream_time = stream_time_secs; p->cur_stream_status = stream_status;
-    return proc_enqueue(p, d_in, d_out, n_in, n_out, frames);
+    return proc_call(p, d_in, d_out, n_in, n_out, frames);
+}
+
+// error word of the plan: (chunk epoch << 4) | code, written by the control kernel (1: record budget) or the exchange (2: peer time-out)
+static int check_device_error(fw_processor* p) {
+    if (!p->plan) return 0;
+    const uint32_t e = *p->h_err;
+    if ((e & 15u) == 0 || (int32_t)((e >> 4) - (p->first_epoch_of_call & 0x0fffffffu)) < 0) return 0;
+    g_dev_err = (e & 15u) == 2 ? "master-bus exchange timed out waiting for a peer rank" : "control pass overflowed its transient-block budget (a gain jump beyond 10000 %?)";
+    return FW_PROC_DEVICE_ERROR;
 }
 
 int fw_processor_process_planar(fw_processor* p, const float* in, float* out, uint32_t n_in, uint32_t n_out, uint64_t frames, double stream_time_secs, uint32_t stream_status, uint64_t* out_mask) {
@@ -1628,14 +1779,22 @@ int fw_processor_process_planar(fw_processor* p, const float* in, float* out, ui
     p->cur_stream_time = stream_time_secs; p->cur_stream_status = stream_status;
     cudaSetDevice(p->device);
     const uint32_t V = p->num_voices;
-    const size_t in_elems = (size_t)V * n_in * frames, out_elems = (size_t)(p->bus ? 1 : V) * n_out * frames;
+    const size_t in_rows = (size_t)V * n_in, out_rows = (size_t)(p->bus ? 1 : V) * n_out;
     if (out_mask) *out_mask = 0;
-    if (!ensure(&p->d_in, &p->cap_in, in_elems) || !ensure(&p->d_out, &p->cap_out, out_elems)) return FW_PROC_DEVICE_ERROR;
-    if (in_elems && !FW_CUDA(cudaMemcpyAsync(p->d_in, in, in_elems * 4, cudaMemcpyHostToDevice, p->stream))) return FW_PROC_DEVICE_ERROR;
-    int rc = proc_enqueue(p, p->d_in, p->d_out, n_in, n_out, frames);
-    if (rc < 0) return rc;
-    join_side(p);
-    if (out_elems && !FW_CUDA(cudaMemcpyAsync(out, p->d_out, out_elems * 4, cudaMemcpyDeviceToHost, p->stream))) return FW_PROC_DEVICE_ERROR;
+    if (n_in != p->n_in || n_out != p->n_out) { g_dev_err = "channel counts do not match the activated stream"; return FW_PROC_BAD_ARGS; }
+    int rc = FW_PROC_OK;
+    uint64_t t0 = 0;
+    const uint32_t first_epoch = p->call_epoch + 1;
+    do {  // host chunks of at most max_call_frames: the staging buffers were sized for that at activate
+        const uint64_t Tc = std::min<uint64_t>(frames - t0, p->max_call_frames);
+        if (in_rows && Tc && !FW_CUDA(cudaMemcpy2DAsync(p->d_in, Tc * 4, in + t0, frames * 4, Tc * 4, in_rows, cudaMemcpyHostToDevice, p->stream))) return FW_PROC_DEVICE_ERROR;
+        rc = proc_call(p, p->d_in, p->d_out, n_in, n_out, Tc);
+        if (rc < 0) return rc;
+        join_side(p);
+        if (out_rows && Tc && !FW_CUDA(cudaMemcpy2DAsync(out + t0, frames * 4, p->d_out, Tc * 4, Tc * 4, out_rows, cudaMemcpyDeviceToHost, p->stream))) return FW_PROC_DEVICE_ERROR;
+        t0 += Tc;
+    } while (t0 < frames && rc == FW_PROC_OK);
+    if (rc == FW_PROC_DROP_PROCESSOR && t0 < frames) for (size_t r = 0; r < out_rows; ++r) std::memset(out + r * frames + t0, 0, (frames - t0) * 4);
     const bool ran = rc == FW_PROC_OK && p->plan && frames > 0;
     if (ran) {
         cudaMemcpyAsync(p->h_masks, p->plan->rec.gout_mask, sizeof(uint64_t) * V, cudaMemcpyDeviceToHost, p->stream);
@@ -1643,7 +1802,8 @@ int fw_processor_process_planar(fw_processor* p, const float* in, float* out, ui
     }
     if (!FW_CUDA(cudaStreamSynchronize(p->stream))) return FW_PROC_DEVICE_ERROR;
     if (ran) {
-        if (*p->h_err) { g_dev_err = *p->h_err == 2 ? "master-bus exchange timed out waiting for a peer rank" : "control pass overflowed its transient-block budget"; return FW_PROC_DEVICE_ERROR; }
+        p->first_epoch_of_call = first_epoch;
+        if (check_device_error(p)) return FW_PROC_DEVICE_ERROR;
         if (out_mask) *out_mask = p->bus ? bus_mask_from(p->h_masks, V, n_out) : p->h_masks[0];
     }
     return rc;
@@ -1654,29 +1814,38 @@ int fw_processor_process_interleaved(fw_processor* p, const float* in, float* ou
     p->cur_stream_time = stream_time_secs; p->cur_stream_status = stream_status;
     cudaSetDevice(p->device);
     const uint32_t V = p->num_voices, Vo = p->bus ? 1 : V;
-    const size_t in_elems = (size_t)V * n_in * frames, out_elems = (size_t)Vo * n_out * frames;
-    const size_t inter_elems = in_elems > out_elems ? in_elems : out_elems;
-    if (!ensure(&p->d_in, &p->cap_in, in_elems) || !ensure(&p->d_out, &p->cap_out, out_elems) || !ensure(&p->d_inter, &p->cap_inter, inter_elems)) return FW_PROC_DEVICE_ERROR;
-    if (in_elems) {
-        if (!FW_CUDA(cudaMemcpyAsync(p->d_inter, in, in_elems * 4, cudaMemcpyHostToDevice, p->stream))) return FW_PROC_DEVICE_ERROR;
-        if (!FW_CUDA(launch_deinterleave(p->d_inter, p->d_in, V, n_in, (uint32_t)frames, p->stream))) return FW_PROC_DEVICE_ERROR;
-        p->launches++;
-    }
-    int rc = proc_enqueue(p, p->d_in, p->d_out, n_in, n_out, frames);
-    if (rc < 0) return rc;
-    join_side(p);
-    if (out_elems) {
-        const bool ran = rc == FW_PROC_OK && p->plan && frames > 0;
-        const uint64_t* masks = nullptr;
-        if (ran) {
-            if (p->bus) { launch_bus_mask(p->plan->rec.gout_mask, V, n_out, p->plan->d_bus_mask, p->stream); p->launches++; masks = p->plan->d_bus_mask; }
-            else masks = p->plan->rec.gout_mask;
+    if (n_in != p->n_in || n_out != p->n_out) { g_dev_err = "channel counts do not match the activated stream"; return FW_PROC_BAD_ARGS; }
+    int rc = FW_PROC_OK;
+    uint64_t t0 = 0;
+    const uint32_t first_epoch = p->call_epoch + 1;
+    do {
+        const uint64_t Tc = std::min<uint64_t>(frames - t0, p->max_call_frames);
+        if (n_in && Tc) {  // voice v's frames [t0, t0 + Tc) are one contiguous run of Tc * n_in floats
+            if (!FW_CUDA(cudaMemcpy2DAsync(p->d_inter, Tc * n_in * 4, in + t0 * n_in, frames * n_in * 4, Tc * n_in * 4, V, cudaMemcpyHostToDevice, p->stream))) return FW_PROC_DEVICE_ERROR;
+            if (!FW_CUDA(launch_deinterleave(p->d_inter, p->d_in, V, n_in, (uint32_t)Tc, p->stream))) return FW_PROC_DEVICE_ERROR;
+            p->launches++;
         }
-        if (!FW_CUDA(launch_interleave(p->d_out, p->d_inter, masks, Vo, n_out, (uint32_t)frames, p->max_block_frames, p->stream))) return FW_PROC_DEVICE_ERROR;
-        p->launches++;
-        if (!FW_CUDA(cudaMemcpyAsync(out, p->d_inter, out_elems * 4, cudaMemcpyDeviceToHost, p->stream))) return FW_PROC_DEVICE_ERROR;
-    }
+        rc = proc_call(p, p->d_in, p->d_out, n_in, n_out, Tc);
+        if (rc < 0) return rc;
+        join_side(p);
+        if (n_out && Tc) {
+            const bool ran = rc == FW_PROC_OK && p->plan;
+            const uint64_t* masks = nullptr;
+            if (ran) {
+                if (p->bus) { launch_bus_mask(p->plan->rec.gout_mask, V, n_out, p->plan->d_bus_mask, p->stream); p->launches++; masks = p->plan->d_bus_mask; }
+                else masks = p->plan->rec.gout_mask;
+            }
+            if (!FW_CUDA(launch_interleave(p->d_out, p->d_inter, masks, Vo, n_out, (uint32_t)Tc, p->max_block_frames, p->stream))) return FW_PROC_DEVICE_ERROR;
+            p->launches++;
+            if (!FW_CUDA(cudaMemcpy2DAsync(out + t0 * n_out, frames * n_out * 4, p->d_inter, Tc * n_out * 4, Tc * n_out * 4, Vo, cudaMemcpyDeviceToHost, p->stream))) return FW_PROC_DEVICE_ERROR;
+        }
+        t0 += Tc;
+    } while (t0 < frames && rc == FW_PROC_OK);
+    if (rc == FW_PROC_DROP_PROCESSOR && t0 < frames) for (size_t v = 0; v < Vo; ++v) std::memset(out + (v * frames + t0) * n_out, 0, (frames - t0) * n_out * 4);
+    const bool ran = rc == FW_PROC_OK && p->plan && frames > 0;
+    if (ran) cudaMemcpyAsync(p->h_err, p->plan->rec.error, sizeof(uint32_t), cudaMemcpyDeviceToHost, p->stream);
     if (!FW_CUDA(cudaStreamSynchronize(p->stream))) return FW_PROC_DEVICE_ERROR;
+    if (ran) { p->first_epoch_of_call = first_epoch; if (check_device_error(p)) return FW_PROC_DEVICE_ERROR; }
     return rc;
 }
 
@@ -1688,7 +1857,7 @@ void fw_processor_free(fw_processor* p) {  // Drop processor.rs:251-263
     if (p->side) { cudaStreamSynchronize(p->side); p2p_teardown(p); cudaStreamDestroy(p->side); cudaEventDestroy(p->ev_bus_ready); cudaEventDestroy(p->ev_exchange_done); }
     ProcToCtx m; m.kind = 1; m.plan = p->plan; m.user_cx = p->user_cx;
     if (!p->ch->to_ctx.push(m)) delete p->plan;
-    cudaFree(p->d_in); cudaFree(p->d_out); cudaFree(p->d_inter); cudaFree(p->d_part[0]); cudaFree(p->d_part[1]); cudaFree(p->d_flush); cudaFree(p->d_tmp[0]); cudaFree(p->d_tmp[1]); cudaFree(p->d_bus_local); cudaFree(p->d_gather); cudaFree(p->d_pool); cudaFree(p->d_slot_of);
+    cudaFree(p->d_in); cudaFree(p->d_out); cudaFree(p->d_inter); cudaFree(p->d_flush); cudaFree(p->d_bus_local); cudaFree(p->d_gather);
     if (p->nccl_comm) g_nccl.CommDestroy(p->nccl_comm);
     cudaFreeHost(p->h_masks); cudaFreeHost(p->h_err);
     for (auto& e : p->ev) if (e) cudaEventDestroy(e);
@@ -1710,7 +1879,7 @@ int fw_processor_sync(fw_processor* p) {
     cudaSetDevice(p->device);
     join_side(p);
     if (!FW_CUDA(cudaStreamSynchronize(p->stream))) return -1;
-    if (p->plan) { uint32_t e = 0; cudaMemcpy(&e, p->plan->rec.error, 4, cudaMemcpyDeviceToHost); if (e) { g_dev_err = "control pass overflowed its transient-block budget"; return -1; } }
+    if (p->plan) { cudaMemcpy(p->h_err, p->plan->rec.error, 4, cudaMemcpyDeviceToHost); p->first_epoch_of_call = p->synced_epoch + 1; p->synced_epoch = p->call_epoch; if (check_device_error(p)) return -1; }
     return 0;
 }
 int fw_processor_event_record(fw_processor* p, int slot) { if (slot < 0 || slot > 3) return -1; cudaSetDevice(p->device); join_side(p); return FW_CUDA(cudaEventRecord(p->ev[slot], p->stream)) ? 0 : -1; }
@@ -1849,6 +2018,8 @@ int fw_processor_comm_init(fw_processor* p, int rank, int world, const uint8_t* 
     if (!FW_CUDA(cudaStreamCreateWithPriority(&p->side, cudaStreamNonBlocking, prio_hi)) || !FW_CUDA(cudaEventCreateWithFlags(&p->ev_bus_ready, cudaEventDisableTiming)) ||
         !FW_CUDA(cudaEventCreateWithFlags(&p->ev_exchange_done, cudaEventDisableTiming))) return -1;
     p->rank = rank; p->world = world;
+    p->d_bus_local = dev_alloc<float>((size_t)p->n_out * p->max_call_frames, false); p->d_gather = dev_alloc<float>((size_t)world * p->n_out * p->max_call_frames, false);
+    if (!p->d_bus_local || !p->d_gather) return -1;
     if (!p2p_setup(p)) return -1;
     return 0;
 }

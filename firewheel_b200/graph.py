@@ -149,6 +149,7 @@ class AudioGraphConfig:  # graph.rs:91-107 + batching
     num_voices: int = 1
     master_bus: bool = False
     device: int = 0
+    max_call_frames: int = 0  # product: device memory is reserved for stretches of this many frames (0 = 64 blocks); longer calls are chunked
 
 
 @dataclass
@@ -279,6 +280,11 @@ class AudioGraph:
         return out, self._lib.schedule_num_buffers(self._ctx)
 
     # ---- parameters -------------------------------------------------------------------------
+    def set_event_block(self, block):
+        """Stamp the parameter stores and sampler / resampler messages that follow with a block offset into the next process call
+        (0 = at its start); see include/fw_b200.h ctx_set_event_block."""
+        self._lib.ctx_set_event_block(self._ctx, int(block))
+
     def _chk(self, rc, what):
         if rc != 0:
             raise ValueError(f"{what}: node is not of that kind / bad voice index")
@@ -510,7 +516,7 @@ class FirewheelGraphCtx:
         gc = graph_config or AudioGraphConfig()
         self.config = gc
         c = K.GraphConfig(gc.num_graph_inputs, gc.num_graph_outputs, gc.initial_node_capacity, gc.initial_edge_capacity,
-                          gc.num_voices, int(gc.master_bus), gc.device, 0)
+                          gc.num_voices, int(gc.master_bus), gc.device, int(gc.max_call_frames))
         self._ctx = lib.ctx_new(C.byref(c))
         if not self._ctx:
             raise RuntimeError("ctx_new failed: " + (lib.last_device_error() or b"").decode())

@@ -60,7 +60,9 @@ typedef struct fw_graph_config {
     uint32_t num_voices;            /* >= 1 */
     uint32_t master_bus;            /* 0 | 1 */
     int32_t device;                 /* CUDA ordinal (ignored by the oracle) */
-    uint32_t reserved;
+    uint32_t max_call_frames;       /* product: all per-call device memory is reserved at activate / update for stretches of this many
+                                       frames (0 = 64 blocks of max_block_frames); a longer process_* call is processed as consecutive
+                                       chunks — same samples, more launches. The stream side never allocates. */
 } fw_graph_config;
 
 /* Built-in node kinds. The Rust side constructs `impl Into<Box<dyn AudioNode>>`
@@ -276,7 +278,16 @@ FW_EXPORT uint32_t FW_FN(schedule_len)(fw_ctx* ctx);                            
 FW_EXPORT uint32_t FW_FN(schedule_num_buffers)(fw_ctx* ctx);                        /* schedule.rs:171 */
 FW_EXPORT int FW_FN(schedule_node)(fw_ctx* ctx, uint32_t i, fw_scheduled_node* out);
 
-/* ---- node parameters (main-thread side; relaxed-atomic stores in the reference) -------- */
+/* ---- node parameters (main-thread side; relaxed-atomic stores in the reference) --------
+ * The reference's processor polls per block: it drains its message ring and loads the atomic parameters at the top of every
+ * process_block (processor.rs:214, volume.rs:92, sampler.rs:331), so a host that calls once per block places every store at a
+ * block boundary of its choice. A batched call (K blocks) keeps that control: set_event_block(b) stamps the parameter stores
+ * and sampler / resampler messages that FOLLOW with block offset b, counted from the first block of the NEXT process_* call;
+ * they take effect exactly there (b = 0, the default: at the start of that call — the reference's behaviour for K = 1). Offsets
+ * beyond that call carry over to the following one. Graph edits (ctx_update -> new schedule) and Stop are picked up at the
+ * start of a call and at every boundary the call is split at; to swap a schedule at a chosen block, split the call there, as
+ * a device callback period would. No call in this section takes a lock or blocks. */
+FW_EXPORT void FW_FN(ctx_set_event_block)(fw_ctx* ctx, uint32_t block);
 FW_EXPORT int FW_FN(volume_set_percent_volume)(fw_ctx* ctx, fw_node_id node, uint32_t voice, float percent); /* volume.rs:28 */
 FW_EXPORT int FW_FN(volume_set_percent_volumes)(fw_ctx* ctx, fw_node_id node, const float* percent, uint32_t n_voices);
 FW_EXPORT int FW_FN(pan_set_pan)(fw_ctx* ctx, fw_node_id node, uint32_t voice, float pan);

@@ -10,6 +10,8 @@
 #include "fw_oracle.hpp"
 
 #include <chrono>
+#include <array>
+#include <functional>
 #include <cstdio>
 #include <cstdlib>
 #include <thread>
@@ -27,7 +29,27 @@ struct fw_ctx {
     std::string last_error;
     fw_processor* live_processor = nullptr;
     std::vector<std::shared_ptr<const SampleResource>> resources;  // handle - 1
+    // ctx_set_event_block: stores / messages stamped with a block offset into the next process call. The reference's processor
+    // polls per block (processor.rs:214), so "at block b" is simply: process b blocks, perform the store, go on — which is what
+    // the process loop below does with this list.
+    uint32_t event_block = 0;
+    struct Deferred { uint32_t block; std::function<void()> fn; };
+    std::vector<Deferred> deferred;
 };
+// run `fn` now (event block 0) or when the process loop reaches the stamped block
+template <class F> static int defer_or_run(fw_ctx* c, int rc_ok, F&& fn) {
+    if (c->event_block == 0 || !c->voices[0]->is_activated()) return fn();
+    c->deferred.push_back(fw_ctx::Deferred{c->event_block, [fn]() { (void)fn(); }});
+    return rc_ok;
+}
+static void run_deferred_at(fw_ctx* c, uint32_t block) {
+    for (size_t i = 0; i < c->deferred.size(); ++i) if (c->deferred[i].block == block) c->deferred[i].fn();
+}
+static void rebase_deferred(fw_ctx* c, uint32_t n_blocks) {
+    std::vector<fw_ctx::Deferred> keep;
+    for (auto& d : c->deferred) if (d.block >= n_blocks) keep.push_back(fw_ctx::Deferred{d.block - n_blocks, d.fn});
+    c->deferred.swap(keep);
+}
 struct fw_processor {
     fw_ctx* ctx;
     std::vector<std::unique_ptr<FirewheelProcessor>> procs;
@@ -180,6 +202,7 @@ void fwo_ctx_free(fw_ctx* c) {
     delete c;
 }
 const char* fwo_ctx_last_error(fw_ctx* c) { return c ? c->last_error.c_str() : "null context"; }
+void fwo_ctx_set_event_block(fw_ctx* c, uint32_t block) { if (c) c->event_block = block; }
 fw_node_id fwo_graph_in_node(fw_ctx* c) { return pack(c->voices[0]->graph.graph_in_node().idx); }
 fw_node_id fwo_graph_out_node(fw_ctx* c) { return pack(c->voices[0]->graph.graph_out_node().idx); }
 
@@ -310,38 +333,42 @@ int fwo_schedule_node(fw_ctx* c, uint32_t i, fw_scheduled_node* out) {
 }
 
 // ---- parameters -------------------------------------------------------------------------------
-int fwo_volume_set_percent_volume(fw_ctx* c, fw_node_id node, uint32_t voice, float pct) {
+static int volume_set_percent_volume_now(fw_ctx* c, fw_node_id node, uint32_t voice, float pct) {
     int ok = -1;
     each_voice(c, voice, [&](FirewheelGraphCtx& v) { if (auto* n = dynamic_cast<VolumeNode*>(v.graph.node(nid(node)))) { n->set_percent_volume(pct); ok = 0; } });
     return ok;
 }
+int fwo_volume_set_percent_volume(fw_ctx* c, fw_node_id node, uint32_t voice, float pct) { return defer_or_run(c, 0, [=]() { return volume_set_percent_volume_now(c, node, voice, pct); }); }
 int fwo_volume_set_percent_volumes(fw_ctx* c, fw_node_id node, const float* pct, uint32_t n) {
     if (n != c->voices.size()) return -1;
     for (uint32_t v = 0; v < n; ++v) if (fwo_volume_set_percent_volume(c, node, v, pct[v]) != 0) return -1;
     return 0;
 }
-int fwo_pan_set_pan(fw_ctx* c, fw_node_id node, uint32_t voice, float pan) {
+static int pan_set_pan_now(fw_ctx* c, fw_node_id node, uint32_t voice, float pan) {
     int ok = -1;
     each_voice(c, voice, [&](FirewheelGraphCtx& v) { if (auto* n = dynamic_cast<PanNode*>(v.graph.node(nid(node)))) { n->set_pan(pan); ok = 0; } });
     return ok;
 }
+int fwo_pan_set_pan(fw_ctx* c, fw_node_id node, uint32_t voice, float pan) { return defer_or_run(c, 0, [=]() { return pan_set_pan_now(c, node, voice, pan); }); }
 int fwo_pan_set_pans(fw_ctx* c, fw_node_id node, const float* pan, uint32_t n) {
     if (n != c->voices.size()) return -1;
     for (uint32_t v = 0; v < n; ++v) if (fwo_pan_set_pan(c, node, v, pan[v]) != 0) return -1;
     return 0;
 }
-int fwo_pan_set_gains(fw_ctx* c, fw_node_id node, uint32_t voice, float gl, float gr) {
+static int pan_set_gains_now(fw_ctx* c, fw_node_id node, uint32_t voice, float gl, float gr) {
     int ok = -1;
     each_voice(c, voice, [&](FirewheelGraphCtx& v) { if (auto* n = dynamic_cast<PanNode*>(v.graph.node(nid(node)))) { n->set_gains(gl, gr); ok = 0; } });
     return ok;
 }
-int fwo_biquad_set_coeffs(fw_ctx* c, fw_node_id node, uint32_t voice, uint32_t stage, const float* k) {
+int fwo_pan_set_gains(fw_ctx* c, fw_node_id node, uint32_t voice, float gl, float gr) { return defer_or_run(c, 0, [=]() { return pan_set_gains_now(c, node, voice, gl, gr); }); }
+static int biquad_set_coeffs_now(fw_ctx* c, fw_node_id node, uint32_t voice, uint32_t stage, const float* k) {
     int ok = -1;
     each_voice(c, voice, [&](FirewheelGraphCtx& v) {
         if (auto* n = dynamic_cast<BiquadNode*>(v.graph.node(nid(node)))) if (stage < n->params->num_stages) { n->params->st[stage] = BiquadCoeffs{k[0], k[1], k[2], k[3], k[4]}; ok = 0; }
     });
     return ok;
 }
+int fwo_biquad_set_coeffs(fw_ctx* c, fw_node_id node, uint32_t voice, uint32_t stage, const float* k) { if (!k) return -1; std::array<float, 5> kk; std::copy(k, k + 5, kk.begin()); return defer_or_run(c, 0, [=]() { return biquad_set_coeffs_now(c, node, voice, stage, kk.data()); }); }
 int fwo_biquad_set_all_coeffs(fw_ctx* c, fw_node_id node, const float* k, uint32_t nv, uint32_t ns) {
     if (nv != c->voices.size()) return -1;
     for (uint32_t v = 0; v < nv; ++v) for (uint32_t s = 0; s < ns; ++s) if (fwo_biquad_set_coeffs(c, node, v, s, k + ((size_t)v * ns + s) * 5) != 0) return -1;
@@ -368,13 +395,14 @@ void fwo_biquad_design_rbj(uint32_t type, double fc, double q, double gain_db, d
 }
 
 // ---- SVF + polyphase resampler (spec ours) ----------------------------------------------------
-int fwo_svf_set_coeffs(fw_ctx* c, fw_node_id node, uint32_t voice, uint32_t stage, const float* k) {
+static int svf_set_coeffs_now(fw_ctx* c, fw_node_id node, uint32_t voice, uint32_t stage, const float* k) {
     int ok = -1;
     each_voice(c, voice, [&](FirewheelGraphCtx& v) {
         if (auto* n = dynamic_cast<SvfNode*>(v.graph.node(nid(node)))) if (stage < n->params->num_stages) { n->params->st[stage] = SvfCoeffs{k[0], k[1], k[2], k[3], k[4], k[5]}; ok = 0; }
     });
     return ok;
 }
+int fwo_svf_set_coeffs(fw_ctx* c, fw_node_id node, uint32_t voice, uint32_t stage, const float* k) { if (!k) return -1; std::array<float, 6> kk; std::copy(k, k + 6, kk.begin()); return defer_or_run(c, 0, [=]() { return svf_set_coeffs_now(c, node, voice, stage, kk.data()); }); }
 int fwo_svf_set_all_coeffs(fw_ctx* c, fw_node_id node, const float* k, uint32_t nv, uint32_t ns) {
     if (nv != c->voices.size()) return -1;
     for (uint32_t v = 0; v < nv; ++v) for (uint32_t s = 0; s < ns; ++s) if (fwo_svf_set_coeffs(c, node, v, s, k + ((size_t)v * ns + s) * 6) != 0) return -1;
@@ -394,7 +422,7 @@ void fwo_svf_design(uint32_t type, double fc, double q, double sr, float* out) {
     }
     out[0] = (float)a1; out[1] = (float)a2; out[2] = (float)a3; out[3] = (float)m0; out[4] = (float)m1; out[5] = (float)m2;
 }
-int fwo_resampler_set(fw_ctx* c, fw_node_id node, uint32_t voice, uint32_t res, uint64_t step, int playing, int loop) {
+static int resampler_set_now(fw_ctx* c, fw_node_id node, uint32_t voice, uint32_t res, uint64_t step, int playing, int loop) {
     if (!c || res > c->resources.size()) return -1;
     int ok = -1;
     each_voice(c, voice, [&](FirewheelGraphCtx& v) {
@@ -402,11 +430,13 @@ int fwo_resampler_set(fw_ctx* c, fw_node_id node, uint32_t voice, uint32_t res, 
     });
     return ok;
 }
-int fwo_resampler_seek(fw_ctx* c, fw_node_id node, uint32_t voice, uint64_t pos_frames) {
+int fwo_resampler_set(fw_ctx* c, fw_node_id node, uint32_t voice, uint32_t res, uint64_t step, int playing, int loop) { return defer_or_run(c, 0, [=]() { return resampler_set_now(c, node, voice, res, step, playing, loop); }); }
+static int resampler_seek_now(fw_ctx* c, fw_node_id node, uint32_t voice, uint64_t pos_frames) {
     int ok = -1;
     each_voice(c, voice, [&](FirewheelGraphCtx& v) { if (auto* n = dynamic_cast<ResamplerNode*>(v.graph.node(nid(node)))) { n->sh->seek_pending = true; n->sh->seek_frames = pos_frames; ok = 0; } });
     return ok;
 }
+int fwo_resampler_seek(fw_ctx* c, fw_node_id node, uint32_t voice, uint64_t pos_frames) { return defer_or_run(c, 0, [=]() { return resampler_seek_now(c, node, voice, pos_frames); }); }
 static double bessel_i0(double x) { double s = 1.0, t = 1.0; for (int k = 1; k < 64; ++k) { t *= (x / (2.0 * k)) * (x / (2.0 * k)); s += t; if (t < 1e-18 * s) break; } return s; }
 void fwo_resampler_design(uint32_t P, uint32_t T, double cutoff, double beta, float* table) {
     const double half = (double)T / 2.0, i0b = bessel_i0(beta);
@@ -430,15 +460,20 @@ uint32_t fwo_sample_resource_create(fw_ctx* c, uint32_t format, uint32_t channel
     c->resources.push_back(std::move(r));
     return (uint32_t)c->resources.size();
 }
-int fwo_sampler_set_sample(fw_ctx* c, fw_node_id node, uint32_t voice, uint32_t res, int stop_playback) {
+static int sampler_set_sample_now(fw_ctx* c, fw_node_id node, uint32_t voice, uint32_t res, int stop_playback) {
     if (!c || res == 0 || res > c->resources.size()) return FW_SAMPLER_BAD_ARGS;
     return each_sampler(c, node, voice, [&](SamplerNode& n) { return n.set_sample(c->resources[res - 1], stop_playback != 0); });
 }
-int fwo_sampler_play(fw_ctx* c, fw_node_id node, uint32_t voice) { return each_sampler(c, node, voice, [](SamplerNode& n) { return n.play(); }); }
-int fwo_sampler_pause(fw_ctx* c, fw_node_id node, uint32_t voice) { return each_sampler(c, node, voice, [](SamplerNode& n) { return n.pause(); }); }
-int fwo_sampler_stop(fw_ctx* c, fw_node_id node, uint32_t voice) { return each_sampler(c, node, voice, [](SamplerNode& n) { return n.stop(); }); }
-int fwo_sampler_set_playhead(fw_ctx* c, fw_node_id node, uint32_t voice, double secs) { return each_sampler(c, node, voice, [&](SamplerNode& n) { return n.set_playhead(secs); }); }
-int fwo_sampler_set_loop_range(fw_ctx* c, fw_node_id node, uint32_t voice, uint32_t mode, double s, double e) {
+int fwo_sampler_set_sample(fw_ctx* c, fw_node_id node, uint32_t voice, uint32_t res, int stop_playback) { return defer_or_run(c, 0, [=]() { return sampler_set_sample_now(c, node, voice, res, stop_playback); }); }
+static int sampler_play_now(fw_ctx* c, fw_node_id node, uint32_t voice) { return each_sampler(c, node, voice, [](SamplerNode& n) { return n.play(); }); }
+int fwo_sampler_play(fw_ctx* c, fw_node_id node, uint32_t voice) { return defer_or_run(c, 0, [=]() { return sampler_play_now(c, node, voice); }); }
+static int sampler_pause_now(fw_ctx* c, fw_node_id node, uint32_t voice) { return each_sampler(c, node, voice, [](SamplerNode& n) { return n.pause(); }); }
+int fwo_sampler_pause(fw_ctx* c, fw_node_id node, uint32_t voice) { return defer_or_run(c, 0, [=]() { return sampler_pause_now(c, node, voice); }); }
+static int sampler_stop_now(fw_ctx* c, fw_node_id node, uint32_t voice) { return each_sampler(c, node, voice, [](SamplerNode& n) { return n.stop(); }); }
+int fwo_sampler_stop(fw_ctx* c, fw_node_id node, uint32_t voice) { return defer_or_run(c, 0, [=]() { return sampler_stop_now(c, node, voice); }); }
+static int sampler_set_playhead_now(fw_ctx* c, fw_node_id node, uint32_t voice, double secs) { return each_sampler(c, node, voice, [&](SamplerNode& n) { return n.set_playhead(secs); }); }
+int fwo_sampler_set_playhead(fw_ctx* c, fw_node_id node, uint32_t voice, double secs) { return defer_or_run(c, 0, [=]() { return sampler_set_playhead_now(c, node, voice, secs); }); }
+static int sampler_set_loop_range_now(fw_ctx* c, fw_node_id node, uint32_t voice, uint32_t mode, double s, double e) {
     if (mode > 2) return FW_SAMPLER_BAD_ARGS;
     if (mode == 2 && c && !c->voices.empty()) {
         const uint32_t sr = c->voices[0]->sample_rate();
@@ -446,7 +481,9 @@ int fwo_sampler_set_loop_range(fw_ctx* c, fw_node_id node, uint32_t voice, uint3
     }
     return each_sampler(c, node, voice, [&](SamplerNode& n) { return n.set_loop_range(mode, s, e); });
 }
-int fwo_sampler_set_percent_volume(fw_ctx* c, fw_node_id node, uint32_t voice, float pct) { return each_sampler(c, node, voice, [&](SamplerNode& n) { n.set_percent_volume(pct); return 0; }); }
+int fwo_sampler_set_loop_range(fw_ctx* c, fw_node_id node, uint32_t voice, uint32_t mode, double s, double e) { return defer_or_run(c, 0, [=]() { return sampler_set_loop_range_now(c, node, voice, mode, s, e); }); }
+static int sampler_set_percent_volume_now(fw_ctx* c, fw_node_id node, uint32_t voice, float pct) { return each_sampler(c, node, voice, [&](SamplerNode& n) { n.set_percent_volume(pct); return 0; }); }
+int fwo_sampler_set_percent_volume(fw_ctx* c, fw_node_id node, uint32_t voice, float pct) { return defer_or_run(c, 0, [=]() { return sampler_set_percent_volume_now(c, node, voice, pct); }); }
 int fwo_sampler_is_playing(fw_ctx* c, fw_node_id node, uint32_t voice) {
     if (!c || voice >= c->voices.size()) return FW_SAMPLER_NOT_A_SAMPLER;
     auto* n = dynamic_cast<SamplerNode*>(c->voices[voice]->graph.node(nid(node)));
@@ -536,9 +573,12 @@ int fwo_processor_process_planar(fw_processor* p, const float* input, float* out
     BusArena& ar = g_arena;
     if (bus) ar.reserve(V, n_out, mbf);
     size_t done = 0;
+    uint32_t block = 0;
     // frames == 0 still polls messages like processor.rs:76-89
     do {
         size_t bf = std::min<size_t>(frames - done, mbf);
+        if (!p->ctx->deferred.empty()) run_deferred_at(p->ctx, block);  // stores stamped with this block (ctx_set_event_block)
+        ++block;
         for (size_t v = 0; v < V; ++v) {
             for (uint32_t c = 0; c < n_in; ++c) in_ptrs[c] = input + ((size_t)v * n_in + c) * frames + done;
             uint64_t m = 0; ProcessorStatus st;
@@ -565,6 +605,7 @@ int fwo_processor_process_planar(fw_processor* p, const float* input, float* out
         }
         done += bf;
     } while (done < frames);
+    if (!p->ctx->deferred.empty()) rebase_deferred(p->ctx, frames ? (uint32_t)((frames + mbf - 1) / mbf) : 0u);
     return rc;
 }
 
@@ -572,13 +613,29 @@ int fwo_processor_process_interleaved(fw_processor* p, const float* input, float
                                       double t, uint32_t status) {
     if (!p) return FW_PROC_BAD_ARGS;
     size_t V = p->procs.size(); bool bus = p->ctx->cfg.master_bus != 0;
-    if (!bus) {
+    if (!bus && p->ctx->deferred.empty()) {
         int rc = FW_PROC_OK;
         for (size_t v = 0; v < V; ++v) {
             ProcessorStatus st = p->procs[v]->process_interleaved(input + v * frames * n_in, frames * n_in, output + v * frames * n_out, frames * n_out,
                                                                   n_in, n_out, frames, t, status);
             if (st == ProcessorStatus::DropProcessor) rc = FW_PROC_DROP_PROCESSOR;
         }
+        return rc;
+    }
+    if (!bus) {  // stores stamped with a block offset: one device callback per block, the store in between (what a host of the reference does)
+        int rc = FW_PROC_OK;
+        const size_t mbf = p->max_block_frames;
+        uint32_t block = 0;
+        for (size_t done = 0; done < frames; done += mbf, ++block) {
+            const size_t bf = std::min<size_t>(frames - done, mbf);
+            run_deferred_at(p->ctx, block);
+            for (size_t v = 0; v < V; ++v) {
+                ProcessorStatus st = p->procs[v]->process_interleaved(input + (v * frames + done) * n_in, bf * n_in, output + (v * frames + done) * n_out, bf * n_out,
+                                                                      n_in, n_out, bf, t, status);
+                if (st == ProcessorStatus::DropProcessor) rc = FW_PROC_DROP_PROCESSOR;
+            }
+        }
+        rebase_deferred(p->ctx, (uint32_t)((frames + mbf - 1) / mbf));
         return rc;
     }
     // master bus: de-interleave per voice, run the planar path, interleave the bus with the root mask
