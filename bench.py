@@ -95,7 +95,7 @@ def build_graph(fw, lib, workload, V, block, device, seed):
     w = WORKLOADS[workload]
     sampler_src = w.get("src") == "sampler"
     cx = fw.FirewheelGraphCtx(lib, fw.AudioGraphConfig(num_graph_inputs=0 if sampler_src else w["ch"], num_graph_outputs=w["ch"], num_voices=V,
-                                                       master_bus=w["bus"], device=device))
+                                                       master_bus=w["bus"], device=device, max_call_frames=w["block"] * w["blocks"]))  # one step = one chunk
     g = cx.graph
     C = w["ch"]
     if workload == "c1":

@@ -147,6 +147,7 @@ SIGNATURES = {
     "processor_event_record": (_i32, [_vp, _i32]),
     "processor_event_elapsed_ms": (_f32, [_vp, _i32, _i32]),
     "processor_kernel_launches": (_u64, [_vp]),
+    "processor_graph_replays": (_u64, [_vp]),
     "processor_l2_flush": (_i32, [_vp]),
     "processor_profile": (_i32, [_vp, _i32]),
     "processor_profile_read": (_i32, [_vp, C.c_void_p, C.c_void_p]),

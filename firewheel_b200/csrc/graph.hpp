@@ -94,7 +94,9 @@ enum CmdKind : uint32_t {
     CMD_BIQUAD = 2,    // a = stage, f[0..4] = {b0, b1, b2, a1, a2}
     CMD_SVF = 3,       // a = stage, f[0..5] = {a1, a2, a3, m0, m1, m2}
     CMD_RS_SET = 4,    // b = resource, x = step (Q32.32), a = flags (bit0 playing, bit1 loop)
-    CMD_RS_SEEK = 5    // x = position in frames
+    CMD_RS_SEEK = 5,   // x = position in frames
+    CMD_UPLOAD = 6     // a whole parameter array at once (set_percent_volumes, set_all_coeffs ...): a = array (0 / 1: smoothed target 0 / 1,
+                       // 2: coefficient table), x = float* snapshot taken by the main thread (handed back through Channels::to_free), y = floats
 };
 struct Cmd { uint32_t kind, block, voice /* or FW_ALL_VOICES */, a, b, pad; uint64_t x, y; float f[6]; const NodeParams* node; };
 
@@ -102,9 +104,8 @@ struct Cmd { uint32_t kind, block, voice /* or FW_ALL_VOICES */, a, b, pad; uint
 struct NodeParams {
     uint32_t kind = FW_NODE_DUMMY;
     uint32_t num_voices = 1;
-    // Bumped (release) after every change of the arrays below; the stream side reads it (acquire) before copying them, so a new
-    // version is never observed with older values (the relaxed atomics of volume.rs:29-32, batched over voices).
-    std::atomic<uint64_t> version{1};
+    // The arrays below are the MAIN THREAD's view of the parameters: they seed the device state at activation. Once the context is
+    // active every store also travels through the command ring, in program order — the stream side never reads these arrays.
     std::shared_ptr<CustomNode> custom;  // kind == FW_NODE_CUSTOM
     // volume (volume.rs:8-34)
     std::vector<float> percent, raw_gain;

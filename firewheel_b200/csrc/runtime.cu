@@ -111,7 +111,6 @@ struct ResTable {
 struct NodeDeviceState {
     int device = 0; uint32_t kind = 0, V = 0, n_sm = 0;
     std::shared_ptr<NodeParams> params;
-    uint64_t uploaded_version = 0;
     float* d_target[2] = {nullptr, nullptr};      // volume: raw_gain; pan: gain_l, gain_r
     float* sm_input[2] = {nullptr, nullptr};
     float* sm_last[2] = {nullptr, nullptr};
@@ -204,7 +203,6 @@ struct NodeDeviceState {
             params->smp_active = true;  // activate() creates the rings (sampler.rs:204-212)
             std::fill(params->smp_pending.begin(), params->smp_pending.end(), (uint16_t)0);
         }
-        uploaded_version = params->version.load(std::memory_order_acquire);
         return true;
     }
     // ---- stream side -------------------------------------------------------------------------------------------------------
@@ -238,18 +236,9 @@ struct NodeDeviceState {
         cudaEventRecord(ev_staged, st); staged_pending = true;
         return ok;
     }
-    // at call start: the relaxed atomic load of volume.rs:92, batched — re-upload the arrays whose version moved
-    bool snapshot_params(cudaStream_t st) {
-        if (kind == FW_NODE_RESAMPLER) { res_table->snapshot(&cur_tab, &cur_n_res); return true; }
-        const uint64_t ver = params->version.load(std::memory_order_acquire);
-        if (ver == uploaded_version) return true;
-        for (uint32_t i = 0; i < n_sm; ++i)
-            if (!FW_CUDA(cudaMemcpyAsync(d_target[i], host_target(i).data(), V * 4, cudaMemcpyHostToDevice, st))) return false;
-        if (kind == FW_NODE_BIQUAD && params->num_stages &&
-            !FW_CUDA(cudaMemcpyAsync(d_coeffs, params->coeffs.data(), params->coeffs.size() * 4, cudaMemcpyHostToDevice, st))) return false;
-        if (kind == FW_NODE_SVF && params->num_stages &&
-            !FW_CUDA(cudaMemcpyAsync(d_coeffs, params->svf_coeffs.data(), params->svf_coeffs.size() * 4, cudaMemcpyHostToDevice, st))) return false;
-        uploaded_version = ver;
+    // at call start: pin the resource table a resampler reads during this call
+    bool snapshot_params(cudaStream_t) {
+        if (kind == FW_NODE_RESAMPLER) res_table->snapshot(&cur_tab, &cur_n_res);
         return true;
     }
 };
@@ -276,6 +265,7 @@ struct Plan {
     // Per-call scratch, sized on the main thread (lower()) for one chunk of at most `chunk_frames` frames: the stream side
     // never allocates (processor.rs:167-206, context.rs:61-64: the reference's audio thread does not either).
     uint32_t chunk_frames = 0, chunk_blocks = 0;
+    bool graphable = false;  // every by-value kernel argument of a chunk is a function of (buffers, frames): the launch sequence can be replayed as a CUDA graph
     float* d_part[2] = {nullptr, nullptr};     // partial buses [groups][c_out][chunk] and the next radix-16 level
     float* d_tmp[2] = {nullptr, nullptr};      // inter-stage scratch [V][2][chunk]
     float* d_pool = nullptr;                   // generic lowering: [buffer][V][chunk]
@@ -324,8 +314,10 @@ struct ProcToCtx { int kind = 0; Plan* plan = nullptr; void* user_cx = nullptr; 
 struct Channels {
     Spsc<CtxToProc> to_proc; Spsc<ProcToCtx> to_ctx;
     DynSpsc<Cmd> cmds;                        // sampler messages, timed parameter stores, resampler transport (see Cmd)
+    DynSpsc<float*> to_free;                  // CMD_UPLOAD snapshots on their way back to the main thread, which frees them
     std::atomic<uint32_t> drain_epoch{1};     // bumped by the stream side after it emptied `cmds` (per-voice ring-full accounting)
-    explicit Channels(size_t cmd_capacity) : cmds(cmd_capacity) {}
+    explicit Channels(size_t cmd_capacity) : cmds(cmd_capacity), to_free(cmd_capacity) {}
+    ~Channels() { float* q; while (to_free.pop(&q)) delete[] q; Cmd m; while (cmds.pop(&m)) if (m.kind == CMD_UPLOAD) delete[] reinterpret_cast<float*>(m.x); }
 };
 
 }  // namespace fw
@@ -357,6 +349,10 @@ struct fw_processor {
     float *d_in = nullptr, *d_out = nullptr, *d_inter = nullptr, *d_flush = nullptr;
     uint32_t max_call_frames = 0; uint32_t call_epoch = 0, first_epoch_of_call = 0, synced_epoch = 0;
     std::vector<Cmd> pend; size_t pend_n = 0; std::vector<const Cmd*> cmd_ptrs;  // drained commands not yet applied (preallocated at activate)
+    // CUDA-graph replay of steady chunks: the launch sequence of a chunk, captured once per (plan, buffers, frames)
+    struct GraphEntry { cudaGraphExec_t exec = nullptr; Plan* plan = nullptr; const float* d_in = nullptr; float* d_out = nullptr; uint32_t t0 = 0, Tc = 0, Tfull = 0;
+                        const void* tabs[2 * kMaxSamplers] = {}; uint32_t seen = 0; uint64_t stamp = 0; };
+    GraphEntry graphs[4]; uint64_t graph_stamp = 0, graph_replays = 0; bool capturing = false, graphs_off = false;
     // multi-GPU master bus: voices shard by rank; the per-rank buses are all-gathered and tree-summed in rank order
     void* nccl_comm = nullptr; int rank = 0, world = 1;
     float *d_bus_local = nullptr, *d_gather = nullptr;  // [n_out][chunk], [world][n_out][chunk]: allocated by comm_init
@@ -610,6 +606,11 @@ static bool lower(fw_ctx* c, const Schedule& s, Plan* plan, std::string* why) {
     }
     if (!plan->d_flags || !r.modes || !r.vals || !r.curves || !r.steady_k || !r.gout_mask || !r.error || !plan->d_bus_mask || !r.st_modes || !r.st_vals || !r.sum_masks || !r.st_sum_masks) { *why = g_dev_err; return false; }
     plan->tables = tb;
+    {   // delay cursors, reverb history cursors + tensor maps, resampler positions and plugin calls change from call to call
+        bool g = true;
+        for (auto& st : plan->states) if (st->kind == FW_NODE_DELAY || st->kind == FW_NODE_CONV_REVERB || st->kind == FW_NODE_RESAMPLER || st->kind == FW_NODE_CUSTOM) g = false;
+        plan->graphable = g;
+    }
     return true;
 }
 
@@ -828,13 +829,25 @@ template <class F> static void each_voice_of(NodeParams* p, uint32_t voice, F&& 
     if (voice == FW_ALL_VOICES) { for (uint32_t v = 0; v < p->num_voices; ++v) f(v); } else f(voice);
 }
 static bool push_cmd(fw_ctx* c, const Cmd& m) { return c->active && c->ch && c->ch->cmds.push(m); }
-// host-array store, then either a version bump (block 0) or a timed command
+static void drain_to_free(fw_ctx* c) { if (c->ch) { float* q; while (c->ch->to_free.pop(&q)) delete[] q; } }
+// store into the main thread's view; once active, the same store travels to the stream side as a command stamped with the
+// current event block (0: the start of the next call)
 template <class F> static int store_param(fw_ctx* c, NodeParams* p, uint32_t voice, Cmd m, F&& write_host) {
     if (!voice_ok(p, voice)) return -1;
     each_voice_of(p, voice, write_host);
-    if (c->event_block == 0 || !c->active) { p->version.fetch_add(1, std::memory_order_release); return 0; }
+    if (!c->active) return 0;
     m.block = c->event_block; m.voice = voice; m.node = p;
     return push_cmd(c, m) ? 0 : -2;  // -2: command ring full
+}
+// a whole array at once: the snapshot is taken here, uploaded by the stream side in ring order, and handed back for freeing
+static int upload_array(fw_ctx* c, NodeParams* p, uint32_t which, const float* data, size_t n) {
+    if (!c->active) return 0;
+    drain_to_free(c);
+    float* snap = new float[n ? n : 1];
+    std::memcpy(snap, data, n * sizeof(float));
+    Cmd m{}; m.kind = CMD_UPLOAD; m.block = c->event_block; m.voice = FW_ALL_VOICES; m.a = which; m.x = reinterpret_cast<uint64_t>(snap); m.y = n; m.node = p;
+    if (!push_cmd(c, m)) { delete[] snap; return -2; }
+    return 0;
 }
 // `(secs * sample_rate).round() as u64` (sampler.rs:250-251,394): saturating float -> int cast, NaN -> 0
 static uint64_t secs_to_frame(double secs, uint32_t sample_rate) {
@@ -886,10 +899,8 @@ int fw_svf_set_coeffs(fw_ctx* c, fw_node_id node, uint32_t voice, uint32_t stage
 int fw_svf_set_all_coeffs(fw_ctx* c, fw_node_id node, const float* k, uint32_t nv, uint32_t ns) {
     NodeParams* p = params_of(c, node, FW_NODE_SVF);
     if (!p || !k || nv != p->num_voices || ns != p->num_stages) return -1;
-    if (c->event_block && c->active) { int rc = 0; for (uint32_t v = 0; v < nv; ++v) for (uint32_t s = 0; s < ns; ++s) rc |= fw_svf_set_coeffs(c, node, v, s, k + ((size_t)v * ns + s) * 6); return rc; }
     std::memcpy(p->svf_coeffs.data(), k, (size_t)nv * ns * 6 * sizeof(float));
-    p->version.fetch_add(1, std::memory_order_release);
-    return 0;
+    return upload_array(c, p, 2, p->svf_coeffs.data(), p->svf_coeffs.size());
 }
 void fw_svf_design(uint32_t type, double fc, double q, double sr, float* out) {
     const double g = std::tan(M_PI * fc / sr), k = 1.0 / q;
@@ -982,10 +993,8 @@ int fw_volume_set_percent_volume(fw_ctx* c, fw_node_id node, uint32_t voice, flo
 int fw_volume_set_percent_volumes(fw_ctx* c, fw_node_id node, const float* pct, uint32_t n) {
     NodeParams* p = params_of(c, node, FW_NODE_VOLUME);
     if (!p || n != p->num_voices) return -1;
-    if (c->event_block && c->active) { int rc = 0; for (uint32_t v = 0; v < n; ++v) rc |= set_raw_gain(c, p, v, pct[v]); return rc; }
     for (uint32_t v = 0; v < n; ++v) { float x = std::fmax(pct[v], 0.0f) * (1.0f / 100.0f); p->raw_gain[v] = x * x; p->percent[v] = std::fmax(pct[v], 0.0f); }
-    p->version.fetch_add(1, std::memory_order_release);
-    return 0;
+    return upload_array(c, p, 0, p->raw_gain.data(), n);
 }
 static void pan_gains(float pan, float* gl, float* gr) {
     double pp = std::fmin(std::fmax((double)pan, -1.0), 1.0), th = (pp + 1.0) * (M_PI / 4.0);
@@ -994,7 +1003,7 @@ static void pan_gains(float pan, float* gl, float* gr) {
 static int set_pan_gains(fw_ctx* c, NodeParams* p, uint32_t voice, float gl, float gr, const float* pan) {
     if (!voice_ok(p, voice)) return -1;
     each_voice_of(p, voice, [&](uint32_t v) { p->gain_l[v] = gl; p->gain_r[v] = gr; if (pan) p->pan[v] = *pan; });
-    if (c->event_block == 0 || !c->active) { p->version.fetch_add(1, std::memory_order_release); return 0; }
+    if (!c->active) return 0;
     Cmd m{}; m.kind = CMD_TARGET; m.block = c->event_block; m.voice = voice; m.node = p;
     m.a = 0; m.f[0] = gl; const bool ok0 = push_cmd(c, m);
     m.a = 1; m.f[0] = gr; const bool ok1 = push_cmd(c, m);
@@ -1007,10 +1016,9 @@ int fw_pan_set_pan(fw_ctx* c, fw_node_id node, uint32_t voice, float pan) {
 int fw_pan_set_pans(fw_ctx* c, fw_node_id node, const float* pan, uint32_t n) {
     NodeParams* p = params_of(c, node, FW_NODE_PAN);
     if (!p || n != p->num_voices) return -1;
-    if (c->event_block && c->active) { int rc = 0; for (uint32_t v = 0; v < n; ++v) rc |= fw_pan_set_pan(c, node, v, pan[v]); return rc; }
     for (uint32_t v = 0; v < n; ++v) { p->pan[v] = pan[v]; pan_gains(pan[v], &p->gain_l[v], &p->gain_r[v]); }
-    p->version.fetch_add(1, std::memory_order_release);
-    return 0;
+    const int r0 = upload_array(c, p, 0, p->gain_l.data(), n), r1 = upload_array(c, p, 1, p->gain_r.data(), n);
+    return r0 ? r0 : r1;
 }
 int fw_pan_set_gains(fw_ctx* c, fw_node_id node, uint32_t voice, float gl, float gr) { return set_pan_gains(c, params_of(c, node, FW_NODE_PAN), voice, gl, gr, nullptr); }
 int fw_biquad_set_coeffs(fw_ctx* c, fw_node_id node, uint32_t voice, uint32_t stage, const float* k) {
@@ -1022,10 +1030,8 @@ int fw_biquad_set_coeffs(fw_ctx* c, fw_node_id node, uint32_t voice, uint32_t st
 int fw_biquad_set_all_coeffs(fw_ctx* c, fw_node_id node, const float* k, uint32_t nv, uint32_t ns) {
     NodeParams* p = params_of(c, node, FW_NODE_BIQUAD);
     if (!p || !k || nv != p->num_voices || ns != p->num_stages) return -1;
-    if (c->event_block && c->active) { int rc = 0; for (uint32_t v = 0; v < nv; ++v) for (uint32_t s = 0; s < ns; ++s) rc |= fw_biquad_set_coeffs(c, node, v, s, k + ((size_t)v * ns + s) * 5); return rc; }
     std::memcpy(p->coeffs.data(), k, (size_t)nv * ns * 5 * sizeof(float));
-    p->version.fetch_add(1, std::memory_order_release);
-    return 0;
+    return upload_array(c, p, 2, p->coeffs.data(), p->coeffs.size());
 }
 void fw_biquad_design_rbj(uint32_t type, double fc, double q, double gain_db, double sr, float* out) {  // RBJ cookbook, f64 -> f32
     const double w0 = 2.0 * M_PI * fc / sr, cw = std::cos(w0), sw = std::sin(w0), alpha = sw / (2.0 * q), A = std::pow(10.0, gain_db / 40.0);
@@ -1086,6 +1092,7 @@ int fw_ctx_is_activated(fw_ctx* c) { return c->active; }
 int fw_ctx_update(fw_ctx* c, fw_update_status* out) {  // context.rs:93-148
     fw_update_status st{}; st.kind = FW_UPDATE_INACTIVE; st.error_node = FW_ID_DANGLING;
     auto done = [&] { if (out) *out = st; return 0; };
+    drain_to_free(c);
     c->graph->each_node([&](Id, NodeRec& r) {  // self.graph.update() (context.rs:94, graph.rs:691-697)
         if (r.params->custom && r.params->custom->info.updates && r.params->custom->vt.update) r.params->custom->vt.update(r.params->custom->node);
     });
@@ -1100,6 +1107,18 @@ int fw_ctx_update(fw_ctx* c, fw_update_status* out) {  // context.rs:93-148
     plan->device = c->cfg.device;
     CompileError e = c->graph->compile_schedule(c->max_block_frames, &plan->sched);
     if (e.code != FW_COMPILE_OK) { st.graph_error = e.code; st.error_node = e.node.pack(); st.error_port = e.port; return done(); }
+    // A live node whose port count changed (set_num_inputs / set_num_outputs, graph.rs:315-393) no longer matches the per-channel
+    // state its device counterpart was sized for: it is activated again with the new counts (fresh state), the old state leaves
+    // with the outgoing plan.
+    c->graph->each_node([&](Id id, NodeRec& r) {
+        auto it = c->node_states.find(id.pack());
+        if (it == c->node_states.end()) return;
+        const uint32_t k = it->second->kind;
+        if ((k == FW_NODE_BIQUAD || k == FW_NODE_SVF || k == FW_NODE_DELAY || k == FW_NODE_CONV_REVERB) && it->second->channels != r.num_inputs) {
+            c->node_states.erase(it);
+            if (std::find(c->graph->nodes_to_activate.begin(), c->graph->nodes_to_activate.end(), id) == c->graph->nodes_to_activate.end()) c->graph->nodes_to_activate.push_back(id);
+        }
+    });
     // activate new nodes in queue order (graph.rs:593-612); a failure rolls back this round's activations
     std::vector<uint64_t> created;
     for (Id id : c->graph->nodes_to_activate) {
@@ -1169,6 +1188,7 @@ void* fw_ctx_deactivate(fw_ctx* c, int stream_is_running) {  // context.rs:162-2
             if (clock::now() - start > std::chrono::seconds(3)) dropped = true;
         }
     }
+    if (c->ch.use_count() == 1) { CtxToProc m; while (c->ch->to_proc.pop(&m)) delete m.plan; }  // the processor is gone: schedules it never adopted are released here
     ctx_graph_deactivate(c);
     c->active = false; c->ch.reset();
     return cx;
@@ -1192,6 +1212,7 @@ static void proc_poll(fw_processor* p) {  // processor.rs:167-206
             p->pending_zero_first = true;  // Q11: the swap happens after this block's inputs were written to the old pool
         }
         p->plan = m.plan;
+        for (auto& g : p->graphs) { if (g.exec) cudaGraphExecDestroy(g.exec); g = fw_processor::GraphEntry{}; }  // captured sequences point into the old plan
     }
 }
 // One chunk of a call: frames [t0, t0 + Tc) of rows that are Tfull frames long in the caller's buffers.
@@ -1570,6 +1591,17 @@ static bool apply_commands(fw_processor* p, Plan& pl, uint32_t b) {
         const Cmd& m = p->pend[i];
         if (m.block != b || m.kind == CMD_SAMPLER) continue;
         NodeDeviceState* st = state_of(pl, m.node);
+        if (m.kind == CMD_UPLOAD) {  // ring order: earlier single stores are flushed first, later ones come after this copy
+            float* snap = reinterpret_cast<float*>(m.x);
+            if (st) {
+                float* dst = m.a < 2 ? (m.a < st->n_sm ? st->d_target[m.a] : nullptr) : ((st->kind == FW_NODE_BIQUAD || st->kind == FW_NODE_SVF) ? st->d_coeffs : nullptr);
+                const size_t cap = m.a < 2 ? (size_t)V : (size_t)V * st->params->num_stages * (st->kind == FW_NODE_SVF ? 6 : 5);
+                pk.flush();
+                if (dst && m.y <= cap) pk.ok = pk.ok && FW_CUDA(cudaMemcpyAsync(dst, snap, m.y * sizeof(float), cudaMemcpyHostToDevice, p->stream));  // pageable source: staged before the call returns
+            }
+            p->ch->to_free.push(snap);  // back to the main thread (never full: one slot per command)
+            continue;
+        }
         if (!st || (m.voice != FW_ALL_VOICES && m.voice >= V)) continue;
         const uint32_t cnt = m.voice == FW_ALL_VOICES ? V : 1u; const size_t v0 = m.voice == FW_ALL_VOICES ? 0 : m.voice;
         switch (m.kind) {
@@ -1594,6 +1626,7 @@ static bool apply_commands(fw_processor* p, Plan& pl, uint32_t b) {
     return true;
 }
 
+static constexpr uint32_t kGraphEpoch = 0x0fffffffu;  // error-word epoch of replayed chunks: always "current" (see check_device_error)
 // One chunk: control kernel + data plane over frames [ck.t0, ck.t0 + ck.Tc) of the caller's rows (ck.Tfull frames long).
 static int enqueue_chunk(fw_processor* p, Plan& pl, const float* d_in, float* d_out, uint32_t n_out, const Chunk& ck) {
     const uint32_t V = p->num_voices, T = ck.Tc;
@@ -1607,7 +1640,7 @@ static int enqueue_chunk(fw_processor* p, Plan& pl, const float* d_in, float* d_
         sc.res_tab = st.cur_tab; sc.n_res = st.cur_n_res; sc.msgs = st.d_msgs; sc.msg_off = st.d_msg_off; sc.n_msgs = st.cur_n_msgs; sc.rec = pl.d_srec[i];
     }
     ca.flags = pl.d_flags; ca.num_voices = V; ca.frames = T; ca.block_frames = pl.block_frames;
-    ca.a = p->sm_a; ca.b = p->sm_b; ca.eps = p->sm_eps; ca.err_value = (p->call_epoch << 4) | 1u;
+    ca.a = p->sm_a; ca.b = p->sm_b; ca.eps = p->sm_eps; ca.err_value = ((p->capturing ? kGraphEpoch : p->call_epoch) << 4) | 1u;
     { ProfScope ps(p, 0); if (!FW_CUDA(launch_control(ca, p->stream))) return FW_PROC_DEVICE_ERROR; }
     p->launches++;
 
@@ -1688,6 +1721,54 @@ static int enqueue_chunk(fw_processor* p, Plan& pl, const float* d_in, float* d_
     return FW_PROC_OK;
 }
 
+// A steady chunk — same plan, same buffers, same frames, no command or upload at its start — is the same launch sequence with the
+// same arguments every time: it is captured into a CUDA graph the second time it is seen and replayed from then on (one
+// cudaGraphLaunch instead of one launch per kernel; what counts for block-sized calls, where the host's launch cost exceeds the
+// kernels' run time). Programmatic-dependent-launch edges are kept by the capture.
+static int run_chunk(fw_processor* p, Plan& pl, const float* d_in, float* d_out, uint32_t n_out, const Chunk& ck, bool steady) {
+    if (!steady || !pl.graphable || p->graphs_off || p->profiling || p->world > 1 || ck.zero_first) return enqueue_chunk(p, pl, d_in, d_out, n_out, ck);
+    const void* tabs[2 * kMaxSamplers] = {};
+    for (size_t i = 0; i < pl.samplers.size() && i < (size_t)kMaxSamplers; ++i) { tabs[2 * i] = pl.samplers[i]->cur_tab; tabs[2 * i + 1] = reinterpret_cast<const void*>((uintptr_t)pl.samplers[i]->cur_n_res); }
+    fw_processor::GraphEntry* e = nullptr; fw_processor::GraphEntry* lru = &p->graphs[0];
+    for (auto& g : p->graphs) {
+        if (g.plan == &pl && g.d_in == d_in && g.d_out == d_out && g.t0 == ck.t0 && g.Tc == ck.Tc && g.Tfull == ck.Tfull && std::memcmp(g.tabs, tabs, sizeof(tabs)) == 0) { e = &g; break; }
+        if (g.stamp < lru->stamp) lru = &g;
+    }
+    if (!e) {  // first sight: remember the key, run normally
+        e = lru;
+        if (e->exec) { cudaGraphExecDestroy(e->exec); e->exec = nullptr; }
+        e->plan = &pl; e->d_in = d_in; e->d_out = d_out; e->t0 = ck.t0; e->Tc = ck.Tc; e->Tfull = ck.Tfull; std::memcpy(e->tabs, tabs, sizeof(tabs)); e->seen = 0;
+    }
+    e->stamp = ++p->graph_stamp;
+    if (e->exec) {
+        if (!FW_CUDA(cudaGraphLaunch(e->exec, p->stream))) return FW_PROC_DEVICE_ERROR;
+        ++p->graph_replays; p->launches += e->seen;  // `seen` holds the kernel count of the captured sequence once instantiated
+        return FW_PROC_OK;
+    }
+    if (++e->seen < 2) return enqueue_chunk(p, pl, d_in, d_out, n_out, ck);
+    // second sight: capture, instantiate, launch
+    const uint64_t l0 = p->launches;
+    if (cudaStreamBeginCapture(p->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); p->graphs_off = true; return enqueue_chunk(p, pl, d_in, d_out, n_out, ck); }
+    p->capturing = true;
+    const int rc = enqueue_chunk(p, pl, d_in, d_out, n_out, ck);
+    p->capturing = false;
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(p->stream, &graph);
+    const uint32_t n_launch = (uint32_t)(p->launches - l0);
+    p->launches = l0;
+    if (rc != FW_PROC_OK || ce != cudaSuccess || !graph || cudaGraphInstantiate(&e->exec, graph, 0) != cudaSuccess) {
+        cudaGetLastError();
+        if (graph) cudaGraphDestroy(graph);
+        e->exec = nullptr; e->plan = nullptr; p->graphs_off = true;  // capture is not available here: stay on plain launches
+        return enqueue_chunk(p, pl, d_in, d_out, n_out, ck);
+    }
+    cudaGraphDestroy(graph);
+    e->seen = n_launch;
+    if (!FW_CUDA(cudaGraphLaunch(e->exec, p->stream))) return FW_PROC_DEVICE_ERROR;
+    ++p->graph_replays; p->launches += n_launch;
+    return FW_PROC_OK;
+}
+
 // One process_* call on device buffers: d_in [V][c_in][T]; d_out [V][c_out][T] or bus [c_out][T]. The call is processed as
 // consecutive chunks; a chunk boundary is (a) every plan.chunk_frames frames — the stretch device memory was reserved for —
 // and (b) every block at which a timed command takes effect. Messages from the context (new schedule, Stop; processor.rs:
@@ -1741,7 +1822,9 @@ static int proc_call(fw_processor* p, const float* d_in, float* d_out, uint32_t 
         next_cmd = nc;
         Chunk ck{b * F, std::min(T, b_end * F) - b * F, T, 0};
         if (p->pending_zero_first) { ck.zero_first = std::min(pl.block_frames, ck.Tc); p->pending_zero_first = false; }  // Q11
-        const int erc = enqueue_chunk(p, pl, d_in, d_out, n_out, ck);
+        bool steady = true;  // no sampler message rides in this chunk's control arguments (stores and uploads precede the chunk: they do not change it)
+        for (auto& st : pl.samplers) if (st->cur_n_msgs) steady = false;
+        const int erc = run_chunk(p, pl, d_in, d_out, n_out, ck, steady);
         if (erc != FW_PROC_OK) return erc;
         b = b_end;
     }
@@ -1769,7 +1852,8 @@ int fw_processor_process_planar_device(fw_processor* p, const float* d_in, float
 static int check_device_error(fw_processor* p) {
     if (!p->plan) return 0;
     const uint32_t e = *p->h_err;
-    if ((e & 15u) == 0 || (int32_t)((e >> 4) - (p->first_epoch_of_call & 0x0fffffffu)) < 0) return 0;
+    if ((e & 15u) == 0 || ((e >> 4) != kGraphEpoch && (int32_t)((e >> 4) - (p->first_epoch_of_call & 0x0fffffffu)) < 0)) return 0;
+    if ((e >> 4) == kGraphEpoch) cudaMemsetAsync(p->plan->rec.error, 0, 4, p->stream);  // a replayed chunk cannot stamp its epoch: report once, then clear
     g_dev_err = (e & 15u) == 2 ? "master-bus exchange timed out waiting for a peer rank" : "control pass overflowed its transient-block budget (a gain jump beyond 10000 %?)";
     return FW_PROC_DEVICE_ERROR;
 }
@@ -1862,6 +1946,8 @@ void fw_processor_free(fw_processor* p) {  // Drop processor.rs:251-263
     cudaFreeHost(p->h_masks); cudaFreeHost(p->h_err);
     for (auto& e : p->ev) if (e) cudaEventDestroy(e);
     for (auto& e : p->prof_ev) if (e) cudaEventDestroy(e);
+    for (auto& g : p->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+    for (size_t i = 0; i < p->pend_n; ++i) if (p->pend[i].kind == CMD_UPLOAD) delete[] reinterpret_cast<float*>(p->pend[i].x);
     cudaStreamDestroy(p->stream);
     delete p;
 }
@@ -1889,6 +1975,7 @@ float fw_processor_event_elapsed_ms(fw_processor* p, int a, int b) {
     return ms;
 }
 uint64_t fw_processor_kernel_launches(fw_processor* p) { return p->launches; }
+uint64_t fw_processor_graph_replays(fw_processor* p) { return p->graph_replays; }
 int fw_processor_profile(fw_processor* p, int enable) {
     cudaSetDevice(p->device);
     if (enable && p->prof_ev.empty()) {

@@ -43,6 +43,9 @@ constexpr int kStateStages = 8;  // state layout [row][8][2] regardless of the c
 //     flushed (coalesced) two chunks later to the ring (DELAY) or to `out`. With a delay, `out` is the old ring chunk.
 // Requires T % 32 == 0, zero_first % 32 == 0 and, with a delay, D % 32 == 0, pos % 32 == 0, D >= 160 (an old-ring
 // chunk is read two chunks ahead and must already hold the y flushed D/32 chunks earlier).
+//   * CHF = 64: 64-frame chunks (T % 64 == 0, zero_first % 64 == 0, D >= 320). The ~140 instructions of per-chunk bookkeeping
+//     (addresses, pipeline slots, flushes) are then paid every 64 samples instead of every 32 — 2.2 instead of 4.5 instructions per
+//     sample on a kernel that is bound by its instruction stream. A ring chunk may wrap between its two 32-frame halves.
 //   * FULL = true: every row of the CTA exists (the host launches the ragged last CTA separately with FULL = false), so the
 //     cooperative copies carry no per-lane predicates or branches.
 //   * SVF = true: the per-stage update is the trapezoidal SVF's (include/fw_b200.h) instead of the TDF-II biquad's; the lane /
@@ -58,12 +61,14 @@ __device__ __forceinline__ f32x2_t pk2(float lo, float hi) { f32x2_t r; asm("mov
 __device__ __forceinline__ float lo2(f32x2_t v) { return __uint_as_float((uint32_t)(v & 0xffffffffull)); }
 __device__ __forceinline__ float hi2(f32x2_t v) { return __uint_as_float((uint32_t)(v >> 32)); }
 __device__ __forceinline__ f32x2_t fma2(f32x2_t a, f32x2_t b, f32x2_t c) { f32x2_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
-template <int NS, int L, bool DELAY, int RPL, bool FULL, bool SVF = false, bool PK = false>
+template <int NS, int L, bool DELAY, int RPL, bool FULL, bool SVF = false, bool PK = false, int CHF = 32>
 __global__ void __launch_bounds__(32) biquad_delay_lanes(TemporalArgs a) {
     static_assert(!PK || (RPL == 2 && NS > 0), "the packed variant pairs the two rows of a lane");
+    static_assert(CHF == 32 || CHF == 64, "frames per chunk");
+    constexpr uint32_t G = CHF / 4;  // 16-byte granules per tile row
     constexpr uint32_t YM = 1u;                       // y tile slots - 1
     // RPL rows per lane: each lane runs stage s of RPL independent rows.
-    constexpr int RSET = 32 / L, ROWS = RPL * RSET, PER = RPL * 8 / L, LAG = NS > 0 ? 2 * (NS - 1) : 0;
+    constexpr int RSET = 32 / L, ROWS = RPL * RSET, PER = RPL * (CHF / 4) / L, LAG = NS > 0 ? 2 * (NS - 1) : 0;
     static_assert(NS <= L && (L == 1 || L == 2 || L == 4 || L == 8), "lanes per row");
     // No early launch_dependents here: this kernel is issue-bound, and dependents parked at griddepcontrol.wait
     // cost it issue slots (measured: 0.92 vs 0.64 ms per step). The implicit trigger at exit is enough.
@@ -71,9 +76,9 @@ __global__ void __launch_bounds__(32) biquad_delay_lanes(TemporalArgs a) {
     const uint32_t lane = threadIdx.x & 31u, s = lane % L;
     const uint32_t row0 = a.row_base + blockIdx.x * ROWS, R = a.R, T = a.T, D = a.D;
     const bool is_first = s == 0, is_last = NS == 0 ? s == 0 : s == (uint32_t)(NS > 0 ? NS - 1 : 0);
-    __shared__ float4 xt[4][ROWS][8];
-    __shared__ float4 rt[DELAY ? 3 : 1][ROWS][8];
-    __shared__ float4 yt[2][ROWS][8];
+    __shared__ float4 xt[4][ROWS][G];
+    __shared__ float4 rt[DELAY ? 3 : 1][ROWS][G];
+    __shared__ float4 yt[2][ROWS][G];
 
     uint32_t row_l[RPL], rsw[RPL]; bool lane_ok[RPL], last_ok[RPL];
     float b0[RPL], b1[RPL], b2[RPL], a1[RPL], a2[RPL], c5[RPL], s1[RPL], s2[RPL], q0[RPL], q1[RPL], yb[RPL][4];
@@ -105,32 +110,35 @@ __global__ void __launch_bounds__(32) biquad_delay_lanes(TemporalArgs a) {
     auto sub2 = [&](f32x2_t x, f32x2_t y) { return fma2(y, KN1, x); };   // RN(x-y): y*-1.0 is exact
 
     // cooperative copies: lane handles PER (row, granule) pairs of every tile
-    const float* in_p[PER]; float* out_p[PER]; float* ring_p[PER]; uint32_t sw[PER]; bool ok[PER];
+    const float* in_p[PER]; float* out_p[PER]; float* ring_p[PER]; uint32_t sw[PER]; bool ok[PER], hi[PER];
 #pragma unroll
     for (int i = 0; i < PER; ++i) {
-        const uint32_t idx = lane + 32u * i, rr = idx >> 3, g = idx & 7u;
+        const uint32_t idx = lane + 32u * i, rr = idx / G, g = idx % G;
+        hi[i] = g >= 8u;  // 64-frame chunks: the second 32 frames of a ring chunk may lie beyond the wrap
         ok[i] = FULL || row0 + rr < R;
         const size_t row = ok[i] ? row0 + rr : 0;
         in_p[i] = a.in + row * a.in_pitch + g * 4u;
         out_p[i] = a.out + row * a.out_pitch + g * 4u;
-        ring_p[i] = DELAY ? a.ring + (row * a.srow_mul + a.srow_add) * D + g * 4u : nullptr;
-        sw[i] = rr * 8u + (g ^ (rr & 7u));  // float4 index inside a tile
+        ring_p[i] = DELAY ? a.ring + (row * a.srow_mul + a.srow_add) * D + (g & 7u) * 4u : nullptr;
+        sw[i] = rr * G + (g ^ (rr & 7u));  // float4 index inside a tile
     }
-    const uint32_t nch = T / 32u;
+    const uint32_t nch = T / (uint32_t)CHF;
     // Ring offsets and tile slots advance incrementally (ring chunks are issued, consumed and flushed strictly in order):
     // a runtime `% D` costs ~20 dependent instructions through MUFU.RCP, three times per chunk, on a one-warp critical path
     // (measured on config 3: 0.506 -> 0.467 ms per step).
     uint32_t ring_issue_off = DELAY ? a.pos % D : 0u, ring_flush_off = ring_issue_off;  // (pos + 32 * chunk) % D
     uint32_t ring_issue_slot = 0, ring_use_slot = 0;                                   // chunk % 3
-    auto advance = [&](uint32_t& off) { off += 32u; if (off >= D) off -= D; };
+    auto advance = [&](uint32_t& off) { off += (uint32_t)CHF; if (off >= D) off -= D; };
+    // offset of a lane's granule inside the ring for a chunk that starts at `off` (D % 32 == 0: a chunk wraps only between its halves)
+    auto ring_off = [&](uint32_t off, bool second_half) { if (CHF == 32 || !second_half) return off; const uint32_t o = off + 32u; return o >= D ? o - D : o; };
     auto issue = [&](uint32_t chx, uint32_t chr) {  // x tile of chunk chx and old-ring tile of chunk chr, one commit group
         if (chx < nch) {
 #pragma unroll
-            for (int i = 0; i < PER; ++i) if (FULL || ok[i]) cp_async16(&xt[chx & 3u][0][0] + sw[i], in_p[i] + chx * 32u);
+            for (int i = 0; i < PER; ++i) if (FULL || ok[i]) cp_async16(&xt[chx & 3u][0][0] + sw[i], in_p[i] + chx * (uint32_t)CHF);
         }
         if (DELAY && chr < nch) {
 #pragma unroll
-            for (int i = 0; i < PER; ++i) if (FULL || ok[i]) cp_async16(&rt[ring_issue_slot][0][0] + sw[i], ring_p[i] + ring_issue_off);
+            for (int i = 0; i < PER; ++i) if (FULL || ok[i]) cp_async16(&rt[ring_issue_slot][0][0] + sw[i], ring_p[i] + ring_off(ring_issue_off, hi[i]));
             advance(ring_issue_off);
             ring_issue_slot = ring_issue_slot == 2u ? 0u : ring_issue_slot + 1u;
         }
@@ -140,8 +148,8 @@ __global__ void __launch_bounds__(32) biquad_delay_lanes(TemporalArgs a) {
 #pragma unroll
         for (int i = 0; i < PER; ++i) if (FULL || ok[i]) {
             const float4 v = (&yt[ch & YM][0][0])[sw[i]];
-            if (DELAY) *reinterpret_cast<float4*>(ring_p[i] + ring_flush_off) = v;
-            else __stcs(reinterpret_cast<float4*>(out_p[i] + ch * 32u), v);
+            if (DELAY) *reinterpret_cast<float4*>(ring_p[i] + ring_off(ring_flush_off, hi[i])) = v;
+            else __stcs(reinterpret_cast<float4*>(out_p[i] + ch * (uint32_t)CHF), v);
         }
         if (DELAY) advance(ring_flush_off);
     };
@@ -151,11 +159,11 @@ __global__ void __launch_bounds__(32) biquad_delay_lanes(TemporalArgs a) {
     // CHECK = true (first chunk, zeroed chunks, drain): stage s is live only while its sample n = gi - 2s is in [0, T).
     // CHECK = false (every other chunk): all stages are live; lanes that own no stage run on garbage that is never stored.
     // per-lane swizzled granule offsets of this lane's row(s) inside a tile row: granule c lives at c ^ (row & 7)
-    uint32_t goff[RPL][8];
+    uint32_t goff[RPL][G];
 #pragma unroll
     for (int j = 0; j < RPL; ++j)
 #pragma unroll
-        for (int c = 0; c < 8; ++c) goff[j][c] = (uint32_t)c ^ rsw[j];
+        for (int c = 0; c < (int)G; ++c) goff[j][c] = (uint32_t)c ^ rsw[j];
     const float4* xbase[RPL] = {}; float4* ybase[RPL][2] = {};  // refreshed per chunk: x tile row, y tile rows of this / the previous chunk
     auto body = [&](auto check, uint32_t gi, const float (&x)[RPL], int u4, int n4) {
         constexpr bool CHECK = decltype(check)::value;
@@ -189,8 +197,8 @@ __global__ void __launch_bounds__(32) biquad_delay_lanes(TemporalArgs a) {
             yb[0][slot] = y0; yb[1][slot] = y1;
             if (slot == 3) {
                 const int ml = n4 * 4 + u4 - LAG;
-                if (CHECK ? (is_last && lane_ok[0] && in_range) : last_ok[0]) ybase[0][ml >= 0 ? 0 : 1][goff[0][(ml >> 2) & 7]] = make_float4(yb[0][0], yb[0][1], yb[0][2], yb[0][3]);
-                if (CHECK ? (is_last && lane_ok[1] && in_range) : last_ok[1]) ybase[1][ml >= 0 ? 0 : 1][goff[1][(ml >> 2) & 7]] = make_float4(yb[1][0], yb[1][1], yb[1][2], yb[1][3]);
+                if (CHECK ? (is_last && lane_ok[0] && in_range) : last_ok[0]) ybase[0][ml >= 0 ? 0 : 1][goff[0][(ml >> 2) & (int)(G - 1)]] = make_float4(yb[0][0], yb[0][1], yb[0][2], yb[0][3]);
+                if (CHECK ? (is_last && lane_ok[1] && in_range) : last_ok[1]) ybase[1][ml >= 0 ? 0 : 1][goff[1][(ml >> 2) & (int)(G - 1)]] = make_float4(yb[1][0], yb[1][1], yb[1][2], yb[1][3]);
             }
         } else {
 #pragma unroll
@@ -222,7 +230,7 @@ __global__ void __launch_bounds__(32) biquad_delay_lanes(TemporalArgs a) {
             if (slot == 3 && (CHECK ? (is_last && active) : last_ok[j])) {
                 // m = gi - LAG lies in this chunk iff n4 * 4 + u4 >= LAG (all compile-time); granule (m >> 2) & 7
                 const int ml = n4 * 4 + u4 - LAG;
-                ybase[j][ml >= 0 ? 0 : 1][goff[j][(ml >> 2) & 7]] = make_float4(yb[j][0], yb[j][1], yb[j][2], yb[j][3]);
+                ybase[j][ml >= 0 ? 0 : 1][goff[j][(ml >> 2) & (int)(G - 1)]] = make_float4(yb[j][0], yb[j][1], yb[j][2], yb[j][3]);
             }
         }
         }
@@ -238,15 +246,15 @@ __global__ void __launch_bounds__(32) biquad_delay_lanes(TemporalArgs a) {
 #pragma unroll
         for (int j = 0; j < RPL; ++j) xnext[j] = xbase[j][goff[j][0]];
 #pragma unroll
-        for (uint32_t n4 = 0; n4 < 8u; ++n4) {
+        for (uint32_t n4 = 0; n4 < G; ++n4) {
             float4 xq[RPL];  // every lane of a row reads the same granule (broadcast); only stage 0 uses it
 #pragma unroll
             for (int j = 0; j < RPL; ++j) {
                 xq[j] = xnext[j];
-                if (n4 + 1u < 8u) xnext[j] = xbase[j][goff[j][(n4 + 1u) & 7u]];
+                if (n4 + 1u < G) xnext[j] = xbase[j][goff[j][(n4 + 1u) & (G - 1u)]];
                 if (decltype(check)::value && zero_in) xq[j] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
             }
-            const uint32_t gi = ch * 32u + n4 * 4u;
+            const uint32_t gi = ch * (uint32_t)CHF + n4 * 4u;
             float x[RPL];
 #pragma unroll
             for (int j = 0; j < RPL; ++j) x[j] = xq[j].x;
@@ -274,10 +282,10 @@ __global__ void __launch_bounds__(32) biquad_delay_lanes(TemporalArgs a) {
         __syncwarp();
         if (DELAY) {
 #pragma unroll
-            for (int i = 0; i < PER; ++i) if (FULL || ok[i]) __stcs(reinterpret_cast<float4*>(out_p[i] + ch * 32u), (&rt[ring_use_slot][0][0])[sw[i]]);
+            for (int i = 0; i < PER; ++i) if (FULL || ok[i]) __stcs(reinterpret_cast<float4*>(out_p[i] + ch * (uint32_t)CHF), (&rt[ring_use_slot][0][0])[sw[i]]);
             ring_use_slot = ring_use_slot == 2u ? 0u : ring_use_slot + 1u;
         }
-        const bool zero_in = ch * 32u < a.zero_first;  // Q11 (chunk-uniform)
+        const bool zero_in = ch * (uint32_t)CHF < a.zero_first;  // Q11 (chunk-uniform)
         if (ch == 0 || zero_in) chunk(std::true_type{}, ch, zero_in);  // warm-up: stage s starts at iteration 2s
         else chunk(std::false_type{}, ch, false);
     }
@@ -378,8 +386,8 @@ static cudaError_t launch_pdl_t(void (*kernel)(KArgs...), dim3 grid, dim3 block,
 // rows per lane every scheduler of the chip (148 SMs x 4) still has two warps to interleave. With fewer rows the kernel is
 // bound by the dependent-issue latency of the recurrence, not by issue slots, and one row per lane keeps twice the warps in
 // flight (config 3, 8192 rows: packed 0.490 ms, one row per lane 0.456 ms).
-template <int NS, int L, bool DELAY, bool SVF = false>
-static cudaError_t launch_lanes(const TemporalArgs& a, cudaStream_t st) {
+template <int NS, int L, bool DELAY, bool SVF, int CHF>
+static cudaError_t launch_lanes_c(const TemporalArgs& a, cudaStream_t st) {
     constexpr uint32_t rows1 = 32 / L;
     bool packed = false;
     if constexpr (L > 1 && NS > 0) packed = a.R / (2 * rows1) >= 2 * 4 * 148;  // >= 2 warps per scheduler even at two rows per lane
@@ -387,7 +395,7 @@ static cudaError_t launch_lanes(const TemporalArgs& a, cudaStream_t st) {
     if constexpr (L > 1 && NS > 0) {
         if (packed) {
             const uint32_t n_full = a.R / (2 * rows1);
-            cudaError_t e = launch_pdl_t(biquad_delay_lanes<NS, L, DELAY, 2, true, SVF, true>, dim3(n_full), dim3(32), st, a);
+            cudaError_t e = launch_pdl_t(biquad_delay_lanes<NS, L, DELAY, 2, true, SVF, true, 32>, dim3(n_full), dim3(32), st, a);
             if (e != cudaSuccess) return e;
             done = n_full * 2 * rows1;
         }
@@ -395,16 +403,25 @@ static cudaError_t launch_lanes(const TemporalArgs& a, cudaStream_t st) {
     if (!packed) {
         const uint32_t n_full = a.R / rows1;
         if (n_full) {
-            cudaError_t e = launch_pdl_t(biquad_delay_lanes<NS, L, DELAY, 1, true, SVF>, dim3(n_full), dim3(32), st, a);
+            cudaError_t e = launch_pdl_t(biquad_delay_lanes<NS, L, DELAY, 1, true, SVF, false, CHF>, dim3(n_full), dim3(32), st, a);
             if (e != cudaSuccess) return e;
         }
         done = n_full * rows1;
     }
     if (done < a.R) {  // ragged tail
         TemporalArgs t = a; t.row_base = done;
-        return launch_pdl_t(biquad_delay_lanes<NS, L, DELAY, 1, false, SVF>, dim3((a.R - done + rows1 - 1) / rows1), dim3(32), st, t);
+        return launch_pdl_t(biquad_delay_lanes<NS, L, DELAY, 1, false, SVF, false, 32>, dim3((a.R - done + rows1 - 1) / rows1), dim3(32), st, t);
     }
     return cudaSuccess;
+}
+
+template <int NS, int L, bool DELAY, bool SVF = false>
+static cudaError_t launch_lanes(const TemporalArgs& a, cudaStream_t st) {
+    // 64-frame chunks when the shape allows (see the kernel's comment); only instantiated for the cascade lengths that matter
+    if constexpr (L == 4 || L == 2) {
+        if (a.T % 64u == 0 && a.zero_first % 64u == 0 && (!DELAY || a.D >= 320u)) return launch_lanes_c<NS, L, DELAY, SVF, 64>(a, st);
+    }
+    return launch_lanes_c<NS, L, DELAY, SVF, 32>(a, st);
 }
 
 bool temporal_fast_path(const TemporalArgs& a) {

@@ -469,6 +469,9 @@ class FirewheelProcessor:
     def kernel_launches(self):
         return self._lib.processor_kernel_launches(self._h)
 
+    def graph_replays(self):
+        return int(self._lib.processor_graph_replays(self._h))
+
     def profile(self, enable):
         return self._lib.processor_profile(self._h, int(enable))
 

@@ -397,6 +397,7 @@ FW_EXPORT int FW_FN(processor_sync)(fw_processor* p);
 FW_EXPORT int FW_FN(processor_event_record)(fw_processor* p, int slot);
 FW_EXPORT float FW_FN(processor_event_elapsed_ms)(fw_processor* p, int slot_start, int slot_stop);
 FW_EXPORT uint64_t FW_FN(processor_kernel_launches)(fw_processor* p); /* kernels launched so far */
+FW_EXPORT uint64_t FW_FN(processor_graph_replays)(fw_processor* p);   /* chunks replayed from a captured CUDA graph so far */
 /* Per-kernel-class device timing with CUDA events on the launching stream.
  * classes: 0 control, 1 fused chain (+bus), 2 bus combine, 3 temporal (biquad/delay/reverb). */
 FW_EXPORT int FW_FN(processor_profile)(fw_processor* p, int enable);

@@ -672,6 +672,7 @@ int fwo_processor_sync(fw_processor*) { return 0; }
 int fwo_processor_event_record(fw_processor*, int) { return -1; }
 float fwo_processor_event_elapsed_ms(fw_processor*, int, int) { return -1.0f; }
 uint64_t fwo_processor_kernel_launches(fw_processor*) { return 0; }
+uint64_t fwo_processor_graph_replays(fw_processor*) { return 0; }
 int fwo_processor_l2_flush(fw_processor*) { return -1; }
 int fwo_processor_profile(fw_processor*, int) { return -1; }
 int fwo_processor_profile_read(fw_processor*, double*, uint64_t*) { return -1; }

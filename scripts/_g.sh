@@ -1,7 +1,7 @@
 mkdir -p gpurun_out
-(timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -25) > gpurun_out/r2_t4.log 2>&1; tail -25 gpurun_out/r2_t4.log
+(timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -25) > gpurun_out/r2_t4.log 2>&1; tail -25 gpurun_out/r2_t4.log | cut -c1-250
 export FW_BENCH_SKIP_CPU=1
-timeout 300 python bench.py --only c2,c4 --steps 20 --warmup 5 2>gpurun_out/r2_b1.err > gpurun_out/r2_b1.json
+timeout 300 python bench.py --only c2,c3,c4 --steps 20 --warmup 5 2>gpurun_out/r2_b1.err > gpurun_out/r2_b1.json
 python - <<'P'
 import json
 for f in ("r2_b1",):
