@@ -511,7 +511,7 @@ def run_config(fw, lib, name, args, rank, world, local_rank, want_cpu):
     if tensor:
         res["tflops"] = flops * world / (ms_per_step * 1e-3) / 1e12
     if world > 1 and w["bus"]:
-        res["exchange"] = "peer-memory (NVLink) push + rank-ordered tree" if os.environ.get("FW_EXCHANGE") == "p2p" else "NCCL all-gather on a high-priority side stream + rank-ordered tree"
+        res["exchange"] = "NCCL all-gather on a high-priority side stream (device-word hand-over, no event on the main stream) + rank-ordered tree"
         res["bus_identical_on_all_ranks"] = ranks_identical
         if parity and "bus" in parity:
             res["bus_parity"] = parity["bus"] if ranks_identical else "mismatch"

@@ -25,10 +25,9 @@ cudaError_t launch_interleave(const float* planar, float* inter, const uint64_t*
                               uint32_t block_frames, cudaStream_t st);
 cudaError_t launch_fill(float* p, size_t n, float val, cudaStream_t st);
 cudaError_t launch_bus_mask(const uint64_t* gout_mask, uint32_t V, uint32_t n_out, uint64_t* bus_mask, cudaStream_t st);
-cudaError_t launch_bus_push(const BusPushArgs& a, cudaStream_t st);
-cudaError_t launch_bus_wait(const uint32_t* words, uint32_t count, uint32_t epoch, uint32_t* error, uint32_t error_value, cudaStream_t st);
+cudaError_t launch_bus_signal(uint32_t* word, uint32_t epoch, cudaStream_t st);
+cudaError_t launch_bus_wait(const uint32_t* word, uint32_t epoch, uint32_t* error, uint32_t error_value, cudaStream_t st);
 cudaError_t launch_poke(const PokeArgs& a, cudaStream_t st);
-cudaError_t launch_bus_recv(const BusRecvArgs& a, cudaStream_t st);
 cudaError_t launch_temporal(const TemporalArgs& a, cudaStream_t st);
 bool temporal_fast_path(const TemporalArgs& a);
 uint32_t reverb_kpad(uint32_t L);

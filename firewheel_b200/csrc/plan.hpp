@@ -162,19 +162,6 @@ struct SilenceFixArgs {
     Records rec;
 };
 
-// Master-bus exchange over peer memory (exchange.cu). Pointers indexed by rank are the IPC-mapped mailboxes.
-struct BusPushArgs {
-    const float* pin; uint32_t n_in, rows, T;   // partial buses [n_in <= 16][rows][T] of this rank
-    float* data[16]; uint32_t* ready[16];       // per destination rank: slot storage and ready words
-    const uint32_t* ack_local; uint32_t* counter; uint32_t* push_done; uint32_t* error; uint32_t error_value, pad_;
-    uint32_t world, me, epoch, cap;             // cap: floats per slot
-};
-struct BusRecvArgs {
-    const float* data_local; float* out; uint32_t rows, T, out_pitch;  // out rows at out_pitch floats (the caller's bus)
-    uint32_t* ack[16]; uint32_t* counter;
-    uint32_t world, me, epoch, cap;
-};
-
 // Polyphase resampler data plane (spec in include/fw_b200.h). out[c] + v * out_vstride is channel c of voice v.
 struct ResamplerArgs {
     float* out[64]; uint64_t out_vstride;

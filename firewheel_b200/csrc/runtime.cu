@@ -265,6 +265,7 @@ struct Plan {
     // Per-call scratch, sized on the main thread (lower()) for one chunk of at most `chunk_frames` frames: the stream side
     // never allocates (processor.rs:167-206, context.rs:61-64: the reference's audio thread does not either).
     uint32_t chunk_frames = 0, chunk_blocks = 0;
+    bool heavy_stage = false;  // a FIR-reverb GEMM is part of the plan (see run_bus_stage)
     bool graphable = false;  // every by-value kernel argument of a chunk is a function of (buffers, frames): the launch sequence can be replayed as a CUDA graph
     float* d_part[2] = {nullptr, nullptr};     // partial buses [groups][c_out][chunk] and the next radix-16 level
     float* d_tmp[2] = {nullptr, nullptr};      // inter-stage scratch [V][2][chunk]
@@ -355,11 +356,10 @@ struct fw_processor {
     GraphEntry graphs[4]; uint64_t graph_stamp = 0, graph_replays = 0; bool capturing = false, graphs_off = false;
     // multi-GPU master bus: voices shard by rank; the per-rank buses are all-gathered and tree-summed in rank order
     void* nccl_comm = nullptr; int rank = 0, world = 1;
-    float *d_bus_local = nullptr, *d_gather = nullptr;  // [n_out][chunk], [world][n_out][chunk]: allocated by comm_init
+    float *d_bus_local[2] = {nullptr, nullptr}, *d_gather[2] = {nullptr, nullptr};  // [n_out][chunk], [world][n_out][chunk] per exchange parity: allocated by comm_init
     // the exchange runs on a side stream so that it overlaps the next call's control + chain kernels
-    cudaStream_t side = nullptr; cudaEvent_t ev_bus_ready = nullptr, ev_exchange_done = nullptr; bool exchange_pending = false;
-    // peer-memory exchange (exchange.cu): IPC-mapped mailboxes of all ranks; falls back to the NCCL all-gather when off
-    struct P2P { bool on = false; uint8_t* base[16] = {}; size_t cap = 0; uint32_t epoch = 0; uint32_t* counters = nullptr; } p2p;
+    cudaStream_t side = nullptr; cudaEvent_t ev_exchange_done[2] = {nullptr, nullptr}; bool exchange_pending[2] = {false, false};
+    uint32_t* d_handover = nullptr; uint32_t xepoch = 0;  // device word main -> side (exchange.cu), exchange counter
     uint64_t* h_masks = nullptr; uint32_t* h_err = nullptr;  // pinned
     // optional per-kernel-class timing (CUDA events on `stream`)
     bool profiling = false; std::vector<cudaEvent_t> prof_ev; std::vector<int> prof_class; size_t prof_used = 0;
@@ -610,6 +610,7 @@ static bool lower(fw_ctx* c, const Schedule& s, Plan* plan, std::string* why) {
         bool g = true;
         for (auto& st : plan->states) if (st->kind == FW_NODE_DELAY || st->kind == FW_NODE_CONV_REVERB || st->kind == FW_NODE_RESAMPLER || st->kind == FW_NODE_CUSTOM) g = false;
         plan->graphable = g;
+        for (auto& st : plan->states) if (st->kind == FW_NODE_CONV_REVERB) plan->heavy_stage = true;
     }
     return true;
 }
@@ -1197,7 +1198,7 @@ void* fw_ctx_deactivate(fw_ctx* c, int stream_is_running) {  // context.rs:162-2
 // ---- stream side --------------------------------------------------------------------------------
 // make the main stream wait for an outstanding master-bus exchange (side stream)
 static void join_side(fw_processor* p) {
-    if (p->exchange_pending) { cudaStreamWaitEvent(p->stream, p->ev_exchange_done, 0); p->exchange_pending = false; }
+    for (int q = 0; q < 2; ++q) if (p->exchange_pending[q]) { cudaStreamWaitEvent(p->stream, p->ev_exchange_done[q], 0); p->exchange_pending[q] = false; }
 }
 
 static void proc_poll(fw_processor* p) {  // processor.rs:167-206
@@ -1221,53 +1222,21 @@ struct Chunk { uint32_t t0, Tc, Tfull, zero_first; };
 // Last stage with a master bus: the chain kernel (BUS variant) reduces 64 voices per CTA into partial buses, the combine
 // kernel finishes the tree, and with several ranks the per-rank buses are exchanged. bus_out = the caller's
 // bus rows (pitch ck.Tfull) at the chunk's first frame.
-static constexpr size_t kMailHeader = 256;  // ready[2][16] u32 at +0, ack[2][16] u32 at +128, slots at +256
 static int run_bus_stage(fw_processor* p, Plan& pl, ChainArgs& xa, uint32_t n_out, const Chunk& ck, float* bus_out) {
     const uint32_t V = p->num_voices, T = ck.Tc;
     uint32_t n = chain_voice_groups(V);
-    const uint32_t err_val = (p->call_epoch << 4) | 2u;
-    if (p->world > 1 && p->p2p.on) {
-        // Peer-memory exchange. MAIN stream: chain -> partial buses (+ radix-16 levels while more than 16 remain) -> K-push = the
-        // last level of the rank-local tree FUSED with the NVLink stores into every rank's mailbox (programmatic dependent launch:
-        // no event, no side-stream hand-over on the critical path; the next call's control kernel overlaps its tail). SIDE stream
-        // (high priority): K-wait polls the mailbox flags, K-recv applies the top levels of the tree in rank order and writes the
-        // caller's bus — it depends on the main stream only through those device words, so nothing is recorded on the main stream.
-        fw_processor::P2P& x = p->p2p;
-        const uint32_t epoch = ++x.epoch;
-        const int s = (int)(epoch & 1u);
-        xa.out = pl.d_part[0]; xa.bus_pitch = 0;
-        { ProfScope ps(p, 1); if (!FW_CUDA(launch_chain(xa, true, p->stream))) return FW_PROC_DEVICE_ERROR; }
-        p->launches++;
-        int cur = 0;
-        ProfScope ps2(p, 2);
-        while (n > 16) {
-            if (!FW_CUDA(launch_combine(pl.d_part[cur], pl.d_part[cur ^ 1], n, n_out, T, p->stream))) return FW_PROC_DEVICE_ERROR;
-            p->launches++;
-            n = (n + 15) / 16; cur ^= 1;
-        }
-        BusPushArgs pa{};
-        pa.pin = pl.d_part[cur]; pa.n_in = n; pa.rows = n_out; pa.T = T;
-        for (int r = 0; r < p->world; ++r) { pa.data[r] = reinterpret_cast<float*>(x.base[r] + kMailHeader); pa.ready[r] = reinterpret_cast<uint32_t*>(x.base[r]); }
-        pa.ack_local = reinterpret_cast<const uint32_t*>(x.base[p->rank] + 128); pa.counter = x.counters; pa.push_done = x.counters + 3; pa.error = xa.rec.error; pa.error_value = err_val;
-        pa.world = (uint32_t)p->world; pa.me = (uint32_t)p->rank; pa.epoch = epoch; pa.cap = (uint32_t)x.cap;
-        if (!FW_CUDA(launch_bus_push(pa, p->stream))) return FW_PROC_DEVICE_ERROR;
-        if (!FW_CUDA(launch_bus_wait(reinterpret_cast<const uint32_t*>(x.base[p->rank]) + s * 16, (uint32_t)p->world, epoch, xa.rec.error, err_val, p->side))) return FW_PROC_DEVICE_ERROR;
-        BusRecvArgs ra{};
-        ra.data_local = reinterpret_cast<const float*>(x.base[p->rank] + kMailHeader); ra.out = bus_out; ra.rows = n_out; ra.T = T; ra.out_pitch = ck.Tfull;
-        for (int r = 0; r < p->world; ++r) ra.ack[r] = reinterpret_cast<uint32_t*>(x.base[r] + 128);
-        ra.counter = x.counters + 1; ra.world = (uint32_t)p->world; ra.me = (uint32_t)p->rank; ra.epoch = epoch; ra.cap = (uint32_t)x.cap;
-        if (!FW_CUDA(launch_bus_recv(ra, p->side))) return FW_PROC_DEVICE_ERROR;
-        p->launches += 3;
-        cudaEventRecord(p->ev_exchange_done, p->side);
-        p->exchange_pending = true;
-        return FW_PROC_OK;
-    }
-    // this rank's bus: with several ranks it is gathered (NCCL) and tree-summed below, else it is the caller's bus
-    float* bus_dst = p->world > 1 ? p->d_bus_local : bus_out;
+    // this rank's bus: with several ranks it is gathered and tree-summed below, else it is the caller's bus
+    const int q = (int)((p->xepoch + 1u) & 1u);
+    float* bus_dst = p->world > 1 ? p->d_bus_local[q] : bus_out;
     const uint32_t bus_pitch = p->world > 1 ? T : ck.Tfull;
+    if (p->world > 1 && p->exchange_pending[q]) {
+        // buffer q was last read by the exchange two calls back: long done in any steady loop. Only if the side stream really lags is
+        // an event wait put on the main stream (it would cut the PDL chain).
+        if (cudaEventQuery(p->ev_exchange_done[q]) != cudaSuccess) { cudaGetLastError(); cudaStreamWaitEvent(p->stream, p->ev_exchange_done[q], 0); }
+        p->exchange_pending[q] = false;
+    }
     if (n == 1) { xa.out = bus_dst; xa.bus_pitch = bus_pitch; }
     else { xa.out = pl.d_part[0]; xa.bus_pitch = 0; }
-    if (p->world > 1 && n == 1) join_side(p);  // the chain kernel writes d_bus_local directly
     { ProfScope ps(p, 1); if (!FW_CUDA(launch_chain(xa, true, p->stream))) return FW_PROC_DEVICE_ERROR; }
     p->launches++;
     ProfScope ps2(p, 2);
@@ -1275,23 +1244,31 @@ static int run_bus_stage(fw_processor* p, Plan& pl, ChainArgs& xa, uint32_t n_ou
     while (n > 1) {
         const uint32_t n_next = (n + 15) / 16;
         float* cdst = n_next == 1 ? bus_dst : pl.d_part[cur ^ 1];
-        if (p->world > 1 && n_next == 1) join_side(p);  // d_bus_local is still being read by the previous exchange
         if (!FW_CUDA(launch_combine(pl.d_part[cur], cdst, n, n_out, T, p->stream, n_next == 1 ? bus_pitch : 0))) return FW_PROC_DEVICE_ERROR;
         p->launches++;
         n = n_next; cur ^= 1;
     }
     if (p->world > 1) {
-        // NCCL exchange (used when the peer-memory mailboxes could not be set up, or FW_EXCHANGE=nccl): all-gather the per-rank buses,
-        // then the top log2(world) levels of the same balanced tree in rank order on every rank — bit-identical on all ranks, unlike
-        // ncclAllReduce. Runs on the side stream so that it overlaps the next call's control + chain.
-        cudaEventRecord(p->ev_bus_ready, p->stream);
-        cudaStreamWaitEvent(p->side, p->ev_bus_ready, 0);
-        if (!g_nccl.ok(g_nccl.AllGather(p->d_bus_local, p->d_gather, (size_t)n_out * T, /*ncclFloat32*/ 7, p->nccl_comm, p->side), "ncclAllGather")) return FW_PROC_DEVICE_ERROR;
+        // Exchange step on the high-priority side stream, overlapping control + chain of the next call: all-gather the
+        // per-rank buses over NVLink (NCCL), then the top log2(world) levels of the same balanced tree in rank order on every rank —
+        // bit-identical on all ranks, unlike ncclAllReduce. Main -> side hand-over through a device word (exchange.cu): the main
+        // stream carries no event, its programmatic-dependent-launch chain runs straight into the next call.
+        // A plan with a FIR-reverb stage keeps every SM occupied by the GEMM's persistent CTAs (197 KB of shared memory each): a
+        // side-stream collective cannot become resident next to them and ends up serialised into the gaps, where it was measured to
+        // cost more (config 5 at 8 GPUs: +0.3 ms per step) than its own ~25 us. Such plans run the exchange in line.
+        const bool in_line = pl.heavy_stage;
+        cudaStream_t xs = in_line ? p->stream : p->side;
+        const uint32_t e = ++p->xepoch;
+        if (!in_line) {
+            if (!FW_CUDA(launch_bus_signal(p->d_handover, e, p->stream))) return FW_PROC_DEVICE_ERROR;
+            if (!FW_CUDA(launch_bus_wait(p->d_handover, e, xa.rec.error, (p->call_epoch << 4) | 2u, p->side))) return FW_PROC_DEVICE_ERROR;
+            p->launches += 2;
+        }
+        if (!g_nccl.ok(g_nccl.AllGather(p->d_bus_local[q], p->d_gather[q], (size_t)n_out * T, /*ncclFloat32*/ 7, p->nccl_comm, xs), "ncclAllGather")) return FW_PROC_DEVICE_ERROR;
         p->launches++;
-        if (!FW_CUDA(launch_combine(p->d_gather, bus_out, (uint32_t)p->world, n_out, T, p->side, ck.Tfull))) return FW_PROC_DEVICE_ERROR;
+        if (!FW_CUDA(launch_combine(p->d_gather[q], bus_out, (uint32_t)p->world, n_out, T, xs, ck.Tfull))) return FW_PROC_DEVICE_ERROR;
         p->launches++;
-        cudaEventRecord(p->ev_exchange_done, p->side);
-        p->exchange_pending = true;
+        if (!in_line) { cudaEventRecord(p->ev_exchange_done[q], p->side); p->exchange_pending[q] = true; }
     }
     return FW_PROC_OK;
 }
@@ -1496,72 +1473,6 @@ static int enqueue_generic(fw_processor* p, Plan& pl, const float* d_in, float* 
         }
     }
     return FW_PROC_OK;
-}
-
-// Peer-memory mailboxes for the bus exchange: allocate, exchange CUDA IPC handles through the communicator, map all peers.
-// Any rank failing turns the feature off on ALL ranks (they then use the NCCL all-gather): decided by a second all-gather.
-static bool p2p_setup(fw_processor* p) {
-    // Default: the peer-memory exchange (push fused into the last tree level on the main stream, exchange.cu). FW_EXCHANGE=nccl
-    // selects the NCCL all-gather instead; it is also what every rank falls back to when CUDA IPC / peer access is unavailable.
-    const char* mode = getenv("FW_EXCHANGE");
-    const bool want = !(mode && std::strcmp(mode, "nccl") == 0);
-    const int W = p->world, me = p->rank;
-    const size_t cap = (((size_t)p->n_out * p->max_call_frames) + 3) & ~(size_t)3;  // floats per slot: one chunk of the bus
-    const size_t bytes = kMailHeader + (size_t)2 * W * cap * sizeof(float);
-    struct Msg { cudaIpcMemHandle_t h; uint32_t ok; uint32_t pad[15]; };
-    static_assert(sizeof(Msg) == 128, "IPC handle message");
-    std::vector<Msg> all((size_t)W);
-    Msg mine{}; uint8_t* local = nullptr;
-    bool ok = want;
-    if (ok && cudaMalloc(&local, bytes) != cudaSuccess) { cudaGetLastError(); ok = false; local = nullptr; }
-    if (ok) { cudaMemset(local, 0, bytes); if (cudaIpcGetMemHandle(&mine.h, local) != cudaSuccess) { cudaGetLastError(); ok = false; } }
-    mine.ok = ok ? 1u : 0u;
-    Msg* d_msg = nullptr;
-    if (!FW_CUDA(cudaMalloc(&d_msg, sizeof(Msg) * W))) return false;
-    auto gather = [&]() -> bool {
-        cudaMemcpy(d_msg + me, &mine, sizeof(Msg), cudaMemcpyHostToDevice);
-        cudaDeviceSynchronize();
-        if (!g_nccl.ok(g_nccl.AllGather(d_msg + me, d_msg, sizeof(Msg), /*ncclInt8*/ 0, p->nccl_comm, p->side), "ncclAllGather(ipc handles)")) return false;
-        if (!FW_CUDA(cudaStreamSynchronize(p->side))) return false;
-        return FW_CUDA(cudaMemcpy(all.data(), d_msg, sizeof(Msg) * W, cudaMemcpyDeviceToHost));
-    };
-    if (!gather()) { cudaFree(d_msg); return false; }
-    for (int r = 0; r < W; ++r) ok = ok && all[r].ok;
-    if (ok) {
-        for (int r = 0; r < W && ok; ++r) {
-            if (r == me) { p->p2p.base[r] = local; continue; }
-            void* ptr = nullptr;
-            if (cudaIpcOpenMemHandle(&ptr, all[r].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
-            p->p2p.base[r] = static_cast<uint8_t*>(ptr);
-        }
-    }
-    mine.ok = ok ? 1u : 0u;  // second round: did every rank map every peer?
-    if (!gather()) { cudaFree(d_msg); return false; }
-    cudaFree(d_msg);
-    for (int r = 0; r < W; ++r) ok = ok && all[r].ok;
-    if (!ok) {
-        for (int r = 0; r < W; ++r) { if (r != me && p->p2p.base[r]) cudaIpcCloseMemHandle(p->p2p.base[r]); p->p2p.base[r] = nullptr; }
-        if (local) cudaFree(local);
-        if (want && me == 0) std::fprintf(stderr, "[firewheel_b200] peer-memory bus exchange unavailable (CUDA IPC / peer access); using the NCCL all-gather\n");
-        return true;
-    }
-    p->p2p.counters = dev_alloc<uint32_t>(4);  // push counter, recv counter, (unused), push_done
-    p->p2p.cap = cap; p->p2p.epoch = 0; p->p2p.on = true;
-    return true;
-}
-
-// All ranks must have drained their streams before any mailbox is unmapped or freed: peers write acknowledgements into it.
-static void p2p_teardown(fw_processor* p) {
-    if (!p->p2p.on) return;
-    uint8_t* d_b = nullptr;
-    if (cudaMalloc(&d_b, 16 * p->world) == cudaSuccess) {
-        g_nccl.AllGather(d_b + 16 * p->rank, d_b, 16, /*ncclInt8*/ 0, p->nccl_comm, p->side);  // barrier
-        cudaStreamSynchronize(p->side);
-        cudaFree(d_b);
-    }
-    for (int r = 0; r < p->world; ++r) if (r != p->rank && p->p2p.base[r]) cudaIpcCloseMemHandle(p->p2p.base[r]);
-    cudaFree(p->p2p.base[p->rank]); cudaFree(p->p2p.counters);
-    p->p2p.on = false;
 }
 
 // ---- timed commands (see Cmd in graph.hpp) -------------------------------------------------------------------------------
@@ -1938,10 +1849,10 @@ void fw_processor_free(fw_processor* p) {  // Drop processor.rs:251-263
     cudaSetDevice(p->device);
     join_side(p);
     cudaStreamSynchronize(p->stream);
-    if (p->side) { cudaStreamSynchronize(p->side); p2p_teardown(p); cudaStreamDestroy(p->side); cudaEventDestroy(p->ev_bus_ready); cudaEventDestroy(p->ev_exchange_done); }
+    if (p->side) { cudaStreamSynchronize(p->side); cudaStreamDestroy(p->side); cudaEventDestroy(p->ev_exchange_done[0]); cudaEventDestroy(p->ev_exchange_done[1]); }
     ProcToCtx m; m.kind = 1; m.plan = p->plan; m.user_cx = p->user_cx;
     if (!p->ch->to_ctx.push(m)) delete p->plan;
-    cudaFree(p->d_in); cudaFree(p->d_out); cudaFree(p->d_inter); cudaFree(p->d_flush); cudaFree(p->d_bus_local); cudaFree(p->d_gather);
+    cudaFree(p->d_in); cudaFree(p->d_out); cudaFree(p->d_inter); cudaFree(p->d_flush); cudaFree(p->d_bus_local[0]); cudaFree(p->d_bus_local[1]); cudaFree(p->d_gather[0]); cudaFree(p->d_gather[1]); cudaFree(p->d_handover);
     if (p->nccl_comm) g_nccl.CommDestroy(p->nccl_comm);
     cudaFreeHost(p->h_masks); cudaFreeHost(p->h_err);
     for (auto& e : p->ev) if (e) cudaEventDestroy(e);
@@ -2102,13 +2013,15 @@ int fw_processor_comm_init(fw_processor* p, int rank, int world, const uint8_t* 
     if (!g_nccl.ok(g_nccl.CommInitRank(&p->nccl_comm, world, id, rank), "ncclCommInitRank")) return -1;
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);  // the exchange must not queue behind the next call's chain CTAs
-    if (!FW_CUDA(cudaStreamCreateWithPriority(&p->side, cudaStreamNonBlocking, prio_hi)) || !FW_CUDA(cudaEventCreateWithFlags(&p->ev_bus_ready, cudaEventDisableTiming)) ||
-        !FW_CUDA(cudaEventCreateWithFlags(&p->ev_exchange_done, cudaEventDisableTiming))) return -1;
+    if (!FW_CUDA(cudaStreamCreateWithPriority(&p->side, cudaStreamNonBlocking, prio_hi)) || !FW_CUDA(cudaEventCreateWithFlags(&p->ev_exchange_done[0], cudaEventDisableTiming)) ||
+        !FW_CUDA(cudaEventCreateWithFlags(&p->ev_exchange_done[1], cudaEventDisableTiming))) return -1;
     p->rank = rank; p->world = world;
-    p->d_bus_local = dev_alloc<float>((size_t)p->n_out * p->max_call_frames, false); p->d_gather = dev_alloc<float>((size_t)world * p->n_out * p->max_call_frames, false);
-    if (!p->d_bus_local || !p->d_gather) return -1;
-    if (!p2p_setup(p)) return -1;
-    return 0;
+    for (int q = 0; q < 2; ++q) {
+        p->d_bus_local[q] = dev_alloc<float>((size_t)p->n_out * p->max_call_frames, false); p->d_gather[q] = dev_alloc<float>((size_t)world * p->n_out * p->max_call_frames, false);
+        if (!p->d_bus_local[q] || !p->d_gather[q]) return -1;
+    }
+    p->d_handover = dev_alloc<uint32_t>(1);
+    return p->d_handover ? 0 : -1;
 }
 // Host-buffer all-gather over the processor's communicator: what a torch-free driver needs for barriers, max-over-ranks
 // timing and result cross-checks (bench.py, tests/multigpu_worker.py). Not on the audio path.
