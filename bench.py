@@ -2,7 +2,7 @@
 """bench.py — benchmark of the per-block audio-graph DSP path (BASELINE.json metric: mono-equivalent samples/s through
 the graph at 1/2/4/8 B200; conv-reverb TFLOPS).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--only c2,c3,c4,c5]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--only c2,c3,c4,c5,dag]
 
 A *step* is one pass of the hot path over one batch of synthetic input. ONE JSON line on rank 0:
   headline (`value`, `ms_per_step`, `roofline`, `e2e`, `cpu_baseline`) = c2, BASELINE configs[1]: 1024 stereo voices per GPU,
@@ -12,6 +12,8 @@ A *step* is one pass of the hot path over one batch of synthetic input. ONE JSON
       c4  256 voices/GPU, 48000-tap stereo FIR reverb as a bf16 tcgen05 GEMM (tensor roofline, TFLOP/s)
       c5  65536 sampler voices IN TOTAL (sampler -> gain -> pan -> 4-stage biquad -> FIR reverb -> master bus), sharded
           over the ranks: STRONG scaling of BASELINE configs[4];
+      dag a non-chain voice graph (dry + SVF send + biquad send -> 6-port SumNode -> pan -> bus) on the generic lowering, plus block-sized
+          calls (one 256-frame block per call) replayed from a captured CUDA graph: us per call;
   `cpu_baseline.c1` = configs[0]: one VolumeNode, mono, 256-frame blocks on the CPU oracle (ns per block of executor plumbing).
 Timing: every config is timed over >= ~1 s as R passes of exactly `--steps` steps; a pass is bracketed by a barrier and a
 stream synchronise on both sides and timed with CUDA events on the processor's stream; per pass the MAX over ranks is
@@ -43,7 +45,7 @@ sys.path.insert(0, str(ROOT / "oracle"))
 
 F32 = np.float32
 SR = 48000
-C5_TOTAL_VOICES = int(os.environ.get("FW_BENCH_C5_VOICES", "65536"))  # (development override; the config is 65536)
+C5_TOTAL_VOICES = int(os.environ.get("FW_BENCH_C5_VOICES", "65536"))  # BASELINE configs[4]; the override exists to profile one rank's share (8192) on one GPU
 WORKLOADS = {
     # voices per GPU (c5: in total), channels, block frames, blocks per step
     "c1": dict(voices=1, ch=1, block=256, blocks=4096, bus=False, desc="c1: single VolumeNode, mono, 256-frame blocks (CPU plumbing, beep_test shape)"),
@@ -60,6 +62,11 @@ WORKLOADS = {
                kernel="reverb_gemm_kernel (tcgen05) + biquad_delay_lanes; sampler_kernel source, chain_kernel before and after",
                desc="c5: 65536 looping stereo sampler voices in total (256 two-second f32 resources per GPU, 188 MiB in HBM) -> gain->pan->4-stage biquad->48000-tap FIR reverb->master-bus sum, 512-frame blocks, 2 blocks/step, voices sharded over the ranks"),
 }
+# a voice graph that is NOT a chain: dry + two filtered sends into a 6-port SumNode, then pan and the master bus. It runs on the
+# generic per-node lowering (one launch group per scheduled node over the reference's own buffer assignment) and, for block-sized calls, on CUDA-graph replay.
+WORKLOADS["dag"] = dict(voices=1024, ch=2, block=256, blocks=64, bus=True, bytes_per_sample=4.004, kernel_class=-1, scaling="weak",
+                        kernel="generic lowering: chain_kernel (gain / pan / copies), biquad_delay_lanes (SVF, biquad), sum_kernel, bus tree",
+                        desc="dag: 1024 stereo voices/GPU, graph_in -> {gain | 2-stage SVF -> gain | 2-stage biquad -> gain} -> 6-port SumNode -> pan -> master bus, 256-frame blocks, 64 blocks/step")
 REVERB_WORKLOADS = ("c4", "c5")
 
 
@@ -105,6 +112,27 @@ def build_graph(fw, lib, workload, V, block, device, seed):
         nodes = [g.add_node(2, 2, fw.VolumeNode(100.0)), g.add_node(2, 2, fw.PanNode(0.0))]
         g.set_percent_volume(nodes[0], pct)
         g.set_pan(nodes[1], pan)
+    elif workload == "dag":
+        pct, pan = voice_params(V, seed)
+        gin, gout = g.graph_in_node(), g.graph_out_node()
+        dry, svf, wet1, bq, wet2 = (g.add_node(2, 2, fw.VolumeNode(80.0)), g.add_node(2, 2, fw.SvfNode(2)), g.add_node(2, 2, fw.VolumeNode(40.0)),
+                                    g.add_node(2, 2, fw.BiquadNode(2)), g.add_node(2, 2, fw.VolumeNode(30.0)))
+        mix, pn = g.add_node(6, 2, fw.SumNode()), g.add_node(2, 2, fw.PanNode(0.0))
+        g.set_percent_volume(dry, pct); g.set_pan(pn, pan)
+        g.set_svf_coeffs(svf, np.stack([[fw.design_svf(lib, 0, 1200.0, 0.8, SR), fw.design_svf(lib, 4, 3000.0, 1.2, SR)] for _ in range(V)]).astype(F32))
+        g.set_biquad_coeffs(bq, biquad_params(fw, lib, V, seed)[:, :2].copy())
+        for c in range(2):
+            g.connect(gin, c, dry, c, False); g.connect(gin, c, svf, c, False); g.connect(gin, c, bq, c, False)
+            g.connect(svf, c, wet1, c, False); g.connect(bq, c, wet2, c, False)
+            g.connect(dry, c, mix, c, False); g.connect(wet1, c, mix, 2 + c, False); g.connect(wet2, c, mix, 4 + c, False)
+            g.connect(mix, c, pn, c, False); g.connect(pn, c, gout, c, False)
+        proc = cx.activate(SR, C, C, block)
+        if proc is None:
+            raise RuntimeError("activate failed")
+        st = cx.update()
+        if st.graph_error is not None:
+            raise RuntimeError(f"compile failed: {st.graph_error} {cx.last_error()}")
+        return cx, proc
     elif workload in REVERB_WORKLOADS:
         nodes = [g.add_node(2, 2, fw.ConvReverbNode(reverb_ir(w["ir_len"])))]
         if workload == "c5":
@@ -470,10 +498,10 @@ def run_config(fw, lib, name, args, rank, world, local_rank, want_cpu):
     # ---- roofline of the dominant kernel class, CUDA events on the launching stream ----
     pk = peaks()
     kc = w["kernel_class"]
-    kernel_ms = prof_ms[kc] / prof_steps  # all launches of the dominant kernel class in one step
+    kernel_ms = (sum(prof_ms) if kc < 0 else prof_ms[kc]) / prof_steps  # all launches of the dominant kernel class in one step (dag: of every class)
     tensor = name in REVERB_WORKLOADS
     # c2 reads V*C*T f32 and writes the C*T bus; c3 moves in + out + delay-ring read + write = 16 B/sample
-    algo_bytes = 4 * C * T * (V + 1) if name == "c2" else int(w["bytes_per_sample"] * V * C * T)
+    algo_bytes = 4 * C * T * (V + 1) if name in ("c2", "dag") else int(w["bytes_per_sample"] * V * C * T)
     flops = 2.0 * w["ir_len"] * V * C * T if tensor else None
     if tensor:
         peak, peak_src = pk["tensor"]
@@ -483,6 +511,8 @@ def run_config(fw, lib, name, args, rank, world, local_rank, want_cpu):
         achieved = algo_bytes / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0
     traffic = None
     tp = ROOT / "profiles" / f"r02_{name}_traffic.json"
+    if not tp.exists():
+        tp = ROOT / "profiles" / f"r02_{name}_tensor.json"
     if tp.exists():
         try:
             traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch")
@@ -500,6 +530,23 @@ def run_config(fw, lib, name, args, rank, world, local_rank, want_cpu):
         roofline["frac_of_sustained_peak"] = (achieved / pk["tensor_sustained"]) if pk["tensor_sustained"] else None
 
     cpu = cpu_leg(name, V, F, KB) if (want_cpu and rank == 0) else None
+    block_call = None
+    if name == "dag":  # the interactive shape: one block per call, the same buffers every time -> captured once, then one cudaGraphLaunch per call
+        n_calls = 2000
+        for _ in range(8):
+            proc.process_planar_device(d_ins[0], d_out, Cin, C, F)
+        proc.sync()
+        r0, l0 = proc.graph_replays(), proc.kernel_launches()
+        t0 = time.perf_counter()
+        proc.event_record(0)
+        for _ in range(n_calls):
+            proc.process_planar_device(d_ins[0], d_out, Cin, C, F)
+        proc.event_record(1)
+        proc.sync()
+        wall = time.perf_counter() - t0
+        block_call = {"frames_per_call": F, "calls": n_calls, "us_per_call_device": proc.event_elapsed_ms(0, 1) * 1e3 / n_calls, "us_per_call_host": wall * 1e6 / n_calls,
+                      "graph_replays": proc.graph_replays() - r0, "kernels_per_call": (proc.kernel_launches() - l0) / n_calls,
+                      "note": "256-frame block for 1024 voices per call through fw_processor_process_planar_device; realtime budget of one block at 48 kHz is 5333 us"}
 
     res = {"metric": "mono_equiv_samples_per_sec", "value": value, "unit": "samples/s", "ms_per_step": ms_per_step,
            "ms_per_step_p10": p10, "ms_per_step_p90": p90, "passes": n_pass, "steps_per_pass": args.steps, "timed_seconds": float(per_pass.sum()) * 1e-3,
@@ -508,6 +555,8 @@ def run_config(fw, lib, name, args, rank, world, local_rank, want_cpu):
            "e2e": {"value": samples_per_step / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": in_bytes * world, "d2h_bytes_per_step": out_bytes * world,
                    "steps": e2e_steps, "ms_per_step": e2e_s * 1e3, "api": "fw_processor_process_planar (pinned host buffers)"},
            "gpu_launches_per_pass": int(launches), "roofline": roofline, "parity": parity, "cpu_baseline": cpu}
+    if block_call:
+        res["block_sized_calls"] = block_call
     if tensor:
         res["tflops"] = flops * world / (ms_per_step * 1e-3) / 1e12
     if world > 1 and w["bus"]:
@@ -625,7 +674,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--only", default="c2,c3,c4,c5", help="comma-separated configs to run (the first of c2 / the list is the headline)")
+    ap.add_argument("--only", default="c2,c3,c4,c5,dag", help="comma-separated configs to run (the first of c2 / the list is the headline)")
     ap.add_argument("--workload", default=None, help="alias of --only for a single config")
     ap.add_argument("--min-seconds", type=float, default=1.0, dest="min_seconds", help="timed seconds per config")
     args = ap.parse_args()

@@ -543,11 +543,10 @@ cudaError_t launch_reverb(const ReverbCall& rc, cudaStream_t st, std::string* er
         cudaError_t e = launch_pdl_r(reverb_prepare, grid, dim3(256), 0, st, rc.in, static_cast<__nv_bfloat16*>(rc.xh), rc.V, rc.C, rc.T, in_pitch, rc.cursor, rc.pitch, rc.zero_first, rc.chan_base);
         if (e != cudaSuccess) return e;
     }
-    const bool pair = rc.V > RV_BM && !(getenv("FW_REVERB_1CTA"));  /* TEMP A/B */  // a pair covers 256 voices: with 128 or fewer the second SM would idle
+    const bool pair = rc.V > RV_BM;  // a pair covers 256 voices: with 128 or fewer the second SM would idle
     const uint32_t sms = reverb_grid_max(), tiles_m = pair ? (rc.V + 2 * RV_BM - 1) / (2 * RV_BM) : (rc.V + RV_BM - 1) / RV_BM;
     const uint32_t units = pair ? reverb_pairs_max() : sms;
-    uint32_t bn = reverb_pick_bn(rc.T, tiles_m * rc.C, units, pair);
-    { static const int k = getenv("FW_REVERB_BN") ? atoi(getenv("FW_REVERB_BN")) : 0; if (k == 256 || k == 224 || k == 192 || k == 128) bn = (uint32_t)k; }  // TEMP A/B
+    const uint32_t bn = reverb_pick_bn(rc.T, tiles_m * rc.C, units, pair);
     const uint32_t kpad = reverb_kpad(rc.L);  // pitch of the Toeplitz rows (built for the widest tile)
     CUtensorMap tm_a, tm_b;
     if (!make_map_bf16_2d(&tm_a, rc.xh, (uint64_t)rc.cursor + rc.T, (uint64_t)(rc.chan_base + rc.C) * rc.V, rc.pitch, RV_BK, RV_BM) ||
