@@ -33,6 +33,7 @@ bool temporal_fast_path(const TemporalArgs& a);
 uint32_t reverb_kpad(uint32_t L);
 uint32_t reverb_hist(uint32_t L);
 uint32_t reverb_grid_max();   // CTAs of the persistent GEMM grid (= SMs)
+size_t reverb_ws_bytes();      // tail-wave fix-up workspace per ConvReverb node
 cudaError_t launch_reverb_build(const float* d_ir, void* d_bt, uint32_t L, uint32_t ir_ch, cudaStream_t st);
 cudaError_t launch_reverb(const ReverbCall& rc, cudaStream_t st, std::string* err);
 }  // namespace fw

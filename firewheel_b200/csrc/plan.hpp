@@ -142,6 +142,7 @@ struct ReverbCall {
     uint32_t V, C, T, L, ir_ch, cursor, pitch, zero_first;
     uint32_t chan_base;                 // history rows / IR channel of data channel c are (chan_base + c)
     uint32_t in_pitch, out_pitch;       // floats between (voice, channel) rows of in / out (0: T)
+    float* ws; uint32_t* flags; uint32_t epoch;  // tail-wave fix-up of the CTA-pair GEMM: reverb_ws_bytes(), one flag per SM, a launch counter (> 0, unique per launch)
 };
 
 // Multi-port SumNode on pool buffers (sum.rs:69-133): out = in[0] + in[1] + ... strictly left to right.

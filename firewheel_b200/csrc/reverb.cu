@@ -141,7 +141,25 @@ struct ReverbGemmArgs {
     float* out;                   // row (v * C + c) at out + row * out_pitch
     uint32_t out_pitch, V, C, T, Lr, cursor, ir_ch, num_kb, chan_base;
     uint32_t tiles_n, tiles_m, total_tiles;  // output tiles along frames / voices (per channel); tiles_n * tiles_m * C
+    // CTA-pair kernel, tail wave: the last `tail_tiles` tiles (fewer than half a wave of pairs) are each split along K between
+    // `tail_split` pairs; the pair with the first slice adds the others' partial sums (fix-up workspace, one flag per CTA).
+    uint32_t full_tiles, tail_tiles, tail_split;
+    float* ws; uint32_t* flags; uint32_t epoch;
 };
+struct RvSeg { uint32_t tile, k0, k1; };
+// segment i of pair P: whole tiles P, P + NP, ... of the full waves, then (at most) one slice of a tail tile
+__device__ __forceinline__ uint32_t rv_seg_count(const ReverbGemmArgs& a, uint32_t P, uint32_t NP) {
+    const uint32_t full = a.full_tiles > P ? (a.full_tiles - P + NP - 1) / NP : 0u;
+    return full + (P < a.tail_tiles * a.tail_split ? 1u : 0u);
+}
+__device__ __forceinline__ RvSeg rv_seg(const ReverbGemmArgs& a, uint32_t P, uint32_t NP, uint32_t i) {
+    const uint32_t t = P + i * NP;
+    if (t < a.full_tiles) return RvSeg{t, 0u, a.num_kb};
+    const uint32_t j = P / a.tail_split, sl = P % a.tail_split;
+    return RvSeg{a.full_tiles + j, (uint32_t)((uint64_t)sl * a.num_kb / a.tail_split), (uint32_t)((uint64_t)(sl + 1) * a.num_kb / a.tail_split)};
+}
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) { uint32_t v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
 
@@ -352,12 +370,15 @@ reverb_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
         asm volatile("griddepcontrol.wait;" ::: "memory");
         if (lane == 0) {
             uint32_t it = 0;
-            for (uint32_t t = P; t < a.total_tiles; t += NP) {
+            const uint32_t nseg = rv_seg_count(a, P, NP);
+            for (uint32_t si = 0; si < nseg; ++si) {
+                const RvSeg sg = rv_seg(a, P, NP, si);
+                const uint32_t t = sg.tile;
                 const uint32_t c = t / tiles_per_ch, rem = t % tiles_per_ch, mt = rem / a.tiles_n, nt = rem % a.tiles_n;
                 const int32_t col_a0 = (int32_t)(a.cursor + nt * BN) - (int32_t)a.Lr;
                 const int32_t row_a = (int32_t)((a.chan_base + c) * a.V + mt * 2u * RV_BM + rank * RV_BM);
                 const int32_t row_b = (int32_t)(((a.chan_base + c) % a.ir_ch) * RV_BN + rank * (BN / 2));
-                for (uint32_t kb = 0; kb < num_kb; ++kb, ++it) {
+                for (uint32_t kb = sg.k0; kb < sg.k1; ++kb, ++it) {
                     const uint32_t s = it % RV2_STAGES, ph = (it / RV2_STAGES) & 1u;
                     mbar_wait(&empty_bar[s], ph ^ 1u);
                     const uint32_t full_leader = mapa_rank(smem_u32(&full_bar[s]), 0);
@@ -370,13 +391,15 @@ reverb_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     } else if (warp == 1 && leader) {
         // ===== MMA issuer: the leader's elected lane drives both tensor cores =====
         constexpr uint32_t idesc = umma_idesc_bf16(2 * RV_BM, BN);
-        uint32_t it = 0, seg = 0;
-        for (uint32_t t = P; t < a.total_tiles; t += NP, ++seg) {
+        uint32_t it = 0;
+        const uint32_t nseg = rv_seg_count(a, P, NP);
+        for (uint32_t seg = 0; seg < nseg; ++seg) {
+            const RvSeg sg = rv_seg(a, P, NP, seg);
             const uint32_t buf = seg & 1u;
             mbar_wait(&tmem_empty_bar[buf], ((seg >> 1) & 1u) ^ 1u);
             tcgen05_fence_after();
             const uint32_t tmem_d = tmem_base + buf * RV_BN;
-            for (uint32_t kb = 0; kb < num_kb; ++kb, ++it) {
+            for (uint32_t kb = sg.k0; kb < sg.k1; ++kb, ++it) {
                 const uint32_t s = it % RV2_STAGES, ph = (it / RV2_STAGES) & 1u;
                 mbar_wait(&full_bar[s], ph);
                 tcgen05_fence_after();
@@ -385,9 +408,9 @@ reverb_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                     const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_b + s * RV2_B_BYTES_MAX));
 #pragma unroll
                     for (uint32_t k = 0; k < RV_BK / 16; ++k)
-                        tcgen05_mma2_f16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+                        tcgen05_mma2_f16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb != sg.k0 || k != 0) ? 1u : 0u);
                     tcgen05_commit2(&empty_bar[s]);
-                    if (kb + 1 == num_kb) tcgen05_commit2(&tmem_full_bar[buf]);
+                    if (kb + 1 == sg.k1) tcgen05_commit2(&tmem_full_bar[buf]);
                 }
                 __syncwarp();
             }
@@ -395,18 +418,43 @@ reverb_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
     } else if (warp >= 4) {
         // ===== epilogue (both CTAs): own 128 rows of the 256-row tile =====
         const uint32_t q = warp & 3u;
-        uint32_t seg = 0;
-        for (uint32_t t = P; t < a.total_tiles; t += NP, ++seg) {
-            const uint32_t buf = seg & 1u;
+        const uint32_t rrow = q * 32u + lane;
+        const uint32_t nseg = rv_seg_count(a, P, NP);
+        constexpr uint32_t WS_F4 = RV_BM * RV_BN / 4;  // float4 per CTA partial: [col / 4][row]
+        for (uint32_t seg = 0; seg < nseg; ++seg) {
+            const RvSeg sg = rv_seg(a, P, NP, seg);
+            const uint32_t buf = seg & 1u, t = sg.tile;
             const uint32_t c = t / tiles_per_ch, rem = t % tiles_per_ch, mt = rem / a.tiles_n, nt = rem % a.tiles_n;
-            const uint32_t n0 = nt * BN, v = mt * 2u * RV_BM + rank * RV_BM + q * 32u + lane;
+            const uint32_t n0 = nt * BN, v = mt * 2u * RV_BM + rank * RV_BM + rrow;
+            const bool partial = sg.k0 != 0;                                  // a later K-slice of a tail tile: park the partial sums
+            const uint32_t n_follow = (sg.k0 == 0 && sg.k1 < num_kb) ? a.tail_split - 1u : 0u;  // first slice: add the others'
+            if (n_follow) {  // the other slices run in this same wave on pairs P + 1 ...: they finish when we do
+                for (uint32_t f = lane; f < n_follow; f += 32u) while (ld_acquire_u32(a.flags + (P + 1u + f) * 2u + rank) != a.epoch) { }
+                __syncwarp();
+            }
             mbar_wait(&tmem_full_bar[buf], (seg >> 1) & 1u);
             tcgen05_fence_after();
             float* dst_row = a.out + ((size_t)v * a.C + c) * a.out_pitch + n0;
+            float4* ws_me = reinterpret_cast<float4*>(a.ws) + (size_t)(P * 2u + rank) * WS_F4 + rrow;
 #pragma unroll 1
             for (uint32_t col = 0; col < BN; col += 32) {
                 uint32_t r[32];
                 tcgen05_ld_32x32b_x32(tmem_base + ((q * 32u) << 16) + buf * RV_BN + col, r);
+                if (partial) {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4)
+                        __stcg(ws_me + (size_t)((col + i) >> 2) * RV_BM, make_float4(__uint_as_float(r[i]), __uint_as_float(r[i + 1]), __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3])));
+                    continue;
+                }
+                for (uint32_t f = 0; f < n_follow; ++f) {  // ascending K: ((first + slice 1) + slice 2) ...
+                    const float4* wf = reinterpret_cast<const float4*>(a.ws) + (size_t)((P + 1u + f) * 2u + rank) * WS_F4 + rrow;
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        const float4 pp = __ldcg(wf + (size_t)((col + i) >> 2) * RV_BM);
+                        r[i] = __float_as_uint(__uint_as_float(r[i]) + pp.x); r[i + 1] = __float_as_uint(__uint_as_float(r[i + 1]) + pp.y);
+                        r[i + 2] = __float_as_uint(__uint_as_float(r[i + 2]) + pp.z); r[i + 3] = __float_as_uint(__uint_as_float(r[i + 3]) + pp.w);
+                    }
+                }
                 if (v < a.V) {
                     if (n0 + col + 32 <= a.T && ((a.T | a.out_pitch) & 3u) == 0) {
 #pragma unroll
@@ -419,7 +467,13 @@ reverb_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
                 }
             }
             tcgen05_fence_before();
-            __syncwarp();
+            if (partial) {  // publish: all 128 epilogue threads of this CTA have stored, then one release store
+                __threadfence();
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (threadIdx.x == 128) st_release_u32(a.flags + P * 2u + rank, a.epoch);
+            } else {
+                __syncwarp();
+            }
             if (lane == 0) mbar_arrive_cluster(mapa_rank(smem_u32(&tmem_empty_bar[buf]), 0));
         }
     }
@@ -465,6 +519,7 @@ cudaError_t launch_reverb_build(const float* d_ir, void* d_bt, uint32_t L, uint3
 
 // One call: append the block (bf16) behind the history at `cursor`, run the GEMM over windows ending in it.
 // The caller owns the cursor policy (compaction when the buffer is full); cursor is a multiple of 8 and >= Lr.
+size_t reverb_ws_bytes() { return (size_t)reverb_grid_max() * RV_BM * RV_BN * sizeof(float); }  // one [128][256] f32 partial per CTA
 uint32_t reverb_grid_max() {
     static int sms = 0;
     if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
@@ -560,6 +615,11 @@ cudaError_t launch_reverb(const ReverbCall& rc, cudaStream_t st, std::string* er
     ga.chan_base = rc.chan_base;
     ga.tiles_n = (rc.T + bn - 1) / bn; ga.tiles_m = tiles_m; ga.total_tiles = ga.tiles_n * ga.tiles_m * rc.C;
     if (ga.total_tiles == 0) return cudaSuccess;
+    ga.full_tiles = ga.total_tiles; ga.tail_tiles = 0; ga.tail_split = 1; ga.ws = rc.ws; ga.flags = rc.flags; ga.epoch = rc.epoch;
+    if (pair && rc.ws && rc.flags && ga.total_tiles > units) {  // a tail wave at most half full is split along K (see ReverbGemmArgs)
+        const uint32_t rem = ga.total_tiles % units;
+        if (rem && rem * 2u <= units && ga.num_kb >= 64u) { ga.tail_tiles = rem; ga.tail_split = units / rem; ga.full_tiles = ga.total_tiles - rem; }
+    }
     if (pair) {
         switch (bn) {
             case 224: return launch_gemm2<224>(tm_a, tm_b, ga, units, st);

@@ -123,6 +123,7 @@ struct NodeDeviceState {
     uint32_t ring_pos = 0;       // stream-side cursor into the ring
     // conv reverb: Toeplitz-expanded IR and the ping-pong bf16 sample history (reverb.cu)
     void* d_bt = nullptr; void* d_xh[2] = {nullptr, nullptr}; uint32_t xh_cur = 0, xh_cursor = 0, xh_pitch = 0;  // cursor: where the next block is appended
+    float* d_rv_ws = nullptr; uint32_t* d_rv_flags = nullptr; uint32_t rv_epoch = 0;  // tail-wave fix-up of the CTA-pair GEMM (reverb.cu)
     static constexpr uint32_t kReverbMaxFrames = 65536;  // longest call the history buffers are sized for
     // polyphase resampler: table + per-voice transport mirrors + the device-resident Q32.32 position
     float* d_rs_table = nullptr; uint32_t* d_rs_res = nullptr; uint32_t* d_rs_flags = nullptr; uint64_t* d_rs_step = nullptr;
@@ -142,7 +143,7 @@ struct NodeDeviceState {
             else if (vt.drop_processor) vt.drop_processor(custom_proc);
         }
         for (int i = 0; i < 2; ++i) { cudaFree(d_target[i]); cudaFree(sm_input[i]); cudaFree(sm_last[i]); cudaFree(sm_status[i]); }
-        cudaFree(d_coeffs); cudaFree(d_state); cudaFree(d_ring); cudaFree(d_bt); cudaFree(d_xh[0]); cudaFree(d_xh[1]);
+        cudaFree(d_coeffs); cudaFree(d_state); cudaFree(d_ring); cudaFree(d_bt); cudaFree(d_xh[0]); cudaFree(d_xh[1]); cudaFree(d_rv_ws); cudaFree(d_rv_flags);
         cudaFree(d_playing); cudaFree(d_playhead); cudaFree(d_loop_flags); cudaFree(d_loop_start); cudaFree(d_loop_end); cudaFree(d_res);
         cudaFree(d_msgs); cudaFree(d_msg_off); cudaFreeHost(h_msgs); cudaFreeHost(h_off); cudaFreeHost(h_cnt); if (ev_staged) cudaEventDestroy(ev_staged);
         cudaFree(d_rs_table); cudaFree(d_rs_res); cudaFree(d_rs_flags); cudaFree(d_rs_step); cudaFree(d_rs_pos);
@@ -174,7 +175,8 @@ struct NodeDeviceState {
             d_xh[0] = dev_alloc<uint16_t>((size_t)V * channels * xh_pitch);  // zero history
             d_xh[1] = dev_alloc<uint16_t>((size_t)V * channels * xh_pitch);
             float* d_ir = dev_alloc<float>((size_t)ich * L, false);
-            if (!d_bt || !d_xh[0] || !d_xh[1] || !d_ir) { cudaFree(d_ir); return false; }
+            d_rv_ws = dev_alloc<float>(reverb_ws_bytes() / sizeof(float), false); d_rv_flags = dev_alloc<uint32_t>(reverb_grid_max());
+            if (!d_bt || !d_xh[0] || !d_xh[1] || !d_ir || !d_rv_ws || !d_rv_flags) { cudaFree(d_ir); return false; }
             bool ok = FW_CUDA(cudaMemcpy(d_ir, params->ir.data(), (size_t)ich * L * 4, cudaMemcpyHostToDevice)) &&
                       FW_CUDA(launch_reverb_build(d_ir, d_bt, L, ich, nullptr)) && FW_CUDA(cudaDeviceSynchronize());
             cudaFree(d_ir);
@@ -1444,6 +1446,7 @@ static int enqueue_generic(fw_processor* p, Plan& pl, const float* d_in, float* 
                     ReverbCall rc{};
                     rc.in = buf(gn.in_buf[c]); rc.out = buf(gn.out_buf[c]); rc.xh = rs.d_xh[rs.xh_cur]; rc.bt = rs.d_bt;
                     rc.V = V; rc.C = 1; rc.T = T; rc.L = rs.params->ir_len; rc.ir_ch = rs.params->ir_channels; rc.cursor = rs.xh_cursor; rc.pitch = rs.xh_pitch; rc.chan_base = c;
+                    rc.ws = rs.d_rv_ws; rc.flags = rs.d_rv_flags; rc.epoch = ++rs.rv_epoch;
                     std::string rerr;
                     ProfScope ps(p, 3);
                     if (!FW_CUDA(launch_reverb(rc, p->stream, &rerr))) { if (!rerr.empty()) g_dev_err = rerr; return FW_PROC_DEVICE_ERROR; }
@@ -1589,6 +1592,7 @@ static int enqueue_chunk(fw_processor* p, Plan& pl, const float* d_in, float* d_
             rc.in = src; rc.out = dst; rc.in_pitch = src_pitch; rc.out_pitch = dst_pitch; rc.xh = rs.d_xh[rs.xh_cur]; rc.bt = rs.d_bt;
             rc.V = V; rc.C = sg.c_in; rc.T = T; rc.L = rs.params->ir_len; rc.ir_ch = rs.params->ir_channels; rc.cursor = rs.xh_cursor; rc.pitch = rs.xh_pitch;
             rc.zero_first = si == 0 ? ck.zero_first : 0u; rc.chan_base = 0;
+            rc.ws = rs.d_rv_ws; rc.flags = rs.d_rv_flags; rc.epoch = ++rs.rv_epoch;
             std::string rerr;
             { ProfScope ps(p, 3); if (!FW_CUDA(launch_reverb(rc, p->stream, &rerr))) { if (!rerr.empty()) g_dev_err = rerr; return FW_PROC_DEVICE_ERROR; } }
             p->launches += 2;

@@ -270,6 +270,35 @@ def test_conv_reverb_full_length_vs_fft(gpu, oracle):
             assert norm_max_err(y[v, c], ref) <= 1e-5, (v, c, norm_max_err(y[v, c], ref))
 
 
+@pytest.mark.parametrize("V,n_tiles,L", [(300, 19, 4100), (129, 41, 4100), (520, 13, 4100)])
+def test_conv_reverb_many_tiles_vs_fft(gpu, oracle, V, n_tiles, L):
+    """More output tiles than CTA pairs on the chip (76, 82, 78 tiles on 74 pairs): full waves of whole tiles plus a short tail wave whose tiles
+    are split along K between many pairs with a fix-up add (reverb.cu). Reference = f64 FFT convolution of the bf16-rounded operands."""
+    import scipy.signal
+    from firewheel_b200 import AudioGraphConfig, ConvReverbNode, FirewheelGraphCtx
+    T = n_tiles * 256
+    ir = reverb_ir(L, 2, 5)
+    x = synth((V, 2, T), 77)
+    cx = FirewheelGraphCtx(gpu, AudioGraphConfig(num_graph_inputs=2, num_graph_outputs=2, num_voices=V, max_call_frames=T))
+    g = cx.graph
+    rv = g.add_node(2, 2, ConvReverbNode(ir))
+    for c in range(2):
+        g.connect(g.graph_in_node(), c, rv, c, False); g.connect(rv, c, g.graph_out_node(), c, False)
+    proc = cx.activate(48000, 2, 2, 256)
+    assert cx.update().graph_error is None, cx.last_error()
+    y1, _ = run_planar(proc, x, 2)
+    y2, _ = run_planar(proc, x, 2)   # second call: history carries over
+    proc.free(); cx.update(); cx.free()
+    rb = np.vectorize(oracle.bf16_round, otypes=[f32])
+    hb = rb(ir).astype(np.float64)
+    for v in list(range(0, V, max(1, V // 7))) + [V - 1]:
+        xb = rb(np.concatenate([x[v], x[v]], axis=1)).astype(np.float64)
+        for c in range(2):
+            ref = scipy.signal.fftconvolve(xb[c], hb[c])[: 2 * T]
+            assert norm_max_err(y1[v, c], ref[:T]) <= 1e-5, (v, c, norm_max_err(y1[v, c], ref[:T]))
+            assert norm_max_err(y2[v, c], ref[T:]) <= 1e-5, (v, c, norm_max_err(y2[v, c], ref[T:]))
+
+
 def test_reverb_in_a_mixed_chain_with_bus(gpu, oracle):
     from firewheel_b200 import ConvReverbNode
     ir = reverb_ir(300, 2, 3)
