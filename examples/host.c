@@ -3,7 +3,8 @@
  *   gcc -std=c99 -I include examples/host.c -o host -L firewheel_b200/lib -lfirewheel_b200 -Wl,-rpath,$PWD/firewheel_b200/lib
  *
  * Builds a voice graph (sampler -> gain -> graph_out), prints the compiled schedule, and — when a CUDA device is present —
- * activates it for 64 voices with a master bus, starts every voice on a looping sample and renders a few blocks.
+ * activates it for 64 voices with a master bus, starts every voice on a looping sample and renders a few blocks, one call with
+ * parameter stores stamped to take effect in the middle of it (fw_ctx_set_event_block).
  * Without a device it stops after the schedule: there is no CPU fallback. */
 #include <math.h>
 #include <stdio.h>
@@ -53,6 +54,11 @@ int main(void) {
     enum { T = 1024 };
     static float bus[T * 2];   /* interleaved stereo master bus */
     for (int call = 0; call < 3; ++call) {
+        if (call == 1) {   /* block-stamped control: duck the gain at block 1 of this 4-block call and pause voice 0 at block 3 */
+            fw_ctx_set_event_block(cx, 1); fw_volume_set_percent_volume(cx, vol, FW_ALL_VOICES, 20.0f);
+            fw_ctx_set_event_block(cx, 3); fw_sampler_pause(cx, smp, 0);
+            fw_ctx_set_event_block(cx, 0);
+        }
         int rc = fw_processor_process_interleaved(proc, NULL, bus, 0, 2, T, call * (double)T / 48000.0, 0);
         double e = 0.0;
         for (int i = 0; i < T * 2; ++i) e += (double)bus[i] * bus[i];

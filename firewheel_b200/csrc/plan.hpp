@@ -131,6 +131,9 @@ struct TemporalArgs {
     uint32_t svf;                  // 1: `coeffs` holds SVF stages [R / C][ns][6] and the recurrence is the SVF's
     uint32_t row_base;             // lanes kernel: first row of CTA 0 (the ragged last CTA is launched on its own)
     uint32_t in_pitch, out_pitch;  // floats between rows of `in` / `out` (0: T). A call chunk is a column window of longer rows.
+    // Two row segments in one pass (generic lowering: two channels of a node live in two pool buffers): rows >= seg_rows read in2 / write out2
+    // at row (r - seg_rows) and use state row + 1 (the next channel). seg_rows == 0: one segment.
+    const float* in2; float* out2; uint32_t seg_rows, pad_seg;
     float k_one, k_negzero, k_negone, k_two;  // set by launch_temporal: opaque constants of the packed kernel's exact-fma spelling
 };
 

@@ -1405,26 +1405,16 @@ static int enqueue_generic(fw_processor* p, Plan& pl, const float* d_in, float* 
                 p->launches += 2;
                 break;
             }
-            case FW_NODE_SVF: {
-                NodeDeviceState& st = *gn.st;
-                const uint32_t nc = (uint32_t)gn.in_buf.size();
-                for (uint32_t c = 0; c < nc; ++c) {
-                    TemporalArgs ta{};
-                    ta.in = buf(gn.in_buf[c]); ta.out = buf(gn.out_buf[c]); ta.R = V; ta.C = 1; ta.T = T; ta.srow_mul = nc; ta.srow_add = c;
-                    ta.svf = 1; ta.ns = st.params->num_stages; ta.coeffs = st.d_coeffs; ta.state = st.d_state;
-                    ProfScope ps(p, 3);
-                    if (!FW_CUDA(launch_temporal(ta, p->stream))) return FW_PROC_DEVICE_ERROR;
-                    p->launches++;
-                }
-                break;
-            }
-            case FW_NODE_BIQUAD: case FW_NODE_DELAY: {
+            case FW_NODE_SVF: case FW_NODE_BIQUAD: case FW_NODE_DELAY: {  // two channels (two pool buffers) per pass: twice the rows per launch
                 NodeDeviceState& st = *gn.st;
                 const uint32_t nc = (uint32_t)gn.in_buf.size(), D = gn.kind == FW_NODE_DELAY ? st.params->delay : 0u;
-                for (uint32_t c = 0; c < nc; ++c) {
+                for (uint32_t c = 0; c < nc; c += 2) {
+                    const bool two = c + 1 < nc;
                     TemporalArgs ta{};
-                    ta.in = buf(gn.in_buf[c]); ta.out = buf(gn.out_buf[c]); ta.R = V; ta.C = 1; ta.T = T; ta.srow_mul = nc; ta.srow_add = c;
-                    if (gn.kind == FW_NODE_BIQUAD) { ta.ns = st.params->num_stages; ta.coeffs = st.d_coeffs; ta.state = st.d_state; }
+                    ta.in = buf(gn.in_buf[c]); ta.out = buf(gn.out_buf[c]); ta.R = two ? 2 * V : V; ta.C = 1; ta.T = T; ta.srow_mul = nc; ta.srow_add = c;
+                    if (two) { ta.in2 = buf(gn.in_buf[c + 1]); ta.out2 = buf(gn.out_buf[c + 1]); ta.seg_rows = V; }
+                    if (gn.kind == FW_NODE_SVF) { ta.svf = 1; ta.ns = st.params->num_stages; ta.coeffs = st.d_coeffs; ta.state = st.d_state; }
+                    else if (gn.kind == FW_NODE_BIQUAD) { ta.ns = st.params->num_stages; ta.coeffs = st.d_coeffs; ta.state = st.d_state; }
                     else if (D) { ta.D = D; ta.ring = st.d_ring; ta.pos = st.ring_pos; }
                     ProfScope ps(p, 3);
                     if (!FW_CUDA(launch_temporal(ta, p->stream))) return FW_PROC_DEVICE_ERROR;

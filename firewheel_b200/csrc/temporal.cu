@@ -30,6 +30,16 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 
 constexpr int kStateStages = 8;  // state layout [row][8][2] regardless of the cascade length
 
+// Row r of a pass -> its segment (TemporalArgs::seg_rows), the row inside the segment, and its state / ring row.
+struct RowMap { uint32_t seg, rr; size_t srow; };
+__device__ __forceinline__ RowMap row_map(const TemporalArgs& a, uint32_t r) {
+    RowMap m; m.seg = (a.seg_rows != 0u && r >= a.seg_rows) ? 1u : 0u; m.rr = r - m.seg * a.seg_rows;
+    m.srow = (size_t)m.rr * a.srow_mul + a.srow_add + m.seg;
+    return m;
+}
+__device__ __forceinline__ const float* row_in(const TemporalArgs& a, const RowMap& m) { return (m.seg ? a.in2 : a.in) + (size_t)m.rr * a.in_pitch; }
+__device__ __forceinline__ float* row_out(const TemporalArgs& a, const RowMap& m) { return (m.seg ? a.out2 : a.out) + (size_t)m.rr * a.out_pitch; }
+
 // Fast path: stage-parallel lanes, one self-contained warp per 32/L rows.
 //   * A row (voice-channel) is owned by L consecutive lanes; lane s runs biquad stage s. Lane s hands its y to lane
 //     s+1 with shfl_up and is skewed by TWO iterations per stage (lane s works on sample n-2s), so the shuffle
@@ -91,10 +101,11 @@ __global__ void __launch_bounds__(32) biquad_delay_lanes(TemporalArgs a) {
         b0[j] = b1[j] = b2[j] = a1[j] = a2[j] = c5[j] = s1[j] = s2[j] = q0[j] = q1[j] = 0.0f;
         yb[j][0] = yb[j][1] = yb[j][2] = yb[j][3] = 0.0f;
         if (NS > 0 && lane_ok[j]) {
-            const float* k = a.coeffs + ((size_t)(r / a.C) * NS + s) * (SVF ? 6 : 5);
+            const RowMap rm = row_map(a, r);
+            const float* k = a.coeffs + ((size_t)(rm.rr / a.C) * NS + s) * (SVF ? 6 : 5);
             b0[j] = k[0]; b1[j] = k[1]; b2[j] = k[2]; a1[j] = k[3]; a2[j] = k[4];
             if (SVF) c5[j] = k[5];
-            const size_t sr = (size_t)r * a.srow_mul + a.srow_add;
+            const size_t sr = rm.srow;
             s1[j] = a.state[(sr * kStateStages + s) * 2]; s2[j] = a.state[(sr * kStateStages + s) * 2 + 1];
         }
     }
@@ -116,10 +127,10 @@ __global__ void __launch_bounds__(32) biquad_delay_lanes(TemporalArgs a) {
         const uint32_t idx = lane + 32u * i, rr = idx / G, g = idx % G;
         hi[i] = g >= 8u;  // 64-frame chunks: the second 32 frames of a ring chunk may lie beyond the wrap
         ok[i] = FULL || row0 + rr < R;
-        const size_t row = ok[i] ? row0 + rr : 0;
-        in_p[i] = a.in + row * a.in_pitch + g * 4u;
-        out_p[i] = a.out + row * a.out_pitch + g * 4u;
-        ring_p[i] = DELAY ? a.ring + (row * a.srow_mul + a.srow_add) * D + (g & 7u) * 4u : nullptr;
+        const RowMap rm = row_map(a, ok[i] ? row0 + rr : 0u);
+        in_p[i] = row_in(a, rm) + g * 4u;
+        out_p[i] = row_out(a, rm) + g * 4u;
+        ring_p[i] = DELAY ? a.ring + rm.srow * D + (g & 7u) * 4u : nullptr;
         sw[i] = rr * G + (g ^ (rr & 7u));  // float4 index inside a tile
     }
     const uint32_t nch = T / (uint32_t)CHF;
@@ -304,7 +315,7 @@ __global__ void __launch_bounds__(32) biquad_delay_lanes(TemporalArgs a) {
 #pragma unroll
     for (int j = 0; j < RPL; ++j) {
         if (NS > 0 && lane_ok[j]) {
-            const size_t sr = (size_t)(row0 + row_l[j]) * a.srow_mul + a.srow_add;
+            const size_t sr = row_map(a, row0 + row_l[j]).srow;
             a.state[(sr * kStateStages + s) * 2] = s1[j];
             a.state[(sr * kStateStages + s) * 2 + 1] = s2[j];
         }
@@ -318,14 +329,15 @@ __global__ void __launch_bounds__(64) biquad_delay_generic(TemporalArgs a) {
     if (r >= a.R) return;
     const uint32_t NS = a.ns, T = a.T, D = a.D;
     float b0[kStateStages], b1[kStateStages], b2[kStateStages], a1[kStateStages], a2[kStateStages], s1[kStateStages], s2[kStateStages];
+    const RowMap rm = row_map(a, r);
     for (uint32_t s = 0; s < NS; ++s) {
-        const float* k = a.coeffs + ((size_t)(r / a.C) * NS + s) * 5;
+        const float* k = a.coeffs + ((size_t)(rm.rr / a.C) * NS + s) * 5;
         b0[s] = k[0]; b1[s] = k[1]; b2[s] = k[2]; a1[s] = k[3]; a2[s] = k[4];
-        s1[s] = a.state[(((size_t)r * a.srow_mul + a.srow_add) * kStateStages + s) * 2]; s2[s] = a.state[(((size_t)r * a.srow_mul + a.srow_add) * kStateStages + s) * 2 + 1];
+        s1[s] = a.state[(rm.srow * kStateStages + s) * 2]; s2[s] = a.state[(rm.srow * kStateStages + s) * 2 + 1];
     }
-    const float* in = a.in + (size_t)r * a.in_pitch;
-    float* out = a.out + (size_t)r * a.out_pitch;
-    float* ring = D ? a.ring + ((size_t)r * a.srow_mul + a.srow_add) * D : nullptr;
+    const float* in = row_in(a, rm);
+    float* out = row_out(a, rm);
+    float* ring = D ? a.ring + rm.srow * D : nullptr;
     uint32_t p = D ? a.pos % D : 0;
     for (uint32_t n = 0; n < T; ++n) {
         float x = n < a.zero_first ? 0.0f : in[n];
@@ -338,7 +350,7 @@ __global__ void __launch_bounds__(64) biquad_delay_generic(TemporalArgs a) {
         if (D) { const float d = ring[p]; ring[p] = x; x = d; p = p + 1 == D ? 0 : p + 1; }
         out[n] = x;
     }
-    for (uint32_t s = 0; s < NS; ++s) { const size_t sr = (size_t)r * a.srow_mul + a.srow_add; a.state[(sr * kStateStages + s) * 2] = s1[s]; a.state[(sr * kStateStages + s) * 2 + 1] = s2[s]; }
+    for (uint32_t s = 0; s < NS; ++s) { const size_t sr = rm.srow; a.state[(sr * kStateStages + s) * 2] = s1[s]; a.state[(sr * kStateStages + s) * 2 + 1] = s2[s]; }
 }
 
 // SVF cascade (spec ours, include/fw_b200.h): one thread per row, scalar. State rows as the biquad's: [row][8][2] = {ic1, ic2}.
@@ -348,14 +360,15 @@ __global__ void __launch_bounds__(64) svf_generic(TemporalArgs a) {
     if (r >= a.R) return;
     const uint32_t NS = a.ns, T = a.T;
     float a1[kStateStages], a2[kStateStages], a3[kStateStages], m0[kStateStages], m1[kStateStages], m2[kStateStages], ic1[kStateStages], ic2[kStateStages];
-    const size_t sr = (size_t)r * a.srow_mul + a.srow_add;
+    const RowMap rm = row_map(a, r);
+    const size_t sr = rm.srow;
     for (uint32_t s = 0; s < NS; ++s) {
-        const float* k = a.coeffs + ((size_t)(r / a.C) * NS + s) * 6;
+        const float* k = a.coeffs + ((size_t)(rm.rr / a.C) * NS + s) * 6;
         a1[s] = k[0]; a2[s] = k[1]; a3[s] = k[2]; m0[s] = k[3]; m1[s] = k[4]; m2[s] = k[5];
         ic1[s] = a.state[(sr * kStateStages + s) * 2]; ic2[s] = a.state[(sr * kStateStages + s) * 2 + 1];
     }
-    const float* in = a.in + (size_t)r * a.in_pitch;
-    float* out = a.out + (size_t)r * a.out_pitch;
+    const float* in = row_in(a, rm);
+    float* out = row_out(a, rm);
     for (uint32_t n = 0; n < T; ++n) {
         float x = n < a.zero_first ? 0.0f : in[n];
         for (uint32_t s = 0; s < NS; ++s) {
@@ -426,7 +439,7 @@ static cudaError_t launch_lanes(const TemporalArgs& a, cudaStream_t st) {
 
 bool temporal_fast_path(const TemporalArgs& a) {
     if (a.T == 0 || a.T % 32u || a.zero_first % 32u) return false;
-    if ((reinterpret_cast<uintptr_t>(a.in) | reinterpret_cast<uintptr_t>(a.out) | reinterpret_cast<uintptr_t>(a.ring)) % 16u) return false;
+    if ((reinterpret_cast<uintptr_t>(a.in) | reinterpret_cast<uintptr_t>(a.out) | reinterpret_cast<uintptr_t>(a.ring) | reinterpret_cast<uintptr_t>(a.in2) | reinterpret_cast<uintptr_t>(a.out2)) % 16u) return false;
     if ((a.in_pitch | a.out_pitch) % 4u) return false;
     if (a.D && (a.D % 32u || a.pos % 32u || a.D < 160u)) return false;
     return true;
