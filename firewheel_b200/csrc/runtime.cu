@@ -35,10 +35,16 @@
 
 namespace fw {
 
+// Last device-side error text. Written on the thread that hit the error (main thread, stream thread, or the fw_stream producer);
+// fw_last_device_error() returns the calling thread's own message if it has one, else the most recent one from any thread.
 static thread_local std::string g_dev_err;
+static std::mutex g_err_mu;              // error path only: never taken on a successful call
+static std::string g_err_any;
+static void publish_error() { std::lock_guard<std::mutex> lk(g_err_mu); g_err_any = g_dev_err; }
 static bool cuda_ok(cudaError_t e, const char* what) {
     if (e == cudaSuccess) return true;
     g_dev_err = std::string(what) + ": " + cudaGetErrorString(e);
+    publish_error();
     return false;
 }
 #define FW_CUDA(call) fw::cuda_ok((call), #call)
@@ -1760,6 +1766,7 @@ static int check_device_error(fw_processor* p) {
     if ((e & 15u) == 0 || ((e >> 4) != kGraphEpoch && (int32_t)((e >> 4) - (p->first_epoch_of_call & 0x0fffffffu)) < 0)) return 0;
     if ((e >> 4) == kGraphEpoch) cudaMemsetAsync(p->plan->rec.error, 0, 4, p->stream);  // a replayed chunk cannot stamp its epoch: report once, then clear
     g_dev_err = (e & 15u) == 2 ? "master-bus exchange timed out waiting for a peer rank" : "control pass overflowed its transient-block budget (a gain jump beyond 10000 %?)";
+    publish_error();
     return FW_PROC_DEVICE_ERROR;
 }
 
@@ -1859,7 +1866,12 @@ void fw_processor_free(fw_processor* p) {  // Drop processor.rs:251-263
 
 // ---- device plumbing ----------------------------------------------------------------------------
 int fw_device_count(void) { int n = 0; if (!FW_CUDA(cudaGetDeviceCount(&n))) return 0; return n; }
-const char* fw_last_device_error(void) { return g_dev_err.c_str(); }
+const char* fw_last_device_error(void) {
+    if (!g_dev_err.empty()) return g_dev_err.c_str();
+    static thread_local std::string copy;
+    { std::lock_guard<std::mutex> lk(g_err_mu); copy = g_err_any; }
+    return copy.c_str();
+}
 void* fw_dev_malloc(int device, uint64_t bytes) { void* p = nullptr; if (!FW_CUDA(cudaSetDevice(device)) || !FW_CUDA(cudaMalloc(&p, bytes))) return nullptr; return p; }
 void fw_dev_free(int device, void* p) { cudaSetDevice(device); cudaFree(p); }
 void* fw_host_alloc_pinned(uint64_t bytes) { void* p = nullptr; if (!FW_CUDA(cudaMallocHost(&p, bytes))) return nullptr; return p; }
@@ -1933,7 +1945,7 @@ static void stream_producer(fw_stream* s) {
         const uint32_t status = s->pending_status.exchange(0, std::memory_order_acq_rel);
         const int rc = fw_processor_process_interleaved(s->p, nullptr, dst, 0, s->n_out, s->period, (double)frames_rendered / (double)s->sample_rate, status);
         if (rc != FW_PROC_OK) {  // DropProcessor (lib.rs:440-448) or a device error: this period is silence, and so is everything after it
-            if (rc < 0) std::fill(dst, dst + (size_t)s->period * s->n_out, 0.0f);
+            if (rc < 0) { std::fill(dst, dst + (size_t)s->period * s->n_out, 0.0f); publish_error(); }  // visible to fw_last_device_error() on the consumer's thread
             s->dropped.store(true, std::memory_order_release);
             s->produced.store(prod + 1, std::memory_order_release);
             return;
