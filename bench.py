@@ -458,6 +458,7 @@ def run_config(fw, lib, name, args, rank, world, local_rank, want_cpu):
     launches = (proc.kernel_launches() - launches0) // n_pass
     clk = clocks.stop()
     per_pass = comm.max(mine)  # max over ranks, pass by pass
+    by_rank = [float(v) / args.steps for v in comm.gather(np.array([np.median(mine)], np.float64))[:, 0]]  # each rank's own median: GPUs of one box differ
     ms_per_step = float(np.median(per_pass)) / args.steps
     p10, p90 = (float(np.percentile(per_pass, q)) / args.steps for q in (10, 90))
     samples_per_step = V * C * T * world
@@ -550,7 +551,7 @@ def run_config(fw, lib, name, args, rank, world, local_rank, want_cpu):
                       "note": "256-frame block for 1024 voices per call through fw_processor_process_planar_device; realtime budget of one block at 48 kHz is 5333 us"}
 
     res = {"metric": "mono_equiv_samples_per_sec", "value": value, "unit": "samples/s", "ms_per_step": ms_per_step,
-           "ms_per_step_p10": p10, "ms_per_step_p90": p90, "passes": n_pass, "steps_per_pass": args.steps, "timed_seconds": float(per_pass.sum()) * 1e-3,
+           "ms_per_step_p10": p10, "ms_per_step_p90": p90, "ms_per_step_by_rank": by_rank, "passes": n_pass, "steps_per_pass": args.steps, "timed_seconds": float(per_pass.sum()) * 1e-3,
            "scaling": w["scaling"], "dtype": "bf16 x bf16 -> f32 (FIR), f32 elsewhere" if tensor else "f32",
            "config": cfg_dict(name, V, world), "clocks": clk,
            "e2e": {"value": samples_per_step / e2e_s, "unit": "samples/s", "h2d_bytes_per_step": in_bytes * world, "d2h_bytes_per_step": out_bytes * world,
@@ -660,7 +661,7 @@ def run_b200(args, rank, world, local_rank):
             "warmup": max(args.warmup, 3), "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": head["scaling"], "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": head["config"], "clocks": head["clocks"], "e2e": head["e2e"],
             "gpu_launches": head["gpu_launches_per_pass"], "roofline": head["roofline"], "cpu_baseline": head["cpu_baseline"]}
-    for k in ("ms_per_step_p10", "ms_per_step_p90", "passes", "timed_seconds", "parity", "exchange", "bus_parity", "bus_identical_on_all_ranks"):
+    for k in ("ms_per_step_p10", "ms_per_step_p90", "ms_per_step_by_rank", "passes", "timed_seconds", "parity", "exchange", "bus_parity", "bus_identical_on_all_ranks"):
         if k in head:
             line[k] = head[k]
     if want_cpu and line["cpu_baseline"] is not None:

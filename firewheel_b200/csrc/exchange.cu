@@ -5,8 +5,9 @@
 // on a high-priority side stream so that it overlaps control + chain of call e + 1. What it needs from the main stream is
 // "the rank-local bus of call e is complete". A CUDA event recorded on the main stream would say that, but an event between
 // two kernels cuts their programmatic-dependent-launch overlap (measured: ~5 us per call on a 94 us step). Instead:
-//   K-signal  (main stream, PDL): runs once the kernel before it — the last combine of call e — has completed, and
-//             publishes e in a device word;
+//   signal    the last CTA of the combine kernel that completes the rank-local bus publishes e in a device word (kernels.cu:
+//             combine_kernel, done_word); K-signal below does the same as a one-warp PDL kernel when there is no combine level
+//             (<= 64 voices: the chain kernel writes the bus itself);
 //   K-wait    (side stream): one warp polls that word until it reaches e; the all-gather is enqueued behind it.
 // The main stream therefore carries no event at all in steady state; a poll that exceeds ~2 s raises the plan's error word
 // instead of hanging the GPU.

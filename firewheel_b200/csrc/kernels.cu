@@ -761,12 +761,13 @@ __global__ void __launch_bounds__(128) resampler_kernel(const __grid_constant__ 
 
 // K-combine: radix-16 levels of the same balanced tree over partial buses [n_in][rows][T] -> [ceil(n_in/16)][rows][T].
 template <int VEC>
-__global__ void __launch_bounds__(128) combine_kernel(const float* __restrict__ pin, float* __restrict__ pout, uint32_t n_in, uint32_t rows, uint32_t T, uint32_t out_pitch) {
+__global__ void __launch_bounds__(128) combine_kernel(const float* __restrict__ pin, float* __restrict__ pout, uint32_t n_in, uint32_t rows, uint32_t T, uint32_t out_pitch,
+                                                      uint32_t* done_word, uint32_t* done_counter, uint32_t done_epoch) {
     pdl_launch_dependents();
     pdl_wait();  // the partial buses come from the preceding kernel
     const uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
-    if (t >= T) return;
     const uint32_t row = blockIdx.y, g = blockIdx.z, p0 = g * 16u;
+    if (t < T) {
     float p[16][VEC];
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
@@ -782,6 +783,18 @@ __global__ void __launch_bounds__(128) combine_kernel(const float* __restrict__ 
         for (int j = 0; j + step < 16; j += 2 * step) FW_COMB1(j, j + step, p0 + j + step)
 #undef FW_COMB1
     VecT<VEC>::store(pout + ((size_t)g * rows + row) * out_pitch + t, p[0]);
+    }
+    // Multi-rank hand-over folded into the kernel that completes the rank-local bus (exchange.cu): the last CTA to finish publishes
+    // the exchange epoch in a device word the side stream polls — no extra kernel and no event on the main stream's PDL chain.
+    if (done_word != nullptr) {
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0 && atomicAdd(done_counter, 1u) == gridDim.x * gridDim.y * gridDim.z - 1u) {
+            *done_counter = 0u;
+            __threadfence();
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(done_word), "r"(done_epoch) : "memory");
+        }
+    }
 }
 
 // =============================================================================================
@@ -884,12 +897,13 @@ cudaError_t launch_chain(const ChainArgs& a, bool bus, cudaStream_t st) {
 }
 uint32_t chain_voice_groups(uint32_t num_voices) { return (num_voices + kVPC - 1) / kVPC; }
 
-cudaError_t launch_combine(const float* pin, float* pout, uint32_t n_in, uint32_t rows, uint32_t T, cudaStream_t st, uint32_t out_pitch) {
+cudaError_t launch_combine(const float* pin, float* pout, uint32_t n_in, uint32_t rows, uint32_t T, cudaStream_t st, uint32_t out_pitch,
+                           uint32_t* done_word, uint32_t* done_counter, uint32_t done_epoch) {
     if (out_pitch == 0) out_pitch = T;
     const bool vec4 = (T % 4 == 0) && (out_pitch % 4 == 0) && ((reinterpret_cast<uintptr_t>(pin) | reinterpret_cast<uintptr_t>(pout)) % 16 == 0);
     const uint32_t n_out = (n_in + 15) / 16;
-    if (vec4) return launch_pdl(combine_kernel<4>, dim3((T / 4 + 127) / 128, rows, n_out), dim3(128), st, pin, pout, n_in, rows, T, out_pitch);
-    return launch_pdl(combine_kernel<1>, dim3((T + 127) / 128, rows, n_out), dim3(128), st, pin, pout, n_in, rows, T, out_pitch);
+    if (vec4) return launch_pdl(combine_kernel<4>, dim3((T / 4 + 127) / 128, rows, n_out), dim3(128), st, pin, pout, n_in, rows, T, out_pitch, done_word, done_counter, done_epoch);
+    return launch_pdl(combine_kernel<1>, dim3((T + 127) / 128, rows, n_out), dim3(128), st, pin, pout, n_in, rows, T, out_pitch, done_word, done_counter, done_epoch);
 }
 cudaError_t launch_sum(const SumArgs& a, cudaStream_t st) {
     uintptr_t al = reinterpret_cast<uintptr_t>(a.out);

@@ -19,7 +19,8 @@ cudaError_t launch_resampler(const ResamplerArgs& a, uint64_t* pos, cudaStream_t
 cudaError_t launch_sampler(const SamplerArgs& a, cudaStream_t st);
 cudaError_t launch_silence_fix(const SilenceFixArgs& a, cudaStream_t st);
 cudaError_t launch_expand_masks(const Records& rec, uint32_t mask_slot, uint32_t V, uint32_t n_blocks, uint64_t* out, cudaStream_t st);
-cudaError_t launch_combine(const float* pin, float* pout, uint32_t n_in, uint32_t rows, uint32_t T, cudaStream_t st, uint32_t out_pitch = 0);
+cudaError_t launch_combine(const float* pin, float* pout, uint32_t n_in, uint32_t rows, uint32_t T, cudaStream_t st, uint32_t out_pitch = 0,
+                           uint32_t* done_word = nullptr, uint32_t* done_counter = nullptr, uint32_t done_epoch = 0);  // done_*: see combine_kernel
 cudaError_t launch_deinterleave(const float* inter, float* planar, uint32_t V, uint32_t C, uint32_t T, cudaStream_t st);
 cudaError_t launch_interleave(const float* planar, float* inter, const uint64_t* masks, uint32_t V, uint32_t C, uint32_t T,
                               uint32_t block_frames, cudaStream_t st);

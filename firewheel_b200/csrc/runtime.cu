@@ -1247,13 +1247,21 @@ static int run_bus_stage(fw_processor* p, Plan& pl, ChainArgs& xa, uint32_t n_ou
     else { xa.out = pl.d_part[0]; xa.bus_pitch = 0; }
     { ProfScope ps(p, 1); if (!FW_CUDA(launch_chain(xa, true, p->stream))) return FW_PROC_DEVICE_ERROR; }
     p->launches++;
+    // With several ranks and the exchange on the side stream, the kernel that completes the rank-local bus also publishes the exchange
+    // epoch (last CTA done -> device word): the main stream then has exactly the kernels of the single-GPU case.
+    const bool in_line = pl.heavy_stage;
+    const bool hand_over = p->world > 1 && !in_line;
+    const uint32_t e = p->world > 1 ? ++p->xepoch : 0u;
+    bool signalled = false;
     ProfScope ps2(p, 2);
     int cur = 0;
     while (n > 1) {
         const uint32_t n_next = (n + 15) / 16;
         float* cdst = n_next == 1 ? bus_dst : pl.d_part[cur ^ 1];
-        if (!FW_CUDA(launch_combine(pl.d_part[cur], cdst, n, n_out, T, p->stream, n_next == 1 ? bus_pitch : 0))) return FW_PROC_DEVICE_ERROR;
+        const bool sig = hand_over && n_next == 1;
+        if (!FW_CUDA(launch_combine(pl.d_part[cur], cdst, n, n_out, T, p->stream, n_next == 1 ? bus_pitch : 0, sig ? p->d_handover : nullptr, sig ? p->d_handover + 1 : nullptr, e))) return FW_PROC_DEVICE_ERROR;
         p->launches++;
+        signalled = signalled || sig;
         n = n_next; cur ^= 1;
     }
     if (p->world > 1) {
@@ -1264,13 +1272,11 @@ static int run_bus_stage(fw_processor* p, Plan& pl, ChainArgs& xa, uint32_t n_ou
         // A plan with a FIR-reverb stage keeps every SM occupied by the GEMM's persistent CTAs (197 KB of shared memory each): a
         // side-stream collective cannot become resident next to them and ends up serialised into the gaps, where it was measured to
         // cost more (config 5 at 8 GPUs: +0.3 ms per step) than its own ~25 us. Such plans run the exchange in line.
-        const bool in_line = pl.heavy_stage;
         cudaStream_t xs = in_line ? p->stream : p->side;
-        const uint32_t e = ++p->xepoch;
-        if (!in_line) {
-            if (!FW_CUDA(launch_bus_signal(p->d_handover, e, p->stream))) return FW_PROC_DEVICE_ERROR;
+        if (hand_over) {
+            if (!signalled) { if (!FW_CUDA(launch_bus_signal(p->d_handover, e, p->stream))) return FW_PROC_DEVICE_ERROR; p->launches++; }  // <= 64 voices: the chain kernel wrote the bus itself
             if (!FW_CUDA(launch_bus_wait(p->d_handover, e, xa.rec.error, (p->call_epoch << 4) | 2u, p->side))) return FW_PROC_DEVICE_ERROR;
-            p->launches += 2;
+            p->launches++;
         }
         if (!g_nccl.ok(g_nccl.AllGather(p->d_bus_local[q], p->d_gather[q], (size_t)n_out * T, /*ncclFloat32*/ 7, p->nccl_comm, xs), "ncclAllGather")) return FW_PROC_DEVICE_ERROR;
         p->launches++;
@@ -2026,7 +2032,7 @@ int fw_processor_comm_init(fw_processor* p, int rank, int world, const uint8_t* 
         p->d_bus_local[q] = dev_alloc<float>((size_t)p->n_out * p->max_call_frames, false); p->d_gather[q] = dev_alloc<float>((size_t)world * p->n_out * p->max_call_frames, false);
         if (!p->d_bus_local[q] || !p->d_gather[q]) return -1;
     }
-    p->d_handover = dev_alloc<uint32_t>(1);
+    p->d_handover = dev_alloc<uint32_t>(2);  // [0] epoch word, [1] last-CTA counter of the signalling combine
     return p->d_handover ? 0 : -1;
 }
 // Host-buffer all-gather over the processor's communicator: what a torch-free driver needs for barriers, max-over-ranks
