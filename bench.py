@@ -661,7 +661,7 @@ def run_b200(args, rank, world, local_rank):
             "warmup": max(args.warmup, 3), "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": head["scaling"], "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": head["config"], "clocks": head["clocks"], "e2e": head["e2e"],
             "gpu_launches": head["gpu_launches_per_pass"], "roofline": head["roofline"], "cpu_baseline": head["cpu_baseline"]}
-    for k in ("ms_per_step_p10", "ms_per_step_p90", "ms_per_step_by_rank", "passes", "timed_seconds", "parity", "exchange", "bus_parity", "bus_identical_on_all_ranks"):
+    for k in ("ms_per_step_p10", "ms_per_step_p90", "ms_per_step_by_rank", "passes", "timed_seconds", "parity", "exchange", "bus_parity", "bus_identical_on_all_ranks", "block_sized_calls"):
         if k in head:
             line[k] = head[k]
     if want_cpu and line["cpu_baseline"] is not None:

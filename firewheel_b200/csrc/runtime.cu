@@ -2,9 +2,9 @@
 //
 //   fw_ctx        main-thread side (FirewheelGraphCtx context.rs:29): graph edits, parameter stores,
 //                 compile + lowering + device allocation in update(), plan hand-off.
-//   fw_processor  stream side (FirewheelProcessor processor.rs:18): adopts plans from the ring, snapshots
-//                 parameters, enqueues the control + data kernels on its CUDA stream. It never allocates
-//                 graph state; only I/O staging grows to a high-water mark.
+//   fw_processor  stream side (FirewheelProcessor processor.rs:18): adopts plans from the ring, drains the command
+//                 ring, enqueues the control + data kernels on its CUDA stream. It never allocates: per-call
+//                 scratch belongs to the plan, I/O staging is sized at activate for max_call_frames.
 //   Plan          ScheduleHeapData analogue (schedule.rs:128-150): schedule + device tables + record buffers.
 //   NodeDeviceState  the device-resident "processor counterpart" of a node (Box<dyn AudioNodeProcessor>):
 //                 parameter mirrors and per-voice state; survives schedule swaps like processors do
@@ -233,7 +233,7 @@ struct NodeDeviceState {
         auto each_voice = [&](const Cmd& m, auto&& f) { if (m.voice == FW_ALL_VOICES) { for (uint32_t v = 0; v < V; ++v) f(v); } else if (m.voice < V) f(m.voice); };
         uint64_t total = 0;
         for (uint32_t i = 0; i < n; ++i) each_voice(*cmds[i], [&](uint32_t v) { h_cnt[v + 1]++; ++total; });
-        if (total > cap_msgs) { g_dev_err = "sampler message staging overflow"; return false; }
+        if (total > cap_msgs) { g_dev_err = "sampler message staging overflow"; publish_error(); return false; }
         h_off[0] = 0;
         for (uint32_t v = 0; v < V; ++v) h_off[v + 1] = h_off[v] + h_cnt[v + 1];
         for (uint32_t v = 0; v <= V; ++v) h_cnt[v] = h_off[v];  // running insert positions
@@ -823,12 +823,11 @@ int fw_schedule_node(fw_ctx* c, uint32_t i, fw_scheduled_node* out) {
 
 }  // extern "C"
 // ---- parameters -----------------------------------------------------------------------------
-// Two paths to the stream side, neither takes a lock (context.rs:61-64, "no mutexes" DESIGN_DOC.md:37):
-//   * event block 0 (default): the store lands in the node's host arrays and bumps `version` (release); the stream side
-//     re-uploads the arrays at the start of the next call — the reference's relaxed atomic store / per-block load
-//     (volume.rs:29-32,92) for a host that calls once per block;
-//   * event block b > 0 (fw_ctx_set_event_block): the store also travels as a command that takes effect at block b of the
-//     next call (the call is split there). The arrays are updated too, without a version bump, so later full uploads agree.
+// One path to the stream side, and it takes no lock (context.rs:61-64, "no mutexes" DESIGN_DOC.md:37): every store lands in the
+// node's host arrays (the main thread's view, which seeds the device state at activation) and, once the context is active, also
+// travels through the wait-free command ring in program order, stamped with the current event block (fw_ctx_set_event_block;
+// 0 = the start of the next call). The stream side applies it as an ordered device store at that block — the reference's relaxed
+// atomic store / per-block load (volume.rs:29-32,92). Whole-array setters travel as one CMD_UPLOAD with a snapshot of the array.
 static NodeParams* params_of(fw_ctx* c, fw_node_id node, uint32_t kind) {
     NodeRec* r = c->graph->node(Id::unpack(node));
     return (r && r->params->kind == kind) ? r->params.get() : nullptr;
