@@ -263,8 +263,15 @@ struct Plan {
     std::vector<Stage> stages;
     // generic lowering (arbitrary DAG of built-in nodes): one launch group per scheduled node over pool buffers [buffer][V][T]
     struct GNode { uint32_t kind = 0; std::vector<uint32_t> in_buf, out_buf; std::vector<uint8_t> in_clear; int sm0 = -1, sm1 = -1, mask_slot = -1, custom_idx = -1, sampler_idx = -1;
-                   float f0 = 0.0f; std::shared_ptr<NodeDeviceState> st; };
+                   float f0 = 0.0f; std::shared_ptr<NodeDeviceState> st;
+                   // fusion of pointwise runs and graph_in aliasing (see fuse_generic): a run of stereo Volume / Pan nodes, optionally ending in
+                   // graph_out, is ONE chain program launched at its last node; the others are `absorbed`. `run_in` = pool buffers the run
+                   // starts from (empty: in_buf), `pre_ops` = the ops of the absorbed nodes. `src_port` non-empty: the node (or its run) reads
+                   // the caller's input channels src_port[k] directly instead of graph_in's pool copy.
+                   bool absorbed = false; std::vector<ChainOp> pre_ops; std::vector<uint32_t> run_in, src_port; };
     bool generic = false; std::vector<GNode> gnodes; uint32_t num_buffers = 0;
+    bool gin_copy = true;  // false: every consumer of graph_in reads the caller's buffer itself, the pool copy is skipped
+    bool reads_caller_rows = false;  // some node reads the caller's input rows directly (row pitch n_in * frames must fit 32 bits)
     std::vector<std::shared_ptr<NodeDeviceState>> samplers;  // index = CtlTables::smp index
     std::vector<std::shared_ptr<NodeDeviceState>> resamplers;  // index = CtlTables::rs index
     bool bus = false; uint32_t n_sm = 0, c_in = 0, c_out = 0, num_voices = 0, block_frames = 0;
@@ -561,7 +568,68 @@ static bool lower(fw_ctx* c, const Schedule& s, Plan* plan, std::string* why) {
         }
         return true;
     };
-    if (!chain_lower()) { if (!generic_lower()) return false; }
+    // Generic lowering, second step ("fuse runs of pointwise nodes between fan-out points"):
+    //  * a run of mask-independent pointwise nodes (stereo Volume, Pan) that are adjacent in the schedule and feed each other port to
+    //    port with no other consumer becomes one chain program, launched where its last node stands; graph_out (copy to the caller's
+    //    rows, or the bus stage) can be that last node. Adjacency makes the fused launch read and write its pool buffers at the same
+    //    point of the schedule as the unfused nodes did, so the compiler's buffer reuse (compiler.rs:302-412) stays valid; a run whose
+    //    last outputs reuse the buffers of its first inputs is not fused (no in-place launches).
+    //  * a run head or a Biquad / SVF / Delay node fed entirely by graph_in reads the caller's input rows itself (pointer + pitch),
+    //    first-block zeroing after a schedule swap (Q11) included; if every consumer of graph_in does, the pool copy of the inputs is skipped.
+    auto fuse_generic = [&]() {
+        auto& gn = plan->gnodes;
+        std::unordered_map<uint64_t, size_t> index_of;
+        for (size_t i = 0; i < n; ++i) index_of[s.nodes[i].id.pack()] = i;
+        std::vector<std::vector<uint32_t>> n_cons(n);
+        for (size_t i = 0; i < n; ++i) n_cons[i].assign(s.nodes[i].out.size(), 0u);
+        for (size_t i = 0; i < n; ++i) for (const InAssign& a : s.nodes[i].in) {
+            if (a.should_clear) continue;
+            auto it = index_of.find(a.producer.pack());
+            if (it != index_of.end() && a.producer_port < n_cons[it->second].size()) n_cons[it->second][a.producer_port]++;
+        }
+        auto connected = [&](size_t i) { for (const InAssign& a : s.nodes[i].in) if (a.should_clear) return false; return true; };
+        auto stereo_pointwise = [&](size_t i) {
+            return i > 0 && i + 1 < n && (gn[i].kind == FW_NODE_PAN || gn[i].kind == FW_NODE_VOLUME) && s.nodes[i].in.size() == 2 && s.nodes[i].out.size() == 2 &&
+                   gn[i].mask_slot < 0 && connected(i);
+        };
+        auto fed_only_by = [&](size_t i, size_t j) {  // node i's inputs are node j's outputs, port to port, and nothing else reads them
+            if (s.nodes[i].in.size() != s.nodes[j].out.size()) return false;
+            for (size_t p = 0; p < s.nodes[i].in.size(); ++p) {
+                const InAssign& a = s.nodes[i].in[p];
+                if (a.should_clear || a.producer != s.nodes[j].id || a.producer_port != p || n_cons[j][p] != 1) return false;
+            }
+            return true;
+        };
+        auto op_of = [&](size_t i) { ChainOp op{}; op.sm1 = -1; op.kind = gn[i].kind == FW_NODE_PAN ? OP_PAN : OP_GAIN; op.sm0 = gn[i].sm0; if (gn[i].kind == FW_NODE_PAN) op.sm1 = gn[i].sm1; return op; };
+        // graph_in aliasing: which nodes can read the caller's rows, and is the pool copy still needed
+        std::vector<uint32_t> alias_cons(s.nodes[0].out.size(), 0u);
+        for (size_t i = 1; i + 1 < n; ++i) {
+            const bool temporal = gn[i].kind == FW_NODE_BIQUAD || gn[i].kind == FW_NODE_SVF || gn[i].kind == FW_NODE_DELAY;
+            if (!(stereo_pointwise(i) || (temporal && connected(i) && !s.nodes[i].in.empty()))) continue;
+            bool all = true;
+            for (const InAssign& a : s.nodes[i].in) if (a.producer != s.nodes[0].id || a.producer_port >= alias_cons.size()) all = false;
+            if (!all) continue;
+            for (const InAssign& a : s.nodes[i].in) { gn[i].src_port.push_back(a.producer_port); alias_cons[a.producer_port]++; }
+            plan->reads_caller_rows = true;
+        }
+        plan->gin_copy = false;
+        for (size_t p = 0; p < alias_cons.size(); ++p) if (n_cons[0][p] > alias_cons[p]) plan->gin_copy = true;
+        // runs
+        for (size_t i = 2; i < n; ++i) {
+            const size_t j = i - 1;
+            const bool tail = i + 1 == n && s.nodes[i].in.size() == 2 && !(c->cfg.master_bus && gout.in.size() > 2);
+            if (!(stereo_pointwise(i) || tail) || !stereo_pointwise(j) || !fed_only_by(i, j)) continue;
+            if (gn[j].pre_ops.size() + 2 > (size_t)kMaxChainOps) continue;
+            const std::vector<uint32_t>& head_in = gn[j].run_in.empty() ? gn[j].in_buf : gn[j].run_in;
+            bool in_place = false;
+            if (gn[j].src_port.empty()) for (uint32_t ob : gn[i].out_buf) for (uint32_t ib : head_in) if (ob == ib) in_place = true;
+            if (in_place) continue;
+            gn[i].pre_ops = gn[j].pre_ops; gn[i].pre_ops.push_back(op_of(j));
+            gn[i].run_in = head_in; gn[i].src_port = gn[j].src_port;
+            gn[j].absorbed = true;
+        }
+    };
+    if (!chain_lower()) { if (!generic_lower()) return false; fuse_generic(); }
     plan->n_sm = n_sm;
 
     // ---- device allocations (main thread) ----
@@ -1293,6 +1361,7 @@ static int enqueue_generic(fw_processor* p, Plan& pl, const float* d_in, float* 
     const uint32_t V = p->num_voices, n_in = pl.c_in, n_out = pl.c_out, T = ck.Tc;
     const size_t BS = (size_t)V * T;  // floats per pool buffer
     auto buf = [&](uint32_t b) { return pl.d_pool + (size_t)b * BS; };
+    if (pl.reads_caller_rows && (uint64_t)n_in * ck.Tfull > 0xffffffffull) { g_dev_err = "input rows of more than 2^32 / channels frames"; return FW_PROC_BAD_ARGS; }
     // one pointwise launch: up to 2 channels, arbitrary channel pointers
     auto pointwise = [&](const ChainProgram& prog, const float* i0, const float* i1, uint64_t ivs, float* o0, float* o1, uint64_t ovs, bool first) -> bool {
         ChainArgs xa{};
@@ -1329,13 +1398,27 @@ static int enqueue_generic(fw_processor* p, Plan& pl, const float* d_in, float* 
         p->launches++;
         return true;
     };
+    // a (fused) stereo program: the run's ops + `own` (kind < 0: none), from the run's first inputs — pool buffers, or the caller's input
+    // channels when the run head is fed by graph_in — to o0 / o1
+    auto stereo_run = [&](const Plan::GNode& gn, int own_kind, float* o0, float* o1, uint64_t ovs) -> bool {
+        ChainProgram pr{}; pr.c_in = 2; pr.c_out = 2;
+        for (const ChainOp& op : gn.pre_ops) pr.ops[pr.n_ops++] = op;
+        if (own_kind >= 0) { ChainOp& op = pr.ops[pr.n_ops++]; op = ChainOp{}; op.kind = (uint32_t)own_kind; op.sm0 = gn.sm0; op.sm1 = own_kind == OP_PAN ? gn.sm1 : -1; op.f0 = gn.f0; }
+        if (!gn.src_port.empty()) {
+            const float* base = d_in + ck.t0;
+            return pointwise(pr, base + (size_t)gn.src_port[0] * ck.Tfull, base + (size_t)gn.src_port[1] * ck.Tfull, (uint64_t)n_in * ck.Tfull, o0, o1, ovs, true);
+        }
+        const std::vector<uint32_t>& ib = gn.run_in.empty() ? gn.in_buf : gn.run_in;
+        return pointwise(pr, buf(ib[0]), buf(ib[1]), T, o0, o1, ovs, false);
+    };
     const size_t N = pl.gnodes.size();
     for (size_t i = 0; i < N; ++i) {
         Plan::GNode& gn = pl.gnodes[i];
+        if (gn.absorbed) continue;  // runs inside the program of the node that ends its run
         for (size_t k = 0; k < gn.in_buf.size(); ++k)  // unconnected inputs are cleared every block (schedule.rs:310-313)
             if (gn.in_clear[k]) { if (!FW_CUDA(launch_fill(buf(gn.in_buf[k]), BS, 0.0f, p->stream))) return FW_PROC_DEVICE_ERROR; p->launches++; }
         if (i == 0) {  // graph_in: stream channels -> pool (prepare_graph_inputs, schedule.rs:213-253)
-            for (size_t c = 0; c < gn.out_buf.size(); c += 2) {
+            for (size_t c = 0; pl.gin_copy && c < gn.out_buf.size(); c += 2) {
                 const bool two = c + 1 < gn.out_buf.size();
                 const float* s0 = d_in + c * (size_t)ck.Tfull + ck.t0;
                 if (!pointwise(prog1(-1, two ? 2 : 1, two ? 2 : 1, -1, -1, 0.f), s0, two ? s0 + ck.Tfull : nullptr, (uint64_t)n_in * ck.Tfull,
@@ -1348,8 +1431,20 @@ static int enqueue_generic(fw_processor* p, Plan& pl, const float* d_in, float* 
                 ChainArgs xa{};
                 xa.in_ch[0] = buf(gn.in_buf[0]); xa.in_ch[1] = buf(gn.in_buf[n_out > 1 ? 1 : 0]); xa.in_vstride = T;
                 xa.num_voices = V; xa.frames = T; xa.block_frames = pl.block_frames; xa.rec = pl.rec; xa.prog = prog1(-1, n_out, n_out, -1, -1, 0.f); xa.in_from_prev_kernel = 1;
+                if (!gn.pre_ops.empty()) {  // the pointwise run that ends here rides in the bus stage's program
+                    xa.prog = ChainProgram{}; xa.prog.c_in = 2; xa.prog.c_out = 2;
+                    for (const ChainOp& op : gn.pre_ops) xa.prog.ops[xa.prog.n_ops++] = op;
+                    if (!gn.src_port.empty()) {
+                        const float* base = d_in + ck.t0;
+                        xa.in_ch[0] = base + (size_t)gn.src_port[0] * ck.Tfull; xa.in_ch[1] = base + (size_t)gn.src_port[1] * ck.Tfull; xa.in_vstride = (uint64_t)n_in * ck.Tfull;
+                        xa.in_from_prev_kernel = 0; xa.zero_first_block = ck.zero_first ? 1u : 0u;
+                    } else { xa.in_ch[0] = buf(gn.run_in[0]); xa.in_ch[1] = buf(gn.run_in[1]); }
+                }
                 const int brc = run_bus_stage(p, pl, xa, n_out, ck, d_out + ck.t0);
                 if (brc != FW_PROC_OK) return brc;
+            } else if (!gn.pre_ops.empty()) {
+                float* o0 = d_out + ck.t0;
+                if (!stereo_run(gn, -1, o0, o0 + ck.Tfull, (uint64_t)n_out * ck.Tfull)) return FW_PROC_DEVICE_ERROR;
             } else {
                 for (size_t c = 0; c < gn.in_buf.size(); c += 2) {
                     const bool two = c + 1 < gn.in_buf.size();
@@ -1374,11 +1469,15 @@ static int enqueue_generic(fw_processor* p, Plan& pl, const float* d_in, float* 
                 break;
             }
             case FW_NODE_VOLUME: case FW_NODE_HARD_CLIP:
+                if (gn.kind == FW_NODE_VOLUME && (!gn.pre_ops.empty() || !gn.src_port.empty())) {  // stereo Volume ending a fused run / reading the caller's rows
+                    if (!stereo_run(gn, OP_GAIN, buf(gn.out_buf[0]), buf(gn.out_buf[1]), T)) return FW_PROC_DEVICE_ERROR;
+                    break;
+                }
                 if (!per_channel(gn, gn.kind == FW_NODE_VOLUME ? OP_GAIN : OP_CLIP)) return FW_PROC_DEVICE_ERROR;
                 for (size_t c = 0; gn.mask_slot >= 0 && c < gn.out_buf.size(); ++c) if (!silence_fix(gn, c, 1ull << c)) return FW_PROC_DEVICE_ERROR;
                 break;
             case FW_NODE_PAN:
-                if (!pointwise(prog1(OP_PAN, 2, 2, gn.sm0, gn.sm1, 0.f), buf(gn.in_buf[0]), buf(gn.in_buf[1]), T, buf(gn.out_buf[0]), buf(gn.out_buf[1]), T, false)) return FW_PROC_DEVICE_ERROR;
+                if (!stereo_run(gn, OP_PAN, buf(gn.out_buf[0]), buf(gn.out_buf[1]), T)) return FW_PROC_DEVICE_ERROR;
                 break;
             case FW_NODE_MONO_TO_STEREO:
                 if (!pointwise(prog1(OP_M2S, 1, 2, -1, -1, 0.f), buf(gn.in_buf[0]), nullptr, T, buf(gn.out_buf[0]), buf(gn.out_buf[1]), T, false)) return FW_PROC_DEVICE_ERROR;
@@ -1424,6 +1523,11 @@ static int enqueue_generic(fw_processor* p, Plan& pl, const float* d_in, float* 
                     TemporalArgs ta{};
                     ta.in = buf(gn.in_buf[c]); ta.out = buf(gn.out_buf[c]); ta.R = two ? 2 * V : V; ta.C = 1; ta.T = T; ta.srow_mul = nc; ta.srow_add = c;
                     if (two) { ta.in2 = buf(gn.in_buf[c + 1]); ta.out2 = buf(gn.out_buf[c + 1]); ta.seg_rows = V; }
+                    if (!gn.src_port.empty()) {  // fed by graph_in: rows of the caller's buffer, one voice apart
+                        const float* base = d_in + ck.t0;
+                        ta.in = base + (size_t)gn.src_port[c] * ck.Tfull; if (two) ta.in2 = base + (size_t)gn.src_port[c + 1] * ck.Tfull;
+                        ta.in_pitch = n_in * ck.Tfull; ta.zero_first = ck.zero_first;
+                    }
                     if (gn.kind == FW_NODE_SVF) { ta.svf = 1; ta.ns = st.params->num_stages; ta.coeffs = st.d_coeffs; ta.state = st.d_state; }
                     else if (gn.kind == FW_NODE_BIQUAD) { ta.ns = st.params->num_stages; ta.coeffs = st.d_coeffs; ta.state = st.d_state; }
                     else if (D) { ta.D = D; ta.ring = st.d_ring; ta.pos = st.ring_pos; }

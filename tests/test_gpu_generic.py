@@ -175,6 +175,65 @@ def test_reverb_send_bus(gpu, oracle):
     compare(gpu, oracle, build, [(x, None), (x, None), (x[:, :, :100].copy(), None), (x, None)], 2, True, tol=1e-5)
 
 
+@pytest.mark.parametrize("bus,F,mcf", [(False, 128, 0), (True, 128, 256), (False, 100, 300), (True, 64, 0)])
+def test_fused_runs_and_caller_row_reads(gpu, oracle, bus, F, mcf):
+    """The second step of the generic lowering (runtime.cu fuse_generic): a run gain -> pan -> gain fed by graph_in's channels (2, 0) is one
+    launch reading the caller's rows; an SVF and a delay fed by graph_in read them too (the pool copy of the inputs disappears); the run
+    gain -> pan behind the SumNode rides in graph_out's launch (strided copy, or the bus stage). Odd call lengths, chunked calls
+    (max_call_frames), ramps through the fused programs, and a schedule swap in between (Q11: the first block after it reads zero inputs,
+    which every reader of the caller's rows has to do itself now)."""
+    from firewheel_b200 import SvfNode, design_svf
+    V = 37
+    rng = np.random.default_rng(11)
+    kf = np.stack([[design_svf(gpu, 0, 900.0 + 40 * v, 0.9, SR)] for v in range(V)]).astype(f32)
+    pct = (30 + 90 * rng.random(V)).astype(f32)
+
+    def build(lib):
+        cx = FirewheelGraphCtx(lib, AudioGraphConfig(num_graph_inputs=3, num_graph_outputs=2, num_voices=V, master_bus=bus, max_call_frames=mcf))
+        g = cx.graph
+        gin, gout = g.graph_in_node(), g.graph_out_node()
+        a1, a2, a3 = g.add_node(2, 2, VolumeNode(80.0)), g.add_node(2, 2, PanNode(-0.3)), g.add_node(2, 2, VolumeNode(120.0))
+        svf, dl = g.add_node(2, 2, SvfNode(1)), g.add_node(1, 1, DelayNode(160))
+        mix = g.add_node(5, 1, SumNode())
+        up = g.add_node(1, 2, MonoToStereoNode())
+        b1, b2 = g.add_node(2, 2, VolumeNode(70.0)), g.add_node(2, 2, PanNode(0.4))
+        for c, port in enumerate((2, 0)):
+            g.connect(gin, port, a1, c, False)
+        for c, port in enumerate((1, 2)):
+            g.connect(gin, port, svf, c, False)
+        g.connect(gin, 1, dl, 0, False)
+        for c in range(2):
+            g.connect(a1, c, a2, c, False); g.connect(a2, c, a3, c, False)
+            g.connect(a3, c, mix, c, False); g.connect(svf, c, mix, 2 + c, False)
+            g.connect(b1, c, b2, c, False); g.connect(b2, c, gout, c, False)
+        g.connect(dl, 0, mix, 4, False)
+        g.connect(mix, 0, up, 0, False)
+        for c in range(2):
+            g.connect(up, c, b1, c, False)
+        g.set_svf_coeffs(svf, kf)
+        g.set_percent_volume(a1, pct)
+        proc = activate(cx, 3, 2, F)
+        state = {}
+
+        def retune(arg):
+            if arg == "swap":  # splice a HardClipNode in front of the mix's mono output and take it out again two calls later
+                state["clip"] = g.add_node(1, 1, HardClipNode(-6.0))
+                assert g.disconnect(mix, 0, up, 0)
+                g.connect(mix, 0, state["clip"], 0, False); g.connect(state["clip"], 0, up, 0, False)
+                assert cx.update().graph_error is None
+            elif arg == "unswap":
+                g.remove_node(state.pop("clip")); g.connect(mix, 0, up, 0, False)
+                assert cx.update().graph_error is None
+            else:
+                g.set_percent_volume(a3, float(arg)); g.set_pan(b2, float(arg) / 100.0 - 0.5); g.set_percent_volume(b1, 100.0 - float(arg) / 2)
+        return cx, proc, retune
+    T = 5 * F + 17
+    x = synth((V, 3, T), 21)
+    x[:, :, T // 3: T // 3 + 5] = -0.0
+    compare(gpu, oracle, build, [(x, None), (x, 40.0), (x, "swap"), (x[:, :, : 2 * F + 3].copy(), 90.0), (x, "unswap"), (x, None)], 2, bus)
+
+
+
 # ---- random DAGs -----------------------------------------------------------------------------------------------
 KINDS = ["vol1", "vol2", "vol3", "pan", "clip1", "clip2", "clip3", "m2s", "s2m", "sum2x1", "sum2x2", "sum3x1", "sum4x1", "sum6x1", "sum5x2", "sum1x2",
          "biquad1", "biquad2", "delay1", "delay2"]
