@@ -8,6 +8,7 @@ import ctypes as C
 
 FW_ID_DANGLING = 0xFFFFFFFFFFFFFFFF
 FW_ALL_VOICES = 0xFFFFFFFF
+FW_PARAM_PERCENT_VOLUME, FW_PARAM_RAW_GAIN, FW_PARAM_PAN, FW_PARAM_GAIN_L, FW_PARAM_GAIN_R, FW_PARAM_COEFFS = range(6)
 FW_MAX_PORTS = 64
 
 # fw_node_kind
@@ -65,6 +66,11 @@ class ScheduledNodeC(C.Structure):
                 ("out_buffer", C.c_uint32 * FW_MAX_PORTS)]
 
 
+class VoiceTemplateC(C.Structure):
+    _fields_ = [("num_voices", C.c_uint32), ("num_template_nodes", C.c_uint32), ("voice_inputs", C.c_uint32), ("voice_outputs", C.c_uint32),
+                ("num_tree_nodes", C.c_uint32)]
+
+
 _vp, _u32, _u64, _i32, _f32, _f64 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int, C.c_float, C.c_double
 _pf = C.c_void_p  # float* passed as raw addresses (numpy .ctypes.data or device pointers)
 _pu64 = C.POINTER(C.c_uint64)
@@ -99,6 +105,10 @@ SIGNATURES = {
     "schedule_len": (_u32, [_vp]),
     "schedule_num_buffers": (_u32, [_vp]),
     "schedule_node": (_i32, [_vp, _u32, C.POINTER(ScheduledNodeC)]),
+    "graph_detect_voices": (_i32, [_vp, C.POINTER(VoiceTemplateC)]),
+    "graph_voice_nodes": (_u32, [_vp, _u32, C.POINTER(C.c_uint64), _u32]),
+    "ctx_new_batched": (_vp, [_vp, _i32, _u32, C.POINTER(C.c_uint64), _u32]),
+    "node_read_params": (_u32, [_vp, C.c_uint64, _u32, _vp, _u32]),
     "ctx_set_event_block": (None, [_vp, _u32]),
     "volume_set_percent_volume": (_i32, [_vp, _u64, _u32, _f32]),
     "volume_set_percent_volumes": (_i32, [_vp, _u64, _pf, _u32]),

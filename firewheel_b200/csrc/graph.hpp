@@ -202,4 +202,23 @@ class Graph {
     uint32_t num_voices_;
 };
 
+// ---- isomorphic-voice detection (voices.cpp) --------------------------------------------------------------------
+// The reference runs ONE graph; a mixer of V identical voices is V copies of a sub-graph feeding a tree of SumNodes in front of
+// graph_out. This recognises that shape in a flat graph, so that it can be run as `num_voices = V` instances of one voice graph with
+// a master bus — bit-identical, because the bus IS that tree (DESIGN.md "Batching extension"): level l adds neighbours (2i, 2i+1)
+// with a 2-port SumNode (2C inputs -> C outputs, sum.rs:69-81), an unpaired last element goes through a 1-port SumNode
+// (C -> C, the copy path sum.rs:58-65).
+struct VoiceDetection {
+    uint32_t num_voices = 0, voice_inputs = 0, voice_outputs = 0;
+    std::vector<std::vector<Id>> nodes;      // [template node, canonical order][voice]
+    struct Src { int node = -1; uint32_t port = 0; };  // node >= 0: template node; -1: unconnected; -2: graph_in, port = channel of the voice
+    std::vector<std::vector<Src>> inputs;    // [template node][input port]
+    std::vector<Src> outputs;                // [voice output channel]: what feeds the bus
+    std::vector<Id> tree;                    // the SumNodes of the bus tree (they disappear into master_bus = 1)
+};
+// The deepest reading of the SumNode tree in front of graph_out whose leaves are disjoint isomorphic voices wins; a graph that is
+// simply one voice answers true with num_voices == 1 (then *why says why a deeper reading was rejected, if there was a tree).
+// false + *why: not even that (e.g. side branches that never reach graph_out).
+bool detect_voices(Graph& g, VoiceDetection* out, std::string* why);
+
 }  // namespace fw

@@ -351,6 +351,7 @@ struct fw_ctx {
     // ActiveState (context.rs:17-27)
     bool active = false; std::shared_ptr<Channels> ch; uint32_t sample_rate = 0, max_block_frames = 0, n_in = 0, n_out = 0;
     uint32_t max_call_frames = 0;     // longest stretch processed in one go; longer calls are chunked (fw_graph_config::max_call_frames)
+    std::unique_ptr<VoiceDetection> voices;  // result of the last successful fw_graph_detect_voices
 };
 
 struct fw_processor {
@@ -887,6 +888,91 @@ int fw_schedule_node(fw_ctx* c, uint32_t i, fw_scheduled_node* out) {
     for (size_t k = 0; k < sn.in.size() && k < 64; ++k) { out->in_buffer[k] = sn.in[k].buffer; out->in_should_clear[k] = sn.in[k].should_clear; }
     for (size_t k = 0; k < sn.out.size() && k < 64; ++k) out->out_buffer[k] = sn.out[k].buffer;
     return 1;
+}
+
+// ---- isomorphic-voice detection (voices.cpp) ---------------------------------------------------------------------
+int fw_graph_detect_voices(fw_ctx* c, fw_voice_template* out) {
+    if (!c) return -1;
+    auto det = std::make_unique<VoiceDetection>();
+    std::string why;
+    c->voices.reset();
+    if (out) std::memset(out, 0, sizeof(*out));
+    if (c->cfg.num_voices != 1) { c->last_error = "detect_voices works on a flat graph (num_voices == 1)"; return -1; }
+    if (!detect_voices(*c->graph, det.get(), &why)) { c->last_error = "not a batch of isomorphic voices: " + why; return -1; }
+    if (out) { out->num_voices = det->num_voices; out->num_template_nodes = (uint32_t)det->nodes.size(); out->voice_inputs = det->voice_inputs;
+               out->voice_outputs = det->voice_outputs; out->num_tree_nodes = (uint32_t)det->tree.size(); }
+    c->last_error = why.empty() ? std::string() : "fewer voices than the SumNode tree has leaves: " + why;
+    c->voices = std::move(det);
+    return 0;
+}
+uint32_t fw_graph_voice_nodes(fw_ctx* c, uint32_t template_node, fw_node_id* out, uint32_t cap) {
+    if (!c || !c->voices || template_node >= c->voices->nodes.size()) return 0;
+    const std::vector<Id>& v = c->voices->nodes[template_node];
+    for (size_t i = 0; i < v.size() && i < cap && out; ++i) out[i] = v[i].pack();
+    return (uint32_t)v.size();
+}
+// The batched context of a detected flat graph: one voice graph (the template, canonical order), num_voices = V, the per-voice
+// parameter tables filled from the V copies, master_bus = 1 in place of the SumNode tree.
+fw_ctx* fw_ctx_new_batched(fw_ctx* flat, int32_t device, uint32_t max_call_frames, fw_node_id* template_ids, uint32_t cap) {
+    if (!flat) return nullptr;
+    if (!flat->voices) { flat->last_error = "ctx_new_batched: call graph_detect_voices first"; return nullptr; }
+    const VoiceDetection& d = *flat->voices;
+    const uint32_t V = d.num_voices;
+    for (const auto& ids : d.nodes) for (Id id : ids) if (!flat->graph->node(id)) { flat->last_error = "ctx_new_batched: the graph changed since detect_voices"; return nullptr; }
+    fw_graph_config cfg = flat->cfg;
+    cfg.num_graph_inputs = d.voice_inputs; cfg.num_graph_outputs = d.voice_outputs; cfg.num_voices = V; cfg.master_bus = V > 1 ? 1u : flat->cfg.master_bus;
+    cfg.device = device; cfg.max_call_frames = max_call_frames;
+    fw_ctx* b = fw_ctx_new(&cfg);
+    if (!b) return nullptr;
+    if (flat->res) b->res = flat->res;  // sample resources are shared: handles stay valid
+    std::vector<Id> ids(d.nodes.size());
+    for (size_t i = 0; i < d.nodes.size(); ++i) {
+        const NodeRec& r0 = *flat->graph->node(d.nodes[i][0]);
+        auto p = std::make_shared<NodeParams>(*r0.params);  // static parameters (stages, delay, IR, tables, threshold) from voice 0
+        p->num_voices = V;
+        auto gather = [&](std::vector<float> NodeParams::*field, size_t per_voice) {
+            if (((*r0.params).*field).empty()) return;
+            std::vector<float>& dst = (*p).*field;
+            dst.assign((size_t)V * per_voice, 0.0f);
+            for (uint32_t v = 0; v < V; ++v) {
+                const std::vector<float>& src = (*flat->graph->node(d.nodes[i][v])->params).*field;
+                std::copy_n(src.begin(), std::min(per_voice, src.size()), dst.begin() + (size_t)v * per_voice);
+            }
+        };
+        gather(&NodeParams::percent, 1); gather(&NodeParams::raw_gain, 1); gather(&NodeParams::pan, 1); gather(&NodeParams::gain_l, 1); gather(&NodeParams::gain_r, 1);
+        gather(&NodeParams::coeffs, (size_t)p->num_stages * 5); gather(&NodeParams::svf_coeffs, (size_t)p->num_stages * 6);
+        if (p->kind == FW_NODE_SAMPLER) { p->smp_active = false; p->smp_playing.assign(V, 0); p->smp_pending.assign(V, 0); p->smp_pending_epoch.assign(V, 0); }
+        ids[i] = b->graph->add_node(r0.num_inputs, r0.num_outputs, std::move(p));
+        if (template_ids && i < cap) template_ids[i] = ids[i].pack();
+    }
+    auto wire = [&](const VoiceDetection::Src& s, Id dst, uint32_t dp) {
+        if (s.node == -1) return true;
+        const Id src = s.node == -2 ? b->graph->graph_in() : ids[(size_t)s.node];
+        Id e; return b->graph->connect(src, s.port, dst, dp, false, &e) == FW_EDGE_OK;
+    };
+    bool ok = true;
+    for (size_t i = 0; i < d.inputs.size(); ++i) for (size_t port = 0; port < d.inputs[i].size(); ++port) ok = ok && wire(d.inputs[i][port], ids[i], (uint32_t)port);
+    for (size_t ch = 0; ch < d.outputs.size(); ++ch) ok = ok && wire(d.outputs[ch], b->graph->graph_out(), (uint32_t)ch);
+    if (!ok) { flat->last_error = "ctx_new_batched: internal: could not rebuild the voice graph"; fw_ctx_free(b); return nullptr; }
+    return b;
+}
+// main-thread view of a node's parameter tables (volume.rs:24,36 / sampler.rs:167,179 are the reference's per-node getters)
+uint32_t fw_node_read_params(fw_ctx* c, fw_node_id node, uint32_t which, float* out, uint32_t cap) {
+    NodeRec* r = c ? c->graph->node(Id::unpack(node)) : nullptr;
+    if (!r) return 0;
+    const NodeParams& p = *r->params;
+    const std::vector<float>* src = nullptr;
+    switch (which) {
+        case FW_PARAM_PERCENT_VOLUME: src = &p.percent; break;
+        case FW_PARAM_RAW_GAIN: src = &p.raw_gain; break;
+        case FW_PARAM_PAN: src = &p.pan; break;
+        case FW_PARAM_GAIN_L: src = &p.gain_l; break;
+        case FW_PARAM_GAIN_R: src = &p.gain_r; break;
+        case FW_PARAM_COEFFS: src = p.kind == FW_NODE_SVF ? &p.svf_coeffs : &p.coeffs; break;
+        default: return 0;
+    }
+    for (size_t i = 0; i < src->size() && i < cap && out; ++i) out[i] = (*src)[i];
+    return (uint32_t)src->size();
 }
 
 }  // extern "C"

@@ -160,6 +160,15 @@ class ScheduledNode:  # schedule.rs:13-30
 
 
 @dataclass
+class VoiceTemplate:  # include/fw_b200.h fw_voice_template
+    num_voices: int
+    num_template_nodes: int
+    voice_inputs: int
+    voice_outputs: int
+    num_tree_nodes: int
+
+
+@dataclass
 class UpdateStatus:  # context.rs:245-254
     kind: str
     graph_error: CompileGraphError = None
@@ -278,6 +287,30 @@ class AudioGraph:
                                      [(sn.in_buffer[k], bool(sn.in_should_clear[k])) for k in range(sn.num_inputs)],
                                      [sn.out_buffer[k] for k in range(sn.num_outputs)]))
         return out, self._lib.schedule_num_buffers(self._ctx)
+
+    # ---- isomorphic-voice detection (ours; include/fw_b200.h graph_detect_voices) ------------------
+    def detect_voices(self):
+        """Recognise V isomorphic voices under a balanced SumNode tree in this flat graph; returns VoiceTemplate or raises ValueError with
+        the reason. The batched equivalent is FirewheelGraphCtx.new_batched(flat_ctx)."""
+        t = K.VoiceTemplateC()
+        if self._lib.graph_detect_voices(self._ctx, C.byref(t)) != 0:
+            raise ValueError(self._lib.ctx_last_error(self._ctx).decode())
+        return VoiceTemplate(t.num_voices, t.num_template_nodes, t.voice_inputs, t.voice_outputs, t.num_tree_nodes)
+
+    def voice_nodes(self, template_node):
+        """ids, in this flat graph, of template node `template_node` in voice 0 .. V-1 (after detect_voices)"""
+        n = self._lib.graph_voice_nodes(self._ctx, template_node, None, 0)
+        buf = (C.c_uint64 * max(n, 1))()
+        self._lib.graph_voice_nodes(self._ctx, template_node, buf, n)
+        return [NodeID(buf[i]) for i in range(n)]
+
+    def read_params(self, node_id, which):
+        """main-thread view of a node's parameter table (K.FW_PARAM_*), as float32 array; empty if the node has no such table"""
+        n = self._lib.node_read_params(self._ctx, node_id, which, None, 0)
+        out = np.zeros(n, dtype=np.float32)
+        if n:
+            self._lib.node_read_params(self._ctx, node_id, which, out.ctypes.data, n)
+        return out
 
     # ---- parameters -------------------------------------------------------------------------
     def set_event_block(self, block):
@@ -524,6 +557,22 @@ class FirewheelGraphCtx:
         if not self._ctx:
             raise RuntimeError("ctx_new failed: " + (lib.last_device_error() or b"").decode())
         self.graph = AudioGraph(lib, self._ctx)
+
+    @classmethod
+    def new_batched(cls, flat, device=0, max_call_frames=0):
+        """The batched context of a flat context whose graph passed detect_voices(): the voice graph once, num_voices = V, master bus in
+        place of the SumNode tree. Returns (ctx, template node ids in the new graph)."""
+        t = flat.graph.detect_voices()
+        ids = (C.c_uint64 * max(t.num_template_nodes, 1))()
+        h = flat._lib.ctx_new_batched(flat._ctx, device, max_call_frames, ids, t.num_template_nodes)
+        if not h:
+            raise ValueError(flat.last_error())
+        self = cls.__new__(cls)
+        self._lib, self._ctx = flat._lib, h
+        self.config = AudioGraphConfig(num_graph_inputs=t.voice_inputs, num_graph_outputs=t.voice_outputs, num_voices=t.num_voices,
+                                       master_bus=t.num_voices > 1 or flat.config.master_bus, device=device, max_call_frames=max_call_frames)
+        self.graph = AudioGraph(flat._lib, h)
+        return self, [NodeID(ids[i]) for i in range(t.num_template_nodes)]
 
     def activate(self, sample_rate, num_stream_in_channels, num_stream_out_channels, max_block_frames, user_cx=None):
         h = C.c_void_p(None)

@@ -278,6 +278,33 @@ FW_EXPORT uint32_t FW_FN(schedule_len)(fw_ctx* ctx);                            
 FW_EXPORT uint32_t FW_FN(schedule_num_buffers)(fw_ctx* ctx);                        /* schedule.rs:171 */
 FW_EXPORT int FW_FN(schedule_node)(fw_ctx* ctx, uint32_t i, fw_scheduled_node* out);
 
+/* ---- isomorphic-voice detection (ours) ------------------------------------------------------------------------
+ * The reference runs ONE graph; a mixer of V identical voices is V copies of a sub-graph that meet in a tree of SumNodes in front of
+ * graph_out (the 64-port limit, compiler.rs:202-203, is why it is a tree). graph_detect_voices recognises that shape in a flat graph
+ * (num_voices == 1): a balanced pairwise tree of 2-port SumNodes (2C inputs -> C outputs, sum.rs:69-81; an unpaired last element of a
+ * level passes a 1-port SumNode, the copy path sum.rs:58-65) over V sub-graphs that are disjoint, read their own slice
+ * [v * voice_inputs, (v + 1) * voice_inputs) of graph_in, and are isomorphic: same node kinds, port counts, wiring and static
+ * parameters (stages, delay length, IR, tables, threshold); gains, pans and coefficients may differ — they become the per-voice tables.
+ * ctx_new_batched then builds the equivalent batched context: the voice graph once, num_voices = V, master_bus = 1 — the bus IS that
+ * tree, so the result is bit-identical to running the flat graph. A graph that is simply one voice answers num_voices == 1.
+ * Returns 0, or -1 with the reason in ctx_last_error (the flat graph still runs as it is, through the generic lowering). */
+typedef struct fw_voice_template {
+    uint32_t num_voices;          /* V */
+    uint32_t num_template_nodes;  /* nodes of one voice (graph_in / graph_out and the tree excluded), in canonical order */
+    uint32_t voice_inputs, voice_outputs;  /* channels per voice */
+    uint32_t num_tree_nodes;      /* SumNodes that disappear into the master bus */
+} fw_voice_template;
+FW_EXPORT int FW_FN(graph_detect_voices)(fw_ctx* flat, fw_voice_template* out);
+/* after a successful detection: the ids, in the flat graph, of template node `template_node` in voice 0 .. V-1; returns V */
+FW_EXPORT uint32_t FW_FN(graph_voice_nodes)(fw_ctx* flat, uint32_t template_node, fw_node_id* out, uint32_t cap);
+/* the batched context of the detected graph (not activated; the flat context stays untouched and shares its sample resources).
+ * template_ids[i] (cap entries, may be NULL) = id of template node i in the new graph. NULL + ctx_last_error(flat) on failure. */
+FW_EXPORT fw_ctx* FW_FN(ctx_new_batched)(fw_ctx* flat, int32_t device, uint32_t max_call_frames, fw_node_id* template_ids, uint32_t cap);
+/* main-thread view of a node's parameter table (the reference's getters: volume.rs:24,36, sampler.rs:167,179): copies up to cap
+ * floats, returns the table's length — num_voices entries ([voice][stage][5 | 6] for FW_PARAM_COEFFS); 0: the node has no such table */
+typedef enum fw_param_table { FW_PARAM_PERCENT_VOLUME = 0, FW_PARAM_RAW_GAIN = 1, FW_PARAM_PAN = 2, FW_PARAM_GAIN_L = 3, FW_PARAM_GAIN_R = 4, FW_PARAM_COEFFS = 5 } fw_param_table;
+FW_EXPORT uint32_t FW_FN(node_read_params)(fw_ctx* ctx, fw_node_id node, uint32_t which, float* out, uint32_t cap);
+
 /* ---- node parameters (main-thread side; relaxed-atomic stores in the reference) --------
  * The reference's processor polls per block: it drains its message ring and loads the atomic parameters at the top of every
  * process_block (processor.rs:214, volume.rs:92, sampler.rs:331), so a host that calls once per block places every store at a

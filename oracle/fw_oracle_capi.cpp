@@ -673,6 +673,12 @@ int fwo_processor_event_record(fw_processor*, int) { return -1; }
 float fwo_processor_event_elapsed_ms(fw_processor*, int, int) { return -1.0f; }
 uint64_t fwo_processor_kernel_launches(fw_processor*) { return 0; }
 uint64_t fwo_processor_graph_replays(fw_processor*) { return 0; }
+// Isomorphic-voice detection and the parameter-table getter are host logic of the product; the oracle runs a flat graph as it is
+// (that is what the detection's equivalence tests compare against) and only answers "not here".
+int fwo_graph_detect_voices(fw_ctx* c, fw_voice_template* out) { if (out) *out = fw_voice_template{}; if (c) c->last_error = "the oracle does not batch: it runs the flat graph"; return -1; }
+uint32_t fwo_graph_voice_nodes(fw_ctx*, uint32_t, fw_node_id*, uint32_t) { return 0; }
+fw_ctx* fwo_ctx_new_batched(fw_ctx* c, int32_t, uint32_t, fw_node_id*, uint32_t) { if (c) c->last_error = "the oracle does not batch: it runs the flat graph"; return nullptr; }
+uint32_t fwo_node_read_params(fw_ctx*, fw_node_id, uint32_t, float*, uint32_t) { return 0; }
 int fwo_processor_l2_flush(fw_processor*) { return -1; }
 int fwo_processor_profile(fw_processor*, int) { return -1; }
 int fwo_processor_profile_read(fw_processor*, double*, uint64_t*) { return -1; }
