@@ -279,3 +279,36 @@ def test_the_batched_context_reproduces_the_flat_graph(oracle, product, V, kind)
     del vol_tid
     for c in (oflat, pflat, bcx, ocx):
         c.free()
+
+
+def test_source_voices_without_inputs(product):
+    """config 5's shape as a flat graph: every voice starts at its own SamplerNode (graph_in has no channels), gain -> pan behind it;
+    the sampler's volume and the gain / pan tables are gathered per voice"""
+    from firewheel_b200 import SamplerNode
+    V = 6
+    prm = voice_params(V, 3)
+    cx = FirewheelGraphCtx(product, AudioGraphConfig(num_graph_inputs=0, num_graph_outputs=2))
+    g = cx.graph
+    leaves, smp_ids = [], []
+    for v in range(V):
+        smp = g.add_node(0, 2, SamplerNode(float(50 + v)))
+        vol, pan = g.add_node(2, 2, VolumeNode(float(prm["pct"][v]))), g.add_node(2, 2, PanNode(float(prm["pan"][v])))
+        for c in range(2):
+            g.connect(smp, c, vol, c, False); g.connect(vol, c, pan, c, False)
+        leaves.append([(pan, 0), (pan, 1)]); smp_ids.append(smp)
+    root = build_tree(g, leaves)
+    for c in range(2):
+        g.connect(root[c][0], root[c][1], g.graph_out_node(), c, False)
+    bcx, tids = FirewheelGraphCtx.new_batched(cx)
+    assert bcx.config.num_voices == V and bcx.config.num_graph_inputs == 0 and len(tids) == 3
+    by_name = {}
+    for tid in tids:
+        info = bcx.graph.node_info(tid)
+        by_name[info.debug_name if isinstance(info.debug_name, str) else info.debug_name.decode()] = tid
+    assert cx.graph.voice_nodes(tids.index(by_name["beep_test"])) == smp_ids  # Q8: the sampler's debug name (sampler.rs:186)
+    assert np.array_equal(bcx.graph.read_params(by_name["beep_test"], K.FW_PARAM_PERCENT_VOLUME), np.arange(50, 50 + V, dtype=f32))
+    assert np.array_equal(bcx.graph.read_params(by_name["volume"], K.FW_PARAM_PERCENT_VOLUME), prm["pct"])
+    assert np.array_equal(bcx.graph.read_params(by_name["pan"], K.FW_PARAM_PAN), prm["pan"])
+    sched, _ = bcx.graph.compile_internal(F)
+    assert len(sched) == 5  # graph_in, sampler, gain, pan, graph_out: the chain the fused device path takes (config 5's head)
+    bcx.free(); cx.free()
