@@ -312,3 +312,60 @@ def test_source_voices_without_inputs(product):
     sched, _ = bcx.graph.compile_internal(F)
     assert len(sched) == 5  # graph_in, sampler, gain, pan, graph_out: the chain the fused device path takes (config 5's head)
     bcx.free(); cx.free()
+
+
+@pytest.mark.parametrize("V", [3, 4, 7])
+def test_mono_voices(oracle, product, V):
+    """C = 1: the tree's SumNodes are 2 -> 1, the carry is a 1 -> 1 SumNode; voice = gain -> hard clip -> 3-stage biquad"""
+    T = 3 * F + 2
+    x = synth((V, 1, T), 40 + V)
+    pct = (30 + 15 * np.arange(V)).astype(f32)
+    co = np.stack([[design_rbj(product, s % 2, 400.0 * (v + 1) + 100 * s, 0.7, 0.0, SR) for s in range(3)] for v in range(V)]).astype(f32)
+
+    def flat_on(lib):
+        cx = FirewheelGraphCtx(lib, AudioGraphConfig(num_graph_inputs=V, num_graph_outputs=1))
+        g = cx.graph
+        level = []
+        for v in reversed(range(V)):  # created back to front: leaf order, not creation order, numbers the voices
+            vol, clip, bq = g.add_node(1, 1, VolumeNode(float(pct[v]))), g.add_node(1, 1, HardClipNode(-2.0)), g.add_node(1, 1, BiquadNode(3))
+            g.set_biquad_coeffs(bq, co[v][None])
+            g.connect(g.graph_in_node(), v, vol, 0, False); g.connect(vol, 0, clip, 0, False); g.connect(clip, 0, bq, 0, False)
+            level.insert(0, bq)
+        while len(level) > 1:
+            nxt = []
+            for i in range(0, len(level) - 1, 2):
+                s_ = g.add_node(2, 1, SumNode())
+                g.connect(level[i], 0, s_, 0, False); g.connect(level[i + 1], 0, s_, 1, False)
+                nxt.append(s_)
+            if len(level) % 2:
+                s_ = g.add_node(1, 1, SumNode())
+                g.connect(level[-1], 0, s_, 0, False)
+                nxt.append(s_)
+            level = nxt
+        g.connect(level[0], 0, g.graph_out_node(), 0, False)
+        return cx
+
+    def run1(cx, xin, n_in, bus):
+        proc = cx.activate(SR, n_in, 1, F)
+        assert cx.update().graph_error is None, cx.last_error()
+        y = run_planar(proc, xin, 1, bus)[0]
+        proc.free(); cx.update()
+        return y
+    oflat = flat_on(oracle)
+    y_flat = run1(oflat, x.reshape(1, V, T), V, False)
+    pflat = flat_on(product)
+    t = pflat.graph.detect_voices()
+    assert (t.num_voices, t.num_template_nodes, t.voice_inputs, t.voice_outputs) == (V, 3, 1, 1)
+    bcx, tids = FirewheelGraphCtx.new_batched(pflat)
+    tables = {(bcx.graph.node_info(tid).debug_name if isinstance(bcx.graph.node_info(tid).debug_name, str) else bcx.graph.node_info(tid).debug_name.decode()): tid for tid in tids}
+    assert np.array_equal(bcx.graph.read_params(tables["volume"], K.FW_PARAM_PERCENT_VOLUME), pct)
+    assert np.array_equal(bcx.graph.read_params(tables["biquad"], K.FW_PARAM_COEFFS).reshape(V, 3, 5), co)
+    # the same batched form on the oracle
+    ocx = FirewheelGraphCtx(oracle, AudioGraphConfig(num_graph_inputs=1, num_graph_outputs=1, num_voices=V, master_bus=True))
+    g = ocx.graph
+    vol, clip, bq = g.add_node(1, 1, VolumeNode(100.0)), g.add_node(1, 1, HardClipNode(-2.0)), g.add_node(1, 1, BiquadNode(3))
+    g.set_percent_volume(vol, pct); g.set_biquad_coeffs(bq, co)
+    g.connect(g.graph_in_node(), 0, vol, 0, False); g.connect(vol, 0, clip, 0, False); g.connect(clip, 0, bq, 0, False); g.connect(bq, 0, g.graph_out_node(), 0, False)
+    assert_bit_exact(run1(ocx, x, 1, True), y_flat[0], f"mono V={V}")
+    for c in (oflat, pflat, bcx, ocx):
+        c.free()
